@@ -1,0 +1,273 @@
+/*
+ * smx.h — C ABI of libsmx, the B200 (sm_100a) SummaryMixing encoder-path library.
+ *
+ * The reference (SamsungLabs/SummaryMixing @ d1b1f42) has no FFI: its operator API is the Python
+ * nn.Module surface.  This header is the boundary a maintainer binds from those modules (ctypes stub in
+ * INTEGRATION.md); every entry point cites the reference code it replaces (paths relative to the
+ * reference root).
+ *
+ * Conventions (all entry points)
+ *  - extern "C", plain pointers and sizes.  Every pointer except the `_host` entry points' buffers is
+ *    a DEVICE pointer.  The library allocates nothing persistent and keeps no pointer after return.
+ *  - Enqueue-only on `stream` (a cudaStream_t passed as void*); no host synchronisation; safe to
+ *    capture in a CUDA graph.  Re-entrant.
+ *  - Returns SMX_OK (0) or a negative smx_status; never throws, never aborts.  smx_last_error()
+ *    returns a thread-local message for the last failure.
+ *  - Activations x/y: row-major (B,T,D) contiguous, fp32 (SMX_F32) or bf16 (SMX_BF16), 16-byte aligned.
+ *    Weights: fp32, in the reference's own state_dict layouts (nn.Linear: (out,in); ParallelLinear:
+ *    (h, in/h, out/h), VanillaNN.py:85-88).  The bf16 tensor-core path additionally takes a packed
+ *    image of the weights built once by smx_*_pack().
+ *  - padding mask: uint8 (B,T), 1 = valid frame (TransformerASR.py:158-162, 348-349); NULL = all valid.
+ *  - sum mask: fp32 (T,T), row t = weights of the frames visible to frame t (summary_mixing.py:188-189,
+ *    235-246); NULL = whole-utterance mean.
+ */
+#ifndef SMX_H_
+#define SMX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#if defined(__GNUC__)
+#define SMX_API __attribute__((visibility("default")))
+#else
+#define SMX_API
+#endif
+
+#define SMX_VERSION 100 /* 0.1.0 */
+#define SMX_MAX_BLOCKS 4 /* max linear blocks per VanillaNN handled by the library */
+
+typedef enum {
+  SMX_OK = 0,
+  SMX_ERR_BAD_ARG = -1,      /* NULL pointer, non-positive size, unknown enum */
+  SMX_ERR_UNSUPPORTED = -2,  /* valid in the reference but not handled by this build (message says what) */
+  SMX_ERR_ALIGNMENT = -3,    /* pointer not 16-byte aligned */
+  SMX_ERR_WORKSPACE = -4,    /* workspace too small */
+  SMX_ERR_CUDA = -5,         /* a CUDA runtime call or launch failed (message has cudaGetErrorString) */
+  SMX_ERR_ARCH = -6          /* device is not compute capability 10.x */
+} smx_status;
+
+typedef enum { SMX_F32 = 0, SMX_BF16 = 1 } smx_dtype;
+
+/* activation of VanillaNN / FFN / conv module (a torch.nn.Module class in the reference,
+ * summary_mixing.py:86; Conformer.py:117,404; Branchformer.py:68-69) */
+typedef enum {
+  SMX_ACT_IDENTITY = 0,
+  SMX_ACT_SWISH = 1,      /* speechbrain Swish / nn.SiLU: x*sigmoid(x) */
+  SMX_ACT_GELU = 2,       /* nn.GELU(): exact erf form */
+  SMX_ACT_RELU = 3,
+  SMX_ACT_LEAKY_RELU = 4, /* negative_slope 0.01 */
+  SMX_ACT_TANH = 5,
+  SMX_ACT_SIGMOID = 6,
+  SMX_ACT_GELU_TANH = 7   /* nn.GELU(approximate="tanh") */
+} smx_act;
+
+/* SummaryMixing.mode, summary_mixing.py:93-101 */
+typedef enum { SMX_MODE_FULL = 0, SMX_MODE_LITE = 1, SMX_MODE_FAST = 2, SMX_MODE_EXPDECAY = 3 } smx_mode;
+
+/* depthwise-convolution boundary rule */
+typedef enum {
+  SMX_CONV_SAME_ZERO = 0, /* Conformer.py:142-151: zero padding (k-1)/2 both sides */
+  SMX_CONV_CAUSAL = 1,    /* Conformer.py:130-131, 327-329: left padding k-1, chomp */
+  SMX_CONV_CHUNKED = 2,   /* Conformer.py:197-320: Dynamic Chunk Convolution (future beyond own chunk masked) */
+  SMX_CONV_SAME_REFLECT = 3 /* speechbrain CSGU depthwise conv: reflect padding */
+} smx_conv_pad;
+
+/* One linear block: n_split == 1 → dense nn.Linear, w (out_dim,in_dim); n_split > 1 → ParallelLinear,
+ * w (n_split, in_dim/n_split, out_dim/n_split) (VanillaNN.py:85-88, 112).  b has out_dim entries. */
+typedef struct {
+  const float* w;
+  const float* b;
+  int32_t in_dim;
+  int32_t out_dim;
+  int32_t n_split;
+  int32_t _pad;
+} smx_linear;
+
+/* SummaryMixing cell parameters (summary_mixing.py:78-167). */
+typedef struct {
+  int32_t mode;            /* smx_mode */
+  int32_t act;             /* smx_act */
+  int32_t use_layernorm;   /* summary_mixing.py:163-165 */
+  int32_t enc_dim;
+  int32_t local_out_dim;   /* D_l */
+  int32_t summary_out_dim; /* D_s */
+  int32_t n_local;         /* blocks in local_proj (FULL/EXPDECAY) */
+  int32_t n_summary;       /* blocks in summary_proj (FULL/EXPDECAY/LITE) */
+  smx_linear local[SMX_MAX_BLOCKS];
+  smx_linear summary[SMX_MAX_BLOCKS];
+  smx_linear global_proj;  /* FAST: dense D -> 2*D_l (summary_mixing.py:133-140) */
+  smx_linear merge;        /* summary_local_merging: dense (D_l+D_s) -> D_s (FULL/EXPDECAY/FAST) */
+  const float* local_norm_w;
+  const float* local_norm_b;
+  const float* summary_norm_w;
+  const float* summary_norm_b;
+  float decay_constant;    /* EXPDECAY (summary_mixing.py:158-161) */
+  int32_t _pad;
+} smx_cell_weights;
+
+/* ffn_module{1,2}: LayerNorm + PositionalwiseFeedForward (Conformer.py:470-484). */
+typedef struct {
+  const float* ln_w;
+  const float* ln_b;
+  smx_linear w1; /* D -> d_ffn */
+  smx_linear w2; /* d_ffn -> D */
+} smx_ffn_weights;
+
+/* ConvolutionModule (Conformer.py:80-340). */
+typedef struct {
+  const float* ln_w;
+  const float* ln_b;
+  smx_linear bottleneck;  /* pointwise Conv1d D -> 2D, weight (2D,D,1) viewed (2D,D) */
+  const float* dw_w;      /* depthwise weight (D,1,k) viewed (D,k) */
+  const float* dw_b;      /* (D) or NULL */
+  const float* after_ln_w;
+  const float* after_ln_b;
+  smx_linear out;         /* after_conv.2: D -> D */
+  int32_t kernel_size;
+  int32_t causal;
+} smx_convmod_weights;
+
+/* ConformerEncoderLayer with attention_type == "SummaryMixing" (Conformer.py:343-548). */
+typedef struct {
+  smx_ffn_weights ffn1;
+  smx_ffn_weights ffn2;
+  const float* norm1_w;
+  const float* norm1_b;
+  const float* norm2_w;
+  const float* norm2_b;
+  smx_cell_weights cell;
+  smx_convmod_weights conv;
+  int32_t act; /* shared by FFN, cell and conv module (Conformer.py:446-484) */
+  int32_t _pad;
+} smx_conformer_layer_weights;
+
+/* ConvolutionBranch + CSGU (Branchformer.py:31-97; speechbrain ConvolutionalSpatialGatingUnit). */
+typedef struct {
+  smx_linear pre;          /* pre_channel_proj D -> U */
+  smx_linear post;         /* post_channel_proj U/2 -> D */
+  const float* csgu_ln_w;  /* (U/2) */
+  const float* csgu_ln_b;
+  const float* csgu_dw_w;  /* (U/2,1,k) */
+  const float* csgu_dw_b;
+  smx_linear csgu_linear;  /* optional (use_linear_after_conv); w == NULL when absent */
+  int32_t kernel_size;
+  int32_t act;             /* activation after pre_channel_proj */
+  int32_t gate_act;
+  int32_t _pad;
+} smx_convbranch_weights;
+
+/* BranchformerEncoderLayer with attention_type == "SummaryMixing" (Branchformer.py:100-334). */
+typedef struct {
+  const float* norm_mhsa_w;
+  const float* norm_mhsa_b;
+  const float* norm_conv_w;
+  const float* norm_conv_b;
+  smx_cell_weights cell;
+  smx_convbranch_weights branch;
+  int32_t n_merge;                   /* blocks in merge_proj (Branchformer.py:220-226) */
+  int32_t act;
+  smx_linear merge[SMX_MAX_BLOCKS];
+} smx_branchformer_layer_weights;
+
+/* ---- library info -------------------------------------------------------------------------- */
+SMX_API int smx_version(void);
+SMX_API const char* smx_last_error(void);
+/* sizeof() of the ABI structs as compiled (0 smx_linear, 1 smx_cell_weights, 2 smx_ffn_weights,
+ * 3 smx_convmod_weights, 4 smx_conformer_layer_weights, 5 smx_convbranch_weights,
+ * 6 smx_branchformer_layer_weights) so a binding can verify its mirror of this header. */
+SMX_API size_t smx_struct_size(int which);
+/* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
+SMX_API uint64_t smx_launch_count(void);
+
+/* ---- primitives (each replaces one reference module call) ---------------------------------- */
+
+/* nn.LayerNorm over the last dim (rows x D).  summary_mixing.py:218,249; Conformer.py:521,547,821. */
+SMX_API int smx_layernorm_fwd(int dtype, int64_t rows, int32_t D, const void* x, const float* w, const float* b,
+                      float eps, void* y, void* stream);
+
+/* VanillaNN.forward: n_blocks x (linear, act) (VanillaNN.py:168-196).  x (rows,in) -> y (rows,out).
+ * workspace: smx_vanilla_nn_workspace_bytes(). */
+SMX_API size_t smx_vanilla_nn_workspace_bytes(const smx_linear* blocks, int32_t n_blocks, int dtype, int64_t rows);
+SMX_API int smx_vanilla_nn_fwd(const smx_linear* blocks, int32_t n_blocks, int act, int dtype, int64_t rows,
+                       const void* x, void* y, void* workspace, size_t workspace_bytes, void* stream);
+
+/* SummaryMixing.forward (summary_mixing.py:169-324), eval mode.
+ * y: (B,T,D_s); for SMX_MODE_LITE y is (B,D_s) — the reference returns a stride-0 expand over T
+ * (summary_mixing.py:322) and the caller does the same.  `residual` (B,T,D_s) or NULL: when given,
+ * y = cell(x) + residual (the `x + skip` of Conformer.py:541 fused; not for LITE). */
+SMX_API size_t smx_summary_mixing_workspace_bytes(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, int has_sum_mask);
+SMX_API int smx_summary_mixing_fwd(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x,
+                           const uint8_t* padding_mask, const float* sum_mask, const void* residual, void* y,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
+/* ConvolutionModule.forward (Conformer.py:166-340): y = conv_module(x) * mask (+ residual if given).
+ * chunk_size > 0 selects Dynamic Chunk Convolution (Conformer.py:197-320). */
+SMX_API size_t smx_conv_module_workspace_bytes(const smx_convmod_weights* w, int dtype, int32_t B, int32_t T);
+SMX_API int smx_conv_module_fwd(const smx_convmod_weights* w, int act, int dtype, int32_t B, int32_t T, int32_t chunk_size,
+                        const void* x, const uint8_t* padding_mask, const void* residual, void* y,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
+/* Macaron half-step FFN: y = x + 0.5 * FFN(LN(x)); if out_ln_w != NULL, y = LN_out(y)
+ * (Conformer.py:518 and :547). */
+SMX_API size_t smx_ffn_workspace_bytes(const smx_ffn_weights* w, int dtype, int64_t rows);
+SMX_API int smx_ffn_fwd(const smx_ffn_weights* w, int act, int dtype, int64_t rows, const void* x,
+                const float* out_ln_w, const float* out_ln_b, float out_ln_eps, void* y,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- encoder blocks ------------------------------------------------------------------------- */
+
+/* ConformerEncoderLayer.forward (Conformer.py:490-548). */
+SMX_API size_t smx_conformer_layer_workspace_bytes(const smx_conformer_layer_weights* w, int dtype, int32_t B, int32_t T,
+                                           int has_sum_mask);
+SMX_API int smx_conformer_layer_fwd(const smx_conformer_layer_weights* w, int dtype, int32_t B, int32_t T, int32_t chunk_size,
+                            const void* x, const uint8_t* padding_mask, const float* sum_mask, void* y,
+                            void* workspace, size_t workspace_bytes, void* stream);
+
+/* ConformerEncoder.forward, eval mode (Conformer.py:765-827): n_layers layers then LayerNorm(eps=1e-6).
+ * x and y may alias.  hidden (optional, may be NULL): n_layers pointers receiving each layer's output
+ * (output_hidden_states, Conformer.py:819-825; the last one receives the normalised output). */
+SMX_API size_t smx_conformer_encoder_workspace_bytes(const smx_conformer_layer_weights* layers, int32_t n_layers, int dtype,
+                                             int32_t B, int32_t T, int has_sum_mask);
+SMX_API int smx_conformer_encoder_fwd(const smx_conformer_layer_weights* layers, int32_t n_layers, const float* final_norm_w,
+                              const float* final_norm_b, int dtype, int32_t B, int32_t T, int32_t chunk_size,
+                              const void* x, const uint8_t* padding_mask, const float* sum_mask, void* y,
+                              void* const* hidden, void* workspace, size_t workspace_bytes, void* stream);
+
+/* BranchformerEncoderLayer.forward (Branchformer.py:243-334) and BranchformerEncoder.forward (:447-491). */
+SMX_API size_t smx_branchformer_layer_workspace_bytes(const smx_branchformer_layer_weights* w, int dtype, int32_t B, int32_t T,
+                                              int has_sum_mask);
+SMX_API int smx_branchformer_layer_fwd(const smx_branchformer_layer_weights* w, int dtype, int32_t B, int32_t T, const void* x,
+                               const uint8_t* padding_mask, const float* sum_mask, void* y, void* workspace,
+                               size_t workspace_bytes, void* stream);
+SMX_API size_t smx_branchformer_encoder_workspace_bytes(const smx_branchformer_layer_weights* layers, int32_t n_layers,
+                                                int dtype, int32_t B, int32_t T, int has_sum_mask);
+SMX_API int smx_branchformer_encoder_fwd(const smx_branchformer_layer_weights* layers, int32_t n_layers,
+                                 const float* final_norm_w, const float* final_norm_b, int dtype, int32_t B, int32_t T,
+                                 const void* x, const uint8_t* padding_mask, const float* sum_mask, void* y,
+                                 void* workspace, size_t workspace_bytes, void* stream);
+
+/* ---- mask builders (TransformerASR.py:50-180) ------------------------------------------------ */
+
+/* padding mask from relative lengths: abs_len = round(wav_len*T); mask[b,t] = t < abs_len[b]
+ * (TransformerASR.py:157-162, masked_false_or_true == False). */
+SMX_API int smx_padding_mask_from_wav_len(const float* wav_len, int32_t B, int32_t T, uint8_t* mask, void* stream);
+/* dynamic-chunk sum mask (T,T) fp32: 1 where frame j is visible to frame i (TransformerASR.py:85-110,
+ * masked_false_or_true == False).  left_context_chunks < 0 = infinite left context. */
+SMX_API int smx_chunk_mask(int32_t T, int32_t chunk_size, int32_t left_context_chunks, float* mask, void* stream);
+
+/* ---- diagnostics ---------------------------------------------------------------------------------- */
+
+/* UMMA self-test: c (M,N) fp32 = a (M,K) bf16 @ w (N,K) fp32->bf16 transposed, computed by the tcgen05
+ * building blocks the fused kernels use (layout 0: 128B-swizzled operands, 1: unswizzled).
+ * N <= 256, K % 8 == 0.  workspace: N*K*2 bytes rounded up to tiles (1 MiB is always enough). */
+SMX_API int smx_debug_tc_gemm(int layout, int32_t M, int32_t N, int32_t K, const void* a_bf16, const float* w_f32,
+                              float* c_f32, void* workspace, size_t workspace_bytes, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SMX_H_ */

@@ -1,0 +1,139 @@
+"""ctypes binding of libsmx.so (the C ABI declared in include/smx.h).
+
+The product path is CUDA only: if the library is missing, or no sm_100 device is present, calls fail
+loudly — there is no CPU fallback (the CPU oracle under oracle/ is test infrastructure and is never
+imported from here).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+PKG = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(PKG, "libsmx.so")
+
+SMX_MAX_BLOCKS = 4
+F32, BF16 = 0, 1
+ACT_IDENTITY, ACT_SWISH, ACT_GELU, ACT_RELU, ACT_LEAKY_RELU, ACT_TANH, ACT_SIGMOID, ACT_GELU_TANH = range(8)
+MODE_FULL, MODE_LITE, MODE_FAST, MODE_EXPDECAY = range(4)
+MODES = {
+    "SummaryMixing": MODE_FULL,
+    "SummaryMixing-lite": MODE_LITE,
+    "SummaryMixing-fast": MODE_FAST,
+    "SummaryMixing-expdecay": MODE_EXPDECAY,
+}
+STATUS = {0: "SMX_OK", -1: "SMX_ERR_BAD_ARG", -2: "SMX_ERR_UNSUPPORTED", -3: "SMX_ERR_ALIGNMENT",
+          -4: "SMX_ERR_WORKSPACE", -5: "SMX_ERR_CUDA", -6: "SMX_ERR_ARCH"}
+
+fp = C.c_void_p  # const float* (device)
+
+
+class Linear(C.Structure):
+    _fields_ = [("w", fp), ("b", fp), ("in_dim", C.c_int32), ("out_dim", C.c_int32), ("n_split", C.c_int32),
+                ("_pad", C.c_int32)]
+
+
+class CellWeights(C.Structure):
+    _fields_ = [("mode", C.c_int32), ("act", C.c_int32), ("use_layernorm", C.c_int32), ("enc_dim", C.c_int32),
+                ("local_out_dim", C.c_int32), ("summary_out_dim", C.c_int32), ("n_local", C.c_int32),
+                ("n_summary", C.c_int32), ("local", Linear * SMX_MAX_BLOCKS), ("summary", Linear * SMX_MAX_BLOCKS),
+                ("global_proj", Linear), ("merge", Linear), ("local_norm_w", fp), ("local_norm_b", fp),
+                ("summary_norm_w", fp), ("summary_norm_b", fp), ("decay_constant", C.c_float), ("_pad", C.c_int32)]
+
+
+class FFNWeights(C.Structure):
+    _fields_ = [("ln_w", fp), ("ln_b", fp), ("w1", Linear), ("w2", Linear)]
+
+
+class ConvModWeights(C.Structure):
+    _fields_ = [("ln_w", fp), ("ln_b", fp), ("bottleneck", Linear), ("dw_w", fp), ("dw_b", fp), ("after_ln_w", fp),
+                ("after_ln_b", fp), ("out", Linear), ("kernel_size", C.c_int32), ("causal", C.c_int32)]
+
+
+class ConformerLayerWeights(C.Structure):
+    _fields_ = [("ffn1", FFNWeights), ("ffn2", FFNWeights), ("norm1_w", fp), ("norm1_b", fp), ("norm2_w", fp),
+                ("norm2_b", fp), ("cell", CellWeights), ("conv", ConvModWeights), ("act", C.c_int32),
+                ("_pad", C.c_int32)]
+
+
+class ConvBranchWeights(C.Structure):
+    _fields_ = [("pre", Linear), ("post", Linear), ("csgu_ln_w", fp), ("csgu_ln_b", fp), ("csgu_dw_w", fp),
+                ("csgu_dw_b", fp), ("csgu_linear", Linear), ("kernel_size", C.c_int32), ("act", C.c_int32),
+                ("gate_act", C.c_int32), ("_pad", C.c_int32)]
+
+
+class BranchformerLayerWeights(C.Structure):
+    _fields_ = [("norm_mhsa_w", fp), ("norm_mhsa_b", fp), ("norm_conv_w", fp), ("norm_conv_b", fp),
+                ("cell", CellWeights), ("branch", ConvBranchWeights), ("n_merge", C.c_int32), ("act", C.c_int32),
+                ("merge", Linear * SMX_MAX_BLOCKS)]
+
+
+class SmxError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__(f"libsmx: {STATUS.get(code, code)}: {msg}")
+        self.code = code
+
+
+_lib = None
+
+_i, _i64, _sz, _vp, _f = C.c_int, C.c_int64, C.c_size_t, C.c_void_p, C.c_float
+_PROTOS = {
+    "smx_version": (C.c_int, []),
+    "smx_last_error": (C.c_char_p, []),
+    "smx_launch_count": (C.c_uint64, []),
+    "smx_struct_size": (_sz, [_i]),
+    "smx_layernorm_fwd": (_i, [_i, _i64, _i, _vp, _vp, _vp, _f, _vp, _vp]),
+    "smx_vanilla_nn_workspace_bytes": (_sz, [C.POINTER(Linear), _i, _i, _i64]),
+    "smx_vanilla_nn_fwd": (_i, [C.POINTER(Linear), _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
+    "smx_summary_mixing_workspace_bytes": (_sz, [C.POINTER(CellWeights), _i, _i, _i, _i]),
+    "smx_summary_mixing_fwd": (_i, [C.POINTER(CellWeights), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "smx_conv_module_workspace_bytes": (_sz, [C.POINTER(ConvModWeights), _i, _i, _i]),
+    "smx_conv_module_fwd": (_i, [C.POINTER(ConvModWeights), _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "smx_ffn_workspace_bytes": (_sz, [C.POINTER(FFNWeights), _i, _i64]),
+    "smx_ffn_fwd": (_i, [C.POINTER(FFNWeights), _i, _i, _i64, _vp, _vp, _vp, _f, _vp, _vp, _sz, _vp]),
+    "smx_conformer_layer_workspace_bytes": (_sz, [C.POINTER(ConformerLayerWeights), _i, _i, _i, _i]),
+    "smx_conformer_layer_fwd": (_i, [C.POINTER(ConformerLayerWeights), _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "smx_conformer_encoder_workspace_bytes": (_sz, [C.POINTER(ConformerLayerWeights), _i, _i, _i, _i, _i]),
+    "smx_conformer_encoder_fwd": (_i, [C.POINTER(ConformerLayerWeights), _i, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp,
+                                       _vp, C.POINTER(C.c_void_p), _vp, _sz, _vp]),
+    "smx_branchformer_layer_workspace_bytes": (_sz, [C.POINTER(BranchformerLayerWeights), _i, _i, _i, _i]),
+    "smx_branchformer_layer_fwd": (_i, [C.POINTER(BranchformerLayerWeights), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "smx_branchformer_encoder_workspace_bytes": (_sz, [C.POINTER(BranchformerLayerWeights), _i, _i, _i, _i, _i]),
+    "smx_branchformer_encoder_fwd": (_i, [C.POINTER(BranchformerLayerWeights), _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp,
+                                          _vp, _vp, _sz, _vp]),
+    "smx_padding_mask_from_wav_len": (_i, [_vp, _i, _i, _vp, _vp]),
+    "smx_chunk_mask": (_i, [_i, _i, _i, _vp, _vp]),
+    "smx_debug_tc_gemm": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+}
+
+
+ABI_STRUCTS = [Linear, CellWeights, FFNWeights, ConvModWeights, ConformerLayerWeights, ConvBranchWeights,
+               BranchformerLayerWeights]
+
+
+def exported_symbols():
+    """Names include/smx.h declares (tests check the built library exports every one)."""
+    return sorted(_PROTOS)
+
+
+def lib():
+    """Load libsmx.so (built in-tree by summarymixing_b200.build / __graft_entry__.build)."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"libsmx.so not found at {LIB_PATH}: build it with `python -m summarymixing_b200.build` "
+                "(there is no CPU fallback)"
+            )
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOS.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(code):
+    if code != 0:
+        raise SmxError(code, lib().smx_last_error().decode())

@@ -1,0 +1,306 @@
+// libsmx C ABI: argument validation, workspace sizing and dispatch between the tcgen05 arm
+// (bf16, smx_tc_*.cu) and the generic fp32-math arm (smx_generic.cu).  See include/smx.h.
+#include "smx_internal.h"
+#include "smx_tc.h"
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+
+namespace smx {
+
+static thread_local char g_err[512] = "";
+static std::atomic<uint64_t> g_launches{0};
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+int check_launch(const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+  return SMX_OK;
+}
+
+static int check_dtype(int dtype) {
+  if (dtype != SMX_F32 && dtype != SMX_BF16) return fail(SMX_ERR_BAD_ARG, "unknown dtype %d", dtype);
+  return SMX_OK;
+}
+static int check_ptr(const void* p, const char* name) {
+  if (!p) return fail(SMX_ERR_BAD_ARG, "%s is NULL", name);
+  if ((uintptr_t)p & 15) return fail(SMX_ERR_ALIGNMENT, "%s is not 16-byte aligned", name);
+  return SMX_OK;
+}
+static int check_bt(int B, int T) {
+  if (B <= 0 || T <= 0) return fail(SMX_ERR_BAD_ARG, "B and T must be positive (got %d, %d)", B, T);
+  return SMX_OK;
+}
+static int check_arch() {
+  static int cached = 0;  // 0 unknown, 1 ok, -1 bad
+  if (cached == 0) {
+    int dev = 0, major = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) {
+      cudaGetLastError();
+      return fail(SMX_ERR_CUDA, "no usable CUDA device");
+    }
+    cached = (major == 10) ? 1 : -1;
+  }
+  if (cached < 0) return fail(SMX_ERR_ARCH, "libsmx is built for sm_100a (B200) only");
+  return SMX_OK;
+}
+static int ws_ok(Arena& a, size_t given) {
+  if (a.peak > given) return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", a.peak, given);
+  return SMX_OK;
+}
+
+}  // namespace smx
+
+using namespace smx;
+
+extern "C" {
+
+int smx_version(void) { return SMX_VERSION; }
+const char* smx_last_error(void) { return g_err; }
+uint64_t smx_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+size_t smx_struct_size(int which) {
+  switch (which) {
+    case 0: return sizeof(smx_linear);
+    case 1: return sizeof(smx_cell_weights);
+    case 2: return sizeof(smx_ffn_weights);
+    case 3: return sizeof(smx_convmod_weights);
+    case 4: return sizeof(smx_conformer_layer_weights);
+    case 5: return sizeof(smx_convbranch_weights);
+    case 6: return sizeof(smx_branchformer_layer_weights);
+    default: return 0;
+  }
+}
+
+// ---- LayerNorm -----------------------------------------------------------------------------
+int smx_layernorm_fwd(int dtype, int64_t rows, int32_t D, const void* x, const float* w, const float* b, float eps,
+                      void* y, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(y, "y"));
+  if (!w || !b) return fail(SMX_ERR_BAD_ARG, "layernorm: NULL weight/bias");
+  if (rows <= 0 || D <= 0) return fail(SMX_ERR_BAD_ARG, "layernorm: rows and D must be positive");
+  SMX_TRY(check_arch());
+  return layernorm(x, dtype, D, w, b, eps, SMX_ACT_IDENTITY, y, dtype, D, rows, D, (cudaStream_t)stream);
+}
+
+// ---- VanillaNN -------------------------------------------------------------------------------
+size_t smx_vanilla_nn_workspace_bytes(const smx_linear* blocks, int32_t n_blocks, int dtype, int64_t rows) {
+  if (!blocks || n_blocks < 1 || n_blocks > SMX_MAX_BLOCKS || rows <= 0) return 0;
+  Arena a(nullptr, 0, true);
+  vanilla_generic(blocks, n_blocks, 0, nullptr, dtype, blocks[0].in_dim, rows, nullptr, nullptr, 0, 0, nullptr, dtype,
+                  blocks[n_blocks - 1].out_dim, a, nullptr);
+  return a.peak;
+}
+int smx_vanilla_nn_fwd(const smx_linear* blocks, int32_t n_blocks, int act, int dtype, int64_t rows, const void* x,
+                       void* y, void* workspace, size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  if (!blocks) return fail(SMX_ERR_BAD_ARG, "blocks is NULL");
+  if (rows <= 0) return fail(SMX_ERR_BAD_ARG, "rows must be positive");
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(y, "y"));
+  SMX_TRY(check_arch());
+  size_t need = smx_vanilla_nn_workspace_bytes(blocks, n_blocks, dtype, rows);
+  if (need > workspace_bytes || (need && !workspace))
+    return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  Arena a(workspace, workspace_bytes, false);
+  return vanilla_generic(blocks, n_blocks, act, x, dtype, blocks[0].in_dim, rows, nullptr, nullptr, 0, 0, y, dtype,
+                         blocks[n_blocks - 1].out_dim, a, (cudaStream_t)stream);
+}
+
+// ---- SummaryMixing cell ------------------------------------------------------------------------
+size_t smx_summary_mixing_workspace_bytes(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, int has_sum_mask) {
+  if (!w || B <= 0 || T <= 0) return 0;
+  Arena a(nullptr, 0, true);
+  const float* sm = has_sum_mask ? (const float*)(uintptr_t)256 : nullptr;
+  int Dout = w->mode == SMX_MODE_LITE ? w->summary_out_dim : w->merge.out_dim;
+  cell_generic(w, B, T, nullptr, dtype, nullptr, sm, nullptr, dtype, nullptr, dtype, Dout, a, nullptr);
+  size_t tc = tc_cell_workspace_bytes(w, dtype, B, T, has_sum_mask);
+  return a.peak > tc ? a.peak : tc;
+}
+int smx_summary_mixing_fwd(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x,
+                           const uint8_t* padding_mask, const float* sum_mask, const void* residual, void* y,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");
+  SMX_TRY(check_bt(B, T));
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(y, "y"));
+  SMX_TRY(check_arch());
+  size_t need = smx_summary_mixing_workspace_bytes(w, dtype, B, T, sum_mask != nullptr);
+  if (need > workspace_bytes || (need && !workspace))
+    return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  Arena a(workspace, workspace_bytes, false);
+  int Dout = w->mode == SMX_MODE_LITE ? w->summary_out_dim : w->merge.out_dim;
+  return cell_generic(w, B, T, x, dtype, padding_mask, sum_mask, residual, dtype, y, dtype, Dout, a, (cudaStream_t)stream);
+}
+
+// ---- ConvolutionModule ---------------------------------------------------------------------------
+size_t smx_conv_module_workspace_bytes(const smx_convmod_weights* w, int dtype, int32_t B, int32_t T) {
+  if (!w || B <= 0 || T <= 0) return 0;
+  Arena a(nullptr, 0, true);
+  convmod_generic(w, 0, B, T, 0, nullptr, dtype, nullptr, nullptr, dtype, nullptr, dtype, a, nullptr);
+  return a.peak;
+}
+int smx_conv_module_fwd(const smx_convmod_weights* w, int act, int dtype, int32_t B, int32_t T, int32_t chunk_size,
+                        const void* x, const uint8_t* padding_mask, const void* residual, void* y, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");
+  SMX_TRY(check_bt(B, T));
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(y, "y"));
+  SMX_TRY(check_arch());
+  size_t need = smx_conv_module_workspace_bytes(w, dtype, B, T);
+  if (need > workspace_bytes || (need && !workspace))
+    return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  Arena a(workspace, workspace_bytes, false);
+  return convmod_generic(w, act, B, T, chunk_size, x, dtype, padding_mask, residual, dtype, y, dtype, a, (cudaStream_t)stream);
+}
+
+// ---- FFN -----------------------------------------------------------------------------------------
+size_t smx_ffn_workspace_bytes(const smx_ffn_weights* w, int dtype, int64_t rows) {
+  if (!w || rows <= 0) return 0;
+  Arena a(nullptr, 0, true);
+  ffn_generic(w, 0, rows, nullptr, dtype, nullptr, nullptr, 0.f, nullptr, dtype, a, nullptr);
+  return a.peak;
+}
+int smx_ffn_fwd(const smx_ffn_weights* w, int act, int dtype, int64_t rows, const void* x, const float* out_ln_w,
+                const float* out_ln_b, float out_ln_eps, void* y, void* workspace, size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");
+  if (rows <= 0) return fail(SMX_ERR_BAD_ARG, "rows must be positive");
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(y, "y"));
+  SMX_TRY(check_arch());
+  size_t need = smx_ffn_workspace_bytes(w, dtype, rows);
+  if (need > workspace_bytes || (need && !workspace))
+    return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  Arena a(workspace, workspace_bytes, false);
+  return ffn_generic(w, act, rows, x, dtype, out_ln_w, out_ln_b, out_ln_eps, y, dtype, a, (cudaStream_t)stream);
+}
+
+// ---- Conformer layer / encoder -------------------------------------------------------------------
+size_t smx_conformer_layer_workspace_bytes(const smx_conformer_layer_weights* w, int dtype, int32_t B, int32_t T,
+                                           int has_sum_mask) {
+  if (!w || B <= 0 || T <= 0) return 0;
+  Arena a(nullptr, 0, true);
+  const float* sm = has_sum_mask ? (const float*)(uintptr_t)256 : nullptr;
+  conformer_layer_generic(w, dtype, B, T, 0, nullptr, nullptr, sm, nullptr, a, nullptr);
+  return a.peak;
+}
+int smx_conformer_layer_fwd(const smx_conformer_layer_weights* w, int dtype, int32_t B, int32_t T, int32_t chunk_size,
+                            const void* x, const uint8_t* padding_mask, const float* sum_mask, void* y, void* workspace,
+                            size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");
+  SMX_TRY(check_bt(B, T));
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(y, "y"));
+  SMX_TRY(check_arch());
+  size_t need = smx_conformer_layer_workspace_bytes(w, dtype, B, T, sum_mask != nullptr);
+  if (need > workspace_bytes || (need && !workspace))
+    return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  Arena a(workspace, workspace_bytes, false);
+  return conformer_layer_generic(w, dtype, B, T, chunk_size, x, padding_mask, sum_mask, y, a, (cudaStream_t)stream);
+}
+
+size_t smx_conformer_encoder_workspace_bytes(const smx_conformer_layer_weights* layers, int32_t n_layers, int dtype,
+                                             int32_t B, int32_t T, int has_sum_mask) {
+  if (!layers || n_layers <= 0 || B <= 0 || T <= 0) return 0;
+  size_t m = 0;
+  for (int i = 0; i < n_layers; ++i) {
+    size_t s = smx_conformer_layer_workspace_bytes(&layers[i], dtype, B, T, has_sum_mask);
+    if (s > m) m = s;
+  }
+  return m;
+}
+int smx_conformer_encoder_fwd(const smx_conformer_layer_weights* layers, int32_t n_layers, const float* final_norm_w,
+                              const float* final_norm_b, int dtype, int32_t B, int32_t T, int32_t chunk_size,
+                              const void* x, const uint8_t* padding_mask, const float* sum_mask, void* y,
+                              void* const* hidden, void* workspace, size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  if (!layers || n_layers <= 0) return fail(SMX_ERR_BAD_ARG, "layers is NULL or n_layers <= 0");
+  if (!final_norm_w || !final_norm_b) return fail(SMX_ERR_BAD_ARG, "final norm weights are NULL");
+  SMX_TRY(check_bt(B, T));
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(y, "y"));
+  SMX_TRY(check_arch());
+  size_t need = smx_conformer_encoder_workspace_bytes(layers, n_layers, dtype, B, T, sum_mask != nullptr);
+  if (need > workspace_bytes || (need && !workspace))
+    return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = layers[0].ffn1.w1.in_dim;
+  const int64_t rows = (int64_t)B * T;
+  const void* cur = x;
+  for (int i = 0; i < n_layers; ++i) {
+    void* out = hidden ? hidden[i] : y;
+    if (hidden) SMX_TRY(check_ptr(out, "hidden[i]"));
+    Arena a(workspace, workspace_bytes, false);
+    SMX_TRY(conformer_layer_generic(&layers[i], dtype, B, T, chunk_size, cur, padding_mask, sum_mask, out, a, st));
+    cur = out;
+  }
+  SMX_TRY(layernorm(cur, dtype, D, final_norm_w, final_norm_b, 1e-6f, SMX_ACT_IDENTITY, y, dtype, D, rows, D, st));
+  if (hidden && hidden[n_layers - 1] != y)  // hidden_lst[-1] = output (Conformer.py:824)
+    SMX_TRY(convert(y, dtype, hidden[n_layers - 1], dtype, rows * D, st));
+  return SMX_OK;
+}
+
+// ---- Branchformer layer / encoder -------------------------------------------------------------------
+size_t smx_branchformer_layer_workspace_bytes(const smx_branchformer_layer_weights* w, int dtype, int32_t B, int32_t T,
+                                              int has_sum_mask) {
+  if (!w || B <= 0 || T <= 0) return 0;
+  Arena a(nullptr, 0, true);
+  const float* sm = has_sum_mask ? (const float*)(uintptr_t)256 : nullptr;
+  branchformer_layer_generic(w, dtype, B, T, nullptr, nullptr, sm, nullptr, a, nullptr);
+  return a.peak;
+}
+int smx_branchformer_layer_fwd(const smx_branchformer_layer_weights* w, int dtype, int32_t B, int32_t T, const void* x,
+                               const uint8_t* padding_mask, const float* sum_mask, void* y, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");
+  SMX_TRY(check_bt(B, T));
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(y, "y"));
+  SMX_TRY(check_arch());
+  size_t need = smx_branchformer_layer_workspace_bytes(w, dtype, B, T, sum_mask != nullptr);
+  if (need > workspace_bytes || (need && !workspace))
+    return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  Arena a(workspace, workspace_bytes, false);
+  return branchformer_layer_generic(w, dtype, B, T, x, padding_mask, sum_mask, y, a, (cudaStream_t)stream);
+}
+size_t smx_branchformer_encoder_workspace_bytes(const smx_branchformer_layer_weights* layers, int32_t n_layers,
+                                                int dtype, int32_t B, int32_t T, int has_sum_mask) {
+  if (!layers || n_layers <= 0 || B <= 0 || T <= 0) return 0;
+  size_t m = 0;
+  for (int i = 0; i < n_layers; ++i) {
+    size_t s = smx_branchformer_layer_workspace_bytes(&layers[i], dtype, B, T, has_sum_mask);
+    if (s > m) m = s;
+  }
+  return m;
+}
+int smx_branchformer_encoder_fwd(const smx_branchformer_layer_weights* layers, int32_t n_layers,
+                                 const float* final_norm_w, const float* final_norm_b, int dtype, int32_t B, int32_t T,
+                                 const void* x, const uint8_t* padding_mask, const float* sum_mask, void* y,
+                                 void* workspace, size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  if (!layers || n_layers <= 0) return fail(SMX_ERR_BAD_ARG, "layers is NULL or n_layers <= 0");
+  if (!final_norm_w || !final_norm_b) return fail(SMX_ERR_BAD_ARG, "final norm weights are NULL");
+  SMX_TRY(check_bt(B, T));
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(y, "y"));
+  SMX_TRY(check_arch());
+  size_t need = smx_branchformer_encoder_workspace_bytes(layers, n_layers, dtype, B, T, sum_mask != nullptr);
+  if (need > workspace_bytes || (need && !workspace))
+    return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int D = layers[0].branch.pre.in_dim;
+  const int64_t rows = (int64_t)B * T;
+  const void* cur = x;
+  for (int i = 0; i < n_layers; ++i) {
+    Arena a(workspace, workspace_bytes, false);
+    SMX_TRY(branchformer_layer_generic(&layers[i], dtype, B, T, cur, padding_mask, sum_mask, y, a, st));
+    cur = y;
+  }
+  return layernorm(cur, dtype, D, final_norm_w, final_norm_b, 1e-6f, SMX_ACT_IDENTITY, y, dtype, D, rows, D, st);
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// Internal declarations shared by the libsmx translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stddef.h>
+#include "smx.h"
+
+namespace smx {
+
+// ---- error plumbing ---------------------------------------------------------------------
+int fail(int code, const char* fmt, ...);
+void count_launch(int n = 1);
+int check_launch(const char* what);  // cudaGetLastError -> SMX_ERR_CUDA
+
+#define SMX_TRY(expr)                \
+  do {                               \
+    int _s = (expr);                 \
+    if (_s != SMX_OK) return _s;     \
+  } while (0)
+
+inline size_t align_up(size_t v, size_t a = 256) { return (v + a - 1) / a * a; }
+
+// bump allocator over the caller's workspace
+struct Arena {
+  char* base;
+  size_t cap;
+  size_t off;
+  size_t peak;
+  bool dry;  // size computation only: nothing is launched, take() returns a dummy
+  Arena(void* p, size_t c, bool dry_run) : base((char*)p), cap(c), off(0), peak(0), dry(dry_run) {}
+  void* take(size_t bytes) {
+    size_t o = off;
+    off += align_up(bytes);
+    if (off > peak) peak = off;
+    if (dry) return (void*)(uintptr_t)256;  // non-null dummy, never dereferenced
+    if (off > cap) return nullptr;
+    return base + o;
+  }
+  float* f32(size_t n) { return (float*)take(n * sizeof(float)); }
+  size_t mark() const { return off; }
+  void release(size_t m) { off = m; }  // stream order makes reuse after release safe
+};
+
+inline size_t elem_size(int dtype) { return dtype == SMX_BF16 ? 2 : 4; }
+
+// ---- generic (fp32 math) kernels: smx_simt.cu -------------------------------------------
+struct GemmP {
+  const void* A;  int a_dtype;  int64_t lda;  int64_t a_bs;     // A[m*lda + k] (+ batch*a_bs)
+  const float* W;  int64_t w_sk;  int64_t w_sn;  int64_t w_bs;  // W[k*w_sk + n*w_sn] (+ batch*w_bs)
+  const float* bias;  int64_t bias_bs;                           // bias[n] (+ batch*bias_bs)
+  const float* rowbias;  int64_t rowbias_ld;  int32_t rowbias_div;  // + rowbias[(m/div)*ld + n]
+  const float* rowdiv;                                           // acc /= rowdiv[m] (before bias)
+  const uint8_t* rowmask;                                        // (after act) *= rowmask[m]
+  const void* residual;  int r_dtype;  int64_t ldr;  float alpha; // out = residual + alpha*v
+  void* C;  int c_dtype;  int64_t ldc;  int64_t c_bs;
+  int M, N, K, batches, act;
+};
+int gemm(const GemmP& p, cudaStream_t st);
+int layernorm(const void* x, int x_dtype, int64_t ldx, const float* w, const float* b, float eps, int act,
+              void* y, int y_dtype, int64_t ldy, int64_t rows, int D, cudaStream_t st);
+int masked_mean(const float* s, int64_t lds, const uint8_t* mask, int B, int T, int D, void* out, int out_dtype,
+                cudaStream_t st);
+int glu(const float* p, int64_t rows, int D, float* out, cudaStream_t st);
+int dwconv(const float* in, int64_t ldin, const float* w, const float* b, int B, int T, int C, int k, int pad_mode,
+           int chunk, float* out, int64_t ldout, cudaStream_t st);
+int gate_mul(const float* gate, int64_t ldg, const float* other, int64_t ldo, int gate_act, int64_t rows, int C,
+             float* out, cudaStream_t st);
+int broadcast_rows(const float* src, int B, int T, int D, float* dst, int64_t lddst, cudaStream_t st);
+int add_bcast(const float* a, const float* s, int64_t rows, int div, int D, float* out, cudaStream_t st);
+int laplace(float decay, const float* binary, int T, float* out, cudaStream_t st);
+int rowsum(const float* m, int rows, int cols, float* out, cudaStream_t st);
+int convert(const void* src, int s_dtype, void* dst, int d_dtype, int64_t n, cudaStream_t st);
+
+// host orchestration of the generic path (smx_generic.cu).  x/y/residual carry their own dtype tags.
+int vanilla_generic(const smx_linear* blocks, int n, int act, const void* x, int x_dt, int64_t ldx, int64_t rows,
+                    const uint8_t* rowmask, const void* residual, int r_dt, int64_t ldr, void* y, int y_dt,
+                    int64_t ldy, Arena& ws, cudaStream_t st);
+int cell_generic(const smx_cell_weights* w, int B, int T, const void* x, int x_dt, const uint8_t* mask,
+                 const float* sum_mask, const void* residual, int r_dt, void* y, int y_dt, int64_t ldy, Arena& ws,
+                 cudaStream_t st);
+int ffn_generic(const smx_ffn_weights* w, int act, int64_t rows, const void* x, int x_dt, const float* oln_w,
+                const float* oln_b, float oln_eps, void* y, int y_dt, Arena& ws, cudaStream_t st);
+int convmod_generic(const smx_convmod_weights* w, int act, int B, int T, int chunk, const void* x, int x_dt,
+                    const uint8_t* mask, const void* residual, int r_dt, void* y, int y_dt, Arena& ws,
+                    cudaStream_t st);
+int conformer_layer_generic(const smx_conformer_layer_weights* w, int dtype, int B, int T, int chunk, const void* x,
+                            const uint8_t* mask, const float* sum_mask, void* y, Arena& ws, cudaStream_t st);
+int branchformer_layer_generic(const smx_branchformer_layer_weights* w, int dtype, int B, int T, const void* x,
+                               const uint8_t* mask, const float* sum_mask, void* y, Arena& ws, cudaStream_t st);
+
+}  // namespace smx

@@ -1,0 +1,387 @@
+// Generic fp32-math kernels of libsmx: the exact-precision arm of the SummaryMixing encoder path.
+// Every tensor carries a runtime dtype tag (fp32 or bf16 storage); arithmetic is fp32 throughout.
+// These kernels handle every shape and mode the reference accepts; the tcgen05 arm (smx_tc_*.cu)
+// takes over for the bf16 shapes it supports.
+#include "smx_internal.h"
+#include <math.h>
+
+namespace smx {
+
+__device__ __forceinline__ float ld_any(const void* p, int dt, int64_t i) {
+  return dt == SMX_BF16 ? __bfloat162float(((const __nv_bfloat16*)p)[i]) : ((const float*)p)[i];
+}
+__device__ __forceinline__ void st_any(void* p, int dt, int64_t i, float v) {
+  if (dt == SMX_BF16) ((__nv_bfloat16*)p)[i] = __float2bfloat16_rn(v);
+  else ((float*)p)[i] = v;
+}
+
+__device__ __forceinline__ float apply_act(int act, float x) {
+  switch (act) {
+    case SMX_ACT_SWISH: return x / (1.0f + expf(-x));
+    case SMX_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    case SMX_ACT_RELU: return fmaxf(x, 0.0f);
+    case SMX_ACT_LEAKY_RELU: return x >= 0.0f ? x : 0.01f * x;
+    case SMX_ACT_TANH: return tanhf(x);
+    case SMX_ACT_SIGMOID: return 1.0f / (1.0f + expf(-x));
+    case SMX_ACT_GELU_TANH: {
+      float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+      return 0.5f * x * (1.0f + tanhf(u));
+    }
+    default: return x;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// batched strided GEMM with fused epilogue.  64x64 tile, BK=16, 256 threads, 4x4 per thread.
+// ---------------------------------------------------------------------------------------------
+constexpr int BM = 64, BN = 64, BK = 16;
+
+__global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
+  __shared__ float As[BK][BM + 4];
+  __shared__ float Ws[BK][BN + 4];
+  const int batch = blockIdx.z;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int64_t a_off = (int64_t)batch * p.a_bs;
+  const float* W = p.W + (int64_t)batch * p.w_bs;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  for (int k0 = 0; k0 < p.K; k0 += BK) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      int idx = tid + e * 256;  // 0..1023
+      int kk = idx % BK, mm = idx / BK;
+      int m = m0 + mm, k = k0 + kk;
+      As[kk][mm] = (m < p.M && k < p.K) ? ld_any(p.A, p.a_dtype, a_off + (int64_t)m * p.lda + k) : 0.0f;
+      // W: choose the faster-varying index according to the strides so that loads coalesce
+      int kk2, nn2;
+      if (p.w_sn == 1) { nn2 = idx % BN; kk2 = idx / BN; } else { kk2 = idx % BK; nn2 = idx / BK; }
+      int n = n0 + nn2, k2 = k0 + kk2;
+      Ws[kk2][nn2] = (n < p.N && k2 < p.K) ? W[(int64_t)k2 * p.w_sk + (int64_t)n * p.w_sn] : 0.0f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Ws[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  const float* bias = p.bias ? p.bias + (int64_t)batch * p.bias_bs : nullptr;
+  const int64_t c_off = (int64_t)batch * p.c_bs;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+    float rd = p.rowdiv ? p.rowdiv[m] : 1.0f;
+    float rm = p.rowmask ? (float)p.rowmask[m] : 1.0f;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      if (p.rowdiv) v = v / rd;
+      if (bias) v += bias[n];
+      if (p.rowbias) v += p.rowbias[(int64_t)(m / p.rowbias_div) * p.rowbias_ld + n];
+      v = apply_act(p.act, v);
+      if (p.rowmask) v *= rm;
+      if (p.residual) v = ld_any(p.residual, p.r_dtype, (int64_t)m * p.ldr + c_off + n) + p.alpha * v;
+      st_any(p.C, p.c_dtype, (int64_t)m * p.ldc + c_off + n, v);
+    }
+  }
+}
+
+int gemm(const GemmP& p, cudaStream_t st) {
+  if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.batches <= 0) return fail(SMX_ERR_BAD_ARG, "gemm: empty problem");
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.batches);
+  if (grid.y > 65535) {  // split rows over several launches
+    GemmP q = p;
+    const int chunk = 65535 * BM;
+    for (int m0 = 0; m0 < p.M; m0 += chunk) {
+      q.M = (p.M - m0 < chunk) ? p.M - m0 : chunk;
+      q.A = (const char*)p.A + (int64_t)m0 * p.lda * (p.a_dtype == SMX_BF16 ? 2 : 4);
+      q.C = (char*)p.C + (int64_t)m0 * p.ldc * (p.c_dtype == SMX_BF16 ? 2 : 4);
+      if (p.residual) q.residual = (const char*)p.residual + (int64_t)m0 * p.ldr * (p.r_dtype == SMX_BF16 ? 2 : 4);
+      if (p.rowmask) q.rowmask = p.rowmask + m0;
+      if (p.rowdiv) q.rowdiv = p.rowdiv + m0;
+      if (p.rowbias) {
+        if (m0 % p.rowbias_div) return fail(SMX_ERR_UNSUPPORTED, "gemm: row split not aligned to rowbias_div");
+        q.rowbias = p.rowbias + (int64_t)(m0 / p.rowbias_div) * p.rowbias_ld;
+      }
+      SMX_TRY(gemm(q, st));
+    }
+    return SMX_OK;
+  }
+  gemm_kernel<<<grid, 256, 0, st>>>(p);
+  count_launch();
+  return check_launch("gemm_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm (+ optional activation) over rows of length D; one warp per row.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) ln_kernel(const void* x, int x_dt, int64_t ldx, const float* w, const float* b,
+                                                 float eps, int act, void* y, int y_dt, int64_t ldy, int64_t rows, int D) {
+  int64_t row = (int64_t)blockIdx.x * 8 + threadIdx.x / 32;
+  int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  float s = 0.0f;
+  for (int c = lane; c < D; c += 32) s += ld_any(x, x_dt, row * ldx + c);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  float mean = s / (float)D;
+  float v = 0.0f;
+  for (int c = lane; c < D; c += 32) {
+    float d = ld_any(x, x_dt, row * ldx + c) - mean;
+    v += d * d;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  float rstd = 1.0f / sqrtf(v / (float)D + eps);
+  for (int c = lane; c < D; c += 32) {
+    float o = (ld_any(x, x_dt, row * ldx + c) - mean) * rstd * w[c] + b[c];
+    st_any(y, y_dt, row * ldy + c, apply_act(act, o));
+  }
+}
+
+int layernorm(const void* x, int x_dtype, int64_t ldx, const float* w, const float* b, float eps, int act, void* y,
+              int y_dtype, int64_t ldy, int64_t rows, int D, cudaStream_t st) {
+  if (rows <= 0 || D <= 0) return fail(SMX_ERR_BAD_ARG, "layernorm: empty problem");
+  ln_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, x_dtype, ldx, w, b, eps, act, y, y_dtype, ldy, rows, D);
+  count_launch();
+  return check_launch("ln_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// masked temporal mean: out[b,d] = sum_t s[b,t,d] / sum_t mask[b,t]   (s is already masked)
+// summary_mixing.py:229-231.  Fixed reduction order: deterministic.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) masked_mean_kernel(const float* s, int64_t lds, const uint8_t* mask, int T, int D,
+                                                          void* out, int out_dt) {
+  __shared__ float red[8][33];
+  __shared__ float cnt[8];
+  int b = blockIdx.y;
+  int cx = threadIdx.x % 32, ry = threadIdx.x / 32;
+  int d = blockIdx.x * 32 + cx;
+  float acc = 0.0f, c = 0.0f;
+  for (int t = ry; t < T; t += 8) {
+    if (d < D) acc += s[((int64_t)b * T + t) * lds + d];
+    c += mask ? (float)mask[(int64_t)b * T + t] : 1.0f;
+  }
+  red[ry][cx] = acc;
+  if (cx == 0) cnt[ry] = c;
+  __syncthreads();
+  if (ry == 0 && d < D) {
+    float tot = 0.0f, n = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) { tot += red[r][cx]; n += cnt[r]; }
+    st_any(out, out_dt, (int64_t)b * D + d, tot / n);
+  }
+}
+
+int masked_mean(const float* s, int64_t lds, const uint8_t* mask, int B, int T, int D, void* out, int out_dtype,
+                cudaStream_t st) {
+  dim3 grid((D + 31) / 32, B);
+  masked_mean_kernel<<<grid, 256, 0, st>>>(s, lds, mask, T, D, out, out_dtype);
+  count_launch();
+  return check_launch("masked_mean_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// GLU over the channel dim: out[r,c] = p[r,c] * sigmoid(p[r,c+D])          Conformer.py:139
+// ---------------------------------------------------------------------------------------------
+__global__ void glu_kernel(const float* p, int64_t rows, int D, float* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * D) return;
+  int64_t r = i / D;
+  int c = (int)(i % D);
+  float a = p[r * 2 * D + c], g = p[r * 2 * D + D + c];
+  out[i] = a / (1.0f + expf(-g));
+}
+int glu(const float* p, int64_t rows, int D, float* out, cudaStream_t st) {
+  int64_t n = rows * D;
+  glu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p, rows, D, out);
+  count_launch();
+  return check_launch("glu_kernel");
+}
+
+// ---------------------------------------------------------------------------------------------
+// depthwise conv along T with the four boundary rules of smx_conv_pad.
+// ---------------------------------------------------------------------------------------------
+__global__ void dwconv_kernel(const float* in, int64_t ldin, const float* w, const float* bias, int B, int T, int C,
+                              int k, int pad_mode, int chunk, float* out, int64_t ldout) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * T * C) return;
+  int c = (int)(i % C);
+  int t = (int)((i / C) % T);
+  int b = (int)(i / ((int64_t)C * T));
+  int pad = (pad_mode == SMX_CONV_CAUSAL) ? (k - 1) : (k - 1) / 2;
+  int hi = T;  // exclusive upper bound of visible frames
+  if (pad_mode == SMX_CONV_CHUNKED) {
+    int ce = (t / chunk + 1) * chunk;
+    hi = ce < T ? ce : T;
+  }
+  float acc = bias ? bias[c] : 0.0f;
+  const float* base = in + (int64_t)b * T * ldin + c;
+  for (int j = 0; j < k; ++j) {
+    int u = t + j - pad;
+    if (pad_mode == SMX_CONV_SAME_REFLECT) {
+      if (u < 0) u = -u;
+      if (u >= T) u = 2 * (T - 1) - u;
+    } else if (u < 0 || u >= hi) {
+      continue;
+    }
+    acc = fmaf(w[(int64_t)c * k + j], base[(int64_t)u * ldin], acc);
+  }
+  out[((int64_t)b * T + t) * ldout + c] = acc;
+}
+int dwconv(const float* in, int64_t ldin, const float* w, const float* b, int B, int T, int C, int k, int pad_mode,
+           int chunk, float* out, int64_t ldout, cudaStream_t st) {
+  if (pad_mode == SMX_CONV_SAME_REFLECT && (k - 1) / 2 >= T)
+    return fail(SMX_ERR_BAD_ARG, "reflect padding %d needs T > pad (T=%d)", (k - 1) / 2, T);
+  if (pad_mode == SMX_CONV_CHUNKED && chunk <= 0) return fail(SMX_ERR_BAD_ARG, "chunked conv needs chunk_size > 0");
+  int64_t n = (int64_t)B * T * C;
+  dwconv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, ldin, w, b, B, T, C, k, pad_mode, chunk, out, ldout);
+  count_launch();
+  return check_launch("dwconv_kernel");
+}
+
+// out = act(gate) * other                                   (CSGU gating)
+__global__ void gate_mul_kernel(const float* gate, int64_t ldg, const float* other, int64_t ldo, int act, int64_t rows,
+                                int C, float* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  int64_t r = i / C;
+  int c = (int)(i % C);
+  out[i] = apply_act(act, gate[r * ldg + c]) * other[r * ldo + c];
+}
+int gate_mul(const float* gate, int64_t ldg, const float* other, int64_t ldo, int gate_act, int64_t rows, int C,
+             float* out, cudaStream_t st) {
+  int64_t n = rows * C;
+  gate_mul_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(gate, ldg, other, ldo, gate_act, rows, C, out);
+  count_launch();
+  return check_launch("gate_mul_kernel");
+}
+
+// dst[(b*T+t)*ld + d] = src[b*D + d]
+__global__ void broadcast_rows_kernel(const float* src, int B, int T, int D, float* dst, int64_t ld) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * T * D) return;
+  int d = (int)(i % D);
+  int64_t bt = i / D;
+  int b = (int)(bt / T);
+  dst[bt * ld + d] = src[(int64_t)b * D + d];
+}
+int broadcast_rows(const float* src, int B, int T, int D, float* dst, int64_t lddst, cudaStream_t st) {
+  int64_t n = (int64_t)B * T * D;
+  broadcast_rows_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, B, T, D, dst, lddst);
+  count_launch();
+  return check_launch("broadcast_rows_kernel");
+}
+
+// out[r,c] = a[r,c] + s[(r/div),c]
+__global__ void add_bcast_kernel(const float* a, const float* s, int64_t rows, int div, int D, float* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * D) return;
+  int64_t r = i / D;
+  int c = (int)(i % D);
+  out[i] = a[i] + s[(r / div) * D + c];
+}
+int add_bcast(const float* a, const float* s, int64_t rows, int div, int D, float* out, cudaStream_t st) {
+  int64_t n = rows * D;
+  add_bcast_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(a, s, rows, div, D, out);
+  count_launch();
+  return check_launch("add_bcast_kernel");
+}
+
+// Laplace weights decay^|i-j| (* binary mask)                  summary_mixing.py:330-379
+__global__ void laplace_kernel(float log_decay, const float* binary, int T, float* out) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)T * T) return;
+  int r = (int)(i / T), c = (int)(i % T);
+  float v = expf((float)abs(r - c) * log_decay);
+  out[i] = binary ? v * binary[i] : v;
+}
+int laplace(float decay, const float* binary, int T, float* out, cudaStream_t st) {
+  int64_t n = (int64_t)T * T;
+  laplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(logf(decay), binary, T, out);
+  count_launch();
+  return check_launch("laplace_kernel");
+}
+
+__global__ void rowsum_kernel(const float* m, int rows, int cols, float* out) {
+  int row = blockIdx.x * 8 + threadIdx.x / 32;
+  int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  float s = 0.0f;
+  for (int c = lane; c < cols; c += 32) s += m[(int64_t)row * cols + c];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  if (lane == 0) out[row] = s;
+}
+int rowsum(const float* m, int rows, int cols, float* out, cudaStream_t st) {
+  rowsum_kernel<<<(rows + 7) / 8, 256, 0, st>>>(m, rows, cols, out);
+  count_launch();
+  return check_launch("rowsum_kernel");
+}
+
+__global__ void convert_kernel(const void* src, int s_dt, void* dst, int d_dt, int64_t n) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) st_any(dst, d_dt, i, ld_any(src, s_dt, i));
+}
+int convert(const void* src, int s_dtype, void* dst, int d_dtype, int64_t n, cudaStream_t st) {
+  if (n <= 0) return SMX_OK;
+  convert_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(src, s_dtype, dst, d_dtype, n);
+  count_launch();
+  return check_launch("convert_kernel");
+}
+
+// mask builders ------------------------------------------------------------------------------
+__global__ void padding_mask_kernel(const float* wav_len, int B, int T, uint8_t* mask) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * T) return;
+  int b = (int)(i / T), t = (int)(i % T);
+  float abs_len = rintf(wav_len[b] * (float)T);  // torch.round: half to even
+  mask[i] = (float)t < abs_len ? 1 : 0;
+}
+__global__ void chunk_mask_kernel(int T, int chunk, int left, float* mask) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)T * T) return;
+  int r = (int)(i / T), c = (int)(i % T);
+  int end = (r / chunk + 1) * chunk;
+  bool vis = c < end;
+  if (left >= 0) vis = vis && (c >= end - chunk * (left + 1));
+  mask[i] = vis ? 1.0f : 0.0f;
+}
+
+}  // namespace smx
+
+extern "C" int smx_padding_mask_from_wav_len(const float* wav_len, int32_t B, int32_t T, uint8_t* mask, void* stream) {
+  if (!wav_len || !mask || B <= 0 || T <= 0) return smx::fail(SMX_ERR_BAD_ARG, "padding_mask: bad argument");
+  int64_t n = (int64_t)B * T;
+  smx::padding_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(wav_len, B, T, mask);
+  smx::count_launch();
+  return smx::check_launch("padding_mask_kernel");
+}
+
+extern "C" int smx_chunk_mask(int32_t T, int32_t chunk_size, int32_t left_context_chunks, float* mask, void* stream) {
+  if (!mask || T <= 0 || chunk_size <= 0) return smx::fail(SMX_ERR_BAD_ARG, "chunk_mask: bad argument");
+  int64_t n = (int64_t)T * T;
+  smx::chunk_mask_kernel<<<(unsigned)((n + 255) / 256), 256, 0, (cudaStream_t)stream>>>(T, chunk_size,
+                                                                                       left_context_chunks, mask);
+  smx::count_launch();
+  return smx::check_launch("chunk_mask_kernel");
+}

@@ -1,0 +1,180 @@
+"""SummaryMixing cell with the reference's surface (reference: speechbrain/nnet/summary_mixing.py).
+
+Constructor signature, mode validation, sub-module names and state_dict keys follow summary_mixing.py:78-167;
+``forward(x, sum_mask=None, src_padding_mask=None)`` follows :169-196.  The arithmetic runs in libsmx
+(smx_summary_mixing_fwd).  Differences, deliberate: the default mask is built on x's device (the reference
+allocates it on the CPU, :186, which breaks on GPU), and dropout is identity (inference path).
+"""
+from __future__ import annotations
+
+from typing import Optional
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from .. import _host as H
+from .. import _lib as L
+from ..lobes.models.VanillaNN import VanillaNN
+
+
+class SummaryMixing(nn.Module):
+    """SummaryMixing (https://arxiv.org/abs/2307.07421): y_t = combiner([f(x_t), mean_t s(x_t)]).
+
+    Arguments are those of the reference class (summary_mixing.py:32-66).
+    """
+
+    def __init__(
+        self,
+        enc_dim,
+        nhead,
+        local_proj_hid_dim: Optional[list] = [512],
+        local_proj_out_dim: Optional[int] = 512,
+        summary_hid_dim: Optional[list] = [512],
+        summary_out_dim: Optional[int] = 512,
+        activation: Optional[nn.Module] = nn.GELU,
+        global_dropout: Optional[float] = 0.1,
+        mode: Optional[str] = "SummaryMixing",
+        use_layernorm: Optional[bool] = True,
+    ):
+        super(SummaryMixing, self).__init__()
+
+        if mode not in L.MODES:
+            raise ValueError(
+                "The SummaryMixing mode should either be 'SummaryMixing', 'SummaryMixing-lite', 'SummaryMixing-fast' or 'SummaryMixing-expdecay'"
+            )
+
+        self.local_proj_hid_dim = local_proj_hid_dim
+        self.local_proj_out_dim = local_proj_out_dim
+        self.summary_hid_dim = summary_hid_dim
+        self.summary_out_dim = summary_out_dim
+        self.summary_reshaped_dim = int(np.sqrt(summary_out_dim))
+        self.enc_dim = enc_dim
+        self.nhead = nhead
+        self.activation = activation()
+        self.local_dnn_blocks = local_proj_hid_dim + [local_proj_out_dim]
+        self.summary_dnn_blocks = summary_hid_dim + [summary_out_dim]
+        self.mode = mode
+        self.use_layernorm = use_layernorm
+        self.dropout = nn.Dropout(global_dropout)
+
+        if self.mode == "SummaryMixing" or self.mode == "SummaryMixing-expdecay":
+            self.local_proj = VanillaNN(
+                input_shape=[None, None, enc_dim],
+                dnn_blocks=len(self.local_dnn_blocks),
+                dnn_neurons=self.local_dnn_blocks,
+                activation=activation,
+                n_split=nhead,
+            )
+            self.summary_local_merging = VanillaNN(
+                input_shape=[None, None, local_proj_out_dim + summary_out_dim],
+                dnn_blocks=1,
+                dnn_neurons=[summary_out_dim],
+                activation=activation,
+            )
+
+        if self.mode == "SummaryMixing-fast":
+            self.global_proj = VanillaNN(
+                input_shape=[None, None, enc_dim],
+                dnn_blocks=1,
+                dnn_neurons=self.local_proj_out_dim * 2,
+                activation=activation,
+                n_split=1,
+            )
+            self.summary_local_merging = VanillaNN(
+                input_shape=[None, None, self.local_proj_out_dim * 2],
+                dnn_blocks=1,
+                dnn_neurons=[summary_out_dim],
+                activation=activation,
+            )
+        else:
+            self.summary_proj = VanillaNN(
+                input_shape=[None, None, enc_dim],
+                dnn_blocks=len(self.summary_dnn_blocks),
+                dnn_neurons=self.summary_dnn_blocks,
+                activation=activation,
+                n_split=nhead,
+            )
+
+        if self.mode == "SummaryMixing-expdecay":
+            self.decay_constant = nn.Parameter(data=torch.tensor(0.995), requires_grad=False)
+
+        if self.use_layernorm:
+            # created in every mode, as in the reference (:163-165); unused by lite and fast
+            self.local_norm = nn.LayerNorm(local_proj_out_dim)
+            self.summary_norm = nn.LayerNorm(summary_out_dim)
+
+        self.apply(self._init_parameters)
+        self._act_code = H.act_code(self.activation)
+        self._wv = H.WeightView()
+
+    def _init_parameters(self, module):
+        if isinstance(module, nn.Linear):
+            torch.nn.init.zeros_(module.bias)
+
+    # -- library plumbing -------------------------------------------------------------------------
+    def params(self):
+        return [p for p in self.parameters()]
+
+    def fill(self, cw: L.CellWeights, wv: H.WeightView, device) -> None:
+        """Fill an smx_cell_weights from this module's parameters."""
+        cw.mode = L.MODES[self.mode]
+        cw.act = self._act_code
+        cw.use_layernorm = int(bool(self.use_layernorm))
+        cw.enc_dim = self.enc_dim
+        cw.local_out_dim = self.local_proj_out_dim
+        cw.summary_out_dim = self.summary_out_dim
+        cw.n_local = cw.n_summary = 0
+        if hasattr(self, "local_proj"):
+            cw.n_local = self.local_proj.fill(cw.local, wv, device)
+        if hasattr(self, "summary_proj"):
+            cw.n_summary = self.summary_proj.fill(cw.summary, wv, device)
+        if hasattr(self, "global_proj"):
+            gp = (L.Linear * L.SMX_MAX_BLOCKS)()
+            self.global_proj.fill(gp, wv, device)
+            cw.global_proj = gp[0]
+        if hasattr(self, "summary_local_merging"):
+            mg = (L.Linear * L.SMX_MAX_BLOCKS)()
+            self.summary_local_merging.fill(mg, wv, device)
+            cw.merge = mg[0]
+        if self.use_layernorm:
+            cw.local_norm_w = wv.ptr(self.local_norm.weight, device)
+            cw.local_norm_b = wv.ptr(self.local_norm.bias, device)
+            cw.summary_norm_w = wv.ptr(self.summary_norm.weight, device)
+            cw.summary_norm_b = wv.ptr(self.summary_norm.bias, device)
+        if self.mode == "SummaryMixing-expdecay":
+            cw.decay_constant = float(self.decay_constant)
+
+    @property
+    def out_dim(self) -> int:
+        return self.summary_out_dim
+
+    def forward(self, x, sum_mask=None, src_padding_mask=None):
+        """x: (B,T,enc_dim); sum_mask: (T,T) or None; src_padding_mask: (B,T), 1/True = valid frame.
+        Returns (B,T,summary_out_dim) in x's dtype (lite: a stride-0 expand over T, as the reference, :322)."""
+        H.require_cuda(x, "SummaryMixing")
+        H.check_grad_mode(self)
+        if x.dim() != 3 or x.shape[-1] != self.enc_dim:
+            raise RuntimeError(f"SummaryMixing expects (B,T,{self.enc_dim}), got {tuple(x.shape)}")
+        B, T, _ = x.shape
+        dev = x.device
+        xc = x.contiguous()
+        mask = H.mask_u8(src_padding_mask, B, T, dev)
+        smask = H.sum_mask_f32(sum_mask, T, dev)
+        if self._wv.stale(self.params(), dev):
+            cw = L.CellWeights()
+            self.fill(cw, self._wv, dev)
+            self._wv.struct = cw
+        lite = self.mode == "SummaryMixing-lite"
+        y = torch.empty((B, self.summary_out_dim) if lite else (B, T, self.summary_out_dim), dtype=x.dtype, device=dev)
+        lib = L.lib()
+        dt = H.dtype_code(xc)
+        with torch.cuda.device(dev):
+            nbytes = lib.smx_summary_mixing_workspace_bytes(self._wv.struct, dt, B, T, int(smask is not None))
+            ws = H.workspace(dev, nbytes)
+            L.check(lib.smx_summary_mixing_fwd(self._wv.struct, dt, B, T, xc.data_ptr(), H.p_or_none(mask),
+                                               H.p_or_none(smask), None, y.data_ptr(), ws.data_ptr(), ws.numel(),
+                                               H.stream_ptr(dev)))
+        if lite:
+            return y.unsqueeze(1).expand(-1, T, -1)
+        return y
