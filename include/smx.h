@@ -105,6 +105,7 @@ typedef struct {
   const float* local_norm_b;
   const float* summary_norm_w;
   const float* summary_norm_b;
+  const void* packed;      /* bf16 operand image from smx_cell_pack(), or NULL (generic arm) */
   float decay_constant;    /* EXPDECAY (summary_mixing.py:158-161) */
   int32_t _pad;
 } smx_cell_weights;
@@ -115,6 +116,7 @@ typedef struct {
   const float* ln_b;
   smx_linear w1; /* D -> d_ffn */
   smx_linear w2; /* d_ffn -> D */
+  const void* packed; /* bf16 operand image from smx_ffn_pack(), or NULL (generic arm) */
 } smx_ffn_weights;
 
 /* ConvolutionModule (Conformer.py:80-340). */
@@ -127,6 +129,7 @@ typedef struct {
   const float* after_ln_w;
   const float* after_ln_b;
   smx_linear out;         /* after_conv.2: D -> D */
+  const void* packed;     /* bf16 operand image from smx_convmod_pack(), or NULL (generic arm) */
   int32_t kernel_size;
   int32_t causal;
 } smx_convmod_weights;
@@ -182,6 +185,19 @@ SMX_API const char* smx_last_error(void);
 SMX_API size_t smx_struct_size(int which);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 SMX_API uint64_t smx_launch_count(void);
+/* of those, launches of tcgen05 (tensor-core arm) kernels */
+SMX_API uint64_t smx_tc_launch_count(void);
+
+/* ---- weight packing for the bf16 tensor-core (tcgen05) arm ----------------------------------------
+ * With dtype SMX_BF16 a module runs on the tensor-core arm when its weights struct carries a `packed`
+ * image; otherwise (or for configurations the arm does not handle: *_packed_bytes() == 0) the generic
+ * fp32-math arm runs.  Pack once per weight set; `packed` must be 1024-byte aligned device memory. */
+SMX_API size_t smx_cell_packed_bytes(const smx_cell_weights* w);
+SMX_API int smx_cell_pack(const smx_cell_weights* w, void* packed, size_t packed_bytes, void* stream);
+SMX_API size_t smx_ffn_packed_bytes(const smx_ffn_weights* w);
+SMX_API int smx_ffn_pack(const smx_ffn_weights* w, void* packed, size_t packed_bytes, void* stream);
+SMX_API size_t smx_convmod_packed_bytes(const smx_convmod_weights* w);
+SMX_API int smx_convmod_pack(const smx_convmod_weights* w, void* packed, size_t packed_bytes, void* stream);
 
 /* ---- primitives (each replaces one reference module call) ---------------------------------- */
 

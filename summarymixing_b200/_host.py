@@ -142,6 +142,21 @@ def check_grad_mode(module: nn.Module) -> None:
         )
 
 
+def pack_tc(wv: WeightView, device, struct, bytes_fn, pack_fn) -> None:
+    """Build the bf16 operand image for the tensor-core arm (once per weight set) and hang it on the
+    weights struct.  Configurations the arm does not handle report 0 bytes and stay on the generic arm."""
+    struct.packed = None
+    nbytes = int(bytes_fn(C.byref(struct)))
+    if nbytes == 0:
+        return
+    buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+    ptr = (buf.data_ptr() + 1023) & ~1023
+    with torch.cuda.device(device):
+        L.check(pack_fn(C.byref(struct), ptr, nbytes, stream_ptr(device)))
+    wv._keep.append(buf)
+    struct.packed = ptr
+
+
 def fill_linear(dst: L.Linear, wv: WeightView, device, w, b, in_dim, out_dim, n_split=1):
     dst.w = wv.ptr(w, device)
     dst.b = wv.ptr(b, device)

@@ -38,16 +38,17 @@ class CellWeights(C.Structure):
                 ("local_out_dim", C.c_int32), ("summary_out_dim", C.c_int32), ("n_local", C.c_int32),
                 ("n_summary", C.c_int32), ("local", Linear * SMX_MAX_BLOCKS), ("summary", Linear * SMX_MAX_BLOCKS),
                 ("global_proj", Linear), ("merge", Linear), ("local_norm_w", fp), ("local_norm_b", fp),
-                ("summary_norm_w", fp), ("summary_norm_b", fp), ("decay_constant", C.c_float), ("_pad", C.c_int32)]
+                ("summary_norm_w", fp), ("summary_norm_b", fp), ("packed", fp), ("decay_constant", C.c_float),
+                ("_pad", C.c_int32)]
 
 
 class FFNWeights(C.Structure):
-    _fields_ = [("ln_w", fp), ("ln_b", fp), ("w1", Linear), ("w2", Linear)]
+    _fields_ = [("ln_w", fp), ("ln_b", fp), ("w1", Linear), ("w2", Linear), ("packed", fp)]
 
 
 class ConvModWeights(C.Structure):
     _fields_ = [("ln_w", fp), ("ln_b", fp), ("bottleneck", Linear), ("dw_w", fp), ("dw_b", fp), ("after_ln_w", fp),
-                ("after_ln_b", fp), ("out", Linear), ("kernel_size", C.c_int32), ("causal", C.c_int32)]
+                ("after_ln_b", fp), ("out", Linear), ("packed", fp), ("kernel_size", C.c_int32), ("causal", C.c_int32)]
 
 
 class ConformerLayerWeights(C.Structure):
@@ -81,7 +82,14 @@ _PROTOS = {
     "smx_version": (C.c_int, []),
     "smx_last_error": (C.c_char_p, []),
     "smx_launch_count": (C.c_uint64, []),
+    "smx_tc_launch_count": (C.c_uint64, []),
     "smx_struct_size": (_sz, [_i]),
+    "smx_cell_packed_bytes": (_sz, [C.POINTER(CellWeights)]),
+    "smx_cell_pack": (_i, [C.POINTER(CellWeights), _vp, _sz, _vp]),
+    "smx_ffn_packed_bytes": (_sz, [C.POINTER(FFNWeights)]),
+    "smx_ffn_pack": (_i, [C.POINTER(FFNWeights), _vp, _sz, _vp]),
+    "smx_convmod_packed_bytes": (_sz, [C.POINTER(ConvModWeights)]),
+    "smx_convmod_pack": (_i, [C.POINTER(ConvModWeights), _vp, _sz, _vp]),
     "smx_layernorm_fwd": (_i, [_i, _i64, _i, _vp, _vp, _vp, _f, _vp, _vp]),
     "smx_vanilla_nn_workspace_bytes": (_sz, [C.POINTER(Linear), _i, _i, _i64]),
     "smx_vanilla_nn_fwd": (_i, [C.POINTER(Linear), _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),

@@ -10,6 +10,7 @@ namespace smx {
 
 static thread_local char g_err[512] = "";
 static std::atomic<uint64_t> g_launches{0};
+static std::atomic<uint64_t> g_tc_launches{0};
 
 int fail(int code, const char* fmt, ...) {
   va_list ap;
@@ -19,6 +20,7 @@ int fail(int code, const char* fmt, ...) {
   return code;
 }
 void count_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
+void count_tc_launch(int n) { g_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); g_tc_launches.fetch_add((uint64_t)n, std::memory_order_relaxed); }
 int check_launch(const char* what) {
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
@@ -51,10 +53,6 @@ static int check_arch() {
   if (cached < 0) return fail(SMX_ERR_ARCH, "libsmx is built for sm_100a (B200) only");
   return SMX_OK;
 }
-static int ws_ok(Arena& a, size_t given) {
-  if (a.peak > given) return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", a.peak, given);
-  return SMX_OK;
-}
 
 }  // namespace smx
 
@@ -65,6 +63,7 @@ extern "C" {
 int smx_version(void) { return SMX_VERSION; }
 const char* smx_last_error(void) { return g_err; }
 uint64_t smx_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+uint64_t smx_tc_launch_count(void) { return g_tc_launches.load(std::memory_order_relaxed); }
 size_t smx_struct_size(int which) {
   switch (which) {
     case 0: return sizeof(smx_linear);
@@ -76,6 +75,36 @@ size_t smx_struct_size(int which) {
     case 6: return sizeof(smx_branchformer_layer_weights);
     default: return 0;
   }
+}
+
+// ---- weight packing for the tcgen05 arm ------------------------------------------------------------
+static int check_packed(const void* packed, size_t given, size_t need) {
+  if (need == 0) return fail(SMX_ERR_UNSUPPORTED, "this configuration is not handled by the tensor-core arm");
+  if (!packed) return fail(SMX_ERR_BAD_ARG, "packed is NULL");
+  if ((uintptr_t)packed & 1023) return fail(SMX_ERR_ALIGNMENT, "packed must be 1024-byte aligned");
+  if (given < need) return fail(SMX_ERR_WORKSPACE, "packed buffer too small: need %zu bytes, got %zu", need, given);
+  return SMX_OK;
+}
+size_t smx_cell_packed_bytes(const smx_cell_weights* w) { return w ? tc_cell_packed_bytes(w) : 0; }
+int smx_cell_pack(const smx_cell_weights* w, void* packed, size_t packed_bytes, void* stream) {
+  if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");
+  SMX_TRY(check_packed(packed, packed_bytes, tc_cell_packed_bytes(w)));
+  SMX_TRY(check_arch());
+  return tc_cell_pack(w, packed, (cudaStream_t)stream);
+}
+size_t smx_ffn_packed_bytes(const smx_ffn_weights* w) { return w ? tc_ffn_packed_bytes(w) : 0; }
+int smx_ffn_pack(const smx_ffn_weights* w, void* packed, size_t packed_bytes, void* stream) {
+  if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");
+  SMX_TRY(check_packed(packed, packed_bytes, tc_ffn_packed_bytes(w)));
+  SMX_TRY(check_arch());
+  return tc_ffn_pack(w, packed, (cudaStream_t)stream);
+}
+size_t smx_convmod_packed_bytes(const smx_convmod_weights* w) { return w ? tc_convmod_packed_bytes(w) : 0; }
+int smx_convmod_pack(const smx_convmod_weights* w, void* packed, size_t packed_bytes, void* stream) {
+  if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");
+  SMX_TRY(check_packed(packed, packed_bytes, tc_convmod_packed_bytes(w)));
+  SMX_TRY(check_arch());
+  return tc_convmod_pack(w, packed, (cudaStream_t)stream);
 }
 
 // ---- LayerNorm -----------------------------------------------------------------------------
@@ -119,7 +148,7 @@ size_t smx_summary_mixing_workspace_bytes(const smx_cell_weights* w, int dtype, 
   const float* sm = has_sum_mask ? (const float*)(uintptr_t)256 : nullptr;
   int Dout = w->mode == SMX_MODE_LITE ? w->summary_out_dim : w->merge.out_dim;
   cell_generic(w, B, T, nullptr, dtype, nullptr, sm, nullptr, dtype, nullptr, dtype, Dout, a, nullptr);
-  size_t tc = tc_cell_workspace_bytes(w, dtype, B, T, has_sum_mask);
+  size_t tc = (dtype == SMX_BF16 && w->packed) ? tc_cell_workspace_bytes(w, B, T) : 0;
   return a.peak > tc ? a.peak : tc;
 }
 int smx_summary_mixing_fwd(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x,
@@ -135,6 +164,9 @@ int smx_summary_mixing_fwd(const smx_cell_weights* w, int dtype, int32_t B, int3
     return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
   Arena a(workspace, workspace_bytes, false);
   int Dout = w->mode == SMX_MODE_LITE ? w->summary_out_dim : w->merge.out_dim;
+  if (dtype == SMX_BF16 && w->packed && tc_cell_supported(w, sum_mask != nullptr))
+    return tc_cell_fwd(w, w->packed, B, T, (const __nv_bfloat16*)x, nullptr, nullptr, padding_mask,
+                       (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, a, (cudaStream_t)stream);
   return cell_generic(w, B, T, x, dtype, padding_mask, sum_mask, residual, dtype, y, dtype, Dout, a, (cudaStream_t)stream);
 }
 
@@ -143,7 +175,8 @@ size_t smx_conv_module_workspace_bytes(const smx_convmod_weights* w, int dtype, 
   if (!w || B <= 0 || T <= 0) return 0;
   Arena a(nullptr, 0, true);
   convmod_generic(w, 0, B, T, 0, nullptr, dtype, nullptr, nullptr, dtype, nullptr, dtype, a, nullptr);
-  return a.peak;
+  size_t tc = (dtype == SMX_BF16 && w->packed) ? tc_convmod_workspace_bytes(w, B, T) : 0;
+  return a.peak > tc ? a.peak : tc;
 }
 int smx_conv_module_fwd(const smx_convmod_weights* w, int act, int dtype, int32_t B, int32_t T, int32_t chunk_size,
                         const void* x, const uint8_t* padding_mask, const void* residual, void* y, void* workspace,
@@ -157,6 +190,9 @@ int smx_conv_module_fwd(const smx_convmod_weights* w, int act, int dtype, int32_
   if (need > workspace_bytes || (need && !workspace))
     return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
   Arena a(workspace, workspace_bytes, false);
+  if (dtype == SMX_BF16 && w->packed && tc_convmod_supported(w, chunk_size))
+    return tc_convmod_fwd(w, w->packed, act, B, T, (const __nv_bfloat16*)x, padding_mask, (const __nv_bfloat16*)residual,
+                          (__nv_bfloat16*)y, a, (cudaStream_t)stream);
   return convmod_generic(w, act, B, T, chunk_size, x, dtype, padding_mask, residual, dtype, y, dtype, a, (cudaStream_t)stream);
 }
 
@@ -178,6 +214,9 @@ int smx_ffn_fwd(const smx_ffn_weights* w, int act, int dtype, int64_t rows, cons
   if (need > workspace_bytes || (need && !workspace))
     return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
   Arena a(workspace, workspace_bytes, false);
+  if (dtype == SMX_BF16 && w->packed && tc_ffn_supported(w))
+    return tc_ffn_fwd(w, w->packed, act, rows, (const __nv_bfloat16*)x, out_ln_w, out_ln_b, out_ln_eps, (__nv_bfloat16*)y, a,
+                      (cudaStream_t)stream);
   return ffn_generic(w, act, rows, x, dtype, out_ln_w, out_ln_b, out_ln_eps, y, dtype, a, (cudaStream_t)stream);
 }
 

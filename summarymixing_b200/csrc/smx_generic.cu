@@ -3,6 +3,7 @@
 // x / y / residual tensors carry their own dtype tag.  Every function also runs "dry" (ws.dry) to size
 // the workspace: same control flow, no launches.
 #include "smx_internal.h"
+#include "smx_tc.h"
 
 namespace smx {
 
@@ -246,35 +247,66 @@ int convmod_generic(const smx_convmod_weights* w, int act, int B, int T, int chu
 
 // ---------------------------------------------------------------------------------------------
 // ConformerEncoderLayer                                               Conformer.py:490-548
+// fp32: generic arm with fp32 intermediates.  bf16: bf16 intermediates; each module runs on the
+// tcgen05 arm when its weights carry a packed image and the configuration is supported, else on the
+// generic arm (which reads/writes bf16 through the dtype tags).
 // ---------------------------------------------------------------------------------------------
 int conformer_layer_generic(const smx_conformer_layer_weights* w, int dtype, int B, int T, int chunk, const void* x,
                             const uint8_t* mask, const float* sum_mask, void* y, Arena& ws, cudaStream_t st) {
   const int64_t rows = (int64_t)B * T;
   const int D = w->ffn1.w1.in_dim;
+  const int idt = dtype;  // dtype of the inter-module activations
+  const size_t es = elem_size(idt);
   const size_t m0 = ws.mark();
-  float* x1 = ws.f32((size_t)rows * D);
-  float* n1 = ws.f32((size_t)rows * D);
-  float* x2 = ws.f32((size_t)rows * D);
-  if (!x1 || !n1 || !x2) return fail(SMX_ERR_WORKSPACE, "workspace too small (conformer layer)");
+  void* x1 = ws.take((size_t)rows * D * es);
+  void* x2 = ws.take((size_t)rows * D * es);
+  if (!x1 || !x2) return fail(SMX_ERR_WORKSPACE, "workspace too small (conformer layer)");
+  const bool bf = (dtype == SMX_BF16);
   // x1 = x + 0.5*ffn1(x)                                                              :518
-  SMX_TRY(ffn_generic(&w->ffn1, w->act, rows, x, dtype, nullptr, nullptr, 0.f, x1, SMX_F32, ws, st));
-  // n1 = norm1(x1); x2 = cell(n1) + x1                                                :520-541
-  if (!ws.dry)
-    SMX_TRY(layernorm(x1, SMX_F32, D, w->norm1_w, w->norm1_b, 1e-5f, SMX_ACT_IDENTITY, n1, SMX_F32, D, rows, D, st));
-  if (w->cell.mode == SMX_MODE_LITE) {
-    if (w->cell.summary_out_dim != D) return fail(SMX_ERR_BAD_ARG, "conformer layer: lite summary_out_dim != d_model");
-    float* mean = ws.f32((size_t)B * D);
-    if (!mean) return fail(SMX_ERR_WORKSPACE, "workspace too small (conformer layer lite)");
-    SMX_TRY(cell_generic(&w->cell, B, T, n1, SMX_F32, mask, sum_mask, nullptr, 0, mean, SMX_F32, D, ws, st));
-    if (!ws.dry) SMX_TRY(add_bcast(x1, mean, rows, T, D, x2, st));
-  } else {
+  if (bf && w->ffn1.packed && tc_ffn_supported(&w->ffn1))
+    SMX_TRY(tc_ffn_fwd(&w->ffn1, w->ffn1.packed, w->act, rows, (const __nv_bfloat16*)x, nullptr, nullptr, 0.f, (__nv_bfloat16*)x1, ws, st));
+  else
+    SMX_TRY(ffn_generic(&w->ffn1, w->act, rows, x, dtype, nullptr, nullptr, 0.f, x1, idt, ws, st));
+  // x2 = cell(norm1(x1)) + x1                                                          :520-541
+  if (bf && w->cell.packed && tc_cell_supported(&w->cell, sum_mask != nullptr)) {
     if (w->cell.merge.out_dim != D) return fail(SMX_ERR_BAD_ARG, "conformer layer: cell output dim != d_model");
-    SMX_TRY(cell_generic(&w->cell, B, T, n1, SMX_F32, mask, sum_mask, x1, SMX_F32, x2, SMX_F32, D, ws, st));
+    SMX_TRY(tc_cell_fwd(&w->cell, w->cell.packed, B, T, (const __nv_bfloat16*)x1, w->norm1_w, w->norm1_b, mask,
+                        (const __nv_bfloat16*)x1, (__nv_bfloat16*)x2, ws, st));
+  } else {
+    const size_t m1 = ws.mark();
+    float* n1 = ws.f32((size_t)rows * D);
+    if (!n1) return fail(SMX_ERR_WORKSPACE, "workspace too small (conformer layer norm1)");
+    if (!ws.dry)
+      SMX_TRY(layernorm(x1, idt, D, w->norm1_w, w->norm1_b, 1e-5f, SMX_ACT_IDENTITY, n1, SMX_F32, D, rows, D, st));
+    if (w->cell.mode == SMX_MODE_LITE) {
+      if (w->cell.summary_out_dim != D) return fail(SMX_ERR_BAD_ARG, "conformer layer: lite summary_out_dim != d_model");
+      float* mean = ws.f32((size_t)B * D);
+      float* x1f = (idt == SMX_F32) ? (float*)x1 : ws.f32((size_t)rows * D);
+      float* x2f = (idt == SMX_F32) ? (float*)x2 : ws.f32((size_t)rows * D);
+      if (!mean || !x1f || !x2f) return fail(SMX_ERR_WORKSPACE, "workspace too small (conformer layer lite)");
+      SMX_TRY(cell_generic(&w->cell, B, T, n1, SMX_F32, mask, sum_mask, nullptr, 0, mean, SMX_F32, D, ws, st));
+      if (!ws.dry) {
+        if (idt != SMX_F32) SMX_TRY(convert(x1, idt, x1f, SMX_F32, rows * D, st));
+        SMX_TRY(add_bcast(x1f, mean, rows, T, D, x2f, st));
+        if (idt != SMX_F32) SMX_TRY(convert(x2f, SMX_F32, x2, idt, rows * D, st));
+      }
+    } else {
+      if (w->cell.merge.out_dim != D) return fail(SMX_ERR_BAD_ARG, "conformer layer: cell output dim != d_model");
+      SMX_TRY(cell_generic(&w->cell, B, T, n1, SMX_F32, mask, sum_mask, x1, idt, x2, idt, D, ws, st));
+    }
+    ws.release(m1);
   }
   // x3 = x2 + conv_module(x2)*mask   (into x1, which is dead)                           :543-545
-  SMX_TRY(convmod_generic(&w->conv, w->act, B, T, chunk, x2, SMX_F32, mask, x2, SMX_F32, x1, SMX_F32, ws, st));
+  if (bf && w->conv.packed && tc_convmod_supported(&w->conv, chunk))
+    SMX_TRY(tc_convmod_fwd(&w->conv, w->conv.packed, w->act, B, T, (const __nv_bfloat16*)x2, mask, (const __nv_bfloat16*)x2,
+                           (__nv_bfloat16*)x1, ws, st));
+  else
+    SMX_TRY(convmod_generic(&w->conv, w->act, B, T, chunk, x2, idt, mask, x2, idt, x1, idt, ws, st));
   // y = norm2(x3 + 0.5*ffn2(x3))                                                        :547
-  SMX_TRY(ffn_generic(&w->ffn2, w->act, rows, x1, SMX_F32, w->norm2_w, w->norm2_b, 1e-5f, y, dtype, ws, st));
+  if (bf && w->ffn2.packed && tc_ffn_supported(&w->ffn2))
+    SMX_TRY(tc_ffn_fwd(&w->ffn2, w->ffn2.packed, w->act, rows, (const __nv_bfloat16*)x1, w->norm2_w, w->norm2_b, 1e-5f, (__nv_bfloat16*)y, ws, st));
+  else
+    SMX_TRY(ffn_generic(&w->ffn2, w->act, rows, x1, idt, w->norm2_w, w->norm2_b, 1e-5f, y, dtype, ws, st));
   ws.release(m0);
   return SMX_OK;
 }

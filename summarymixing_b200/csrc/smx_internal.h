@@ -11,6 +11,7 @@ namespace smx {
 // ---- error plumbing ---------------------------------------------------------------------
 int fail(int code, const char* fmt, ...);
 void count_launch(int n = 1);
+void count_tc_launch(int n = 1);
 int check_launch(const char* what);  // cudaGetLastError -> SMX_ERR_CUDA
 
 #define SMX_TRY(expr)                \

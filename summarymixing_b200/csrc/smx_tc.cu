@@ -6,7 +6,6 @@
 
 namespace smx {
 
-size_t tc_cell_workspace_bytes(const smx_cell_weights*, int, int, int, int) { return 0; }
 
 static inline int round_up(int v, int a) { return (v + a - 1) / a * a; }
 

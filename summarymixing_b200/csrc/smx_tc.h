@@ -4,15 +4,67 @@
 
 namespace smx {
 
-// bytes of workspace the tcgen05 cell path needs for this problem, or 0 when it does not apply
-size_t tc_cell_workspace_bytes(const smx_cell_weights* w, int dtype, int B, int T, int has_sum_mask);
-
-// Pack an fp32 weight (element (n,k) at w[n*stride_n + k*stride_k]) into bf16 operand images:
-// layout 0: [n_tile][k_block] tiles of (NT rows x 64 cols) in the 128B-swizzled K-major layout
-// layout 1: [n_tile] tiles of (NT rows x Kpad cols) in the no-swizzle core-matrix layout
-// Rows >= N and cols >= K are zero.  Returns bytes written via *bytes.
+// ---- smx_tc.cu: packing for the self-test -------------------------------------------------------
 size_t tc_packed_bytes(int N, int K, int NT);
 int tc_pack_weight(const float* w, int64_t stride_n, int64_t stride_k, int N, int K, int NT, int layout,
                    __nv_bfloat16* out, cudaStream_t st);
+
+// ---- smx_tc_lin.cu: K-LIN, the row-tile linear kernel -------------------------------------------
+struct LinP {
+  const __nv_bfloat16* x; int64_t ldx;   // input rows (bf16)
+  int64_t rows;                          // number of rows (B*T)
+  int T;                                 // frames per utterance: row group for rowbias; tile alignment if utt_tiles
+  int utt_tiles;                         // 1: tiles are utterance-aligned (ceil(T/128) tiles per utterance)
+  int K, N;                              // GEMM dims
+  int head_in, head_out;                 // block-diagonal structure (0 = dense)
+  const __nv_bfloat16* wp;               // packed weight image (tc_pack_linear)
+  const float* ln_w; const float* ln_b; float ln_eps;   // prologue LayerNorm over K (NULL = none)
+  const float* bias;                     // [N]
+  const float* rowbias; int64_t rowbias_ld;             // [rows/T][N] added before the activation
+  int act;
+  const uint8_t* rowmask;                // [rows] multiplies the activated value
+  const __nv_bfloat16* resid; int64_t ldr; float alpha; // out = resid + alpha * v
+  const float* oln_w; const float* oln_b; float oln_eps; // LIN_OLN: LayerNorm over the output row
+  __nv_bfloat16* out; int64_t ldo;
+  float* colsum;                         // LIN_COLSUM: [tiles][N] masked column sums
+  // filled by tc_linear_launch
+  int NT, n_tiles, glu, stage_bytes, n_stages; uint32_t tmem_cols;
+};
+enum { TC_LIN_PLAIN = 0, TC_LIN_GLU = 1, TC_LIN_OLN = 2, TC_LIN_COLSUM = 3 };
+bool tc_linear_supported(int K, int N);
+size_t tc_linear_packed_bytes(int K, int N);
+int tc_pack_linear(const smx_linear& L, int k_offset, int K, int glu, void* out, cudaStream_t st);
+int tc_pick_nt(int N, int glu);
+int tc_linear_launch(LinP p, int mode, cudaStream_t st);
+
+// ---- smx_tc_path.cu: module forwards composed from tcgen05 kernels --------------------------------
+// Each *_supported() says whether the bf16 tensor-core arm handles the configuration; *_packed_bytes /
+// *_pack build the bf16 operand images once per weight set; *_ws sizes the workspace.
+bool tc_cell_supported(const smx_cell_weights* w, int has_sum_mask);
+size_t tc_cell_packed_bytes(const smx_cell_weights* w);
+int tc_cell_pack(const smx_cell_weights* w, void* packed, cudaStream_t st);
+size_t tc_cell_workspace_bytes(const smx_cell_weights* w, int B, int T);
+// x: rows to mix (bf16); pre_ln_*: LayerNorm applied to x first (norm1 of the encoder layer) or NULL
+int tc_cell_fwd(const smx_cell_weights* w, const void* packed, int B, int T, const __nv_bfloat16* x,
+                const float* pre_ln_w, const float* pre_ln_b, const uint8_t* mask, const __nv_bfloat16* residual,
+                __nv_bfloat16* y, Arena& ws, cudaStream_t st);
+
+bool tc_ffn_supported(const smx_ffn_weights* w);
+size_t tc_ffn_packed_bytes(const smx_ffn_weights* w);
+int tc_ffn_pack(const smx_ffn_weights* w, void* packed, cudaStream_t st);
+size_t tc_ffn_workspace_bytes(const smx_ffn_weights* w, int64_t rows);
+int tc_ffn_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t rows, const __nv_bfloat16* x,
+               const float* oln_w, const float* oln_b, float oln_eps, __nv_bfloat16* y, Arena& ws, cudaStream_t st);
+
+bool tc_convmod_supported(const smx_convmod_weights* w, int chunk);
+size_t tc_convmod_packed_bytes(const smx_convmod_weights* w);
+int tc_convmod_pack(const smx_convmod_weights* w, void* packed, cudaStream_t st);
+size_t tc_convmod_workspace_bytes(const smx_convmod_weights* w, int B, int T);
+int tc_convmod_fwd(const smx_convmod_weights* w, const void* packed, int act, int B, int T, const __nv_bfloat16* x,
+                   const uint8_t* mask, const __nv_bfloat16* residual, __nv_bfloat16* y, Arena& ws, cudaStream_t st);
+
+// depthwise conv (zero 'same' padding) + LayerNorm + activation over bf16 rows (smx_tc_path.cu)
+int tc_dwconv_ln_act(const __nv_bfloat16* g, const float* dw_w, const float* dw_b, const float* ln_w,
+                     const float* ln_b, int act, int B, int T, int D, int k, __nv_bfloat16* out, cudaStream_t st);
 
 }  // namespace smx

@@ -110,6 +110,21 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "r"(taddr)
       : "memory");
 }
+// warp-collective store of 32 fp32 columns per lane (inverse of tmem_ld32)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const float* v) {
+  const uint32_t* r = reinterpret_cast<const uint32_t*>(v);
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // ---- tcgen05.mma ----------------------------------------------------------------------------------
@@ -153,6 +168,76 @@ __device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint64_t* bar) {
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
                : "memory");
+}
+
+// named barrier among a subset of warps (id 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// ---- activations on the fast path -------------------------------------------------------------------
+__device__ __forceinline__ float tanh_approx(float x) {
+  float y;
+  asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// act codes mirror smx_act.  swish/sigmoid use one MUFU (tanh.approx, |rel err| ~ 2^-11, below the bf16
+// rounding the result receives); gelu(erf) keeps erff for parity with nn.GELU().
+__device__ __forceinline__ float act_swish(float x) { float h = 0.5f * x; return fmaf(h, tanh_approx(h), h); }
+__device__ __forceinline__ float act_sigmoid(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
+__device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+__device__ __forceinline__ float act_gelu_tanh(float x) {
+  float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+  float h = 0.5f * x;
+  return fmaf(h, tanh_approx(u), h);
+}
+// scalar form (cold paths only: the switch sits inside the caller's element loop)
+__device__ __forceinline__ float act_fast(int act, float x) {
+  switch (act) {
+    case 1: return act_swish(x);
+    case 2: return act_gelu_erf(x);
+    case 3: return fmaxf(x, 0.0f);
+    case 4: return x >= 0.0f ? x : 0.01f * x;
+    case 5: return tanh_approx(x);
+    case 6: return act_sigmoid(x);
+    case 7: return act_gelu_tanh(x);
+    default: return x;
+  }
+}
+// in-place activation of N values; the dispatch is OUTSIDE the element loops (one tight loop per case)
+template <int N>
+__device__ __forceinline__ void act_apply(int act, float* v) {
+  switch (act) {
+    case 1:
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = act_swish(v[i]);
+      break;
+    case 2:
+#pragma unroll 4
+      for (int i = 0; i < N; ++i) v[i] = act_gelu_erf(v[i]);
+      break;
+    case 3:
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = fmaxf(v[i], 0.0f);
+      break;
+    case 4:
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = v[i] >= 0.0f ? v[i] : 0.01f * v[i];
+      break;
+    case 5:
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = tanh_approx(v[i]);
+      break;
+    case 6:
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = act_sigmoid(v[i]);
+      break;
+    case 7:
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[i] = act_gelu_tanh(v[i]);
+      break;
+    default: break;
+  }
 }
 
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {

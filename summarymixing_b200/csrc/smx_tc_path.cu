@@ -1,0 +1,415 @@
+// tcgen05 arm of libsmx, part 3: the reference's module forwards composed from tensor-core kernels
+// (bf16 activations, fp32 accumulation).  Small per-utterance work (mean finalisation) and the
+// depthwise convolution run on CUDA cores.
+#include "smx_tc.h"
+#include "smx_tc_common.cuh"
+
+namespace smx {
+
+// =============================================================================================
+// SummaryMixing cell, mode "SummaryMixing", whole-utterance mean          summary_mixing.py:198-253
+// =============================================================================================
+static bool mlp_ok(const smx_linear* blk, int n, int in_dim) {
+  if (n < 1 || n > SMX_MAX_BLOCKS) return false;
+  int cur = in_dim;
+  for (int i = 0; i < n; ++i) {
+    const smx_linear& L = blk[i];
+    if (!L.w || !L.b || L.in_dim != cur) return false;
+    if (!tc_linear_supported(L.in_dim, L.out_dim)) return false;
+    if (L.n_split > 1) {
+      if (L.in_dim % L.n_split || L.out_dim % L.n_split) return false;
+      if ((L.in_dim / L.n_split) % 64 || (L.out_dim / L.n_split) % 16) return false;
+    }
+    cur = L.out_dim;
+  }
+  return true;
+}
+
+bool tc_cell_supported(const smx_cell_weights* w, int has_sum_mask) {
+  if (w->mode != SMX_MODE_FULL || has_sum_mask) return false;
+  if (!mlp_ok(w->local, w->n_local, w->enc_dim) || !mlp_ok(w->summary, w->n_summary, w->enc_dim)) return false;
+  const int Dl = w->local_out_dim, Ds = w->summary_out_dim;
+  if (w->local[w->n_local - 1].out_dim != Dl || w->summary[w->n_summary - 1].out_dim != Ds) return false;
+  if (w->merge.n_split > 1 || w->merge.in_dim != Dl + Ds || !w->merge.w || !w->merge.b) return false;
+  if (!tc_linear_supported(Dl, w->merge.out_dim)) return false;
+  if (Ds > 1024) return false;
+  if (w->use_layernorm && (!w->local_norm_w || !w->summary_norm_w)) return false;
+  return true;
+}
+
+struct CellLayout {
+  size_t local[SMX_MAX_BLOCKS], summary[SMX_MAX_BLOCKS], merge, total;
+};
+static CellLayout cell_layout(const smx_cell_weights* w) {
+  CellLayout l{};
+  size_t off = 0;
+  for (int i = 0; i < w->n_local; ++i) { l.local[i] = off; off += align_up(tc_linear_packed_bytes(w->local[i].in_dim, w->local[i].out_dim)); }
+  for (int i = 0; i < w->n_summary; ++i) { l.summary[i] = off; off += align_up(tc_linear_packed_bytes(w->summary[i].in_dim, w->summary[i].out_dim)); }
+  l.merge = off; off += align_up(tc_linear_packed_bytes(w->local_out_dim, w->merge.out_dim));
+  l.total = off;
+  return l;
+}
+size_t tc_cell_packed_bytes(const smx_cell_weights* w) { return tc_cell_supported(w, 0) ? cell_layout(w).total : 0; }
+
+int tc_cell_pack(const smx_cell_weights* w, void* packed, cudaStream_t st) {
+  if (!tc_cell_supported(w, 0)) return fail(SMX_ERR_UNSUPPORTED, "cell configuration not handled by the tensor-core arm");
+  const CellLayout l = cell_layout(w);
+  char* base = (char*)packed;
+  for (int i = 0; i < w->n_local; ++i) SMX_TRY(tc_pack_linear(w->local[i], 0, w->local[i].in_dim, 0, base + l.local[i], st));
+  for (int i = 0; i < w->n_summary; ++i) SMX_TRY(tc_pack_linear(w->summary[i], 0, w->summary[i].in_dim, 0, base + l.summary[i], st));
+  SMX_TRY(tc_pack_linear(w->merge, 0, w->local_out_dim, 0, base + l.merge, st));  // W_c[:, :D_l]
+  return SMX_OK;
+}
+
+// per-utterance finalisation: mean over time, LayerNorm, and the summary's share of the combiner
+//   c[b] = W_c[:, D_l:] @ LN_s( sum_t s[b,t] / sum_t mask[b,t] ) + b_c          summary_mixing.py:229-231,248-253
+__global__ void __launch_bounds__(256) cell_finalize_kernel(const float* __restrict__ colsum, int tiles_per_utt, int T,
+                                                            const uint8_t* __restrict__ mask, int Ds, int Dl, int Dout,
+                                                            const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                            const float* __restrict__ Wc, const float* __restrict__ bc,
+                                                            float* __restrict__ rowbias) {
+  __shared__ float mu[1024];
+  __shared__ float red[8];
+  __shared__ float stat[2];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  // number of valid frames (an integer-valued float, like torch.sum(mask) in the reference)
+  float cnt = 0.0f;
+  if (mask) {
+    for (int t = tid; t < T; t += 256) cnt += (float)mask[(size_t)b * T + t];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) red[warp] = cnt;
+    __syncthreads();
+    cnt = 0.0f;
+    for (int i = 0; i < 8; ++i) cnt += red[i];
+    __syncthreads();
+  } else {
+    cnt = (float)T;
+  }
+  for (int d = tid; d < Ds; d += 256) {
+    float s = 0.0f;
+    for (int i = 0; i < tiles_per_utt; ++i) s += colsum[((size_t)b * tiles_per_utt + i) * Ds + d];  // fixed order
+    mu[d] = s / cnt;
+  }
+  __syncthreads();
+  if (ln_w) {
+    float s = 0.0f;
+    for (int d = tid; d < Ds; d += 256) s += mu[d];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[warp] = s;
+    __syncthreads();
+    if (tid == 0) { float t = 0.0f; for (int i = 0; i < 8; ++i) t += red[i]; stat[0] = t / (float)Ds; }
+    __syncthreads();
+    const float mean = stat[0];
+    float q = 0.0f;
+    for (int d = tid; d < Ds; d += 256) { float e = mu[d] - mean; q += e * e; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    __syncthreads();
+    if (lane == 0) red[warp] = q;
+    __syncthreads();
+    if (tid == 0) { float t = 0.0f; for (int i = 0; i < 8; ++i) t += red[i]; stat[1] = rsqrtf(t / (float)Ds + 1e-5f); }
+    __syncthreads();
+    const float rstd = stat[1];
+    for (int d = tid; d < Ds; d += 256) mu[d] = (mu[d] - mean) * rstd * ln_w[d] + ln_b[d];
+    __syncthreads();
+  }
+  const int ldw = Dl + Ds;
+  for (int n = warp; n < Dout; n += 8) {  // one warp per output, lanes along k: coalesced weight rows
+    const float* wr = Wc + (size_t)n * ldw + Dl;
+    float acc = 0.0f;
+    for (int k = lane; k < Ds; k += 32) acc = fmaf(wr[k], mu[k], acc);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) rowbias[(size_t)b * Dout + n] = acc + bc[n];
+  }
+}
+
+struct CellWs {
+  __nv_bfloat16 *h, *L;
+  float *colsum, *rowbias;
+};
+static int cell_ws(const smx_cell_weights* w, int B, int T, Arena& ws, CellWs& o) {
+  const int64_t rows = (int64_t)B * T;
+  int maxh = 0;
+  for (int i = 0; i + 1 < w->n_local; ++i) maxh = w->local[i].out_dim > maxh ? w->local[i].out_dim : maxh;
+  for (int i = 0; i + 1 < w->n_summary; ++i) maxh = w->summary[i].out_dim > maxh ? w->summary[i].out_dim : maxh;
+  const int tpu = (T + 127) / 128;
+  // two hidden buffers (ping-pong through the MLP chain) + L
+  o.h = (__nv_bfloat16*)ws.take((size_t)rows * (maxh > 0 ? maxh : 1) * 2 * 2);
+  o.L = (__nv_bfloat16*)ws.take((size_t)rows * w->local_out_dim * 2);
+  o.colsum = ws.f32((size_t)B * tpu * w->summary_out_dim);
+  o.rowbias = ws.f32((size_t)B * w->merge.out_dim);
+  if (!o.h || !o.L || !o.colsum || !o.rowbias) return fail(SMX_ERR_WORKSPACE, "workspace too small (tc cell)");
+  return SMX_OK;
+}
+size_t tc_cell_workspace_bytes(const smx_cell_weights* w, int B, int T) {
+  if (!tc_cell_supported(w, 0)) return 0;
+  Arena a(nullptr, 0, true);
+  CellWs o;
+  cell_ws(w, B, T, a, o);
+  return a.peak;
+}
+
+static LinP lin_base(int B, int T) {
+  LinP p{};
+  p.rows = (int64_t)B * T;
+  p.T = T;
+  p.utt_tiles = 1;
+  p.alpha = 1.0f;
+  p.ln_eps = 1e-5f;
+  p.oln_eps = 1e-5f;
+  p.act = SMX_ACT_IDENTITY;
+  return p;
+}
+static void lin_weight(LinP& p, const smx_linear& L, const void* packed, int K) {
+  p.K = K; p.N = L.out_dim; p.wp = (const __nv_bfloat16*)packed; p.bias = L.b;
+  if (L.n_split > 1) { p.head_in = L.in_dim / L.n_split; p.head_out = L.out_dim / L.n_split; }
+  else { p.head_in = p.head_out = 0; }
+}
+
+int tc_cell_fwd(const smx_cell_weights* w, const void* packed, int B, int T, const __nv_bfloat16* x,
+                const float* pre_ln_w, const float* pre_ln_b, const uint8_t* mask, const __nv_bfloat16* residual,
+                __nv_bfloat16* y, Arena& ws, cudaStream_t st) {
+  const CellLayout l = cell_layout(w);
+  const char* pk = (const char*)packed;
+  const size_t m0 = ws.mark();
+  if (ws.dry) { ws.take(tc_cell_workspace_bytes(w, B, T)); ws.release(m0); return SMX_OK; }
+  CellWs o;
+  SMX_TRY(cell_ws(w, B, T, ws, o));
+  const int64_t rows = (int64_t)B * T;
+  int maxh = 1;
+  for (int i = 0; i + 1 < w->n_local; ++i) maxh = w->local[i].out_dim > maxh ? w->local[i].out_dim : maxh;
+  for (int i = 0; i + 1 < w->n_summary; ++i) maxh = w->summary[i].out_dim > maxh ? w->summary[i].out_dim : maxh;
+  __nv_bfloat16* hb[2] = {o.h, o.h + (size_t)rows * maxh};
+  const int Dl = w->local_out_dim, Ds = w->summary_out_dim, Dout = w->merge.out_dim;
+
+  // ---- s(): summary branch -> masked column sums per tile                               :221, 229-231
+  {
+    const __nv_bfloat16* cur = x; int64_t ld = w->enc_dim;
+    for (int i = 0; i < w->n_summary; ++i) {
+      const bool last = (i == w->n_summary - 1);
+      LinP p = lin_base(B, T);
+      p.x = cur; p.ldx = ld;
+      lin_weight(p, w->summary[i], pk + l.summary[i], w->summary[i].in_dim);
+      p.act = w->act;
+      if (i == 0) { p.ln_w = pre_ln_w; p.ln_b = pre_ln_b; }
+      if (last) {
+        p.rowmask = mask; p.colsum = o.colsum;
+        SMX_TRY(tc_linear_launch(p, TC_LIN_COLSUM, st));
+      } else {
+        p.out = hb[i & 1]; p.ldo = w->summary[i].out_dim;
+        SMX_TRY(tc_linear_launch(p, TC_LIN_PLAIN, st));
+        cur = p.out; ld = p.ldo;
+      }
+    }
+  }
+  // ---- mean, LN_s, summary share of the combiner                                        :229-233, 248-253
+  cell_finalize_kernel<<<B, 256, 0, st>>>(o.colsum, (T + 127) / 128, T, mask, Ds, Dl, Dout,
+                                          w->use_layernorm ? w->summary_norm_w : nullptr,
+                                          w->use_layernorm ? w->summary_norm_b : nullptr, w->merge.w, w->merge.b, o.rowbias);
+  count_launch();
+  SMX_TRY(check_launch("cell_finalize_kernel"));
+  // ---- f(): local branch -> mask -> LN_l                                                :215-218
+  {
+    const __nv_bfloat16* cur = x; int64_t ld = w->enc_dim;
+    for (int i = 0; i < w->n_local; ++i) {
+      const bool last = (i == w->n_local - 1);
+      LinP p = lin_base(B, T);
+      p.x = cur; p.ldx = ld;
+      lin_weight(p, w->local[i], pk + l.local[i], w->local[i].in_dim);
+      p.act = w->act;
+      if (i == 0) { p.ln_w = pre_ln_w; p.ln_b = pre_ln_b; }
+      if (last) {
+        p.rowmask = mask; p.out = o.L; p.ldo = Dl;
+        if (w->use_layernorm && Dl <= 256) {
+          p.oln_w = w->local_norm_w; p.oln_b = w->local_norm_b;
+          SMX_TRY(tc_linear_launch(p, TC_LIN_OLN, st));
+        } else {
+          SMX_TRY(tc_linear_launch(p, TC_LIN_PLAIN, st));
+          if (w->use_layernorm)
+            SMX_TRY(layernorm(o.L, SMX_BF16, Dl, w->local_norm_w, w->local_norm_b, 1e-5f, SMX_ACT_IDENTITY, o.L, SMX_BF16, Dl, rows, Dl, st));
+        }
+      } else {
+        p.out = hb[i & 1]; p.ldo = w->local[i].out_dim;
+        SMX_TRY(tc_linear_launch(p, TC_LIN_PLAIN, st));
+        cur = p.out; ld = p.ldo;
+      }
+    }
+  }
+  // ---- combiner: y = act(W_c[:, :D_l] @ local + c[b]) (+ residual)                         :251-253
+  {
+    LinP p = lin_base(B, T);
+    p.x = o.L; p.ldx = Dl;
+    lin_weight(p, w->merge, pk + l.merge, Dl);
+    p.bias = nullptr;  // b_c is inside c[b]
+    p.head_in = p.head_out = 0;
+    p.rowbias = o.rowbias; p.rowbias_ld = Dout;
+    p.act = w->act;
+    p.resid = residual; p.ldr = Dout;
+    p.out = y; p.ldo = Dout;
+    SMX_TRY(tc_linear_launch(p, TC_LIN_PLAIN, st));
+  }
+  ws.release(m0);
+  return SMX_OK;
+}
+
+// =============================================================================================
+// ConvolutionModule                                                         Conformer.py:322-338
+// =============================================================================================
+bool tc_convmod_supported(const smx_convmod_weights* w, int chunk) {
+  const int D = w->bottleneck.in_dim;
+  if (chunk > 0 || w->causal) return false;
+  if (w->bottleneck.out_dim != 2 * D || w->out.in_dim != D || w->out.out_dim != D) return false;
+  if (!tc_linear_supported(D, 2 * D) || !tc_linear_supported(D, D)) return false;
+  if (w->kernel_size < 1 || w->kernel_size > 63 || w->kernel_size % 2 == 0) return false;
+  if (!w->bottleneck.b || !w->out.b || !w->dw_w) return false;
+  return true;
+}
+size_t tc_convmod_packed_bytes(const smx_convmod_weights* w) {
+  if (!tc_convmod_supported(w, 0)) return 0;
+  const int D = w->bottleneck.in_dim;
+  return align_up(tc_linear_packed_bytes(D, 2 * D)) + align_up(tc_linear_packed_bytes(D, D));
+}
+int tc_convmod_pack(const smx_convmod_weights* w, void* packed, cudaStream_t st) {
+  if (!tc_convmod_supported(w, 0)) return fail(SMX_ERR_UNSUPPORTED, "conv module not handled by the tensor-core arm");
+  const int D = w->bottleneck.in_dim;
+  SMX_TRY(tc_pack_linear(w->bottleneck, 0, D, 1, packed, st));
+  SMX_TRY(tc_pack_linear(w->out, 0, D, 0, (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)), st));
+  return SMX_OK;
+}
+size_t tc_convmod_workspace_bytes(const smx_convmod_weights* w, int B, int T) {
+  const int D = w->bottleneck.in_dim;
+  return 2 * align_up((size_t)B * T * D * 2);
+}
+
+// depthwise conv over time (zero padding at utterance edges) + LayerNorm over channels + activation.
+// One warp per output frame; a lane owns 8 channels (two chunks when D > 256).
+constexpr int DW_FRAMES = 64;  // frames per block
+__global__ void __launch_bounds__(256) dwconv_ln_act_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ dw_w,
+                                                            const float* __restrict__ dw_b, const float* __restrict__ ln_w,
+                                                            const float* __restrict__ ln_b, int act, int T, int D, int k,
+                                                            __nv_bfloat16* __restrict__ out) {
+  extern __shared__ float wT[];  // [k][D] transposed taps
+  const int b = blockIdx.y, t0 = blockIdx.x * DW_FRAMES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < k * D; i += 256) {
+    int c = i / k, j = i % k;
+    wT[j * D + c] = dw_w[i];
+  }
+  __syncthreads();
+  const int pad = (k - 1) / 2;
+  const int nch = D / 8;  // 16-byte chunks per row
+  for (int f = warp; f < DW_FRAMES; f += 8) {
+    const int t = t0 + f;
+    if (t >= T) break;
+    float acc[2][8];
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int ck = lane + 32 * c;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) acc[c][e] = (ck < nch && dw_b) ? dw_b[ck * 8 + e] : 0.0f;
+    }
+    for (int j = 0; j < k; ++j) {
+      const int u = t + j - pad;
+      if (u < 0 || u >= T) continue;
+      const __nv_bfloat16* row = g + ((size_t)b * T + u) * D;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int ck = lane + 32 * c;
+        if (ck < nch) {
+          const uint4 raw = *reinterpret_cast<const uint4*>(row + ck * 8);
+          const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+          const float4 w0 = *reinterpret_cast<const float4*>(wT + j * D + ck * 8);
+          const float4 w1 = *reinterpret_cast<const float4*>(wT + j * D + ck * 8 + 4);
+          float2 f0 = __bfloat1622float2(h[0]), f1 = __bfloat1622float2(h[1]), f2 = __bfloat1622float2(h[2]), f3 = __bfloat1622float2(h[3]);
+          acc[c][0] = fmaf(w0.x, f0.x, acc[c][0]); acc[c][1] = fmaf(w0.y, f0.y, acc[c][1]);
+          acc[c][2] = fmaf(w0.z, f1.x, acc[c][2]); acc[c][3] = fmaf(w0.w, f1.y, acc[c][3]);
+          acc[c][4] = fmaf(w1.x, f2.x, acc[c][4]); acc[c][5] = fmaf(w1.y, f2.y, acc[c][5]);
+          acc[c][6] = fmaf(w1.z, f3.x, acc[c][6]); acc[c][7] = fmaf(w1.w, f3.y, acc[c][7]);
+        }
+      }
+    }
+    // LayerNorm over the D channels of this frame (the warp holds the whole row)
+    float s = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+      if (lane + 32 * c < nch) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) s += acc[c][e];
+      }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)D;
+    float q = 0.0f;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+      if (lane + 32 * c < nch) {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { float d = acc[c][e] - mean; q += d * d; }
+      }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q / (float)D + 1e-5f);
+#pragma unroll
+    for (int c = 0; c < 2; ++c) {
+      const int ck = lane + 32 * c;
+      if (ck < nch) {
+        float o[8];
+#pragma unroll
+        for (int e = 0; e < 8; ++e) o[e] = tc::act_fast(act, (acc[c][e] - mean) * rstd * ln_w[ck * 8 + e] + ln_b[ck * 8 + e]);
+        *reinterpret_cast<uint4*>(out + ((size_t)b * T + t) * D + ck * 8) =
+            make_uint4(tc::pack_bf16x2(o[0], o[1]), tc::pack_bf16x2(o[2], o[3]), tc::pack_bf16x2(o[4], o[5]), tc::pack_bf16x2(o[6], o[7]));
+      }
+    }
+  }
+}
+
+int tc_dwconv_ln_act(const __nv_bfloat16* g, const float* dw_w, const float* dw_b, const float* ln_w,
+                     const float* ln_b, int act, int B, int T, int D, int k, __nv_bfloat16* out, cudaStream_t st) {
+  if (D % 8 || D > 512) return fail(SMX_ERR_UNSUPPORTED, "dwconv: D=%d", D);
+  const size_t smem = (size_t)k * D * sizeof(float);
+  cudaError_t e = cudaFuncSetAttribute(dwconv_ln_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(dwconv): %s", cudaGetErrorString(e));
+  dim3 grid((T + DW_FRAMES - 1) / DW_FRAMES, B);
+  dwconv_ln_act_kernel<<<grid, 256, smem, st>>>(g, dw_w, dw_b, ln_w, ln_b, act, T, D, k, out);
+  count_launch();
+  return check_launch("dwconv_ln_act_kernel");
+}
+
+int tc_convmod_fwd(const smx_convmod_weights* w, const void* packed, int act, int B, int T, const __nv_bfloat16* x,
+                   const uint8_t* mask, const __nv_bfloat16* residual, __nv_bfloat16* y, Arena& ws, cudaStream_t st) {
+  const int D = w->bottleneck.in_dim;
+  const int64_t rows = (int64_t)B * T;
+  const size_t m0 = ws.mark();
+  if (ws.dry) { ws.take(tc_convmod_workspace_bytes(w, B, T)); ws.release(m0); return SMX_OK; }
+  __nv_bfloat16* g = (__nv_bfloat16*)ws.take((size_t)rows * D * 2);
+  __nv_bfloat16* c = (__nv_bfloat16*)ws.take((size_t)rows * D * 2);
+  if (!g || !c) return fail(SMX_ERR_WORKSPACE, "workspace too small (tc conv module)");
+  {  // LN -> pointwise conv (D -> 2D) -> GLU                                              :322-324
+    LinP p = lin_base(B, T);
+    p.utt_tiles = 0;
+    p.x = x; p.ldx = D;
+    lin_weight(p, w->bottleneck, packed, D);
+    p.ln_w = w->ln_w; p.ln_b = w->ln_b;
+    p.out = g; p.ldo = D;
+    SMX_TRY(tc_linear_launch(p, TC_LIN_GLU, st));
+  }
+  // depthwise conv -> LN -> act                                                           :325, :331-332
+  SMX_TRY(tc_dwconv_ln_act(g, w->dw_w, w->dw_b, w->after_ln_w, w->after_ln_b, act, B, T, D, w->kernel_size, c, st));
+  {  // Linear D -> D, * mask, + residual                                                  :332-338, :543
+    LinP p = lin_base(B, T);
+    p.utt_tiles = 0;
+    p.x = c; p.ldx = D;
+    lin_weight(p, w->out, (const char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)), D);
+    p.rowmask = mask;
+    p.resid = residual; p.ldr = D;
+    p.out = y; p.ldo = D;
+    SMX_TRY(tc_linear_launch(p, TC_LIN_PLAIN, st));
+  }
+  ws.release(m0);
+  return SMX_OK;
+}
+
+}  // namespace smx

@@ -91,6 +91,7 @@ class ConvolutionModule(nn.Module):
         H.fill_linear(cw.out, wv, device, self.after_conv[2].weight, self.after_conv[2].bias, D, D)
         cw.kernel_size = self.kernel_size
         cw.causal = int(self.causal)
+        H.pack_tc(wv, device, cw, L.lib().smx_convmod_packed_bytes, L.lib().smx_convmod_pack)
 
     def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, dynchunktrain_config=None):
         """x: (B,T,D); mask: (B,T,1) or (B,T) in the convention selected by ``masked_false_or_true``."""
@@ -194,6 +195,7 @@ class ConformerEncoderLayer(nn.Module):
         l1, l2 = pw.ffn[0], pw.ffn[3]
         H.fill_linear(fw.w1, wv, device, l1.weight, l1.bias, l1.in_features, l1.out_features)
         H.fill_linear(fw.w2, wv, device, l2.weight, l2.bias, l2.in_features, l2.out_features)
+        H.pack_tc(wv, device, fw, L.lib().smx_ffn_packed_bytes, L.lib().smx_ffn_pack)
 
     def fill(self, lw: L.ConformerLayerWeights, wv: H.WeightView, device) -> None:
         self._fill_ffn(lw.ffn1, self.ffn_module1, wv, device)

@@ -144,6 +144,7 @@ class SummaryMixing(nn.Module):
             cw.summary_norm_b = wv.ptr(self.summary_norm.bias, device)
         if self.mode == "SummaryMixing-expdecay":
             cw.decay_constant = float(self.decay_constant)
+        H.pack_tc(wv, device, cw, L.lib().smx_cell_packed_bytes, L.lib().smx_cell_pack)
 
     @property
     def out_dim(self) -> int:
