@@ -1,59 +1,371 @@
 """bench.py — encoder-forward frames/s of the SummaryMixing-Conformer hot path (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W [--impl reference]
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path (libsmx through the module surface)
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU (oracle port)
+    torchrun --nproc-per-node N bench.py --gpus N ...        # one rank per GPU; utterances sharded, no collective
 
-Placeholder of round 1, step 1: device-resident timing of the 12-layer D=256 encoder.  The full contract
-(roofline, cpu_baseline, e2e, clocks, reference arm) is filled in as the kernels land.
+Workload (BASELINE.json configs[1]): 12-layer SummaryMixing-Conformer encoder, d_model 256,
+d_ffn 1024, nhead 4, kernel 31, Swish, mode "SummaryMixing"; per GPU one padded batch of B=32 utterances x
+T=1000 frames x D=256 features (bf16), prefix padding masks with lengths in [500,1000].  A "step" is one
+encoder forward over one batch.  Frames are counted as B*T (padded frames are computed, like the reference).
+
+One JSON line on stdout (rank 0).  Keys follow the driver contract; see DESIGN.md "Measurement".
 """
+from __future__ import annotations
+
 import argparse
 import json
 import os
+import subprocess
 import sys
+import threading
 import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+B, T, D, FFN, HEADS, LAYERS, KSIZE = 32, 1000, 256, 1024, 4, 12, 31
+METRIC = "encoder-fwd frames/sec (B=32,T=1000,D=256)"
+N_ROTATE = 12  # distinct input batches cycled through the timed loop: 12 x 16.4 MB (+ outputs) > 126 MB of L2
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": float(d["hbm_gbs"]), "bf16_tflops": float(d["bf16_tflops"]),
+                "bf16_tflops_sustained": float(d.get("bf16_tflops_sustained", d["bf16_tflops"])), "source": "measured"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons sampled every 100 ms while the timed region runs."""
+
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.rows = []
+        self.proc = None
+        self.index = index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except OSError:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, reasons = [], 0.0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            f = [c.strip() for c in r.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx = max(mx, float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        if not sm:
+            return None
+        sm.sort()
+        # "under load": the upper half of the samples (the sampler also sees the idle edges of the region)
+        load = sm[len(sm) // 2:]
+        return {"sm_mhz": load[len(load) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------
+def make_inputs(seed: int, n: int):
+    """n seeded synthetic batches: x ~ N(0,1) (B,T,D) and prefix masks with lens in [500,1000], lens[0]=T."""
+    import torch
+
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n):
+        x = torch.randn(B, T, D, generator=g)
+        lens = torch.randint(500, T + 1, (B,), generator=g)
+        lens[0] = T
+        mask = torch.arange(T)[None] < lens[:, None]
+        out.append((x, mask))
+    return out
+
+
+def build_encoder(seed: int = 0):
+    import torch
+
+    import summarymixing_b200 as S
+
+    torch.manual_seed(seed)
+    return S.ConformerEncoder(LAYERS, D, FFN, HEADS, KSIZE, attention_type="SummaryMixing", local_proj_hid_dim=[D],
+                              local_proj_out_dim=D, summary_hid_dim=[D], mode="SummaryMixing").eval()
+
+
+def cpu_reference_throughput(state_dict, budget_s: float, steps: int, warmup: int):
+    """The reference's algorithm (oracle port, fp32 torch ops — what the reference's nn.Modules execute) on
+    the host cores: frames/s over `steps` forwards of a bounded sample of the workload (first Bs utterances)."""
+    import torch
+
+    from oracle import smx_oracle as O  # checker / CPU baseline only
+
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sd = {k: v.float().cpu() for k, v in state_dict.items()}
+    x, mask = make_inputs(0, 1)[0]
+
+    def run(bs):
+        with torch.no_grad():
+            t0 = time.perf_counter()
+            O.conformer_encoder(x[:bs], sd, LAYERS, act="swish", src_key_padding_mask=mask[:bs])
+            return time.perf_counter() - t0
+
+    run(1)  # page in
+    t2 = run(2)
+    per_utt = t2 / 2
+    n = max(1, steps + warmup)
+    bs = int(max(1, min(B, budget_s / n / max(per_utt, 1e-6))))
+    for _ in range(warmup):
+        run(bs)
+    times = [run(bs) for _ in range(steps)]
+    tot = sum(times)
+    return {"value": bs * T * steps / tot, "unit": "frames/s", "cores": cores, "kind": "port",
+            "sample": f"{steps} forwards of the first {bs} of {B} utterances (T={T}, all {LAYERS} layers, fp32, "
+                      f"{torch.get_num_threads()} torch threads); oracle/smx_oracle.py restates the reference modules",
+            "ms_per_step": 1e3 * tot / steps, "frames_per_step": bs * T}
+
+
+# ---------------------------------------------------------------------------------------------
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    enc = build_encoder()
+    r = cpu_reference_throughput(enc.state_dict(), budget_s=150.0, steps=args.steps, warmup=min(args.warmup, 2))
+    line = {"metric": METRIC, "value": r["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": "cfg2: 12-layer SummaryMixing-Conformer encoder forward, D=256 d_ffn=1024 h=4 k=31, "
+                                   "B=32 x T=1000 padded batch per GPU", "frames_per_step": r["frames_per_step"],
+                       "device": "host CPU"},
+            "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------
+def time_module_calls(enc, x, mask, iters: int):
+    """Per-module device time through the C ABI (CUDA events on the launching stream) for the roofline section."""
+    import ctypes as C
+
+    import torch
+
+    from summarymixing_b200 import _host as H
+    from summarymixing_b200 import _lib as L
+
+    lib = L.lib()
+    dev = x.device
+    lw = enc._wv.struct[0]  # layer 0 weights (filled by the warm-up forwards)
+    m8 = mask.to(torch.uint8).contiguous()
+    st = H.stream_ptr(dev)
+    rows = B * T
+    nb = max(lib.smx_conformer_layer_workspace_bytes(C.byref(lw), L.BF16, B, T, 0),
+             lib.smx_summary_mixing_workspace_bytes(C.byref(lw.cell), L.BF16, B, T, 0),
+             lib.smx_ffn_workspace_bytes(C.byref(lw.ffn1), L.BF16, rows),
+             lib.smx_conv_module_workspace_bytes(C.byref(lw.conv), L.BF16, B, T), 1 << 20)
+    ws = torch.empty(nb, dtype=torch.uint8, device=dev)
+    xs = [torch.randn(B, T, D, device=dev).to(torch.bfloat16) for _ in range(N_ROTATE)]
+    ys = [torch.empty_like(xs[0]) for _ in range(N_ROTATE)]
+
+    def cell(i):
+        L.check(lib.smx_summary_mixing_fwd(C.byref(lw.cell), L.BF16, B, T, xs[i].data_ptr(), m8.data_ptr(), None,
+                                           xs[i].data_ptr(), ys[i].data_ptr(), ws.data_ptr(), ws.numel(), st))
+
+    def ffn(i):
+        L.check(lib.smx_ffn_fwd(C.byref(lw.ffn1), lw.act, L.BF16, rows, xs[i].data_ptr(), None, None, 0.0,
+                                ys[i].data_ptr(), ws.data_ptr(), ws.numel(), st))
+
+    def conv(i):
+        L.check(lib.smx_conv_module_fwd(C.byref(lw.conv), lw.act, L.BF16, B, T, 0, xs[i].data_ptr(), m8.data_ptr(),
+                                        xs[i].data_ptr(), ys[i].data_ptr(), ws.data_ptr(), ws.numel(), st))
+
+    out = {}
+    for name, fn in (("cell", cell), ("ffn", ffn), ("conv", conv)):
+        for i in range(3):
+            fn(i)
+        torch.cuda.synchronize()
+        n0 = lib.smx_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(iters):
+            fn(i % N_ROTATE)
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = {"us": 1e3 * e0.elapsed_time(e1) / iters, "launches": int(lib.smx_launch_count() - n0) // iters}
+    return out
+
+
+def run_smx(args):
+    import torch
+    import torch.distributed as dist
+
+    from summarymixing_b200 import _lib as L
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device (the product path is CUDA only; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.lib()
+    pk = peaks()
+
+    enc = build_encoder().to(dev)
+    # utterances are sharded over ranks (weak scaling: every rank owns its own B=32 batch; no data-path collective)
+    host = make_inputs(1000 + rank, N_ROTATE)
+    xs = [x.to(torch.bfloat16).to(dev) for x, _ in host]
+    ms = [m.to(dev) for _, m in host]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    with torch.no_grad():
+        for i in range(max(args.warmup, 3)):
+            enc(xs[i % N_ROTATE], src_key_padding_mask=ms[i % N_ROTATE])
+        barrier()
+        sampler = ClockSampler(local) if rank == 0 else None
+        if sampler:
+            sampler.start()
+        n0, t0 = lib.smx_launch_count(), lib.smx_tc_launch_count()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(args.steps):
+            enc(xs[i % N_ROTATE], src_key_padding_mask=ms[i % N_ROTATE])
+        e1.record()
+        barrier()
+        launches, tc_launches = int(lib.smx_launch_count() - n0), int(lib.smx_tc_launch_count() - t0)
+        ms_total = e0.elapsed_time(e1)
+
+        # ---- e2e: same metric through the public module call with HOST buffers (pinned), copies inside the region
+        hx = [x.to(torch.bfloat16).pin_memory() for x, _ in host[:4]]
+        hm = [m.pin_memory() for _, m in host[:4]]
+        hy = [torch.empty(B, T, D, dtype=torch.bfloat16).pin_memory() for _ in range(4)]
+
+        def e2e_step(i):
+            xd = hx[i % 4].to(dev, non_blocking=True)
+            md = hm[i % 4].to(dev, non_blocking=True)
+            y = enc(xd, src_key_padding_mask=md)[0]
+            hy[i % 4].copy_(y, non_blocking=True)
+
+        for i in range(3):
+            e2e_step(i)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        for i in range(args.steps):
+            e2e_step(i)
+        f1.record()
+        barrier()
+        e2e_ms = f0.elapsed_time(f1)
+        clocks = sampler.stop() if sampler else None
+
+    t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_total, e2e_ms = float(t[0]), float(t[1])
+    ms_step = ms_total / args.steps
+    value = world * B * T / (ms_step / 1e3)
+    e2e_value = world * B * T / (e2e_ms / args.steps / 1e3)
+
+    line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": "cfg2: 12-layer SummaryMixing-Conformer encoder forward, D=256 d_ffn=1024 h=4 k=31, "
+                                   "B=32 x T=1000 padded batch per GPU", "frames_per_step": world * B * T,
+                       "parallelism": f"utterance-sharded x{world} (no collective)",
+                       "l2": f"inputs rotate over {N_ROTATE} distinct batches ({N_ROTATE * B * T * D * 2 / 1e6:.0f} MB "
+                             "of x > 126 MB L2) so no step finds its input in L2",
+                       "accumulate": "fp32", "io": "bf16"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * T * D * 2 + B * T,
+                    "d2h_bytes_per_step": B * T * D * 2, "ms_per_step": e2e_ms / args.steps,
+                    "api": "summarymixing_b200.ConformerEncoder.forward on pinned host tensors"},
+            "gpu_launches": launches, "tc_launches": tc_launches, "clocks": clocks}
+
+    if rank == 0:
+        with torch.no_grad():
+            mod = time_module_calls(enc, xs[0], ms[0], iters=max(args.steps, 10))
+        # K-SM, the kernel north_star names: algorithmic bytes = read x + write y (bf16) + 1 mask byte per frame
+        # (SURVEY.md 8d); FLOPs as executed (block-diagonal f/s projections, split combiner).
+        frames = B * T
+        hd = D // HEADS
+        bytes_cell = frames * ((D + D) * 2 + 1)
+        flops_cell = frames * (4 * 2 * HEADS * hd * hd + 2 * D * D)
+        us = mod["cell"]["us"]
+        line["roofline"] = {"kernel": f"smx_summary_mixing_fwd (SummaryMixing cell, {mod['cell']['launches']} launches)",
+                            "bound": "hbm", "achieved": bytes_cell / us / 1e3, "peak": pk["hbm_gbs"], "unit": "GB/s",
+                            "frac": bytes_cell / us / 1e3 / pk["hbm_gbs"], "traffic": None,
+                            "us_per_call": us, "peak_source": pk["source"] + " (burst copy)",
+                            "tensor_tflops": flops_cell / us / 1e6, "tensor_frac": flops_cell / us / 1e6 / pk["bf16_tflops"]}
+        flops_ffn = frames * 4 * D * FFN
+        flops_conv = frames * 2 * D * 3 * D
+        step_us = ms_step * 1e3
+        line["kernels"] = {
+            "cell": {"us": us, "launches": mod["cell"]["launches"], "share_of_step": LAYERS * us / step_us},
+            "ffn": {"us": mod["ffn"]["us"], "launches": mod["ffn"]["launches"],
+                    "share_of_step": 2 * LAYERS * mod["ffn"]["us"] / step_us, "bound": "tensor",
+                    "tflops": flops_ffn / mod["ffn"]["us"] / 1e6,
+                    "frac": flops_ffn / mod["ffn"]["us"] / 1e6 / pk["bf16_tflops_sustained"]},
+            "conv": {"us": mod["conv"]["us"], "launches": mod["conv"]["launches"],
+                     "share_of_step": LAYERS * mod["conv"]["us"] / step_us, "bound": "tensor",
+                     "tflops": flops_conv / mod["conv"]["us"] / 1e6,
+                     "frac": flops_conv / mod["conv"]["us"] / 1e6 / pk["bf16_tflops_sustained"]},
+        }
+        if world == 1 and not args.no_cpu:
+            r = cpu_reference_throughput(enc.state_dict(), budget_s=20.0, steps=2, warmup=1)
+            line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
 
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="smx")
-    ap.add_argument("--dtype", default="fp32")
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="smx", choices=["smx", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
     args = ap.parse_args()
-    import torch
-    import summarymixing_b200 as S
-    from summarymixing_b200 import _lib
-
-    dev = "cuda:0"
-    torch.manual_seed(0)
-    B, T, D = 32, 1000, 256
-    enc = S.ConformerEncoder(12, D, 1024, 4, 31, attention_type="SummaryMixing", local_proj_hid_dim=[D],
-                             local_proj_out_dim=D, summary_hid_dim=[D], mode="SummaryMixing").eval().to(dev)
-    g = torch.Generator().manual_seed(0)
-    dt = torch.bfloat16 if args.dtype == "bf16" else torch.float32
-    x = torch.randn(B, T, D, generator=g).to(dt).to(dev)
-    lens = torch.randint(500, 1001, (B,), generator=g)
-    lens[0] = T
-    mask = (torch.arange(T)[None] < lens[:, None]).to(dev)
-    with torch.no_grad():
-        for _ in range(args.warmup):
-            enc(x, src_key_padding_mask=mask)
-        torch.cuda.synchronize()
-        n0 = _lib.lib().smx_launch_count()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(args.steps):
-            enc(x, src_key_padding_mask=mask)
-        e1.record()
-        torch.cuda.synchronize()
-    ms = e0.elapsed_time(e1) / args.steps
-    print(json.dumps({"metric": "encoder-fwd frames/sec (B=32,T=1000,D=256)", "value": B * T / (ms / 1e3),
-                      "unit": "frames/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
-                      "higher_is_better": True, "dtype": args.dtype,
-                      "gpu_launches": int(_lib.lib().smx_launch_count() - n0)}))
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_smx(args)
 
 
 if __name__ == "__main__":
