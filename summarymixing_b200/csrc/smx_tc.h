@@ -34,6 +34,7 @@ enum { TC_LIN_PLAIN = 0, TC_LIN_GLU = 1, TC_LIN_OLN = 2, TC_LIN_COLSUM = 3 };
 bool tc_linear_supported(int K, int N);
 size_t tc_linear_packed_bytes(int K, int N);
 int tc_pack_linear(const smx_linear& L, int k_offset, int K, int glu, void* out, cudaStream_t st);
+int tc_pack_linear_nt(const smx_linear& L, int k_offset, int K, int NT, void* out, cudaStream_t st);  // explicit n-tile width
 int tc_pick_nt(int N, int glu);
 int tc_linear_launch(LinP p, int mode, cudaStream_t st);
 
@@ -48,6 +49,13 @@ size_t tc_cell_workspace_bytes(const smx_cell_weights* w, int B, int T);
 int tc_cell_fwd(const smx_cell_weights* w, const void* packed, int B, int T, const __nv_bfloat16* x,
                 const float* pre_ln_w, const float* pre_ln_b, const uint8_t* mask, const __nv_bfloat16* residual,
                 __nv_bfloat16* y, Arena& ws, cudaStream_t st);
+
+// ---- smx_tc_cell.cu: K-SM, the fused persistent cell (two passes) ---------------------------------
+bool tc_cellf_supported(const smx_cell_weights* w);
+size_t tc_cellf_workspace_bytes(const smx_cell_weights* w, int B, int T);
+int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_s2, const void* img_f1, const void* img_f2,
+                 const void* img_c, int B, int T, const __nv_bfloat16* x, const float* pre_ln_w, const float* pre_ln_b,
+                 const uint8_t* mask, const __nv_bfloat16* residual, __nv_bfloat16* y, Arena& ws, cudaStream_t st);
 
 bool tc_ffn_supported(const smx_ffn_weights* w);
 size_t tc_ffn_packed_bytes(const smx_ffn_weights* w);

@@ -1,0 +1,674 @@
+// tcgen05 arm of libsmx, part 5: K-SM, the fused SummaryMixing cell (mode "SummaryMixing", whole-utterance
+// mean)                                                                   summary_mixing.py:198-253
+//
+// Two persistent, warp-specialised passes over utterance-aligned 128-frame tiles (one CTA per SM):
+//
+//   pass A (summary):  X = LN1(x tile)  ->  S = act(act(X W_s1 + b) W_s2 + b) * mask  ->  column sums of the tile
+//                      the CTA that delivers the last tile of an utterance (one atomic per tile on a per-utterance
+//                      counter) finalises it: mean over valid frames, LN_s, c[b] = W_c[:, D_l:] mean + b_c
+//   pass B (local):    X = LN1(x tile)  ->  L = LN_l(act(act(X W_f1 + b) W_f2 + b) * mask)
+//                      ->  y = act(L W_c[:, :D_l]^T + c[b]) (+ residual)
+//
+// The frame tile is read from HBM once per pass (the second read hits L2) and only y is written: hidden
+// activations, S, L and the concatenation never exist in global memory.  Inside a CTA:
+//   warp 0      weight producer: 8 KB (64 x 64 bf16) weight blocks stream from the packed image (L2) through a
+//               shared-memory ring with cp.async.bulk + mbarrier; zero blocks of block-diagonal weights are skipped
+//   warp 1      MMA issuer: tcgen05.mma (M=128, N=64, K=16) into 64-column TMEM accumulator chunks
+//   warps 2-5   prologue: coalesced 16-byte loads of the next tile, LayerNorm (norm1), bf16 A operand (128B swizzle)
+//   warps 6-13  epilogue: two groups of four warps (one per TMEM lane quadrant) take alternate 64-column chunks:
+//               tcgen05.ld -> bias/activation/mask -> next GEMM's A operand in shared memory (or LN_l through
+//               TMEM, column sums, or the staged output tile which leaves with coalesced 16-byte stores)
+// so the tensor pipe, the TMA engine, the prologue loads and the epilogue math of neighbouring chunks/tiles overlap.
+#include "smx_tc.h"
+#include "smx_tc_common.cuh"
+
+namespace smx {
+
+using tc::kblock_bytes;
+
+constexpr int CF_THREADS = 448;      // 14 warps
+constexpr int CF_PRO_WARP0 = 2;      // warps 2..5
+constexpr int CF_EPI_WARP0 = 6;      // warps 6..13
+constexpr int CF_MAX_STAGES = 12;
+constexpr uint32_t CF_BLOCK_BYTES = 8192;  // one 64 x 64 bf16 weight block
+
+struct CfGemm {
+  const uint8_t* img;  // packed image: [chunk][kblock] blocks of 64 rows x 128 B (128B swizzle)
+  int nkb, nc;         // K/64, N/64
+  int head_in, head_out;  // block-diagonal structure (0 = dense)
+};
+
+struct CellFP {
+  const __nv_bfloat16* x; int64_t ldx;
+  const float* pre_w; const float* pre_b;   // norm1 (NULL: none)
+  const uint8_t* mask;                       // (B,T) or NULL
+  const __nv_bfloat16* resid; int64_t ldr;
+  __nv_bfloat16* y; int64_t ldy;
+  int B, T, tpu, n_tiles;
+  int D;                                     // enc_dim
+  CfGemm g[3];                               // A: s1, s2     B: f1, f2, combiner(local part)
+  const float* b1; const float* b2;          // biases of the two MLP blocks of this pass
+  const float* ln_w; const float* ln_b;      // A: summary_norm   B: local_norm      (NULL: no LayerNorm)
+  const float* Wc; const float* bc; int Dl, Ds, Dout;   // merge weight (fp32, (Dout, Dl+Ds)) and bias
+  int act;
+  float* colsum;        // [n_tiles][Ds]
+  float* rowbias;       // [B][Dout]
+  unsigned* counters;   // [B]
+  int n_stages;
+  uint32_t off_y, off_ring, off_par, off_red;   // shared-memory carve-up (bytes from the 1024-aligned base)
+};
+
+__device__ __forceinline__ bool cf_live(const CfGemm& g, int c, int kb) {
+  return g.head_in == 0 || (kb * 64) / g.head_in == (c * 64) / g.head_out;
+}
+__device__ __forceinline__ bool cf_first(const CfGemm& g, int kb) { return g.head_in == 0 ? kb == 0 : (kb * 64) % g.head_in == 0; }
+__device__ __forceinline__ bool cf_last(const CfGemm& g, int kb) {
+  return g.head_in == 0 ? kb == g.nkb - 1 : ((kb + 1) * 64) % g.head_in == 0;
+}
+
+__device__ __forceinline__ uint4 cf_pack8(const float* v) {
+  return make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]), tc::pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void cf_unpack8(const uint4& raw, float* v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+}
+
+// sum over the 32 lanes of v[j] for each j; lane l ends up holding column l's total
+__device__ __forceinline__ float cf_column_sums(float* v, int lane) {
+#pragma unroll
+  for (int s = 16; s >= 1; s >>= 1) {
+    const bool up = (lane & s) != 0;
+#pragma unroll
+    for (int j = 0; j < s; ++j) {
+      float send = up ? v[j] : v[j + s];
+      float keep = up ? v[j + s] : v[j];
+      v[j] = keep + __shfl_xor_sync(0xffffffffu, send, s);
+    }
+  }
+  return v[0];
+}
+
+// per-utterance finalisation by the 256 epilogue threads of the CTA that delivered the utterance's last tile:
+//   c[b] = W_c[:, D_l:] @ LN_s( sum_t s[b,t] / sum_t mask[b,t] ) + b_c           summary_mixing.py:229-231, 248-253
+__device__ void cf_finalize(const CellFP& p, int b, float* scr, int etid) {
+  float* mu = scr;          // [256]
+  float* red = scr + 256;   // [8]
+  float* stat = scr + 264;  // [2]
+  const int warp = etid >> 5, lane = etid & 31;
+  const int Ds = p.Ds;
+  float cnt;
+  if (p.mask) {  // number of valid frames (integer-valued float, like torch.sum(mask) in the reference)
+    float c = 0.0f;
+    for (int t = etid; t < p.T; t += 256) c += (float)p.mask[(size_t)b * p.T + t];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+    if (lane == 0) red[warp] = c;
+    tc::named_bar_sync(1, 256);
+    cnt = 0.0f;
+    for (int i = 0; i < 8; ++i) cnt += red[i];
+    tc::named_bar_sync(1, 256);
+  } else {
+    cnt = (float)p.T;
+  }
+  for (int d = etid; d < Ds; d += 256) {
+    float s = 0.0f;
+    for (int i = 0; i < p.tpu; ++i) s += __ldcg(p.colsum + ((size_t)b * p.tpu + i) * Ds + d);  // fixed order
+    mu[d] = s / cnt;
+  }
+  tc::named_bar_sync(1, 256);
+  if (p.ln_w) {
+    float s = 0.0f;
+    for (int d = etid; d < Ds; d += 256) s += mu[d];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) red[warp] = s;
+    tc::named_bar_sync(1, 256);
+    if (etid == 0) { float t = 0.0f; for (int i = 0; i < 8; ++i) t += red[i]; stat[0] = t / (float)Ds; }
+    tc::named_bar_sync(1, 256);
+    const float mean = stat[0];
+    float q = 0.0f;
+    for (int d = etid; d < Ds; d += 256) { float e = mu[d] - mean; q += e * e; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    if (lane == 0) red[warp] = q;
+    tc::named_bar_sync(1, 256);
+    if (etid == 0) { float t = 0.0f; for (int i = 0; i < 8; ++i) t += red[i]; stat[1] = rsqrtf(t / (float)Ds + 1e-5f); }
+    tc::named_bar_sync(1, 256);
+    const float rstd = stat[1];
+    for (int d = etid; d < Ds; d += 256) mu[d] = (mu[d] - mean) * rstd * p.ln_w[d] + p.ln_b[d];
+    tc::named_bar_sync(1, 256);
+  }
+  const int ldw = p.Dl + Ds;
+  for (int n = warp; n < p.Dout; n += 8) {  // one warp per output; lanes along k: coalesced weight rows
+    const float* wr = p.Wc + (size_t)n * ldw + p.Dl;
+    float acc = 0.0f;
+    for (int k = lane; k < Ds; k += 32) acc = fmaf(wr[k], mu[k], acc);
+#pragma unroll
+    for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) p.rowbias[(size_t)b * p.Dout + n] = acc + p.bc[n];
+  }
+  tc::named_bar_sync(1, 256);
+}
+
+template <int PHASE>  // 0: pass A (summary), 1: pass B (local + combiner)
+__global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  uint8_t* sX = smem;
+  uint8_t* sY = smem + p.off_y;
+  uint8_t* sRing = smem + p.off_ring;
+  float* sPar = reinterpret_cast<float*>(smem + p.off_par);   // [b1 | b2 | ln_w | ln_b], 256 floats each
+  float* sRed = reinterpret_cast<float*>(smem + p.off_red);   // 1024 floats: column partials / LN statistics / finalize
+  __shared__ __align__(8) uint64_t full_bar[CF_MAX_STAGES], empty_bar[CF_MAX_STAGES];
+  __shared__ __align__(8) uint64_t x_full, x_free, a2_full, epi_done;
+  __shared__ __align__(8) uint64_t acc1_full[4], a1_full[4], acc2_full[4], acc3_full[4];
+  __shared__ uint32_t tmem_base_s;
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  constexpr int NG = PHASE == 0 ? 2 : 3;
+
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 32) {
+    for (int s = 0; s < p.n_stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    tc::mbar_init(&x_full, 4); tc::mbar_init(&x_free, 1); tc::mbar_init(&a2_full, 8); tc::mbar_init(&epi_done, 8);
+    for (int c = 0; c < 4; ++c) {
+      tc::mbar_init(&acc1_full[c], 1); tc::mbar_init(&a1_full[c], 4);
+      tc::mbar_init(&acc2_full[c], 1); tc::mbar_init(&acc3_full[c], 1);
+    }
+    tc::fence_barrier_init();
+  }
+  for (int i = tid; i < 256; i += CF_THREADS) {
+    sPar[i] = i < p.g[0].nc * 64 ? p.b1[i] : 0.0f;
+    sPar[256 + i] = i < p.g[1].nc * 64 ? p.b2[i] : 0.0f;
+    sPar[512 + i] = (p.ln_w && i < p.g[1].nc * 64) ? p.ln_w[i] : 1.0f;
+    sPar[768 + i] = (p.ln_b && i < p.g[1].nc * 64) ? p.ln_b[i] : 0.0f;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = tmem_base_s;
+  const int first_tile = blockIdx.x, tile_step = gridDim.x;
+
+  if (warp == 0) {
+    // =============================== weight producer ===============================
+    if (lane == 0) {
+      int s = 0, ph = 0;
+      for (int tile = first_tile; tile < p.n_tiles; tile += tile_step) {
+        for (int gi = 0; gi < NG; ++gi) {
+          const CfGemm& g = p.g[gi];
+          for (int c = 0; c < g.nc; ++c)
+            for (int kb = 0; kb < g.nkb; ++kb) {
+              if (!cf_live(g, c, kb)) continue;
+              tc::mbar_wait(&empty_bar[s], ph ^ 1);
+              tc::mbar_arrive_expect_tx(&full_bar[s], CF_BLOCK_BYTES);
+              tc::bulk_g2s(sRing + (size_t)s * CF_BLOCK_BYTES, g.img + (size_t)(c * g.nkb + kb) * CF_BLOCK_BYTES, CF_BLOCK_BYTES,
+                           &full_bar[s]);
+              if (++s == p.n_stages) { s = 0; ph ^= 1; }
+            }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    if (lane == 0) {
+      int s = 0, ph = 0;
+      const uint32_t x0 = tc::smem_u32(sX), y0 = tc::smem_u32(sY), r0 = tc::smem_u32(sRing);
+      const uint32_t idesc = tc::make_idesc_bf16(128, 64);
+      int it = 0;
+      for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
+        const uint32_t par = it & 1;
+        for (int gi = 0; gi < NG; ++gi) {
+          const CfGemm& g = p.g[gi];
+          const uint32_t a0 = gi == 0 ? x0 : y0;
+          const uint32_t dcol = gi == 0 ? 0u : 256u;
+          if (gi == 0) {
+            tc::mbar_wait(&x_full, par);
+          } else if (gi == 1) {
+            if (it > 0) tc::mbar_wait(&epi_done, par ^ 1);  // previous tile's accumulators in [256,512) are drained
+          } else {
+            tc::mbar_wait(&a2_full, par);
+          }
+          tc::tc_fence_after();
+          uint32_t seen = 0;  // K-blocks of A1 already waited for (gi == 1)
+          for (int c = 0; c < g.nc; ++c)
+            for (int kb = 0; kb < g.nkb; ++kb) {
+              if (!cf_live(g, c, kb)) continue;
+              if (gi == 1 && !(seen & (1u << kb))) {
+                tc::mbar_wait(&a1_full[kb], par);
+                tc::tc_fence_after();
+                seen |= 1u << kb;
+              }
+              tc::mbar_wait(&full_bar[s], ph);
+              tc::tc_fence_after();
+              const uint32_t a_addr = a0 + kb * kblock_bytes(128);
+              const uint32_t b_addr = r0 + s * CF_BLOCK_BYTES;
+              const uint32_t d_addr = tmem + dcol + c * 64;
+              const bool first = cf_first(g, kb);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks)
+                tc::umma_bf16(d_addr, tc::make_desc_sw128(a_addr + ks * 32), tc::make_desc_sw128(b_addr + ks * 32), idesc,
+                              (first && ks == 0) ? 0u : 1u);
+              tc::umma_commit(&empty_bar[s]);
+              if (++s == p.n_stages) { s = 0; ph ^= 1; }
+              if (cf_last(g, kb)) tc::umma_commit(gi == 0 ? &acc1_full[c] : (gi == 1 ? &acc2_full[c] : &acc3_full[c]));
+            }
+          if (gi == 0) tc::umma_commit(&x_free);
+        }
+      }
+    }
+  } else if (warp < CF_EPI_WARP0) {
+    // =============================== prologue: x tile -> LN1 -> A operand ===============================
+    const int pw = warp - CF_PRO_WARP0;
+    const int nchunk = p.D / 8;  // 16-byte chunks per row (<= 32)
+    const bool has = lane < nchunk;
+    float gw[8], gb[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) {
+      gw[e] = (p.pre_w && has) ? p.pre_w[lane * 8 + e] : 1.0f;
+      gb[e] = (p.pre_b && has) ? p.pre_b[lane * 8 + e] : 0.0f;
+    }
+    const float invD = 1.0f / (float)p.D;
+    int it = 0;
+    for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
+      const int b = tile / p.tpu, t0 = (tile % p.tpu) * 128;
+      const int64_t row0 = (int64_t)b * p.T + t0;
+      const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
+      if (it > 0) tc::mbar_wait(&x_free, (it - 1) & 1);
+#pragma unroll 1
+      for (int r8 = 0; r8 < 32; r8 += 8) {
+        uint4 raw[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = pw * 32 + r8 + j;
+          raw[j] = make_uint4(0, 0, 0, 0);
+          if (has && r < nrows) raw[j] = *reinterpret_cast<const uint4*>(p.x + (row0 + r) * p.ldx + lane * 8);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int r = pw * 32 + r8 + j;
+          float v[8];
+          cf_unpack8(raw[j], v);
+          if (p.pre_w) {
+            float s = 0.0f;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s += v[e];
+#pragma unroll
+            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+            const float mean = s * invD;
+            float q = 0.0f;
+            if (has) {
+#pragma unroll
+              for (int e = 0; e < 8; ++e) { float d = v[e] - mean; q += d * d; }
+            }
+#pragma unroll
+            for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+            const float rstd = rsqrtf(q * invD + 1e-5f);
+            const bool live = r < nrows;
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = live ? (v[e] - mean) * rstd * gw[e] + gb[e] : 0.0f;
+          }
+          if (has) *reinterpret_cast<uint4*>(sX + (size_t)(lane >> 3) * kblock_bytes(128) + tc::sw128_offset(r, lane & 7)) = cf_pack8(v);
+        }
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&x_full);
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int e = warp - CF_EPI_WARP0;
+    const int grp = e >> 2;            // chunk parity this warp handles
+    const int q = warp & 3;            // TMEM lane quadrant this warp may access
+    const int r = q * 32 + lane;       // row inside the tile
+    const int etid = e * 32 + lane;    // 0..255
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const float* sB1 = sPar; const float* sB2 = sPar + 256; const float* sLw = sPar + 512; const float* sLb = sPar + 768;
+    const int nc1 = p.g[0].nc, nc2 = p.g[1].nc;
+    int it = 0;
+    for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
+      const uint32_t par = it & 1;
+      const int b = tile / p.tpu, t0 = (tile % p.tpu) * 128;
+      const int64_t row0 = (int64_t)b * p.T + t0;
+      const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
+      const bool live = r < nrows;
+      const float rscale = live ? (p.mask ? (float)p.mask[row0 + r] : 1.0f) : 0.0f;
+
+      // ---- E1: hidden = act(acc1 + b1) -> A operand of the second GEMM (K-block c of Y)
+      for (int c = grp; c < nc1; c += 2) {
+        tc::mbar_wait(&acc1_full[c], par);
+        tc::tc_fence_after();
+#pragma unroll
+        for (int pc = 0; pc < 2; ++pc) {
+          float v[32];
+          tc::tmem_ld32(tmem + lane_sel + c * 64 + pc * 32, v);
+          tc::tmem_ld_wait();
+          const float4* bp = reinterpret_cast<const float4*>(sB1 + c * 64 + pc * 32);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float4 bb = bp[j]; v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w; }
+          tc::act_apply<32>(p.act, v);
+#pragma unroll
+          for (int k = 0; k < 4; ++k)
+            *reinterpret_cast<uint4*>(sY + (size_t)c * kblock_bytes(128) + tc::sw128_offset(r, pc * 4 + k)) = cf_pack8(v + 8 * k);
+        }
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&a1_full[c]);
+      }
+
+      if (PHASE == 0) {
+        // ---- E2': S = act(acc2 + b2) * mask -> column sums of this tile                      :221, 229-231
+        for (int c = grp; c < nc2; c += 2) {
+          tc::mbar_wait(&acc2_full[c], par);
+          tc::tc_fence_after();
+#pragma unroll
+          for (int pc = 0; pc < 2; ++pc) {
+            float v[32];
+            tc::tmem_ld32(tmem + lane_sel + 256 + c * 64 + pc * 32, v);
+            tc::tmem_ld_wait();
+            const float4* bp = reinterpret_cast<const float4*>(sB2 + c * 64 + pc * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { const float4 bb = bp[j]; v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w; }
+            tc::act_apply<32>(p.act, v);
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= rscale;
+            const float tot = cf_column_sums(v, lane);
+            sRed[q * 256 + c * 64 + pc * 32 + lane] = tot;
+          }
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&epi_done);
+        tc::named_bar_sync(1, 256);
+        if (etid < p.Ds)  // fixed-order reduction over the four row quadrants: deterministic
+          p.colsum[(size_t)tile * p.Ds + etid] = (sRed[etid] + sRed[256 + etid]) + (sRed[512 + etid] + sRed[768 + etid]);
+        __threadfence();
+        tc::named_bar_sync(1, 256);
+        if (etid == 0) {
+          const unsigned old = atomicAdd(p.counters + b, 1u);  // the one cross-CTA atomic of this tile
+          s_last = (old == (unsigned)(p.tpu - 1));
+          __threadfence();
+        }
+        tc::named_bar_sync(1, 256);
+        if (s_last) cf_finalize(p, b, sRed, etid);
+        tc::named_bar_sync(1, 256);
+      } else {
+        // ---- E2: L = LN_l(act(acc2 + b2) * mask) -> A operand of the combiner (Y, in place)     :215-218
+        const int Dl = nc2 * 64;
+        if (p.ln_w) {
+          float s1 = 0.0f;
+          for (int c = grp; c < nc2; c += 2) {
+            tc::mbar_wait(&acc2_full[c], par);
+            tc::tc_fence_after();
+#pragma unroll
+            for (int pc = 0; pc < 2; ++pc) {
+              float v[32];
+              const uint32_t ta = tmem + lane_sel + 256 + c * 64 + pc * 32;
+              tc::tmem_ld32(ta, v);
+              tc::tmem_ld_wait();
+              const float4* bp = reinterpret_cast<const float4*>(sB2 + c * 64 + pc * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { const float4 bb = bp[j]; v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w; }
+              tc::act_apply<32>(p.act, v);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { v[j] *= rscale; s1 += v[j]; }
+              tc::tmem_st32(ta, v);  // park the fp32 values in TMEM for the two LayerNorm passes
+            }
+          }
+          tc::tmem_st_wait();
+          sRed[grp * 128 + r] = s1;
+          tc::named_bar_sync(1, 256);
+          const float mean = (sRed[r] + sRed[128 + r]) / (float)Dl;
+          float s2 = 0.0f;
+          for (int c = grp; c < nc2; c += 2) {
+#pragma unroll
+            for (int pc = 0; pc < 2; ++pc) {
+              float v[32];
+              tc::tmem_ld32(tmem + lane_sel + 256 + c * 64 + pc * 32, v);
+              tc::tmem_ld_wait();
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { const float d = v[j] - mean; s2 = fmaf(d, d, s2); }
+            }
+          }
+          sRed[256 + grp * 128 + r] = s2;
+          tc::named_bar_sync(1, 256);
+          const float rstd = rsqrtf((sRed[256 + r] + sRed[384 + r]) / (float)Dl + 1e-5f);
+          for (int c = grp; c < nc2; c += 2) {
+#pragma unroll
+            for (int pc = 0; pc < 2; ++pc) {
+              float v[32];
+              tc::tmem_ld32(tmem + lane_sel + 256 + c * 64 + pc * 32, v);
+              tc::tmem_ld_wait();
+              const float4* wp = reinterpret_cast<const float4*>(sLw + c * 64 + pc * 32);
+              const float4* bp = reinterpret_cast<const float4*>(sLb + c * 64 + pc * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) {
+                const float4 ww = wp[j], bb = bp[j];
+                v[4 * j] = (v[4 * j] - mean) * rstd * ww.x + bb.x;
+                v[4 * j + 1] = (v[4 * j + 1] - mean) * rstd * ww.y + bb.y;
+                v[4 * j + 2] = (v[4 * j + 2] - mean) * rstd * ww.z + bb.z;
+                v[4 * j + 3] = (v[4 * j + 3] - mean) * rstd * ww.w + bb.w;
+              }
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                *reinterpret_cast<uint4*>(sY + (size_t)c * kblock_bytes(128) + tc::sw128_offset(r, pc * 4 + k)) = cf_pack8(v + 8 * k);
+            }
+          }
+        } else {
+          for (int c = grp; c < nc2; c += 2) {
+            tc::mbar_wait(&acc2_full[c], par);
+            tc::tc_fence_after();
+          }
+          // without LayerNorm the values go straight to Y; all G2 chunks must have finished reading Y first
+          tc::named_bar_sync(1, 256);
+          for (int c = grp; c < nc2; c += 2) {
+#pragma unroll
+            for (int pc = 0; pc < 2; ++pc) {
+              float v[32];
+              tc::tmem_ld32(tmem + lane_sel + 256 + c * 64 + pc * 32, v);
+              tc::tmem_ld_wait();
+              const float4* bp = reinterpret_cast<const float4*>(sB2 + c * 64 + pc * 32);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) { const float4 bb = bp[j]; v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w; }
+              tc::act_apply<32>(p.act, v);
+#pragma unroll
+              for (int j = 0; j < 32; ++j) v[j] *= rscale;
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                *reinterpret_cast<uint4*>(sY + (size_t)c * kblock_bytes(128) + tc::sw128_offset(r, pc * 4 + k)) = cf_pack8(v + 8 * k);
+            }
+          }
+        }
+        tc::fence_proxy_async();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&a2_full);
+
+        // ---- E3: y = act(acc3 + c[b]) (+ residual) -> staged tile -> coalesced stores            :251-253, :541
+        const int nc3 = p.g[2].nc;
+        tc::mbar_wait(&acc3_full[nc3 - 1], par);  // commits complete in order: every combiner chunk is done, Y is free
+        tc::tc_fence_after();
+        const float* rb = p.rowbias + (size_t)b * p.Dout;
+        for (int c = grp; c < nc3; c += 2) {
+#pragma unroll
+          for (int pc = 0; pc < 2; ++pc) {
+            const int col = c * 64 + pc * 32;
+            float v[32];
+            tc::tmem_ld32(tmem + lane_sel + 256 + col, v);
+            tc::tmem_ld_wait();
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 bb = __ldcg(reinterpret_cast<const float4*>(rb + col) + j);
+              v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
+            }
+            tc::act_apply<32>(p.act, v);
+            if (p.resid && live) {
+              const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (row0 + r) * p.ldr + col);
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                float f[8];
+                cf_unpack8(rp[k], f);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) v[8 * k + j] += f[j];
+              }
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              *reinterpret_cast<uint4*>(sY + (size_t)c * kblock_bytes(128) + tc::sw128_offset(r, pc * 4 + k)) = cf_pack8(v + 8 * k);
+          }
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&epi_done);
+        tc::named_bar_sync(1, 256);
+        const int cpr = p.Dout / 8;
+        for (int idx = etid; idx < nrows * cpr; idx += 256) {
+          const int rr = idx / cpr, ch = idx - rr * cpr;
+          const uint4 val = *reinterpret_cast<const uint4*>(sY + (size_t)(ch >> 3) * kblock_bytes(128) + tc::sw128_offset(rr, ch & 7));
+          *reinterpret_cast<uint4*>(p.y + (row0 + rr) * p.ldy + ch * 8) = val;
+        }
+        tc::named_bar_sync(1, 256);
+      }
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+static bool dim_ok(int d) { return d >= 64 && d <= 256 && d % 64 == 0; }
+
+bool tc_cellf_supported(const smx_cell_weights* w) {
+  if (w->mode != SMX_MODE_FULL || w->n_local != 2 || w->n_summary != 2) return false;
+  const int D = w->enc_dim;
+  if (!dim_ok(D)) return false;
+  for (int i = 0; i < 2; ++i) {
+    const smx_linear* L[2] = {&w->local[i], &w->summary[i]};
+    for (const smx_linear* l : L) {
+      if (!l->w || !l->b || !dim_ok(l->in_dim) || !dim_ok(l->out_dim)) return false;
+      if (l->n_split > 1 && (l->in_dim % l->n_split || l->out_dim % l->n_split)) return false;
+    }
+  }
+  if (w->local[0].in_dim != D || w->summary[0].in_dim != D) return false;
+  if (w->local[1].in_dim != w->local[0].out_dim || w->summary[1].in_dim != w->summary[0].out_dim) return false;
+  if (w->local[1].out_dim != w->local_out_dim || w->summary[1].out_dim != w->summary_out_dim) return false;
+  if (w->merge.n_split > 1 || !w->merge.w || !w->merge.b) return false;
+  if (w->merge.in_dim != w->local_out_dim + w->summary_out_dim || !dim_ok(w->merge.out_dim)) return false;
+  if (w->use_layernorm && (!w->local_norm_w || !w->local_norm_b || !w->summary_norm_w || !w->summary_norm_b)) return false;
+  return true;
+}
+
+// block-diagonal structure the kernel can skip zero blocks for; anything else is packed (with its zeros) as dense
+static void head_dims(const smx_linear& L, int& hin, int& hout) {
+  hin = hout = 0;
+  if (L.n_split > 1) {
+    const int a = L.in_dim / L.n_split, b = L.out_dim / L.n_split;
+    if (a % 64 == 0 && b % 64 == 0) { hin = a; hout = b; }
+  }
+}
+
+static CfGemm make_gemm(const smx_linear& L, const void* img, int K) {
+  CfGemm g{};
+  g.img = (const uint8_t*)img;
+  g.nkb = K / 64;
+  g.nc = L.out_dim / 64;
+  head_dims(L, g.head_in, g.head_out);
+  return g;
+}
+
+size_t tc_cellf_workspace_bytes(const smx_cell_weights* w, int B, int T) {
+  const int tpu = (T + 127) / 128;
+  return align_up((size_t)B * tpu * w->summary_out_dim * 4) + align_up((size_t)B * w->merge.out_dim * 4) + align_up((size_t)B * 4);
+}
+
+static int g_num_sms = 0;
+static int num_sms() {
+  if (g_num_sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&g_num_sms, cudaDevAttrMultiProcessorCount, dev);
+    if (g_num_sms <= 0) g_num_sms = 148;
+  }
+  return g_num_sms;
+}
+
+// images: [s1][s2][f1][f2][merge local part], each N*K*2 bytes in 64x64 blocks (NT = 64)
+int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_s2, const void* img_f1, const void* img_f2,
+                 const void* img_c, int B, int T, const __nv_bfloat16* x, const float* pre_ln_w, const float* pre_ln_b,
+                 const uint8_t* mask, const __nv_bfloat16* residual, __nv_bfloat16* y, Arena& ws, cudaStream_t st) {
+  const int tpu = (T + 127) / 128;
+  const int Ds = w->summary_out_dim, Dl = w->local_out_dim, Dout = w->merge.out_dim, D = w->enc_dim;
+  const size_t m0 = ws.mark();
+  float* colsum = ws.f32((size_t)B * tpu * Ds);
+  float* rowbias = ws.f32((size_t)B * Dout);
+  unsigned* counters = (unsigned*)ws.take((size_t)B * 4);
+  if (!colsum || !rowbias || !counters) return fail(SMX_ERR_WORKSPACE, "workspace too small (fused cell)");
+  cudaError_t e = cudaMemsetAsync(counters, 0, (size_t)B * 4, st);
+  if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+
+  CellFP p{};
+  p.x = x; p.ldx = D; p.pre_w = pre_ln_w; p.pre_b = pre_ln_b; p.mask = mask;
+  p.resid = residual; p.ldr = Dout; p.y = y; p.ldy = Dout;
+  p.B = B; p.T = T; p.tpu = tpu; p.n_tiles = B * tpu; p.D = D;
+  p.Wc = w->merge.w; p.bc = w->merge.b; p.Dl = Dl; p.Ds = Ds; p.Dout = Dout;
+  p.act = w->act; p.colsum = colsum; p.rowbias = rowbias; p.counters = counters;
+
+  auto carve = [&](int ycols) {
+    const uint32_t xb = (uint32_t)(D / 64) * kblock_bytes(128), yb = (uint32_t)(ycols / 64) * kblock_bytes(128);
+    p.off_y = xb;
+    p.off_ring = xb + yb;
+    const size_t fixed = (size_t)xb + yb + 4096 /*params*/ + 4096 /*reductions*/ + 1024 /*align*/ + 1024 /*static*/;
+    int stages = (int)((227 * 1024 - fixed) / CF_BLOCK_BYTES);
+    if (stages > CF_MAX_STAGES) stages = CF_MAX_STAGES;
+    p.n_stages = stages;
+    p.off_par = p.off_ring + stages * CF_BLOCK_BYTES;
+    p.off_red = p.off_par + 4096;
+    return (size_t)p.off_red + 4096 + 1024;
+  };
+  const unsigned grid = (unsigned)(p.n_tiles < num_sms() ? p.n_tiles : num_sms());
+
+  {  // pass A
+    p.g[0] = make_gemm(w->summary[0], img_s1, D);
+    p.g[1] = make_gemm(w->summary[1], img_s2, w->summary[0].out_dim);
+    p.b1 = w->summary[0].b; p.b2 = w->summary[1].b;
+    p.ln_w = w->use_layernorm ? w->summary_norm_w : nullptr;
+    p.ln_b = w->use_layernorm ? w->summary_norm_b : nullptr;
+    const size_t smem = carve(w->summary[0].out_dim);
+    if (p.n_stages < 2) return fail(SMX_ERR_UNSUPPORTED, "fused cell: tile does not fit shared memory");
+    e = cudaFuncSetAttribute(cell_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(cell_kernel<0>): %s", cudaGetErrorString(e));
+    cell_kernel<0><<<grid, CF_THREADS, smem, st>>>(p);
+    count_tc_launch();
+    SMX_TRY(check_launch("cell_kernel<0>"));
+  }
+  {  // pass B
+    p.g[0] = make_gemm(w->local[0], img_f1, D);
+    p.g[1] = make_gemm(w->local[1], img_f2, w->local[0].out_dim);
+    smx_linear mg = w->merge;
+    mg.n_split = 1;
+    p.g[2] = make_gemm(mg, img_c, Dl);
+    p.b1 = w->local[0].b; p.b2 = w->local[1].b;
+    p.ln_w = w->use_layernorm ? w->local_norm_w : nullptr;
+    p.ln_b = w->use_layernorm ? w->local_norm_b : nullptr;
+    int ycols = w->local[0].out_dim;
+    if (Dl > ycols) ycols = Dl;
+    if (Dout > ycols) ycols = Dout;
+    const size_t smem = carve(ycols);
+    if (p.n_stages < 2) return fail(SMX_ERR_UNSUPPORTED, "fused cell: tile does not fit shared memory");
+    e = cudaFuncSetAttribute(cell_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(cell_kernel<1>): %s", cudaGetErrorString(e));
+    cell_kernel<1><<<grid, CF_THREADS, smem, st>>>(p);
+    count_tc_launch();
+    SMX_TRY(check_launch("cell_kernel<1>"));
+  }
+  ws.release(m0);
+  return SMX_OK;
+}
+
+}  // namespace smx

@@ -213,7 +213,7 @@ __device__ __forceinline__ void act_apply(int act, float* v) {
       for (int i = 0; i < N; ++i) v[i] = act_swish(v[i]);
       break;
     case 2:
-#pragma unroll 4
+#pragma unroll
       for (int i = 0; i < N; ++i) v[i] = act_gelu_erf(v[i]);
       break;
     case 3:

@@ -416,6 +416,16 @@ int tc_pack_linear(const smx_linear& L, int k_offset, int K, int glu, void* out,
   return check_launch("pack_linear_kernel");
 }
 
+int tc_pack_linear_nt(const smx_linear& L, int k_offset, int K, int NT, void* out, cudaStream_t st) {
+  const int N = L.out_dim;
+  if (K % 64 || N % NT || NT % 8) return fail(SMX_ERR_UNSUPPORTED, "tc pack: K=%d N=%d NT=%d not supported", K, N, NT);
+  int64_t n = (int64_t)N * (K / 8);
+  pack_linear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L.w, L.in_dim, L.out_dim, L.n_split, k_offset, K, N, NT,
+                                                                  (__nv_bfloat16*)out);
+  count_launch();
+  return check_launch("pack_linear_kernel");
+}
+
 int tc_linear_launch(LinP p, int mode, cudaStream_t st) {
   if (!tc_linear_supported(p.K, p.N)) return fail(SMX_ERR_UNSUPPORTED, "tc linear: K=%d N=%d not supported", p.K, p.N);
   p.NT = tc_pick_nt(p.N, mode == LIN_GLU);

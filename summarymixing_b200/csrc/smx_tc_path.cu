@@ -55,6 +55,11 @@ int tc_cell_pack(const smx_cell_weights* w, void* packed, cudaStream_t st) {
   if (!tc_cell_supported(w, 0)) return fail(SMX_ERR_UNSUPPORTED, "cell configuration not handled by the tensor-core arm");
   const CellLayout l = cell_layout(w);
   char* base = (char*)packed;
+  if (tc_cellf_supported(w)) {  // fused persistent cell: 64 x 64 weight blocks
+    for (int i = 0; i < 2; ++i) SMX_TRY(tc_pack_linear_nt(w->local[i], 0, w->local[i].in_dim, 64, base + l.local[i], st));
+    for (int i = 0; i < 2; ++i) SMX_TRY(tc_pack_linear_nt(w->summary[i], 0, w->summary[i].in_dim, 64, base + l.summary[i], st));
+    return tc_pack_linear_nt(w->merge, 0, w->local_out_dim, 64, base + l.merge, st);
+  }
   for (int i = 0; i < w->n_local; ++i) SMX_TRY(tc_pack_linear(w->local[i], 0, w->local[i].in_dim, 0, base + l.local[i], st));
   for (int i = 0; i < w->n_summary; ++i) SMX_TRY(tc_pack_linear(w->summary[i], 0, w->summary[i].in_dim, 0, base + l.summary[i], st));
   SMX_TRY(tc_pack_linear(w->merge, 0, w->local_out_dim, 0, base + l.merge, st));  // W_c[:, :D_l]
@@ -146,6 +151,7 @@ static int cell_ws(const smx_cell_weights* w, int B, int T, Arena& ws, CellWs& o
 }
 size_t tc_cell_workspace_bytes(const smx_cell_weights* w, int B, int T) {
   if (!tc_cell_supported(w, 0)) return 0;
+  if (tc_cellf_supported(w)) return tc_cellf_workspace_bytes(w, B, T);
   Arena a(nullptr, 0, true);
   CellWs o;
   cell_ws(w, B, T, a, o);
@@ -176,6 +182,9 @@ int tc_cell_fwd(const smx_cell_weights* w, const void* packed, int B, int T, con
   const char* pk = (const char*)packed;
   const size_t m0 = ws.mark();
   if (ws.dry) { ws.take(tc_cell_workspace_bytes(w, B, T)); ws.release(m0); return SMX_OK; }
+  if (tc_cellf_supported(w))
+    return tc_cellf_fwd(w, pk + l.summary[0], pk + l.summary[1], pk + l.local[0], pk + l.local[1], pk + l.merge, B, T, x,
+                        pre_ln_w, pre_ln_b, mask, residual, y, ws, st);
   CellWs o;
   SMX_TRY(cell_ws(w, B, T, ws, o));
   const int64_t rows = (int64_t)B * T;
