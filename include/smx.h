@@ -283,6 +283,10 @@ SMX_API int smx_chunk_mask(int32_t T, int32_t chunk_size, int32_t left_context_c
 SMX_API int smx_debug_tc_gemm(int layout, int32_t M, int32_t N, int32_t K, const void* a_bf16, const float* w_f32,
                               float* c_f32, void* workspace, size_t workspace_bytes, void* stream);
 
+/* Timeline of CTA 0 of the fused persistent kernels: device buffer of >= 1024 uint64 (zeroed by the caller)
+ * receiving clock64() stamps per warp role / tile / event; NULL switches tracing off.  Diagnostics only. */
+SMX_API int smx_debug_set_trace(void* device_u64_buffer);
+
 #ifdef __cplusplus
 }
 #endif

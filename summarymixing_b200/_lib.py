@@ -112,6 +112,7 @@ _PROTOS = {
     "smx_padding_mask_from_wav_len": (_i, [_vp, _i, _i, _vp, _vp]),
     "smx_chunk_mask": (_i, [_i, _i, _i, _vp, _vp]),
     "smx_debug_tc_gemm": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "smx_debug_set_trace": (_i, [_vp]),
 }
 
 

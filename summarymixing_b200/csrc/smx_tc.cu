@@ -165,3 +165,10 @@ extern "C" SMX_API int smx_debug_tc_gemm(int layout, int32_t M, int32_t N, int32
   count_launch();
   return check_launch("tc_gemm_test_kernel");
 }
+
+// debug: device buffer (>= 1024 x uint64, zeroed by the caller) receiving clock64() timelines of CTA 0 of the fused
+// kernels; NULL switches tracing off.  Not thread-safe; diagnostics only.
+extern "C" SMX_API int smx_debug_set_trace(void* device_u64_buffer) {
+  tc_set_trace(device_u64_buffer);
+  return SMX_OK;
+}

@@ -51,6 +51,7 @@ int tc_cell_fwd(const smx_cell_weights* w, const void* packed, int B, int T, con
                 __nv_bfloat16* y, Arena& ws, cudaStream_t st);
 
 // ---- smx_tc_cell.cu: K-SM, the fused persistent cell (two passes) ---------------------------------
+void tc_set_trace(void* p);  // debug timeline buffer (>= 1024 x u64) or NULL
 bool tc_cellf_supported(const smx_cell_weights* w);
 size_t tc_cellf_workspace_bytes(const smx_cell_weights* w, int B, int T);
 int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_s2, const void* img_f1, const void* img_f2,

@@ -11,13 +11,13 @@
 //
 // The frame tile is read from HBM once per pass (the second read hits L2) and only y is written: hidden
 // activations, S, L and the concatenation never exist in global memory.  Inside a CTA:
-//   warp 0      weight producer: 8 KB (64 x 64 bf16) weight blocks stream from the packed image (L2) through a
-//               shared-memory ring with cp.async.bulk + mbarrier; zero blocks of block-diagonal weights are skipped
-//   warp 1      MMA issuer: tcgen05.mma (M=128, N=64, K=16) into 64-column TMEM accumulator chunks
-//   warps 2-5   prologue: coalesced 16-byte loads of the next tile, LayerNorm (norm1), bf16 A operand (128B swizzle)
-//   warps 6-13  epilogue: two groups of four warps (one per TMEM lane quadrant) take alternate 64-column chunks:
+//   warps 0-7   epilogue: two groups of four warps (one per TMEM lane quadrant) take alternate 64-column chunks:
 //               tcgen05.ld -> bias/activation/mask -> next GEMM's A operand in shared memory (or LN_l through
 //               TMEM, column sums, or the staged output tile which leaves with coalesced 16-byte stores)
+//   warps 8-11  prologue: coalesced 16-byte loads of the next tile, LayerNorm (norm1), bf16 A operand (128B swizzle)
+//   warp 12     weight producer: 8 KB (64 x 64 bf16) weight blocks stream from the packed image (L2) through a
+//               shared-memory ring with cp.async.bulk + mbarrier; zero blocks of block-diagonal weights are skipped
+//   warp 13     MMA issuer: tcgen05.mma (M=128, N=64, K=16) into 64-column TMEM accumulator chunks
 // so the tensor pipe, the TMA engine, the prologue loads and the epilogue math of neighbouring chunks/tiles overlap.
 #include "smx_tc.h"
 #include "smx_tc_common.cuh"
@@ -27,15 +27,20 @@ namespace smx {
 using tc::kblock_bytes;
 
 constexpr int CF_THREADS = 448;      // 14 warps
-constexpr int CF_PRO_WARP0 = 2;      // warps 2..5
-constexpr int CF_EPI_WARP0 = 6;      // warps 6..13
-constexpr int CF_MAX_STAGES = 12;
+// Warp roles.  The SM's warp arbiter favours the highest warp id among eligible warps, so the two single-thread,
+// latency-critical roles (MMA issuer, weight producer) sit in the top warps and the bulk math below them.
+constexpr int CF_EPI_WARP0 = 0;      // warps 0..7   epilogue
+constexpr int CF_PRO_WARP0 = 8;      // warps 8..11  prologue
+constexpr int CF_PROD_WARP = 12;     // weight producer (also owns the TMEM allocation)
+constexpr int CF_MMA_WARP = 13;      // MMA issuer
+constexpr int CF_MAX_STAGES = 12;     // ring slots (a multiple of 4 is used)
 constexpr uint32_t CF_BLOCK_BYTES = 8192;  // one 64 x 64 bf16 weight block
 
 struct CfGemm {
   const uint8_t* img;  // packed image: [chunk][kblock] blocks of 64 rows x 128 B (128B swizzle)
   int nkb, nc;         // K/64, N/64
-  int head_in, head_out;  // block-diagonal structure (0 = dense)
+  int nheads, cph, kph;   // block-diagonal structure: heads, chunks per head, K-blocks per head (dense: 1, nc, nkb)
+  int gw;                 // chunks per MMA column group (1, 2 or 4; divides cph)
 };
 
 struct CellFP {
@@ -54,17 +59,16 @@ struct CellFP {
   float* colsum;        // [n_tiles][Ds]
   float* rowbias;       // [B][Dout]
   unsigned* counters;   // [B]
+  unsigned long long* trace;  // debug timeline of CTA 0 (NULL: off)
   int n_stages;
   uint32_t off_y, off_ring, off_par, off_red;   // shared-memory carve-up (bytes from the 1024-aligned base)
 };
 
-__device__ __forceinline__ bool cf_live(const CfGemm& g, int c, int kb) {
-  return g.head_in == 0 || (kb * 64) / g.head_in == (c * 64) / g.head_out;
-}
-__device__ __forceinline__ bool cf_first(const CfGemm& g, int kb) { return g.head_in == 0 ? kb == 0 : (kb * 64) % g.head_in == 0; }
-__device__ __forceinline__ bool cf_last(const CfGemm& g, int kb) {
-  return g.head_in == 0 ? kb == g.nkb - 1 : ((kb + 1) * 64) % g.head_in == 0;
-}
+// debug timeline: role (0 producer, 1 issuer, 2 prologue, 3/4 epilogue groups) x tile iteration (< 4) x event (< 16)
+#define CF_TRACE(role, it, ev)                                                                          \
+  do {                                                                                                  \
+    if (p.trace && blockIdx.x == 0 && lane == 0 && (it) < 4) p.trace[(((role)*4 + (it)) * 16) + (ev)] = clock64(); \
+  } while (0)
 
 __device__ __forceinline__ uint4 cf_pack8(const float* v) {
   return make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]), tc::pack_bf16x2(v[6], v[7]));
@@ -159,7 +163,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
   uint8_t* sX = smem;
   uint8_t* sY = smem + p.off_y;
   uint8_t* sRing = smem + p.off_ring;
-  float* sPar = reinterpret_cast<float*>(smem + p.off_par);   // [b1 | b2 | ln_w | ln_b], 256 floats each
+  float* sPar = reinterpret_cast<float*>(smem + p.off_par);   // [b1 | b2 | ln_w | ln_b | c[b]], 256 floats each
   float* sRed = reinterpret_cast<float*>(smem + p.off_red);   // 1024 floats: column partials / LN statistics / finalize
   __shared__ __align__(8) uint64_t full_bar[CF_MAX_STAGES], empty_bar[CF_MAX_STAGES];
   __shared__ __align__(8) uint64_t x_full, x_free, a2_full, epi_done;
@@ -170,8 +174,8 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   constexpr int NG = PHASE == 0 ? 2 : 3;
 
-  if (warp == 0) tc::tmem_alloc(&tmem_base_s, 512);
-  if (tid == 32) {
+  if (warp == CF_PROD_WARP) tc::tmem_alloc(&tmem_base_s, 512);
+  if (tid == 0) {
     for (int s = 0; s < p.n_stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     tc::mbar_init(&x_full, 4); tc::mbar_init(&x_free, 1); tc::mbar_init(&a2_full, 8); tc::mbar_init(&epi_done, 8);
     for (int c = 0; c < 4; ++c) {
@@ -192,74 +196,98 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
   const uint32_t tmem = tmem_base_s;
   const int first_tile = blockIdx.x, tile_step = gridDim.x;
 
-  if (warp == 0) {
+  if (warp == CF_PROD_WARP) {
     // =============================== weight producer ===============================
+    // Schedule (identical in the MMA issuer): block-diagonal weights are walked head by head; head m owns chunks
+    // [m*cph, (m+1)*cph) and K-blocks [m*kph, (m+1)*kph) (dense = one head).  Inside a head, gw consecutive chunks
+    // form a column group that one MMA covers (N = 64*gw); its K-block step takes gw consecutive, gw-aligned ring
+    // slots (one 8 KB block per chunk): the data arrival is tracked on the first slot's full barrier, consumption
+    // on every slot's own empty barrier (slots are also used singly).  Ring parity is tracked per slot.
     if (lane == 0) {
-      int s = 0, ph = 0;
+      int s = 0;
+      uint32_t pe = 0;  // per-slot parity of the next empty-barrier wait
       for (int tile = first_tile; tile < p.n_tiles; tile += tile_step) {
+#pragma unroll
         for (int gi = 0; gi < NG; ++gi) {
-          const CfGemm& g = p.g[gi];
-          for (int c = 0; c < g.nc; ++c)
-            for (int kb = 0; kb < g.nkb; ++kb) {
-              if (!cf_live(g, c, kb)) continue;
-              tc::mbar_wait(&empty_bar[s], ph ^ 1);
-              tc::mbar_arrive_expect_tx(&full_bar[s], CF_BLOCK_BYTES);
-              tc::bulk_g2s(sRing + (size_t)s * CF_BLOCK_BYTES, g.img + (size_t)(c * g.nkb + kb) * CF_BLOCK_BYTES, CF_BLOCK_BYTES,
-                           &full_bar[s]);
-              if (++s == p.n_stages) { s = 0; ph ^= 1; }
-            }
+          const CfGemm g = p.g[gi];
+          for (int m = 0; m < g.nheads; ++m)
+            for (int j = 0; j < g.cph; j += g.gw)
+              for (int kb = m * g.kph; kb < (m + 1) * g.kph; ++kb) {
+                s = (s + g.gw - 1) & ~(g.gw - 1);
+                if (s >= p.n_stages) s = 0;
+                for (int u = 0; u < g.gw; ++u) {  // every slot of the group must have been consumed
+                  tc::mbar_wait(&empty_bar[s + u], ((pe >> (s + u)) & 1u) ^ 1u);
+                  pe ^= 1u << (s + u);
+                }
+                tc::mbar_arrive_expect_tx(&full_bar[s], CF_BLOCK_BYTES * g.gw);
+                for (int u = 0; u < g.gw; ++u)
+                  tc::bulk_g2s(sRing + (size_t)(s + u) * CF_BLOCK_BYTES,
+                               g.img + (size_t)((m * g.cph + j + u) * g.nkb + kb) * CF_BLOCK_BYTES, CF_BLOCK_BYTES, &full_bar[s]);
+                s += g.gw;
+              }
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == CF_MMA_WARP) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
-      int s = 0, ph = 0;
-      const uint32_t x0 = tc::smem_u32(sX), y0 = tc::smem_u32(sY), r0 = tc::smem_u32(sRing);
-      const uint32_t idesc = tc::make_idesc_bf16(128, 64);
-      int it = 0;
-      for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
-        const uint32_t par = it & 1;
-        for (int gi = 0; gi < NG; ++gi) {
-          const CfGemm& g = p.g[gi];
-          const uint32_t a0 = gi == 0 ? x0 : y0;
-          const uint32_t dcol = gi == 0 ? 0u : 256u;
-          if (gi == 0) {
-            tc::mbar_wait(&x_full, par);
-          } else if (gi == 1) {
-            if (it > 0) tc::mbar_wait(&epi_done, par ^ 1);  // previous tile's accumulators in [256,512) are drained
-          } else {
-            tc::mbar_wait(&a2_full, par);
+    int s = 0;
+    uint32_t pf = 0;  // per-slot parity of the next full-barrier wait
+    const uint32_t x0 = tc::smem_u32(sX), y0 = tc::smem_u32(sY), r0 = tc::smem_u32(sRing);
+    int it = 0;
+    for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
+      const uint32_t par = it & 1;
+#pragma unroll
+      for (int gi = 0; gi < NG; ++gi) {
+        const CfGemm g = p.g[gi];
+        const uint32_t a0 = gi == 0 ? x0 : y0;
+        const uint32_t dcol = gi == 0 ? 0u : 256u;
+        uint64_t* accbar = gi == 0 ? acc1_full : (gi == 1 ? acc2_full : acc3_full);
+        const uint32_t idesc = tc::make_idesc_bf16(128, 64u * g.gw);
+        if (gi == 0) {
+          tc::mbar_wait(&x_full, par);
+        } else if (gi == 1) {
+          if (it > 0) tc::mbar_wait(&epi_done, par ^ 1);  // previous tile's accumulators in [256,512) are drained
+        } else {
+          tc::mbar_wait(&a2_full, par);
+        }
+        tc::tc_fence_after();
+        CF_TRACE(1, it, gi * 2);
+        for (int m = 0; m < g.nheads; ++m) {
+          if (gi == 1) {  // A1 K-blocks of this head (every K-block belongs to exactly one head)
+            for (int kb = m * g.kph; kb < (m + 1) * g.kph; ++kb) tc::mbar_wait(&a1_full[kb], par);
+            tc::tc_fence_after();
           }
-          tc::tc_fence_after();
-          uint32_t seen = 0;  // K-blocks of A1 already waited for (gi == 1)
-          for (int c = 0; c < g.nc; ++c)
-            for (int kb = 0; kb < g.nkb; ++kb) {
-              if (!cf_live(g, c, kb)) continue;
-              if (gi == 1 && !(seen & (1u << kb))) {
-                tc::mbar_wait(&a1_full[kb], par);
-                tc::tc_fence_after();
-                seen |= 1u << kb;
-              }
-              tc::mbar_wait(&full_bar[s], ph);
+          for (int j = 0; j < g.cph; j += g.gw) {
+            const int c0 = m * g.cph + j;
+            const uint32_t d_addr = tmem + dcol + c0 * 64;
+            for (int kb = m * g.kph; kb < (m + 1) * g.kph; ++kb) {
+              s = (s + g.gw - 1) & ~(g.gw - 1);
+              if (s >= p.n_stages) s = 0;
+              tc::mbar_wait(&full_bar[s], (pf >> s) & 1u);
+              pf ^= 1u << s;
               tc::tc_fence_after();
               const uint32_t a_addr = a0 + kb * kblock_bytes(128);
               const uint32_t b_addr = r0 + s * CF_BLOCK_BYTES;
-              const uint32_t d_addr = tmem + dcol + c * 64;
-              const bool first = cf_first(g, kb);
+              if (lane == 0) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks)
-                tc::umma_bf16(d_addr, tc::make_desc_sw128(a_addr + ks * 32), tc::make_desc_sw128(b_addr + ks * 32), idesc,
-                              (first && ks == 0) ? 0u : 1u);
-              tc::umma_commit(&empty_bar[s]);
-              if (++s == p.n_stages) { s = 0; ph ^= 1; }
-              if (cf_last(g, kb)) tc::umma_commit(gi == 0 ? &acc1_full[c] : (gi == 1 ? &acc2_full[c] : &acc3_full[c]));
+                for (int ks = 0; ks < 4; ++ks)
+                  tc::umma_bf16(d_addr, tc::make_desc_sw128(a_addr + ks * 32), tc::make_desc_sw128(b_addr + ks * 32), idesc,
+                                (kb == m * g.kph && ks == 0) ? 0u : 1u);
+                for (int u = 0; u < g.gw; ++u) tc::umma_commit(&empty_bar[s + u]);
+                if (kb == (m + 1) * g.kph - 1)
+                  for (int u = 0; u < g.gw; ++u) tc::umma_commit(&accbar[c0 + u]);
+              }
+              __syncwarp();
+              s += g.gw;
             }
-          if (gi == 0) tc::umma_commit(&x_free);
+          }
         }
+        if (gi == 0 && lane == 0) tc::umma_commit(&x_free);
+        __syncwarp();
+        CF_TRACE(1, it, gi * 2 + 1);
       }
     }
-  } else if (warp < CF_EPI_WARP0) {
+  } else if (warp >= CF_PRO_WARP0) {
     // =============================== prologue: x tile -> LN1 -> A operand ===============================
     const int pw = warp - CF_PRO_WARP0;
     const int nchunk = p.D / 8;  // 16-byte chunks per row (<= 32)
@@ -277,6 +305,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
       const int64_t row0 = (int64_t)b * p.T + t0;
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
       if (it > 0) tc::mbar_wait(&x_free, (it - 1) & 1);
+      if (pw == 0) CF_TRACE(2, it, 0);
 #pragma unroll 1
       for (int r8 = 0; r8 < 32; r8 += 8) {
         uint4 raw[8];
@@ -316,6 +345,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&x_full);
+      if (pw == 0) CF_TRACE(2, it, 1);
     }
   } else {
     // =============================== epilogue ===============================
@@ -326,6 +356,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
     const int etid = e * 32 + lane;    // 0..255
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const float* sB1 = sPar; const float* sB2 = sPar + 256; const float* sLw = sPar + 512; const float* sLb = sPar + 768;
+    float* sRB = sPar + 1024;
     const int nc1 = p.g[0].nc, nc2 = p.g[1].nc;
     int it = 0;
     for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
@@ -337,9 +368,11 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
       const float rscale = live ? (p.mask ? (float)p.mask[row0 + r] : 1.0f) : 0.0f;
 
       // ---- E1: hidden = act(acc1 + b1) -> A operand of the second GEMM (K-block c of Y)
+      if (q == 0) CF_TRACE(3 + grp, it, 0);
       for (int c = grp; c < nc1; c += 2) {
         tc::mbar_wait(&acc1_full[c], par);
         tc::tc_fence_after();
+        if (q == 0 && c == grp) CF_TRACE(3 + grp, it, 1);
 #pragma unroll
         for (int pc = 0; pc < 2; ++pc) {
           float v[32];
@@ -359,6 +392,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
         if (lane == 0) tc::mbar_arrive(&a1_full[c]);
       }
 
+      if (q == 0) CF_TRACE(3 + grp, it, 2);
       if (PHASE == 0) {
         // ---- E2': S = act(acc2 + b2) * mask -> column sums of this tile                      :221, 229-231
         for (int c = grp; c < nc2; c += 2) {
@@ -382,6 +416,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&epi_done);
+        if (q == 0) CF_TRACE(3 + grp, it, 3);
         tc::named_bar_sync(1, 256);
         if (etid < p.Ds)  // fixed-order reduction over the four row quadrants: deterministic
           p.colsum[(size_t)tile * p.Ds + etid] = (sRed[etid] + sRed[256 + etid]) + (sRed[512 + etid] + sRed[768 + etid]);
@@ -393,8 +428,10 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
           __threadfence();
         }
         tc::named_bar_sync(1, 256);
+        if (q == 0) CF_TRACE(3 + grp, it, 4);
         if (s_last) cf_finalize(p, b, sRed, etid);
         tc::named_bar_sync(1, 256);
+        if (q == 0) CF_TRACE(3 + grp, it, 5);
       } else {
         // ---- E2: L = LN_l(act(acc2 + b2) * mask) -> A operand of the combiner (Y, in place)     :215-218
         const int Dl = nc2 * 64;
@@ -419,6 +456,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
             }
           }
           tc::tmem_st_wait();
+          if (q == 0) CF_TRACE(3 + grp, it, 3);
           sRed[grp * 128 + r] = s1;
           tc::named_bar_sync(1, 256);
           const float mean = (sRed[r] + sRed[128 + r]) / (float)Dl;
@@ -486,12 +524,40 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&a2_full);
+        if (q == 0) CF_TRACE(3 + grp, it, 4);
 
         // ---- E3: y = act(acc3 + c[b]) (+ residual) -> staged tile -> coalesced stores            :251-253, :541
+        // While the combiner GEMM runs, the residual tile is fetched with coalesced 16-byte loads (thread etid takes
+        // chunk idx = etid + 256k of the tile) and c[b] goes to shared memory; once Y is free the residual is parked
+        // there (swizzled, conflict-free) so that each thread can add its own row in fp32 and round once.
         const int nc3 = p.g[2].nc;
+        const int cpr = p.Dout / 8;           // 16-byte chunks per output row
+        const int rr0 = etid / cpr, ch0 = etid - rr0 * cpr, drr = 256 / cpr, dch = 256 - drr * cpr;
+        uint4 rres[16];
+        if (p.resid) {
+          int rr = rr0, ch = ch0;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            rres[k] = make_uint4(0, 0, 0, 0);
+            if (rr < nrows) rres[k] = *reinterpret_cast<const uint4*>(p.resid + (row0 + rr) * p.ldr + ch * 8);
+            rr += drr; ch += dch;
+            if (ch >= cpr) { ch -= cpr; ++rr; }
+          }
+        }
+        if (etid < p.Dout) sRB[etid] = __ldcg(p.rowbias + (size_t)b * p.Dout + etid);
         tc::mbar_wait(&acc3_full[nc3 - 1], par);  // commits complete in order: every combiner chunk is done, Y is free
         tc::tc_fence_after();
-        const float* rb = p.rowbias + (size_t)b * p.Dout;
+        if (q == 0) CF_TRACE(3 + grp, it, 5);
+        if (p.resid) {
+          int rr = rr0, ch = ch0;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            if (rr < 128) *reinterpret_cast<uint4*>(sY + (size_t)(ch >> 3) * kblock_bytes(128) + tc::sw128_offset(rr, ch & 7)) = rres[k];
+            rr += drr; ch += dch;
+            if (ch >= cpr) { ch -= cpr; ++rr; }
+          }
+        }
+        tc::named_bar_sync(1, 256);
         for (int c = grp; c < nc3; c += 2) {
 #pragma unroll
           for (int pc = 0; pc < 2; ++pc) {
@@ -499,44 +565,48 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
             float v[32];
             tc::tmem_ld32(tmem + lane_sel + 256 + col, v);
             tc::tmem_ld_wait();
+            const float4* bp = reinterpret_cast<const float4*>(sRB + col);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 bb = __ldcg(reinterpret_cast<const float4*>(rb + col) + j);
-              v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w;
-            }
+            for (int j = 0; j < 8; ++j) { const float4 bb = bp[j]; v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w; }
             tc::act_apply<32>(p.act, v);
-            if (p.resid && live) {
-              const uint4* rp = reinterpret_cast<const uint4*>(p.resid + (row0 + r) * p.ldr + col);
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
+            for (int k = 0; k < 4; ++k) {
+              uint4* sp = reinterpret_cast<uint4*>(sY + (size_t)c * kblock_bytes(128) + tc::sw128_offset(r, pc * 4 + k));
+              if (p.resid) {
                 float f[8];
-                cf_unpack8(rp[k], f);
+                cf_unpack8(*sp, f);
 #pragma unroll
                 for (int j = 0; j < 8; ++j) v[8 * k + j] += f[j];
               }
+              *sp = cf_pack8(v + 8 * k);
             }
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              *reinterpret_cast<uint4*>(sY + (size_t)c * kblock_bytes(128) + tc::sw128_offset(r, pc * 4 + k)) = cf_pack8(v + 8 * k);
           }
         }
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&epi_done);
+        if (q == 0) CF_TRACE(3 + grp, it, 6);
         tc::named_bar_sync(1, 256);
-        const int cpr = p.Dout / 8;
-        for (int idx = etid; idx < nrows * cpr; idx += 256) {
-          const int rr = idx / cpr, ch = idx - rr * cpr;
-          const uint4 val = *reinterpret_cast<const uint4*>(sY + (size_t)(ch >> 3) * kblock_bytes(128) + tc::sw128_offset(rr, ch & 7));
-          *reinterpret_cast<uint4*>(p.y + (row0 + rr) * p.ldy + ch * 8) = val;
+        {
+          int rr = rr0, ch = ch0;
+#pragma unroll 4
+          for (int k = 0; k < 16; ++k) {
+            if (rr < nrows) {
+              const uint4 val = *reinterpret_cast<const uint4*>(sY + (size_t)(ch >> 3) * kblock_bytes(128) + tc::sw128_offset(rr, ch & 7));
+              *reinterpret_cast<uint4*>(p.y + (row0 + rr) * p.ldy + ch * 8) = val;
+            }
+            rr += drr; ch += dch;
+            if (ch >= cpr) { ch -= cpr; ++rr; }
+          }
         }
         tc::named_bar_sync(1, 256);
+        if (q == 0) CF_TRACE(3 + grp, it, 7);
       }
     }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (warp == 0) tc::tmem_dealloc(tmem, 512);
+  if (warp == CF_PROD_WARP) tc::tmem_dealloc(tmem, 512);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -564,21 +634,19 @@ bool tc_cellf_supported(const smx_cell_weights* w) {
   return true;
 }
 
-// block-diagonal structure the kernel can skip zero blocks for; anything else is packed (with its zeros) as dense
-static void head_dims(const smx_linear& L, int& hin, int& hout) {
-  hin = hout = 0;
-  if (L.n_split > 1) {
-    const int a = L.in_dim / L.n_split, b = L.out_dim / L.n_split;
-    if (a % 64 == 0 && b % 64 == 0) { hin = a; hout = b; }
-  }
-}
-
+// block-diagonal structure the kernel can skip zero blocks for (head dims multiples of 64); anything else is
+// packed with its zeros and run as dense
 static CfGemm make_gemm(const smx_linear& L, const void* img, int K) {
   CfGemm g{};
   g.img = (const uint8_t*)img;
   g.nkb = K / 64;
   g.nc = L.out_dim / 64;
-  head_dims(L, g.head_in, g.head_out);
+  g.nheads = 1; g.cph = g.nc; g.kph = g.nkb;
+  if (L.n_split > 1) {
+    const int a = L.in_dim / L.n_split, b = L.out_dim / L.n_split;
+    if (a % 64 == 0 && b % 64 == 0 && a * L.n_split == K) { g.nheads = L.n_split; g.kph = a / 64; g.cph = b / 64; }
+  }
+  g.gw = g.cph % 4 == 0 ? 4 : (g.cph % 2 == 0 ? 2 : 1);
   return g;
 }
 
@@ -586,6 +654,9 @@ size_t tc_cellf_workspace_bytes(const smx_cell_weights* w, int B, int T) {
   const int tpu = (T + 127) / 128;
   return align_up((size_t)B * tpu * w->summary_out_dim * 4) + align_up((size_t)B * w->merge.out_dim * 4) + align_up((size_t)B * 4);
 }
+
+static unsigned long long* g_trace = nullptr;  // set by smx_debug_set_trace
+void tc_set_trace(void* p) { g_trace = (unsigned long long*)p; }
 
 static int g_num_sms = 0;
 static int num_sms() {
@@ -623,16 +694,18 @@ int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
     const uint32_t xb = (uint32_t)(D / 64) * kblock_bytes(128), yb = (uint32_t)(ycols / 64) * kblock_bytes(128);
     p.off_y = xb;
     p.off_ring = xb + yb;
-    const size_t fixed = (size_t)xb + yb + 4096 /*params*/ + 4096 /*reductions*/ + 1024 /*align*/ + 1024 /*static*/;
+    const size_t fixed = (size_t)xb + yb + 8192 /*params*/ + 4096 /*reductions*/ + 1024 /*align*/ + 1024 /*static*/;
     int stages = (int)((227 * 1024 - fixed) / CF_BLOCK_BYTES);
     if (stages > CF_MAX_STAGES) stages = CF_MAX_STAGES;
+    stages &= ~3;  // column groups take up to 4 aligned consecutive slots
     p.n_stages = stages;
     p.off_par = p.off_ring + stages * CF_BLOCK_BYTES;
-    p.off_red = p.off_par + 4096;
+    p.off_red = p.off_par + 8192;
     return (size_t)p.off_red + 4096 + 1024;
   };
   const unsigned grid = (unsigned)(p.n_tiles < num_sms() ? p.n_tiles : num_sms());
 
+  p.trace = g_trace;
   {  // pass A
     p.g[0] = make_gemm(w->summary[0], img_s1, D);
     p.g[1] = make_gemm(w->summary[1], img_s2, w->summary[0].out_dim);
@@ -640,13 +713,14 @@ int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
     p.ln_w = w->use_layernorm ? w->summary_norm_w : nullptr;
     p.ln_b = w->use_layernorm ? w->summary_norm_b : nullptr;
     const size_t smem = carve(w->summary[0].out_dim);
-    if (p.n_stages < 2) return fail(SMX_ERR_UNSUPPORTED, "fused cell: tile does not fit shared memory");
+    if (p.n_stages < 4) return fail(SMX_ERR_UNSUPPORTED, "fused cell: tile does not fit shared memory");
     e = cudaFuncSetAttribute(cell_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(cell_kernel<0>): %s", cudaGetErrorString(e));
     cell_kernel<0><<<grid, CF_THREADS, smem, st>>>(p);
     count_tc_launch();
     SMX_TRY(check_launch("cell_kernel<0>"));
   }
+  if (g_trace) p.trace = g_trace + 512;
   {  // pass B
     p.g[0] = make_gemm(w->local[0], img_f1, D);
     p.g[1] = make_gemm(w->local[1], img_f2, w->local[0].out_dim);
@@ -660,7 +734,7 @@ int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
     if (Dl > ycols) ycols = Dl;
     if (Dout > ycols) ycols = Dout;
     const size_t smem = carve(ycols);
-    if (p.n_stages < 2) return fail(SMX_ERR_UNSUPPORTED, "fused cell: tile does not fit shared memory");
+    if (p.n_stages < 4) return fail(SMX_ERR_UNSUPPORTED, "fused cell: tile does not fit shared memory");
     e = cudaFuncSetAttribute(cell_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(cell_kernel<1>): %s", cudaGetErrorString(e));
     cell_kernel<1><<<grid, CF_THREADS, smem, st>>>(p);
