@@ -56,8 +56,7 @@ int tc_pack_weight(const float* w, int64_t stride_n, int64_t stride_k, int N, in
 __global__ void __launch_bounds__(128) tc_gemm_test_kernel(const __nv_bfloat16* __restrict__ A,
                                                            const __nv_bfloat16* __restrict__ Wp, float* __restrict__ C,
                                                            int M, int N, int K, int NT, int layout, uint32_t tmem_cols) {
-  extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];
   const int Kpad = (K + 63) / 64 * 64;
   const int nkb = Kpad / 64;
   uint8_t* sA = smem;                                  // 128 x Kpad bf16

@@ -4,8 +4,8 @@
 // Two persistent, warp-specialised passes over utterance-aligned 128-frame tiles (one CTA per SM):
 //
 //   pass A (summary):  X = LN1(x tile)  ->  S = act(act(X W_s1 + b) W_s2 + b) * mask  ->  column sums of the tile
-//                      the CTA that delivers the last tile of an utterance (one atomic per tile on a per-utterance
-//                      counter) finalises it: mean over valid frames, LN_s, c[b] = W_c[:, D_l:] mean + b_c
+//   finalise (tiny):   per utterance: mean over valid frames (fixed-order sum of the tile partials: no atomics,
+//                      deterministic), LN_s, c[b] = W_c[:, D_l:] mean + b_c
 //   pass B (local):    X = LN1(x tile)  ->  L = LN_l(act(act(X W_f1 + b) W_f2 + b) * mask)
 //                      ->  y = act(L W_c[:, :D_l]^T + c[b]) (+ residual)
 //
@@ -58,7 +58,6 @@ struct CellFP {
   int act;
   float* colsum;        // [n_tiles][Ds]
   float* rowbias;       // [B][Dout]
-  unsigned* counters;   // [B]
   unsigned long long* trace;  // debug timeline of CTA 0 (NULL: off)
   int n_stages;
   uint32_t off_y, off_ring, off_par, off_red;   // shared-memory carve-up (bytes from the 1024-aligned base)
@@ -94,72 +93,98 @@ __device__ __forceinline__ float cf_column_sums(float* v, int lane) {
   return v[0];
 }
 
-// per-utterance finalisation by the 256 epilogue threads of the CTA that delivered the utterance's last tile:
+// Per-utterance finalisation between the two passes: CTA (b, j) recomputes the utterance mean from the per-tile
+// column sums (fixed order: deterministic), applies LN_s and produces 64 entries of
 //   c[b] = W_c[:, D_l:] @ LN_s( sum_t s[b,t] / sum_t mask[b,t] ) + b_c           summary_mixing.py:229-231, 248-253
-__device__ void cf_finalize(const CellFP& p, int b, float* scr, int etid) {
-  float* mu = scr;          // [256]
-  float* red = scr + 256;   // [8]
-  float* stat = scr + 264;  // [2]
-  const int warp = etid >> 5, lane = etid & 31;
+// Eight warps x eight outputs each; a warp streams its eight weight rows with all loads in flight at once.
+struct CellFinP {
+  const float* colsum; const uint8_t* mask; const float* ln_w; const float* ln_b; const float* Wc; const float* bc;
+  float* rowbias;
+  int T, tpu, Ds, Dl, Dout;
+};
+__global__ void __launch_bounds__(256) cell_finalize2_kernel(const CellFinP p) {
+  __shared__ float mu[256];
+  __shared__ float red[8];
+  __shared__ float stat[2];
+  const int b = blockIdx.x, n0 = blockIdx.y * 64;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Ds = p.Ds;
   float cnt;
   if (p.mask) {  // number of valid frames (integer-valued float, like torch.sum(mask) in the reference)
     float c = 0.0f;
-    for (int t = etid; t < p.T; t += 256) c += (float)p.mask[(size_t)b * p.T + t];
+    for (int t = tid; t < p.T; t += 256) c += (float)p.mask[(size_t)b * p.T + t];
 #pragma unroll
     for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
     if (lane == 0) red[warp] = c;
-    tc::named_bar_sync(1, 256);
+    __syncthreads();
     cnt = 0.0f;
     for (int i = 0; i < 8; ++i) cnt += red[i];
-    tc::named_bar_sync(1, 256);
+    __syncthreads();
   } else {
     cnt = (float)p.T;
   }
-  for (int d = etid; d < Ds; d += 256) {
+  if (tid < Ds) {
+    const float* cs = p.colsum + (size_t)b * p.tpu * Ds + tid;
     float s = 0.0f;
-    for (int i = 0; i < p.tpu; ++i) s += __ldcg(p.colsum + ((size_t)b * p.tpu + i) * Ds + d);  // fixed order
-    mu[d] = s / cnt;
+    int i = 0;
+    for (; i + 8 <= p.tpu; i += 8) {  // eight loads in flight, summed in tile order
+      float v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = cs[(size_t)(i + u) * Ds];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) s += v[u];
+    }
+    for (; i < p.tpu; ++i) s += cs[(size_t)i * Ds];
+    mu[tid] = s / cnt;
   }
-  tc::named_bar_sync(1, 256);
+  __syncthreads();
   if (p.ln_w) {
-    float s = 0.0f;
-    for (int d = etid; d < Ds; d += 256) s += mu[d];
+    float v = tid < Ds ? mu[tid] : 0.0f, s = v;
 #pragma unroll
     for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
     if (lane == 0) red[warp] = s;
-    tc::named_bar_sync(1, 256);
-    if (etid == 0) { float t = 0.0f; for (int i = 0; i < 8; ++i) t += red[i]; stat[0] = t / (float)Ds; }
-    tc::named_bar_sync(1, 256);
+    __syncthreads();
+    if (tid == 0) { float t = 0.0f; for (int i = 0; i < 8; ++i) t += red[i]; stat[0] = t / (float)Ds; }
+    __syncthreads();
     const float mean = stat[0];
-    float q = 0.0f;
-    for (int d = etid; d < Ds; d += 256) { float e = mu[d] - mean; q += e * e; }
+    float d = tid < Ds ? v - mean : 0.0f, q = d * d;
 #pragma unroll
     for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    __syncthreads();
     if (lane == 0) red[warp] = q;
-    tc::named_bar_sync(1, 256);
-    if (etid == 0) { float t = 0.0f; for (int i = 0; i < 8; ++i) t += red[i]; stat[1] = rsqrtf(t / (float)Ds + 1e-5f); }
-    tc::named_bar_sync(1, 256);
-    const float rstd = stat[1];
-    for (int d = etid; d < Ds; d += 256) mu[d] = (mu[d] - mean) * rstd * p.ln_w[d] + p.ln_b[d];
-    tc::named_bar_sync(1, 256);
+    __syncthreads();
+    if (tid == 0) { float t = 0.0f; for (int i = 0; i < 8; ++i) t += red[i]; stat[1] = rsqrtf(t / (float)Ds + 1e-5f); }
+    __syncthreads();
+    if (tid < Ds) mu[tid] = d * stat[1] * p.ln_w[tid] + p.ln_b[tid];
+    __syncthreads();
   }
+  // Ds <= 256: lane covers k = 4*lane..+3 and 128 + 4*lane..+3
   const int ldw = p.Dl + Ds;
-  for (int n = warp; n < p.Dout; n += 8) {  // one warp per output; lanes along k: coalesced weight rows
+  const bool h0 = 4 * lane < Ds, h1 = 128 + 4 * lane < Ds;
+  float4 w0[8], w1[8];
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    const int n = n0 + warp * 8 + u;
     const float* wr = p.Wc + (size_t)n * ldw + p.Dl;
-    float acc = 0.0f;
-    for (int k = lane; k < Ds; k += 32) acc = fmaf(wr[k], mu[k], acc);
+    w0[u] = (n < p.Dout && h0) ? *reinterpret_cast<const float4*>(wr + 4 * lane) : make_float4(0, 0, 0, 0);
+    w1[u] = (n < p.Dout && h1) ? *reinterpret_cast<const float4*>(wr + 128 + 4 * lane) : make_float4(0, 0, 0, 0);
+  }
+  const float4 m0 = h0 ? *reinterpret_cast<const float4*>(mu + 4 * lane) : make_float4(0, 0, 0, 0);
+  const float4 m1 = h1 ? *reinterpret_cast<const float4*>(mu + 128 + 4 * lane) : make_float4(0, 0, 0, 0);
+#pragma unroll
+  for (int u = 0; u < 8; ++u) {
+    float acc = w0[u].x * m0.x + w0[u].y * m0.y + w0[u].z * m0.z + w0[u].w * m0.w;
+    acc += w1[u].x * m1.x + w1[u].y * m1.y + w1[u].z * m1.z + w1[u].w * m1.w;
 #pragma unroll
     for (int o = 16; o; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) p.rowbias[(size_t)b * p.Dout + n] = acc + p.bc[n];
+    const int n = n0 + warp * 8 + u;
+    if (lane == 0 && n < p.Dout) p.rowbias[(size_t)b * p.Dout + n] = acc + p.bc[n];
   }
-  tc::named_bar_sync(1, 256);
 }
 
 template <int PHASE>  // 0: pass A (summary), 1: pass B (local + combiner)
 __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];  // no pointer arithmetic through integers: keeps LDS/STS addressing
   uint8_t* sX = smem;
   uint8_t* sY = smem + p.off_y;
   uint8_t* sRing = smem + p.off_ring;
@@ -169,9 +194,9 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
   __shared__ __align__(8) uint64_t x_full, x_free, a2_full, epi_done;
   __shared__ __align__(8) uint64_t acc1_full[4], a1_full[4], acc2_full[4], acc3_full[4];
   __shared__ uint32_t tmem_base_s;
-  __shared__ int s_last;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler (role dispatch below)
   constexpr int NG = PHASE == 0 ? 2 : 3;
 
   if (warp == CF_PROD_WARP) tc::tmem_alloc(&tmem_base_s, 512);
@@ -193,7 +218,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
   const int first_tile = blockIdx.x, tile_step = gridDim.x;
 
   if (warp == CF_PROD_WARP) {
@@ -268,7 +293,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
               tc::tc_fence_after();
               const uint32_t a_addr = a0 + kb * kblock_bytes(128);
               const uint32_t b_addr = r0 + s * CF_BLOCK_BYTES;
-              if (lane == 0) {
+              if (tc::elect_one()) {
 #pragma unroll
                 for (int ks = 0; ks < 4; ++ks)
                   tc::umma_bf16(d_addr, tc::make_desc_sw128(a_addr + ks * 32), tc::make_desc_sw128(b_addr + ks * 32), idesc,
@@ -282,7 +307,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
             }
           }
         }
-        if (gi == 0 && lane == 0) tc::umma_commit(&x_free);
+        if (gi == 0 && tc::elect_one()) tc::umma_commit(&x_free);
         __syncwarp();
         CF_TRACE(1, it, gi * 2 + 1);
       }
@@ -420,17 +445,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
         tc::named_bar_sync(1, 256);
         if (etid < p.Ds)  // fixed-order reduction over the four row quadrants: deterministic
           p.colsum[(size_t)tile * p.Ds + etid] = (sRed[etid] + sRed[256 + etid]) + (sRed[512 + etid] + sRed[768 + etid]);
-        __threadfence();
-        tc::named_bar_sync(1, 256);
-        if (etid == 0) {
-          const unsigned old = atomicAdd(p.counters + b, 1u);  // the one cross-CTA atomic of this tile
-          s_last = (old == (unsigned)(p.tpu - 1));
-          __threadfence();
-        }
-        tc::named_bar_sync(1, 256);
-        if (q == 0) CF_TRACE(3 + grp, it, 4);
-        if (s_last) cf_finalize(p, b, sRed, etid);
-        tc::named_bar_sync(1, 256);
+        tc::named_bar_sync(1, 256);  // sRed is rewritten by the next tile
         if (q == 0) CF_TRACE(3 + grp, it, 5);
       } else {
         // ---- E2: L = LN_l(act(acc2 + b2) * mask) -> A operand of the combiner (Y, in place)     :215-218
@@ -652,7 +667,7 @@ static CfGemm make_gemm(const smx_linear& L, const void* img, int K) {
 
 size_t tc_cellf_workspace_bytes(const smx_cell_weights* w, int B, int T) {
   const int tpu = (T + 127) / 128;
-  return align_up((size_t)B * tpu * w->summary_out_dim * 4) + align_up((size_t)B * w->merge.out_dim * 4) + align_up((size_t)B * 4);
+  return align_up((size_t)B * tpu * w->summary_out_dim * 4) + align_up((size_t)B * w->merge.out_dim * 4);
 }
 
 static unsigned long long* g_trace = nullptr;  // set by smx_debug_set_trace
@@ -678,17 +693,15 @@ int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
   const size_t m0 = ws.mark();
   float* colsum = ws.f32((size_t)B * tpu * Ds);
   float* rowbias = ws.f32((size_t)B * Dout);
-  unsigned* counters = (unsigned*)ws.take((size_t)B * 4);
-  if (!colsum || !rowbias || !counters) return fail(SMX_ERR_WORKSPACE, "workspace too small (fused cell)");
-  cudaError_t e = cudaMemsetAsync(counters, 0, (size_t)B * 4, st);
-  if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  if (!colsum || !rowbias) return fail(SMX_ERR_WORKSPACE, "workspace too small (fused cell)");
+  cudaError_t e;
 
   CellFP p{};
   p.x = x; p.ldx = D; p.pre_w = pre_ln_w; p.pre_b = pre_ln_b; p.mask = mask;
   p.resid = residual; p.ldr = Dout; p.y = y; p.ldy = Dout;
   p.B = B; p.T = T; p.tpu = tpu; p.n_tiles = B * tpu; p.D = D;
   p.Wc = w->merge.w; p.bc = w->merge.b; p.Dl = Dl; p.Ds = Ds; p.Dout = Dout;
-  p.act = w->act; p.colsum = colsum; p.rowbias = rowbias; p.counters = counters;
+  p.act = w->act; p.colsum = colsum; p.rowbias = rowbias;
 
   auto carve = [&](int ycols) {
     const uint32_t xb = (uint32_t)(D / 64) * kblock_bytes(128), yb = (uint32_t)(ycols / 64) * kblock_bytes(128);
@@ -719,6 +732,16 @@ int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
     cell_kernel<0><<<grid, CF_THREADS, smem, st>>>(p);
     count_tc_launch();
     SMX_TRY(check_launch("cell_kernel<0>"));
+  }
+  {  // per-utterance mean -> LN_s -> summary share of the combiner
+    CellFinP f{};
+    f.colsum = colsum; f.mask = mask; f.Wc = w->merge.w; f.bc = w->merge.b; f.rowbias = rowbias;
+    f.ln_w = w->use_layernorm ? w->summary_norm_w : nullptr;
+    f.ln_b = w->use_layernorm ? w->summary_norm_b : nullptr;
+    f.T = T; f.tpu = tpu; f.Ds = Ds; f.Dl = Dl; f.Dout = Dout;
+    cell_finalize2_kernel<<<dim3(B, (Dout + 63) / 64), 256, 0, st>>>(f);
+    count_launch();
+    SMX_TRY(check_launch("cell_finalize2_kernel"));
   }
   if (g_trace) p.trace = g_trace + 512;
   {  // pass B

@@ -52,18 +52,37 @@ __device__ __forceinline__ uint64_t global_timer_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-// Bounded wait: a protocol bug traps (launch error) after ~2 s instead of hanging the GPU.
+// Bounded wait: a protocol bug traps (launch error) instead of hanging the GPU.  The retry loop lives inside one
+// asm block so that the surrounding C++ control flow stays warp-uniform for the compiler (the MMA issuer's address
+// arithmetic then stays in uniform registers).  try_wait suspends the thread in hardware for a bounded time per
+// attempt (~0.5 us observed), so 2^23 attempts bound the wait to a few seconds.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  if (mbar_try_wait(bar, parity)) return;
-  uint64_t t0 = 0;
-  uint32_t spins = 0;
-  while (!mbar_try_wait(bar, parity)) {
-    if ((++spins & 0x3ffu) == 0) {
-      uint64_t now = global_timer_ns();
-      if (t0 == 0) t0 = now;
-      else if (now - t0 > 2000000000ull) __trap();
-    }
-  }
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .u32 n;\n\t"
+      "mov.u32 n, 0;\n\t"
+      "MBAR_WAIT_%=:\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+      "@p bra MBAR_DONE_%=;\n\t"
+      "add.u32 n, n, 1;\n\t"
+      "setp.lt.u32 p, n, 8388608;\n\t"
+      "@p bra MBAR_WAIT_%=;\n\t"
+      "trap;\n\t"
+      "MBAR_DONE_%=:\n\t"
+      "}" ::"r"(smem_u32(bar)),
+      "r"(parity)
+      : "memory");
+}
+// one lane of the (converged) warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 // ---- bulk async copies (TMA engine, 1-D) ---------------------------------------------------------

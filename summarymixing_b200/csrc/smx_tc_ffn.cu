@@ -39,7 +39,8 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const FfnP p) {
   __shared__ __align__(8) uint64_t full_bar[2], empty_bar[2], acc1_full[2], acc1_empty[2], h_full[2], h_empty[2], acc2_full;
   __shared__ uint32_t tmem_base_s;
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler (role dispatch below)
   const int64_t row0 = (int64_t)blockIdx.x * 128;
   const int nrows = p.rows - row0 < 128 ? (int)(p.rows - row0) : 128;
 
@@ -64,14 +65,30 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const FfnP p) {
   // ---- prologue: LN(x tile) -> A operand ----------------------------------------------------------
   {
     const int nchunk = D / 8;
-    for (int r = warp; r < 128; r += FFN_THREADS / 32) {
+    constexpr int NW = FFN_THREADS / 32;
+    for (int rb = warp; rb < 128; rb += 4 * NW) {  // four rows per round trip to memory
+    uint4 rawb[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = rb + j * NW;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int ck = lane + 32 * c;
+        rawb[j][c] = make_uint4(0, 0, 0, 0);
+        if (ck < nchunk && r < nrows) rawb[j][c] = *reinterpret_cast<const uint4*>(p.x + (row0 + r) * D + ck * 8);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = rb + j * NW;
+      if (r >= 128) break;
       const bool live = r < nrows;
       float v[2][8];
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int ck = lane + 32 * c;
         if (ck < nchunk && live) {
-          uint4 raw = *reinterpret_cast<const uint4*>(p.x + (row0 + r) * D + ck * 8);
+          uint4 raw = rawb[j][c];
           const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
           for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(h[e]); v[c][2 * e] = f.x; v[c][2 * e + 1] = f.y; }
@@ -110,12 +127,13 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const FfnP p) {
         }
       }
     }
+    }
   }
   tc::fence_proxy_async();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
   const uint32_t t_acc2 = tmem, t_acc1 = tmem + D;  // acc1 buffers at D and D+64
 
   if (warp == 8) {
@@ -130,7 +148,8 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const FfnP p) {
     }
   } else if (warp == 9) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // the whole warp walks the (warp-uniform) schedule; one elected lane issues tcgen05.mma / tcgen05.commit
+    {
       const uint32_t a0 = tc::smem_u32(sA), h0 = tc::smem_u32(sH), w0 = tc::smem_u32(sW);
       const uint32_t idesc1 = tc::make_idesc_bf16(128, FFN_HC), idesc2 = tc::make_idesc_bf16(128, (uint32_t)D);
       auto gemm1 = [&](int j) {  // acc1[j&1] = LN(x) @ W1[j]^T
@@ -139,12 +158,15 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const FfnP p) {
         tc::mbar_wait(&acc1_empty[s], ((j >> 1) & 1) ^ 1);
         tc::tc_fence_after();
         const uint32_t wb = w0 + s * p.stage_bytes;
-        for (int kb = 0; kb < nkb; ++kb)
+        if (tc::elect_one()) {
+          for (int kb = 0; kb < nkb; ++kb)
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            tc::umma_bf16(t_acc1 + s * FFN_HC, tc::make_desc_sw128(a0 + kb * kblock_bytes(128) + ks * 32),
-                          tc::make_desc_sw128(wb + kb * kblock_bytes(FFN_HC) + ks * 32), idesc1, (kb | ks) ? 1u : 0u);
-        tc::umma_commit(&acc1_full[s]);
+            for (int ks = 0; ks < 4; ++ks)
+              tc::umma_bf16(t_acc1 + s * FFN_HC, tc::make_desc_sw128(a0 + kb * kblock_bytes(128) + ks * 32),
+                            tc::make_desc_sw128(wb + kb * kblock_bytes(FFN_HC) + ks * 32), idesc1, (kb | ks) ? 1u : 0u);
+          tc::umma_commit(&acc1_full[s]);
+        }
+        __syncwarp();
       };
       gemm1(0);
       for (int j = 0; j < nc; ++j) {
@@ -153,14 +175,18 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const FfnP p) {
         tc::mbar_wait(&h_full[s], (j >> 1) & 1);
         tc::tc_fence_after();
         const uint32_t wb = w0 + s * p.stage_bytes + p.w2_off;
+        if (tc::elect_one()) {
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks)  // acc2 += H[j] @ W2[:, j]^T
-          tc::umma_bf16(t_acc2, tc::make_desc_sw128(h0 + s * kblock_bytes(128) + ks * 32), tc::make_desc_sw128(wb + ks * 32),
-                        idesc2, (j | ks) ? 1u : 0u);
-        tc::umma_commit(&empty_bar[s]);
-        tc::umma_commit(&h_empty[s]);
+          for (int ks = 0; ks < 4; ++ks)  // acc2 += H[j] @ W2[:, j]^T
+            tc::umma_bf16(t_acc2, tc::make_desc_sw128(h0 + s * kblock_bytes(128) + ks * 32), tc::make_desc_sw128(wb + ks * 32),
+                          idesc2, (j | ks) ? 1u : 0u);
+          tc::umma_commit(&empty_bar[s]);
+          tc::umma_commit(&h_empty[s]);
+        }
+        __syncwarp();
       }
-      tc::umma_commit(&acc2_full);
+      if (tc::elect_one()) tc::umma_commit(&acc2_full);
+      __syncwarp();
     }
   } else {
     // =============================== epilogue ===============================

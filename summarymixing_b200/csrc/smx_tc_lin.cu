@@ -57,8 +57,7 @@ __device__ __forceinline__ float warp_column_sums(float* v, int lane) {
 
 template <int MODE>
 __global__ void __launch_bounds__(LIN_THREADS, 1) lin_kernel(const LinP p) {
-  extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~(uintptr_t)1023);
+  extern __shared__ __align__(1024) uint8_t smem[];  // no pointer arithmetic through integers: keeps LDS/STS addressing
   uint8_t* sA = smem;
   uint8_t* sW = smem + (size_t)128 * p.K * 2;
   __shared__ __align__(8) uint64_t full_bar[LIN_MAX_STAGES], empty_bar[LIN_MAX_STAGES], acc_full[2], acc_empty[2];
@@ -66,7 +65,8 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) lin_kernel(const LinP p) {
   __shared__ float red[2][2][128];   // [sum|sq][column half][row]   (LIN_OLN)
   __shared__ float colred[4][256];   // [quadrant][column]           (LIN_COLSUM)
 
-  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler (role dispatch below)
   // tile -> first row and number of valid rows (utterance-aligned tiles never straddle two utterances)
   int64_t row0;
   int nrows;
@@ -114,15 +114,30 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) lin_kernel(const LinP p) {
   // ---- prologue: x tile -> (LayerNorm) -> A operand ------------------------------------------------
   {
     const int nchunk = p.K / 8;  // 16-byte chunks per row
-    for (int r = warp; r < 128; r += LIN_THREADS / 32) {
-      const int64_t row = row0 + r;
+    constexpr int NW = LIN_THREADS / 32;
+    for (int rb = warp; rb < 128; rb += 4 * NW) {  // four rows per round trip to memory
+    uint4 rawb[4][2];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = rb + j * NW;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        const int ck = lane + 32 * c;
+        rawb[j][c] = make_uint4(0, 0, 0, 0);
+        if (ck < nchunk && r < nrows) rawb[j][c] = *reinterpret_cast<const uint4*>(p.x + (row0 + r) * p.ldx + ck * 8);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int r = rb + j * NW;
+      if (r >= 128) break;
       float v[2][8];
       const bool live = r < nrows;
 #pragma unroll
       for (int c = 0; c < 2; ++c) {
         const int ck = lane + 32 * c;
         if (ck < nchunk && live) {
-          uint4 raw = *reinterpret_cast<const uint4*>(p.x + row * p.ldx + ck * 8);
+          uint4 raw = rawb[j][c];
           const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
 #pragma unroll
           for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(h[e]); v[c][2 * e] = f.x; v[c][2 * e + 1] = f.y; }
@@ -175,19 +190,21 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) lin_kernel(const LinP p) {
         }
       }
     }
+    }
   }
   tc::fence_proxy_async();
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  const uint32_t tmem = tmem_base_s;
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
 
   if (warp == 8) {
     // =============================== producer ===============================
     if (lane == 0) produce(1 << 30);
   } else if (warp == 9) {
     // =============================== MMA issuer ===============================
-    if (lane == 0) {
+    // the whole warp walks the (warp-uniform) schedule; one elected lane issues tcgen05.mma / tcgen05.commit
+    {
       int s = 0, ph = 0;
       const uint32_t a0 = tc::smem_u32(sA), w0 = tc::smem_u32(sW);
       for (int i = 0; i < p.n_tiles; ++i) {
@@ -203,14 +220,18 @@ __global__ void __launch_bounds__(LIN_THREADS, 1) lin_kernel(const LinP p) {
           const uint32_t a_addr = a0 + kb * kblock_bytes(128);
           const uint32_t b_addr = w0 + s * p.stage_bytes + rel_lo * 128;
           const uint32_t d_addr = tmem + buf * NT + rel_lo;
+          if (tc::elect_one()) {
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks)
-            tc::umma_bf16(d_addr, tc::make_desc_sw128(a_addr + ks * 32), tc::make_desc_sw128(b_addr + ks * 32), idesc,
-                          (first && ks == 0) ? 0u : 1u);
-          tc::umma_commit(&empty_bar[s]);
+            for (int ks = 0; ks < 4; ++ks)
+              tc::umma_bf16(d_addr, tc::make_desc_sw128(a_addr + ks * 32), tc::make_desc_sw128(b_addr + ks * 32), idesc,
+                            (first && ks == 0) ? 0u : 1u);
+            tc::umma_commit(&empty_bar[s]);
+          }
+          __syncwarp();
           if (++s == p.n_stages) { s = 0; ph ^= 1; }
         }
-        tc::umma_commit(&acc_full[buf]);
+        if (tc::elect_one()) tc::umma_commit(&acc_full[buf]);
+        __syncwarp();
       }
     }
   } else {

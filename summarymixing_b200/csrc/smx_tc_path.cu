@@ -375,9 +375,107 @@ __global__ void __launch_bounds__(256) dwconv_ln_act_kernel(const __nv_bfloat16*
   }
 }
 
+// Tiled variant for kernel size K and D % 128 == 0, D <= 512.  A block takes 32 output frames of one utterance:
+// the (32 + K - 1) input frames are staged once in shared memory; phase 1 gives every thread one channel pair and
+// blocks of eight consecutive frames (taps and accumulators in registers: 8*K*2 FMAs per K+7 shared-memory loads);
+// phase 2 normalises each frame over the channels (one warp per frame) and applies the activation.
+constexpr int DWT_FRAMES = 32;
+template <int K>
+__global__ void __launch_bounds__(256) dwconv_tiled_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ dw_w,
+                                                           const float* __restrict__ dw_b, const float* __restrict__ ln_w,
+                                                           const float* __restrict__ ln_b, int act, int T, int D,
+                                                           __nv_bfloat16* __restrict__ out) {
+  constexpr int PAD = (K - 1) / 2, NIN = DWT_FRAMES + K - 1;
+  extern __shared__ __align__(16) uint8_t dsm[];
+  __nv_bfloat16* sIn = reinterpret_cast<__nv_bfloat16*>(dsm);                          // [NIN][D]
+  float* sOut = reinterpret_cast<float*>(dsm + (size_t)NIN * D * sizeof(__nv_bfloat16));  // [32][D]
+  const int b = blockIdx.y, t0 = blockIdx.x * DWT_FRAMES;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int cpr = D / 8;
+  for (int idx = tid; idx < NIN * cpr; idx += 256) {
+    const int row = idx / cpr, ch = idx - row * cpr, u = t0 - PAD + row;
+    uint4 val = make_uint4(0, 0, 0, 0);  // zero padding at the utterance edges (Conformer.py:142-151)
+    if (u >= 0 && u < T) val = *reinterpret_cast<const uint4*>(g + ((size_t)b * T + u) * D + ch * 8);
+    *reinterpret_cast<uint4*>(sIn + (size_t)row * D + ch * 8) = val;
+  }
+  __syncthreads();
+  {
+    const int pairs = D / 2, pr = tid % pairs, fb0 = tid / pairs, nfbp = 256 / pairs;
+    const int c0 = pr * 2;
+    float w0[K], w1[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) { w0[j] = dw_w[(size_t)c0 * K + j]; w1[j] = dw_w[(size_t)(c0 + 1) * K + j]; }
+    const float b0 = dw_b ? dw_b[c0] : 0.0f, b1 = dw_b ? dw_b[c0 + 1] : 0.0f;
+    for (int fb = fb0; fb < DWT_FRAMES / 8; fb += nfbp) {
+      float a0[8], a1[8];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) { a0[o] = b0; a1[o] = b1; }
+#pragma unroll
+      for (int i = 0; i < K + 7; ++i) {
+        const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sIn + (size_t)(fb * 8 + i) * D + c0));
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          const int j = i - o;
+          if (j >= 0 && j < K) { a0[o] = fmaf(w0[j], x.x, a0[o]); a1[o] = fmaf(w1[j], x.y, a1[o]); }
+        }
+      }
+#pragma unroll
+      for (int o = 0; o < 8; ++o) *reinterpret_cast<float2*>(sOut + (size_t)(fb * 8 + o) * D + c0) = make_float2(a0[o], a1[o]);
+    }
+  }
+  __syncthreads();
+  const int nseg = D / 128;  // a lane owns 4 channels in each 128-channel segment: conflict-free 16-byte accesses
+  const float invD = 1.0f / (float)D;
+  for (int f = warp; f < DWT_FRAMES; f += 8) {
+    const int t = t0 + f;
+    if (t >= T) break;
+    float v[4][4];
+    float s = 0.0f;
+#pragma unroll
+    for (int sg = 0; sg < 4; ++sg)
+      if (sg < nseg) {
+        const float4 x = *reinterpret_cast<const float4*>(sOut + (size_t)f * D + sg * 128 + lane * 4);
+        v[sg][0] = x.x; v[sg][1] = x.y; v[sg][2] = x.z; v[sg][3] = x.w;
+        s += (x.x + x.y) + (x.z + x.w);
+      }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s * invD;
+    float q = 0.0f;
+#pragma unroll
+    for (int sg = 0; sg < 4; ++sg)
+      if (sg < nseg) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) { const float d = v[sg][e] - mean; q = fmaf(d, d, q); }
+      }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = rsqrtf(q * invD + 1e-5f);
+#pragma unroll
+    for (int sg = 0; sg < 4; ++sg)
+      if (sg < nseg) {
+        const int c = sg * 128 + lane * 4;
+        const float4 lw = *reinterpret_cast<const float4*>(ln_w + c), lb = *reinterpret_cast<const float4*>(ln_b + c);
+        float o[4] = {(v[sg][0] - mean) * rstd * lw.x + lb.x, (v[sg][1] - mean) * rstd * lw.y + lb.y,
+                      (v[sg][2] - mean) * rstd * lw.z + lb.z, (v[sg][3] - mean) * rstd * lw.w + lb.w};
+        tc::act_apply<4>(act, o);
+        *reinterpret_cast<uint2*>(out + ((size_t)b * T + t) * D + c) = make_uint2(tc::pack_bf16x2(o[0], o[1]), tc::pack_bf16x2(o[2], o[3]));
+      }
+  }
+}
+
 int tc_dwconv_ln_act(const __nv_bfloat16* g, const float* dw_w, const float* dw_b, const float* ln_w,
                      const float* ln_b, int act, int B, int T, int D, int k, __nv_bfloat16* out, cudaStream_t st) {
   if (D % 8 || D > 512) return fail(SMX_ERR_UNSUPPORTED, "dwconv: D=%d", D);
+  if (k == 31 && D % 128 == 0) {
+    const size_t smem = (size_t)(DWT_FRAMES + 30) * D * 2 + (size_t)DWT_FRAMES * D * 4;
+    cudaError_t e = cudaFuncSetAttribute(dwconv_tiled_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(dwconv_tiled): %s", cudaGetErrorString(e));
+    dim3 grid((T + DWT_FRAMES - 1) / DWT_FRAMES, B);
+    dwconv_tiled_kernel<31><<<grid, 256, smem, st>>>(g, dw_w, dw_b, ln_w, ln_b, act, T, D, out);
+    count_launch();
+    return check_launch("dwconv_tiled_kernel");
+  }
   const size_t smem = (size_t)k * D * sizeof(float);
   cudaError_t e = cudaFuncSetAttribute(dwconv_ln_act_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(dwconv): %s", cudaGetErrorString(e));
