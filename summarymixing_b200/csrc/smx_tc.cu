@@ -169,5 +169,6 @@ extern "C" SMX_API int smx_debug_tc_gemm(int layout, int32_t M, int32_t N, int32
 // kernels; NULL switches tracing off.  Not thread-safe; diagnostics only.
 extern "C" SMX_API int smx_debug_set_trace(void* device_u64_buffer) {
   tc_set_trace(device_u64_buffer);
+  tc_set_trace_ffn(device_u64_buffer ? (char*)device_u64_buffer + 4096 : nullptr);  // entries 512..1023
   return SMX_OK;
 }

@@ -65,6 +65,14 @@ size_t tc_ffn_workspace_bytes(const smx_ffn_weights* w, int64_t rows);
 int tc_ffn_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t rows, const __nv_bfloat16* x,
                const float* oln_w, const float* oln_b, float oln_eps, __nv_bfloat16* y, Arena& ws, cudaStream_t st);
 
+// smx_tc_ffn2.cu: persistent K-FFN (preferred when supported)
+bool tc_ffn2_supported(const smx_ffn_weights* w);
+size_t tc_ffn2_packed_bytes(const smx_ffn_weights* w);
+int tc_ffn2_pack(const smx_ffn_weights* w, void* packed, cudaStream_t st);
+int tc_ffn2_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t rows, const __nv_bfloat16* x,
+                const float* oln_w, const float* oln_b, float oln_eps, __nv_bfloat16* y, cudaStream_t st);
+void tc_set_trace_ffn(void* p);
+
 bool tc_convmod_supported(const smx_convmod_weights* w, int chunk);
 size_t tc_convmod_packed_bytes(const smx_convmod_weights* w);
 int tc_convmod_pack(const smx_convmod_weights* w, void* packed, cudaStream_t st);

@@ -124,6 +124,28 @@ def test_conformer_layer_tc_vs_oracle(D, F, h):
     _check(y, y_or, f"conformer layer D={D}", abs_tol=4e-2, rel_tol=2e-2)
 
 
+def test_conformer_layer_persistent_bench_shape():
+    """One layer at the bench shape (B=32, T=1000: 250/256 tiles > 148 SMs, so every persistent kernel loops)."""
+    torch.manual_seed(21)
+    D = 256
+    m = S.ConformerEncoderLayer(D, 1024, 4, 31, attention_type="SummaryMixing", local_proj_hid_dim=[D],
+                                local_proj_out_dim=D, summary_hid_dim=[D]).eval()
+    _perturb(m, 21)
+    B, T = 32, 1000
+    g = torch.Generator().manual_seed(22)
+    x = torch.randn(B, T, D, generator=g).to(torch.bfloat16)
+    lens = torch.randint(500, T + 1, (B,), generator=g)
+    lens[0] = T
+    mask = torch.arange(T)[None] < lens[:, None]
+    y_or = O.conformer_layer(x.float(), dict(m.state_dict()), "", act="swish", src_key_padding_mask=mask)
+    with torch.no_grad():
+        m = m.to(DEV)
+        y = m(x.to(DEV), src_key_padding_mask=mask.to(DEV))[0]
+        y2 = m(x.to(DEV), src_key_padding_mask=mask.to(DEV))[0]
+    assert torch.equal(y, y2), "layer forward must be run-to-run deterministic"
+    _check(y, y_or, "conformer layer at the bench shape", abs_tol=4e-2, rel_tol=2e-2)
+
+
 def test_conformer_encoder_tc_vs_oracle_and_fp32_arm():
     """4 layers at D=256: the bf16 tensor-core arm vs the oracle, with the fp32 arm's error for reference."""
     torch.manual_seed(11)

@@ -1,0 +1,36 @@
+"""Timeline (clock64) of CTA 0 of the persistent FFN kernel at the bench shape (first call in a layer = ffn1)."""
+import os
+import sys
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+
+import summarymixing_b200 as S
+from summarymixing_b200 import _lib as L
+
+B, T, D = 32, 1000, 256
+dev = "cuda:0"
+torch.manual_seed(0)
+layer = S.ConformerEncoderLayer(D, 1024, 4, 31, attention_type="SummaryMixing", local_proj_hid_dim=[D],
+                                local_proj_out_dim=D, summary_hid_dim=[D]).eval().to(dev)
+x = torch.randn(B, T, D, device=dev).to(torch.bfloat16)
+mask = torch.ones(B, T, dtype=torch.bool, device=dev)
+buf = torch.zeros(1024, dtype=torch.int64, device=dev)
+with torch.no_grad():
+    for _ in range(3):
+        layer(x, src_key_padding_mask=mask)
+    torch.cuda.synchronize()
+    L.lib().smx_debug_set_trace(buf.data_ptr())
+    layer(x, src_key_padding_mask=mask)
+    torch.cuda.synchronize()
+    L.lib().smx_debug_set_trace(None)
+t = buf.cpu()[512:512 + 5 * 2 * 32].view(5, 2, 32)   # the last FFN call of the layer (ffn2, with output LayerNorm) wins
+roles = ["producer", "issuer", "prologue", "epi-g0", "epi-g1"]
+nz = t[t > 0]
+t0 = int(nz.min())
+for r in range(5):
+    for it in range(2):
+        ev = t[r, it]
+        if int(ev.max()) == 0:
+            continue
+        print(f"  {roles[r]:9s} it{it}: " + " ".join(f"{int(v) - t0:7d}" if int(v) else "      -" for v in ev[:13]))
