@@ -286,6 +286,9 @@ SMX_API int smx_debug_tc_gemm(int layout, int32_t M, int32_t N, int32_t K, const
 /* Timeline of CTA 0 of the fused persistent kernels: device buffer of >= 1024 uint64 (zeroed by the caller)
  * receiving clock64() stamps per warp role / tile / event; NULL switches tracing off.  Diagnostics only. */
 SMX_API int smx_debug_set_trace(void* device_u64_buffer);
+/* Thread-block cluster size (1, 2 or 4) of the persistent FFN kernel: CTAs of a cluster multicast weight blocks
+ * to each other.  Tuning / diagnostics. */
+SMX_API int smx_debug_set_ffn_cluster(int cluster_size);
 
 #ifdef __cplusplus
 }

@@ -113,6 +113,7 @@ _PROTOS = {
     "smx_chunk_mask": (_i, [_i, _i, _i, _vp, _vp]),
     "smx_debug_tc_gemm": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "smx_debug_set_trace": (_i, [_vp]),
+    "smx_debug_set_ffn_cluster": (_i, [_i]),
 }
 
 

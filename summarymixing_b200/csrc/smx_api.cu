@@ -149,6 +149,7 @@ size_t smx_summary_mixing_workspace_bytes(const smx_cell_weights* w, int dtype, 
   int Dout = w->mode == SMX_MODE_LITE ? w->summary_out_dim : w->merge.out_dim;
   cell_generic(w, B, T, nullptr, dtype, nullptr, sm, nullptr, dtype, nullptr, dtype, Dout, a, nullptr);
   size_t tc = (dtype == SMX_BF16 && w->packed) ? tc_cell_workspace_bytes(w, B, T) : 0;
+  if (tc && !has_sum_mask && tc_cell_supported(w, 0)) return tc;  // the tensor-core arm runs: only its scratch is needed
   return a.peak > tc ? a.peak : tc;
 }
 int smx_summary_mixing_fwd(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x,
@@ -199,6 +200,7 @@ int smx_conv_module_fwd(const smx_convmod_weights* w, int act, int dtype, int32_
 // ---- FFN -----------------------------------------------------------------------------------------
 size_t smx_ffn_workspace_bytes(const smx_ffn_weights* w, int dtype, int64_t rows) {
   if (!w || rows <= 0) return 0;
+  if (dtype == SMX_BF16 && w->packed && tc_ffn_supported(w)) return tc_ffn_workspace_bytes(w, rows);  // fused: no scratch
   Arena a(nullptr, 0, true);
   ffn_generic(w, 0, rows, nullptr, dtype, nullptr, nullptr, 0.f, nullptr, dtype, a, nullptr);
   return a.peak;

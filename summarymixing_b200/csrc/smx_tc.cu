@@ -172,3 +172,9 @@ extern "C" SMX_API int smx_debug_set_trace(void* device_u64_buffer) {
   tc_set_trace_ffn(device_u64_buffer ? (char*)device_u64_buffer + 4096 : nullptr);  // entries 512..1023
   return SMX_OK;
 }
+
+// tuning knob: thread-block cluster size (1, 2 or 4) of the persistent FFN kernel (weight multicast)
+extern "C" SMX_API int smx_debug_set_ffn_cluster(int cluster_size) {
+  tc_set_ffn_cluster(cluster_size);
+  return SMX_OK;
+}

@@ -33,6 +33,7 @@ struct Ffn2P {
   const float* ln_w; const float* ln_b; const float* b1; const float* b2;
   const float* oln_w; const float* oln_b; float oln_eps;
   int act;
+  int cl;                                  // thread-block cluster size (1, 2 or 4): weight blocks are multicast
   int gw2;                                 // GEMM2 column group width in 64-col chunks (1, 2 or 4; divides D/64)
   unsigned long long* trace;
   uint32_t off_h, off_ring, off_par, off_red;
@@ -69,9 +70,14 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ffn2_kernel(const Ffn2P p) {
   const int D = p.D, nkbD = D / 64, nj = p.F / F2_HC, nkbF = p.F / 64;
   const int act = ACT >= 0 ? ACT : p.act;
 
+  // Cluster of cl CTAs: every CTA fetches 1/cl of each weight block and multicasts it to all of them, so the L2
+  // (whose bandwidth is what bounds this kernel) serves each block once per cluster instead of once per CTA.
+  const int cl = p.cl;
+  const uint32_t crank = cl > 1 ? tc::cluster_ctarank() : 0u;
+  const uint16_t cmask = (uint16_t)((1u << cl) - 1u);
   if (warp == F2_PROD_WARP) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
-    for (int s = 0; s < F2_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < F2_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], (uint32_t)cl); }
     tc::mbar_init(&x_full, 4); tc::mbar_init(&x_free, 1); tc::mbar_init(&acc2_full, 1); tc::mbar_init(&epi_done, 8);
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&acc1_full[i], 1); tc::mbar_init(&acc1_empty[i], 8);
@@ -88,11 +94,19 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ffn2_kernel(const Ffn2P p) {
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (cl > 1) tc::cluster_sync();  // peers' barriers are initialised before any multicast / remote arrive
   tc::tc_fence_after();
   const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
   const uint32_t t_acc2 = tmem, t_acc1 = tmem + 256;  // acc1 buffers at +256 and +384
-  const int first_tile = blockIdx.x, tile_step = gridDim.x;
+  // cluster c takes tile groups c, c + n_clusters, ...; CTA rank r the r-th tile of the group.  All CTAs of a cluster
+  // run the same number of iterations (the ring protocol is collective); tiles past the end are empty (nrows <= 0).
+  const int first_base = (cl > 1 ? (int)tc::cluster_id_x() : (int)blockIdx.x) * cl;
+  const int base_step = (cl > 1 ? (int)tc::cluster_count_x() : (int)gridDim.x) * cl;
   const int gw2 = p.gw2, ng2 = nkbD / gw2;  // GEMM2 column groups
+  // CTAs walk the hidden chunks in rotated order so that at any moment different SMs ask the L2 for different weight
+  // blocks (all SMs fetching the same lines at once serialises on the L2 slices that hold them)
+  const int rot = (int)(blockIdx.x % (unsigned)nj);
+  auto chunk_of = [&](int j) { int c = j + rot; return c >= nj ? c - nj : c; };
 
   if (warp == F2_PROD_WARP) {
     // =============================== weight producer ===============================
@@ -108,17 +122,26 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ffn2_kernel(const Ffn2P p) {
           tc::mbar_wait(&empty_bar[s + u], ((pe >> (s + u)) & 1u) ^ 1u);
           pe ^= 1u << (s + u);
         }
-        tc::mbar_arrive_expect_tx(&full_bar[s], F2_BLOCK * gw);
-        for (int u = 0; u < gw; ++u)
-          tc::bulk_g2s(sRing + (size_t)(s + u) * F2_BLOCK, img + (size_t)((c0 + u) * nkb_img + kb) * F2_BLOCK, F2_BLOCK, &full_bar[s]);
+        tc::mbar_arrive_expect_tx(&full_bar[s], F2_BLOCK * gw);  // all slices of the step land here, whoever fetched them
+        for (int u = 0; u < gw; ++u) {
+          uint8_t* dst = sRing + (size_t)(s + u) * F2_BLOCK;
+          const uint8_t* src = img + (size_t)((c0 + u) * nkb_img + kb) * F2_BLOCK;
+          if (cl == 1) {
+            tc::bulk_g2s(dst, src, F2_BLOCK, &full_bar[s]);
+          } else {
+            const uint32_t slice = F2_BLOCK / (uint32_t)cl;
+            tc::bulk_g2s_multicast(dst + crank * slice, src + crank * slice, slice, &full_bar[s], cmask);
+          }
+        }
         s += gw;
       };
-      auto load_g1 = [&](int j) { for (int kb = 0; kb < nkbD; ++kb) load(p.w1, nkbD, 2 * j, 2, kb); };
+      auto load_g1 = [&](int j) { const int c = chunk_of(j); for (int kb = 0; kb < nkbD; ++kb) load(p.w1, nkbD, 2 * c, 2, kb); };
       auto load_g2 = [&](int j) {
+        const int c = chunk_of(j);
         for (int g = 0; g < ng2; ++g)
-          for (int u = 0; u < 2; ++u) load(p.w2, nkbF, g * gw2, gw2, 2 * j + u);
+          for (int u = 0; u < 2; ++u) load(p.w2, nkbF, g * gw2, gw2, 2 * c + u);
       };
-      for (int tile = first_tile; tile < p.n_tiles; tile += tile_step) {
+      for (int base = first_base; base < p.n_tiles; base += base_step) {
         load_g1(0);
         for (int j = 0; j < nj; ++j) {
           if (j + 1 < nj) load_g1(j + 1);
@@ -134,10 +157,14 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ffn2_kernel(const Ffn2P p) {
     const uint32_t x0 = tc::smem_u32(sX), h0 = tc::smem_u32(sH), r0 = tc::smem_u32(sRing);
     const uint32_t idesc1 = tc::make_idesc_bf16(128, F2_HC), idesc2 = tc::make_idesc_bf16(128, 64u * gw2);
     int it = 0;
+    int tr = -1;  // fine-grained trace cursor (chunk 2 of the first tile)
+    auto stamp = [&]() { if (tr >= 0 && tr < 40 && p.trace && blockIdx.x == 0 && lane == 0) p.trace[320 + tr] = clock64(); if (tr >= 0) ++tr; };
     auto step = [&](int gw, uint32_t a_addr, uint32_t d_addr, uint32_t idesc, bool first) {
       s = (s + gw - 1) & ~(gw - 1);
       if (s >= F2_STAGES) s = 0;
+      stamp();
       tc::mbar_wait(&full_bar[s], (pf >> s) & 1u);
+      stamp();
       pf ^= 1u << s;
       tc::tc_fence_after();
       const uint32_t b_addr = r0 + s * F2_BLOCK;
@@ -146,14 +173,19 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ffn2_kernel(const Ffn2P p) {
         for (int ks = 0; ks < 4; ++ks)
           tc::umma_bf16(d_addr, tc::make_desc_sw128(a_addr + ks * 32), tc::make_desc_sw128(b_addr + ks * 32), idesc,
                         (first && ks == 0) ? 0u : 1u);
-        for (int u = 0; u < gw; ++u) tc::umma_commit(&empty_bar[s + u]);
+        for (int u = 0; u < gw; ++u) {
+          if (cl == 1) tc::umma_commit(&empty_bar[s + u]);
+          else tc::umma_commit_multicast(&empty_bar[s + u], cmask);  // every CTA's producer waits for all consumers
+        }
       }
       __syncwarp();
       s += gw;
     };
     auto gemm1 = [&](int j) {  // acc1[j&1] = LN(x) @ W1[chunk j]^T
       const int bsel = j & 1;
+      stamp();
       tc::mbar_wait(&acc1_empty[bsel], ((ph_a1e >> bsel) & 1u) ^ 1u);
+      stamp();
       ph_a1e ^= 1u << bsel;
       tc::tc_fence_after();
       for (int kb = 0; kb < nkbD; ++kb) step(2, x0 + kb * kblock_bytes(128), t_acc1 + bsel * F2_HC, idesc1, kb == 0);
@@ -163,17 +195,20 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ffn2_kernel(const Ffn2P p) {
       }
       __syncwarp();
     };
-    for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
+    for (int base = first_base; base < p.n_tiles; base += base_step, ++it) {
       const uint32_t par = it & 1;
       tc::mbar_wait(&x_full, par);
       tc::tc_fence_after();
       F2_TRACE(1, it, 0);
       gemm1(0);
       for (int j = 0; j < nj; ++j) {
+        tr = (it == 0 && j == 2) ? 0 : -1;
         if (j + 1 < nj) gemm1(j + 1);
         const int bsel = j & 1;
         if (j == 0 && it > 0) tc::mbar_wait(&epi_done, par ^ 1);  // previous tile's output accumulator is drained
+        stamp();
         tc::mbar_wait(&h_full[bsel], (ph_hf >> bsel) & 1u);
+        stamp();
         ph_hf ^= 1u << bsel;
         tc::tc_fence_after();
         for (int g = 0; g < ng2; ++g)
@@ -198,8 +233,8 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ffn2_kernel(const Ffn2P p) {
     for (int e = 0; e < 8; ++e) { gw[e] = has ? p.ln_w[lane * 8 + e] : 1.0f; gb[e] = has ? p.ln_b[lane * 8 + e] : 0.0f; }
     const float invD = 1.0f / (float)D;
     int it = 0;
-    for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
-      const int64_t row0 = (int64_t)tile * 128;
+    for (int base = first_base; base < p.n_tiles; base += base_step, ++it) {
+      const int64_t row0 = (int64_t)(base + (int)crank) * 128;
       const int nrows = p.rows - row0 < 128 ? (int)(p.rows - row0) : 128;
       // Half of this warp's rows are fetched and normalised while the previous tile still owns X (they wait in
       // registers as packed bf16); the other half follows once X is released.
@@ -267,9 +302,9 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ffn2_kernel(const Ffn2P p) {
     const int cpr = D / 8;
     const int rr0 = etid / cpr, ch0 = etid - rr0 * cpr, drr = 256 / cpr, dch = 256 - drr * cpr;
     int it = 0;
-    for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
+    for (int base = first_base; base < p.n_tiles; base += base_step, ++it) {
       const uint32_t par = it & 1;
-      const int64_t row0 = (int64_t)tile * 128;
+      const int64_t row0 = (int64_t)(base + (int)crank) * 128;
       const int nrows = p.rows - row0 < 128 ? (int)(p.rows - row0) : 128;
       for (int j = 0; j < nj; ++j) {
         const int bsel = j & 1;
@@ -286,7 +321,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ffn2_kernel(const Ffn2P p) {
         if (lane == 0) tc::mbar_arrive(&acc1_empty[bsel]);
 #pragma unroll
         for (int pc = 0; pc < 2; ++pc) {
-          const float4* bp = reinterpret_cast<const float4*>(sPar + j * F2_HC + grp * 64 + pc * 32);
+          const float4* bp = reinterpret_cast<const float4*>(sPar + chunk_of(j) * F2_HC + grp * 64 + pc * 32);
 #pragma unroll
           for (int i = 0; i < 8; ++i) { const float4 bb = bp[i]; v[pc][4 * i] += bb.x; v[pc][4 * i + 1] += bb.y; v[pc][4 * i + 2] += bb.z; v[pc][4 * i + 3] += bb.w; }
           tc::act_apply<32>(act, v[pc]);
@@ -418,6 +453,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ffn2_kernel(const Ffn2P p) {
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (cl > 1) tc::cluster_sync();  // no CTA leaves while a peer may still multicast into it or arrive on its barriers
   if (warp == F2_PROD_WARP) tc::tmem_dealloc(tmem, 512);
 }
 
@@ -439,6 +475,8 @@ int tc_ffn2_pack(const smx_ffn_weights* w, void* packed, cudaStream_t st) {
   return tc_pack_linear_nt(w->w2, 0, F, 64, (char*)packed + align_up((size_t)D * F * 2, 1024), st);
 }
 
+static int g_ffn_cluster = 1;  // measured on B200: multicast clusters couple the CTAs' rings and run slower (85/101/120 us for 1/2/4)
+void tc_set_ffn_cluster(int cl) { g_ffn_cluster = (cl == 4 || cl == 2) ? cl : 1; }
 static unsigned long long* g_trace2 = nullptr;
 void tc_set_trace_ffn(void* p) { g_trace2 = (unsigned long long*)p; }
 
@@ -456,10 +494,17 @@ static int ffn2_sms() {
 template <bool OLN>
 static int launch_ffn2(const Ffn2P& p, unsigned grid, size_t smem, cudaStream_t st) {
   cudaError_t e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(F2_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)p.cl; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
 #define SMX_FFN2_LAUNCH(A)                                                                                   \
   e = cudaFuncSetAttribute(ffn2_kernel<OLN, A>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);     \
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(ffn2_kernel): %s", cudaGetErrorString(e)); \
-  ffn2_kernel<OLN, A><<<grid, F2_THREADS, smem, st>>>(p);
+  e = cudaLaunchKernelEx(&cfg, ffn2_kernel<OLN, A>, p);                                                      \
+  if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaLaunchKernelEx(ffn2_kernel): %s", cudaGetErrorString(e));
   switch (p.act) {
     case SMX_ACT_SWISH: SMX_FFN2_LAUNCH(SMX_ACT_SWISH); break;
     case SMX_ACT_GELU: SMX_FFN2_LAUNCH(SMX_ACT_GELU); break;
@@ -492,7 +537,12 @@ int tc_ffn2_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t r
   p.off_red = p.off_par + (uint32_t)align_up((size_t)(F + 768) * 4, 1024);
   const size_t smem = (size_t)p.off_red + 2048;
   if (smem > 227 * 1024 - 1024) return fail(SMX_ERR_UNSUPPORTED, "ffn: tile does not fit shared memory");
-  const unsigned grid = (unsigned)(p.n_tiles < ffn2_sms() ? p.n_tiles : ffn2_sms());
+  // cluster size: pairs (or quads) of CTAs share every weight block; single CTAs when there is too little work
+  p.cl = g_ffn_cluster;
+  while (p.cl > 1 && p.n_tiles < 2 * p.cl) p.cl >>= 1;
+  unsigned grid = (unsigned)(p.n_tiles < ffn2_sms() ? p.n_tiles : ffn2_sms());
+  grid = (grid + p.cl - 1) / p.cl * p.cl;
+  if ((int)grid > ffn2_sms()) grid = (unsigned)(ffn2_sms() / p.cl * p.cl);
   return oln_w ? launch_ffn2<true>(p, grid, smem, st) : launch_ffn2<false>(p, grid, smem, st);
 }
 

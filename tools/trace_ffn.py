@@ -34,3 +34,7 @@ for r in range(5):
         if int(ev.max()) == 0:
             continue
         print(f"  {roles[r]:9s} it{it}: " + " ".join(f"{int(v) - t0:7d}" if int(v) else "      -" for v in ev[:13]))
+
+fine = buf.cpu()[512 + 320:512 + 360]
+print("issuer, chunk 2 of tile 0 (gemm1(3): a1e-wait b/a, 4 x (full-wait b/a); h_full wait b/a; gemm2(2): 2 x (full-wait b/a)):")
+print("  " + " ".join(f"{int(v) - t0:7d}" if int(v) else "      -" for v in fine[:20]))
