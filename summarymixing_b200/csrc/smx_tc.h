@@ -34,7 +34,8 @@ enum { TC_LIN_PLAIN = 0, TC_LIN_GLU = 1, TC_LIN_OLN = 2, TC_LIN_COLSUM = 3 };
 bool tc_linear_supported(int K, int N);
 size_t tc_linear_packed_bytes(int K, int N);
 int tc_pack_linear(const smx_linear& L, int k_offset, int K, int glu, void* out, cudaStream_t st);
-int tc_pack_linear_nt(const smx_linear& L, int k_offset, int K, int NT, void* out, cudaStream_t st);  // explicit n-tile width
+int tc_pack_linear_nt(const smx_linear& L, int k_offset, int K, int NT, void* out, cudaStream_t st,
+                      int glu_interleave = 0);  // explicit n-tile width; value/gate 64-row blocks interleaved for GLU
 int tc_pick_nt(int N, int glu);
 int tc_linear_launch(LinP p, int mode, cudaStream_t st);
 
@@ -57,6 +58,14 @@ size_t tc_cellf_workspace_bytes(const smx_cell_weights* w, int B, int T);
 int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_s2, const void* img_f1, const void* img_f2,
                  const void* img_c, int B, int T, const __nv_bfloat16* x, const float* pre_ln_w, const float* pre_ln_b,
                  const uint8_t* mask, const __nv_bfloat16* residual, __nv_bfloat16* y, Arena& ws, cudaStream_t st);
+
+int tc_glu_fwd(const smx_linear& L, const void* img, const float* ln_w, const float* ln_b, int64_t rows,
+               const __nv_bfloat16* x, __nv_bfloat16* out, cudaStream_t st);
+
+// ---- smx_tc_conv.cu: K-CONV, depthwise conv + LN + act + output GEMM + mask/residual, persistent -------
+bool tc_convf_supported(const smx_convmod_weights* w, int chunk);
+int tc_convf_second_half(const smx_convmod_weights* w, const void* img_out, int act, int B, int T, const __nv_bfloat16* g,
+                         const uint8_t* mask, const __nv_bfloat16* residual, __nv_bfloat16* y, cudaStream_t st);
 
 bool tc_ffn_supported(const smx_ffn_weights* w);
 size_t tc_ffn_packed_bytes(const smx_ffn_weights* w);

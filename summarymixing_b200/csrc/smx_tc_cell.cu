@@ -52,7 +52,8 @@ struct CellFP {
   int B, T, tpu, n_tiles;
   int D;                                     // enc_dim
   CfGemm g[3];                               // A: s1, s2     B: f1, f2, combiner(local part)
-  const float* b1; const float* b2;          // biases of the two MLP blocks of this pass
+  const float* b1; const float* b2;          // biases of the two MLP blocks of this pass (GLU pass: value / gate halves)
+  int nb1, nb2;                              // their lengths (<= 256)
   const float* ln_w; const float* ln_b;      // A: summary_norm   B: local_norm      (NULL: no LayerNorm)
   const float* Wc; const float* bc; int Dl, Ds, Dout;   // merge weight (fp32, (Dout, Dl+Ds)) and bias
   int act;
@@ -192,17 +193,18 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
   float* sRed = reinterpret_cast<float*>(smem + p.off_red);   // 1024 floats: column partials / LN statistics / finalize
   __shared__ __align__(8) uint64_t full_bar[CF_MAX_STAGES], empty_bar[CF_MAX_STAGES];
   __shared__ __align__(8) uint64_t x_full, x_free, a2_full, epi_done;
-  __shared__ __align__(8) uint64_t acc1_full[4], a1_full[4], acc2_full[4], acc3_full[4];
+  __shared__ __align__(8) uint64_t acc1_full[8], a1_full[4], acc2_full[4], acc3_full[4];
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler (role dispatch below)
-  constexpr int NG = PHASE == 0 ? 2 : 3;
+  constexpr int NG = PHASE == 0 ? 2 : (PHASE == 1 ? 3 : 1);
 
   if (warp == CF_PROD_WARP) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int s = 0; s < p.n_stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     tc::mbar_init(&x_full, 4); tc::mbar_init(&x_free, 1); tc::mbar_init(&a2_full, 8); tc::mbar_init(&epi_done, 8);
+    for (int c = 4; c < 8; ++c) tc::mbar_init(&acc1_full[c], 1);
     for (int c = 0; c < 4; ++c) {
       tc::mbar_init(&acc1_full[c], 1); tc::mbar_init(&a1_full[c], 4);
       tc::mbar_init(&acc2_full[c], 1); tc::mbar_init(&acc3_full[c], 1);
@@ -210,10 +212,10 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
     tc::fence_barrier_init();
   }
   for (int i = tid; i < 256; i += CF_THREADS) {
-    sPar[i] = i < p.g[0].nc * 64 ? p.b1[i] : 0.0f;
-    sPar[256 + i] = i < p.g[1].nc * 64 ? p.b2[i] : 0.0f;
-    sPar[512 + i] = (p.ln_w && i < p.g[1].nc * 64) ? p.ln_w[i] : 1.0f;
-    sPar[768 + i] = (p.ln_b && i < p.g[1].nc * 64) ? p.ln_b[i] : 0.0f;
+    sPar[i] = i < p.nb1 ? p.b1[i] : 0.0f;
+    sPar[256 + i] = i < p.nb2 ? p.b2[i] : 0.0f;
+    sPar[512 + i] = (p.ln_w && i < p.nb2) ? p.ln_w[i] : 1.0f;
+    sPar[768 + i] = (p.ln_b && i < p.nb2) ? p.ln_b[i] : 0.0f;
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -270,6 +272,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
         const uint32_t idesc = tc::make_idesc_bf16(128, 64u * g.gw);
         if (gi == 0) {
           tc::mbar_wait(&x_full, par);
+          if (PHASE == 2 && it > 0) tc::mbar_wait(&epi_done, par ^ 1);  // the single accumulator set is drained
         } else if (gi == 1) {
           if (it > 0) tc::mbar_wait(&epi_done, par ^ 1);  // previous tile's accumulators in [256,512) are drained
         } else {
@@ -392,6 +395,55 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
       const bool live = r < nrows;
       const float rscale = live ? (p.mask ? (float)p.mask[row0 + r] : 1.0f) : 0.0f;
 
+      if (PHASE == 2) {
+        // ---- GLU pass: out = (acc[value] + b) * sigmoid(acc[gate] + b) -> staged tile -> coalesced stores
+        // (value / gate 64-column chunks are interleaved in the packed weight image: chunk 2c / 2c+1)     Conformer.py:322-324
+        const int npair = p.g[0].nc / 2;
+        for (int c = grp; c < npair; c += 2) {
+          tc::mbar_wait(&acc1_full[2 * c + 1], par);
+          tc::tc_fence_after();
+#pragma unroll
+          for (int pc = 0; pc < 2; ++pc) {
+            float v[32], gt[32];
+            tc::tmem_ld32(tmem + lane_sel + (2 * c) * 64 + pc * 32, v);
+            tc::tmem_ld32(tmem + lane_sel + (2 * c + 1) * 64 + pc * 32, gt);
+            tc::tmem_ld_wait();
+            const float4* ba = reinterpret_cast<const float4*>(sB1 + c * 64 + pc * 32);
+            const float4* bg = reinterpret_cast<const float4*>(sB2 + c * 64 + pc * 32);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 a4 = ba[j], g4 = bg[j];
+              v[4 * j] += a4.x; v[4 * j + 1] += a4.y; v[4 * j + 2] += a4.z; v[4 * j + 3] += a4.w;
+              gt[4 * j] += g4.x; gt[4 * j + 1] += g4.y; gt[4 * j + 2] += g4.z; gt[4 * j + 3] += g4.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] *= tc::act_sigmoid(gt[j]);
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              *reinterpret_cast<uint4*>(sY + (size_t)c * kblock_bytes(128) + tc::sw128_offset(r, pc * 4 + k)) = cf_pack8(v + 8 * k);
+          }
+        }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&epi_done);
+        tc::named_bar_sync(1, 256);
+        {
+          const int cpr = p.Dout / 8;
+          const int rr0 = etid / cpr, ch0 = etid - rr0 * cpr, drr = 256 / cpr, dch = 256 - drr * cpr;
+          int rr = rr0, ch = ch0;
+#pragma unroll 4
+          for (int k = 0; k < 16; ++k) {
+            if (rr < nrows) {
+              const uint4 val = *reinterpret_cast<const uint4*>(sY + (size_t)(ch >> 3) * kblock_bytes(128) + tc::sw128_offset(rr, ch & 7));
+              *reinterpret_cast<uint4*>(p.y + (row0 + rr) * p.ldy + ch * 8) = val;
+            }
+            rr += drr; ch += dch;
+            if (ch >= cpr) { ch -= cpr; ++rr; }
+          }
+        }
+        tc::named_bar_sync(1, 256);
+        continue;
+      }
       // ---- E1: hidden = act(acc1 + b1) -> A operand of the second GEMM (K-block c of Y)
       if (q == 0) CF_TRACE(3 + grp, it, 0);
       for (int c = grp; c < nc1; c += 2) {
@@ -722,7 +774,7 @@ int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
   {  // pass A
     p.g[0] = make_gemm(w->summary[0], img_s1, D);
     p.g[1] = make_gemm(w->summary[1], img_s2, w->summary[0].out_dim);
-    p.b1 = w->summary[0].b; p.b2 = w->summary[1].b;
+    p.b1 = w->summary[0].b; p.b2 = w->summary[1].b; p.nb1 = w->summary[0].out_dim; p.nb2 = w->summary[1].out_dim;
     p.ln_w = w->use_layernorm ? w->summary_norm_w : nullptr;
     p.ln_b = w->use_layernorm ? w->summary_norm_b : nullptr;
     const size_t smem = carve(w->summary[0].out_dim);
@@ -750,7 +802,7 @@ int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
     smx_linear mg = w->merge;
     mg.n_split = 1;
     p.g[2] = make_gemm(mg, img_c, Dl);
-    p.b1 = w->local[0].b; p.b2 = w->local[1].b;
+    p.b1 = w->local[0].b; p.b2 = w->local[1].b; p.nb1 = w->local[0].out_dim; p.nb2 = w->local[1].out_dim;
     p.ln_w = w->use_layernorm ? w->local_norm_w : nullptr;
     p.ln_b = w->use_layernorm ? w->local_norm_b : nullptr;
     int ycols = w->local[0].out_dim;
@@ -766,6 +818,38 @@ int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
   }
   ws.release(m0);
   return SMX_OK;
+}
+
+
+// GLU pass: out (rows, D) = value * sigmoid(gate), [value | gate] = LN(x) @ W^T + b with W (2D, D) packed with its
+// value / gate 64-row blocks interleaved (tc_pack_linear_nt(..., glu_interleave = 1)).          Conformer.py:322-324
+int tc_glu_fwd(const smx_linear& L, const void* img, const float* ln_w, const float* ln_b, int64_t rows,
+               const __nv_bfloat16* x, __nv_bfloat16* out, cudaStream_t st) {
+  const int D = L.in_dim;
+  if (L.out_dim != 2 * D || !dim_ok(D) || rows > 0x7fffffff) return fail(SMX_ERR_UNSUPPORTED, "glu pass: D=%d", D);
+  CellFP p{};
+  p.x = x; p.ldx = D; p.pre_w = ln_w; p.pre_b = ln_b;
+  p.y = out; p.ldy = D;
+  p.B = 1; p.T = (int)rows; p.tpu = (int)((rows + 127) / 128); p.n_tiles = p.tpu; p.D = D;
+  p.Dout = D; p.Dl = D; p.Ds = D;
+  smx_linear Ld = L;
+  Ld.n_split = 1;
+  p.g[0] = make_gemm(Ld, img, D);
+  p.b1 = L.b; p.b2 = L.b + D; p.nb1 = D; p.nb2 = D;
+  p.trace = nullptr;
+  const uint32_t xb = (uint32_t)(D / 64) * kblock_bytes(128);
+  p.off_y = xb;
+  p.off_ring = 2 * xb;
+  p.n_stages = 8;
+  p.off_par = p.off_ring + p.n_stages * CF_BLOCK_BYTES;
+  p.off_red = p.off_par + 8192;
+  const size_t smem = (size_t)p.off_red + 4096;
+  const unsigned grid = (unsigned)(p.n_tiles < num_sms() ? p.n_tiles : num_sms());
+  cudaError_t e = cudaFuncSetAttribute(cell_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(cell_kernel<2>): %s", cudaGetErrorString(e));
+  cell_kernel<2><<<grid, CF_THREADS, smem, st>>>(p);
+  count_tc_launch();
+  return check_launch("cell_kernel<2>");
 }
 
 }  // namespace smx

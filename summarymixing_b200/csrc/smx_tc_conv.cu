@@ -1,0 +1,352 @@
+// tcgen05 arm of libsmx, part 7: K-CONV, the second half of the ConvolutionModule fused into one persistent kernel
+//
+//   y = x + mask * ( W_out @ act( LN( dwconv_k(g) ) ) + b_out )                       Conformer.py:325-338, :543
+//
+// where g = GLU(W_bottleneck @ LN(x)) is produced by the GLU pass of the fused cell skeleton (smx_tc_cell.cu, PHASE 2).
+// One CTA per SM walks utterance-aligned 128-frame tiles:
+//   warps 0-7  (1) stage the (128 + k - 1) frames of g the tile needs in shared memory (zero rows outside the utterance:
+//                  the reference's zero padding, Conformer.py:142-151);
+//              (2) depthwise conv: a thread owns one channel pair and blocks of eight consecutive frames, taps and
+//                  accumulators in registers (8*k*2 FMAs per k+7 shared-memory loads); LayerNorm statistics per frame
+//                  by warp shuffles + one small shared-memory exchange; normalise, activate and write the bf16 A
+//                  operand (128B swizzle) for the tensor core;
+//              (4) epilogue of the output GEMM: + bias, * mask, + residual (parked in the idle g buffer with coalesced
+//                  loads issued while the GEMM runs), staged tile, coalesced stores
+//   warp 8     weight producer (8 KB blocks of W_out through a shared-memory ring, cp.async.bulk + mbarrier)
+//   warp 9     (3) MMA issuer: tcgen05.mma, N = up to 256 per instruction, accumulator in TMEM
+// The depthwise output, its LayerNorm and the activation never exist in global memory.
+#include "smx_tc.h"
+#include "smx_tc_common.cuh"
+
+namespace smx {
+
+using tc::kblock_bytes;
+
+constexpr int CV_THREADS = 320;
+constexpr int CV_PROD_WARP = 8, CV_MMA_WARP = 9;
+constexpr int CV_STAGES = 8;
+constexpr uint32_t CV_BLOCK = 8192;
+
+struct ConvFP {
+  const __nv_bfloat16* g;
+  const float* dw_w; const float* dw_b; const float* ln_w; const float* ln_b;
+  const uint8_t* w_img; const float* b_out;
+  const uint8_t* mask; const __nv_bfloat16* resid; __nv_bfloat16* y;
+  int B, T, D, tpu, n_tiles, act, gw;
+  uint32_t off_a, off_ring, off_par, off_stat;
+};
+
+__device__ __forceinline__ uint4 cv_pack8(const float* v) {
+  return make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]), tc::pack_bf16x2(v[6], v[7]));
+}
+__device__ __forceinline__ void cv_unpack8(const uint4& raw, float* v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+}
+
+template <int K, int ACT>
+__global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
+  constexpr int PAD = (K - 1) / 2, NIN = 128 + K - 1;
+  extern __shared__ __align__(1024) uint8_t smem[];
+  __nv_bfloat16* sG = reinterpret_cast<__nv_bfloat16*>(smem);   // [NIN][D] staged GLU output; later the residual/output tile
+  uint8_t* sStage = smem;
+  uint8_t* sA = smem + p.off_a;
+  uint8_t* sRing = smem + p.off_ring;
+  float* sPar = reinterpret_cast<float*>(smem + p.off_par);     // [b_out | ln_w | ln_b], 256 floats each
+  float* sStat = reinterpret_cast<float*>(smem + p.off_stat);   // [2][8 warps][8 frames][2]
+  __shared__ __align__(8) uint64_t full_bar[CV_STAGES], empty_bar[CV_STAGES], a_full, acc_full;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int D = p.D, nkb = D / 64, gw = p.gw, ng = nkb / gw;
+  const int act = ACT >= 0 ? ACT : p.act;
+
+  if (warp == CV_PROD_WARP) tc::tmem_alloc(&tmem_base_s, 256);
+  if (tid == 0) {
+    for (int s = 0; s < CV_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    tc::mbar_init(&a_full, 8); tc::mbar_init(&acc_full, 1);
+    tc::fence_barrier_init();
+  }
+  for (int i = tid; i < 256; i += CV_THREADS) {
+    sPar[i] = i < D ? p.b_out[i] : 0.0f;
+    sPar[256 + i] = i < D ? p.ln_w[i] : 1.0f;
+    sPar[512 + i] = i < D ? p.ln_b[i] : 0.0f;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+  const int first_tile = blockIdx.x, tile_step = gridDim.x;
+
+  if (warp == CV_PROD_WARP) {
+    // =============================== weight producer ===============================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t pe = 0;
+      for (int tile = first_tile; tile < p.n_tiles; tile += tile_step)
+        for (int j = 0; j < ng; ++j)
+          for (int kb = 0; kb < nkb; ++kb) {
+            s = (s + gw - 1) & ~(gw - 1);
+            if (s >= CV_STAGES) s = 0;
+            for (int u = 0; u < gw; ++u) {
+              tc::mbar_wait(&empty_bar[s + u], ((pe >> (s + u)) & 1u) ^ 1u);
+              pe ^= 1u << (s + u);
+            }
+            tc::mbar_arrive_expect_tx(&full_bar[s], CV_BLOCK * gw);
+            for (int u = 0; u < gw; ++u)
+              tc::bulk_g2s(sRing + (size_t)(s + u) * CV_BLOCK, p.w_img + (size_t)((j * gw + u) * nkb + kb) * CV_BLOCK, CV_BLOCK, &full_bar[s]);
+            s += gw;
+          }
+    }
+  } else if (warp == CV_MMA_WARP) {
+    // =============================== MMA issuer ===============================
+    int s = 0, it = 0;
+    uint32_t pf = 0;
+    const uint32_t a0 = tc::smem_u32(sA), r0 = tc::smem_u32(sRing);
+    const uint32_t idesc = tc::make_idesc_bf16(128, 64u * gw);
+    for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
+      tc::mbar_wait(&a_full, it & 1);  // also: the previous tile's accumulator has been drained (same warps, program order)
+      tc::tc_fence_after();
+      for (int j = 0; j < ng; ++j)
+        for (int kb = 0; kb < nkb; ++kb) {
+          s = (s + gw - 1) & ~(gw - 1);
+          if (s >= CV_STAGES) s = 0;
+          tc::mbar_wait(&full_bar[s], (pf >> s) & 1u);
+          pf ^= 1u << s;
+          tc::tc_fence_after();
+          const uint32_t a_addr = a0 + kb * kblock_bytes(128), b_addr = r0 + s * CV_BLOCK, d_addr = tmem + j * gw * 64;
+          if (tc::elect_one()) {
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+              tc::umma_bf16(d_addr, tc::make_desc_sw128(a_addr + ks * 32), tc::make_desc_sw128(b_addr + ks * 32), idesc,
+                            (kb == 0 && ks == 0) ? 0u : 1u);
+            for (int u = 0; u < gw; ++u) tc::umma_commit(&empty_bar[s + u]);
+          }
+          __syncwarp();
+          s += gw;
+        }
+      if (tc::elect_one()) tc::umma_commit(&acc_full);
+      __syncwarp();
+    }
+  } else {
+    // =============================== compute warps ===============================
+    const int q = warp & 3, grp = warp >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const int pairs = D / 2, pr = tid % pairs, fb0 = tid / pairs, nfbp = 256 / pairs, wpf = pairs / 32;
+    const int c0 = pr * 2;                      // this thread's channel pair
+    const int wig = (tid % pairs) >> 5;         // warp index inside its frame-block group
+    float w0[K], w1[K];
+#pragma unroll
+    for (int j = 0; j < K; ++j) { w0[j] = p.dw_w[(size_t)c0 * K + j]; w1[j] = p.dw_w[(size_t)(c0 + 1) * K + j]; }
+    const float bias0 = p.dw_b ? p.dw_b[c0] : 0.0f, bias1 = p.dw_b ? p.dw_b[c0 + 1] : 0.0f;
+    const float lw0 = sPar[256 + c0], lw1 = sPar[256 + c0 + 1], lb0 = sPar[512 + c0], lb1 = sPar[512 + c0 + 1];
+    const float invD = 1.0f / (float)D;
+    const int cpr = D / 8;
+    const int rr0 = tid / cpr, ch0 = tid - rr0 * cpr, drr = 256 / cpr, dch = 256 - drr * cpr;
+    uint32_t sp = 0;  // statistics buffer parity
+    int it = 0;
+    for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
+      const int b = tile / p.tpu, t0 = (tile % p.tpu) * 128;
+      const int64_t row0 = (int64_t)b * p.T + t0;
+      const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
+      // ---- (1) stage g[t0 - PAD, t0 + 128 + PAD) -----------------------------------------------------
+      for (int base = 0; base < NIN * cpr; base += 256 * 5) {
+        uint4 val[5];
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int idx = base + k * 256 + tid;
+          val[k] = make_uint4(0, 0, 0, 0);
+          if (idx < NIN * cpr) {
+            const int row = idx / cpr, ch = idx - row * cpr, u = t0 - PAD + row;
+            if (u >= 0 && u < p.T) val[k] = *reinterpret_cast<const uint4*>(p.g + ((int64_t)b * p.T + u) * D + ch * 8);
+          }
+        }
+#pragma unroll
+        for (int k = 0; k < 5; ++k) {
+          const int idx = base + k * 256 + tid;
+          if (idx < NIN * cpr) *reinterpret_cast<uint4*>(sG + (size_t)idx * 8) = val[k];
+        }
+      }
+      tc::named_bar_sync(1, 256);
+      // ---- (2) depthwise conv -> LayerNorm -> activation -> A operand --------------------------------
+      for (int fb = fb0; fb < 16; fb += nfbp) {
+        float a0[8], a1[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) { a0[o] = bias0; a1[o] = bias1; }
+#pragma unroll
+        for (int i = 0; i < K + 7; ++i) {
+          const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sG + (size_t)(fb * 8 + i) * D + c0));
+#pragma unroll
+          for (int o = 0; o < 8; ++o) {
+            const int j = i - o;
+            if (j >= 0 && j < K) { a0[o] = fmaf(w0[j], x.x, a0[o]); a1[o] = fmaf(w1[j], x.y, a1[o]); }
+          }
+        }
+        // per-frame statistics over the D channels: this thread's pair -> warp -> the group's warps
+        float ps[8], pq[8];
+#pragma unroll
+        for (int o = 0; o < 8; ++o) { ps[o] = a0[o] + a1[o]; pq[o] = fmaf(a0[o], a0[o], a1[o] * a1[o]); }
+#pragma unroll
+        for (int sh = 16; sh; sh >>= 1)
+#pragma unroll
+          for (int o = 0; o < 8; ++o) { ps[o] += __shfl_xor_sync(0xffffffffu, ps[o], sh); pq[o] += __shfl_xor_sync(0xffffffffu, pq[o], sh); }
+        float* st = sStat + (size_t)sp * 128;
+        if (lane == 0) {
+#pragma unroll
+          for (int o = 0; o < 8; ++o) { st[(warp * 8 + o) * 2] = ps[o]; st[(warp * 8 + o) * 2 + 1] = pq[o]; }
+        }
+        if (wpf > 1) tc::named_bar_sync(2 + fb0, wpf * 32); else __syncwarp();
+        const int wbase = warp - wig;  // first warp of this group
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          float s1 = 0.0f, s2 = 0.0f;
+          for (int w = 0; w < wpf; ++w) { s1 += st[((wbase + w) * 8 + o) * 2]; s2 += st[((wbase + w) * 8 + o) * 2 + 1]; }
+          const float mean = s1 * invD;
+          const float var = fmaxf(s2 * invD - mean * mean, 0.0f);
+          const float rstd = rsqrtf(var + 1e-5f);
+          float v[2] = {(a0[o] - mean) * rstd * lw0 + lb0, (a1[o] - mean) * rstd * lw1 + lb1};
+          tc::act_apply<2>(act, v);
+          const int row = fb * 8 + o;
+          *reinterpret_cast<uint32_t*>(sA + (size_t)(c0 >> 6) * kblock_bytes(128) + tc::sw128_offset(row, (c0 & 63) >> 3) + (c0 & 7) * 2) =
+              tc::pack_bf16x2(v[0], v[1]);
+        }
+        sp ^= 1u;
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&a_full);
+      // ---- (4) epilogue of the output GEMM -----------------------------------------------------------
+      uint4 rres[16];
+      {
+        int rr = rr0, ch = ch0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          rres[k] = make_uint4(0, 0, 0, 0);
+          if (p.resid && rr < nrows) rres[k] = *reinterpret_cast<const uint4*>(p.resid + (row0 + rr) * D + ch * 8);
+          rr += drr; ch += dch;
+          if (ch >= cpr) { ch -= cpr; ++rr; }
+        }
+      }
+      tc::named_bar_sync(1, 256);  // every warp has finished reading the staged g tile
+      {
+        int rr = rr0, ch = ch0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) {
+          if (rr < 128) *reinterpret_cast<uint4*>(sStage + (size_t)(ch >> 3) * kblock_bytes(128) + tc::sw128_offset(rr, ch & 7)) = rres[k];
+          rr += drr; ch += dch;
+          if (ch >= cpr) { ch -= cpr; ++rr; }
+        }
+      }
+      const bool live = r < nrows;
+      const float rscale = live ? (p.mask ? (float)p.mask[row0 + r] : 1.0f) : 0.0f;
+      tc::mbar_wait(&acc_full, it & 1);
+      tc::tc_fence_after();
+      tc::named_bar_sync(1, 256);
+      for (int c = grp; c < nkb; c += 2) {
+#pragma unroll
+        for (int pc = 0; pc < 2; ++pc) {
+          const int col = c * 64 + pc * 32;
+          float v[32];
+          tc::tmem_ld32(tmem + lane_sel + col, v);
+          tc::tmem_ld_wait();
+          const float4* bp = reinterpret_cast<const float4*>(sPar + col);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            uint4* spp = reinterpret_cast<uint4*>(sStage + (size_t)c * kblock_bytes(128) + tc::sw128_offset(r, pc * 4 + k));
+            float f[8];
+            cv_unpack8(*spp, f);
+            const float4 ba = bp[2 * k], bb = bp[2 * k + 1];
+            const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[8 * k + e] = fmaf(v[8 * k + e] + bv[e], rscale, f[e]);  // out*mask (:338) then x + out (:543)
+            *spp = cv_pack8(v + 8 * k);
+          }
+        }
+      }
+      tc::tc_fence_before();
+      tc::named_bar_sync(1, 256);
+      {
+        int rr = rr0, ch = ch0;
+#pragma unroll 4
+        for (int k = 0; k < 16; ++k) {
+          if (rr < nrows) {
+            const uint4 val = *reinterpret_cast<const uint4*>(sStage + (size_t)(ch >> 3) * kblock_bytes(128) + tc::sw128_offset(rr, ch & 7));
+            *reinterpret_cast<uint4*>(p.y + (row0 + rr) * D + ch * 8) = val;
+          }
+          rr += drr; ch += dch;
+          if (ch >= cpr) { ch -= cpr; ++rr; }
+        }
+      }
+      tc::named_bar_sync(1, 256);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == CV_PROD_WARP) tc::tmem_dealloc(tmem, 256);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+bool tc_convf_supported(const smx_convmod_weights* w, int chunk) {
+  const int D = w->bottleneck.in_dim;
+  if (chunk > 0 || w->causal) return false;
+  if (w->kernel_size != 31) return false;
+  if (D != 64 && D != 128 && D != 256) return false;
+  if (w->bottleneck.out_dim != 2 * D || w->out.in_dim != D || w->out.out_dim != D) return false;
+  if (w->bottleneck.n_split > 1 || w->out.n_split > 1) return false;
+  if (!w->bottleneck.w || !w->bottleneck.b || !w->out.w || !w->out.b || !w->dw_w || !w->ln_w || !w->ln_b || !w->after_ln_w ||
+      !w->after_ln_b)
+    return false;
+  return true;
+}
+
+static int convf_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <int ACT>
+static int launch_conv(const ConvFP& p, unsigned grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(conv_kernel<31, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(conv_kernel): %s", cudaGetErrorString(e));
+  conv_kernel<31, ACT><<<grid, CV_THREADS, smem, st>>>(p);
+  count_tc_launch();
+  return check_launch("conv_kernel");
+}
+
+// g: GLU output (B,T,D) bf16; img_out: packed after_conv.2 weight (64 x 64 blocks)
+int tc_convf_second_half(const smx_convmod_weights* w, const void* img_out, int act, int B, int T, const __nv_bfloat16* g,
+                         const uint8_t* mask, const __nv_bfloat16* residual, __nv_bfloat16* y, cudaStream_t st) {
+  const int D = w->bottleneck.in_dim;
+  ConvFP p{};
+  p.g = g; p.dw_w = w->dw_w; p.dw_b = w->dw_b; p.ln_w = w->after_ln_w; p.ln_b = w->after_ln_b;
+  p.w_img = (const uint8_t*)img_out; p.b_out = w->out.b; p.mask = mask; p.resid = residual; p.y = y;
+  p.B = B; p.T = T; p.D = D; p.tpu = (T + 127) / 128; p.n_tiles = B * p.tpu; p.act = act;
+  const int nkb = D / 64;
+  p.gw = nkb % 4 == 0 ? 4 : (nkb % 2 == 0 ? 2 : 1);
+  const size_t gbytes = align_up((size_t)(128 + 30) * D * 2, 1024), stage = (size_t)nkb * kblock_bytes(128);
+  p.off_a = (uint32_t)(gbytes > stage ? gbytes : stage);
+  p.off_ring = p.off_a + (uint32_t)stage;
+  p.off_par = p.off_ring + CV_STAGES * CV_BLOCK;
+  p.off_stat = p.off_par + 3072;
+  const size_t smem = (size_t)p.off_stat + 1024;
+  const unsigned grid = (unsigned)(p.n_tiles < convf_sms() ? p.n_tiles : convf_sms());
+  switch (act) {
+    case SMX_ACT_SWISH: return launch_conv<SMX_ACT_SWISH>(p, grid, smem, st);
+    case SMX_ACT_GELU: return launch_conv<SMX_ACT_GELU>(p, grid, smem, st);
+    case SMX_ACT_RELU: return launch_conv<SMX_ACT_RELU>(p, grid, smem, st);
+    default: return launch_conv<-1>(p, grid, smem, st);
+  }
+}
+
+}  // namespace smx

@@ -399,12 +399,14 @@ bool tc_linear_supported(int K, int N) { return K >= 64 && K <= 512 && K % 64 ==
 size_t tc_linear_packed_bytes(int K, int N) { return (size_t)N * (size_t)K * 2; }
 
 // block-diagonal aware gather: element (n,k) of the dense (N x K) view of an smx_linear
+// glu_il: image row block 2c holds value rows [64c, 64c+64), block 2c+1 the gate rows [N/2 + 64c, ...) (NT == 64)
 __global__ void pack_linear_kernel(const float* w, int in_dim, int out_dim, int n_split, int k_offset, int K, int N,
-                                   int NT, __nv_bfloat16* out) {
+                                   int NT, __nv_bfloat16* out, int glu_il = 0) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   const int chunks_per_row = K / 8;
   if (i >= (int64_t)N * chunks_per_row) return;
-  const int n = (int)(i / chunks_per_row), ck = (int)(i % chunks_per_row);
+  const int n_img = (int)(i / chunks_per_row), ck = (int)(i % chunks_per_row);
+  const int n = glu_il ? ((n_img / 64) & 1) * (N / 2) + (n_img / 128) * 64 + (n_img % 64) : n_img;
   float f[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) {
@@ -419,7 +421,7 @@ __global__ void pack_linear_kernel(const float* w, int in_dim, int out_dim, int 
     }
     f[e] = val;
   }
-  const int tile = n / NT, r = n % NT, kb = ck / 8, c16 = ck % 8;
+  const int tile = n_img / NT, r = n_img % NT, kb = ck / 8, c16 = ck % 8;
   const size_t off = ((size_t)tile * (K / 64) + kb) * kblock_bytes(NT) + tc::sw128_offset(r, c16);
   *reinterpret_cast<uint4*>(reinterpret_cast<char*>(out) + off) =
       make_uint4(tc::pack_bf16x2(f[0], f[1]), tc::pack_bf16x2(f[2], f[3]), tc::pack_bf16x2(f[4], f[5]), tc::pack_bf16x2(f[6], f[7]));
@@ -437,12 +439,13 @@ int tc_pack_linear(const smx_linear& L, int k_offset, int K, int glu, void* out,
   return check_launch("pack_linear_kernel");
 }
 
-int tc_pack_linear_nt(const smx_linear& L, int k_offset, int K, int NT, void* out, cudaStream_t st) {
+int tc_pack_linear_nt(const smx_linear& L, int k_offset, int K, int NT, void* out, cudaStream_t st, int glu_interleave) {
   const int N = L.out_dim;
   if (K % 64 || N % NT || NT % 8) return fail(SMX_ERR_UNSUPPORTED, "tc pack: K=%d N=%d NT=%d not supported", K, N, NT);
+  if (glu_interleave && (NT != 64 || N % 128)) return fail(SMX_ERR_UNSUPPORTED, "tc pack: GLU interleave needs NT=64, N%%128==0");
   int64_t n = (int64_t)N * (K / 8);
   pack_linear_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L.w, L.in_dim, L.out_dim, L.n_split, k_offset, K, N, NT,
-                                                                  (__nv_bfloat16*)out);
+                                                                  (__nv_bfloat16*)out, glu_interleave);
   count_launch();
   return check_launch("pack_linear_kernel");
 }

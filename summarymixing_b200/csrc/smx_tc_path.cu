@@ -284,6 +284,10 @@ size_t tc_convmod_packed_bytes(const smx_convmod_weights* w) {
 int tc_convmod_pack(const smx_convmod_weights* w, void* packed, cudaStream_t st) {
   if (!tc_convmod_supported(w, 0)) return fail(SMX_ERR_UNSUPPORTED, "conv module not handled by the tensor-core arm");
   const int D = w->bottleneck.in_dim;
+  if (tc_convf_supported(w, 0)) {  // fused path: 64 x 64 blocks, value/gate blocks interleaved for the GLU pass
+    SMX_TRY(tc_pack_linear_nt(w->bottleneck, 0, D, 64, packed, st, 1));
+    return tc_pack_linear_nt(w->out, 0, D, 64, (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)), st);
+  }
   SMX_TRY(tc_pack_linear(w->bottleneck, 0, D, 1, packed, st));
   SMX_TRY(tc_pack_linear(w->out, 0, D, 0, (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)), st));
   return SMX_OK;
@@ -491,6 +495,15 @@ int tc_convmod_fwd(const smx_convmod_weights* w, const void* packed, int act, in
   const int64_t rows = (int64_t)B * T;
   const size_t m0 = ws.mark();
   if (ws.dry) { ws.take(tc_convmod_workspace_bytes(w, B, T)); ws.release(m0); return SMX_OK; }
+  if (tc_convf_supported(w, 0)) {
+    __nv_bfloat16* gb = (__nv_bfloat16*)ws.take((size_t)rows * D * 2);
+    if (!gb) return fail(SMX_ERR_WORKSPACE, "workspace too small (tc conv module)");
+    SMX_TRY(tc_glu_fwd(w->bottleneck, packed, w->ln_w, w->ln_b, rows, x, gb, st));                       // :322-324
+    SMX_TRY(tc_convf_second_half(w, (const char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)), act, B, T, gb, mask,
+                                 residual, y, st));                                                        // :325-338, :543
+    ws.release(m0);
+    return SMX_OK;
+  }
   __nv_bfloat16* g = (__nv_bfloat16*)ws.take((size_t)rows * D * 2);
   __nv_bfloat16* c = (__nv_bfloat16*)ws.take((size_t)rows * D * 2);
   if (!g || !c) return fail(SMX_ERR_WORKSPACE, "workspace too small (tc conv module)");
