@@ -81,6 +81,7 @@ int tc_ffn2_pack(const smx_ffn_weights* w, void* packed, cudaStream_t st);
 int tc_ffn2_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t rows, const __nv_bfloat16* x,
                 const float* oln_w, const float* oln_b, float oln_eps, __nv_bfloat16* y, cudaStream_t st);
 void tc_set_trace_ffn(void* p);
+void tc_set_trace_conv(void* p);
 void tc_set_ffn_cluster(int cl);  // 1, 2 or 4 CTAs share each weight block (diagnostics / tuning)
 
 bool tc_convmod_supported(const smx_convmod_weights* w, int chunk);

@@ -26,11 +26,12 @@ namespace smx {
 
 using tc::kblock_bytes;
 
-constexpr int CF_THREADS = 448;      // 14 warps
+constexpr int CF_THREADS = 448;      // 14 warps (measured: 4 prologue warps beat 2 even with a 128-register cap)
 // Warp roles.  The SM's warp arbiter favours the highest warp id among eligible warps, so the two single-thread,
 // latency-critical roles (MMA issuer, weight producer) sit in the top warps and the bulk math below them.
 constexpr int CF_EPI_WARP0 = 0;      // warps 0..7   epilogue
 constexpr int CF_PRO_WARP0 = 8;      // warps 8..11  prologue
+constexpr int CF_NPW = 4;            // prologue warps, 128 / CF_NPW rows each
 constexpr int CF_PROD_WARP = 12;     // weight producer (also owns the TMEM allocation)
 constexpr int CF_MMA_WARP = 13;      // MMA issuer
 constexpr int CF_MAX_STAGES = 12;     // ring slots (a multiple of 4 is used)
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
   if (warp == CF_PROD_WARP) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int s = 0; s < p.n_stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    tc::mbar_init(&x_full, 4); tc::mbar_init(&x_free, 1); tc::mbar_init(&a2_full, 8); tc::mbar_init(&epi_done, 8);
+    tc::mbar_init(&x_full, CF_NPW); tc::mbar_init(&x_free, 1); tc::mbar_init(&a2_full, 8); tc::mbar_init(&epi_done, 8);
     for (int c = 4; c < 8; ++c) tc::mbar_init(&acc1_full[c], 1);
     for (int c = 0; c < 4; ++c) {
       tc::mbar_init(&acc1_full[c], 1); tc::mbar_init(&a1_full[c], 4);
@@ -335,17 +336,17 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
       if (it > 0) tc::mbar_wait(&x_free, (it - 1) & 1);
       if (pw == 0) CF_TRACE(2, it, 0);
 #pragma unroll 1
-      for (int r8 = 0; r8 < 32; r8 += 8) {
+      for (int r8 = 0; r8 < 128 / CF_NPW; r8 += 8) {
         uint4 raw[8];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int r = pw * 32 + r8 + j;
+          const int r = pw * (128 / CF_NPW) + r8 + j;
           raw[j] = make_uint4(0, 0, 0, 0);
           if (has && r < nrows) raw[j] = *reinterpret_cast<const uint4*>(p.x + (row0 + r) * p.ldx + lane * 8);
         }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-          const int r = pw * 32 + r8 + j;
+          const int r = pw * (128 / CF_NPW) + r8 + j;
           float v[8];
           cf_unpack8(raw[j], v);
           if (p.pre_w) {

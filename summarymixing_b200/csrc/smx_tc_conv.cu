@@ -33,6 +33,7 @@ struct ConvFP {
   const uint8_t* w_img; const float* b_out;
   const uint8_t* mask; const __nv_bfloat16* resid; __nv_bfloat16* y;
   int B, T, D, tpu, n_tiles, act, gw;
+  unsigned long long* trace;
   uint32_t off_a, off_ring, off_par, off_stat;
 };
 
@@ -44,6 +45,11 @@ __device__ __forceinline__ void cv_unpack8(const uint4& raw, float* v) {
 #pragma unroll
   for (int e = 0; e < 4; ++e) { float2 f = __bfloat1622float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
 }
+
+#define CV_TRACE(it, ev)                                                                                  \
+  do {                                                                                                    \
+    if (p.trace && blockIdx.x == 0 && tid == 0 && (it) < 4) p.trace[(it) * 16 + (ev)] = clock64();          \
+  } while (0)
 
 template <int K, int ACT>
 __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
@@ -152,25 +158,17 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
       const int b = tile / p.tpu, t0 = (tile % p.tpu) * 128;
       const int64_t row0 = (int64_t)b * p.T + t0;
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
+      CV_TRACE(it, 0);
       // ---- (1) stage g[t0 - PAD, t0 + 128 + PAD) -----------------------------------------------------
-      for (int base = 0; base < NIN * cpr; base += 256 * 5) {
-        uint4 val[5];
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const int idx = base + k * 256 + tid;
-          val[k] = make_uint4(0, 0, 0, 0);
-          if (idx < NIN * cpr) {
-            const int row = idx / cpr, ch = idx - row * cpr, u = t0 - PAD + row;
-            if (u >= 0 && u < p.T) val[k] = *reinterpret_cast<const uint4*>(p.g + ((int64_t)b * p.T + u) * D + ch * 8);
-          }
-        }
-#pragma unroll
-        for (int k = 0; k < 5; ++k) {
-          const int idx = base + k * 256 + tid;
-          if (idx < NIN * cpr) *reinterpret_cast<uint4*>(sG + (size_t)idx * 8) = val[k];
-        }
+      for (int idx = tid; idx < NIN * cpr; idx += 256) {
+        const int row = idx / cpr, ch = idx - row * cpr, u = t0 - PAD + row;
+        const bool in = u >= 0 && u < p.T;
+        tc::cp_async16(sG + (size_t)idx * 8, in ? (const void*)(p.g + ((int64_t)b * p.T + u) * D + ch * 8) : (const void*)p.g, in ? 16u : 0u);
       }
+      tc::cp_async_commit();
+      tc::cp_async_wait_all();
       tc::named_bar_sync(1, 256);
+      CV_TRACE(it, 1);
       // ---- (2) depthwise conv -> LayerNorm -> activation -> A operand --------------------------------
       for (int fb = fb0; fb < 16; fb += nfbp) {
         float a0[8], a1[8];
@@ -186,17 +184,26 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
           }
         }
         // per-frame statistics over the D channels: this thread's pair -> warp -> the group's warps
-        float ps[8], pq[8];
+        // 16 partial sums (8 frames x {sum, sum of squares}) reduced over the warp with a halving butterfly: 16 shuffles
+        // instead of 80; lane l (even) ends with the warp total of value (l >> 1)
+        float pv[16];
 #pragma unroll
-        for (int o = 0; o < 8; ++o) { ps[o] = a0[o] + a1[o]; pq[o] = fmaf(a0[o], a0[o], a1[o] * a1[o]); }
+        for (int o = 0; o < 8; ++o) { pv[o] = a0[o] + a1[o]; pv[8 + o] = fmaf(a0[o], a0[o], a1[o] * a1[o]); }
 #pragma unroll
-        for (int sh = 16; sh; sh >>= 1)
+        for (int sh = 16, n = 8; sh >= 2; sh >>= 1, n >>= 1) {
+          const bool up = (lane & sh) != 0;
 #pragma unroll
-          for (int o = 0; o < 8; ++o) { ps[o] += __shfl_xor_sync(0xffffffffu, ps[o], sh); pq[o] += __shfl_xor_sync(0xffffffffu, pq[o], sh); }
+          for (int j = 0; j < n; ++j) {
+            const float send = up ? pv[j] : pv[j + n];
+            const float keepv = up ? pv[j + n] : pv[j];
+            pv[j] = keepv + __shfl_xor_sync(0xffffffffu, send, sh);
+          }
+        }
+        pv[0] += __shfl_xor_sync(0xffffffffu, pv[0], 1);
         float* st = sStat + (size_t)sp * 128;
-        if (lane == 0) {
-#pragma unroll
-          for (int o = 0; o < 8; ++o) { st[(warp * 8 + o) * 2] = ps[o]; st[(warp * 8 + o) * 2 + 1] = pq[o]; }
+        if ((lane & 1) == 0) {  // value index = lane bits 4..1: bit 4 selects {sum, sumsq}, bits 3..1 the frame
+          const int vi = lane >> 1;
+          st[(warp * 8 + (vi & 7)) * 2 + (vi >> 3)] = pv[0];
         }
         if (wpf > 1) tc::named_bar_sync(2 + fb0, wpf * 32); else __syncwarp();
         const int wbase = warp - wig;  // first warp of this group
@@ -218,32 +225,30 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&a_full);
+      CV_TRACE(it, 2);
       // ---- (4) epilogue of the output GEMM -----------------------------------------------------------
-      uint4 rres[16];
-      {
-        int rr = rr0, ch = ch0;
-#pragma unroll
-        for (int k = 0; k < 16; ++k) {
-          rres[k] = make_uint4(0, 0, 0, 0);
-          if (p.resid && rr < nrows) rres[k] = *reinterpret_cast<const uint4*>(p.resid + (row0 + rr) * D + ch * 8);
-          rr += drr; ch += dch;
-          if (ch >= cpr) { ch -= cpr; ++rr; }
-        }
-      }
       tc::named_bar_sync(1, 256);  // every warp has finished reading the staged g tile
-      {
+      CV_TRACE(it, 3);
+      {  // the residual tile goes straight to shared memory (swizzled staging layout) while the output GEMM runs
         int rr = rr0, ch = ch0;
-#pragma unroll
+#pragma unroll 4
         for (int k = 0; k < 16; ++k) {
-          if (rr < 128) *reinterpret_cast<uint4*>(sStage + (size_t)(ch >> 3) * kblock_bytes(128) + tc::sw128_offset(rr, ch & 7)) = rres[k];
+          if (rr < 128) {
+            const bool in = p.resid && rr < nrows;
+            tc::cp_async16(sStage + (size_t)(ch >> 3) * kblock_bytes(128) + tc::sw128_offset(rr, ch & 7),
+                           in ? (const void*)(p.resid + (row0 + rr) * D + ch * 8) : (const void*)p.g, in ? 16u : 0u);
+          }
           rr += drr; ch += dch;
           if (ch >= cpr) { ch -= cpr; ++rr; }
         }
+        tc::cp_async_commit();
       }
       const bool live = r < nrows;
       const float rscale = live ? (p.mask ? (float)p.mask[row0 + r] : 1.0f) : 0.0f;
       tc::mbar_wait(&acc_full, it & 1);
       tc::tc_fence_after();
+      tc::cp_async_wait_all();
+      CV_TRACE(it, 4);
       tc::named_bar_sync(1, 256);
       for (int c = grp; c < nkb; c += 2) {
 #pragma unroll
@@ -268,6 +273,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
       }
       tc::tc_fence_before();
       tc::named_bar_sync(1, 256);
+      CV_TRACE(it, 5);
       {
         int rr = rr0, ch = ch0;
 #pragma unroll 4
@@ -281,6 +287,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
         }
       }
       tc::named_bar_sync(1, 256);
+      CV_TRACE(it, 6);
     }
   }
   tc::tc_fence_before();
@@ -303,6 +310,9 @@ bool tc_convf_supported(const smx_convmod_weights* w, int chunk) {
     return false;
   return true;
 }
+
+static unsigned long long* g_trace3 = nullptr;
+void tc_set_trace_conv(void* p) { g_trace3 = (unsigned long long*)p; }
 
 static int convf_sms() {
   static int n = 0;
@@ -331,6 +341,7 @@ int tc_convf_second_half(const smx_convmod_weights* w, const void* img_out, int 
   ConvFP p{};
   p.g = g; p.dw_w = w->dw_w; p.dw_b = w->dw_b; p.ln_w = w->after_ln_w; p.ln_b = w->after_ln_b;
   p.w_img = (const uint8_t*)img_out; p.b_out = w->out.b; p.mask = mask; p.resid = residual; p.y = y;
+  p.trace = g_trace3;
   p.B = B; p.T = T; p.D = D; p.tpu = (T + 127) / 128; p.n_tiles = B * p.tpu; p.act = act;
   const int nkb = D / 64;
   p.gw = nkb % 4 == 0 ? 4 : (nkb % 2 == 0 ? 2 : 1);

@@ -20,8 +20,9 @@ namespace smx {
 
 using tc::kblock_bytes;
 
-constexpr int F2_THREADS = 448;
-constexpr int F2_PRO_WARP0 = 8, F2_PROD_WARP = 12, F2_MMA_WARP = 13;
+constexpr int F2_THREADS = 448;       // 14 warps (measured: 4 prologue warps beat 2 even with a 128-register cap)
+constexpr int F2_PRO_WARP0 = 8, F2_NPW = 4, F2_PROD_WARP = 12, F2_MMA_WARP = 13;
+constexpr int F2_RPW = 128 / F2_NPW;  // rows per prologue warp
 constexpr int F2_HC = 128;            // hidden chunk width
 constexpr int F2_STAGES = 8;          // ring slots of 8 KB
 constexpr uint32_t F2_BLOCK = 8192;
@@ -78,7 +79,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ffn2_kernel(const Ffn2P p) {
   if (warp == F2_PROD_WARP) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int s = 0; s < F2_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], (uint32_t)cl); }
-    tc::mbar_init(&x_full, 4); tc::mbar_init(&x_free, 1); tc::mbar_init(&acc2_full, 1); tc::mbar_init(&epi_done, 8);
+    tc::mbar_init(&x_full, F2_NPW); tc::mbar_init(&x_free, 1); tc::mbar_init(&acc2_full, 1); tc::mbar_init(&epi_done, 8);
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&acc1_full[i], 1); tc::mbar_init(&acc1_empty[i], 8);
       tc::mbar_init(&h_full[i], 8); tc::mbar_init(&h_empty[i], 1);
@@ -259,33 +260,36 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ffn2_kernel(const Ffn2P p) {
         for (int e = 0; e < 8; ++e) v[e] = live ? (v[e] - mean) * rstd * gw[e] + gb[e] : 0.0f;
         return f2_pack8(v);
       };
-      uint4 keep[16];
+      uint4 keep[8];
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int r = pw * 32 + j;
+      for (int j = 0; j < 8; ++j) {
+        const int r = pw * F2_RPW + j;
         keep[j] = make_uint4(0, 0, 0, 0);
         if (has && r < nrows) keep[j] = *reinterpret_cast<const uint4*>(p.x + (row0 + r) * D + lane * 8);
       }
 #pragma unroll
-      for (int j = 0; j < 16; ++j) keep[j] = ln_row(keep[j], pw * 32 + j < nrows);
+      for (int j = 0; j < 8; ++j) keep[j] = ln_row(keep[j], pw * F2_RPW + j < nrows);
       if (it > 0) tc::mbar_wait(&x_free, (it - 1) & 1);
       if (pw == 0) F2_TRACE(2, it, 0);
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int r = pw * 32 + j;
+      for (int j = 0; j < 8; ++j) {
+        const int r = pw * F2_RPW + j;
         if (has) *reinterpret_cast<uint4*>(sX + (size_t)(lane >> 3) * kblock_bytes(128) + tc::sw128_offset(r, lane & 7)) = keep[j];
       }
+#pragma unroll 1
+      for (int rb = 8; rb < F2_RPW; rb += 8) {
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int r = pw * 32 + 16 + j;
-        keep[j] = make_uint4(0, 0, 0, 0);
-        if (has && r < nrows) keep[j] = *reinterpret_cast<const uint4*>(p.x + (row0 + r) * D + lane * 8);
-      }
+        for (int j = 0; j < 8; ++j) {
+          const int r = pw * F2_RPW + rb + j;
+          keep[j] = make_uint4(0, 0, 0, 0);
+          if (has && r < nrows) keep[j] = *reinterpret_cast<const uint4*>(p.x + (row0 + r) * D + lane * 8);
+        }
 #pragma unroll
-      for (int j = 0; j < 16; ++j) {
-        const int r = pw * 32 + 16 + j;
-        const uint4 o = ln_row(keep[j], r < nrows);
-        if (has) *reinterpret_cast<uint4*>(sX + (size_t)(lane >> 3) * kblock_bytes(128) + tc::sw128_offset(r, lane & 7)) = o;
+        for (int j = 0; j < 8; ++j) {
+          const int r = pw * F2_RPW + rb + j;
+          const uint4 o = ln_row(keep[j], r < nrows);
+          if (has) *reinterpret_cast<uint4*>(sX + (size_t)(lane >> 3) * kblock_bytes(128) + tc::sw128_offset(r, lane & 7)) = o;
+        }
       }
       tc::fence_proxy_async();
       __syncwarp();

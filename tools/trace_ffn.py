@@ -38,3 +38,10 @@ for r in range(5):
 fine = buf.cpu()[512 + 320:512 + 360]
 print("issuer, chunk 2 of tile 0 (gemm1(3): a1e-wait b/a, 4 x (full-wait b/a); h_full wait b/a; gemm2(2): 2 x (full-wait b/a)):")
 print("  " + " ".join(f"{int(v) - t0:7d}" if int(v) else "      -" for v in fine[:20]))
+
+cv = buf.cpu()[960:1024].view(4, 16)
+c0 = int(cv[cv > 0].min())
+print("conv kernel (tile: start, g staged, conv done, g free, acc ready, epilogue math done, stored):")
+for it in range(4):
+    if int(cv[it].max()):
+        print(f"  it{it}: " + " ".join(f"{int(v) - c0:7d}" if int(v) else "      -" for v in cv[it][:7]))
