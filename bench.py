@@ -329,7 +329,11 @@ def run_smx(args):
         us = mod["cell"]["us"]
         line["roofline"] = {"kernel": f"smx_summary_mixing_fwd (SummaryMixing cell, {mod['cell']['launches']} launches)",
                             "bound": "hbm", "achieved": bytes_cell / us / 1e3, "peak": pk["hbm_gbs"], "unit": "GB/s",
-                            "frac": bytes_cell / us / 1e3 / pk["hbm_gbs"], "traffic": None,
+                            "frac": bytes_cell / us / 1e3 / pk["hbm_gbs"],
+                            # dram__bytes_read+write per cell call from the ncu --set full capture committed as
+                            # profiles/r01_call11_ncu_cell_raw.csv (pass A 16.58 MB + finalise 0.58 MB + pass B 16.78 MB read;
+                            # the 16.4 MB output tile was still in L2 when the capture window closed)
+                            "traffic": 33.94e6, "algorithmic_bytes": bytes_cell,
                             "us_per_call": us, "peak_source": pk["source"] + " (burst copy)",
                             "tensor_tflops": flops_cell / us / 1e6, "tensor_frac": flops_cell / us / 1e6 / pk["bf16_tflops"]}
         flops_ffn = frames * 4 * D * FFN

@@ -1,0 +1,61 @@
+"""Multi-GPU host plumbing for the encoder path: utterance sharding, one process per GPU.
+
+The SummaryMixing cell reduces over time inside one utterance only (summary_mixing.py:229-231, dim=1), and every
+other op of the encoder block is per-frame or per-utterance (the depthwise conv never crosses utterances), so the
+forward path shards over utterances with NO data-path collective.  `torch.distributed` (NCCL over NVLink on the
+B200 box, gloo in the CPU tests) is used only to agree on timing / to gather results when the caller wants them
+on one rank.  Training would add one gradient all-reduce per step; this package is the forward path.
+"""
+from __future__ import annotations
+
+from typing import Callable, Optional, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(n_utts: int, rank: int, world: int) -> Tuple[int, int]:
+    """Contiguous, balanced split of n_utts utterances: ranks < n_utts % world get one more."""
+    if world <= 0 or not (0 <= rank < world):
+        raise ValueError(f"bad rank/world: {rank}/{world}")
+    base, rem = divmod(n_utts, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_batch(x: torch.Tensor, mask: Optional[torch.Tensor], rank: int, world: int):
+    """This rank's utterances of a padded batch x (B,T,D) and its (B,T) padding mask (1/True = valid)."""
+    lo, hi = shard_bounds(x.shape[0], rank, world)
+    return x[lo:hi], (None if mask is None else mask[lo:hi])
+
+
+def sharded_forward(fn: Callable, x: torch.Tensor, mask: Optional[torch.Tensor], gather: bool = False,
+                    group=None) -> torch.Tensor:
+    """Run `fn(x_shard, mask_shard) -> (b,T,D')` on this rank's utterances.  With gather=True every rank returns the
+    full (B,T,D') result (all_gather of equal-size padded shards); otherwise only its own shard."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    xs, ms = shard_batch(x, mask, rank, world)
+    y = fn(xs, ms) if xs.shape[0] > 0 else x.new_zeros((0,) + tuple(x.shape[1:]))
+    if not gather or world == 1:
+        return y
+    B = x.shape[0]
+    per = (B + world - 1) // world
+    pad = y.new_zeros((per,) + tuple(y.shape[1:]))
+    pad[: y.shape[0]] = y
+    outs = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(outs, pad, group=group)
+    parts = []
+    for r in range(world):
+        lo, hi = shard_bounds(B, r, world)
+        parts.append(outs[r][: hi - lo])
+    return torch.cat(parts, dim=0)
+
+
+def max_over_ranks(value: float, device=None, group=None) -> float:
+    """Timing helper: the slowest rank's value (bench.py reports device time as the max over ranks)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return float(value)
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX, group=group)
+    return float(t[0])
