@@ -27,6 +27,7 @@ static bool mlp_ok(const smx_linear* blk, int n, int in_dim) {
 
 bool tc_cell_supported(const smx_cell_weights* w, int has_sum_mask) {
   if (w->mode != SMX_MODE_FULL || has_sum_mask) return false;
+  if (tc_cellf_supported(w)) return true;  // fused kernels: any n_split (heads not aligned to 64 are packed as dense)
   if (!mlp_ok(w->local, w->n_local, w->enc_dim) || !mlp_ok(w->summary, w->n_summary, w->enc_dim)) return false;
   const int Dl = w->local_out_dim, Ds = w->summary_out_dim;
   if (w->local[w->n_local - 1].out_dim != Dl || w->summary[w->n_summary - 1].out_dim != Ds) return false;
