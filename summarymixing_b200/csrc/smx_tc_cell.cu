@@ -184,13 +184,13 @@ __global__ void __launch_bounds__(256) cell_finalize2_kernel(const CellFinP p) {
   }
 }
 
-template <int PHASE>  // 0: pass A (summary), 1: pass B (local + combiner)
+template <int PHASE, int ACT>  // PHASE 0: pass A (summary), 1: pass B (local + combiner), 2: GLU pass; ACT >= 0: compile-time smx_act
 __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
   extern __shared__ __align__(1024) uint8_t smem[];  // no pointer arithmetic through integers: keeps LDS/STS addressing
   uint8_t* sX = smem;
   uint8_t* sY = smem + p.off_y;
   uint8_t* sRing = smem + p.off_ring;
-  float* sPar = reinterpret_cast<float*>(smem + p.off_par);   // [b1 | b2 | ln_w | ln_b | c[b]], 256 floats each
+  float* sPar = reinterpret_cast<float*>(smem + p.off_par);   // [b1 | b2 | ln_w | ln_b | c[b] | norm1 w | norm1 b], 256 floats each
   float* sRed = reinterpret_cast<float*>(smem + p.off_red);   // 1024 floats: column partials / LN statistics / finalize
   __shared__ __align__(8) uint64_t full_bar[CF_MAX_STAGES], empty_bar[CF_MAX_STAGES];
   __shared__ __align__(8) uint64_t x_full, x_free, a2_full, epi_done;
@@ -200,6 +200,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler (role dispatch below)
   constexpr int NG = PHASE == 0 ? 2 : (PHASE == 1 ? 3 : 1);
+  const int act = ACT >= 0 ? ACT : p.act;  // compile-time activation: one tight loop per epilogue instead of a 7-way switch
 
   if (warp == CF_PROD_WARP) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
@@ -217,6 +218,8 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
     sPar[256 + i] = i < p.nb2 ? p.b2[i] : 0.0f;
     sPar[512 + i] = (p.ln_w && i < p.nb2) ? p.ln_w[i] : 1.0f;
     sPar[768 + i] = (p.ln_b && i < p.nb2) ? p.ln_b[i] : 0.0f;
+    sPar[1280 + i] = (p.pre_w && i < p.D) ? p.pre_w[i] : 1.0f;   // norm1 (prologue LayerNorm)
+    sPar[1536 + i] = (p.pre_b && i < p.D) ? p.pre_b[i] : 0.0f;
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -319,15 +322,6 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
   } else if (warp >= CF_PRO_WARP0) {
     // =============================== prologue: x tile -> LN1 -> A operand ===============================
     const int pw = warp - CF_PRO_WARP0;
-    const int nchunk = p.D / 8;  // 16-byte chunks per row (<= 32)
-    const bool has = lane < nchunk;
-    float gw[8], gb[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) {
-      gw[e] = (p.pre_w && has) ? p.pre_w[lane * 8 + e] : 1.0f;
-      gb[e] = (p.pre_b && has) ? p.pre_b[lane * 8 + e] : 0.0f;
-    }
-    const float invD = 1.0f / (float)p.D;
     int it = 0;
     for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
       const int b = tile / p.tpu, t0 = (tile % p.tpu) * 128;
@@ -335,42 +329,9 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
       if (it > 0) tc::mbar_wait(&x_free, (it - 1) & 1);
       if (pw == 0) CF_TRACE(2, it, 0);
-#pragma unroll 1
-      for (int r8 = 0; r8 < 128 / CF_NPW; r8 += 8) {
-        uint4 raw[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = pw * (128 / CF_NPW) + r8 + j;
-          raw[j] = make_uint4(0, 0, 0, 0);
-          if (has && r < nrows) raw[j] = *reinterpret_cast<const uint4*>(p.x + (row0 + r) * p.ldx + lane * 8);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = pw * (128 / CF_NPW) + r8 + j;
-          float v[8];
-          cf_unpack8(raw[j], v);
-          if (p.pre_w) {
-            float s = 0.0f;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) s += v[e];
-#pragma unroll
-            for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-            const float mean = s * invD;
-            float q = 0.0f;
-            if (has) {
-#pragma unroll
-              for (int e = 0; e < 8; ++e) { float d = v[e] - mean; q += d * d; }
-            }
-#pragma unroll
-            for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-            const float rstd = rsqrtf(q * invD + 1e-5f);
-            const bool live = r < nrows;
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = live ? (v[e] - mean) * rstd * gw[e] + gb[e] : 0.0f;
-          }
-          if (has) *reinterpret_cast<uint4*>(sX + (size_t)(lane >> 3) * kblock_bytes(128) + tc::sw128_offset(r, lane & 7)) = cf_pack8(v);
-        }
-      }
+      // all rows of this warp in flight at once (cp.async straight into the operand image), then LayerNorm in place, a thread per row
+      tc::stage_ln_rows(sX, p.x, p.ldx, row0, nrows, p.D, pw, lane, p.pre_w != nullptr, sPar + 1280, sPar + 1536,
+                        (p.trace && blockIdx.x == 0 && pw == 0 && it < 4) ? p.trace + ((2 * 4 + it) * 16) + 4 : nullptr);
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&x_full);
@@ -459,7 +420,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
           const float4* bp = reinterpret_cast<const float4*>(sB1 + c * 64 + pc * 32);
 #pragma unroll
           for (int j = 0; j < 8; ++j) { const float4 bb = bp[j]; v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w; }
-          tc::act_apply<32>(p.act, v);
+          tc::act_apply<32>(act, v);
 #pragma unroll
           for (int k = 0; k < 4; ++k)
             *reinterpret_cast<uint4*>(sY + (size_t)c * kblock_bytes(128) + tc::sw128_offset(r, pc * 4 + k)) = cf_pack8(v + 8 * k);
@@ -484,7 +445,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
             const float4* bp = reinterpret_cast<const float4*>(sB2 + c * 64 + pc * 32);
 #pragma unroll
             for (int j = 0; j < 8; ++j) { const float4 bb = bp[j]; v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w; }
-            tc::act_apply<32>(p.act, v);
+            tc::act_apply<32>(act, v);
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] *= rscale;
             const float tot = cf_column_sums(v, lane);
@@ -517,7 +478,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
               const float4* bp = reinterpret_cast<const float4*>(sB2 + c * 64 + pc * 32);
 #pragma unroll
               for (int j = 0; j < 8; ++j) { const float4 bb = bp[j]; v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w; }
-              tc::act_apply<32>(p.act, v);
+              tc::act_apply<32>(act, v);
 #pragma unroll
               for (int j = 0; j < 32; ++j) { v[j] *= rscale; s1 += v[j]; }
               tc::tmem_st32(ta, v);  // park the fp32 values in TMEM for the two LayerNorm passes
@@ -579,7 +540,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
               const float4* bp = reinterpret_cast<const float4*>(sB2 + c * 64 + pc * 32);
 #pragma unroll
               for (int j = 0; j < 8; ++j) { const float4 bb = bp[j]; v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w; }
-              tc::act_apply<32>(p.act, v);
+              tc::act_apply<32>(act, v);
 #pragma unroll
               for (int j = 0; j < 32; ++j) v[j] *= rscale;
 #pragma unroll
@@ -636,7 +597,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
             const float4* bp = reinterpret_cast<const float4*>(sRB + col);
 #pragma unroll
             for (int j = 0; j < 8; ++j) { const float4 bb = bp[j]; v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w; }
-            tc::act_apply<32>(p.act, v);
+            tc::act_apply<32>(act, v);
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
               uint4* sp = reinterpret_cast<uint4*>(sY + (size_t)c * kblock_bytes(128) + tc::sw128_offset(r, pc * 4 + k));
@@ -737,6 +698,24 @@ static int num_sms() {
   return g_num_sms;
 }
 
+template <int PHASE, int ACT>
+static int launch_cell_act(const CellFP& p, unsigned grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(cell_kernel<PHASE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(cell_kernel): %s", cudaGetErrorString(e));
+  cell_kernel<PHASE, ACT><<<grid, CF_THREADS, smem, st>>>(p);
+  count_tc_launch();
+  return check_launch("cell_kernel");
+}
+template <int PHASE>
+static int launch_cell(const CellFP& p, unsigned grid, size_t smem, cudaStream_t st) {
+  switch (p.act) {
+    case SMX_ACT_SWISH: return launch_cell_act<PHASE, SMX_ACT_SWISH>(p, grid, smem, st);
+    case SMX_ACT_GELU: return launch_cell_act<PHASE, SMX_ACT_GELU>(p, grid, smem, st);
+    case SMX_ACT_RELU: return launch_cell_act<PHASE, SMX_ACT_RELU>(p, grid, smem, st);
+    default: return launch_cell_act<PHASE, -1>(p, grid, smem, st);
+  }
+}
+
 // images: [s1][s2][f1][f2][merge local part], each N*K*2 bytes in 64x64 blocks (NT = 64)
 int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_s2, const void* img_f1, const void* img_f2,
                  const void* img_c, int B, int T, const __nv_bfloat16* x, const float* pre_ln_w, const float* pre_ln_b,
@@ -747,7 +726,6 @@ int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
   float* colsum = ws.f32((size_t)B * tpu * Ds);
   float* rowbias = ws.f32((size_t)B * Dout);
   if (!colsum || !rowbias) return fail(SMX_ERR_WORKSPACE, "workspace too small (fused cell)");
-  cudaError_t e;
 
   CellFP p{};
   p.x = x; p.ldx = D; p.pre_w = pre_ln_w; p.pre_b = pre_ln_b; p.mask = mask;
@@ -780,11 +758,7 @@ int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
     p.ln_b = w->use_layernorm ? w->summary_norm_b : nullptr;
     const size_t smem = carve(w->summary[0].out_dim);
     if (p.n_stages < 4) return fail(SMX_ERR_UNSUPPORTED, "fused cell: tile does not fit shared memory");
-    e = cudaFuncSetAttribute(cell_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(cell_kernel<0>): %s", cudaGetErrorString(e));
-    cell_kernel<0><<<grid, CF_THREADS, smem, st>>>(p);
-    count_tc_launch();
-    SMX_TRY(check_launch("cell_kernel<0>"));
+    SMX_TRY(launch_cell<0>(p, grid, smem, st));
   }
   {  // per-utterance mean -> LN_s -> summary share of the combiner
     CellFinP f{};
@@ -811,11 +785,7 @@ int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
     if (Dout > ycols) ycols = Dout;
     const size_t smem = carve(ycols);
     if (p.n_stages < 4) return fail(SMX_ERR_UNSUPPORTED, "fused cell: tile does not fit shared memory");
-    e = cudaFuncSetAttribute(cell_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(cell_kernel<1>): %s", cudaGetErrorString(e));
-    cell_kernel<1><<<grid, CF_THREADS, smem, st>>>(p);
-    count_tc_launch();
-    SMX_TRY(check_launch("cell_kernel<1>"));
+    SMX_TRY(launch_cell<1>(p, grid, smem, st));
   }
   ws.release(m0);
   return SMX_OK;
@@ -846,11 +816,7 @@ int tc_glu_fwd(const smx_linear& L, const void* img, const float* ln_w, const fl
   p.off_red = p.off_par + 8192;
   const size_t smem = (size_t)p.off_red + 4096;
   const unsigned grid = (unsigned)(p.n_tiles < num_sms() ? p.n_tiles : num_sms());
-  cudaError_t e = cudaFuncSetAttribute(cell_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(cell_kernel<2>): %s", cudaGetErrorString(e));
-  cell_kernel<2><<<grid, CF_THREADS, smem, st>>>(p);
-  count_tc_launch();
-  return check_launch("cell_kernel<2>");
+  return launch_cell_act<2, 0>(p, grid, smem, st);  // the GLU pass has no runtime activation (sigmoid gate only)
 }
 
 }  // namespace smx

@@ -125,6 +125,8 @@ __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc, uin
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
 // ---- TMEM ----------------------------------------------------------------------------------------
 __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t ncols) {  // one full warp
@@ -293,6 +295,79 @@ __device__ __forceinline__ void act_apply(int act, float* v) {
 __device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);
   return *reinterpret_cast<uint32_t*>(&v);
+}
+
+// ---- row-tile prologue shared by the fused kernels ----------------------------------------------------
+// Prologue warp pw (of four) brings rows [32 pw, 32 pw + 32) of the (128 x D) bf16 tile straight into the A operand image
+// (K-blocks of 128 rows x 128 B, 128B swizzle) with 16-byte cp.async copies: lane l copies the 16-byte chunk l of every
+// row, all 32 rows in flight at once, no registers held.  LayerNorm (eps 1e-5, fp32) then runs in place with ONE THREAD PER
+// ROW: lane l owns row 32 pw + l and walks its D / 8 chunks (the swizzle makes the row-per-lane accesses conflict-free), so
+// there are no shuffles and every chunk is independent work.  Statistics are shifted by the row's first element
+// (var = E[(x-x0)^2] - E[x-x0]^2: one read, no cancellation for rows with a large mean); a second read normalises.
+// Rows >= nrows become zero rows.  D % 8 == 0, D <= 256.  sW / sB: LN weight / bias in shared memory (D floats each).
+// The caller orders the A operand for the async proxy afterwards (fence_proxy_async).
+__device__ __forceinline__ void unpack_bf16x8(const uint4& raw, float* v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[2 * e] = f.x; v[2 * e + 1] = f.y; }
+}
+__device__ __forceinline__ void stage_ln_rows(uint8_t* sX, const __nv_bfloat16* x, int64_t ldx, int64_t row0, int nrows, int D,
+                                              int pw, int lane, bool do_ln, const float* sW, const float* sB,
+                                              unsigned long long* tr = nullptr) {
+  const int nch = D >> 3;
+  {
+    const bool has = lane < nch;
+    uint8_t* const base = sX + (size_t)(lane >> 3) * kblock_bytes(128);
+    const __nv_bfloat16* src = x + (row0 + pw * 32) * ldx + lane * 8;
+    if (has) {
+#pragma unroll 8
+      for (int j = 0; j < 32; ++j) {
+        const int r = pw * 32 + j;
+        const bool in = r < nrows;
+        cp_async16(base + sw128_offset(r, lane & 7), in ? (const void*)(src + (int64_t)j * ldx) : (const void*)x, in ? 16u : 0u);
+      }
+    }
+    cp_async_commit();
+  }
+  if (tr && lane == 0) tr[0] = clock64();
+  cp_async_wait_all();
+  __syncwarp();  // the row a lane normalises was copied by all lanes of this warp
+  if (tr && lane == 0) tr[1] = clock64();
+  if (!do_ln) return;
+  const int r = pw * 32 + lane;
+  uint8_t* const rowp = sX + (r >> 3) * 1024 + (r & 7) * 128;
+  const uint32_t rx = (uint32_t)(r & 7);
+  float v[8];
+  unpack_bf16x8(*reinterpret_cast<const uint4*>(rowp + (rx << 4)), v);  // chunk 0
+  const float x0 = v[0];
+  float a1[8], a2[8];  // eight independent accumulator chains
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { a1[e] = 0.0f; a2[e] = 0.0f; }
+#pragma unroll 4
+  for (int c = 0; c < nch; ++c) {
+    unpack_bf16x8(*reinterpret_cast<const uint4*>(rowp + (size_t)(c >> 3) * kblock_bytes(128) + ((((uint32_t)c & 7u) ^ rx) << 4)), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float d = v[e] - x0; a1[e] += d; a2[e] = fmaf(d, d, a2[e]); }
+  }
+  const float s1 = ((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((a1[4] + a1[5]) + (a1[6] + a1[7]));
+  const float s2 = ((a2[0] + a2[1]) + (a2[2] + a2[3])) + ((a2[4] + a2[5]) + (a2[6] + a2[7]));
+  const float invD = 1.0f / (float)D;
+  const float m0 = s1 * invD;                                  // mean - x0
+  const float rstd = rsqrtf(fmaxf(s2 * invD - m0 * m0, 0.0f) + 1e-5f);
+  const float shift = -(m0 + x0) * rstd;                       // (x - mean) * rstd = x * rstd + shift
+  const bool live = r < nrows;
+#pragma unroll 4
+  for (int c = 0; c < nch; ++c) {
+    uint4* const cp = reinterpret_cast<uint4*>(rowp + (size_t)(c >> 3) * kblock_bytes(128) + ((((uint32_t)c & 7u) ^ rx) << 4));
+    unpack_bf16x8(*cp, v);
+    const float4 w0 = *reinterpret_cast<const float4*>(sW + c * 8), w1 = *reinterpret_cast<const float4*>(sW + c * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(sB + c * 8), b1 = *reinterpret_cast<const float4*>(sB + c * 8 + 4);
+    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = live ? fmaf(fmaf(v[e], rstd, shift), wv[e], bv[e]) : 0.0f;
+    *cp = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
 }
 
 }  // namespace tc

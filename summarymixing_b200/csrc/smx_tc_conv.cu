@@ -4,16 +4,17 @@
 //
 // where g = GLU(W_bottleneck @ LN(x)) is produced by the GLU pass of the fused cell skeleton (smx_tc_cell.cu, PHASE 2).
 // One CTA per SM walks utterance-aligned 128-frame tiles:
-//   warps 0-7  (1) stage the (128 + k - 1) frames of g the tile needs in shared memory (zero rows outside the utterance:
+//   warps 0-11 (1) stage the (128 + k - 1) frames of g the tile needs in shared memory (zero rows outside the utterance:
 //                  the reference's zero padding, Conformer.py:142-151);
 //              (2) depthwise conv: a thread owns one channel pair and blocks of eight consecutive frames, taps and
-//                  accumulators in registers (8*k*2 FMAs per k+7 shared-memory loads); LayerNorm statistics per frame
+//                  accumulators in registers as fp32 pairs; one packed fma.rn.f32x2 (FFMA2) updates both channels
+//                  (8*k FFMA2 per k+7 shared-memory loads); LayerNorm statistics per frame
 //                  by warp shuffles + one small shared-memory exchange; normalise, activate and write the bf16 A
 //                  operand (128B swizzle) for the tensor core;
 //              (4) epilogue of the output GEMM: + bias, * mask, + residual (parked in the idle g buffer with coalesced
 //                  loads issued while the GEMM runs), staged tile, coalesced stores
-//   warp 8     weight producer (8 KB blocks of W_out through a shared-memory ring, cp.async.bulk + mbarrier)
-//   warp 9     (3) MMA issuer: tcgen05.mma, N = up to 256 per instruction, accumulator in TMEM
+//   warp 12    weight producer (8 KB blocks of W_out through a shared-memory ring, cp.async.bulk + mbarrier)
+//   warp 13    (3) MMA issuer: tcgen05.mma, N = up to 256 per instruction, accumulator in TMEM
 // The depthwise output, its LayerNorm and the activation never exist in global memory.
 #include "smx_tc.h"
 #include "smx_tc_common.cuh"
@@ -22,8 +23,10 @@ namespace smx {
 
 using tc::kblock_bytes;
 
-constexpr int CV_THREADS = 320;
-constexpr int CV_PROD_WARP = 8, CV_MMA_WARP = 9;
+constexpr int CV_NCW = 12;                    // compute warps, three per TMEM lane quadrant (16 would need < 100 registers: spills)
+constexpr int CV_CT = CV_NCW * 32;            // compute threads
+constexpr int CV_THREADS = CV_CT + 64;
+constexpr int CV_PROD_WARP = CV_NCW, CV_MMA_WARP = CV_NCW + 1;
 constexpr int CV_STAGES = 8;
 constexpr uint32_t CV_BLOCK = 8192;
 
@@ -37,6 +40,15 @@ struct ConvFP {
   uint32_t off_a, off_ring, off_par, off_stat;
 };
 
+// both channels of a pair in one instruction: d = a * b + c on (x, y) fp32 pairs (FFMA2)
+__device__ __forceinline__ float2 cv_fma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
 __device__ __forceinline__ uint4 cv_pack8(const float* v) {
   return make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]), tc::pack_bf16x2(v[6], v[7]));
 }
@@ -51,7 +63,7 @@ __device__ __forceinline__ void cv_unpack8(const uint4& raw, float* v) {
     if (p.trace && blockIdx.x == 0 && tid == 0 && (it) < 4) p.trace[(it) * 16 + (ev)] = clock64();          \
   } while (0)
 
-template <int K, int ACT>
+template <int K, int ACT, int D>  // D (64, 128, 256) is compile time: immediate shared-memory offsets, unrolled statistics
 __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
   constexpr int PAD = (K - 1) / 2, NIN = 128 + K - 1;
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -60,19 +72,20 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
   uint8_t* sA = smem + p.off_a;
   uint8_t* sRing = smem + p.off_ring;
   float* sPar = reinterpret_cast<float*>(smem + p.off_par);     // [b_out | ln_w | ln_b], 256 floats each
-  float* sStat = reinterpret_cast<float*>(smem + p.off_stat);   // [2][8 warps][8 frames][2]
+  float* sStat = reinterpret_cast<float*>(smem + p.off_stat);   // [2][CV_NCW warps][8 frames][2]
   __shared__ __align__(8) uint64_t full_bar[CV_STAGES], empty_bar[CV_STAGES], a_full, acc_full;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int D = p.D, nkb = D / 64, gw = p.gw, ng = nkb / gw;
+  constexpr int nkb = D / 64;
+  const int gw = p.gw, ng = nkb / gw;
   const int act = ACT >= 0 ? ACT : p.act;
 
   if (warp == CV_PROD_WARP) tc::tmem_alloc(&tmem_base_s, 256);
   if (tid == 0) {
     for (int s = 0; s < CV_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    tc::mbar_init(&a_full, 8); tc::mbar_init(&acc_full, 1);
+    tc::mbar_init(&a_full, CV_NCW); tc::mbar_init(&acc_full, 1);
     tc::fence_barrier_init();
   }
   for (int i = tid; i < 256; i += CV_THREADS) {
@@ -136,22 +149,24 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
       if (tc::elect_one()) tc::umma_commit(&acc_full);
       __syncwarp();
     }
-  } else {
+  } else if (warp < CV_NCW) {
     // =============================== compute warps ===============================
-    const int q = warp & 3, grp = warp >> 2;
+    const int q = warp & 3, grp = warp >> 2;  // TMEM lane quadrant; 64-column chunk (chunks grp, grp + 4, ...)
     const int r = q * 32 + lane;
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    const int pairs = D / 2, pr = tid % pairs, fb0 = tid / pairs, nfbp = 256 / pairs, wpf = pairs / 32;
+    constexpr int pairs = D / 2, nfbp = CV_CT / pairs, wpf = pairs / 32;
+    const int pr = tid % pairs, fb0 = tid / pairs;
     const int c0 = pr * 2;                      // this thread's channel pair
     const int wig = (tid % pairs) >> 5;         // warp index inside its frame-block group
-    float w0[K], w1[K];
+    float2 w2[K];  // taps of both channels
 #pragma unroll
-    for (int j = 0; j < K; ++j) { w0[j] = p.dw_w[(size_t)c0 * K + j]; w1[j] = p.dw_w[(size_t)(c0 + 1) * K + j]; }
-    const float bias0 = p.dw_b ? p.dw_b[c0] : 0.0f, bias1 = p.dw_b ? p.dw_b[c0 + 1] : 0.0f;
-    const float lw0 = sPar[256 + c0], lw1 = sPar[256 + c0 + 1], lb0 = sPar[512 + c0], lb1 = sPar[512 + c0 + 1];
-    const float invD = 1.0f / (float)D;
-    const int cpr = D / 8;
-    const int rr0 = tid / cpr, ch0 = tid - rr0 * cpr, drr = 256 / cpr, dch = 256 - drr * cpr;
+    for (int j = 0; j < K; ++j) w2[j] = make_float2(p.dw_w[(size_t)c0 * K + j], p.dw_w[(size_t)(c0 + 1) * K + j]);
+    const float2 bias2 = make_float2(p.dw_b ? p.dw_b[c0] : 0.0f, p.dw_b ? p.dw_b[c0 + 1] : 0.0f);
+    const float2 lw2 = make_float2(sPar[256 + c0], sPar[256 + c0 + 1]), lb2 = make_float2(sPar[512 + c0], sPar[512 + c0 + 1]);
+    constexpr float invD = 1.0f / (float)D;
+    constexpr int cpr = D / 8;
+    const int rr0 = tid / cpr, ch0 = tid - rr0 * cpr, drr = CV_CT / cpr, dch = CV_CT - drr * cpr;
+    constexpr int NST = (128 * 32 + CV_CT - 1) / CV_CT;       // 16-byte chunks of a D = 256 tile per thread (residual / output staging)
     uint32_t sp = 0;  // statistics buffer parity
     int it = 0;
     for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
@@ -160,27 +175,27 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
       CV_TRACE(it, 0);
       // ---- (1) stage g[t0 - PAD, t0 + 128 + PAD) -----------------------------------------------------
-      for (int idx = tid; idx < NIN * cpr; idx += 256) {
+      for (int idx = tid; idx < NIN * cpr; idx += CV_CT) {
         const int row = idx / cpr, ch = idx - row * cpr, u = t0 - PAD + row;
         const bool in = u >= 0 && u < p.T;
         tc::cp_async16(sG + (size_t)idx * 8, in ? (const void*)(p.g + ((int64_t)b * p.T + u) * D + ch * 8) : (const void*)p.g, in ? 16u : 0u);
       }
       tc::cp_async_commit();
       tc::cp_async_wait_all();
-      tc::named_bar_sync(1, 256);
+      tc::named_bar_sync(1, CV_CT);
       CV_TRACE(it, 1);
       // ---- (2) depthwise conv -> LayerNorm -> activation -> A operand --------------------------------
       for (int fb = fb0; fb < 16; fb += nfbp) {
-        float a0[8], a1[8];
+        float2 a[8];
 #pragma unroll
-        for (int o = 0; o < 8; ++o) { a0[o] = bias0; a1[o] = bias1; }
+        for (int o = 0; o < 8; ++o) a[o] = bias2;
 #pragma unroll
         for (int i = 0; i < K + 7; ++i) {
           const float2 x = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(sG + (size_t)(fb * 8 + i) * D + c0));
 #pragma unroll
           for (int o = 0; o < 8; ++o) {
             const int j = i - o;
-            if (j >= 0 && j < K) { a0[o] = fmaf(w0[j], x.x, a0[o]); a1[o] = fmaf(w1[j], x.y, a1[o]); }
+            if (j >= 0 && j < K) a[o] = cv_fma2(w2[j], x, a[o]);
           }
         }
         // per-frame statistics over the D channels: this thread's pair -> warp -> the group's warps
@@ -188,7 +203,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
         // instead of 80; lane l (even) ends with the warp total of value (l >> 1)
         float pv[16];
 #pragma unroll
-        for (int o = 0; o < 8; ++o) { pv[o] = a0[o] + a1[o]; pv[8 + o] = fmaf(a0[o], a0[o], a1[o] * a1[o]); }
+        for (int o = 0; o < 8; ++o) { pv[o] = a[o].x + a[o].y; pv[8 + o] = fmaf(a[o].x, a[o].x, a[o].y * a[o].y); }
 #pragma unroll
         for (int sh = 16, n = 8; sh >= 2; sh >>= 1, n >>= 1) {
           const bool up = (lane & sh) != 0;
@@ -200,25 +215,31 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
           }
         }
         pv[0] += __shfl_xor_sync(0xffffffffu, pv[0], 1);
-        float* st = sStat + (size_t)sp * 128;
+        float* st = sStat + (size_t)sp * (CV_NCW * 16);
         if ((lane & 1) == 0) {  // value index = lane bits 4..1: bit 4 selects {sum, sumsq}, bits 3..1 the frame
           const int vi = lane >> 1;
           st[(warp * 8 + (vi & 7)) * 2 + (vi >> 3)] = pv[0];
         }
         if (wpf > 1) tc::named_bar_sync(2 + fb0, wpf * 32); else __syncwarp();
+        // lane l < 16 adds the group's warp totals of value l (frame l & 7, statistic l >> 3); lanes 0..7 then hold the
+        // frame's mean and 1/std, which every lane fetches with one shuffle per frame
         const int wbase = warp - wig;  // first warp of this group
+        float tot = 0.0f;
+#pragma unroll
+        for (int w = 0; w < wpf; ++w) tot += st[((wbase + w) * 8 + (lane & 7)) * 2 + ((lane >> 3) & 1)];
+        const float sq = __shfl_xor_sync(0xffffffffu, tot, 8);
+        const float mean_l = tot * invD;
+        const float rstd_l = rsqrtf(fmaxf(sq * invD - mean_l * mean_l, 0.0f) + 1e-5f);
+        uint8_t* const arow = sA + (size_t)(c0 >> 6) * kblock_bytes(128) + (c0 & 7) * 2;
 #pragma unroll
         for (int o = 0; o < 8; ++o) {
-          float s1 = 0.0f, s2 = 0.0f;
-          for (int w = 0; w < wpf; ++w) { s1 += st[((wbase + w) * 8 + o) * 2]; s2 += st[((wbase + w) * 8 + o) * 2 + 1]; }
-          const float mean = s1 * invD;
-          const float var = fmaxf(s2 * invD - mean * mean, 0.0f);
-          const float rstd = rsqrtf(var + 1e-5f);
-          float v[2] = {(a0[o] - mean) * rstd * lw0 + lb0, (a1[o] - mean) * rstd * lw1 + lb1};
+          const float mean = __shfl_sync(0xffffffffu, mean_l, o), rstd = __shfl_sync(0xffffffffu, rstd_l, o);
+          const float2 d = make_float2(a[o].x - mean, a[o].y - mean);
+          const float2 t = cv_fma2(d, make_float2(rstd * lw2.x, rstd * lw2.y), lb2);
+          float v[2] = {t.x, t.y};
           tc::act_apply<2>(act, v);
           const int row = fb * 8 + o;
-          *reinterpret_cast<uint32_t*>(sA + (size_t)(c0 >> 6) * kblock_bytes(128) + tc::sw128_offset(row, (c0 & 63) >> 3) + (c0 & 7) * 2) =
-              tc::pack_bf16x2(v[0], v[1]);
+          *reinterpret_cast<uint32_t*>(arow + tc::sw128_offset(row, (c0 & 63) >> 3)) = tc::pack_bf16x2(v[0], v[1]);
         }
         sp ^= 1u;
       }
@@ -227,12 +248,12 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
       if (lane == 0) tc::mbar_arrive(&a_full);
       CV_TRACE(it, 2);
       // ---- (4) epilogue of the output GEMM -----------------------------------------------------------
-      tc::named_bar_sync(1, 256);  // every warp has finished reading the staged g tile
+      tc::named_bar_sync(1, CV_CT);  // every warp has finished reading the staged g tile
       CV_TRACE(it, 3);
       {  // the residual tile goes straight to shared memory (swizzled staging layout) while the output GEMM runs
         int rr = rr0, ch = ch0;
 #pragma unroll 4
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < NST; ++k) {
           if (rr < 128) {
             const bool in = p.resid && rr < nrows;
             tc::cp_async16(sStage + (size_t)(ch >> 3) * kblock_bytes(128) + tc::sw128_offset(rr, ch & 7),
@@ -249,8 +270,8 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
       tc::tc_fence_after();
       tc::cp_async_wait_all();
       CV_TRACE(it, 4);
-      tc::named_bar_sync(1, 256);
-      for (int c = grp; c < nkb; c += 2) {
+      tc::named_bar_sync(1, CV_CT);
+      for (int c = grp; c < nkb; c += CV_NCW / 4) {
 #pragma unroll
         for (int pc = 0; pc < 2; ++pc) {
           const int col = c * 64 + pc * 32;
@@ -272,12 +293,12 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
         }
       }
       tc::tc_fence_before();
-      tc::named_bar_sync(1, 256);
+      tc::named_bar_sync(1, CV_CT);
       CV_TRACE(it, 5);
       {
         int rr = rr0, ch = ch0;
 #pragma unroll 4
-        for (int k = 0; k < 16; ++k) {
+        for (int k = 0; k < NST; ++k) {
           if (rr < nrows) {
             const uint4 val = *reinterpret_cast<const uint4*>(sStage + (size_t)(ch >> 3) * kblock_bytes(128) + tc::sw128_offset(rr, ch & 7));
             *reinterpret_cast<uint4*>(p.y + (row0 + rr) * D + ch * 8) = val;
@@ -286,7 +307,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
           if (ch >= cpr) { ch -= cpr; ++rr; }
         }
       }
-      tc::named_bar_sync(1, 256);
+      tc::named_bar_sync(1, CV_CT);
       CV_TRACE(it, 6);
     }
   }
@@ -325,13 +346,21 @@ static int convf_sms() {
   return n;
 }
 
-template <int ACT>
-static int launch_conv(const ConvFP& p, unsigned grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(conv_kernel<31, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int ACT, int D>
+static int launch_conv_d(const ConvFP& p, unsigned grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(conv_kernel<31, ACT, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(conv_kernel): %s", cudaGetErrorString(e));
-  conv_kernel<31, ACT><<<grid, CV_THREADS, smem, st>>>(p);
+  conv_kernel<31, ACT, D><<<grid, CV_THREADS, smem, st>>>(p);
   count_tc_launch();
   return check_launch("conv_kernel");
+}
+template <int ACT>
+static int launch_conv(const ConvFP& p, unsigned grid, size_t smem, cudaStream_t st) {
+  switch (p.D) {
+    case 256: return launch_conv_d<ACT, 256>(p, grid, smem, st);
+    case 128: return launch_conv_d<ACT, 128>(p, grid, smem, st);
+    default: return launch_conv_d<ACT, 64>(p, grid, smem, st);
+  }
 }
 
 // g: GLU output (B,T,D) bf16; img_out: packed after_conv.2 weight (64 x 64 blocks)
@@ -350,7 +379,7 @@ int tc_convf_second_half(const smx_convmod_weights* w, const void* img_out, int 
   p.off_ring = p.off_a + (uint32_t)stage;
   p.off_par = p.off_ring + CV_STAGES * CV_BLOCK;
   p.off_stat = p.off_par + 3072;
-  const size_t smem = (size_t)p.off_stat + 1024;
+  const size_t smem = (size_t)p.off_stat + 2048;
   const unsigned grid = (unsigned)(p.n_tiles < convf_sms() ? p.n_tiles : convf_sms());
   switch (act) {
     case SMX_ACT_SWISH: return launch_conv<SMX_ACT_SWISH>(p, grid, smem, st);

@@ -60,7 +60,7 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ffn2_kernel(const Ffn2P p) {
   uint8_t* sX = smem;
   uint8_t* sH = smem + p.off_h;       // two hidden buffers of 2 K-blocks (32 KB each); also the output staging tile
   uint8_t* sRing = smem + p.off_ring;
-  float* sPar = reinterpret_cast<float*>(smem + p.off_par);  // [b1 (F) | b2 (256) | oln_w (256) | oln_b (256)]
+  float* sPar = reinterpret_cast<float*>(smem + p.off_par);  // [b1 (F) | b2 | oln_w | oln_b | ln_w | ln_b (256 each)]
   float* sRed = reinterpret_cast<float*>(smem + p.off_red);  // [2 stats][2 groups][128 rows]
   __shared__ __align__(8) uint64_t full_bar[F2_STAGES], empty_bar[F2_STAGES];
   __shared__ __align__(8) uint64_t x_full, x_free, acc1_full[2], acc1_empty[2], h_full[2], h_empty[2], acc2_full, epi_done;
@@ -87,11 +87,13 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ffn2_kernel(const Ffn2P p) {
     tc::fence_barrier_init();
   }
   for (int i = tid; i < p.F; i += F2_THREADS) sPar[i] = p.b1[i];
-  float* sB2 = sPar + p.F; float* sOw = sB2 + 256; float* sOb = sOw + 256;
+  float* sB2 = sPar + p.F; float* sOw = sB2 + 256; float* sOb = sOw + 256; float* sLw = sOb + 256; float* sLb = sLw + 256;
   for (int i = tid; i < 256; i += F2_THREADS) {
     sB2[i] = i < D ? p.b2[i] : 0.0f;
     sOw[i] = (OLN && i < D) ? p.oln_w[i] : 1.0f;
     sOb[i] = (OLN && i < D) ? p.oln_b[i] : 0.0f;
+    sLw[i] = i < D ? p.ln_w[i] : 1.0f;
+    sLb[i] = i < D ? p.ln_b[i] : 0.0f;
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -227,70 +229,15 @@ __global__ void __launch_bounds__(F2_THREADS, 1) ffn2_kernel(const Ffn2P p) {
   } else if (warp >= F2_PRO_WARP0) {
     // =============================== prologue: x tile -> LN -> A operand ===============================
     const int pw = warp - F2_PRO_WARP0;
-    const int nchunk = D / 8;
-    const bool has = lane < nchunk;
-    float gw[8], gb[8];
-#pragma unroll
-    for (int e = 0; e < 8; ++e) { gw[e] = has ? p.ln_w[lane * 8 + e] : 1.0f; gb[e] = has ? p.ln_b[lane * 8 + e] : 0.0f; }
-    const float invD = 1.0f / (float)D;
     int it = 0;
     for (int base = first_base; base < p.n_tiles; base += base_step, ++it) {
       const int64_t row0 = (int64_t)(base + (int)crank) * 128;
       const int nrows = p.rows - row0 < 128 ? (int)(p.rows - row0) : 128;
-      // Half of this warp's rows are fetched and normalised while the previous tile still owns X (they wait in
-      // registers as packed bf16); the other half follows once X is released.
-      auto ln_row = [&](const uint4& rw, bool live) -> uint4 {
-        float v[8];
-        f2_unpack8(rw, v);
-        float sm = 0.0f;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) sm += v[e];
-#pragma unroll
-        for (int o = 16; o; o >>= 1) sm += __shfl_xor_sync(0xffffffffu, sm, o);
-        const float mean = sm * invD;
-        float q = 0.0f;
-        if (has) {
-#pragma unroll
-          for (int e = 0; e < 8; ++e) { float d = v[e] - mean; q += d * d; }
-        }
-#pragma unroll
-        for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-        const float rstd = rsqrtf(q * invD + 1e-5f);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) v[e] = live ? (v[e] - mean) * rstd * gw[e] + gb[e] : 0.0f;
-        return f2_pack8(v);
-      };
-      uint4 keep[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = pw * F2_RPW + j;
-        keep[j] = make_uint4(0, 0, 0, 0);
-        if (has && r < nrows) keep[j] = *reinterpret_cast<const uint4*>(p.x + (row0 + r) * D + lane * 8);
-      }
-#pragma unroll
-      for (int j = 0; j < 8; ++j) keep[j] = ln_row(keep[j], pw * F2_RPW + j < nrows);
       if (it > 0) tc::mbar_wait(&x_free, (it - 1) & 1);
       if (pw == 0) F2_TRACE(2, it, 0);
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const int r = pw * F2_RPW + j;
-        if (has) *reinterpret_cast<uint4*>(sX + (size_t)(lane >> 3) * kblock_bytes(128) + tc::sw128_offset(r, lane & 7)) = keep[j];
-      }
-#pragma unroll 1
-      for (int rb = 8; rb < F2_RPW; rb += 8) {
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = pw * F2_RPW + rb + j;
-          keep[j] = make_uint4(0, 0, 0, 0);
-          if (has && r < nrows) keep[j] = *reinterpret_cast<const uint4*>(p.x + (row0 + r) * D + lane * 8);
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-          const int r = pw * F2_RPW + rb + j;
-          const uint4 o = ln_row(keep[j], r < nrows);
-          if (has) *reinterpret_cast<uint4*>(sX + (size_t)(lane >> 3) * kblock_bytes(128) + tc::sw128_offset(r, lane & 7)) = o;
-        }
-      }
+      // all rows of this warp in flight at once (cp.async straight into the operand image), then LayerNorm in place
+      tc::stage_ln_rows(sX, p.x, D, row0, nrows, D, pw, lane, true, sLw, sLb,
+                        (p.trace && blockIdx.x == 0 && pw == 0 && it < 2) ? p.trace + ((2 * 2 + it) * 32) + 4 : nullptr);
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&x_full);
@@ -538,7 +485,7 @@ int tc_ffn2_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t r
   p.off_h = xb;
   p.off_ring = xb + 4 * kblock_bytes(128);
   p.off_par = p.off_ring + F2_STAGES * F2_BLOCK;
-  p.off_red = p.off_par + (uint32_t)align_up((size_t)(F + 768) * 4, 1024);
+  p.off_red = p.off_par + (uint32_t)align_up((size_t)(F + 1280) * 4, 1024);
   const size_t smem = (size_t)p.off_red + 2048;
   if (smem > 227 * 1024 - 1024) return fail(SMX_ERR_UNSUPPORTED, "ffn: tile does not fit shared memory");
   // cluster size: pairs (or quads) of CTAs share every weight block; single CTAs when there is too little work
