@@ -114,6 +114,7 @@ _PROTOS = {
     "smx_debug_tc_gemm": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),
     "smx_debug_set_trace": (_i, [_vp]),
     "smx_debug_set_ffn_cluster": (_i, [_i]),
+    "smx_debug_set_ffn_version": (_i, [_i]),
 }
 
 

@@ -170,6 +170,7 @@ extern "C" SMX_API int smx_debug_tc_gemm(int layout, int32_t M, int32_t N, int32
 extern "C" SMX_API int smx_debug_set_trace(void* device_u64_buffer) {
   tc_set_trace(device_u64_buffer);
   tc_set_trace_ffn(device_u64_buffer ? (char*)device_u64_buffer + 4096 : nullptr);  // entries 512..1023
+  tc_set_trace_ffn3(device_u64_buffer ? (char*)device_u64_buffer + 4096 : nullptr);
   tc_set_trace_conv(device_u64_buffer ? (char*)device_u64_buffer + 7680 : nullptr); // entries 960..1023
   return SMX_OK;
 }
@@ -177,5 +178,11 @@ extern "C" SMX_API int smx_debug_set_trace(void* device_u64_buffer) {
 // tuning knob: thread-block cluster size (1, 2 or 4) of the persistent FFN kernel (weight multicast)
 extern "C" SMX_API int smx_debug_set_ffn_cluster(int cluster_size) {
   tc_set_ffn_cluster(cluster_size);
+  return SMX_OK;
+}
+
+// A-B switch between the fused FFN generations (3: hidden activation in tensor memory, 2: in shared memory)
+extern "C" SMX_API int smx_debug_set_ffn_version(int version) {
+  tc_set_ffn_version(version);
   return SMX_OK;
 }

@@ -80,6 +80,13 @@ size_t tc_ffn2_packed_bytes(const smx_ffn_weights* w);
 int tc_ffn2_pack(const smx_ffn_weights* w, void* packed, cudaStream_t st);
 int tc_ffn2_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t rows, const __nv_bfloat16* x,
                 const float* oln_w, const float* oln_b, float oln_eps, __nv_bfloat16* y, cudaStream_t st);
+// smx_tc_ffn3.cu: K-FFN v3, hidden activation resident in tensor memory (preferred; same packed images as v2)
+bool tc_ffn3_supported(const smx_ffn_weights* w);
+int tc_ffn3_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t rows, const __nv_bfloat16* x,
+                const float* oln_w, const float* oln_b, float oln_eps, __nv_bfloat16* y, cudaStream_t st);
+void tc_set_ffn_version(int v);  // 2 or 3 (diagnostics / A-B timing)
+int tc_ffn_version();
+void tc_set_trace_ffn3(void* p);
 void tc_set_trace_ffn(void* p);
 void tc_set_trace_conv(void* p);
 void tc_set_ffn_cluster(int cl);  // 1, 2 or 4 CTAs share each weight block (diagnostics / tuning)

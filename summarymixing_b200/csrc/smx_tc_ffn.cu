@@ -361,6 +361,9 @@ size_t tc_ffn_workspace_bytes(const smx_ffn_weights*, int64_t) { return 0; }
 int tc_ffn_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t rows, const __nv_bfloat16* x,
                const float* oln_w, const float* oln_b, float oln_eps, __nv_bfloat16* y, Arena& ws, cudaStream_t st) {
   if (ws.dry) return SMX_OK;
+  // v3 (hidden activation in tensor memory) moves rows with 256-bit global accesses: 32-byte aligned x / y
+  if (tc_ffn_version() == 3 && tc_ffn3_supported(w) && ((uintptr_t)x % 32 == 0) && ((uintptr_t)y % 32 == 0))
+    return tc_ffn3_fwd(w, packed, act, rows, x, oln_w, oln_b, oln_eps, y, st);
   if (tc_ffn2_supported(w)) return tc_ffn2_fwd(w, packed, act, rows, x, oln_w, oln_b, oln_eps, y, st);
   const int D = w->w1.in_dim, F = w->w1.out_dim;
   FfnP p{};

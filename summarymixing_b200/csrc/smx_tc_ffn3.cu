@@ -1,0 +1,545 @@
+// tcgen05 arm of libsmx, part 8: K-FFN v3, the persistent fused macaron feed-forward half-step with the hidden
+// activation resident in TENSOR MEMORY
+//
+//   y = x + 0.5 * ( W2 @ act( W1 @ LN(x) + b1 ) + b2 )        [optionally y = LN_out(y)]
+//   (Conformer.py:470-484, :518, :547)
+//
+// One CTA per SM walks 128-row tiles; the hidden dimension is processed in 128-wide chunks.  Differences from v2
+// (smx_tc_ffn2.cu), each aimed at what the v2 timelines and ncu captures showed (profiles/r01_notes.md):
+//   * GEMM1 (K = D, N = 128) fills one of two fp32 TMEM accumulators; the epilogue warps add b1, activate and write the
+//     chunk back as packed bf16 INTO THE SAME TMEM COLUMNS (the first 64 of the 128): GEMM2 takes it from there as its
+//     A operand (tcgen05.mma with A in tensor memory).  The hidden activation costs no shared-memory write, no
+//     shared-memory operand read and no shared-memory space -- v2 was bound by shared-memory bandwidth plus the L2
+//     latency its 64 KB weight ring could not cover.
+//   * the freed 64 KB go to the weight ring: 16 slots of 8 KB (128 KB in flight / being consumed).
+//   * 16 epilogue warps (four per TMEM lane quadrant, 32 hidden columns each) instead of 8: the chunk epilogue is a
+//     latency chain (tcgen05.ld -> bias/activation -> pack -> tcgen05.st), so more warps shorten it directly.
+//   * the final epilogue needs no staging: a thread owns 64 consecutive output columns of its row and moves them with
+//     256-bit global loads (residual) and stores (y); the output LayerNorm combines per-thread (mean, M2) pairs.
+// Warp roles:  0-15 epilogue | 16-19 prologue (cp.async tile staging + in-place LayerNorm, a thread per row)
+//              | 20 weight producer (cp.async.bulk + mbarrier ring) | 21 MMA issuer
+#include "smx_tc.h"
+#include "smx_tc_common.cuh"
+
+namespace smx {
+
+using tc::kblock_bytes;
+
+constexpr int F3_NEW = 16;                       // epilogue warps
+constexpr int F3_PRO_WARP0 = 16, F3_NPW = 4, F3_PROD_WARP = 20, F3_MMA_WARP = 21;
+constexpr int F3_THREADS = 22 * 32;
+constexpr int F3_HC = 128;                       // hidden chunk width
+constexpr int F3_STAGES = 16;                    // ring slots of 8 KB
+constexpr uint32_t F3_BLOCK = 8192;
+
+struct Ffn3P {
+  const __nv_bfloat16* x; __nv_bfloat16* y; int64_t rows;
+  int D, F, n_tiles;
+  const uint8_t* w1; const uint8_t* w2;   // packed images, 64 x 64 blocks: w1 [F/64][D/64], w2 [D/64][F/64]
+  const float* ln_w; const float* ln_b; const float* b1; const float* b2;
+  const float* oln_w; const float* oln_b; float oln_eps;
+  int act;
+  int gw2;                                 // GEMM2 column group width in 64-col chunks (1, 2 or 4; divides D/64)
+  unsigned long long* trace;
+  uint32_t off_ring, off_par, off_red;
+  int cl2;                                 // 1: CTA pairs (cta_group::2)
+};
+
+#define F3_TRACE(role, it, ev)                                                                                \
+  do {                                                                                                        \
+    if (p.trace && blockIdx.x == 0 && lane == 0 && (it) < 2) p.trace[(((role)*2 + (it)) * 32) + (ev)] = clock64(); \
+  } while (0)
+
+// D[tmem] (+)= A[tmem: 128 lanes x K bf16, two per 32-bit column] * B[smem]^T ; issued by ONE thread
+__device__ __forceinline__ void f3_umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// warp-collective: lane i of warp w writes 16 consecutive 32-bit columns of TMEM lane 32*(w%4)+i
+__device__ __forceinline__ void f3_tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+      :
+      : "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+// warp-collective 16-column fp32 load / store (lane i <-> TMEM lane 32*(w%4)+i)
+__device__ __forceinline__ void f3_tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void f3_tmem_st16f(uint32_t taddr, const float* v) { f3_tmem_st16(taddr, reinterpret_cast<const uint32_t*>(v)); }
+__device__ __forceinline__ void f3_ldg256(const void* p, uint32_t* r) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void f3_stg256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+__device__ __forceinline__ float2 f3_bf2(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u)); }
+
+template <bool OLN, int ACT, bool CL2>  // ACT >= 0: compile-time activation (smx_act); -1: runtime p.act; CL2: CTA pairs
+__global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
+  extern __shared__ __align__(1024) uint8_t smem[];
+  uint8_t* sX = smem;
+  uint8_t* sRing = smem + p.off_ring;
+  float* sPar = reinterpret_cast<float*>(smem + p.off_par);  // [b1 (F) | b2 | oln_w | oln_b | ln_w | ln_b (256 each)]
+  float* sRed = reinterpret_cast<float*>(smem + p.off_red);  // [4 column quarters][128 rows][2]: per-thread (mean, M2)
+  __shared__ __align__(8) uint64_t full_bar[F3_STAGES], peer_full[F3_STAGES], empty_bar[F3_STAGES];
+  __shared__ __align__(8) uint64_t x_full, x_free, acc1_full[2], h_full[2], acc2_full, epi_done;
+  __shared__ uint32_t tmem_base_s;
+
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int D = p.D, nkbD = D / 64, nj = p.F / F3_HC, nkbF = p.F / 64;
+  const int act = ACT >= 0 ? ACT : p.act;
+  // CTA pair (CL2): the two CTAs of a cluster take the two 128-row tiles of a 256-row pair; every tcgen05.mma is issued by
+  // the leader (rank 0) with cta_group::2 and spans both SMs: M = 256 (each CTA its own A operand and accumulators), each
+  // CTA streams only HALF of every weight step (N/2 rows of B) from L2 into its own ring -- half the L2 requests and
+  // shared-memory fill per SM, and the 16-slot ring covers two hidden chunks instead of one.  Cross-CTA protocol:
+  //   leader <- both CTAs : x_full, h_full, epi_done (arrivals from the peer are remote mbarrier arrives), peer_full[s]
+  //                         (the peer's otherwise idle MMA warp relays "my half of step s has landed")
+  //   leader -> both CTAs : empty_bar[s], acc1_full, acc2_full, x_free (tcgen05.commit multicast to the pair)
+  constexpr uint32_t NCTA = CL2 ? 2u : 1u;
+  const uint32_t crank = CL2 ? tc::cluster_ctarank() : 0u;
+  const bool leader = crank == 0;
+
+  if (warp == F3_PROD_WARP) { if (CL2) tc::tmem_alloc2(&tmem_base_s, 512); else tc::tmem_alloc(&tmem_base_s, 512); }
+  if (tid == 0) {
+    for (int s = 0; s < F3_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&peer_full[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    tc::mbar_init(&x_full, F3_NPW * NCTA); tc::mbar_init(&x_free, 1); tc::mbar_init(&acc2_full, 1); tc::mbar_init(&epi_done, F3_NEW * NCTA);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc1_full[i], 1); tc::mbar_init(&h_full[i], F3_NEW * NCTA); }
+    tc::fence_barrier_init();
+  }
+  for (int i = tid; i < p.F; i += F3_THREADS) sPar[i] = p.b1[i];
+  float* sB2 = sPar + p.F; float* sOw = sB2 + 256; float* sOb = sOw + 256; float* sLw = sOb + 256; float* sLb = sLw + 256;
+  for (int i = tid; i < 256; i += F3_THREADS) {
+    sB2[i] = i < D ? p.b2[i] : 0.0f;
+    sOw[i] = (OLN && i < D) ? p.oln_w[i] : 1.0f;
+    sOb[i] = (OLN && i < D) ? p.oln_b[i] : 0.0f;
+    sLw[i] = i < D ? p.ln_w[i] : 1.0f;
+    sLb[i] = i < D ? p.ln_b[i] : 0.0f;
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (CL2) tc::cluster_sync();  // the peer's barriers are initialised before any remote arrive / multicast commit
+  tc::tc_fence_after();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+  const uint32_t t_acc2 = tmem, t_acc1 = tmem + 256;  // acc1 buffers at +256 and +384; the bf16 chunk H[b] overlays acc1[b][0:64]
+  // tile walk: CTA (or pair) g takes tile groups g, g + n_groups, ...; in a pair, rank r takes the r-th tile of the group
+  // (both CTAs run the same number of iterations: the protocol is collective; a tile past the end has nrows <= 0)
+  const int first_base = CL2 ? (int)tc::cluster_id_x() * 2 : (int)blockIdx.x;
+  const int base_step = CL2 ? (int)tc::cluster_count_x() * 2 : (int)gridDim.x;
+  const int gw2 = p.gw2, ng2 = nkbD / gw2;  // GEMM2 column groups (gw2 64-column chunks per MMA)
+  const int sl1 = CL2 ? 1 : 2;              // ring slots this CTA fills per GEMM1 step (N = 128: 64 rows per slot)
+  const int sl2 = CL2 ? gw2 / 2 : gw2;      // ... per GEMM2 step
+  // CTAs walk the hidden chunks in rotated order so that at any moment different SMs ask the L2 for different weight blocks
+  const int rot = (int)((CL2 ? tc::cluster_id_x() : blockIdx.x) % (unsigned)nj);
+  auto chunk_of = [&](int j) { int c = j + rot; return c >= nj ? c - nj : c; };
+  // barriers owned by the leader: an arrival from the peer CTA is a remote arrive
+  auto arrive_leader = [&](uint64_t* bar) { if (CL2) tc::mbar_arrive_remote(bar, 0); else tc::mbar_arrive(bar); };
+
+  if (warp == F3_PROD_WARP) {
+    // =============================== weight producer ===============================
+    // ring order == issue order: W1[0], W1[1], W2[0], W1[2], W2[1], ..., W2[nj-1]; a step takes n consecutive,
+    // n-aligned slots: data arrival on the first slot's full barrier, consumption on every slot's empty barrier
+    if (lane == 0) {
+      int s = 0;
+      uint32_t pe = 0;
+      long long tw_empty = 0, t_tile0 = 0;
+      const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+      auto load = [&](const uint8_t* img, int nkb_img, int c0, int n, int kb) {
+        s = (s + n - 1) & ~(n - 1);
+        if (s >= F3_STAGES) s = 0;
+        const long long c0t = tracing ? clock64() : 0;
+        for (int u = 0; u < n; ++u) {
+          tc::mbar_wait_spin(&empty_bar[s + u], ((pe >> (s + u)) & 1u) ^ 1u);
+          pe ^= 1u << (s + u);
+        }
+        if (tracing) tw_empty += clock64() - c0t;
+        tc::mbar_arrive_expect_tx(&full_bar[s], F3_BLOCK * n);
+        for (int u = 0; u < n; ++u)
+          tc::bulk_g2s(sRing + (size_t)(s + u) * F3_BLOCK, img + (size_t)((c0 + u) * nkb_img + kb) * F3_BLOCK, F3_BLOCK, &full_bar[s]);
+        s += n;
+      };
+      // this CTA's share of a step: all of its 64-row blocks (single CTA) or the rank-th half of them (pair)
+      auto load_g1 = [&](int j) { const int c = chunk_of(j); for (int kb = 0; kb < nkbD; ++kb) load(p.w1, nkbD, 2 * c + (int)crank * sl1 * (CL2 ? 1 : 0), sl1, kb); };
+      auto load_g2 = [&](int j) {
+        const int c = chunk_of(j);
+        for (int g = 0; g < ng2; ++g)
+          for (int u = 0; u < 2; ++u) load(p.w2, nkbF, g * gw2 + (CL2 ? (int)crank * sl2 : 0), sl2, 2 * c + u);
+      };
+      int itp = 0;
+      for (int base = first_base; base < p.n_tiles; base += base_step, ++itp) {
+        if (tracing) t_tile0 = clock64();
+        load_g1(0);
+        for (int j = 0; j < nj; ++j) {
+          if (j + 1 < nj) load_g1(j + 1);
+          load_g2(j);
+        }
+        if (tracing && itp < 2) {  // producer: cycles blocked on empty slots / total cycles for this tile's loads
+          p.trace[((0 * 2 + itp) * 32) + 16] = (unsigned long long)tw_empty;
+          p.trace[((0 * 2 + itp) * 32) + 17] = (unsigned long long)(clock64() - t_tile0);
+        }
+        tw_empty = 0;
+      }
+    }
+  } else if (warp == F3_MMA_WARP) {
+    // =============================== MMA issuer (leader) / "my half has landed" relay (peer) ===============================
+    // Issue order G1(0), G1(1), G2(0), G1(2), G2(1), ...: the tensor pipe executes in issue order, so G1(j+2), which
+    // overwrites acc1[j&1] (and with it H[j&1]), runs after G2(j) has read H[j&1]; G2(j) itself is issued only after
+    // the epilogue has loaded acc1[j&1] and stored H[j&1] (h_full).  No separate "accumulator drained" barrier.
+    int s = 0;
+    uint32_t pf = 0;
+    uint32_t ph_hf = 0;  // per-buffer parity of h_full
+    const uint32_t x0 = tc::smem_u32(sX), r0 = tc::smem_u32(sRing);
+    const uint32_t idesc1 = tc::make_idesc_bf16(128 * NCTA, F3_HC), idesc2 = tc::make_idesc_bf16(128 * NCTA, 64u * gw2);
+    int it = 0;
+    long long tw_ring = 0, tw_h = 0, tw_epi = 0;  // cycles this warp waited for weights / hidden chunks / the drained accumulator
+    const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+    auto ring_next = [&](int n) -> uint32_t {  // wait for the next n-slot step (both halves); returns its shared-memory address
+      s = (s + n - 1) & ~(n - 1);
+      if (s >= F3_STAGES) s = 0;
+      const long long c0 = tracing ? clock64() : 0;
+      tc::mbar_wait_spin(&full_bar[s], (pf >> s) & 1u);
+      if (CL2) {
+        if (leader) tc::mbar_wait_spin_cluster(&peer_full[s], (pf >> s) & 1u);
+        else if (lane == 0) tc::mbar_arrive_remote(&peer_full[s], 0);
+      }
+      if (tracing) tw_ring += clock64() - c0;
+      pf ^= 1u << s;
+      tc::tc_fence_after();
+      return r0 + s * F3_BLOCK;
+    };
+    auto gemm1 = [&](int j) {  // acc1[j&1] = LN(x) @ W1[chunk j]^T
+      const int bsel = j & 1;
+      for (int kb = 0; kb < nkbD; ++kb) {
+        const uint32_t b_addr = ring_next(sl1);
+        const uint32_t a_addr = x0 + kb * kblock_bytes(128);
+        if (leader && tc::elect_one()) {
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) {
+            if (CL2) tc::umma2_bf16(t_acc1 + bsel * F3_HC, tc::make_desc_sw128(a_addr + ks * 32), tc::make_desc_sw128(b_addr + ks * 32), idesc1, (kb == 0 && ks == 0) ? 0u : 1u);
+            else tc::umma_bf16(t_acc1 + bsel * F3_HC, tc::make_desc_sw128(a_addr + ks * 32), tc::make_desc_sw128(b_addr + ks * 32), idesc1, (kb == 0 && ks == 0) ? 0u : 1u);
+          }
+          for (int u = 0; u < sl1; ++u) { if (CL2) tc::umma2_commit(&empty_bar[s + u]); else tc::umma_commit(&empty_bar[s + u]); }
+        }
+        __syncwarp();
+        s += sl1;
+      }
+      if (leader && tc::elect_one()) {
+        if (CL2) { tc::umma2_commit(&acc1_full[bsel]); if (j == nj - 1) tc::umma2_commit(&x_free); }
+        else { tc::umma_commit(&acc1_full[bsel]); if (j == nj - 1) tc::umma_commit(&x_free); }
+      }
+      __syncwarp();
+    };
+    for (int base = first_base; base < p.n_tiles; base += base_step, ++it) {
+      const uint32_t par = it & 1;
+      if (leader) { if (CL2) tc::mbar_wait_cluster(&x_full, par); else tc::mbar_wait(&x_full, par); }
+      tc::tc_fence_after();
+      F3_TRACE(1, it, 0);
+      gemm1(0);
+      for (int j = 0; j < nj; ++j) {
+        if (j + 1 < nj) gemm1(j + 1);
+        const int bsel = j & 1;
+        if (leader) {
+          long long c0 = tracing ? clock64() : 0;
+          if (j == 0 && it > 0) { if (CL2) tc::mbar_wait_cluster(&epi_done, par ^ 1); else tc::mbar_wait(&epi_done, par ^ 1); }  // acc2 drained
+          if (tracing) { const long long c1 = clock64(); tw_epi += c1 - c0; c0 = c1; }
+          if (CL2) tc::mbar_wait_spin_cluster(&h_full[bsel], (ph_hf >> bsel) & 1u); else tc::mbar_wait_spin(&h_full[bsel], (ph_hf >> bsel) & 1u);
+          if (tracing) tw_h += clock64() - c0;
+          ph_hf ^= 1u << bsel;
+        }
+        tc::tc_fence_after();
+        const uint32_t a_tmem = t_acc1 + bsel * F3_HC;  // H[bsel]: K = 128 bf16 in 64 columns
+        for (int g = 0; g < ng2; ++g)
+          for (int u = 0; u < 2; ++u) {  // acc2[:, group g] += H[j][:, K-block u] @ W2[group g, K-block 2j+u]^T
+            const uint32_t b_addr = ring_next(sl2);
+            if (leader && tc::elect_one()) {
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) {
+                if (CL2) tc::umma2_bf16_ts(t_acc2 + g * gw2 * 64, a_tmem + (u * 4 + ks) * 8, tc::make_desc_sw128(b_addr + ks * 32), idesc2, (j == 0 && u == 0 && ks == 0) ? 0u : 1u);
+                else f3_umma_ts(t_acc2 + g * gw2 * 64, a_tmem + (u * 4 + ks) * 8, tc::make_desc_sw128(b_addr + ks * 32), idesc2, (j == 0 && u == 0 && ks == 0) ? 0u : 1u);
+              }
+              for (int v = 0; v < sl2; ++v) { if (CL2) tc::umma2_commit(&empty_bar[s + v]); else tc::umma_commit(&empty_bar[s + v]); }
+            }
+            __syncwarp();
+            s += sl2;
+          }
+        if (j == nj - 1) {
+          if (leader && tc::elect_one()) { if (CL2) tc::umma2_commit(&acc2_full); else tc::umma_commit(&acc2_full); }
+          __syncwarp();
+        }
+        if (j < 4) F3_TRACE(1, it, 1 + j);
+      }
+      F3_TRACE(1, it, 8);
+      if (tracing && lane == 0 && it < 2) {
+        p.trace[((1 * 2 + it) * 32) + 16] = (unsigned long long)tw_ring;
+        p.trace[((1 * 2 + it) * 32) + 17] = (unsigned long long)tw_h;
+        p.trace[((1 * 2 + it) * 32) + 18] = (unsigned long long)tw_epi;
+      }
+      tw_ring = tw_h = tw_epi = 0;
+    }
+  } else if (warp >= F3_PRO_WARP0) {
+    // =============================== prologue: x tile -> LN -> A operand ===============================
+    const int pw = warp - F3_PRO_WARP0;
+    int it = 0;
+    for (int base = first_base; base < p.n_tiles; base += base_step, ++it) {
+      const int64_t row0 = (int64_t)(base + (int)crank) * 128;
+      const int nrows = p.rows - row0 < 128 ? (int)(p.rows - row0) : 128;
+      if (it > 0) tc::mbar_wait(&x_free, (it - 1) & 1);
+      if (pw == 0) F3_TRACE(2, it, 0);
+      tc::stage_ln_rows(sX, p.x, D, row0, nrows, D, pw, lane, true, sLw, sLb,
+                        (p.trace && blockIdx.x == 0 && pw == 0 && it < 2) ? p.trace + ((2 * 2 + it) * 32) + 4 : nullptr);
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) arrive_leader(&x_full);
+      if (pw == 0) F3_TRACE(2, it, 1);
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int q = warp & 3, k = warp >> 2;   // TMEM lane quadrant; column quarter (32 hidden columns / 64 output columns)
+    const int r = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    uint32_t ph_a1f = 0;
+    int it = 0;
+    for (int base = first_base; base < p.n_tiles; base += base_step, ++it) {
+      const uint32_t par = it & 1;
+      const int64_t row0 = (int64_t)(base + (int)crank) * 128;
+      const int nrows = p.rows - row0 < 128 ? (int)(p.rows - row0) : 128;
+      for (int j = 0; j < nj; ++j) {
+        const int bsel = j & 1;
+        tc::mbar_wait(&acc1_full[bsel], (ph_a1f >> bsel) & 1u);
+        ph_a1f ^= 1u << bsel;
+        tc::tc_fence_after();
+        if (warp == 0 && j < 4) F3_TRACE(3, it, 2 * j);
+        float v[32];
+        tc::tmem_ld32(t_acc1 + lane_sel + bsel * F3_HC + k * 32, v);
+        tc::tmem_ld_wait();
+        // H[bsel] overlays the first 64 columns of acc1[bsel]: every warp of this lane quadrant must hold its columns
+        // before any of them writes
+        tc::named_bar_sync(1 + q, 128);
+        const float4* bp = reinterpret_cast<const float4*>(sPar + chunk_of(j) * F3_HC + k * 32);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { const float4 bb = bp[i]; v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w; }
+        tc::act_apply<32>(act, v);
+        uint32_t hp[16];
+#pragma unroll
+        for (int i = 0; i < 16; ++i) hp[i] = tc::pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        f3_tmem_st16(t_acc1 + lane_sel + bsel * F3_HC + k * 16, hp);
+        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) arrive_leader(&h_full[bsel]);
+        if (warp == 0 && j < 4) F3_TRACE(3, it, 2 * j + 1);
+      }
+      // ---- final: y = x + 0.5*(acc2 + b2)  [-> LN_out]; this thread: row r, output columns [64k, 64k + 64), in four
+      // pieces of 16 columns (one 256-bit residual load and one 256-bit store each)
+      const bool active = k * 64 < D;
+      const bool live = r < nrows;
+      uint32_t rres[32];  // the residual (bf16 pairs), fetched while the last GEMMs run
+      if (active) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          if (live) f3_ldg256(p.x + (row0 + r) * D + k * 64 + h * 16, rres + 8 * h);
+          else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) rres[8 * h + e] = 0u;
+          }
+        }
+      }
+      tc::mbar_wait(&acc2_full, par);
+      tc::tc_fence_after();
+      if (warp == 0) F3_TRACE(3, it, 10);
+      float mean_t = 0.0f, m2_t = 0.0f;
+      if (active) {
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+          const int col = k * 64 + h * 16;
+          float v[16];
+          f3_tmem_ld16(t_acc2 + lane_sel + col, v);
+          tc::tmem_ld_wait();
+          const float4* bp = reinterpret_cast<const float4*>(sB2 + col);
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const float4 bb = bp[i];
+            const float2 ra = f3_bf2(rres[h * 8 + 2 * i]), rb = f3_bf2(rres[h * 8 + 2 * i + 1]);
+            v[4 * i] = fmaf(0.5f, v[4 * i] + bb.x, ra.x);
+            v[4 * i + 1] = fmaf(0.5f, v[4 * i + 1] + bb.y, ra.y);
+            v[4 * i + 2] = fmaf(0.5f, v[4 * i + 2] + bb.z, rb.x);
+            v[4 * i + 3] = fmaf(0.5f, v[4 * i + 3] + bb.w, rb.y);
+          }
+          if (OLN) {
+            // running (mean, M2) of this thread's 64 values: exact two-pass inside a piece, Chan's merge across pieces
+            float sm = 0.0f;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) sm += v[e];
+            const float mh = sm * (1.0f / 16.0f);
+            float qh = 0.0f;
+#pragma unroll
+            for (int e = 0; e < 16; ++e) { const float d = v[e] - mh; qh = fmaf(d, d, qh); }
+            if (h == 0) { mean_t = mh; m2_t = qh; }
+            else {
+              const float dl = mh - mean_t, na = 16.0f * h;
+              mean_t += dl * (16.0f / (na + 16.0f));
+              m2_t += qh + dl * dl * (na * 16.0f / (na + 16.0f));
+            }
+            f3_tmem_st16f(t_acc2 + lane_sel + col, v);  // park the pre-norm values for the normalisation pass
+          } else if (live) {
+            uint32_t o[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) o[i] = tc::pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            f3_stg256(p.y + (row0 + r) * D + col, o);
+          }
+        }
+      }
+      if (OLN) {
+        tc::tmem_st_wait();
+        if (active) { sRed[(k * 128 + r) * 2] = mean_t; sRed[(k * 128 + r) * 2 + 1] = m2_t; }
+        tc::named_bar_sync(1 + q, 128);
+        const int nq = D / 64;  // column quarters in use (64 values each)
+        float mean = 0.0f;
+        for (int i = 0; i < nq; ++i) mean += sRed[(i * 128 + r) * 2];
+        mean /= (float)nq;
+        float m2 = 0.0f;
+        for (int i = 0; i < nq; ++i) { const float dl = sRed[(i * 128 + r) * 2] - mean; m2 += sRed[(i * 128 + r) * 2 + 1] + 64.0f * dl * dl; }
+        const float rstd = rsqrtf(m2 / (float)D + p.oln_eps);
+        const float shift = -mean * rstd;
+        if (active) {
+#pragma unroll
+          for (int h = 0; h < 4; ++h) {
+            const int col = k * 64 + h * 16;
+            float v[16];
+            f3_tmem_ld16(t_acc2 + lane_sel + col, v);
+            tc::tmem_ld_wait();
+            const float4* wp = reinterpret_cast<const float4*>(sOw + col);
+            const float4* bp = reinterpret_cast<const float4*>(sOb + col);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const float4 ww = wp[i], bb = bp[i];
+              v[4 * i] = fmaf(fmaf(v[4 * i], rstd, shift), ww.x, bb.x);
+              v[4 * i + 1] = fmaf(fmaf(v[4 * i + 1], rstd, shift), ww.y, bb.y);
+              v[4 * i + 2] = fmaf(fmaf(v[4 * i + 2], rstd, shift), ww.z, bb.z);
+              v[4 * i + 3] = fmaf(fmaf(v[4 * i + 3], rstd, shift), ww.w, bb.w);
+            }
+            if (live) {
+              uint32_t o[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) o[i] = tc::pack_bf16x2(v[2 * i], v[2 * i + 1]);
+              f3_stg256(p.y + (row0 + r) * D + col, o);
+            }
+          }
+        }
+        tc::named_bar_sync(1 + q, 128);  // sRed is rewritten by the next tile
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) arrive_leader(&epi_done);
+      if (warp == 0) F3_TRACE(3, it, 11);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (CL2) tc::cluster_sync();  // no CTA leaves (or frees tensor memory) while the pair's MMAs, multicast commits or remote arrives may still land
+  if (warp == F3_PROD_WARP) { if (CL2) tc::tmem_dealloc2(tmem, 512); else tc::tmem_dealloc(tmem, 512); }
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side (weights packed by tc_ffn2_pack: the images are shared with v2)
+// ---------------------------------------------------------------------------------------------
+static int g_ffn_ver = 3;   // smx_debug_set_ffn_version: 2 = shared-memory hidden (v2), 3 = TMEM hidden, single CTAs (default),
+static int g_ffn_pair = 0;  //                            4 = TMEM hidden + CTA pairs (cta_group::2; bit-identical, measured slower)
+void tc_set_ffn_version(int v) { g_ffn_ver = v == 2 ? 2 : 3; g_ffn_pair = v == 4 ? 1 : 0; }
+int tc_ffn_version() { return g_ffn_ver; }
+
+bool tc_ffn3_supported(const smx_ffn_weights* w) {
+  if (!tc_ffn2_supported(w)) return false;
+  const int D = w->w1.in_dim;
+  return D % 64 == 0 && D <= 256;
+}
+
+static unsigned long long* g_trace3f = nullptr;
+void tc_set_trace_ffn3(void* p) { g_trace3f = (unsigned long long*)p; }
+
+static int ffn3_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+template <bool OLN, bool CL2>
+static int launch_ffn3(const Ffn3P& p, unsigned grid, size_t smem, cudaStream_t st) {
+  cudaError_t e;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(F3_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = CL2 ? 2u : 1u; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+#define SMX_FFN3_LAUNCH(A)                                                                                   \
+  e = cudaFuncSetAttribute(ffn3_kernel<OLN, A, CL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
+  if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(ffn3_kernel): %s", cudaGetErrorString(e)); \
+  e = cudaLaunchKernelEx(&cfg, ffn3_kernel<OLN, A, CL2>, p);                                                 \
+  if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaLaunchKernelEx(ffn3_kernel): %s", cudaGetErrorString(e));
+  switch (p.act) {
+    case SMX_ACT_SWISH: SMX_FFN3_LAUNCH(SMX_ACT_SWISH); break;
+    case SMX_ACT_GELU: SMX_FFN3_LAUNCH(SMX_ACT_GELU); break;
+    case SMX_ACT_RELU: SMX_FFN3_LAUNCH(SMX_ACT_RELU); break;
+    default: SMX_FFN3_LAUNCH(-1); break;
+  }
+#undef SMX_FFN3_LAUNCH
+  count_tc_launch();
+  return check_launch("ffn3_kernel");
+}
+
+int tc_ffn3_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t rows, const __nv_bfloat16* x,
+                const float* oln_w, const float* oln_b, float oln_eps, __nv_bfloat16* y, cudaStream_t st) {
+  const int D = w->w1.in_dim, F = w->w1.out_dim;
+  Ffn3P p{};
+  p.x = x; p.y = y; p.rows = rows; p.D = D; p.F = F;
+  p.n_tiles = (int)((rows + 127) / 128);
+  p.w1 = (const uint8_t*)packed;
+  p.w2 = p.w1 + align_up((size_t)D * F * 2, 1024);
+  p.ln_w = w->ln_w; p.ln_b = w->ln_b; p.b1 = w->w1.b; p.b2 = w->w2.b;
+  p.oln_w = oln_w; p.oln_b = oln_b; p.oln_eps = oln_eps;
+  p.act = act;
+  const int nc = D / 64;
+  p.gw2 = nc % 4 == 0 ? 4 : (nc % 2 == 0 ? 2 : 1);
+  p.trace = g_trace3f;
+  p.off_ring = (uint32_t)nc * kblock_bytes(128);
+  p.off_par = p.off_ring + F3_STAGES * F3_BLOCK;
+  p.off_red = p.off_par + (uint32_t)align_up((size_t)(F + 1280) * 4, 1024);
+  const size_t smem = (size_t)p.off_red + 4096;
+  if (smem > 227 * 1024 - 1024) return fail(SMX_ERR_UNSUPPORTED, "ffn: tile does not fit shared memory");
+  // CTA pairs when the weight steps split evenly over two CTAs (D a multiple of 128) and there is more than one tile
+  p.cl2 = (g_ffn_pair && D % 128 == 0 && p.n_tiles >= 2) ? 1 : 0;
+  if (p.cl2) {
+    const int n_pairs = (p.n_tiles + 1) / 2, max_pairs = ffn3_sms() / 2;
+    const unsigned grid = 2u * (unsigned)(n_pairs < max_pairs ? n_pairs : max_pairs);
+    return oln_w ? launch_ffn3<true, true>(p, grid, smem, st) : launch_ffn3<false, true>(p, grid, smem, st);
+  }
+  const unsigned grid = (unsigned)(p.n_tiles < ffn3_sms() ? p.n_tiles : ffn3_sms());
+  return oln_w ? launch_ffn3<true, false>(p, grid, smem, st) : launch_ffn3<false, false>(p, grid, smem, st);
+}
+
+}  // namespace smx

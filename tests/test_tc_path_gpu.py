@@ -166,3 +166,30 @@ def test_conformer_encoder_tc_vs_oracle_and_fp32_arm():
     assert L.lib().smx_tc_launch_count() - n0 == 6 * n
     assert float((y32.cpu() - y_or).abs().max()) < 5e-4
     _check(y16, y_or, "conformer encoder (4 layers) bf16 tensor-core arm", abs_tol=6e-2, rel_tol=3e-2)
+
+
+@pytest.mark.parametrize("version", [2, 3, 4])
+def test_ffn_kernel_generations_agree(version):
+    """K-FFN v2 (hidden chunk in shared memory), v3 (hidden chunk in tensor memory, A operand of GEMM2 read from TMEM)
+    and v4 (v3 on CTA pairs, cta_group::2) compute the same layer: each against the oracle at the bench width, with
+    more tiles than SMs and a ragged last tile."""
+    torch.manual_seed(31)
+    D = 256
+    m = S.ConformerEncoderLayer(D, 1024, 4, 31, attention_type="SummaryMixing", local_proj_hid_dim=[D],
+                                local_proj_out_dim=D, summary_hid_dim=[D]).eval()
+    _perturb(m, 31)
+    B, T = 21, 933
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(B, T, D, generator=g).to(torch.bfloat16)
+    lens = torch.randint(300, T + 1, (B,), generator=g)
+    lens[0] = T
+    mask = torch.arange(T)[None] < lens[:, None]
+    y_or = O.conformer_layer(x.float(), dict(m.state_dict()), "", act="swish", src_key_padding_mask=mask)
+    try:
+        assert L.lib().smx_debug_set_ffn_version(version) == 0
+        with torch.no_grad():
+            y = m.to(DEV)(x.to(DEV), src_key_padding_mask=mask.to(DEV))[0]
+        torch.cuda.synchronize()
+    finally:
+        L.lib().smx_debug_set_ffn_version(3)
+    _check(y, y_or, f"conformer layer, FFN generation {version}", abs_tol=4e-2, rel_tol=2e-2)

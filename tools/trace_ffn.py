@@ -35,6 +35,12 @@ for r in range(5):
             continue
         print(f"  {roles[r]:9s} it{it}: " + " ".join(f"{int(v) - t0:7d}" if int(v) else "      -" for v in ev[:13]))
 
+for it in range(2):
+    w = t[1, it, 16:19]
+    print(f"  issuer it{it} waited (cycles): weights {int(w[0])}, hidden chunk {int(w[1])}, drained accumulator {int(w[2])}")
+for it in range(2):
+    w = t[0, it, 16:18]
+    print(f"  producer it{it}: blocked on empty slots {int(w[0])} of {int(w[1])} cycles")
 fine = buf.cpu()[512 + 320:512 + 360]
 print("issuer, chunk 2 of tile 0 (gemm1(3): a1e-wait b/a, 4 x (full-wait b/a); h_full wait b/a; gemm2(2): 2 x (full-wait b/a)):")
 print("  " + " ".join(f"{int(v) - t0:7d}" if int(v) else "      -" for v in fine[:20]))
