@@ -293,6 +293,9 @@ SMX_API int smx_debug_set_ffn_cluster(int cluster_size);
  * with CTA pairs: cta_group::2 MMAs, each CTA streams half of every weight step) or 2 (hidden activation staged through
  * shared memory).  All compute the same function; diagnostics / A-B timing. */
 SMX_API int smx_debug_set_ffn_version(int version);
+/* Programmatic dependent launch of the fused kernels (default on): a kernel's set-up overlaps the tail of its
+ * predecessor; results are identical.  Diagnostics / A-B timing. */
+SMX_API int smx_debug_set_pdl(int on);
 
 #ifdef __cplusplus
 }

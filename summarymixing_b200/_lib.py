@@ -115,6 +115,7 @@ _PROTOS = {
     "smx_debug_set_trace": (_i, [_vp]),
     "smx_debug_set_ffn_cluster": (_i, [_i]),
     "smx_debug_set_ffn_version": (_i, [_i]),
+    "smx_debug_set_pdl": (_i, [_i]),
 }
 
 

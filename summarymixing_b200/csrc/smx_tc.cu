@@ -181,6 +181,17 @@ extern "C" SMX_API int smx_debug_set_ffn_cluster(int cluster_size) {
   return SMX_OK;
 }
 
+namespace smx {
+static int g_pdl = 1;
+bool tc_pdl_enabled() { return g_pdl != 0; }
+void tc_set_pdl(int on) { g_pdl = on ? 1 : 0; }
+}  // namespace smx
+// programmatic dependent launch of the fused kernels on (default) / off
+extern "C" SMX_API int smx_debug_set_pdl(int on) {
+  tc_set_pdl(on);
+  return SMX_OK;
+}
+
 // A-B switch between the fused FFN generations (3: hidden activation in tensor memory, 2: in shared memory)
 extern "C" SMX_API int smx_debug_set_ffn_version(int version) {
   tc_set_ffn_version(version);

@@ -1,8 +1,30 @@
 // Declarations of the tcgen05 (bf16 tensor-core) arm of libsmx.
 #pragma once
+#include <utility>
 #include "smx_internal.h"
 
 namespace smx {
+
+// ---- programmatic dependent launch (PDL) -----------------------------------------------------------------
+// The fused kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization: every kernel executes
+// griddepcontrol.launch_dependents when it starts and griddepcontrol.wait before its first access to activations, so the
+// next kernel's CTAs take over SMs as soon as this kernel's CTAs leave them and run their set-up (barrier init, TMEM
+// allocation, parameter staging) and their launch latency under the tail of this kernel instead of after it.
+// Weights / parameters are never written by a kernel, so reading them before the wait is safe.
+bool tc_pdl_enabled();
+void tc_set_pdl(int on);
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, unsigned cluster_x,
+                              Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  unsigned n = 0;
+  if (tc_pdl_enabled()) { attr[n].id = cudaLaunchAttributeProgrammaticStreamSerialization; attr[n].val.programmaticStreamSerializationAllowed = 1; ++n; }
+  if (cluster_x > 1) { attr[n].id = cudaLaunchAttributeClusterDimension; attr[n].val.clusterDim.x = cluster_x; attr[n].val.clusterDim.y = 1; attr[n].val.clusterDim.z = 1; ++n; }
+  cfg.attrs = attr; cfg.numAttrs = n;
+  return cudaLaunchKernelEx(&cfg, kern, std::forward<Args>(args)...);
+}
 
 // ---- smx_tc.cu: packing for the self-test -------------------------------------------------------
 size_t tc_packed_bytes(int N, int K, int NT);
@@ -82,6 +104,8 @@ int tc_ffn2_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t r
                 const float* oln_w, const float* oln_b, float oln_eps, __nv_bfloat16* y, cudaStream_t st);
 // smx_tc_ffn3.cu: K-FFN v3, hidden activation resident in tensor memory (preferred; same packed images as v2)
 bool tc_ffn3_supported(const smx_ffn_weights* w);
+size_t tc_ffn3_packed_bytes(const smx_ffn_weights* w);  // v2 images + the same blocks in ring-step order
+int tc_ffn3_pack(const smx_ffn_weights* w, void* packed, cudaStream_t st);
 int tc_ffn3_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t rows, const __nv_bfloat16* x,
                 const float* oln_w, const float* oln_b, float oln_eps, __nv_bfloat16* y, cudaStream_t st);
 void tc_set_ffn_version(int v);  // 2 or 3 (diagnostics / A-B timing)

@@ -111,6 +111,8 @@ __global__ void __launch_bounds__(256) cell_finalize2_kernel(const CellFinP p) {
   const int b = blockIdx.x, n0 = blockIdx.y * 64;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int Ds = p.Ds;
+  tc::pdl_launch_dependents();
+  tc::pdl_wait();  // the column sums come from pass A
   float cnt;
   if (p.mask) {  // number of valid frames (integer-valued float, like torch.sum(mask) in the reference)
     float c = 0.0f;
@@ -202,6 +204,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
   constexpr int NG = PHASE == 0 ? 2 : (PHASE == 1 ? 3 : 1);
   const int act = ACT >= 0 ? ACT : p.act;  // compile-time activation: one tight loop per epilogue instead of a 7-way switch
 
+  tc::pdl_launch_dependents();
   if (warp == CF_PROD_WARP) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int s = 0; s < p.n_stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
@@ -224,6 +227,7 @@ __global__ void __launch_bounds__(CF_THREADS, 1) cell_kernel(const CellFP p) {
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
+  tc::pdl_wait();  // x / column sums / c[b] come from the preceding kernels (everything above touched only parameters)
   const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
   const int first_tile = blockIdx.x, tile_step = gridDim.x;
 
@@ -702,7 +706,8 @@ template <int PHASE, int ACT>
 static int launch_cell_act(const CellFP& p, unsigned grid, size_t smem, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(cell_kernel<PHASE, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(cell_kernel): %s", cudaGetErrorString(e));
-  cell_kernel<PHASE, ACT><<<grid, CF_THREADS, smem, st>>>(p);
+  e = launch_pdl(cell_kernel<PHASE, ACT>, dim3(grid), dim3(CF_THREADS), smem, st, 1u, p);
+  if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaLaunchKernelEx(cell_kernel): %s", cudaGetErrorString(e));
   count_tc_launch();
   return check_launch("cell_kernel");
 }
@@ -766,7 +771,8 @@ int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
     f.ln_w = w->use_layernorm ? w->summary_norm_w : nullptr;
     f.ln_b = w->use_layernorm ? w->summary_norm_b : nullptr;
     f.T = T; f.tpu = tpu; f.Ds = Ds; f.Dl = Dl; f.Dout = Dout;
-    cell_finalize2_kernel<<<dim3(B, (Dout + 63) / 64), 256, 0, st>>>(f);
+    cudaError_t e = launch_pdl(cell_finalize2_kernel, dim3(B, (Dout + 63) / 64), dim3(256), 0, st, 1u, f);
+    if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaLaunchKernelEx(cell_finalize2_kernel): %s", cudaGetErrorString(e));
     count_launch();
     SMX_TRY(check_launch("cell_finalize2_kernel"));
   }

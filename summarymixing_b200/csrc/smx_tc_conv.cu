@@ -82,6 +82,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
   const int gw = p.gw, ng = nkb / gw;
   const int act = ACT >= 0 ? ACT : p.act;
 
+  tc::pdl_launch_dependents();
   if (warp == CV_PROD_WARP) tc::tmem_alloc(&tmem_base_s, 256);
   if (tid == 0) {
     for (int s = 0; s < CV_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
@@ -162,6 +163,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
 #pragma unroll
     for (int j = 0; j < K; ++j) w2[j] = make_float2(p.dw_w[(size_t)c0 * K + j], p.dw_w[(size_t)(c0 + 1) * K + j]);
     const float2 bias2 = make_float2(p.dw_b ? p.dw_b[c0] : 0.0f, p.dw_b ? p.dw_b[c0 + 1] : 0.0f);
+    tc::pdl_wait();  // g / residual come from the preceding kernels (the taps above are parameters)
     const float2 lw2 = make_float2(sPar[256 + c0], sPar[256 + c0 + 1]), lb2 = make_float2(sPar[512 + c0], sPar[512 + c0 + 1]);
     constexpr float invD = 1.0f / (float)D;
     constexpr int cpr = D / 8;
@@ -350,7 +352,8 @@ template <int ACT, int D>
 static int launch_conv_d(const ConvFP& p, unsigned grid, size_t smem, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(conv_kernel<31, ACT, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(conv_kernel): %s", cudaGetErrorString(e));
-  conv_kernel<31, ACT, D><<<grid, CV_THREADS, smem, st>>>(p);
+  e = launch_pdl(conv_kernel<31, ACT, D>, dim3(grid), dim3(CV_THREADS), smem, st, 1u, p);
+  if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaLaunchKernelEx(conv_kernel): %s", cudaGetErrorString(e));
   count_tc_launch();
   return check_launch("conv_kernel");
 }

@@ -317,6 +317,7 @@ bool tc_ffn_supported(const smx_ffn_weights* w) {
 }
 size_t tc_ffn_packed_bytes(const smx_ffn_weights* w) {
   if (!tc_ffn_supported(w)) return 0;
+  if (tc_ffn3_supported(w)) return tc_ffn3_packed_bytes(w);
   if (tc_ffn2_supported(w)) return tc_ffn2_packed_bytes(w);
   return (size_t)(w->w1.out_dim / FFN_HC) * ffn_stage_bytes(w->w1.in_dim);
 }
@@ -347,6 +348,7 @@ __global__ void ffn_pack_kernel(const float* w1, const float* w2, int D, int F, 
 
 int tc_ffn_pack(const smx_ffn_weights* w, void* packed, cudaStream_t st) {
   if (!tc_ffn_supported(w)) return fail(SMX_ERR_UNSUPPORTED, "ffn configuration not handled by the tensor-core arm");
+  if (tc_ffn3_supported(w)) return tc_ffn3_pack(w, packed, st);
   if (tc_ffn2_supported(w)) return tc_ffn2_pack(w, packed, st);
   const int D = w->w1.in_dim, F = w->w1.out_dim;
   const uint32_t sb = ffn_stage_bytes(D), w2_off = (D / 64) * kblock_bytes(FFN_HC);

@@ -29,17 +29,17 @@ constexpr int F3_NEW = 16;                       // epilogue warps
 constexpr int F3_PRO_WARP0 = 16, F3_NPW = 4, F3_PROD_WARP = 20, F3_MMA_WARP = 21;
 constexpr int F3_THREADS = 22 * 32;
 constexpr int F3_HC = 128;                       // hidden chunk width
-constexpr int F3_STAGES = 16;                    // ring slots of 8 KB
-constexpr uint32_t F3_BLOCK = 8192;
+constexpr int F3_STAGES = 8;                     // ring slots: 4 x 32 KB (one CTA per tile) or 8 x 16 KB (CTA pairs)
+constexpr uint32_t F3_RING_BYTES = 131072;
+constexpr uint32_t F3_BLOCK = 8192;              // one 64 x 64 bf16 weight block
 
 struct Ffn3P {
   const __nv_bfloat16* x; __nv_bfloat16* y; int64_t rows;
   int D, F, n_tiles;
-  const uint8_t* w1; const uint8_t* w2;   // packed images, 64 x 64 blocks: w1 [F/64][D/64], w2 [D/64][F/64]
+  const uint8_t* w1; const uint8_t* w2;   // v3 images of 64 x 64 blocks in step order: w1 [F/128][D/64][2], w2 [F/64][D/64]
   const float* ln_w; const float* ln_b; const float* b1; const float* b2;
   const float* oln_w; const float* oln_b; float oln_eps;
   int act;
-  int gw2;                                 // GEMM2 column group width in 64-col chunks (1, 2 or 4; divides D/64)
   unsigned long long* trace;
   uint32_t off_ring, off_par, off_red;
   int cl2;                                 // 1: CTA pairs (cta_group::2)
@@ -119,6 +119,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
   const uint32_t crank = CL2 ? tc::cluster_ctarank() : 0u;
   const bool leader = crank == 0;
 
+  tc::pdl_launch_dependents();  // the next kernel may start taking over SMs as CTAs of this grid leave them
   if (warp == F3_PROD_WARP) { if (CL2) tc::tmem_alloc2(&tmem_base_s, 512); else tc::tmem_alloc(&tmem_base_s, 512); }
   if (tid == 0) {
     for (int s = 0; s < F3_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&peer_full[s], 1); tc::mbar_init(&empty_bar[s], 1); }
@@ -139,15 +140,21 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
   __syncthreads();
   if (CL2) tc::cluster_sync();  // the peer's barriers are initialised before any remote arrive / multicast commit
   tc::tc_fence_after();
+  tc::pdl_wait();  // the producer of x has completed (everything above touched only parameters)
   const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
   const uint32_t t_acc2 = tmem, t_acc1 = tmem + 256;  // acc1 buffers at +256 and +384; the bf16 chunk H[b] overlays acc1[b][0:64]
   // tile walk: CTA (or pair) g takes tile groups g, g + n_groups, ...; in a pair, rank r takes the r-th tile of the group
   // (both CTAs run the same number of iterations: the protocol is collective; a tile past the end has nrows <= 0)
   const int first_base = CL2 ? (int)tc::cluster_id_x() * 2 : (int)blockIdx.x;
   const int base_step = CL2 ? (int)tc::cluster_count_x() * 2 : (int)gridDim.x;
-  const int gw2 = p.gw2, ng2 = nkbD / gw2;  // GEMM2 column groups (gw2 64-column chunks per MMA)
-  const int sl1 = CL2 ? 1 : 2;              // ring slots this CTA fills per GEMM1 step (N = 128: 64 rows per slot)
-  const int sl2 = CL2 ? gw2 / 2 : gw2;      // ... per GEMM2 step
+  // Weight ring: step-granular slots (one full and one empty barrier, one tcgen05.commit and -- single CTA -- one bulk copy
+  // per step: the single-thread roles pay ~100+ cycles of latency for every mbarrier / commit operation, so their count
+  // per step, not the bytes, sets the pace of the ring).  Steps per hidden chunk: ceil(nkbD / 2) GEMM1 steps of up to two
+  // K-blocks (N = 128 rows each) and two GEMM2 steps of one K-block (N = D rows).  The v3 weight images are laid out in
+  // step order (tc_ffn3_pack), so a step is one contiguous run of 8 KB blocks.
+  const int ng1 = (nkbD + 1) / 2;
+  const uint32_t slot_bytes = CL2 ? 16384u : 32768u;
+  const int nslots = (int)(F3_RING_BYTES / slot_bytes);
   // CTAs walk the hidden chunks in rotated order so that at any moment different SMs ask the L2 for different weight blocks
   const int rot = (int)((CL2 ? tc::cluster_id_x() : blockIdx.x) % (unsigned)nj);
   auto chunk_of = [&](int j) { int c = j + rot; return c >= nj ? c - nj : c; };
@@ -156,33 +163,44 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
 
   if (warp == F3_PROD_WARP) {
     // =============================== weight producer ===============================
-    // ring order == issue order: W1[0], W1[1], W2[0], W1[2], W2[1], ..., W2[nj-1]; a step takes n consecutive,
-    // n-aligned slots: data arrival on the first slot's full barrier, consumption on every slot's empty barrier
+    // ring order == issue order: W1[0], W1[1], W2[0], W1[2], W2[1], ..., W2[nj-1]
     if (lane == 0) {
       int s = 0;
       uint32_t pe = 0;
       long long tw_empty = 0, t_tile0 = 0;
       const bool tracing = p.trace != nullptr && blockIdx.x == 0;
-      auto load = [&](const uint8_t* img, int nkb_img, int c0, int n, int kb) {
-        s = (s + n - 1) & ~(n - 1);
-        if (s >= F3_STAGES) s = 0;
+      auto next_slot = [&](uint32_t bytes) -> uint8_t* {  // wait until the slot is free, arm its full barrier
         const long long c0t = tracing ? clock64() : 0;
-        for (int u = 0; u < n; ++u) {
-          tc::mbar_wait_spin(&empty_bar[s + u], ((pe >> (s + u)) & 1u) ^ 1u);
-          pe ^= 1u << (s + u);
-        }
+        tc::mbar_wait_spin(&empty_bar[s], ((pe >> s) & 1u) ^ 1u);
+        pe ^= 1u << s;
         if (tracing) tw_empty += clock64() - c0t;
-        tc::mbar_arrive_expect_tx(&full_bar[s], F3_BLOCK * n);
-        for (int u = 0; u < n; ++u)
-          tc::bulk_g2s(sRing + (size_t)(s + u) * F3_BLOCK, img + (size_t)((c0 + u) * nkb_img + kb) * F3_BLOCK, F3_BLOCK, &full_bar[s]);
-        s += n;
+        tc::mbar_arrive_expect_tx(&full_bar[s], bytes);
+        return sRing + (size_t)s * slot_bytes;
       };
-      // this CTA's share of a step: all of its 64-row blocks (single CTA) or the rank-th half of them (pair)
-      auto load_g1 = [&](int j) { const int c = chunk_of(j); for (int kb = 0; kb < nkbD; ++kb) load(p.w1, nkbD, 2 * c + (int)crank * sl1 * (CL2 ? 1 : 0), sl1, kb); };
+      auto load_g1 = [&](int j) {
+        const int c = chunk_of(j);
+        for (int h = 0; h < ng1; ++h) {
+          const int nk = nkbD - 2 * h < 2 ? nkbD - 2 * h : 2;
+          const uint8_t* src = p.w1 + (size_t)((c * nkbD + 2 * h) * 2) * F3_BLOCK;  // blocks [c][kb][u]
+          if (!CL2) {
+            uint8_t* dst = next_slot((uint32_t)nk * 2u * F3_BLOCK);
+            tc::bulk_g2s(dst, src, (uint32_t)nk * 2u * F3_BLOCK, &full_bar[s]);
+          } else {  // this CTA's 64 of the 128 rows of every K-block
+            uint8_t* dst = next_slot((uint32_t)nk * F3_BLOCK);
+            for (int kbl = 0; kbl < nk; ++kbl) tc::bulk_g2s(dst + (size_t)kbl * F3_BLOCK, src + (size_t)(kbl * 2 + (int)crank) * F3_BLOCK, F3_BLOCK, &full_bar[s]);
+          }
+          if (++s == nslots) s = 0;
+        }
+      };
       auto load_g2 = [&](int j) {
         const int c = chunk_of(j);
-        for (int g = 0; g < ng2; ++g)
-          for (int u = 0; u < 2; ++u) load(p.w2, nkbF, g * gw2 + (CL2 ? (int)crank * sl2 : 0), sl2, 2 * c + u);
+        for (int u = 0; u < 2; ++u) {
+          const uint8_t* src = p.w2 + (size_t)((2 * c + u) * nkbD) * F3_BLOCK;  // blocks [kb of F][n-chunk]
+          const uint32_t bytes = (uint32_t)nkbD * F3_BLOCK / NCTA;              // this CTA's share of the D rows
+          uint8_t* dst = next_slot(bytes);
+          tc::bulk_g2s(dst, src + (size_t)crank * bytes, bytes, &full_bar[s]);
+          if (++s == nslots) s = 0;
+        }
       };
       int itp = 0;
       for (int base = first_base; base < p.n_tiles; base += base_step, ++itp) {
@@ -208,13 +226,12 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
     uint32_t pf = 0;
     uint32_t ph_hf = 0;  // per-buffer parity of h_full
     const uint32_t x0 = tc::smem_u32(sX), r0 = tc::smem_u32(sRing);
-    const uint32_t idesc1 = tc::make_idesc_bf16(128 * NCTA, F3_HC), idesc2 = tc::make_idesc_bf16(128 * NCTA, 64u * gw2);
+    const uint32_t idesc1 = tc::make_idesc_bf16(128 * NCTA, F3_HC), idesc2 = tc::make_idesc_bf16(128 * NCTA, (uint32_t)D);
+    const uint32_t g1_kb_bytes = 2u * F3_BLOCK / NCTA;  // one K-block of a GEMM1 step in this CTA's slot (128 or 64 rows)
     int it = 0;
     long long tw_ring = 0, tw_h = 0, tw_epi = 0;  // cycles this warp waited for weights / hidden chunks / the drained accumulator
     const bool tracing = p.trace != nullptr && blockIdx.x == 0;
-    auto ring_next = [&](int n) -> uint32_t {  // wait for the next n-slot step (both halves); returns its shared-memory address
-      s = (s + n - 1) & ~(n - 1);
-      if (s >= F3_STAGES) s = 0;
+    auto ring_next = [&]() -> uint32_t {  // wait for the next step (both halves); returns its shared-memory address
       const long long c0 = tracing ? clock64() : 0;
       tc::mbar_wait_spin(&full_bar[s], (pf >> s) & 1u);
       if (CL2) {
@@ -224,23 +241,31 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
       if (tracing) tw_ring += clock64() - c0;
       pf ^= 1u << s;
       tc::tc_fence_after();
-      return r0 + s * F3_BLOCK;
+      return r0 + (uint32_t)s * slot_bytes;
+    };
+    auto release = [&]() {  // one commit per step: the slot is free when the MMAs issued so far have completed
+      if (leader && tc::elect_one()) { if (CL2) tc::umma2_commit(&empty_bar[s]); else tc::umma_commit(&empty_bar[s]); }
+      __syncwarp();
+      if (++s == nslots) s = 0;
     };
     auto gemm1 = [&](int j) {  // acc1[j&1] = LN(x) @ W1[chunk j]^T
       const int bsel = j & 1;
-      for (int kb = 0; kb < nkbD; ++kb) {
-        const uint32_t b_addr = ring_next(sl1);
-        const uint32_t a_addr = x0 + kb * kblock_bytes(128);
+      for (int h = 0; h < ng1; ++h) {
+        const int nk = nkbD - 2 * h < 2 ? nkbD - 2 * h : 2;
+        const uint32_t b_addr = ring_next();
         if (leader && tc::elect_one()) {
+          for (int kbl = 0; kbl < nk; ++kbl) {
+            const uint32_t a_addr = x0 + (uint32_t)(2 * h + kbl) * kblock_bytes(128), bk = b_addr + (uint32_t)kbl * g1_kb_bytes;
 #pragma unroll
-          for (int ks = 0; ks < 4; ++ks) {
-            if (CL2) tc::umma2_bf16(t_acc1 + bsel * F3_HC, tc::make_desc_sw128(a_addr + ks * 32), tc::make_desc_sw128(b_addr + ks * 32), idesc1, (kb == 0 && ks == 0) ? 0u : 1u);
-            else tc::umma_bf16(t_acc1 + bsel * F3_HC, tc::make_desc_sw128(a_addr + ks * 32), tc::make_desc_sw128(b_addr + ks * 32), idesc1, (kb == 0 && ks == 0) ? 0u : 1u);
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t acc = (h == 0 && kbl == 0 && ks == 0) ? 0u : 1u;
+              if (CL2) tc::umma2_bf16(t_acc1 + bsel * F3_HC, tc::make_desc_sw128(a_addr + ks * 32), tc::make_desc_sw128(bk + ks * 32), idesc1, acc);
+              else tc::umma_bf16(t_acc1 + bsel * F3_HC, tc::make_desc_sw128(a_addr + ks * 32), tc::make_desc_sw128(bk + ks * 32), idesc1, acc);
+            }
           }
-          for (int u = 0; u < sl1; ++u) { if (CL2) tc::umma2_commit(&empty_bar[s + u]); else tc::umma_commit(&empty_bar[s + u]); }
         }
         __syncwarp();
-        s += sl1;
+        release();
       }
       if (leader && tc::elect_one()) {
         if (CL2) { tc::umma2_commit(&acc1_full[bsel]); if (j == nj - 1) tc::umma2_commit(&x_free); }
@@ -267,20 +292,19 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
         }
         tc::tc_fence_after();
         const uint32_t a_tmem = t_acc1 + bsel * F3_HC;  // H[bsel]: K = 128 bf16 in 64 columns
-        for (int g = 0; g < ng2; ++g)
-          for (int u = 0; u < 2; ++u) {  // acc2[:, group g] += H[j][:, K-block u] @ W2[group g, K-block 2j+u]^T
-            const uint32_t b_addr = ring_next(sl2);
-            if (leader && tc::elect_one()) {
+        for (int u = 0; u < 2; ++u) {  // acc2 += H[j][:, K-block u] @ W2[:, K-block 2j+u]^T
+          const uint32_t b_addr = ring_next();
+          if (leader && tc::elect_one()) {
 #pragma unroll
-              for (int ks = 0; ks < 4; ++ks) {
-                if (CL2) tc::umma2_bf16_ts(t_acc2 + g * gw2 * 64, a_tmem + (u * 4 + ks) * 8, tc::make_desc_sw128(b_addr + ks * 32), idesc2, (j == 0 && u == 0 && ks == 0) ? 0u : 1u);
-                else f3_umma_ts(t_acc2 + g * gw2 * 64, a_tmem + (u * 4 + ks) * 8, tc::make_desc_sw128(b_addr + ks * 32), idesc2, (j == 0 && u == 0 && ks == 0) ? 0u : 1u);
-              }
-              for (int v = 0; v < sl2; ++v) { if (CL2) tc::umma2_commit(&empty_bar[s + v]); else tc::umma_commit(&empty_bar[s + v]); }
+            for (int ks = 0; ks < 4; ++ks) {
+              const uint32_t acc = (j == 0 && u == 0 && ks == 0) ? 0u : 1u;
+              if (CL2) tc::umma2_bf16_ts(t_acc2, a_tmem + (u * 4 + ks) * 8, tc::make_desc_sw128(b_addr + ks * 32), idesc2, acc);
+              else f3_umma_ts(t_acc2, a_tmem + (u * 4 + ks) * 8, tc::make_desc_sw128(b_addr + ks * 32), idesc2, acc);
             }
-            __syncwarp();
-            s += sl2;
           }
+          __syncwarp();
+          release();
+        }
         if (j == nj - 1) {
           if (leader && tc::elect_one()) { if (CL2) tc::umma2_commit(&acc2_full); else tc::umma_commit(&acc2_full); }
           __syncwarp();
@@ -467,6 +491,32 @@ static int g_ffn_pair = 0;  //                            4 = TMEM hidden + CTA 
 void tc_set_ffn_version(int v) { g_ffn_ver = v == 2 ? 2 : 3; g_ffn_pair = v == 4 ? 1 : 0; }
 int tc_ffn_version() { return g_ffn_ver; }
 
+// v3 images = the v2 images with their 8 KB blocks reordered into ring-step order:
+//   W1: [hidden chunk c][K-block kb][row half u]  <-  v2 block ((2c + u) * nkbD + kb)
+//   W2: [K-block kb of F][64-row chunk n of D]    <-  v2 block (n * nkbF + kb)
+__global__ void ffn3_reorder_kernel(const uint4* w1v2, const uint4* w2v2, uint4* w1v3, uint4* w2v3, int nkbD, int nkbF) {
+  const int blk = blockIdx.x, n1 = nkbD * nkbF;  // blocks per image
+  const uint4* src; uint4* dst;
+  if (blk < n1) {
+    const int u = blk & 1, kb = (blk >> 1) % nkbD, c = (blk >> 1) / nkbD;
+    src = w1v2 + (size_t)((2 * c + u) * nkbD + kb) * 512; dst = w1v3 + (size_t)blk * 512;
+  } else {
+    const int b2 = blk - n1, n = b2 % nkbD, kb = b2 / nkbD;
+    src = w2v2 + (size_t)(n * nkbF + kb) * 512; dst = w2v3 + (size_t)b2 * 512;
+  }
+  for (int i = threadIdx.x; i < 512; i += blockDim.x) dst[i] = src[i];
+}
+size_t tc_ffn3_packed_bytes(const smx_ffn_weights* w) { return 2 * tc_ffn2_packed_bytes(w); }
+int tc_ffn3_pack(const smx_ffn_weights* w, void* packed, cudaStream_t st) {
+  SMX_TRY(tc_ffn2_pack(w, packed, st));
+  const int D = w->w1.in_dim, F = w->w1.out_dim, nkbD = D / 64, nkbF = F / 64;
+  const size_t img = align_up((size_t)D * F * 2, 1024);
+  const uint8_t* b = (const uint8_t*)packed;
+  ffn3_reorder_kernel<<<2 * nkbD * nkbF, 128, 0, st>>>((const uint4*)b, (const uint4*)(b + img), (uint4*)(b + 2 * img), (uint4*)(b + 3 * img), nkbD, nkbF);
+  count_launch();
+  return check_launch("ffn3_reorder_kernel");
+}
+
 bool tc_ffn3_supported(const smx_ffn_weights* w) {
   if (!tc_ffn2_supported(w)) return false;
   const int D = w->w1.in_dim;
@@ -490,16 +540,10 @@ static int ffn3_sms() {
 template <bool OLN, bool CL2>
 static int launch_ffn3(const Ffn3P& p, unsigned grid, size_t smem, cudaStream_t st) {
   cudaError_t e;
-  cudaLaunchConfig_t cfg{};
-  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(F3_THREADS); cfg.dynamicSmemBytes = smem; cfg.stream = st;
-  cudaLaunchAttribute attr[1];
-  attr[0].id = cudaLaunchAttributeClusterDimension;
-  attr[0].val.clusterDim.x = CL2 ? 2u : 1u; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
-  cfg.attrs = attr; cfg.numAttrs = 1;
 #define SMX_FFN3_LAUNCH(A)                                                                                   \
   e = cudaFuncSetAttribute(ffn3_kernel<OLN, A, CL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(ffn3_kernel): %s", cudaGetErrorString(e)); \
-  e = cudaLaunchKernelEx(&cfg, ffn3_kernel<OLN, A, CL2>, p);                                                 \
+  e = launch_pdl(ffn3_kernel<OLN, A, CL2>, dim3(grid), dim3(F3_THREADS), smem, st, CL2 ? 2u : 1u, p);         \
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaLaunchKernelEx(ffn3_kernel): %s", cudaGetErrorString(e));
   switch (p.act) {
     case SMX_ACT_SWISH: SMX_FFN3_LAUNCH(SMX_ACT_SWISH); break;
@@ -518,16 +562,15 @@ int tc_ffn3_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t r
   Ffn3P p{};
   p.x = x; p.y = y; p.rows = rows; p.D = D; p.F = F;
   p.n_tiles = (int)((rows + 127) / 128);
-  p.w1 = (const uint8_t*)packed;
+  p.w1 = (const uint8_t*)packed + 2 * align_up((size_t)D * F * 2, 1024);  // the v3 images follow the v2 images
   p.w2 = p.w1 + align_up((size_t)D * F * 2, 1024);
   p.ln_w = w->ln_w; p.ln_b = w->ln_b; p.b1 = w->w1.b; p.b2 = w->w2.b;
   p.oln_w = oln_w; p.oln_b = oln_b; p.oln_eps = oln_eps;
   p.act = act;
   const int nc = D / 64;
-  p.gw2 = nc % 4 == 0 ? 4 : (nc % 2 == 0 ? 2 : 1);
   p.trace = g_trace3f;
   p.off_ring = (uint32_t)nc * kblock_bytes(128);
-  p.off_par = p.off_ring + F3_STAGES * F3_BLOCK;
+  p.off_par = p.off_ring + F3_RING_BYTES;
   p.off_red = p.off_par + (uint32_t)align_up((size_t)(F + 1280) * 4, 1024);
   const size_t smem = (size_t)p.off_red + 4096;
   if (smem > 227 * 1024 - 1024) return fail(SMX_ERR_UNSUPPORTED, "ffn: tile does not fit shared memory");
