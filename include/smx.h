@@ -296,6 +296,10 @@ SMX_API int smx_debug_set_ffn_version(int version);
 /* Programmatic dependent launch of the fused kernels (default on): a kernel's set-up overlaps the tail of its
  * predecessor; results are identical.  Diagnostics / A-B timing. */
 SMX_API int smx_debug_set_pdl(int on);
+/* Fused SummaryMixing cell / GLU pass generation: 3 (default; hidden activations and the normalised local branch stay in
+ * tensor memory as MMA A operands, step-granular weight ring, 16 epilogue warps) or 1 (first generation, operands staged
+ * through shared memory).  Same function; diagnostics / A-B timing. */
+SMX_API int smx_debug_set_cell_version(int version);
 
 #ifdef __cplusplus
 }

@@ -116,6 +116,7 @@ _PROTOS = {
     "smx_debug_set_ffn_cluster": (_i, [_i]),
     "smx_debug_set_ffn_version": (_i, [_i]),
     "smx_debug_set_pdl": (_i, [_i]),
+    "smx_debug_set_cell_version": (_i, [_i]),
 }
 
 

@@ -169,6 +169,7 @@ extern "C" SMX_API int smx_debug_tc_gemm(int layout, int32_t M, int32_t N, int32
 // kernels; NULL switches tracing off.  Not thread-safe; diagnostics only.
 extern "C" SMX_API int smx_debug_set_trace(void* device_u64_buffer) {
   tc_set_trace(device_u64_buffer);
+  tc_set_trace_cell3(device_u64_buffer);
   tc_set_trace_ffn(device_u64_buffer ? (char*)device_u64_buffer + 4096 : nullptr);  // entries 512..1023
   tc_set_trace_ffn3(device_u64_buffer ? (char*)device_u64_buffer + 4096 : nullptr);
   tc_set_trace_conv(device_u64_buffer ? (char*)device_u64_buffer + 7680 : nullptr); // entries 960..1023
@@ -189,6 +190,12 @@ void tc_set_pdl(int on) { g_pdl = on ? 1 : 0; }
 // programmatic dependent launch of the fused kernels on (default) / off
 extern "C" SMX_API int smx_debug_set_pdl(int on) {
   tc_set_pdl(on);
+  return SMX_OK;
+}
+
+// A-B switch between the fused cell / GLU-pass generations (3: operands in tensor memory, 1: first generation)
+extern "C" SMX_API int smx_debug_set_cell_version(int version) {
+  tc_set_cell_version(version);
   return SMX_OK;
 }
 

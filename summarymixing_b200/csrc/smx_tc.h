@@ -83,6 +83,20 @@ int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
 
 int tc_glu_fwd(const smx_linear& L, const void* img, const float* ln_w, const float* ln_b, int64_t rows,
                const __nv_bfloat16* x, __nv_bfloat16* out, cudaStream_t st);
+int tc_cell_finalize(const smx_cell_weights* w, int B, int T, const float* colsum, const uint8_t* mask, float* rowbias, cudaStream_t st);
+
+// ---- smx_tc_cell3.cu: K-SM v3 (operands resident in tensor memory, step-granular weight ring, 16 epilogue warps) -----
+// images in SCHEDULE order (tc_cell3_reorder from the [chunk][K-block] images of tc_pack_linear_nt)
+bool tc_cell3_supported(const smx_cell_weights* w);
+int tc_cell3_reorder(const smx_linear& L, int K, int n_split, const void* img_chunk_major, void* img_sched, cudaStream_t st);
+int tc_cell3_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_s2, const void* img_f1, const void* img_f2,
+                 const void* img_c, int B, int T, const __nv_bfloat16* x, const float* pre_ln_w, const float* pre_ln_b,
+                 const uint8_t* mask, const __nv_bfloat16* residual, __nv_bfloat16* y, Arena& ws, cudaStream_t st);
+int tc_glu3_fwd(const smx_linear& L, const void* img_sched, const float* ln_w, const float* ln_b, int64_t rows,
+                const __nv_bfloat16* x, __nv_bfloat16* out, cudaStream_t st);
+void tc_set_cell_version(int v);  // 1 or 3 (diagnostics / A-B timing)
+void tc_set_trace_cell3(void* p);
+int tc_cell_version();
 
 // ---- smx_tc_conv.cu: K-CONV, depthwise conv + LN + act + output GEMM + mask/residual, persistent -------
 bool tc_convf_supported(const smx_convmod_weights* w, int chunk);

@@ -721,6 +721,19 @@ static int launch_cell(const CellFP& p, unsigned grid, size_t smem, cudaStream_t
   }
 }
 
+// per-utterance finalisation between the two passes (shared by both kernel generations)
+int tc_cell_finalize(const smx_cell_weights* w, int B, int T, const float* colsum, const uint8_t* mask, float* rowbias, cudaStream_t st) {
+  CellFinP f{};
+  f.colsum = colsum; f.mask = mask; f.Wc = w->merge.w; f.bc = w->merge.b; f.rowbias = rowbias;
+  f.ln_w = w->use_layernorm ? w->summary_norm_w : nullptr;
+  f.ln_b = w->use_layernorm ? w->summary_norm_b : nullptr;
+  f.T = T; f.tpu = (T + 127) / 128; f.Ds = w->summary_out_dim; f.Dl = w->local_out_dim; f.Dout = w->merge.out_dim;
+  cudaError_t e = launch_pdl(cell_finalize2_kernel, dim3(B, (f.Dout + 63) / 64), dim3(256), 0, st, 1u, f);
+  if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaLaunchKernelEx(cell_finalize2_kernel): %s", cudaGetErrorString(e));
+  count_launch();
+  return check_launch("cell_finalize2_kernel");
+}
+
 // images: [s1][s2][f1][f2][merge local part], each N*K*2 bytes in 64x64 blocks (NT = 64)
 int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_s2, const void* img_f1, const void* img_f2,
                  const void* img_c, int B, int T, const __nv_bfloat16* x, const float* pre_ln_w, const float* pre_ln_b,
@@ -765,17 +778,7 @@ int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
     if (p.n_stages < 4) return fail(SMX_ERR_UNSUPPORTED, "fused cell: tile does not fit shared memory");
     SMX_TRY(launch_cell<0>(p, grid, smem, st));
   }
-  {  // per-utterance mean -> LN_s -> summary share of the combiner
-    CellFinP f{};
-    f.colsum = colsum; f.mask = mask; f.Wc = w->merge.w; f.bc = w->merge.b; f.rowbias = rowbias;
-    f.ln_w = w->use_layernorm ? w->summary_norm_w : nullptr;
-    f.ln_b = w->use_layernorm ? w->summary_norm_b : nullptr;
-    f.T = T; f.tpu = tpu; f.Ds = Ds; f.Dl = Dl; f.Dout = Dout;
-    cudaError_t e = launch_pdl(cell_finalize2_kernel, dim3(B, (Dout + 63) / 64), dim3(256), 0, st, 1u, f);
-    if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaLaunchKernelEx(cell_finalize2_kernel): %s", cudaGetErrorString(e));
-    count_launch();
-    SMX_TRY(check_launch("cell_finalize2_kernel"));
-  }
+  SMX_TRY(tc_cell_finalize(w, B, T, colsum, mask, rowbias, st));  // per-utterance mean -> LN_s -> summary share of the combiner
   if (g_trace) p.trace = g_trace + 512;
   {  // pass B
     p.g[0] = make_gemm(w->local[0], img_f1, D);

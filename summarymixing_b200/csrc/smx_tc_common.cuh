@@ -478,5 +478,67 @@ __device__ __forceinline__ void stage_ln_rows(uint8_t* sX, const __nv_bfloat16* 
   }
 }
 
+// The same tile prologue spread over 16 warps (the epilogue warps, idle while a CTA's FIRST tile is being staged): warp w
+// takes rows [8w, 8w + 8); for the copy lane l moves chunk l of each row, for the LayerNorm lane l owns row 8w + (l & 7)
+// and the column quarter l >> 3 (D / 32 chunks), the four partial statistics of a row meeting through two shuffles.
+// The 8 lanes of each 128-bit shared-memory phase hold 8 different rows of one quarter: conflict-free under the swizzle.
+// D % 32 == 0, D <= 256.
+__device__ __forceinline__ void stage_ln_rows_wide(uint8_t* sX, const __nv_bfloat16* x, int64_t ldx, int64_t row0, int nrows, int D,
+                                                   int w, int lane, bool do_ln, const float* sW, const float* sB) {
+  const int nch = D >> 3;
+  if (lane < nch) {
+    uint8_t* const base = sX + (size_t)(lane >> 3) * kblock_bytes(128);
+    const __nv_bfloat16* src = x + (row0 + w * 8) * ldx + lane * 8;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int r = w * 8 + j;
+      const bool in = r < nrows;
+      cp_async16(base + sw128_offset(r, lane & 7), in ? (const void*)(src + (int64_t)j * ldx) : (const void*)x, in ? 16u : 0u);
+    }
+  }
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncwarp();
+  if (!do_ln) return;
+  const int r = w * 8 + (lane & 7), qq = lane >> 3, cq = nch >> 2;  // chunks per quarter
+  const uint32_t rx = (uint32_t)(r & 7);
+  uint8_t* const rowp = sX + (r >> 3) * 1024 + (r & 7) * 128;
+  float v[8];
+  unpack_bf16x8(*reinterpret_cast<const uint4*>(rowp + (rx << 4)), v);  // chunk 0 of the row: the common shift
+  const float x0 = v[0];
+  float a1[8], a2[8];
+#pragma unroll
+  for (int e = 0; e < 8; ++e) { a1[e] = 0.0f; a2[e] = 0.0f; }
+#pragma unroll 4
+  for (int i = 0; i < cq; ++i) {
+    const int c = qq * cq + i;
+    unpack_bf16x8(*reinterpret_cast<const uint4*>(rowp + (size_t)(c >> 3) * kblock_bytes(128) + ((((uint32_t)c & 7u) ^ rx) << 4)), v);
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float d = v[e] - x0; a1[e] += d; a2[e] = fmaf(d, d, a2[e]); }
+  }
+  float s1 = ((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((a1[4] + a1[5]) + (a1[6] + a1[7]));
+  float s2 = ((a2[0] + a2[1]) + (a2[2] + a2[3])) + ((a2[4] + a2[5]) + (a2[6] + a2[7]));
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 8); s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+  s1 += __shfl_xor_sync(0xffffffffu, s1, 16); s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+  const float invD = 1.0f / (float)D;
+  const float m0 = s1 * invD;
+  const float rstd = rsqrtf(fmaxf(s2 * invD - m0 * m0, 0.0f) + 1e-5f);
+  const float shift = -(m0 + x0) * rstd;
+  const bool live = r < nrows;
+#pragma unroll 4
+  for (int i = 0; i < cq; ++i) {
+    const int c = qq * cq + i;
+    uint4* const cp = reinterpret_cast<uint4*>(rowp + (size_t)(c >> 3) * kblock_bytes(128) + ((((uint32_t)c & 7u) ^ rx) << 4));
+    unpack_bf16x8(*cp, v);
+    const float4 w0 = *reinterpret_cast<const float4*>(sW + c * 8), w1 = *reinterpret_cast<const float4*>(sW + c * 8 + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(sB + c * 8), b1 = *reinterpret_cast<const float4*>(sB + c * 8 + 4);
+    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+    for (int e = 0; e < 8; ++e) v[e] = live ? fmaf(fmaf(v[e], rstd, shift), wv[e], bv[e]) : 0.0f;
+    *cp = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+  }
+}
+
 }  // namespace tc
 }  // namespace smx

@@ -321,12 +321,13 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
     }
   } else if (warp >= F3_PRO_WARP0) {
     // =============================== prologue: x tile -> LN -> A operand ===============================
+    // (the CTA's first tile is staged by the 16 epilogue warps, which have nothing else to do yet)
     const int pw = warp - F3_PRO_WARP0;
-    int it = 0;
-    for (int base = first_base; base < p.n_tiles; base += base_step, ++it) {
+    int it = 1;
+    for (int base = first_base + base_step; base < p.n_tiles; base += base_step, ++it) {
       const int64_t row0 = (int64_t)(base + (int)crank) * 128;
       const int nrows = p.rows - row0 < 128 ? (int)(p.rows - row0) : 128;
-      if (it > 0) tc::mbar_wait(&x_free, (it - 1) & 1);
+      tc::mbar_wait(&x_free, (it - 1) & 1);
       if (pw == 0) F3_TRACE(2, it, 0);
       tc::stage_ln_rows(sX, p.x, D, row0, nrows, D, pw, lane, true, sLw, sLb,
                         (p.trace && blockIdx.x == 0 && pw == 0 && it < 2) ? p.trace + ((2 * 2 + it) * 32) + 4 : nullptr);
@@ -346,6 +347,12 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
       const uint32_t par = it & 1;
       const int64_t row0 = (int64_t)(base + (int)crank) * 128;
       const int nrows = p.rows - row0 < 128 ? (int)(p.rows - row0) : 128;
+      if (it == 0) {  // first tile: all 16 epilogue warps stage and normalise it (8 rows each)
+        tc::stage_ln_rows_wide(sX, p.x, D, row0, nrows, D, warp, lane, true, sLw, sLb);
+        tc::fence_proxy_async();
+        tc::named_bar_sync(5, F3_NEW * 32);
+        if (warp < F3_NPW && lane == 0) arrive_leader(&x_full);
+      }
       for (int j = 0; j < nj; ++j) {
         const int bsel = j & 1;
         tc::mbar_wait(&acc1_full[bsel], (ph_a1f >> bsel) & 1u);

@@ -40,6 +40,7 @@ bool tc_cell_supported(const smx_cell_weights* w, int has_sum_mask) {
 
 struct CellLayout {
   size_t local[SMX_MAX_BLOCKS], summary[SMX_MAX_BLOCKS], merge, total;
+  size_t local_s[2], summary_s[2], merge_s;  // the same images in schedule order (K-SM v3)
 };
 static CellLayout cell_layout(const smx_cell_weights* w) {
   CellLayout l{};
@@ -47,6 +48,11 @@ static CellLayout cell_layout(const smx_cell_weights* w) {
   for (int i = 0; i < w->n_local; ++i) { l.local[i] = off; off += align_up(tc_linear_packed_bytes(w->local[i].in_dim, w->local[i].out_dim)); }
   for (int i = 0; i < w->n_summary; ++i) { l.summary[i] = off; off += align_up(tc_linear_packed_bytes(w->summary[i].in_dim, w->summary[i].out_dim)); }
   l.merge = off; off += align_up(tc_linear_packed_bytes(w->local_out_dim, w->merge.out_dim));
+  if (tc_cellf_supported(w)) {
+    for (int i = 0; i < 2; ++i) { l.local_s[i] = off; off += align_up(tc_linear_packed_bytes(w->local[i].in_dim, w->local[i].out_dim)); }
+    for (int i = 0; i < 2; ++i) { l.summary_s[i] = off; off += align_up(tc_linear_packed_bytes(w->summary[i].in_dim, w->summary[i].out_dim)); }
+    l.merge_s = off; off += align_up(tc_linear_packed_bytes(w->local_out_dim, w->merge.out_dim));
+  }
   l.total = off;
   return l;
 }
@@ -59,7 +65,12 @@ int tc_cell_pack(const smx_cell_weights* w, void* packed, cudaStream_t st) {
   if (tc_cellf_supported(w)) {  // fused persistent cell: 64 x 64 weight blocks
     for (int i = 0; i < 2; ++i) SMX_TRY(tc_pack_linear_nt(w->local[i], 0, w->local[i].in_dim, 64, base + l.local[i], st));
     for (int i = 0; i < 2; ++i) SMX_TRY(tc_pack_linear_nt(w->summary[i], 0, w->summary[i].in_dim, 64, base + l.summary[i], st));
-    return tc_pack_linear_nt(w->merge, 0, w->local_out_dim, 64, base + l.merge, st);
+    SMX_TRY(tc_pack_linear_nt(w->merge, 0, w->local_out_dim, 64, base + l.merge, st));
+    for (int i = 0; i < 2; ++i) {
+      SMX_TRY(tc_cell3_reorder(w->local[i], w->local[i].in_dim, w->local[i].n_split, base + l.local[i], base + l.local_s[i], st));
+      SMX_TRY(tc_cell3_reorder(w->summary[i], w->summary[i].in_dim, w->summary[i].n_split, base + l.summary[i], base + l.summary_s[i], st));
+    }
+    return tc_cell3_reorder(w->merge, w->local_out_dim, 1, base + l.merge, base + l.merge_s, st);
   }
   for (int i = 0; i < w->n_local; ++i) SMX_TRY(tc_pack_linear(w->local[i], 0, w->local[i].in_dim, 0, base + l.local[i], st));
   for (int i = 0; i < w->n_summary; ++i) SMX_TRY(tc_pack_linear(w->summary[i], 0, w->summary[i].in_dim, 0, base + l.summary[i], st));
@@ -183,9 +194,15 @@ int tc_cell_fwd(const smx_cell_weights* w, const void* packed, int B, int T, con
   const char* pk = (const char*)packed;
   const size_t m0 = ws.mark();
   if (ws.dry) { ws.take(tc_cell_workspace_bytes(w, B, T)); ws.release(m0); return SMX_OK; }
-  if (tc_cellf_supported(w))
+  if (tc_cellf_supported(w)) {
+    // v3 moves rows with 256-bit global accesses: 32-byte aligned x / y / residual
+    const bool al = ((uintptr_t)x % 32 == 0) && ((uintptr_t)y % 32 == 0) && ((uintptr_t)residual % 32 == 0);
+    if (tc_cell_version() == 3 && tc_cell3_supported(w) && al)
+      return tc_cell3_fwd(w, pk + l.summary_s[0], pk + l.summary_s[1], pk + l.local_s[0], pk + l.local_s[1], pk + l.merge_s, B, T, x,
+                          pre_ln_w, pre_ln_b, mask, residual, y, ws, st);
     return tc_cellf_fwd(w, pk + l.summary[0], pk + l.summary[1], pk + l.local[0], pk + l.local[1], pk + l.merge, B, T, x,
                         pre_ln_w, pre_ln_b, mask, residual, y, ws, st);
+  }
   CellWs o;
   SMX_TRY(cell_ws(w, B, T, ws, o));
   const int64_t rows = (int64_t)B * T;
@@ -280,14 +297,16 @@ bool tc_convmod_supported(const smx_convmod_weights* w, int chunk) {
 size_t tc_convmod_packed_bytes(const smx_convmod_weights* w) {
   if (!tc_convmod_supported(w, 0)) return 0;
   const int D = w->bottleneck.in_dim;
-  return align_up(tc_linear_packed_bytes(D, 2 * D)) + align_up(tc_linear_packed_bytes(D, D));
+  return 2 * align_up(tc_linear_packed_bytes(D, 2 * D)) + align_up(tc_linear_packed_bytes(D, D));  // [GLU][out][GLU in schedule order]
 }
 int tc_convmod_pack(const smx_convmod_weights* w, void* packed, cudaStream_t st) {
   if (!tc_convmod_supported(w, 0)) return fail(SMX_ERR_UNSUPPORTED, "conv module not handled by the tensor-core arm");
   const int D = w->bottleneck.in_dim;
   if (tc_convf_supported(w, 0)) {  // fused path: 64 x 64 blocks, value/gate blocks interleaved for the GLU pass
     SMX_TRY(tc_pack_linear_nt(w->bottleneck, 0, D, 64, packed, st, 1));
-    return tc_pack_linear_nt(w->out, 0, D, 64, (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)), st);
+    SMX_TRY(tc_pack_linear_nt(w->out, 0, D, 64, (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)), st));
+    return tc_cell3_reorder(w->bottleneck, D, 1, packed,
+                            (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)) + align_up(tc_linear_packed_bytes(D, D)), st);
   }
   SMX_TRY(tc_pack_linear(w->bottleneck, 0, D, 1, packed, st));
   SMX_TRY(tc_pack_linear(w->out, 0, D, 0, (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)), st));
@@ -499,7 +518,11 @@ int tc_convmod_fwd(const smx_convmod_weights* w, const void* packed, int act, in
   if (tc_convf_supported(w, 0)) {
     __nv_bfloat16* gb = (__nv_bfloat16*)ws.take((size_t)rows * D * 2);
     if (!gb) return fail(SMX_ERR_WORKSPACE, "workspace too small (tc conv module)");
-    SMX_TRY(tc_glu_fwd(w->bottleneck, packed, w->ln_w, w->ln_b, rows, x, gb, st));                       // :322-324
+    if (tc_cell_version() == 3 && ((uintptr_t)x % 32 == 0) && ((uintptr_t)gb % 32 == 0))                 // :322-324
+      SMX_TRY(tc_glu3_fwd(w->bottleneck, (const char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)) + align_up(tc_linear_packed_bytes(D, D)),
+                          w->ln_w, w->ln_b, rows, x, gb, st));
+    else
+      SMX_TRY(tc_glu_fwd(w->bottleneck, packed, w->ln_w, w->ln_b, rows, x, gb, st));
     SMX_TRY(tc_convf_second_half(w, (const char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)), act, B, T, gb, mask,
                                  residual, y, st));                                                        // :325-338, :543
     ws.release(m0);

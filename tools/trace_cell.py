@@ -26,7 +26,7 @@ with torch.no_grad():
     torch.cuda.synchronize()
     L.lib().smx_debug_set_trace(None)
 t = buf.cpu().view(2, 8, 4, 16)[:, :5]
-roles = ["producer", "issuer", "prologue", "epi-g0", "epi-g1"]
+roles = ["producer", "issuer", "prologue", "epilogue", "epi-g1"]
 for ph in range(2):
     nz = t[ph][t[ph] > 0]
     if nz.numel() == 0:
