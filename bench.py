@@ -272,24 +272,45 @@ def run_smx(args):
         launches, tc_launches = int(lib.smx_launch_count() - n0), int(lib.smx_tc_launch_count() - t0)
         ms_total = e0.elapsed_time(e1)
 
-        # ---- e2e: same metric through the public module call with HOST buffers (pinned), copies inside the region
+        # ---- e2e: same metric through the public module call with HOST buffers (pinned), copies inside the region.
+        # A serving loop: step i's input travels host -> device on a copy stream while step i-1 computes, its result
+        # travels back on the same copy stream; every step's H2D and D2H happen inside the timed region.
         hx = [x.to(torch.bfloat16).pin_memory() for x, _ in host[:4]]
         hm = [m.pin_memory() for _, m in host[:4]]
         hy = [torch.empty(B, T, D, dtype=torch.bfloat16).pin_memory() for _ in range(4)]
+        copy_stream = torch.cuda.Stream(dev)
+        main_stream = torch.cuda.current_stream(dev)
+        xd = [torch.empty(B, T, D, dtype=torch.bfloat16, device=dev) for _ in range(2)]
+        md = [torch.empty(B, T, dtype=torch.bool, device=dev) for _ in range(2)]
+        in_ready = [torch.cuda.Event() for _ in range(2)]
+        in_free = [torch.cuda.Event() for _ in range(2)]
+        out_ready = [torch.cuda.Event() for _ in range(2)]
 
-        def e2e_step(i):
-            xd = hx[i % 4].to(dev, non_blocking=True)
-            md = hm[i % 4].to(dev, non_blocking=True)
-            y = enc(xd, src_key_padding_mask=md)[0]
-            hy[i % 4].copy_(y, non_blocking=True)
+        def e2e_loop(n):
+            for j in range(2):
+                in_free[j].record(main_stream)
+            for i in range(n):
+                j = i & 1
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(in_free[j])          # the forward that read this buffer has finished
+                    xd[j].copy_(hx[i % 4], non_blocking=True)
+                    md[j].copy_(hm[i % 4], non_blocking=True)
+                    in_ready[j].record(copy_stream)
+                main_stream.wait_event(in_ready[j])
+                y = enc(xd[j], src_key_padding_mask=md[j])[0]
+                in_free[j].record(main_stream)
+                out_ready[j].record(main_stream)
+                with torch.cuda.stream(copy_stream):
+                    copy_stream.wait_event(out_ready[j])
+                    hy[i % 4].copy_(y, non_blocking=True)
+                    y.record_stream(copy_stream)
+            main_stream.wait_stream(copy_stream)                # the last result is on the host when the region ends
 
-        for i in range(3):
-            e2e_step(i)
+        e2e_loop(3)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        for i in range(args.steps):
-            e2e_step(i)
+        e2e_loop(args.steps)
         f1.record()
         barrier()
         e2e_ms = f0.elapsed_time(f1)
@@ -314,7 +335,7 @@ def run_smx(args):
                        "accumulate": "fp32", "io": "bf16"},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * T * D * 2 + B * T,
                     "d2h_bytes_per_step": B * T * D * 2, "ms_per_step": e2e_ms / args.steps,
-                    "api": "summarymixing_b200.ConformerEncoder.forward on pinned host tensors"},
+                    "api": "summarymixing_b200.ConformerEncoder.forward; pinned host inputs/outputs, H2D/D2H on a copy stream overlapped with the previous/next step"},
             "gpu_launches": launches, "tc_launches": tc_launches, "clocks": clocks}
 
     if rank == 0:
@@ -330,10 +351,10 @@ def run_smx(args):
         line["roofline"] = {"kernel": f"smx_summary_mixing_fwd (SummaryMixing cell, {mod['cell']['launches']} launches)",
                             "bound": "hbm", "achieved": bytes_cell / us / 1e3, "peak": pk["hbm_gbs"], "unit": "GB/s",
                             "frac": bytes_cell / us / 1e3 / pk["hbm_gbs"],
-                            # dram__bytes_read+write per cell call from the ncu --set full capture committed as
-                            # profiles/r01_call11_ncu_cell_raw.csv (pass A 16.58 MB + finalise 0.58 MB + pass B 16.78 MB read;
-                            # the 16.4 MB output tile was still in L2 when the capture window closed)
-                            "traffic": 33.94e6, "algorithmic_bytes": bytes_cell,
+                            # dram__bytes_read+write per cell call from the ncu --set full capture summarised in
+                            # profiles/r01_call60_ncu_layer_summary.csv (pass A 16.57 MB + finalise 0.58 MB + pass B 16.77 MB
+                            # read, 0.29 MB written: most of the 16.4 MB output was still in L2 when the window closed)
+                            "traffic": 34.21e6, "algorithmic_bytes": bytes_cell,
                             "us_per_call": us, "peak_source": pk["source"] + " (burst copy)",
                             "tensor_tflops": flops_cell / us / 1e6, "tensor_frac": flops_cell / us / 1e6 / pk["bf16_tflops"]}
         flops_ffn = frames * 4 * D * FFN

@@ -193,3 +193,44 @@ def test_ffn_kernel_generations_agree(version):
     finally:
         L.lib().smx_debug_set_ffn_version(3)
     _check(y, y_or, f"conformer layer, FFN generation {version}", abs_tol=4e-2, rel_tol=2e-2)
+
+
+def test_cfg3_conformer_large_dims():
+    """BASELINE.json configs[2]: the conformer_summarymixing.yaml dims (D=512, h=8, d_ffn=2048, hid/out 512) -- wider than
+    the fused tcgen05 kernels take (D <= 256), so the layer runs on the unfused tensor-core kernels / the fp32-math arm.
+    fp32 I/O within 5e-4 of the oracle, bf16 I/O within the bf16 tolerance."""
+    torch.manual_seed(41)
+    D = 512
+    m = S.ConformerEncoderLayer(D, 2048, 8, 31, attention_type="SummaryMixing", local_proj_hid_dim=[D],
+                                local_proj_out_dim=D, summary_hid_dim=[D]).eval()
+    _perturb(m, 41)
+    B, T = 2, 170
+    x = torch.randn(B, T, D, generator=torch.Generator().manual_seed(42))
+    mask = _mask(B, T, [170, 61])
+    y_or = O.conformer_layer(x, dict(m.state_dict()), "", act="swish", src_key_padding_mask=mask)
+    m = m.to(DEV)
+    with torch.no_grad():
+        y32 = m(x.to(DEV), src_key_padding_mask=mask.to(DEV))[0]
+        xb = x.to(torch.bfloat16)
+        y16 = m(xb.to(DEV), src_key_padding_mask=mask.to(DEV))[0]
+    assert float((y32.cpu() - y_or).abs().max()) < 5e-4
+    y_or16 = O.conformer_layer(xb.float(), dict(m.cpu().state_dict()), "", act="swish", src_key_padding_mask=mask)
+    _check(y16, y_or16, "conformer_large layer (D=512) bf16 I/O", abs_tol=4e-2, rel_tol=2e-2)
+
+
+def test_cfg4_branchformer_lite_dims():
+    """BASELINE.json configs[3]: Branchformer SummaryMixing-lite, D=512, csgu 3072, ragged padded batch with mask;
+    fp32 within 5e-4 of the oracle."""
+    torch.manual_seed(43)
+    D = 512
+    m = S.BranchformerEncoderLayer(D, 1, 31, csgu_linear_units=3072, local_proj_hid_dim=[D], local_proj_out_dim=D,
+                                   summary_hid_dim=[D], summary_out_dim=D, mode="SummaryMixing-lite").eval()
+    _perturb(m, 43)
+    B, T = 3, 230
+    x = torch.randn(B, T, D, generator=torch.Generator().manual_seed(44))
+    mask = _mask(B, T, [230, 200, 37])
+    y_or = O.branchformer_layer(x, dict(m.state_dict()), "", mode="SummaryMixing-lite", src_key_padding_mask=mask)
+    with torch.no_grad():
+        y = m.to(DEV)(x.to(DEV), src_key_padding_mask=mask.to(DEV))[0]
+    torch.cuda.synchronize()
+    assert float((y.cpu() - y_or).abs().max()) < 5e-4
