@@ -285,10 +285,13 @@ def run_smx(args):
         in_ready = [torch.cuda.Event() for _ in range(2)]
         in_free = [torch.cuda.Event() for _ in range(2)]
         out_ready = [torch.cuda.Event() for _ in range(2)]
+        out_free = [torch.cuda.Event() for _ in range(2)]
+        yd = [torch.empty(B, T, D, dtype=torch.bfloat16, device=dev) for _ in range(2)]  # results wait here for their D2H
 
         def e2e_loop(n):
             for j in range(2):
                 in_free[j].record(main_stream)
+                out_free[j].record(copy_stream)
             for i in range(n):
                 j = i & 1
                 with torch.cuda.stream(copy_stream):
@@ -299,11 +302,13 @@ def run_smx(args):
                 main_stream.wait_event(in_ready[j])
                 y = enc(xd[j], src_key_padding_mask=md[j])[0]
                 in_free[j].record(main_stream)
+                main_stream.wait_event(out_free[j])             # the D2H that read this staging buffer has finished
+                yd[j].copy_(y)
                 out_ready[j].record(main_stream)
                 with torch.cuda.stream(copy_stream):
                     copy_stream.wait_event(out_ready[j])
-                    hy[i % 4].copy_(y, non_blocking=True)
-                    y.record_stream(copy_stream)
+                    hy[i % 4].copy_(yd[j], non_blocking=True)
+                    out_free[j].record(copy_stream)
             main_stream.wait_stream(copy_stream)                # the last result is on the host when the region ends
 
         e2e_loop(3)

@@ -142,7 +142,13 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
   constexpr int NG = PHASE == 0 ? 2 : (PHASE == 1 ? 3 : 1);
   const int act = ACT >= 0 ? ACT : p.act;
 
-  tc::pdl_launch_dependents();
+  // Programmatic dependent launch.  Pass A and the GLU pass read the output of their immediate predecessor: they wait for it
+  // below and only then let their own dependents launch.  Pass B reads x, which is three launches old (FFN1 -> pass A ->
+  // finalise -> pass B) and therefore complete once pass B can run at all (pass A's CTAs trigger only after their own
+  // wait); what pass B needs from its predecessors is c[b], so its epilogue warps wait right before they fetch it (and
+  // before the kernel's first global store) -- the first tile's GEMMs and epilogues overlap pass A's tail and the
+  // finalisation kernel.
+  if (PHASE == 1) tc::pdl_launch_dependents();
   if (warp == C3_PROD_WARP) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int s = 0; s < C3_MAX_SLOTS; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
@@ -162,7 +168,10 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  tc::pdl_wait();  // x / column sums / c[b] come from the preceding kernels (everything above touched only parameters)
+  if (PHASE != 1) {
+    tc::pdl_wait();  // x comes from the preceding kernel (everything above touched only parameters)
+    tc::pdl_launch_dependents();
+  }
   const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
   const uint32_t regA = tmem, regB = tmem + 256;
   const int first_tile = blockIdx.x, tile_step = gridDim.x;
@@ -409,8 +418,6 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
         if (warp == 0) C3_TRACE(3, it, 5);
       } else {
         // ---- E2: L = LN_l(act(acc2 + b2) * mask) as packed bf16 into region A [128, 256) (A operand of the combiner)
-        // c[b] for E3 goes to shared memory meanwhile
-        if (etid < p.Dout) sRB[etid] = __ldcg(p.rowbias + (size_t)b * p.Dout + etid);
         tc::mbar_wait(&acc_full[1], par);
         tc::tc_fence_after();
         if (warp == 0) C3_TRACE(3, it, 4);
@@ -493,6 +500,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
         }
         tc::tmem_st_wait();
         tc::tc_fence_before();
+        if (it == 0) tc::pdl_wait();  // pass A and the finalisation kernel have completed: c[b] is there, y may be written
+        if (etid < p.Dout) sRB[etid] = __ldcg(p.rowbias + (size_t)b * p.Dout + etid);  // c[b] for E3
         tc::named_bar_sync(5, C3_NEW * 32);  // c[b] is in shared memory; sRed may be rewritten
         if (lane == 0) tc::mbar_arrive(&op_full[1]);
         if (warp == 0) C3_TRACE(3, it, 5);
