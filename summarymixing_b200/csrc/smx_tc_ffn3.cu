@@ -222,6 +222,24 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
     // Issue order G1(0), G1(1), G2(0), G1(2), G2(1), ...: the tensor pipe executes in issue order, so G1(j+2), which
     // overwrites acc1[j&1] (and with it H[j&1]), runs after G2(j) has read H[j&1]; G2(j) itself is issued only after
     // the epilogue has loaded acc1[j&1] and stored H[j&1] (h_full).  No separate "accumulator drained" barrier.
+    if (CL2 && !leader) {
+      // Peer CTA: this warp has no MMAs to issue.  One lane relays "my half of the step has landed" to the leader in a
+      // loop that is as short as it can be (the ring is a plain cyclic sequence of slots: no schedule knowledge needed):
+      // wait for the local full barrier, arrive on the leader's peer_full barrier of the same slot.
+      if (lane == 0) {
+        int n_mine = 0;
+        for (int base = first_base; base < p.n_tiles; base += base_step) ++n_mine;
+        const int total = n_mine * nj * (ng1 + 2);
+        int s = 0;
+        uint32_t pf = 0;
+        for (int st = 0; st < total; ++st) {
+          tc::mbar_wait_spin(&full_bar[s], (pf >> s) & 1u);
+          tc::mbar_arrive_remote(&peer_full[s], 0);
+          pf ^= 1u << s;
+          if (++s == nslots) s = 0;
+        }
+      }
+    } else {
     int s = 0;
     uint32_t pf = 0;
     uint32_t ph_hf = 0;  // per-buffer parity of h_full
@@ -234,10 +252,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
     auto ring_next = [&]() -> uint32_t {  // wait for the next step (both halves); returns its shared-memory address
       const long long c0 = tracing ? clock64() : 0;
       tc::mbar_wait_spin(&full_bar[s], (pf >> s) & 1u);
-      if (CL2) {
-        if (leader) tc::mbar_wait_spin_cluster(&peer_full[s], (pf >> s) & 1u);
-        else if (lane == 0) tc::mbar_arrive_remote(&peer_full[s], 0);
-      }
+      if (CL2) tc::mbar_wait_spin_cluster(&peer_full[s], (pf >> s) & 1u);
       if (tracing) tw_ring += clock64() - c0;
       pf ^= 1u << s;
       tc::tc_fence_after();
@@ -318,6 +333,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
         p.trace[((1 * 2 + it) * 32) + 18] = (unsigned long long)tw_epi;
       }
       tw_ring = tw_h = tw_epi = 0;
+    }
     }
   } else if (warp >= F3_PRO_WARP0) {
     // =============================== prologue: x tile -> LN -> A operand ===============================
@@ -439,6 +455,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
           }
         }
       }
+      if (warp == 0) F3_TRACE(3, it, 12);
       if (OLN) {
         tc::tmem_st_wait();
         if (active) { sRed[(k * 128 + r) * 2] = mean_t; sRed[(k * 128 + r) * 2 + 1] = m2_t; }
@@ -451,6 +468,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
         for (int i = 0; i < nq; ++i) { const float dl = sRed[(i * 128 + r) * 2] - mean; m2 += sRed[(i * 128 + r) * 2 + 1] + 64.0f * dl * dl; }
         const float rstd = rsqrtf(m2 / (float)D + p.oln_eps);
         const float shift = -mean * rstd;
+        if (warp == 0) F3_TRACE(3, it, 13);
         if (active) {
 #pragma unroll
           for (int h = 0; h < 4; ++h) {

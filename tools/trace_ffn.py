@@ -26,14 +26,14 @@ with torch.no_grad():
     L.lib().smx_debug_set_trace(None)
 t = buf.cpu()[512:512 + 5 * 2 * 32].view(5, 2, 32)   # the last FFN call of the layer (ffn2, with output LayerNorm) wins
 roles = ["producer", "issuer", "prologue", "epi-g0", "epi-g1"]
-nz = t[t > 0]
+nz = t[:, :, :16][t[:, :, :16] > 1000000]
 t0 = int(nz.min())
 for r in range(5):
     for it in range(2):
         ev = t[r, it]
         if int(ev.max()) == 0:
             continue
-        print(f"  {roles[r]:9s} it{it}: " + " ".join(f"{int(v) - t0:7d}" if int(v) else "      -" for v in ev[:13]))
+        print(f"  {roles[r]:9s} it{it}: " + " ".join(f"{int(v) - t0:7d}" if int(v) else "      -" for v in ev[:14]))
 
 for it in range(2):
     w = t[1, it, 16:19]
