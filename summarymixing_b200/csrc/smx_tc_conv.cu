@@ -13,7 +13,8 @@
 //                  operand (128B swizzle) for the tensor core;
 //              (4) epilogue of the output GEMM: + bias, * mask, + residual (parked in the idle g buffer with coalesced
 //                  loads issued while the GEMM runs), staged tile, coalesced stores
-//   warp 12    weight producer (8 KB blocks of W_out through a shared-memory ring, cp.async.bulk + mbarrier)
+//   warp 12    weight producer (32 KB steps of the schedule-ordered W_out image through a shared-memory ring: one
+//              cp.async.bulk, one mbarrier pair and one tcgen05.commit per step)
 //   warp 13    (3) MMA issuer: tcgen05.mma, N = up to 256 per instruction, accumulator in TMEM
 // The depthwise output, its LayerNorm and the activation never exist in global memory.
 #include "smx_tc.h"
@@ -27,8 +28,8 @@ constexpr int CV_NCW = 12;                    // compute warps, three per TMEM l
 constexpr int CV_CT = CV_NCW * 32;            // compute threads
 constexpr int CV_THREADS = CV_CT + 64;
 constexpr int CV_PROD_WARP = CV_NCW, CV_MMA_WARP = CV_NCW + 1;
-constexpr int CV_STAGES = 8;
-constexpr uint32_t CV_BLOCK = 8192;
+constexpr int CV_STAGES = 2;                  // ring slots of 32 KB (one step each)
+constexpr uint32_t CV_BLOCK = 8192, CV_SLOT = 32768;
 
 struct ConvFP {
   const __nv_bfloat16* g;
@@ -36,6 +37,7 @@ struct ConvFP {
   const uint8_t* w_img; const float* b_out;
   const uint8_t* mask; const __nv_bfloat16* resid; __nv_bfloat16* y;
   int B, T, D, tpu, n_tiles, act, gw;
+  int al32;  // y is 32-byte aligned: rows leave with 256-bit stores (else two 128-bit stores)
   unsigned long long* trace;
   uint32_t off_a, off_ring, off_par, off_stat;
 };
@@ -48,6 +50,21 @@ __device__ __forceinline__ float2 cv_fma2(float2 a, float2 b, float2 c) {
       : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
         "l"(*reinterpret_cast<unsigned long long*>(&c)));
   return *reinterpret_cast<float2*>(&d);
+}
+// warp-collective 16-column fp32 TMEM load (lane i <-> TMEM lane 32*(w%4)+i)
+__device__ __forceinline__ void cv_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void cv_stg256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
 }
 __device__ __forceinline__ uint4 cv_pack8(const float* v) {
   return make_uint4(tc::pack_bf16x2(v[0], v[1]), tc::pack_bf16x2(v[2], v[3]), tc::pack_bf16x2(v[4], v[5]), tc::pack_bf16x2(v[6], v[7]));
@@ -79,7 +96,6 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   constexpr int nkb = D / 64;
-  const int gw = p.gw, ng = nkb / gw;
   const int act = ACT >= 0 ? ACT : p.act;
 
   tc::pdl_launch_dependents();
@@ -100,55 +116,55 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
   const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
   const int first_tile = blockIdx.x, tile_step = gridDim.x;
 
+  // W_out streams through a step-granular ring: its image is in schedule order ([K-block][64-row chunk]), a step is up to
+  // four 8 KB blocks = (4 / gw) K-blocks of the N = D wide GEMM: one bulk copy, one barrier pair, one commit per step.
+  constexpr int UPS = 4 / nkb;                    // K-blocks (MMA units) per step: gw == nkb chunks per unit
+  constexpr int NSTEP = (nkb + UPS - 1) / UPS;
+  constexpr uint32_t STEP_BYTES = (uint32_t)(UPS < nkb ? UPS : nkb) * nkb * CV_BLOCK;
   if (warp == CV_PROD_WARP) {
     // =============================== weight producer ===============================
     if (lane == 0) {
       int s = 0;
       uint32_t pe = 0;
       for (int tile = first_tile; tile < p.n_tiles; tile += tile_step)
-        for (int j = 0; j < ng; ++j)
-          for (int kb = 0; kb < nkb; ++kb) {
-            s = (s + gw - 1) & ~(gw - 1);
-            if (s >= CV_STAGES) s = 0;
-            for (int u = 0; u < gw; ++u) {
-              tc::mbar_wait(&empty_bar[s + u], ((pe >> (s + u)) & 1u) ^ 1u);
-              pe ^= 1u << (s + u);
-            }
-            tc::mbar_arrive_expect_tx(&full_bar[s], CV_BLOCK * gw);
-            for (int u = 0; u < gw; ++u)
-              tc::bulk_g2s(sRing + (size_t)(s + u) * CV_BLOCK, p.w_img + (size_t)((j * gw + u) * nkb + kb) * CV_BLOCK, CV_BLOCK, &full_bar[s]);
-            s += gw;
-          }
+        for (int st = 0; st < NSTEP; ++st) {
+          tc::mbar_wait_spin(&empty_bar[s], ((pe >> s) & 1u) ^ 1u);
+          pe ^= 1u << s;
+          tc::mbar_arrive_expect_tx(&full_bar[s], STEP_BYTES);
+          tc::bulk_g2s(sRing + (size_t)s * CV_SLOT, p.w_img + (size_t)st * STEP_BYTES, STEP_BYTES, &full_bar[s]);
+          if (++s == CV_STAGES) s = 0;
+        }
     }
   } else if (warp == CV_MMA_WARP) {
     // =============================== MMA issuer ===============================
     int s = 0, it = 0;
     uint32_t pf = 0;
     const uint32_t a0 = tc::smem_u32(sA), r0 = tc::smem_u32(sRing);
-    const uint32_t idesc = tc::make_idesc_bf16(128, 64u * gw);
+    const uint32_t idesc = tc::make_idesc_bf16(128, (uint32_t)D);
     for (int tile = first_tile; tile < p.n_tiles; tile += tile_step, ++it) {
       tc::mbar_wait(&a_full, it & 1);  // also: the previous tile's accumulator has been drained (same warps, program order)
       tc::tc_fence_after();
-      for (int j = 0; j < ng; ++j)
-        for (int kb = 0; kb < nkb; ++kb) {
-          s = (s + gw - 1) & ~(gw - 1);
-          if (s >= CV_STAGES) s = 0;
-          tc::mbar_wait(&full_bar[s], (pf >> s) & 1u);
-          pf ^= 1u << s;
-          tc::tc_fence_after();
-          const uint32_t a_addr = a0 + kb * kblock_bytes(128), b_addr = r0 + s * CV_BLOCK, d_addr = tmem + j * gw * 64;
-          if (tc::elect_one()) {
+      for (int st = 0; st < NSTEP; ++st) {
+        tc::mbar_wait_spin(&full_bar[s], (pf >> s) & 1u);
+        pf ^= 1u << s;
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
 #pragma unroll
-            for (int ks = 0; ks < 4; ++ks)
-              tc::umma_bf16(d_addr, tc::make_desc_sw128(a_addr + ks * 32), tc::make_desc_sw128(b_addr + ks * 32), idesc,
-                            (kb == 0 && ks == 0) ? 0u : 1u);
-            for (int u = 0; u < gw; ++u) tc::umma_commit(&empty_bar[s + u]);
+          for (int u = 0; u < UPS; ++u) {
+            const int kb = st * UPS + u;
+            if (kb < nkb) {
+              const uint64_t ad = tc::make_desc_sw128(a0 + kb * kblock_bytes(128));
+              const uint64_t bd = tc::make_desc_sw128(r0 + (uint32_t)s * CV_SLOT + (uint32_t)u * nkb * CV_BLOCK);
+#pragma unroll
+              for (int ks = 0; ks < 4; ++ks) tc::umma_bf16(tmem, ad + 2u * ks, bd + 2u * ks, idesc, (kb == 0 && ks == 0) ? 0u : 1u);
+            }
           }
-          __syncwarp();
-          s += gw;
+          tc::umma_commit(&empty_bar[s]);
+          if (st == NSTEP - 1) tc::umma_commit(&acc_full);
         }
-      if (tc::elect_one()) tc::umma_commit(&acc_full);
-      __syncwarp();
+        __syncwarp();
+        if (++s == CV_STAGES) s = 0;
+      }
     }
   } else if (warp < CV_NCW) {
     // =============================== compute warps ===============================
@@ -272,44 +288,37 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
       tc::tc_fence_after();
       tc::cp_async_wait_all();
       CV_TRACE(it, 4);
-      tc::named_bar_sync(1, CV_CT);
-      for (int c = grp; c < nkb; c += CV_NCW / 4) {
+      tc::named_bar_sync(1, CV_CT);   // the residual tile is in shared memory
+      // this thread: row r, 16-column pieces grp, grp + 3, ...: TMEM -> + bias, * mask, + residual -> one 256-bit store
+      for (int pc = grp; pc < D / 16; pc += CV_NCW / 4) {
+        const int col = pc * 16;
+        float v[16];
+        cv_ld16(tmem + lane_sel + col, v);
+        tc::tmem_ld_wait();
+        const float4* bp = reinterpret_cast<const float4*>(sPar + col);
+        float f[16];
+        cv_unpack8(*reinterpret_cast<const uint4*>(sStage + (size_t)(col >> 6) * kblock_bytes(128) + tc::sw128_offset(r, (col & 63) >> 3)), f);
+        cv_unpack8(*reinterpret_cast<const uint4*>(sStage + (size_t)(col >> 6) * kblock_bytes(128) + tc::sw128_offset(r, ((col & 63) >> 3) + 1)), f + 8);
 #pragma unroll
-        for (int pc = 0; pc < 2; ++pc) {
-          const int col = c * 64 + pc * 32;
-          float v[32];
-          tc::tmem_ld32(tmem + lane_sel + col, v);
-          tc::tmem_ld_wait();
-          const float4* bp = reinterpret_cast<const float4*>(sPar + col);
+        for (int i = 0; i < 4; ++i) {
+          const float4 bb = bp[i];
+          v[4 * i] = fmaf(v[4 * i] + bb.x, rscale, f[4 * i]);          // out*mask (:338) then x + out (:543)
+          v[4 * i + 1] = fmaf(v[4 * i + 1] + bb.y, rscale, f[4 * i + 1]);
+          v[4 * i + 2] = fmaf(v[4 * i + 2] + bb.z, rscale, f[4 * i + 2]);
+          v[4 * i + 3] = fmaf(v[4 * i + 3] + bb.w, rscale, f[4 * i + 3]);
+        }
+        if (live) {
+          uint32_t o[8];
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            uint4* spp = reinterpret_cast<uint4*>(sStage + (size_t)c * kblock_bytes(128) + tc::sw128_offset(r, pc * 4 + k));
-            float f[8];
-            cv_unpack8(*spp, f);
-            const float4 ba = bp[2 * k], bb = bp[2 * k + 1];
-            const float bv[8] = {ba.x, ba.y, ba.z, ba.w, bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-            for (int e = 0; e < 8; ++e) v[8 * k + e] = fmaf(v[8 * k + e] + bv[e], rscale, f[e]);  // out*mask (:338) then x + out (:543)
-            *spp = cv_pack8(v + 8 * k);
-          }
+          for (int i = 0; i < 8; ++i) o[i] = tc::pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          __nv_bfloat16* dst = p.y + (row0 + r) * D + col;
+          if (p.al32) cv_stg256(dst, o);
+          else { *reinterpret_cast<uint4*>(dst) = make_uint4(o[0], o[1], o[2], o[3]); *reinterpret_cast<uint4*>(dst + 8) = make_uint4(o[4], o[5], o[6], o[7]); }
         }
       }
       tc::tc_fence_before();
-      tc::named_bar_sync(1, CV_CT);
       CV_TRACE(it, 5);
-      {
-        int rr = rr0, ch = ch0;
-#pragma unroll 4
-        for (int k = 0; k < NST; ++k) {
-          if (rr < nrows) {
-            const uint4 val = *reinterpret_cast<const uint4*>(sStage + (size_t)(ch >> 3) * kblock_bytes(128) + tc::sw128_offset(rr, ch & 7));
-            *reinterpret_cast<uint4*>(p.y + (row0 + rr) * D + ch * 8) = val;
-          }
-          rr += drr; ch += dch;
-          if (ch >= cpr) { ch -= cpr; ++rr; }
-        }
-      }
-      tc::named_bar_sync(1, CV_CT);
+      tc::named_bar_sync(1, CV_CT);   // the staged tile (= the next tile's g buffer) is free; the accumulator is drained
       CV_TRACE(it, 6);
     }
   }
@@ -366,7 +375,7 @@ static int launch_conv(const ConvFP& p, unsigned grid, size_t smem, cudaStream_t
   }
 }
 
-// g: GLU output (B,T,D) bf16; img_out: packed after_conv.2 weight (64 x 64 blocks)
+// g: GLU output (B,T,D) bf16; img_out: packed after_conv.2 weight (64 x 64 blocks) in schedule order ([K-block][chunk])
 int tc_convf_second_half(const smx_convmod_weights* w, const void* img_out, int act, int B, int T, const __nv_bfloat16* g,
                          const uint8_t* mask, const __nv_bfloat16* residual, __nv_bfloat16* y, cudaStream_t st) {
   const int D = w->bottleneck.in_dim;
@@ -374,13 +383,14 @@ int tc_convf_second_half(const smx_convmod_weights* w, const void* img_out, int 
   p.g = g; p.dw_w = w->dw_w; p.dw_b = w->dw_b; p.ln_w = w->after_ln_w; p.ln_b = w->after_ln_b;
   p.w_img = (const uint8_t*)img_out; p.b_out = w->out.b; p.mask = mask; p.resid = residual; p.y = y;
   p.trace = g_trace3;
+  p.al32 = ((uintptr_t)y % 32 == 0) ? 1 : 0;
   p.B = B; p.T = T; p.D = D; p.tpu = (T + 127) / 128; p.n_tiles = B * p.tpu; p.act = act;
   const int nkb = D / 64;
   p.gw = nkb % 4 == 0 ? 4 : (nkb % 2 == 0 ? 2 : 1);
   const size_t gbytes = align_up((size_t)(128 + 30) * D * 2, 1024), stage = (size_t)nkb * kblock_bytes(128);
   p.off_a = (uint32_t)(gbytes > stage ? gbytes : stage);
   p.off_ring = p.off_a + (uint32_t)stage;
-  p.off_par = p.off_ring + CV_STAGES * CV_BLOCK;
+  p.off_par = p.off_ring + CV_STAGES * CV_SLOT;
   p.off_stat = p.off_par + 3072;
   const size_t smem = (size_t)p.off_stat + 2048;
   const unsigned grid = (unsigned)(p.n_tiles < convf_sms() ? p.n_tiles : convf_sms());

@@ -297,7 +297,7 @@ bool tc_convmod_supported(const smx_convmod_weights* w, int chunk) {
 size_t tc_convmod_packed_bytes(const smx_convmod_weights* w) {
   if (!tc_convmod_supported(w, 0)) return 0;
   const int D = w->bottleneck.in_dim;
-  return 2 * align_up(tc_linear_packed_bytes(D, 2 * D)) + align_up(tc_linear_packed_bytes(D, D));  // [GLU][out][GLU in schedule order]
+  return 2 * align_up(tc_linear_packed_bytes(D, 2 * D)) + 2 * align_up(tc_linear_packed_bytes(D, D));  // [GLU][out][GLU, out in schedule order]
 }
 int tc_convmod_pack(const smx_convmod_weights* w, void* packed, cudaStream_t st) {
   if (!tc_convmod_supported(w, 0)) return fail(SMX_ERR_UNSUPPORTED, "conv module not handled by the tensor-core arm");
@@ -305,8 +305,10 @@ int tc_convmod_pack(const smx_convmod_weights* w, void* packed, cudaStream_t st)
   if (tc_convf_supported(w, 0)) {  // fused path: 64 x 64 blocks, value/gate blocks interleaved for the GLU pass
     SMX_TRY(tc_pack_linear_nt(w->bottleneck, 0, D, 64, packed, st, 1));
     SMX_TRY(tc_pack_linear_nt(w->out, 0, D, 64, (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)), st));
-    return tc_cell3_reorder(w->bottleneck, D, 1, packed,
-                            (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)) + align_up(tc_linear_packed_bytes(D, D)), st);
+    char* sched = (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)) + align_up(tc_linear_packed_bytes(D, D));
+    SMX_TRY(tc_cell3_reorder(w->bottleneck, D, 1, packed, sched, st));
+    return tc_cell3_reorder(w->out, D, 1, (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)),
+                            sched + align_up(tc_linear_packed_bytes(D, 2 * D)), st);
   }
   SMX_TRY(tc_pack_linear(w->bottleneck, 0, D, 1, packed, st));
   SMX_TRY(tc_pack_linear(w->out, 0, D, 0, (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)), st));
@@ -523,8 +525,8 @@ int tc_convmod_fwd(const smx_convmod_weights* w, const void* packed, int act, in
                           w->ln_w, w->ln_b, rows, x, gb, st));
     else
       SMX_TRY(tc_glu_fwd(w->bottleneck, packed, w->ln_w, w->ln_b, rows, x, gb, st));
-    SMX_TRY(tc_convf_second_half(w, (const char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)), act, B, T, gb, mask,
-                                 residual, y, st));                                                        // :325-338, :543
+    SMX_TRY(tc_convf_second_half(w, (const char*)packed + 2 * align_up(tc_linear_packed_bytes(D, 2 * D)) + align_up(tc_linear_packed_bytes(D, D)),
+                                 act, B, T, gb, mask, residual, y, st));                                   // :325-338, :543
     ws.release(m0);
     return SMX_OK;
   }

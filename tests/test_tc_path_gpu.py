@@ -234,3 +234,59 @@ def test_cfg4_branchformer_lite_dims():
         y = m.to(DEV)(x.to(DEV), src_key_padding_mask=mask.to(DEV))[0]
     torch.cuda.synchronize()
     assert float((y.cpu() - y_or).abs().max()) < 5e-4
+
+
+@pytest.mark.parametrize("version", [1, 3])
+def test_cell_kernel_generations_agree(version):
+    """K-SM first generation (operands staged through shared memory) and v3 (H / L operands resident in tensor memory,
+    schedule-ordered weight ring) compute the same cell and GLU pass: each against the oracle on a ragged batch with
+    more tiles than SMs; run-to-run bit-identical."""
+    torch.manual_seed(51)
+    D = 256
+    m = S.ConformerEncoderLayer(D, 1024, 4, 31, attention_type="SummaryMixing", local_proj_hid_dim=[D],
+                                local_proj_out_dim=D, summary_hid_dim=[D]).eval()
+    _perturb(m, 51)
+    B, T = 23, 901
+    g = torch.Generator().manual_seed(52)
+    x = torch.randn(B, T, D, generator=g).to(torch.bfloat16)
+    lens = torch.randint(200, T + 1, (B,), generator=g)
+    lens[0] = T
+    mask = torch.arange(T)[None] < lens[:, None]
+    y_or = O.conformer_layer(x.float(), dict(m.state_dict()), "", act="swish", src_key_padding_mask=mask)
+    try:
+        assert L.lib().smx_debug_set_cell_version(version) == 0
+        with torch.no_grad():
+            m = m.to(DEV)
+            y = m(x.to(DEV), src_key_padding_mask=mask.to(DEV))[0]
+            y2 = m(x.to(DEV), src_key_padding_mask=mask.to(DEV))[0]
+        torch.cuda.synchronize()
+    finally:
+        L.lib().smx_debug_set_cell_version(3)
+    assert torch.equal(y, y2)
+    _check(y, y_or, f"conformer layer, cell generation {version}", abs_tol=4e-2, rel_tol=2e-2)
+
+
+def test_programmatic_dependent_launch_is_transparent():
+    """The fused kernels overlap their set-up (and pass B of the cell its first tile) with their predecessors through
+    griddepcontrol; the results must be bit-identical with it switched off."""
+    torch.manual_seed(61)
+    n = 3
+    m = S.ConformerEncoder(n, 256, 1024, 4, 31, attention_type="SummaryMixing", local_proj_hid_dim=[256],
+                           local_proj_out_dim=256, summary_hid_dim=[256]).eval().to(DEV)
+    g = torch.Generator().manual_seed(62)
+    B, T = 32, 1000
+    x = torch.randn(B, T, 256, generator=g).to(torch.bfloat16).to(DEV)
+    lens = torch.randint(500, T + 1, (B,), generator=g)
+    mask = (torch.arange(T)[None] < lens[:, None]).to(DEV)
+    with torch.no_grad():
+        outs = []
+        for on in (1, 0, 1):
+            try:
+                assert L.lib().smx_debug_set_pdl(on) == 0
+                for _ in range(3):  # back-to-back forwards: every kernel has a programmatic predecessor
+                    y = m(x, src_key_padding_mask=mask)[0]
+                torch.cuda.synchronize()
+            finally:
+                L.lib().smx_debug_set_pdl(1)
+            outs.append(y.clone())
+    assert torch.equal(outs[0], outs[1]) and torch.equal(outs[0], outs[2])
