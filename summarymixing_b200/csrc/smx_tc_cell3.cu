@@ -183,9 +183,9 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
       int s = 0;
       uint32_t pe = 0;
       for (int tile = first_tile; tile < p.n_tiles; tile += tile_step) {
-#pragma unroll
+#pragma unroll 1
         for (int gi = 0; gi < NG; ++gi) {
-          const C3Gemm g = p.g[gi];
+          const C3Gemm& g = p.g[gi];
           const int ups = 4 / g.gw;  // units per step
           for (int st = 0; st < g.n_steps; ++st) {
             const int nu = g.n_units - st * ups < ups ? g.n_units - st * ups : ups;
@@ -284,7 +284,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
       tc::mbar_wait(&x_free, (it - 1) & 1);
       if (pw == 0) C3_TRACE(2, it, 0);
-      tc::stage_ln_rows(sX, p.x, p.ldx, row0, nrows, p.D, pw, lane, p.pre_w != nullptr, sPar + 1280, sPar + 1536);
+      tc::stage_ln_rows_wide(sX, p.x, p.ldx, row0, nrows, p.D, pw * 4, 4, lane, p.pre_w != nullptr, sPar + 1280, sPar + 1536);
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&x_full);
@@ -308,7 +308,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
       if (warp == 0) C3_TRACE(3, it, 0);
       if (it == 0) {  // first tile: all 16 epilogue warps stage and normalise it (8 rows each)
-        tc::stage_ln_rows_wide(sX, p.x, p.ldx, row0, nrows, p.D, warp, lane, p.pre_w != nullptr, sPar + 1280, sPar + 1536);
+        tc::stage_ln_rows_wide(sX, p.x, p.ldx, row0, nrows, p.D, warp, 1, lane, p.pre_w != nullptr, sPar + 1280, sPar + 1536);
         tc::fence_proxy_async();
         tc::named_bar_sync(5, C3_NEW * 32);
         if (warp < C3_NPW && lane == 0) tc::mbar_arrive(&x_full);
@@ -360,7 +360,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
       tc::mbar_wait(&acc_full[0], par);
       tc::tc_fence_after();
       if (warp == 0) C3_TRACE(3, it, 2);
-#pragma unroll
+#pragma unroll 1
       for (int rd = 0; rd < 2; ++rd) {
         const int piece = k + 4 * rd, col = piece * 32;
         float v[32];
@@ -391,7 +391,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
         tc::mbar_wait(&acc_full[1], par);
         tc::tc_fence_after();
         if (warp == 0) C3_TRACE(3, it, 4);
-#pragma unroll
+#pragma unroll 1
         for (int rd = 0; rd < 2; ++rd) {
           const int col = (k + 4 * rd) * 32;
           if (col < H2) {
@@ -425,7 +425,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
         if (p.ln_w) {
           // pass 1: activated, masked values parked as fp32 in region B; per-thread (mean, M2) over its <= 64 values
           float mean_t = 0.0f, m2_t = 0.0f, n_t = 0.0f;
-#pragma unroll
+#pragma unroll 1
           for (int rd = 0; rd < 2; ++rd) {
             const int col = (k + 4 * rd) * 32;
             if (col < H2) {
@@ -465,7 +465,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
           }
           rstd = rsqrtf(m2 / n + 1e-5f);
         }
-#pragma unroll
+#pragma unroll 1
         for (int rd = 0; rd < 2; ++rd) {
           const int piece = k + 4 * rd, col = piece * 32;
           if (col < H2) {

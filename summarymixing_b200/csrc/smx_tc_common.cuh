@@ -483,8 +483,7 @@ __device__ __forceinline__ void stage_ln_rows(uint8_t* sX, const __nv_bfloat16* 
 // and the column quarter l >> 3 (D / 32 chunks), the four partial statistics of a row meeting through two shuffles.
 // The 8 lanes of each 128-bit shared-memory phase hold 8 different rows of one quarter: conflict-free under the swizzle.
 // D % 32 == 0, D <= 256.
-__device__ __forceinline__ void stage_ln_rows_wide(uint8_t* sX, const __nv_bfloat16* x, int64_t ldx, int64_t row0, int nrows, int D,
-                                                   int w, int lane, bool do_ln, const float* sW, const float* sB) {
+__device__ __forceinline__ void rows8_copy(uint8_t* sX, const __nv_bfloat16* x, int64_t ldx, int64_t row0, int nrows, int D, int w, int lane) {
   const int nch = D >> 3;
   if (lane < nch) {
     uint8_t* const base = sX + (size_t)(lane >> 3) * kblock_bytes(128);
@@ -496,10 +495,9 @@ __device__ __forceinline__ void stage_ln_rows_wide(uint8_t* sX, const __nv_bfloa
       cp_async16(base + sw128_offset(r, lane & 7), in ? (const void*)(src + (int64_t)j * ldx) : (const void*)x, in ? 16u : 0u);
     }
   }
-  cp_async_commit();
-  cp_async_wait_all();
-  __syncwarp();
-  if (!do_ln) return;
+}
+__device__ __forceinline__ void rows8_ln(uint8_t* sX, int nrows, int D, int w, int lane, const float* sW, const float* sB) {
+  const int nch = D >> 3;
   const int r = w * 8 + (lane & 7), qq = lane >> 3, cq = nch >> 2;  // chunks per quarter
   const uint32_t rx = (uint32_t)(r & 7);
   uint8_t* const rowp = sX + (r >> 3) * 1024 + (r & 7) * 128;
@@ -509,7 +507,7 @@ __device__ __forceinline__ void stage_ln_rows_wide(uint8_t* sX, const __nv_bfloa
   float a1[8], a2[8];
 #pragma unroll
   for (int e = 0; e < 8; ++e) { a1[e] = 0.0f; a2[e] = 0.0f; }
-#pragma unroll 4
+#pragma unroll 2
   for (int i = 0; i < cq; ++i) {
     const int c = qq * cq + i;
     unpack_bf16x8(*reinterpret_cast<const uint4*>(rowp + (size_t)(c >> 3) * kblock_bytes(128) + ((((uint32_t)c & 7u) ^ rx) << 4)), v);
@@ -525,7 +523,7 @@ __device__ __forceinline__ void stage_ln_rows_wide(uint8_t* sX, const __nv_bfloa
   const float rstd = rsqrtf(fmaxf(s2 * invD - m0 * m0, 0.0f) + 1e-5f);
   const float shift = -(m0 + x0) * rstd;
   const bool live = r < nrows;
-#pragma unroll 4
+#pragma unroll 2
   for (int i = 0; i < cq; ++i) {
     const int c = qq * cq + i;
     uint4* const cp = reinterpret_cast<uint4*>(rowp + (size_t)(c >> 3) * kblock_bytes(128) + ((((uint32_t)c & 7u) ^ rx) << 4));
@@ -538,6 +536,20 @@ __device__ __forceinline__ void stage_ln_rows_wide(uint8_t* sX, const __nv_bfloa
     for (int e = 0; e < 8; ++e) v[e] = live ? fmaf(fmaf(v[e], rstd, shift), wv[e], bv[e]) : 0.0f;
     *cp = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
   }
+}
+// n_groups consecutive 8-row groups starting at group w0 (1 for each of the 16 epilogue warps on a CTA's first tile, 4 for
+// each of the 4 prologue warps afterwards): every copy in flight first, then the LayerNorm passes.  One implementation for
+// both callers keeps the kernels' code small (each kernel's code is fetched cold at every launch of a layer's chain).
+static __device__ __noinline__ void stage_ln_rows_wide(uint8_t* sX, const __nv_bfloat16* x, int64_t ldx, int64_t row0, int nrows, int D,
+                                                   int w0, int n_groups, int lane, bool do_ln, const float* sW, const float* sB) {
+#pragma unroll 1
+  for (int i = 0; i < n_groups; ++i) rows8_copy(sX, x, ldx, row0, nrows, D, w0 + i, lane);
+  cp_async_commit();
+  cp_async_wait_all();
+  __syncwarp();
+  if (!do_ln) return;
+#pragma unroll 1
+  for (int i = 0; i < n_groups; ++i) rows8_ln(sX, nrows, D, w0 + i, lane, sW, sB);
 }
 
 }  // namespace tc

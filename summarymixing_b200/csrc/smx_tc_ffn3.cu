@@ -101,7 +101,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
   float* sPar = reinterpret_cast<float*>(smem + p.off_par);  // [b1 (F) | b2 | oln_w | oln_b | ln_w | ln_b (256 each)]
   float* sRed = reinterpret_cast<float*>(smem + p.off_red);  // [4 column quarters][128 rows][2]: per-thread (mean, M2)
   __shared__ __align__(8) uint64_t full_bar[F3_STAGES], peer_full[F3_STAGES], empty_bar[F3_STAGES];
-  __shared__ __align__(8) uint64_t x_full, x_free, acc1_full[2], h_full[2], acc2_full, epi_done;
+  __shared__ __align__(8) uint64_t x_full, x_free, x_copied, acc1_full[2], h_full[2], acc2_full, epi_done;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -123,7 +123,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
   if (warp == F3_PROD_WARP) { if (CL2) tc::tmem_alloc2(&tmem_base_s, 512); else tc::tmem_alloc(&tmem_base_s, 512); }
   if (tid == 0) {
     for (int s = 0; s < F3_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&peer_full[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    tc::mbar_init(&x_full, F3_NPW * NCTA); tc::mbar_init(&x_free, 1); tc::mbar_init(&acc2_full, 1); tc::mbar_init(&epi_done, F3_NEW * NCTA);
+    tc::mbar_init(&x_full, F3_NPW * NCTA); tc::mbar_init(&x_free, 1); tc::mbar_init(&x_copied, F3_NPW); tc::mbar_init(&acc2_full, 1); tc::mbar_init(&epi_done, F3_NEW * NCTA);
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc1_full[i], 1); tc::mbar_init(&h_full[i], F3_NEW * NCTA); }
     tc::fence_barrier_init();
   }
@@ -336,20 +336,23 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
     }
     }
   } else if (warp >= F3_PRO_WARP0) {
-    // =============================== prologue: x tile -> LN -> A operand ===============================
-    // (the CTA's first tile is staged by the 16 epilogue warps, which have nothing else to do yet)
+    // =============================== prologue: x tile -> A operand image (copy only) ===============================
+    // The copy of tile t+1 starts as soon as the last GEMM1 of tile t has released X; the LayerNorm is left to the 16
+    // epilogue warps, which run it in 2 k cycles right after the final epilogue of tile t (four prologue warps competing
+    // with the busy epilogue warps took 20 k and sat on the critical path between two tiles).
     const int pw = warp - F3_PRO_WARP0;
-    int it = 1;
-    for (int base = first_base + base_step; base < p.n_tiles; base += base_step, ++it) {
+    int it = 0;
+    for (int base = first_base; base < p.n_tiles; base += base_step, ++it) {
       const int64_t row0 = (int64_t)(base + (int)crank) * 128;
       const int nrows = p.rows - row0 < 128 ? (int)(p.rows - row0) : 128;
-      tc::mbar_wait(&x_free, (it - 1) & 1);
+      if (it > 0) tc::mbar_wait(&x_free, (it - 1) & 1);
       if (pw == 0) F3_TRACE(2, it, 0);
-      tc::stage_ln_rows(sX, p.x, D, row0, nrows, D, pw, lane, true, sLw, sLb,
-                        (p.trace && blockIdx.x == 0 && pw == 0 && it < 2) ? p.trace + ((2 * 2 + it) * 32) + 4 : nullptr);
-      tc::fence_proxy_async();
+#pragma unroll 1
+      for (int i = 0; i < 4; ++i) tc::rows8_copy(sX, p.x, D, row0, nrows, D, pw * 4 + i, lane);
+      tc::cp_async_commit();
+      tc::cp_async_wait_all();
       __syncwarp();
-      if (lane == 0) arrive_leader(&x_full);
+      if (lane == 0) tc::mbar_arrive(&x_copied);
       if (pw == 0) F3_TRACE(2, it, 1);
     }
   } else {
@@ -363,12 +366,12 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
       const uint32_t par = it & 1;
       const int64_t row0 = (int64_t)(base + (int)crank) * 128;
       const int nrows = p.rows - row0 < 128 ? (int)(p.rows - row0) : 128;
-      if (it == 0) {  // first tile: all 16 epilogue warps stage and normalise it (8 rows each)
-        tc::stage_ln_rows_wide(sX, p.x, D, row0, nrows, D, warp, lane, true, sLw, sLb);
-        tc::fence_proxy_async();
-        tc::named_bar_sync(5, F3_NEW * 32);
-        if (warp < F3_NPW && lane == 0) arrive_leader(&x_full);
-      }
+      // the tile has been copied into the operand image: LayerNorm in place, 8 rows per warp
+      tc::mbar_wait(&x_copied, par);
+      tc::rows8_ln(sX, nrows, D, warp, lane, sLw, sLb);
+      tc::fence_proxy_async();
+      tc::named_bar_sync(5, F3_NEW * 32);
+      if (warp < F3_NPW && lane == 0) arrive_leader(&x_full);
       for (int j = 0; j < nj; ++j) {
         const int bsel = j & 1;
         tc::mbar_wait(&acc1_full[bsel], (ph_a1f >> bsel) & 1u);
@@ -470,7 +473,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
         const float shift = -mean * rstd;
         if (warp == 0) F3_TRACE(3, it, 13);
         if (active) {
-#pragma unroll
+#pragma unroll 1
           for (int h = 0; h < 4; ++h) {
             const int col = k * 64 + h * 16;
             float v[16];
