@@ -227,44 +227,45 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
         }
         tc::tc_fence_after();
         C3_TRACE(1, it, gi * 2);
-        // The issue loop is a serial scalar instruction stream on one warp: keep it short (no divisions, descriptors
-        // advanced by adding to their encoded form: +2 in the 16-byte address field per 32-byte K step).
-        const uint32_t ups_mask = (uint32_t)(4 / g.gw) - 1u;  // units per step - 1 (1, 2 or 4 units)
+        // The issue loop is a serial scalar instruction stream on one warp: keep it short.  Per step: one barrier wait by
+        // the warp, then ONE elected lane walks the step's units (up to four 4-MMA groups) in straight-line code with
+        // incrementally maintained schedule coordinates (no divisions, no per-unit elect/sync; descriptors advance by adding
+        // to their encoded form: +2 in the 16-byte address field per 32-byte K step), then one commit.
+        const int ups = 4 / g.gw;  // units per step (1, 2 or 4)
         const uint32_t unit_bytes = (uint32_t)g.gw * C3_BLOCK;
-        const int last_unit = g.n_units - 1;
-        uint32_t unit = 0, b_addr = 0;
-        uint32_t kba = 0, dcol = 0;  // K-block of the A operand / first accumulator column, advanced with the loops
-        for (int m = 0; m < g.nheads; ++m)
-          for (int j = 0; j < g.cph; j += g.gw, dcol += 64u * (uint32_t)g.gw) {
-            kba = (uint32_t)(m * g.kph);
-            for (int kb = 0; kb < g.kph; ++kb, ++unit, ++kba) {
-              const uint32_t uis = unit & ups_mask;  // unit inside its step
-              if (uis == 0) {
-                tc::mbar_wait_spin(&full_bar[s], (pf >> s) & 1u);
-                pf ^= 1u << s;
-                tc::tc_fence_after();
-                b_addr = r0 + (uint32_t)s * C3_SLOT;
-              }
-              const bool step_end = uis == ups_mask || (int)unit == last_unit;
-              if (tc::elect_one()) {
-                const uint64_t bd = tc::make_desc_sw128(b_addr);
-                const uint32_t d_addr = dbase + dcol;
-                if (gi == 0) {
-                  const uint64_t ad = tc::make_desc_sw128(x0 + kba * kblock_bytes(128));
+        int m = 0, j = 0, kb = 0, units_left = g.n_units;
+        for (int st = 0; st < g.n_steps; ++st) {
+          tc::mbar_wait_spin(&full_bar[s], (pf >> s) & 1u);
+          pf ^= 1u << s;
+          tc::tc_fence_after();
+          const int nu = units_left < ups ? units_left : ups;
+          if (tc::elect_one()) {
+            uint32_t b_addr = r0 + (uint32_t)s * C3_SLOT;
+            int mm = m, jj = j, kk = kb;
+            for (int u = 0; u < nu; ++u) {
+              const uint64_t bd = tc::make_desc_sw128(b_addr);
+              const uint32_t d_addr = dbase + (uint32_t)(mm * g.cph + jj) * 64u;
+              const uint32_t kba = (uint32_t)(mm * g.kph + kk);  // K-block of the A operand
+              if (gi == 0) {
+                const uint64_t ad = tc::make_desc_sw128(x0 + kba * kblock_bytes(128));
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) tc::umma_bf16(d_addr, ad + 2u * ks, bd + 2u * ks, idesc, (kb == 0 && ks == 0) ? 0u : 1u);
-                } else {
-                  const uint32_t at = regA + (gi == 2 ? 128u : 0u) + kba * 32u;
+                for (int ks = 0; ks < 4; ++ks) tc::umma_bf16(d_addr, ad + 2u * ks, bd + 2u * ks, idesc, (kk == 0 && ks == 0) ? 0u : 1u);
+              } else {
+                const uint32_t at = regA + (gi == 2 ? 128u : 0u) + kba * 32u;
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) c3_umma_ts(d_addr, at + 8u * ks, bd + 2u * ks, idesc, (kb == 0 && ks == 0) ? 0u : 1u);
-                }
-                if (step_end) tc::umma_commit(&empty_bar[s]);  // one commit per step
+                for (int ks = 0; ks < 4; ++ks) c3_umma_ts(d_addr, at + 8u * ks, bd + 2u * ks, idesc, (kk == 0 && ks == 0) ? 0u : 1u);
               }
-              __syncwarp();
               b_addr += unit_bytes;
-              if (step_end) { if (++s == nslots) s = 0; }
+              if (++kk == g.kph) { kk = 0; jj += g.gw; if (jj == g.cph) { jj = 0; ++mm; } }
             }
+            tc::umma_commit(&empty_bar[s]);  // one commit per step
           }
+          __syncwarp();
+          // every lane advances the schedule coordinates by the step's units (warp-uniform state)
+          for (int u = 0; u < nu; ++u) { if (++kb == g.kph) { kb = 0; j += g.gw; if (j == g.cph) { j = 0; ++m; } } }
+          units_left -= nu;
+          if (++s == nslots) s = 0;
+        }
         if (tc::elect_one()) {
           tc::umma_commit(&acc_full[gi]);
           if (gi == 0) tc::umma_commit(&x_free);
@@ -436,19 +437,21 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
 #pragma unroll
               for (int j = 0; j < 8; ++j) { const float4 bb = bp[j]; v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w; }
               tc::act_apply<32>(act, v);
-              float sm = 0.0f;
+              float sa[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // four independent chains (fixed association: deterministic)
 #pragma unroll
-              for (int j = 0; j < 32; ++j) { v[j] *= rscale; sm += v[j]; }
-              const float mh = sm * (1.0f / 32.0f);
-              float qh = 0.0f;
+              for (int j = 0; j < 32; ++j) { v[j] *= rscale; sa[j & 3] += v[j]; }
+              const float mh = ((sa[0] + sa[1]) + (sa[2] + sa[3])) * (1.0f / 32.0f);
+              float qa[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-              for (int j = 0; j < 32; ++j) { const float d = v[j] - mh; qh = fmaf(d, d, qh); }
+              for (int j = 0; j < 32; ++j) { const float d = v[j] - mh; qa[j & 3] = fmaf(d, d, qa[j & 3]); }
+              const float qh = (qa[0] + qa[1]) + (qa[2] + qa[3]);
               if (n_t == 0.0f) { mean_t = mh; m2_t = qh; n_t = 32.0f; }
               else { const float dl = mh - mean_t; mean_t += 0.5f * dl; m2_t += qh + dl * dl * 16.0f; n_t = 64.0f; }
               tc::tmem_st32(regB + lane_sel + col, v);
             }
           }
           tc::tmem_st_wait();
+          if (warp == 0) C3_TRACE(3, it, 8);
           sRed[(k * 128 + r) * 3] = mean_t; sRed[(k * 128 + r) * 3 + 1] = m2_t; sRed[(k * 128 + r) * 3 + 2] = n_t;
           tc::named_bar_sync(1 + q, 128);
           // Chan's merge of the (up to) four per-thread partials of this row, in fixed order
@@ -464,6 +467,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
             }
           }
           rstd = rsqrtf(m2 / n + 1e-5f);
+          if (warp == 0) C3_TRACE(3, it, 9);
         }
 #pragma unroll 1
         for (int rd = 0; rd < 2; ++rd) {

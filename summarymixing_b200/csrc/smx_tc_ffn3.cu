@@ -436,13 +436,14 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
           }
           if (OLN) {
             // running (mean, M2) of this thread's 64 values: exact two-pass inside a piece, Chan's merge across pieces
-            float sm = 0.0f;
+            float sa[4] = {0.0f, 0.0f, 0.0f, 0.0f};  // four independent chains (fixed association: deterministic)
 #pragma unroll
-            for (int e = 0; e < 16; ++e) sm += v[e];
-            const float mh = sm * (1.0f / 16.0f);
-            float qh = 0.0f;
+            for (int e = 0; e < 16; ++e) sa[e & 3] += v[e];
+            const float mh = ((sa[0] + sa[1]) + (sa[2] + sa[3])) * (1.0f / 16.0f);
+            float qa[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
-            for (int e = 0; e < 16; ++e) { const float d = v[e] - mh; qh = fmaf(d, d, qh); }
+            for (int e = 0; e < 16; ++e) { const float d = v[e] - mh; qa[e & 3] = fmaf(d, d, qa[e & 3]); }
+            const float qh = (qa[0] + qa[1]) + (qa[2] + qa[3]);
             if (h == 0) { mean_t = mh; m2_t = qh; }
             else {
               const float dl = mh - mean_t, na = 16.0f * h;
