@@ -292,11 +292,13 @@ def run_smx(args):
 
         # ---- e2e: same metric through the public module call with HOST buffers (pinned), copies inside the region.
         # A serving loop: step i's input travels host -> device on a copy stream while step i-1 computes, its result
-        # travels back on the same copy stream; every step's H2D and D2H happen inside the timed region.
+        # travels back on a second copy stream; every step's H2D and D2H happen inside the timed region.
         hx = [x.to(torch.bfloat16).pin_memory() for x, _ in host[:4]]
         hm = [m.pin_memory() for _, m in host[:4]]
         hy = [torch.empty(B, T, D, dtype=torch.bfloat16).pin_memory() for _ in range(4)]
-        copy_stream = torch.cuda.Stream(dev)
+        copy_stream = torch.cuda.Stream(dev)   # host -> device
+        back_stream = torch.cuda.Stream(dev)   # device -> host (its own stream: an in-order single copy stream would hold
+                                               # the next step's input behind this step's result)
         main_stream = torch.cuda.current_stream(dev)
         try:
             if args.eager:
@@ -318,7 +320,7 @@ def run_smx(args):
         def e2e_loop(n):
             for j in range(2):
                 in_free[j].record(main_stream)
-                out_free[j].record(copy_stream)
+                out_free[j].record(back_stream)
             for i in range(n):
                 j = i & 1
                 with torch.cuda.stream(copy_stream):
@@ -332,11 +334,12 @@ def run_smx(args):
                 main_stream.wait_event(out_free[j])             # the D2H that read this staging buffer has finished
                 yd[j].copy_(y)
                 out_ready[j].record(main_stream)
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(out_ready[j])
+                with torch.cuda.stream(back_stream):
+                    back_stream.wait_event(out_ready[j])
                     hy[i % 4].copy_(yd[j], non_blocking=True)
-                    out_free[j].record(copy_stream)
-            main_stream.wait_stream(copy_stream)                # the last result is on the host when the region ends
+                    out_free[j].record(back_stream)
+            main_stream.wait_stream(copy_stream)
+            main_stream.wait_stream(back_stream)                # the last result is on the host when the region ends
 
         e2e_loop(3)
         barrier()
@@ -367,7 +370,7 @@ def run_smx(args):
                        "accumulate": "fp32", "io": "bf16", "launch": mode},
             "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * T * D * 2 + B * T,
                     "d2h_bytes_per_step": B * T * D * 2, "ms_per_step": e2e_ms / args.steps,
-                    "api": "summarymixing_b200.GraphedForward(ConformerEncoder) (CUDA-graph replay of ConformerEncoder.forward); pinned host inputs/outputs, H2D/D2H on a copy stream overlapped with the previous/next step"},
+                    "api": "summarymixing_b200.GraphedForward(ConformerEncoder) (CUDA-graph replay of ConformerEncoder.forward); pinned host inputs/outputs, H2D and D2H on their own streams, overlapped with the previous/next step"},
             "gpu_launches": launches, "tc_launches": tc_launches, "clocks": clocks}
 
     if rank == 0:
@@ -384,9 +387,9 @@ def run_smx(args):
                             "bound": "hbm", "achieved": bytes_cell / us / 1e3, "peak": pk["hbm_gbs"], "unit": "GB/s",
                             "frac": bytes_cell / us / 1e3 / pk["hbm_gbs"],
                             # dram__bytes_read+write per cell call from the ncu --set full capture summarised in
-                            # profiles/r01_call60_ncu_layer_summary.csv (pass A 16.57 MB + finalise 0.58 MB + pass B 16.77 MB
-                            # read, 0.29 MB written: most of the 16.4 MB output was still in L2 when the window closed)
-                            "traffic": 34.21e6, "algorithmic_bytes": bytes_cell,
+                            # profiles/r01_call80_ncu_layer_summary.csv (pass A 16.54 MB + finalise 0.58 MB + pass B 16.73 MB
+                            # read, 0.30 MB written: most of the 16.4 MB output was still in L2 when the window closed)
+                            "traffic": 34.15e6, "algorithmic_bytes": bytes_cell,
                             "us_per_call": us, "peak_source": pk["source"] + " (burst copy)",
                             "tensor_tflops": flops_cell / us / 1e6, "tensor_frac": flops_cell / us / 1e6 / pk["bf16_tflops"]}
         flops_ffn = frames * 4 * D * FFN
