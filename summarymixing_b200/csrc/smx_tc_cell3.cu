@@ -134,12 +134,18 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
   float* sPar = reinterpret_cast<float*>(smem + p.off_par);   // [b1 | b2 | ln_w | ln_b | c[b] | norm1 w | norm1 b], 256 floats each
   float* sRed = reinterpret_cast<float*>(smem + p.off_red);   // 1024 floats: column partials / LayerNorm statistics
   __shared__ __align__(8) uint64_t full_bar[C3_MAX_SLOTS], empty_bar[C3_MAX_SLOTS];
-  __shared__ __align__(8) uint64_t x_full, x_free, acc_full[3], op_full[2], epi_done;
+  __shared__ __align__(8) uint64_t x_full, x_free, x_copied, acc_full[3], op_full[2], epi_done;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler (role dispatch below)
   constexpr int NG = PHASE == 0 ? 2 : (PHASE == 1 ? 3 : 1);
+  // Who normalises a tile.  Pass B's tiles are long (three GEMMs, three epilogues): the four prologue warps copy AND
+  // normalise the next tile in their shadow (the CTA's first tile is done by the 16 idle epilogue warps).  Pass A and the
+  // GLU pass have short tiles: four solo warps competing with the busy epilogue warps need ~14 k cycles and would sit on
+  // the critical path between two tiles, so there the prologue warps only copy (early) and the 16 epilogue warps
+  // normalise in place right after the previous tile's epilogue.
+  constexpr bool EPI_LN = PHASE != 1;
   const int act = ACT >= 0 ? ACT : p.act;
 
   // Programmatic dependent launch.  Pass A and the GLU pass read the output of their immediate predecessor: they wait for it
@@ -152,7 +158,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
   if (warp == C3_PROD_WARP) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int s = 0; s < C3_MAX_SLOTS; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    tc::mbar_init(&x_full, C3_NPW); tc::mbar_init(&x_free, 1); tc::mbar_init(&epi_done, C3_NEW);
+    tc::mbar_init(&x_full, C3_NPW); tc::mbar_init(&x_free, 1); tc::mbar_init(&x_copied, C3_NPW); tc::mbar_init(&epi_done, C3_NEW);
     for (int i = 0; i < 3; ++i) tc::mbar_init(&acc_full[i], 1);
     for (int i = 0; i < 2; ++i) tc::mbar_init(&op_full[i], C3_NEW);
     tc::fence_barrier_init();
@@ -162,8 +168,10 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
     sPar[256 + i] = i < p.nb2 ? p.b2[i] : 0.0f;
     sPar[512 + i] = (p.ln_w && i < p.nb2) ? p.ln_w[i] : 1.0f;
     sPar[768 + i] = (p.ln_b && i < p.nb2) ? p.ln_b[i] : 0.0f;
-    sPar[1280 + i] = (p.pre_w && i < p.D) ? p.pre_w[i] : 1.0f;
-    sPar[1536 + i] = (p.pre_b && i < p.D) ? p.pre_b[i] : 0.0f;
+    if (i < p.D) {  // norm1 / conv-module LayerNorm parameters, padded layout (tc::ln_pad_index)
+      sPar[1280 + tc::ln_pad_index(i, p.D)] = p.pre_w ? p.pre_w[i] : 1.0f;
+      sPar[1552 + tc::ln_pad_index(i, p.D)] = p.pre_b ? p.pre_b[i] : 0.0f;
+    }
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -276,19 +284,27 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
     }
   } else if (warp >= C3_PRO_WARP0) {
     // =============================== prologue: x tile -> LN -> A operand ===============================
-    // (the CTA's first tile is staged by the 16 epilogue warps, which have nothing else to do yet)
     const int pw = warp - C3_PRO_WARP0;
-    int it = 1;
-    for (int tile = first_tile + tile_step; tile < p.n_tiles; tile += tile_step, ++it) {
+    int it = EPI_LN ? 0 : 1;  // (pass B: the CTA's first tile is staged by the 16 epilogue warps, idle at that point)
+    for (int tile = first_tile + (EPI_LN ? 0 : tile_step); tile < p.n_tiles; tile += tile_step, ++it) {
       const int b = tile / p.tpu, t0 = (tile % p.tpu) * 128;
       const int64_t row0 = (int64_t)b * p.T + t0;
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
-      tc::mbar_wait(&x_free, (it - 1) & 1);
+      if (it > 0) tc::mbar_wait(&x_free, (it - 1) & 1);
       if (pw == 0) C3_TRACE(2, it, 0);
-      tc::stage_ln_rows_wide(sX, p.x, p.ldx, row0, nrows, p.D, pw * 4, 4, lane, p.pre_w != nullptr, sPar + 1280, sPar + 1536);
-      tc::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&x_full);
+      if (EPI_LN) {  // copy only
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) tc::rows8_copy(sX, p.x, p.ldx, row0, nrows, p.D, pw * 4 + i, lane);
+        tc::cp_async_commit();
+        tc::cp_async_wait_all();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&x_copied);
+      } else {
+        tc::stage_ln_rows_wide(sX, p.x, p.ldx, row0, nrows, p.D, pw * 4, 4, lane, p.pre_w != nullptr, sPar + 1280, sPar + 1552);
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&x_full);
+      }
       if (pw == 0) C3_TRACE(2, it, 1);
     }
   } else {
@@ -308,8 +324,15 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
       const int64_t row0 = (int64_t)b * p.T + t0;
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
       if (warp == 0) C3_TRACE(3, it, 0);
-      if (it == 0) {  // first tile: all 16 epilogue warps stage and normalise it (8 rows each)
-        tc::stage_ln_rows_wide(sX, p.x, p.ldx, row0, nrows, p.D, warp, 1, lane, p.pre_w != nullptr, sPar + 1280, sPar + 1536);
+      if (EPI_LN) {  // the tile has been copied into the operand image: LayerNorm in place, 8 rows per warp
+        tc::mbar_wait(&x_copied, par);
+        if (p.pre_w) tc::rows8_ln(sX, nrows, p.D, warp, lane, sPar + 1280, sPar + 1552);
+        tc::fence_proxy_async();
+        tc::named_bar_sync(5, C3_NEW * 32);
+        if (warp < C3_NPW && lane == 0) tc::mbar_arrive(&x_full);
+        if (warp == 0) C3_TRACE(3, it, 1);
+      } else if (it == 0) {  // first tile: all 16 epilogue warps stage and normalise it (8 rows each)
+        tc::stage_ln_rows_wide(sX, p.x, p.ldx, row0, nrows, p.D, warp, 1, lane, p.pre_w != nullptr, sPar + 1280, sPar + 1552);
         tc::fence_proxy_async();
         tc::named_bar_sync(5, C3_NEW * 32);
         if (warp < C3_NPW && lane == 0) tc::mbar_arrive(&x_full);
@@ -323,6 +346,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
         // (chunk 2c / 2c+1).  This warp: output columns [64k, 64k + 64) in four pieces of 16, one 256-bit store each.
         tc::mbar_wait(&acc_full[0], par);
         tc::tc_fence_after();
+        if (warp == 0) C3_TRACE(3, it, 2);
         if (k * 64 < p.Dout) {
 #pragma unroll
           for (int h = 0; h < 4; ++h) {
@@ -351,6 +375,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&epi_done);
+        if (warp == 0) C3_TRACE(3, it, 3);
         continue;
       }
 
@@ -713,6 +738,7 @@ int tc_glu3_fwd(const smx_linear& L, const void* img_sched, const float* ln_w, c
   p.Dout = D; p.Ds = D;
   p.g[0] = c3_make_gemm(L, D, 1); p.g[0].img = (const uint8_t*)img_sched;
   p.b1 = L.b; p.b2 = L.b + D; p.nb1 = D; p.nb2 = D;
+  p.trace = g_trace_c3;  // (diagnostics) the GLU pass writes its timeline where pass A would
   const size_t smem = c3_carve(p, D);
   const unsigned grid = (unsigned)(p.n_tiles < c3_sms() ? p.n_tiles : c3_sms());
   return launch_cell3_act<2, 0>(p, grid, smem, st);  // the GLU pass has no runtime activation (sigmoid gate only)

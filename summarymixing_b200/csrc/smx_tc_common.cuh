@@ -528,8 +528,10 @@ __device__ __forceinline__ void rows8_ln(uint8_t* sX, int nrows, int D, int w, i
     const int c = qq * cq + i;
     uint4* const cp = reinterpret_cast<uint4*>(rowp + (size_t)(c >> 3) * kblock_bytes(128) + ((((uint32_t)c & 7u) ^ rx) << 4));
     unpack_bf16x8(*cp, v);
-    const float4 w0 = *reinterpret_cast<const float4*>(sW + c * 8), w1 = *reinterpret_cast<const float4*>(sW + c * 8 + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(sB + c * 8), b1 = *reinterpret_cast<const float4*>(sB + c * 8 + 4);
+    // LN parameters in the PADDED layout (ln_pad_index): the four column quarters a warp reads at once sit 16 bytes further
+    // apart than a multiple of 128 bytes, so the four distinct addresses of a load fall into different banks
+    const float4 w0 = *reinterpret_cast<const float4*>(sW + c * 8 + 4 * qq), w1 = *reinterpret_cast<const float4*>(sW + c * 8 + 4 * qq + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(sB + c * 8 + 4 * qq), b1 = *reinterpret_cast<const float4*>(sB + c * 8 + 4 * qq + 4);
     const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
     const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
@@ -537,6 +539,8 @@ __device__ __forceinline__ void rows8_ln(uint8_t* sX, int nrows, int D, int w, i
     *cp = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
   }
 }
+// shared-memory index of LN parameter i (of D) in the padded layout rows8_ln reads: 4 floats of padding per column quarter
+__device__ __forceinline__ int ln_pad_index(int i, int D) { return i + 4 * (i / (D >> 2)); }
 // n_groups consecutive 8-row groups starting at group w0 (1 for each of the 16 epilogue warps on a CTA's first tile, 4 for
 // each of the 4 prologue warps afterwards): every copy in flight first, then the LayerNorm passes.  One implementation for
 // both callers keeps the kernels' code small (each kernel's code is fetched cold at every launch of a layer's chain).

@@ -128,13 +128,12 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
     tc::fence_barrier_init();
   }
   for (int i = tid; i < p.F; i += F3_THREADS) sPar[i] = p.b1[i];
-  float* sB2 = sPar + p.F; float* sOw = sB2 + 256; float* sOb = sOw + 256; float* sLw = sOb + 256; float* sLb = sLw + 256;
+  float* sB2 = sPar + p.F; float* sOw = sB2 + 256; float* sOb = sOw + 256; float* sLw = sOb + 256; float* sLb = sLw + 272;
   for (int i = tid; i < 256; i += F3_THREADS) {
     sB2[i] = i < D ? p.b2[i] : 0.0f;
     sOw[i] = (OLN && i < D) ? p.oln_w[i] : 1.0f;
     sOb[i] = (OLN && i < D) ? p.oln_b[i] : 0.0f;
-    sLw[i] = i < D ? p.ln_w[i] : 1.0f;
-    sLb[i] = i < D ? p.ln_b[i] : 0.0f;
+    if (i < D) { sLw[tc::ln_pad_index(i, D)] = p.ln_w[i]; sLb[tc::ln_pad_index(i, D)] = p.ln_b[i]; }  // padded layout
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -600,7 +599,7 @@ int tc_ffn3_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t r
   p.trace = g_trace3f;
   p.off_ring = (uint32_t)nc * kblock_bytes(128);
   p.off_par = p.off_ring + F3_RING_BYTES;
-  p.off_red = p.off_par + (uint32_t)align_up((size_t)(F + 1280) * 4, 1024);
+  p.off_red = p.off_par + (uint32_t)align_up((size_t)(F + 1280 + 32) * 4, 1024);
   const size_t smem = (size_t)p.off_red + 4096;
   if (smem > 227 * 1024 - 1024) return fail(SMX_ERR_UNSUPPORTED, "ffn: tile does not fit shared memory");
   // CTA pairs when the weight steps split evenly over two CTAs (D a multiple of 128) and there is more than one tile
