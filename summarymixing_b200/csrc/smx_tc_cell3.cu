@@ -132,7 +132,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
   uint8_t* sX = smem;
   uint8_t* sRing = smem + p.off_ring;
   float* sPar = reinterpret_cast<float*>(smem + p.off_par);   // [b1 | b2 | ln_w | ln_b | c[b] | norm1 w | norm1 b], 256 floats each
-  float* sRed = reinterpret_cast<float*>(smem + p.off_red);   // 1024 floats: column partials / LayerNorm statistics
+  float* sRed = reinterpret_cast<float*>(smem + p.off_red);   // 1536 floats: column partials / LayerNorm statistics
+  float2* sStat = reinterpret_cast<float2*>(smem + p.off_red + 6144);  // per-row (1/std, -mean/std) of the prologue LayerNorm
   __shared__ __align__(8) uint64_t full_bar[C3_MAX_SLOTS], empty_bar[C3_MAX_SLOTS];
   __shared__ __align__(8) uint64_t x_full, x_free, x_copied, acc_full[3], op_full[2], epi_done;
   __shared__ uint32_t tmem_base_s;
@@ -198,7 +199,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
           for (int st = 0; st < g.n_steps; ++st) {
             const int nu = g.n_units - st * ups < ups ? g.n_units - st * ups : ups;
             const uint32_t bytes = (uint32_t)(nu * g.gw) * C3_BLOCK;
-            tc::mbar_wait_spin(&empty_bar[s], ((pe >> s) & 1u) ^ 1u);
+            tc::mbar_wait(&empty_bar[s], ((pe >> s) & 1u) ^ 1u);  // suspending wait: a polling producer floods the SM sub-partition's shared-memory queue
             pe ^= 1u << s;
             tc::mbar_arrive_expect_tx(&full_bar[s], bytes);
             tc::bulk_g2s(sRing + (size_t)s * C3_SLOT, g.img + (size_t)st * C3_SLOT, bytes, &full_bar[s]);
@@ -300,7 +301,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&x_copied);
       } else {
-        tc::stage_ln_rows_wide(sX, p.x, p.ldx, row0, nrows, p.D, pw * 4, 4, lane, p.pre_w != nullptr, sPar + 1280, sPar + 1552);
+        tc::stage_ln_rows_wide(sX, p.x, p.ldx, row0, nrows, p.D, pw * 4, 4, lane, p.pre_w != nullptr, sPar + 1280, sPar + 1552, sStat);
         tc::fence_proxy_async();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&x_full);
@@ -326,13 +327,17 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
       if (warp == 0) C3_TRACE(3, it, 0);
       if (EPI_LN) {  // the tile has been copied into the operand image: LayerNorm in place, 8 rows per warp
         tc::mbar_wait(&x_copied, par);
-        if (p.pre_w) tc::rows8_ln(sX, nrows, p.D, warp, lane, sPar + 1280, sPar + 1552);
+        if (warp == 0) C3_TRACE(3, it, 10);
+        if (p.pre_w) tc::rows8_ln(sX, nrows, p.D, warp, lane, sPar + 1280, sPar + 1552, sStat,
+                                  (p.trace && blockIdx.x == 0 && warp == 0 && it < 4) ? p.trace + ((3 * 4 + it) * 16) + 9 : nullptr);
+        if (warp == 0) C3_TRACE(3, it, 11);
         tc::fence_proxy_async();
+        if (warp == 0) C3_TRACE(3, it, 12);
         tc::named_bar_sync(5, C3_NEW * 32);
         if (warp < C3_NPW && lane == 0) tc::mbar_arrive(&x_full);
         if (warp == 0) C3_TRACE(3, it, 1);
       } else if (it == 0) {  // first tile: all 16 epilogue warps stage and normalise it (8 rows each)
-        tc::stage_ln_rows_wide(sX, p.x, p.ldx, row0, nrows, p.D, warp, 1, lane, p.pre_w != nullptr, sPar + 1280, sPar + 1552);
+        tc::stage_ln_rows_wide(sX, p.x, p.ldx, row0, nrows, p.D, warp, 1, lane, p.pre_w != nullptr, sPar + 1280, sPar + 1552, sStat);
         tc::fence_proxy_async();
         tc::named_bar_sync(5, C3_NEW * 32);
         if (warp < C3_NPW && lane == 0) tc::mbar_arrive(&x_full);
@@ -652,13 +657,13 @@ static int c3_sms() {
 static size_t c3_carve(Cell3P& p, int D) {
   const uint32_t xb = (uint32_t)(D / 64) * kblock_bytes(128);
   p.off_ring = xb;
-  const size_t fixed = (size_t)xb + 8192 /*params*/ + 6144 /*reductions*/ + 1024 /*align*/ + 1024 /*static*/;
+  const size_t fixed = (size_t)xb + 8192 /*params*/ + 7168 /*reductions + row statistics*/ + 1024 /*align*/ + 1024 /*static*/;
   int slots = (int)((227 * 1024 - fixed) / C3_SLOT);
   if (slots > C3_MAX_SLOTS) slots = C3_MAX_SLOTS;
   p.nslots = slots;
   p.off_par = p.off_ring + (uint32_t)slots * C3_SLOT;
   p.off_red = p.off_par + 8192;
-  return (size_t)p.off_red + 6144 + 1024;
+  return (size_t)p.off_red + 7168 + 1024;
 }
 
 template <int PHASE, int ACT>

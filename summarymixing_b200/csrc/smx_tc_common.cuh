@@ -496,48 +496,93 @@ __device__ __forceinline__ void rows8_copy(uint8_t* sX, const __nv_bfloat16* x, 
     }
   }
 }
-__device__ __forceinline__ void rows8_ln(uint8_t* sX, int nrows, int D, int w, int lane, const float* sW, const float* sB) {
+// packed fp32 pairs (Blackwell FFMA2 / FADD2: one issue slot for two independent IEEE operations)
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  unsigned long long d;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)));
+  return *reinterpret_cast<float2*>(&d);
+}
+__device__ __forceinline__ void unpack_bf16x8_pairs(const uint4& raw, float2* v) {
+  const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+  for (int e = 0; e < 4; ++e) v[e] = __bfloat1622float2(h[e]);
+}
+// LayerNorm of rows [8w, 8w + 8) of the staged tile, in place, by one warp.
+//   pass 1 (statistics): lane l owns row 8w + (l & 7) and the column quarter l >> 3; shifted one-pass sums, the four
+//     partials of a row meet through two shuffles; lanes 0..7 publish (1/std, -mean/std) of their row in sStat;
+//   pass 2 (normalise): lane l owns 16-byte chunk l of every row: its eight weights / biases sit in registers for the
+//     whole call, so the pass costs one shared-memory load and one store per row and lane (reading the parameters per
+//     row quarter instead made the shared-memory pipe, not the math, the limit of this phase).
+// Both mappings are conflict-free under the 128-byte swizzle.  sStat: 128 float2 (one per row of the tile).
+__device__ __forceinline__ void rows8_ln(uint8_t* sX, int nrows, int D, int w, int lane, const float* sW, const float* sB, float2* sStat,
+                                         unsigned long long* tr = nullptr) {
   const int nch = D >> 3;
-  const int r = w * 8 + (lane & 7), qq = lane >> 3, cq = nch >> 2;  // chunks per quarter
-  const uint32_t rx = (uint32_t)(r & 7);
-  uint8_t* const rowp = sX + (r >> 3) * 1024 + (r & 7) * 128;
-  float v[8];
-  unpack_bf16x8(*reinterpret_cast<const uint4*>(rowp + (rx << 4)), v);  // chunk 0 of the row: the common shift
-  const float x0 = v[0];
-  float a1[8], a2[8];
+  {
+    const int r = w * 8 + (lane & 7), qq = lane >> 3, cq = nch >> 2;  // chunks per quarter
+    const uint32_t rx = (uint32_t)(r & 7);
+    const uint8_t* const rowp = sX + (r >> 3) * 1024 + (r & 7) * 128;
+    float2 v[4];
+    unpack_bf16x8_pairs(*reinterpret_cast<const uint4*>(rowp + (rx << 4)), v);  // chunk 0 of the row: the common shift
+    const float x0 = v[0].x;
+    const float2 nx0 = make_float2(-x0, -x0);
+    float2 a1[4], a2[4];  // four independent pair-accumulator chains
 #pragma unroll
-  for (int e = 0; e < 8; ++e) { a1[e] = 0.0f; a2[e] = 0.0f; }
+    for (int e = 0; e < 4; ++e) { a1[e] = make_float2(0.0f, 0.0f); a2[e] = make_float2(0.0f, 0.0f); }
 #pragma unroll 2
-  for (int i = 0; i < cq; ++i) {
-    const int c = qq * cq + i;
-    unpack_bf16x8(*reinterpret_cast<const uint4*>(rowp + (size_t)(c >> 3) * kblock_bytes(128) + ((((uint32_t)c & 7u) ^ rx) << 4)), v);
+    for (int i = 0; i < cq; ++i) {
+      const int c = qq * cq + i;
+      unpack_bf16x8_pairs(*reinterpret_cast<const uint4*>(rowp + (size_t)(c >> 3) * kblock_bytes(128) + ((((uint32_t)c & 7u) ^ rx) << 4)), v);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { const float d = v[e] - x0; a1[e] += d; a2[e] = fmaf(d, d, a2[e]); }
+      for (int e = 0; e < 4; ++e) { const float2 d = add2(v[e], nx0); a1[e] = add2(a1[e], d); a2[e] = fma2(d, d, a2[e]); }
+    }
+    const float2 s1p = add2(add2(a1[0], a1[1]), add2(a1[2], a1[3])), s2p = add2(add2(a2[0], a2[1]), add2(a2[2], a2[3]));
+    float s1 = s1p.x + s1p.y, s2 = s2p.x + s2p.y;
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 8); s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
+    s1 += __shfl_xor_sync(0xffffffffu, s1, 16); s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
+    const float invD = 1.0f / (float)D;
+    const float m0 = s1 * invD;
+    // rows past the end of the tile become zero rows: scale and shift vanish (and pass 2 drops the bias)
+    const float rstd = r < nrows ? rsqrtf(fmaxf(s2 * invD - m0 * m0, 0.0f) + 1e-5f) : 0.0f;
+    if (lane < 8) sStat[r] = make_float2(rstd, -(m0 + x0) * rstd);
   }
-  float s1 = ((a1[0] + a1[1]) + (a1[2] + a1[3])) + ((a1[4] + a1[5]) + (a1[6] + a1[7]));
-  float s2 = ((a2[0] + a2[1]) + (a2[2] + a2[3])) + ((a2[4] + a2[5]) + (a2[6] + a2[7]));
-  s1 += __shfl_xor_sync(0xffffffffu, s1, 8); s2 += __shfl_xor_sync(0xffffffffu, s2, 8);
-  s1 += __shfl_xor_sync(0xffffffffu, s1, 16); s2 += __shfl_xor_sync(0xffffffffu, s2, 16);
-  const float invD = 1.0f / (float)D;
-  const float m0 = s1 * invD;
-  const float rstd = rsqrtf(fmaxf(s2 * invD - m0 * m0, 0.0f) + 1e-5f);
-  const float shift = -(m0 + x0) * rstd;
-  const bool live = r < nrows;
-#pragma unroll 2
-  for (int i = 0; i < cq; ++i) {
-    const int c = qq * cq + i;
-    uint4* const cp = reinterpret_cast<uint4*>(rowp + (size_t)(c >> 3) * kblock_bytes(128) + ((((uint32_t)c & 7u) ^ rx) << 4));
-    unpack_bf16x8(*cp, v);
-    // LN parameters in the PADDED layout (ln_pad_index): the four column quarters a warp reads at once sit 16 bytes further
-    // apart than a multiple of 128 bytes, so the four distinct addresses of a load fall into different banks
-    const float4 w0 = *reinterpret_cast<const float4*>(sW + c * 8 + 4 * qq), w1 = *reinterpret_cast<const float4*>(sW + c * 8 + 4 * qq + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(sB + c * 8 + 4 * qq), b1 = *reinterpret_cast<const float4*>(sB + c * 8 + 4 * qq + 4);
-    const float wv[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-    const float bv[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+  __syncwarp();
+  if (tr && lane == 0) *tr = clock64();
+  if (lane < nch) {
+    const int c = lane;
+    const int po = c * 8 + 4 * (c / (nch >> 2));  // padded parameter layout (ln_pad_index)
+    const float4 w0 = *reinterpret_cast<const float4*>(sW + po), w1 = *reinterpret_cast<const float4*>(sW + po + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(sB + po), b1 = *reinterpret_cast<const float4*>(sB + po + 4);
+    const float2 wv[4] = {make_float2(w0.x, w0.y), make_float2(w0.z, w0.w), make_float2(w1.x, w1.y), make_float2(w1.z, w1.w)};
+    const float2 bv[4] = {make_float2(b0.x, b0.y), make_float2(b0.z, b0.w), make_float2(b1.x, b1.y), make_float2(b1.z, b1.w)};
+    const float2 z2 = make_float2(0.0f, 0.0f);
+    uint8_t* const kb = sX + (size_t)(c >> 3) * kblock_bytes(128);
+#pragma unroll 4
+    for (int j = 0; j < 8; ++j) {
+      const int r = w * 8 + j;
+      const float2 st = sStat[r];
+      const float lv = r < nrows ? 1.0f : 0.0f;
+      const float2 rs2 = make_float2(st.x, st.x), sh2 = make_float2(st.y, st.y), lv2 = make_float2(lv, lv);
+      uint4* const cp = reinterpret_cast<uint4*>(kb + (r >> 3) * 1024 + (r & 7) * 128 + ((((uint32_t)c & 7u) ^ (uint32_t)(r & 7)) << 4));
+      float2 v[4];
+      unpack_bf16x8_pairs(*cp, v);
+      uint32_t o[4];
 #pragma unroll
-    for (int e = 0; e < 8; ++e) v[e] = live ? fmaf(fmaf(v[e], rstd, shift), wv[e], bv[e]) : 0.0f;
-    *cp = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      for (int e = 0; e < 4; ++e) {
+        const float2 y = fma2(fma2(v[e], rs2, sh2), wv[e], fma2(bv[e], lv2, z2));  // (x*rstd + shift) * w + b; b -> 0 on dead rows
+        o[e] = pack_bf16x2(y.x, y.y);
+      }
+      *cp = make_uint4(o[0], o[1], o[2], o[3]);
+    }
   }
+  __syncwarp();
 }
 // shared-memory index of LN parameter i (of D) in the padded layout rows8_ln reads: 4 floats of padding per column quarter
 __device__ __forceinline__ int ln_pad_index(int i, int D) { return i + 4 * (i / (D >> 2)); }
@@ -545,7 +590,7 @@ __device__ __forceinline__ int ln_pad_index(int i, int D) { return i + 4 * (i / 
 // each of the 4 prologue warps afterwards): every copy in flight first, then the LayerNorm passes.  One implementation for
 // both callers keeps the kernels' code small (each kernel's code is fetched cold at every launch of a layer's chain).
 static __device__ __noinline__ void stage_ln_rows_wide(uint8_t* sX, const __nv_bfloat16* x, int64_t ldx, int64_t row0, int nrows, int D,
-                                                   int w0, int n_groups, int lane, bool do_ln, const float* sW, const float* sB) {
+                                                   int w0, int n_groups, int lane, bool do_ln, const float* sW, const float* sB, float2* sStat) {
 #pragma unroll 1
   for (int i = 0; i < n_groups; ++i) rows8_copy(sX, x, ldx, row0, nrows, D, w0 + i, lane);
   cp_async_commit();
@@ -553,7 +598,7 @@ static __device__ __noinline__ void stage_ln_rows_wide(uint8_t* sX, const __nv_b
   __syncwarp();
   if (!do_ln) return;
 #pragma unroll 1
-  for (int i = 0; i < n_groups; ++i) rows8_ln(sX, nrows, D, w0 + i, lane, sW, sB);
+  for (int i = 0; i < n_groups; ++i) rows8_ln(sX, nrows, D, w0 + i, lane, sW, sB, sStat);
 }
 
 }  // namespace tc

@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
       uint32_t pe = 0;
       for (int tile = first_tile; tile < p.n_tiles; tile += tile_step)
         for (int st = 0; st < NSTEP; ++st) {
-          tc::mbar_wait_spin(&empty_bar[s], ((pe >> s) & 1u) ^ 1u);
+          tc::mbar_wait(&empty_bar[s], ((pe >> s) & 1u) ^ 1u);  // suspending wait: a polling producer floods the SM sub-partition's shared-memory queue
           pe ^= 1u << s;
           tc::mbar_arrive_expect_tx(&full_bar[s], STEP_BYTES);
           tc::bulk_g2s(sRing + (size_t)s * CV_SLOT, p.w_img + (size_t)st * STEP_BYTES, STEP_BYTES, &full_bar[s]);

@@ -100,6 +100,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
   uint8_t* sRing = smem + p.off_ring;
   float* sPar = reinterpret_cast<float*>(smem + p.off_par);  // [b1 (F) | b2 | oln_w | oln_b | ln_w | ln_b (256 each)]
   float* sRed = reinterpret_cast<float*>(smem + p.off_red);  // [4 column quarters][128 rows][2]: per-thread (mean, M2)
+  float2* sStat = reinterpret_cast<float2*>(smem + p.off_red + 4096);  // per-row (1/std, -mean/std) of the prologue LayerNorm
   __shared__ __align__(8) uint64_t full_bar[F3_STAGES], peer_full[F3_STAGES], empty_bar[F3_STAGES];
   __shared__ __align__(8) uint64_t x_full, x_free, x_copied, acc1_full[2], h_full[2], acc2_full, epi_done;
   __shared__ uint32_t tmem_base_s;
@@ -170,7 +171,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
       const bool tracing = p.trace != nullptr && blockIdx.x == 0;
       auto next_slot = [&](uint32_t bytes) -> uint8_t* {  // wait until the slot is free, arm its full barrier
         const long long c0t = tracing ? clock64() : 0;
-        tc::mbar_wait_spin(&empty_bar[s], ((pe >> s) & 1u) ^ 1u);
+        tc::mbar_wait(&empty_bar[s], ((pe >> s) & 1u) ^ 1u);  // suspending wait: a polling producer floods the SM sub-partition's shared-memory queue
         pe ^= 1u << s;
         if (tracing) tw_empty += clock64() - c0t;
         tc::mbar_arrive_expect_tx(&full_bar[s], bytes);
@@ -367,7 +368,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
       const int nrows = p.rows - row0 < 128 ? (int)(p.rows - row0) : 128;
       // the tile has been copied into the operand image: LayerNorm in place, 8 rows per warp
       tc::mbar_wait(&x_copied, par);
-      tc::rows8_ln(sX, nrows, D, warp, lane, sLw, sLb);
+      tc::rows8_ln(sX, nrows, D, warp, lane, sLw, sLb, sStat);
       tc::fence_proxy_async();
       tc::named_bar_sync(5, F3_NEW * 32);
       if (warp < F3_NPW && lane == 0) arrive_leader(&x_full);
@@ -600,7 +601,7 @@ int tc_ffn3_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t r
   p.off_ring = (uint32_t)nc * kblock_bytes(128);
   p.off_par = p.off_ring + F3_RING_BYTES;
   p.off_red = p.off_par + (uint32_t)align_up((size_t)(F + 1280 + 32) * 4, 1024);
-  const size_t smem = (size_t)p.off_red + 4096;
+  const size_t smem = (size_t)p.off_red + 4096 + 1024;
   if (smem > 227 * 1024 - 1024) return fail(SMX_ERR_UNSUPPORTED, "ffn: tile does not fit shared memory");
   // CTA pairs when the weight steps split evenly over two CTAs (D a multiple of 128) and there is more than one tile
   p.cl2 = (g_ffn_pair && D % 128 == 0 && p.n_tiles >= 2) ? 1 : 0;

@@ -33,4 +33,4 @@ for r in range(5):
         ev = t[r, it]
         if int(ev.max()) == 0:
             continue
-        print(f"  {roles[r]:9s} it{it}: " + " ".join(f"{int(v) - t0:7d}" if int(v) else "      -" for v in ev[:6]))
+        print(f"  {roles[r]:9s} it{it}: " + " ".join(f"{int(v) - t0:7d}" if int(v) else "      -" for v in ev[:13]))
