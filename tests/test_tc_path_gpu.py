@@ -310,3 +310,53 @@ def test_cuda_graph_replay_matches_eager():
             y = gf(xs[i], masks[i])
             torch.cuda.synchronize()
             assert torch.equal(y, eager[i])
+
+
+def test_16_byte_aligned_buffers_take_the_fallback_kernels():
+    """The newest kernels move rows with 256-bit accesses and need 32-byte aligned activations; buffers that are only
+    16-byte aligned (the C ABI's stated minimum) must still give the same answer through the fallbacks: first-generation
+    cell / FFN kernels for an unaligned input, two 128-bit stores in the conv kernel for an unaligned output."""
+    import ctypes as C
+
+    from summarymixing_b200 import _host as H
+
+    torch.manual_seed(81)
+    D, B, T = 256, 5, 333
+    m = S.ConformerEncoderLayer(D, 1024, 4, 31, attention_type="SummaryMixing", local_proj_hid_dim=[D],
+                                local_proj_out_dim=D, summary_hid_dim=[D]).eval().to(DEV)
+    g = torch.Generator().manual_seed(82)
+    x = torch.randn(B, T, D, generator=g).to(torch.bfloat16)
+    lens = torch.randint(50, T + 1, (B,), generator=g)
+    lens[0] = T
+    mask = (torch.arange(T)[None] < lens[:, None])
+    with torch.no_grad():
+        y_ref = m(x.to(DEV), src_key_padding_mask=mask.to(DEV))[0]
+        # (1) the same input at an address that is 16- but not 32-byte aligned
+        flat = torch.empty(B * T * D + 8, dtype=torch.bfloat16, device=DEV)
+        xu = flat[8:].view(B, T, D)
+        xu.copy_(x)
+        assert xu.data_ptr() % 32 == 16 and xu.is_contiguous()
+        y_u = m(xu, src_key_padding_mask=mask.to(DEV))[0]
+    torch.cuda.synchronize()
+    d = float((y_u.float() - y_ref.float()).abs().max())
+    assert d <= 2.5e-2 * max(1.0, float(y_ref.float().abs().max())), d  # different kernel generation on the first FFN: bf16 tolerance
+
+    # (2) the conv module straight through the C ABI with an output pointer that is only 16-byte aligned
+    lib = L.lib()
+    with torch.no_grad():
+        m(x.to(DEV), src_key_padding_mask=mask.to(DEV))  # make sure the weight structs are filled
+    lw = m._wv.struct
+    m8 = mask.to(torch.uint8).to(DEV).contiguous()
+    xd = x.to(DEV).contiguous()
+    nb = max(lib.smx_conv_module_workspace_bytes(C.byref(lw.conv), L.BF16, B, T), 1 << 20)
+    ws = torch.empty(nb, dtype=torch.uint8, device=DEV)
+    st = H.stream_ptr(torch.device(DEV))
+    ya = torch.empty(B * T * D + 8, dtype=torch.bfloat16, device=DEV)
+    yb = torch.empty(B * T * D + 8, dtype=torch.bfloat16, device=DEV)
+    assert ya.data_ptr() % 32 == 0
+    L.check(lib.smx_conv_module_fwd(C.byref(lw.conv), lw.act, L.BF16, B, T, 0, xd.data_ptr(), m8.data_ptr(), xd.data_ptr(),
+                                    ya.data_ptr(), ws.data_ptr(), ws.numel(), st))
+    L.check(lib.smx_conv_module_fwd(C.byref(lw.conv), lw.act, L.BF16, B, T, 0, xd.data_ptr(), m8.data_ptr(), xd.data_ptr(),
+                                    yb.data_ptr() + 16, ws.data_ptr(), ws.numel(), st))
+    torch.cuda.synchronize()
+    assert torch.equal(ya[: B * T * D], yb[8: 8 + B * T * D]), "aligned and unaligned output stores must give identical bytes"
