@@ -418,12 +418,14 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
       if (warp == 0) F3_TRACE(3, it, 10);
       float mean_t = 0.0f, m2_t = 0.0f;
       if (active) {
+        float vbuf[2][16];  // the next piece's tcgen05.ld is in flight while this piece is processed
+        f3_tmem_ld16(t_acc2 + lane_sel + k * 64, vbuf[0]);
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
           const int col = k * 64 + h * 16;
-          float v[16];
-          f3_tmem_ld16(t_acc2 + lane_sel + col, v);
           tc::tmem_ld_wait();
+          if (h + 1 < 4) f3_tmem_ld16(t_acc2 + lane_sel + col + 16, vbuf[(h + 1) & 1]);
+          float* v = vbuf[h & 1];
           const float4* bp = reinterpret_cast<const float4*>(sB2 + col);
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
