@@ -155,9 +155,10 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
   const int ng1 = (nkbD + 1) / 2;
   const uint32_t slot_bytes = CL2 ? 16384u : 32768u;
   const int nslots = (int)(F3_RING_BYTES / slot_bytes);
-  // CTAs walk the hidden chunks in rotated order so that at any moment different SMs ask the L2 for different weight blocks
-  const int rot = (int)((CL2 ? tc::cluster_id_x() : blockIdx.x) % (unsigned)nj);
-  auto chunk_of = [&](int j) { int c = j + rot; return c >= nj ? c - nj : c; };
+  // Every CTA walks the hidden chunks in the same order: a row's result does not depend on which CTA / tile computes it
+  // (bit-exact batch invariance).  A per-CTA rotation of the order, meant to spread L2 requests, measured no gain
+  // (replicating the weight images showed there is no hot-line effect to avoid).
+  auto chunk_of = [&](int j) { return j; };
   // barriers owned by the leader: an arrival from the peer CTA is a remote arrive
   auto arrive_leader = [&](uint64_t* bar) { if (CL2) tc::mbar_arrive_remote(bar, 0); else tc::mbar_arrive(bar); };
 

@@ -360,3 +360,29 @@ def test_16_byte_aligned_buffers_take_the_fallback_kernels():
                                     yb.data_ptr() + 16, ws.data_ptr(), ws.numel(), st))
     torch.cuda.synchronize()
     assert torch.equal(ya[: B * T * D], yb[8: 8 + B * T * D]), "aligned and unaligned output stores must give identical bytes"
+
+
+def test_tensor_core_arm_is_bit_exactly_batch_invariant():
+    """Size-independent property at the bench shape (B=32, T=1000, D=256, bf16 tensor-core arm): the path is per utterance,
+    so permuting the batch, or running a slice of it alone (different tile -> CTA assignment, different tile positions in
+    the flat row space of the FFN kernels), must reproduce the same rows BIT FOR BIT -- the partition that multi-GPU
+    sharding relies on."""
+    torch.manual_seed(91)
+    m = S.ConformerEncoder(2, 256, 1024, 4, 31, attention_type="SummaryMixing", local_proj_hid_dim=[256],
+                           local_proj_out_dim=256, summary_hid_dim=[256]).eval().to(DEV)
+    g = torch.Generator().manual_seed(92)
+    B, T = 32, 1000
+    x = torch.randn(B, T, 256, generator=g).to(torch.bfloat16).to(DEV)
+    lens = torch.randint(500, T + 1, (B,), generator=g)
+    lens[0] = T
+    mask = (torch.arange(T)[None] < lens[:, None]).to(DEV)
+    with torch.no_grad():
+        y = m(x, src_key_padding_mask=mask)[0]
+        perm = torch.randperm(B, generator=g).to(DEV)
+        yp = m(x[perm].contiguous(), src_key_padding_mask=mask[perm].contiguous())[0]
+        ys = m(x[5:18].contiguous(), src_key_padding_mask=mask[5:18].contiguous())[0]
+        y1 = m(x[31:32].contiguous(), src_key_padding_mask=mask[31:32].contiguous())[0]
+    torch.cuda.synchronize()
+    assert torch.equal(yp, y[perm])
+    assert torch.equal(ys, y[5:18])
+    assert torch.equal(y1, y[31:32])
