@@ -220,6 +220,31 @@ SMX_API int smx_summary_mixing_fwd(const smx_cell_weights* w, int dtype, int32_t
                            const uint8_t* padding_mask, const float* sum_mask, const void* residual, void* y,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* Gradient of SummaryMixing.forward with respect to x and every parameter — what torch.autograd computes for
+ * summary_mixing.py:198-253 (mode "SummaryMixing", whole-utterance mean: sum_mask == None), dropout off.
+ * The call is self-contained: it recomputes the forward intermediates from x in fp32 (nothing is saved by
+ * smx_summary_mixing_fwd), then back-propagates dy.  x, dy, dx are (B,T,*) in `dtype`; parameter gradients are fp32
+ * in the parameters' own layouts (dense (out,in) / ParallelLinear (n_split,in/n_split,out/n_split)), OVERWRITTEN,
+ * not accumulated; any gradient pointer may be NULL (not wanted).  dx may be NULL.
+ * Other modes and sum_mask != None: SMX_ERR_UNSUPPORTED. */
+typedef struct {
+  float* dw;
+  float* db;
+} smx_linear_grad;
+typedef struct {
+  smx_linear_grad local[SMX_MAX_BLOCKS];
+  smx_linear_grad summary[SMX_MAX_BLOCKS];
+  smx_linear_grad merge;
+  float* local_norm_dw;
+  float* local_norm_db;
+  float* summary_norm_dw;
+  float* summary_norm_db;
+} smx_cell_grads;
+SMX_API size_t smx_summary_mixing_bwd_workspace_bytes(const smx_cell_weights* w, int dtype, int32_t B, int32_t T);
+SMX_API int smx_summary_mixing_bwd(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x,
+                           const uint8_t* padding_mask, const void* dy, void* dx, const smx_cell_grads* grads,
+                           void* workspace, size_t workspace_bytes, void* stream);
+
 /* ConvolutionModule.forward (Conformer.py:166-340): y = conv_module(x) * mask (+ residual if given).
  * chunk_size > 0 selects Dynamic Chunk Convolution (Conformer.py:197-320). */
 SMX_API size_t smx_conv_module_workspace_bytes(const smx_convmod_weights* w, int dtype, int32_t B, int32_t T);

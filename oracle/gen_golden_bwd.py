@@ -1,0 +1,59 @@
+"""Golden GRADIENTS of the SummaryMixing cell from the UNMODIFIED reference (run in the build container).
+
+    python oracle/gen_golden_bwd.py        # writes tests/golden/bwd/*.npz
+
+For each listed forward fixture (tests/golden/<name>.npz, written by gen_golden.py) the reference module
+(speechbrain/nnet/summary_mixing.py, imported from /root/reference through oracle/sbshim) is rebuilt from the fixture's
+config and state_dict, run in eval mode (dropout off) with autograd on the fixture's input, and back-propagated from a
+seeded dy.  Stored: dy, dx and one gradient per state_dict key.  tests/ compare the oracle's autograd (CPU) and
+smx_summary_mixing_bwd (GPU) against these.  No reference source is copied; test infrastructure only.
+"""
+from __future__ import annotations
+
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(HERE)
+sys.path.insert(0, os.path.join(HERE, "sbshim"))
+sys.path.insert(0, ROOT)
+
+from speechbrain.nnet.activations import Swish  # noqa: E402
+from speechbrain.nnet.summary_mixing import SummaryMixing  # noqa: E402
+from tests import _golden as G  # noqa: E402
+
+ACTS = {"swish": Swish, "gelu": nn.GELU, "relu": nn.ReLU, "leaky_relu": nn.LeakyReLU}
+CASES = ["cell_sm_h4_swish", "cell_sm_h1_gelu", "cell_sm_h4_relu_noln_deep_nomask", "cell_reftest_sm_h4", "cell_sm_h4_gelu"]
+OUT = os.path.join(ROOT, "tests", "golden", "bwd")
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    for i, name in enumerate(CASES):
+        fx = G.Fixture(name)
+        c = fx.cfg
+        sm = SummaryMixing(c["enc_dim"], c["nhead"], c["local_proj_hid_dim"], c["local_proj_out_dim"], c["summary_hid_dim"],
+                           c["summary_out_dim"], activation=ACTS[c["act"]], mode=c["mode"], use_layernorm=c["use_layernorm"])
+        sm.load_state_dict(fx.sd)
+        sm.eval()
+        x = fx.x.clone().requires_grad_(True)
+        y = sm(x, src_padding_mask=fx.mask) if fx.mask is not None else sm(x)
+        assert float((y.detach() - fx.y).abs().max()) < 1e-6, name
+        dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(7000 + i))
+        y.backward(dy)
+        arrays = {"dy": dy.numpy(), "dx": x.grad.numpy()}
+        for k, p in sm.named_parameters():
+            if p.grad is not None:
+                arrays["grad." + k] = p.grad.numpy()
+        arrays["cfg"] = np.frombuffer(json.dumps(dict(forward_fixture=name, torch=torch.__version__)).encode(), dtype=np.uint8)
+        np.savez(os.path.join(OUT, name + ".npz"), **arrays)
+        print(name, "dx max", float(x.grad.abs().max()), "grads", len(arrays) - 3)
+
+
+if __name__ == "__main__":
+    main()

@@ -42,6 +42,15 @@ class CellWeights(C.Structure):
                 ("_pad", C.c_int32)]
 
 
+class LinearGrad(C.Structure):
+    _fields_ = [("dw", fp), ("db", fp)]
+
+
+class CellGrads(C.Structure):
+    _fields_ = [("local", LinearGrad * SMX_MAX_BLOCKS), ("summary", LinearGrad * SMX_MAX_BLOCKS), ("merge", LinearGrad),
+                ("local_norm_dw", fp), ("local_norm_db", fp), ("summary_norm_dw", fp), ("summary_norm_db", fp)]
+
+
 class FFNWeights(C.Structure):
     _fields_ = [("ln_w", fp), ("ln_b", fp), ("w1", Linear), ("w2", Linear), ("packed", fp)]
 
@@ -95,6 +104,9 @@ _PROTOS = {
     "smx_vanilla_nn_fwd": (_i, [C.POINTER(Linear), _i, _i, _i, _i64, _vp, _vp, _vp, _sz, _vp]),
     "smx_summary_mixing_workspace_bytes": (_sz, [C.POINTER(CellWeights), _i, _i, _i, _i]),
     "smx_summary_mixing_fwd": (_i, [C.POINTER(CellWeights), _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "smx_summary_mixing_bwd_workspace_bytes": (_sz, [C.POINTER(CellWeights), _i, _i, _i]),
+    "smx_summary_mixing_bwd": (_i, [C.POINTER(CellWeights), _i, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(CellGrads), _vp, _sz,
+                                    _vp]),
     "smx_conv_module_workspace_bytes": (_sz, [C.POINTER(ConvModWeights), _i, _i, _i]),
     "smx_conv_module_fwd": (_i, [C.POINTER(ConvModWeights), _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "smx_ffn_workspace_bytes": (_sz, [C.POINTER(FFNWeights), _i, _i64]),
@@ -121,7 +133,7 @@ _PROTOS = {
 
 
 ABI_STRUCTS = [Linear, CellWeights, FFNWeights, ConvModWeights, ConformerLayerWeights, ConvBranchWeights,
-               BranchformerLayerWeights]
+               BranchformerLayerWeights, CellGrads]
 
 
 def exported_symbols():

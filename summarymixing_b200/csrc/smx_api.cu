@@ -73,6 +73,7 @@ size_t smx_struct_size(int which) {
     case 4: return sizeof(smx_conformer_layer_weights);
     case 5: return sizeof(smx_convbranch_weights);
     case 6: return sizeof(smx_branchformer_layer_weights);
+    case 7: return sizeof(smx_cell_grads);
     default: return 0;
   }
 }
@@ -169,6 +170,40 @@ int smx_summary_mixing_fwd(const smx_cell_weights* w, int dtype, int32_t B, int3
     return tc_cell_fwd(w, w->packed, B, T, (const __nv_bfloat16*)x, nullptr, nullptr, padding_mask,
                        (const __nv_bfloat16*)residual, (__nv_bfloat16*)y, a, (cudaStream_t)stream);
   return cell_generic(w, B, T, x, dtype, padding_mask, sum_mask, residual, dtype, y, dtype, Dout, a, (cudaStream_t)stream);
+}
+
+// ---- SummaryMixing cell, backward ----------------------------------------------------------------
+static void all_grads_wanted(smx_cell_grads& g) {
+  float* dummy = (float*)(uintptr_t)256;  // sizing only: never dereferenced
+  for (int i = 0; i < SMX_MAX_BLOCKS; ++i) { g.local[i] = {dummy, dummy}; g.summary[i] = {dummy, dummy}; }
+  g.merge = {dummy, dummy};
+  g.local_norm_dw = g.local_norm_db = g.summary_norm_dw = g.summary_norm_db = dummy;
+}
+size_t smx_summary_mixing_bwd_workspace_bytes(const smx_cell_weights* w, int dtype, int32_t B, int32_t T) {
+  if (!w || B <= 0 || T <= 0) return 0;
+  smx_cell_grads g;
+  all_grads_wanted(g);
+  Arena a(nullptr, 0, true);
+  if (cell_bwd_generic(w, B, T, nullptr, dtype, nullptr, nullptr, dtype, (void*)(uintptr_t)256, dtype, &g, a, nullptr) != SMX_OK)
+    return 0;
+  return a.peak;
+}
+int smx_summary_mixing_bwd(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x,
+                           const uint8_t* padding_mask, const void* dy, void* dx, const smx_cell_grads* grads,
+                           void* workspace, size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");
+  if (!grads) return fail(SMX_ERR_BAD_ARG, "grads is NULL");
+  SMX_TRY(check_bt(B, T));
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(dy, "dy"));
+  if (dx) SMX_TRY(check_ptr(dx, "dx"));
+  SMX_TRY(check_arch());
+  Arena dry(nullptr, 0, true);
+  SMX_TRY(cell_bwd_generic(w, B, T, x, dtype, padding_mask, dy, dtype, dx, dtype, grads, dry, nullptr));
+  if (dry.peak > workspace_bytes || (dry.peak && !workspace))
+    return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", dry.peak, workspace_bytes);
+  Arena a(workspace, workspace_bytes, false);
+  return cell_bwd_generic(w, B, T, x, dtype, padding_mask, dy, dtype, dx, dtype, grads, a, (cudaStream_t)stream);
 }
 
 // ---- ConvolutionModule ---------------------------------------------------------------------------

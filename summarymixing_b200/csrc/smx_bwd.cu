@@ -1,0 +1,479 @@
+// libsmx, backward of the SummaryMixing cell (fp32-math arm): what torch.autograd derives from
+// summary_mixing.py:198-253 (mode "SummaryMixing", whole-utterance mean), written out by hand.
+//
+//   forward (recomputed here from x, fp32):
+//     f-branch  a_0 = x;  z_i = lin_i(a_i);  a_{i+1} = act(z_i);  Lm = a_n * mask;  L = LN_l(Lm)            :215-218
+//     s-branch  same blocks of summary_proj;  Sm = a_n * mask;  mean_b = sum_t Sm / sum_t mask;  mu = LN_s(mean)  :221-249
+//     combiner  zc = L Wc[:, :D_l]^T + (mu_b Wc[:, D_l:]^T + b_c);  y = act(zc)                                  :251-253
+//   backward:
+//     dzc = dy * act'(zc);  dWc = [dzc^T L | dcb^T mu] with dcb_b = sum_t dzc[b,t];  db_c = sum dzc
+//     dL = dzc Wc[:, :D_l];  dmu = dcb Wc[:, D_l:];  LayerNorm backward on both;  dSm[b,t] = dmean_b / count_b
+//     MLP backward per branch: dz_i = da_{i+1} * act'(z_i) (* mask on the last block), dW_i = a_i^T dz_i (split-K over
+//     row slices, fixed-order reduction: deterministic), db_i = sum dz_i, da_i = dz_i W_i;  dx = da_0(f) + da_0(s)
+//
+// First-correct implementation on the generic kernels (strided fp32 GEMM of smx_simt.cu + the elementwise / reduction
+// kernels below); not tuned.  Parity: tests/test_backward_gpu.py against torch.autograd of the oracle restatement.
+#include "smx_internal.h"
+#include <math.h>
+
+namespace smx {
+
+namespace {
+
+__device__ __forceinline__ float bw_ld(const void* p, int dt, int64_t i) {
+  return dt == SMX_BF16 ? __bfloat162float(((const __nv_bfloat16*)p)[i]) : ((const float*)p)[i];
+}
+
+__device__ __forceinline__ float bw_act(int act, float x) {
+  switch (act) {
+    case SMX_ACT_SWISH: return x / (1.0f + expf(-x));
+    case SMX_ACT_GELU: return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
+    case SMX_ACT_RELU: return fmaxf(x, 0.0f);
+    case SMX_ACT_LEAKY_RELU: return x >= 0.0f ? x : 0.01f * x;
+    case SMX_ACT_TANH: return tanhf(x);
+    case SMX_ACT_SIGMOID: return 1.0f / (1.0f + expf(-x));
+    case SMX_ACT_GELU_TANH: {
+      float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
+      return 0.5f * x * (1.0f + tanhf(u));
+    }
+    default: return x;
+  }
+}
+
+// d act(x) / dx
+__device__ __forceinline__ float bw_dact(int act, float x) {
+  switch (act) {
+    case SMX_ACT_SWISH: {
+      const float s = 1.0f / (1.0f + expf(-x));
+      return s * (1.0f + x * (1.0f - s));
+    }
+    case SMX_ACT_GELU: {
+      const float cdf = 0.5f * (1.0f + erff(x * 0.70710678118654752440f));
+      const float pdf = 0.3989422804014327f * expf(-0.5f * x * x);
+      return cdf + x * pdf;
+    }
+    case SMX_ACT_RELU: return x > 0.0f ? 1.0f : 0.0f;
+    case SMX_ACT_LEAKY_RELU: return x > 0.0f ? 1.0f : 0.01f;
+    case SMX_ACT_TANH: {
+      const float t = tanhf(x);
+      return 1.0f - t * t;
+    }
+    case SMX_ACT_SIGMOID: {
+      const float s = 1.0f / (1.0f + expf(-x));
+      return s * (1.0f - s);
+    }
+    case SMX_ACT_GELU_TANH: {
+      const float x2 = x * x;
+      const float u = 0.7978845608028654f * (x + 0.044715f * x * x2);
+      const float t = tanhf(u);
+      const float du = 0.7978845608028654f * (1.0f + 3.0f * 0.044715f * x2);
+      return 0.5f * (1.0f + t) + 0.5f * x * (1.0f - t * t) * du;
+    }
+    default: return 1.0f;
+  }
+}
+
+// out = act(z) (* rowmask[row])
+__global__ void __launch_bounds__(256) act_fwd_kernel(const float* z, int64_t n, int ncols, int act, const uint8_t* rowmask,
+                                                      float* out) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    float v = bw_act(act, z[i]);
+    if (rowmask) v *= (float)rowmask[i / ncols];
+    out[i] = v;
+  }
+}
+
+// dz = da * act'(z) (* rowmask[row]);  dz may alias z or da
+__global__ void __launch_bounds__(256) act_bwd_kernel(const float* z, const void* da, int da_dt, int64_t n, int ncols, int act,
+                                                      const uint8_t* rowmask, float* dz) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    float v = bw_ld(da, da_dt, i) * bw_dact(act, z[i]);
+    if (rowmask) v *= (float)rowmask[i / ncols];
+    dz[i] = v;
+  }
+}
+
+// dst[slice*N + n] = sum over the slice's rows of src[row*ld + n]; fixed order
+__global__ void __launch_bounds__(256) colsum_kernel(const float* src, int64_t ld, int64_t rows, int rows_per_slice, int N,
+                                                     float* dst) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x % 32, ry = threadIdx.x / 32;
+  const int n = blockIdx.x * 32 + cx;
+  const int64_t r0 = (int64_t)blockIdx.y * rows_per_slice;
+  const int64_t r1 = r0 + rows_per_slice < rows ? r0 + rows_per_slice : rows;
+  float acc = 0.0f;
+  if (n < N)
+    for (int64_t r = r0 + ry; r < r1; r += 8) acc += src[r * ld + n];
+  red[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && n < N) {
+    float tot = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) tot += red[r][cx];
+    dst[(int64_t)blockIdx.y * N + n] = tot;
+  }
+}
+
+// dst[r*ldd + c] = sum_s P[s][r][c]; fixed order
+__global__ void __launch_bounds__(256) sum_slices_kernel(const float* P, int ns, int nrows, int ncols, float* dst, int64_t ldd) {
+  const int64_t n = (int64_t)nrows * ncols;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    float tot = 0.0f;
+    for (int s = 0; s < ns; ++s) tot += P[(int64_t)s * n + i];
+    dst[(i / ncols) * ldd + (i % ncols)] = tot;
+  }
+}
+
+// LayerNorm backward, one warp per row.  v: the LayerNorm input; g (in): dy, (out): dv;  t (out): dy * xhat (its column
+// sums are the weight gradient; the column sums of dy, taken BEFORE this kernel, are the bias gradient).
+__global__ void __launch_bounds__(256) ln_bwd_kernel(const float* v, int64_t rows, int D, const float* w, float eps, float* g,
+                                                     float* t) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  const float* vr = v + row * D;
+  float* gr = g + row * D;
+  float* tr = t + row * D;
+  float s = 0.0f;
+  for (int c = lane; c < D; c += 32) s += vr[c];
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)D;
+  float q = 0.0f;
+  for (int c = lane; c < D; c += 32) { const float d = vr[c] - mean; q += d * d; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.0f / sqrtf(q / (float)D + eps);
+  float m1 = 0.0f, m2 = 0.0f;
+  for (int c = lane; c < D; c += 32) {
+    const float gw = gr[c] * w[c];
+    m1 += gw;
+    m2 += gw * (vr[c] - mean) * rstd;
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { m1 += __shfl_xor_sync(0xffffffffu, m1, o); m2 += __shfl_xor_sync(0xffffffffu, m2, o); }
+  m1 /= (float)D; m2 /= (float)D;
+  for (int c = lane; c < D; c += 32) {
+    const float xh = (vr[c] - mean) * rstd;
+    const float dy = gr[c];
+    tr[c] = dy * xh;
+    gr[c] = rstd * (dy * w[c] - m1 - xh * m2);
+  }
+}
+
+// inv[b] = 1 / (number of valid frames of utterance b)            summary_mixing.py:229-231
+__global__ void inv_count_kernel(const uint8_t* mask, int T, float* inv) {
+  const int b = blockIdx.x;
+  float c = 0.0f;
+  for (int t = threadIdx.x; t < T; t += 32) c += mask ? (float)mask[(int64_t)b * T + t] : 1.0f;
+#pragma unroll
+  for (int o = 16; o; o >>= 1) c += __shfl_xor_sync(0xffffffffu, c, o);
+  if (threadIdx.x == 0) inv[b] = 1.0f / c;
+}
+
+// dst[(b*T + t)*D + d] = src[b*D + d] * inv[b]   (gradient of the mean, broadcast back over the frames)
+__global__ void __launch_bounds__(256) bcast_scale_kernel(const float* src, const float* inv, int T, int D, int64_t n, float* dst) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const int64_t row = i / D;
+    const int b = (int)(row / T), d = (int)(i % D);
+    dst[i] = src[(int64_t)b * D + d] * inv[b];
+  }
+}
+
+unsigned ew_grid(int64_t n) {
+  int64_t g = (n + 255) / 256;
+  return (unsigned)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+GemmP bw_gemm() {
+  GemmP p{};
+  p.alpha = 1.0f;
+  p.rowbias_div = 1;
+  p.batches = 1;
+  p.act = SMX_ACT_IDENTITY;
+  p.a_dtype = SMX_F32;
+  p.c_dtype = SMX_F32;
+  return p;
+}
+
+// z = A @ L (+ b): pre-activation of one block (dense columns [k_offset, k_offset + K) when K > 0)
+int lin_fwd(const smx_linear& L, const float* A, int64_t lda, int64_t rows, float* C, int64_t ldc, bool use_bias, int k_offset,
+            int K, const float* rowbias, int rowbias_div, cudaStream_t st) {
+  GemmP p = bw_gemm();
+  p.A = A; p.lda = lda; p.C = C; p.ldc = ldc; p.M = (int)rows;
+  p.rowbias = rowbias; p.rowbias_ld = L.out_dim; p.rowbias_div = rowbias_div;
+  if (L.n_split <= 1) {
+    p.K = K > 0 ? K : L.in_dim - k_offset; p.N = L.out_dim;
+    p.W = L.w + k_offset; p.w_sk = 1; p.w_sn = L.in_dim;
+    p.bias = (use_bias && L.b) ? L.b : nullptr;
+  } else {
+    const int h = L.n_split;
+    p.K = L.in_dim / h; p.N = L.out_dim / h; p.batches = h;
+    p.a_bs = p.K; p.c_bs = p.N;
+    p.W = L.w; p.w_sk = p.N; p.w_sn = 1; p.w_bs = (int64_t)p.K * p.N;
+    p.bias = (use_bias && L.b) ? L.b : nullptr; p.bias_bs = p.N;
+  }
+  return gemm(p, st);
+}
+
+// dX = dZ @ W (+ residual), the gradient with respect to the block's input (dense: columns [k_offset, k_offset + K))
+int lin_dgrad(const smx_linear& L, const float* dZ, int64_t ldz, int64_t rows, void* dX, int dx_dt, int64_t ldx, int k_offset, int K,
+              const float* residual, cudaStream_t st) {
+  GemmP p = bw_gemm();
+  p.A = dZ; p.lda = ldz; p.C = dX; p.c_dtype = dx_dt; p.ldc = ldx; p.M = (int)rows;
+  p.residual = residual; p.r_dtype = SMX_F32; p.ldr = ldx;
+  if (L.n_split <= 1) {
+    p.K = L.out_dim; p.N = K > 0 ? K : L.in_dim - k_offset;
+    p.W = L.w + k_offset; p.w_sk = L.in_dim; p.w_sn = 1;
+  } else {
+    const int h = L.n_split, a = L.in_dim / h, b = L.out_dim / h;
+    p.K = b; p.N = a; p.batches = h;
+    p.a_bs = b; p.c_bs = a;
+    p.W = L.w; p.w_sk = 1; p.w_sn = b; p.w_bs = (int64_t)a * b;
+  }
+  return gemm(p, st);
+}
+
+int sum_slices(const float* P, int ns, int nrows, int ncols, float* dst, int64_t ldd, cudaStream_t st) {
+  sum_slices_kernel<<<ew_grid((int64_t)nrows * ncols), 256, 0, st>>>(P, ns, nrows, ncols, dst, ldd);
+  count_launch();
+  return check_launch("sum_slices_kernel");
+}
+
+void slice_plan(int64_t rows, int& chunk, int& ns) {
+  int64_t want = (rows + 255) / 256;
+  if (want > 64) want = 64;
+  if (want < 1) want = 1;
+  chunk = (int)((rows + want - 1) / want);
+  ns = (int)((rows + chunk - 1) / chunk);
+}
+
+// dW = X^T dZ in the parameter's own layout; split-K over row slices, then a fixed-order reduction.
+int lin_wgrad(const smx_linear& L, const float* dZ, int64_t ldz, const float* X, int64_t ldx, int64_t rows, float* dW, int k_offset,
+              int K, Arena& ws, cudaStream_t st) {
+  int chunk, ns;
+  slice_plan(rows, chunk, ns);
+  const size_t m0 = ws.mark();
+  if (L.n_split <= 1) {
+    const int Kin = K > 0 ? K : L.in_dim - k_offset;
+    float* P = ws.f32((size_t)ns * L.out_dim * Kin);
+    if (!P) return fail(SMX_ERR_WORKSPACE, "workspace too small (weight gradient)");
+    if (!ws.dry) {
+      GemmP p = bw_gemm();  // C[o][i] = sum_m dZ[m,o] X[m,i]
+      p.A = dZ; p.lda = 1; p.a_sk = ldz; p.a_bs = (int64_t)chunk * ldz;
+      p.W = X; p.w_sk = ldx; p.w_sn = 1; p.w_bs = (int64_t)chunk * ldx;
+      p.C = P; p.ldc = Kin; p.c_bs = (int64_t)L.out_dim * Kin;
+      p.M = L.out_dim; p.N = Kin; p.K = chunk; p.k_total = (int)rows; p.batches = ns;
+      SMX_TRY(gemm(p, st));
+      SMX_TRY(sum_slices(P, ns, L.out_dim, Kin, dW + k_offset, L.in_dim, st));
+    }
+  } else {
+    const int h = L.n_split, a = L.in_dim / h, b = L.out_dim / h;
+    float* P = ws.f32((size_t)ns * a * b);
+    if (!P) return fail(SMX_ERR_WORKSPACE, "workspace too small (weight gradient)");
+    if (!ws.dry) {
+      for (int hh = 0; hh < h; ++hh) {  // C[i][o] = sum_m X[m, hh*a + i] dZ[m, hh*b + o]
+        GemmP p = bw_gemm();
+        p.A = X + (int64_t)hh * a; p.lda = 1; p.a_sk = ldx; p.a_bs = (int64_t)chunk * ldx;
+        p.W = dZ + (int64_t)hh * b; p.w_sk = ldz; p.w_sn = 1; p.w_bs = (int64_t)chunk * ldz;
+        p.C = P; p.ldc = b; p.c_bs = (int64_t)a * b;
+        p.M = a; p.N = b; p.K = chunk; p.k_total = (int)rows; p.batches = ns;
+        SMX_TRY(gemm(p, st));
+        SMX_TRY(sum_slices(P, ns, a, b, dW + (int64_t)hh * a * b, b, st));
+      }
+    }
+  }
+  ws.release(m0);
+  return SMX_OK;
+}
+
+// dst[n] = sum over all rows of src[row*ld + n]
+int colsum_all(const float* src, int64_t ld, int64_t rows, int N, float* dst, Arena& ws, cudaStream_t st) {
+  const int rps = 512;
+  const int ns = (int)((rows + rps - 1) / rps);
+  const size_t m0 = ws.mark();
+  float* P = ws.f32((size_t)ns * N);
+  if (!P) return fail(SMX_ERR_WORKSPACE, "workspace too small (column sums)");
+  if (!ws.dry) {
+    colsum_kernel<<<dim3((N + 31) / 32, ns), 256, 0, st>>>(src, ld, rows, rps, N, P);
+    count_launch();
+    SMX_TRY(check_launch("colsum_kernel"));
+    SMX_TRY(sum_slices(P, ns, 1, N, dst, N, st));
+  }
+  ws.release(m0);
+  return SMX_OK;
+}
+
+int act_fwd(const float* z, int64_t rows, int ncols, int act, const uint8_t* rowmask, float* out, cudaStream_t st) {
+  act_fwd_kernel<<<ew_grid(rows * ncols), 256, 0, st>>>(z, rows * ncols, ncols, act, rowmask, out);
+  count_launch();
+  return check_launch("act_fwd_kernel");
+}
+int act_bwd(const float* z, const void* da, int da_dt, int64_t rows, int ncols, int act, const uint8_t* rowmask, float* dz,
+            cudaStream_t st) {
+  act_bwd_kernel<<<ew_grid(rows * ncols), 256, 0, st>>>(z, da, da_dt, rows * ncols, ncols, act, rowmask, dz);
+  count_launch();
+  return check_launch("act_bwd_kernel");
+}
+
+// LayerNorm backward over `rows` rows: g (dy -> dv, in place), parameter gradients into dw / db (either may be NULL)
+int ln_bwd(const float* v, int64_t rows, int D, const float* w, float* g, float* dw, float* db, Arena& ws, cudaStream_t st) {
+  const size_t m0 = ws.mark();
+  float* t = ws.f32((size_t)rows * D);
+  if (!t) return fail(SMX_ERR_WORKSPACE, "workspace too small (LayerNorm backward)");
+  if (db) SMX_TRY(colsum_all(g, D, rows, D, db, ws, st));  // before g is overwritten
+  if (!ws.dry) {
+    ln_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(v, rows, D, w, 1e-5f, g, t);
+    count_launch();
+    SMX_TRY(check_launch("ln_bwd_kernel"));
+  }
+  if (dw) SMX_TRY(colsum_all(t, D, rows, D, dw, ws, st));
+  ws.release(m0);
+  return SMX_OK;
+}
+
+struct BranchFwd {
+  float* z[SMX_MAX_BLOCKS];      // pre-activations
+  const float* a[SMX_MAX_BLOCKS + 1];  // block inputs; a[n] = act(z[n-1]) * mask
+};
+
+int branch_fwd(const smx_linear* blocks, int n, int act, const float* x32, int64_t rows, const uint8_t* mask, BranchFwd& f, Arena& ws,
+               cudaStream_t st) {
+  f.a[0] = x32;
+  for (int i = 0; i < n; ++i) {
+    if (i > 0 && blocks[i].in_dim != blocks[i - 1].out_dim) return fail(SMX_ERR_BAD_ARG, "VanillaNN block %d: inconsistent dims", i);
+    const int N = blocks[i].out_dim;
+    f.z[i] = ws.f32((size_t)rows * N);
+    float* an = ws.f32((size_t)rows * N);
+    if (!f.z[i] || !an) return fail(SMX_ERR_WORKSPACE, "workspace too small (cell backward, forward recomputation)");
+    if (!ws.dry) {
+      SMX_TRY(lin_fwd(blocks[i], f.a[i], blocks[i].in_dim, rows, f.z[i], N, true, 0, 0, nullptr, 1, st));
+      SMX_TRY(act_fwd(f.z[i], rows, N, act, i == n - 1 ? mask : nullptr, an, st));
+    }
+    f.a[i + 1] = an;
+  }
+  return SMX_OK;
+}
+
+// da_n (rows, out_{n-1}; overwritten) -> parameter gradients, and the gradient with respect to x: dx_out = dX (+ dx_add)
+int branch_bwd(const smx_linear* blocks, const smx_linear_grad* g, int n, int act, const BranchFwd& f, int64_t rows, const uint8_t* mask,
+               float* da, void* dx_out, int dx_dt, const float* dx_add, bool want_dx, Arena& ws, cudaStream_t st) {
+  float* cur = da;
+  for (int i = n - 1; i >= 0; --i) {
+    const smx_linear& L = blocks[i];
+    if (!ws.dry) SMX_TRY(act_bwd(f.z[i], cur, SMX_F32, rows, L.out_dim, act, i == n - 1 ? mask : nullptr, cur, st));
+    if (g[i].dw) SMX_TRY(lin_wgrad(L, cur, L.out_dim, f.a[i], L.in_dim, rows, g[i].dw, 0, 0, ws, st));
+    if (g[i].db) SMX_TRY(colsum_all(cur, L.out_dim, rows, L.out_dim, g[i].db, ws, st));
+    if (i > 0) {
+      float* prev = ws.f32((size_t)rows * L.in_dim);
+      if (!prev) return fail(SMX_ERR_WORKSPACE, "workspace too small (cell backward)");
+      if (!ws.dry) SMX_TRY(lin_dgrad(L, cur, L.out_dim, rows, prev, SMX_F32, L.in_dim, 0, 0, nullptr, st));
+      cur = prev;
+    } else if (want_dx) {
+      if (!ws.dry) SMX_TRY(lin_dgrad(L, cur, L.out_dim, rows, dx_out, dx_dt, L.in_dim, 0, 0, dx_add, st));
+    }
+  }
+  return SMX_OK;
+}
+
+}  // namespace
+
+int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int x_dt, const uint8_t* mask, const void* dy, int dy_dt,
+                     void* dx, int dx_dt, const smx_cell_grads* g, Arena& ws, cudaStream_t st) {
+  if (w->mode != SMX_MODE_FULL)
+    return fail(SMX_ERR_UNSUPPORTED, "smx_summary_mixing_bwd handles mode 'SummaryMixing' only (got mode %d)", w->mode);
+  const int64_t rows = (int64_t)B * T;
+  if (rows > 0x7fffffff) return fail(SMX_ERR_UNSUPPORTED, "cell backward: more than 2^31 frames");
+  const int D = w->enc_dim, Dl = w->local_out_dim, Ds = w->summary_out_dim, Dout = w->merge.out_dim;
+  const int nl = w->n_local, nsm = w->n_summary, act = w->act;
+  if (nl < 1 || nl > SMX_MAX_BLOCKS || nsm < 1 || nsm > SMX_MAX_BLOCKS) return fail(SMX_ERR_BAD_ARG, "cell backward: block counts");
+  if (w->local[0].in_dim != D || w->summary[0].in_dim != D || w->local[nl - 1].out_dim != Dl || w->summary[nsm - 1].out_dim != Ds)
+    return fail(SMX_ERR_BAD_ARG, "cell backward: projection dims do not match enc_dim / local_out_dim / summary_out_dim");
+  if (w->merge.in_dim != Dl + Ds || w->merge.n_split > 1)
+    return fail(SMX_ERR_BAD_ARG, "summary_local_merging must be dense with in_dim == D_l + D_s");
+  const bool use_ln = w->use_layernorm != 0;
+  if (use_ln && (!w->local_norm_w || !w->local_norm_b || !w->summary_norm_w || !w->summary_norm_b))
+    return fail(SMX_ERR_BAD_ARG, "cell backward: use_layernorm without LayerNorm parameters");
+  const size_t m0 = ws.mark();
+#define BW_RUN(expr) do { if (!ws.dry) SMX_TRY(expr); } while (0)
+#define BW_BUF(name, n) float* name = ws.f32((size_t)(n)); if (!name) return fail(SMX_ERR_WORKSPACE, "workspace too small (cell backward)")
+
+  // ---- forward recomputation ----
+  const float* x32 = (const float*)x;
+  if (x_dt != SMX_F32) {
+    BW_BUF(xc, rows * D);
+    BW_RUN(convert(x, x_dt, xc, SMX_F32, rows * D, st));
+    x32 = xc;
+  }
+  BranchFwd ff{}, fs{};
+  SMX_TRY(branch_fwd(w->local, nl, act, x32, rows, mask, ff, ws, st));
+  SMX_TRY(branch_fwd(w->summary, nsm, act, x32, rows, mask, fs, ws, st));
+  const float* Lm = ff.a[nl];
+  const float* Sm = fs.a[nsm];
+  const float* Lmat = Lm;
+  if (use_ln) {
+    BW_BUF(Lb, rows * Dl);
+    BW_RUN(layernorm(Lm, SMX_F32, Dl, w->local_norm_w, w->local_norm_b, 1e-5f, SMX_ACT_IDENTITY, Lb, SMX_F32, Dl, rows, Dl, st));
+    Lmat = Lb;
+  }
+  BW_BUF(mean, (size_t)B * Ds);
+  BW_RUN(masked_mean(Sm, Ds, mask, B, T, Ds, mean, SMX_F32, st));
+  const float* mu = mean;
+  if (use_ln) {
+    BW_BUF(mub, (size_t)B * Ds);
+    BW_RUN(layernorm(mean, SMX_F32, Ds, w->summary_norm_w, w->summary_norm_b, 1e-5f, SMX_ACT_IDENTITY, mub, SMX_F32, Ds, B, Ds, st));
+    mu = mub;
+  }
+  BW_BUF(cbias, (size_t)B * Dout);
+  BW_RUN(lin_fwd(w->merge, mu, Ds, B, cbias, Dout, true, Dl, Ds, nullptr, 1, st));
+  BW_BUF(zc, rows * Dout);
+  BW_RUN(lin_fwd(w->merge, Lmat, Dl, rows, zc, Dout, false, 0, Dl, cbias, T, st));
+
+  // ---- combiner ----
+  float* dzc = zc;
+  BW_RUN(act_bwd(zc, dy, dy_dt, rows, Dout, act, nullptr, dzc, st));
+  BW_BUF(dcb, (size_t)B * Dout);
+  if (!ws.dry) {  // per-utterance column sums
+    colsum_kernel<<<dim3((Dout + 31) / 32, B), 256, 0, st>>>(dzc, Dout, rows, T, Dout, dcb);
+    count_launch();
+    SMX_TRY(check_launch("colsum_kernel"));
+  }
+  if (g->merge.dw) {
+    SMX_TRY(lin_wgrad(w->merge, dzc, Dout, Lmat, Dl, rows, g->merge.dw, 0, Dl, ws, st));
+    SMX_TRY(lin_wgrad(w->merge, dcb, Dout, mu, Ds, B, g->merge.dw, Dl, Ds, ws, st));
+  }
+  if (g->merge.db) SMX_TRY(colsum_all(dcb, Dout, B, Dout, g->merge.db, ws, st));
+  BW_BUF(dL, rows * Dl);
+  BW_RUN(lin_dgrad(w->merge, dzc, Dout, rows, dL, SMX_F32, Dl, 0, Dl, nullptr, st));
+  BW_BUF(dmu, (size_t)B * Ds);
+  BW_RUN(lin_dgrad(w->merge, dcb, Dout, B, dmu, SMX_F32, Ds, Dl, Ds, nullptr, st));
+
+  // ---- summary branch: LN_s, mean, MLP ----
+  if (use_ln) SMX_TRY(ln_bwd(mean, B, Ds, w->summary_norm_w, dmu, g->summary_norm_dw, g->summary_norm_db, ws, st));
+  BW_BUF(inv, (size_t)B);
+  BW_BUF(dS, rows * Ds);
+  if (!ws.dry) {
+    inv_count_kernel<<<B, 32, 0, st>>>(mask, T, inv);
+    count_launch();
+    SMX_TRY(check_launch("inv_count_kernel"));
+    bcast_scale_kernel<<<ew_grid(rows * Ds), 256, 0, st>>>(dmu, inv, T, Ds, rows * Ds, dS);
+    count_launch();
+    SMX_TRY(check_launch("bcast_scale_kernel"));
+  }
+  float* dxs = nullptr;
+  if (dx) {
+    dxs = ws.f32((size_t)rows * D);
+    if (!dxs) return fail(SMX_ERR_WORKSPACE, "workspace too small (cell backward)");
+  }
+  SMX_TRY(branch_bwd(w->summary, g->summary, nsm, act, fs, rows, mask, dS, dxs, SMX_F32, nullptr, dx != nullptr, ws, st));
+
+  // ---- local branch: LN_l, MLP; dx = dx(local) + dx(summary) ----
+  if (use_ln) SMX_TRY(ln_bwd(Lm, rows, Dl, w->local_norm_w, dL, g->local_norm_dw, g->local_norm_db, ws, st));
+  SMX_TRY(branch_bwd(w->local, g->local, nl, act, ff, rows, mask, dL, dx, dx_dt, dxs, dx != nullptr, ws, st));
+#undef BW_RUN
+#undef BW_BUF
+  ws.release(m0);
+  return SMX_OK;
+}
+
+}  // namespace smx

@@ -47,7 +47,9 @@ inline size_t elem_size(int dtype) { return dtype == SMX_BF16 ? 2 : 4; }
 
 // ---- generic (fp32 math) kernels: smx_simt.cu -------------------------------------------
 struct GemmP {
-  const void* A;  int a_dtype;  int64_t lda;  int64_t a_bs;     // A[m*lda + k] (+ batch*a_bs)
+  const void* A;  int a_dtype;  int64_t lda;  int64_t a_bs;     // A[m*lda + k*a_sk] (+ batch*a_bs)
+  int64_t a_sk;                                                  // k stride of A (0 means 1); != 1: A is read transposed
+  int k_total;                                                   // > 0: split-K over batches, batch i covers k in [i*K, min((i+1)*K, k_total))
   const float* W;  int64_t w_sk;  int64_t w_sn;  int64_t w_bs;  // W[k*w_sk + n*w_sn] (+ batch*w_bs)
   const float* bias;  int64_t bias_bs;                           // bias[n] (+ batch*bias_bs)
   const float* rowbias;  int64_t rowbias_ld;  int32_t rowbias_div;  // + rowbias[(m/div)*ld + n]
@@ -80,6 +82,9 @@ int vanilla_generic(const smx_linear* blocks, int n, int act, const void* x, int
 int cell_generic(const smx_cell_weights* w, int B, int T, const void* x, int x_dt, const uint8_t* mask,
                  const float* sum_mask, const void* residual, int r_dt, void* y, int y_dt, int64_t ldy, Arena& ws,
                  cudaStream_t st);
+// backward of the cell, mode "SummaryMixing" (smx_bwd.cu); recomputes the forward intermediates from x
+int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int x_dt, const uint8_t* mask, const void* dy, int dy_dt,
+                     void* dx, int dx_dt, const smx_cell_grads* g, Arena& ws, cudaStream_t st);
 int ffn_generic(const smx_ffn_weights* w, int act, int64_t rows, const void* x, int x_dt, const float* oln_w,
                 const float* oln_b, float oln_eps, void* y, int y_dt, Arena& ws, cudaStream_t st);
 int convmod_generic(const smx_convmod_weights* w, int act, int B, int T, int chunk, const void* x, int x_dt,

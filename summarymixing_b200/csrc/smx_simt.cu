@@ -45,24 +45,28 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
   const int tx = tid % 16, ty = tid / 16;
   const int64_t a_off = (int64_t)batch * p.a_bs;
   const float* W = p.W + (int64_t)batch * p.w_bs;
+  const int64_t ask = p.a_sk ? p.a_sk : 1;
+  int K = p.K;
+  if (p.k_total > 0) { const int rem = p.k_total - batch * p.K; K = rem < p.K ? rem : p.K; }
   float acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
-  for (int k0 = 0; k0 < p.K; k0 += BK) {
+  for (int k0 = 0; k0 < K; k0 += BK) {
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       int idx = tid + e * 256;  // 0..1023
-      int kk = idx % BK, mm = idx / BK;
+      int kk, mm;  // the faster-varying index follows the unit stride of A
+      if (ask == 1) { kk = idx % BK; mm = idx / BK; } else { mm = idx % BM; kk = idx / BM; }
       int m = m0 + mm, k = k0 + kk;
-      As[kk][mm] = (m < p.M && k < p.K) ? ld_any(p.A, p.a_dtype, a_off + (int64_t)m * p.lda + k) : 0.0f;
+      As[kk][mm] = (m < p.M && k < K) ? ld_any(p.A, p.a_dtype, a_off + (int64_t)m * p.lda + (int64_t)k * ask) : 0.0f;
       // W: choose the faster-varying index according to the strides so that loads coalesce
       int kk2, nn2;
       if (p.w_sn == 1) { nn2 = idx % BN; kk2 = idx / BN; } else { kk2 = idx % BK; nn2 = idx / BK; }
       int n = n0 + nn2, k2 = k0 + kk2;
-      Ws[kk2][nn2] = (n < p.N && k2 < p.K) ? W[(int64_t)k2 * p.w_sk + (int64_t)n * p.w_sn] : 0.0f;
+      Ws[kk2][nn2] = (n < p.N && k2 < K) ? W[(int64_t)k2 * p.w_sk + (int64_t)n * p.w_sn] : 0.0f;
     }
     __syncthreads();
 #pragma unroll

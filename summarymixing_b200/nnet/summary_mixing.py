@@ -9,6 +9,8 @@ from __future__ import annotations
 
 from typing import Optional
 
+import ctypes as C
+
 import numpy as np
 import torch
 import torch.nn as nn
@@ -152,30 +154,107 @@ class SummaryMixing(nn.Module):
 
     def forward(self, x, sum_mask=None, src_padding_mask=None):
         """x: (B,T,enc_dim); sum_mask: (T,T) or None; src_padding_mask: (B,T), 1/True = valid frame.
-        Returns (B,T,summary_out_dim) in x's dtype (lite: a stride-0 expand over T, as the reference, :322)."""
+        Returns (B,T,summary_out_dim) in x's dtype (lite: a stride-0 expand over T, as the reference, :322).
+
+        Differentiable (smx_summary_mixing_bwd) for mode "SummaryMixing" without sum_mask when x requires grad, or in
+        training mode with global_dropout == 0; everything else is the inference path."""
         H.require_cuda(x, "SummaryMixing")
-        H.check_grad_mode(self)
         if x.dim() != 3 or x.shape[-1] != self.enc_dim:
             raise RuntimeError(f"SummaryMixing expects (B,T,{self.enc_dim}), got {tuple(x.shape)}")
         B, T, _ = x.shape
         dev = x.device
-        xc = x.contiguous()
         mask = H.mask_u8(src_padding_mask, B, T, dev)
         smask = H.sum_mask_f32(sum_mask, T, dev)
+        if torch.is_grad_enabled() and (x.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
+            if self.mode != "SummaryMixing" or smask is not None:
+                raise NotImplementedError(
+                    "summarymixing_b200: backward is implemented for mode 'SummaryMixing' without sum_mask only; "
+                    "wrap other configurations in torch.no_grad()")
+            if self.training and self.dropout.p > 0:
+                raise NotImplementedError(
+                    "summarymixing_b200: training-mode dropout is not implemented (set global_dropout=0 or call .eval())")
+            return _CellFunction.apply(self, x, mask, *self.grad_params())
+        H.check_grad_mode(self)
+        return self._forward_impl(x, mask, smask)
+
+    def grad_params(self):
+        """Parameters in the order smx_cell_grads lists their gradients (mode "SummaryMixing")."""
+        out = self.local_proj.params() + self.summary_proj.params() + self.summary_local_merging.params()
+        if self.use_layernorm:
+            out += [self.local_norm.weight, self.local_norm.bias, self.summary_norm.weight, self.summary_norm.bias]
+        return out
+
+    def _weights(self, dev):
         if self._wv.stale(self.params(), dev):
             cw = L.CellWeights()
             self.fill(cw, self._wv, dev)
             self._wv.struct = cw
+        return self._wv.struct
+
+    def _forward_impl(self, x, mask, smask):
+        B, T, _ = x.shape
+        dev = x.device
+        xc = x.contiguous()
+        cw = self._weights(dev)
         lite = self.mode == "SummaryMixing-lite"
         y = torch.empty((B, self.summary_out_dim) if lite else (B, T, self.summary_out_dim), dtype=x.dtype, device=dev)
         lib = L.lib()
         dt = H.dtype_code(xc)
         with torch.cuda.device(dev):
-            nbytes = lib.smx_summary_mixing_workspace_bytes(self._wv.struct, dt, B, T, int(smask is not None))
+            nbytes = lib.smx_summary_mixing_workspace_bytes(cw, dt, B, T, int(smask is not None))
             ws = H.workspace(dev, nbytes)
-            L.check(lib.smx_summary_mixing_fwd(self._wv.struct, dt, B, T, xc.data_ptr(), H.p_or_none(mask),
+            L.check(lib.smx_summary_mixing_fwd(cw, dt, B, T, xc.data_ptr(), H.p_or_none(mask),
                                                H.p_or_none(smask), None, y.data_ptr(), ws.data_ptr(), ws.numel(),
                                                H.stream_ptr(dev)))
         if lite:
             return y.unsqueeze(1).expand(-1, T, -1)
         return y
+
+    def _backward_impl(self, x, mask, dy, want_dx):
+        """(dx or None, [fp32 gradient per grad_params() entry]) through smx_summary_mixing_bwd."""
+        B, T, _ = x.shape
+        dev = x.device
+        xc, dyc = x.contiguous(), dy.contiguous()
+        cw = self._weights(dev)
+        plist = self.grad_params()
+        grads = [torch.empty(p.shape, dtype=torch.float32, device=dev) for p in plist]
+        cg = L.CellGrads()
+        it = iter(grads)
+        for dst, net in ((cg.local, self.local_proj), (cg.summary, self.summary_proj)):
+            for i in range(len(net._linears)):
+                dst[i].dw = next(it).data_ptr()
+                dst[i].db = next(it).data_ptr()
+        cg.merge.dw = next(it).data_ptr()
+        cg.merge.db = next(it).data_ptr()
+        if self.use_layernorm:
+            cg.local_norm_dw, cg.local_norm_db = next(it).data_ptr(), next(it).data_ptr()
+            cg.summary_norm_dw, cg.summary_norm_db = next(it).data_ptr(), next(it).data_ptr()
+        dx = torch.empty_like(xc) if want_dx else None
+        lib = L.lib()
+        dt = H.dtype_code(xc)
+        with torch.cuda.device(dev):
+            nbytes = lib.smx_summary_mixing_bwd_workspace_bytes(cw, dt, B, T)
+            ws = H.workspace(dev, nbytes)
+            L.check(lib.smx_summary_mixing_bwd(cw, dt, B, T, xc.data_ptr(), H.p_or_none(mask), dyc.data_ptr(),
+                                               H.p_or_none(dx), C.byref(cg), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+        return dx, grads
+
+
+class _CellFunction(torch.autograd.Function):
+    """autograd node of the cell: forward = smx_summary_mixing_fwd, backward = smx_summary_mixing_bwd (which recomputes
+    the intermediates from x, so only x and the mask are kept)."""
+
+    @staticmethod
+    def forward(ctx, module, x, mask, *params):
+        ctx.module = module
+        ctx.save_for_backward(x, mask)
+        return module._forward_impl(x, mask, None)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, mask = ctx.saved_tensors
+        module = ctx.module
+        dx, grads = module._backward_impl(x, mask, dy, ctx.needs_input_grad[1])
+        plist = module.grad_params()
+        out = [g.to(p.dtype) if ctx.needs_input_grad[3 + i] else None for i, (g, p) in enumerate(zip(grads, plist))]
+        return (None, dx, None, *out)

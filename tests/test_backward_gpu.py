@@ -1,0 +1,139 @@
+"""GPU parity of smx_summary_mixing_bwd (through SummaryMixing.forward + autograd -> C ABI -> libsmx kernels) against
+(1) gradients the unmodified reference produced (tests/golden/bwd, oracle/gen_golden_bwd.py) and (2) torch.autograd of
+the CPU oracle on seeded inputs, plus size-independent properties at the BASELINE shape.
+
+Tolerance (fp32 I/O): max-abs <= 1e-4 x max(1, |reference gradient|max) — fp32 arithmetic in a different summation order
+(split-K over row slices); bf16 I/O: x, dy, dx rounded to bf16, compared against the oracle fed the same rounded inputs,
+dx within 2 bf16 ulps of its scale, parameter gradients (fp32) within 1e-3 relative."""
+import pytest
+import torch
+import torch.nn as nn
+
+from oracle import smx_oracle as O
+from tests import _golden as G
+from tests._build import module_from_fixture
+from tests.test_backward_golden import bwd_names, load_bwd
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+
+
+def _close(a, b, rel, what):
+    err = float((a.detach().cpu().double() - b.double()).abs().max())
+    assert err <= rel * max(1.0, float(b.abs().max())), f"{what}: max-abs {err:.3e}"
+
+
+@pytest.mark.parametrize("name", bwd_names())
+def test_backward_matches_reference_gradients(name):
+    fx = G.Fixture(name)
+    dy, dx_ref, g_ref = load_bwd(name)
+    m = module_from_fixture(fx).to(DEV)
+    x = fx.x.to(DEV).requires_grad_(True)
+    mask = None if fx.mask is None else fx.mask.to(DEV)
+    y = m(x, src_padding_mask=mask)
+    assert y.requires_grad
+    _close(y, fx.y, 1e-4, "forward")
+    y.backward(dy.to(DEV))
+    _close(x.grad, dx_ref, 1e-4, "dx")
+    named = dict(m.named_parameters())
+    assert set(g_ref) <= set(named)
+    for k, v in g_ref.items():
+        assert named[k].grad is not None, k
+        _close(named[k].grad, v, 1e-4, k)
+
+
+def _oracle_grads(m, x, mask, dy, act):
+    sd = {k: v.detach().cpu().float().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    xo = x.detach().cpu().float().clone().requires_grad_(True)
+    y = O.summary_mixing(xo, sd, mode="SummaryMixing", act=act, use_layernorm=m.use_layernorm,
+                         src_padding_mask=None if mask is None else mask.cpu())
+    y.backward(dy.detach().cpu().float())
+    return xo.grad, {k: v.grad for k, v in sd.items()}
+
+
+def _perturbed(m, seed):
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.05 * torch.randn(p.shape, generator=g))
+    return m
+
+
+def test_backward_ragged_odd_sizes_against_oracle():
+    """Nothing is a multiple of a tile: D=72 (h=3), hidden 48 / 96, D_l=60, D_s=36, T=131, ragged lengths; training mode
+    (global_dropout=0) with only the parameters requiring grad."""
+    import summarymixing_b200 as S
+
+    torch.manual_seed(11)
+    m = _perturbed(S.SummaryMixing(72, 3, [48], 60, [96], 36, activation=nn.GELU, global_dropout=0.0), 11).to(DEV).train()
+    x = torch.randn(5, 131, 72, device=DEV)
+    lens = torch.tensor([131, 1, 77, 130, 64])
+    mask = (torch.arange(131)[None] < lens[:, None]).to(DEV)
+    dy = torch.randn(5, 131, 36, device=DEV)
+    y = m(x, src_padding_mask=mask)
+    y.backward(dy)
+    assert x.grad is None
+    _, g = _oracle_grads(m, x, mask, dy, "gelu")
+    for k, p in m.named_parameters():
+        _close(p.grad, g[k], 1e-4, k)
+
+
+def test_backward_bf16_io():
+    import summarymixing_b200 as S
+
+    torch.manual_seed(12)
+    m = _perturbed(S.SummaryMixing(64, 4, [64], 64, [64], 64, activation=S.Swish), 12).to(DEV).eval()
+    x = torch.randn(3, 200, 64, device=DEV).bfloat16().requires_grad_(True)
+    mask = (torch.arange(200)[None] < torch.tensor([200, 150, 9])[:, None]).to(DEV)
+    dy = torch.randn(3, 200, 64, device=DEV).bfloat16()
+    m(x, src_padding_mask=mask).backward(dy)
+    assert x.grad.dtype == torch.bfloat16
+    dx, g = _oracle_grads(m, x, mask, dy, "swish")
+    _close(x.grad.float(), dx, 2 ** -7, "dx (bf16)")
+    for k, p in m.named_parameters():
+        assert p.grad.dtype == torch.float32
+        _close(p.grad, g[k], 1e-3, k)
+
+
+def test_backward_unsupported_configurations_fail_loudly():
+    import summarymixing_b200 as S
+
+    x = torch.randn(2, 16, 64, device=DEV, requires_grad=True)
+    with pytest.raises(NotImplementedError, match="backward"):
+        S.SummaryMixing(64, 4, [64], 64, [64], 64, mode="SummaryMixing-lite").to(DEV).eval()(x)
+    with pytest.raises(NotImplementedError, match="backward"):
+        S.SummaryMixing(64, 4, [64], 64, [64], 64).to(DEV).eval()(x, sum_mask=torch.ones(16, 16, device=DEV))
+    with pytest.raises(NotImplementedError, match="dropout"):
+        S.SummaryMixing(64, 4, [64], 64, [64], 64).to(DEV).train()(x)
+
+
+def test_backward_properties_at_baseline_shape():
+    """B=32, T=1000, D=256, h=4 (BASELINE configs[1] cell): the backward is linear in dy, padded frames receive no
+    gradient, and an utterance's dx does not depend on the other utterances in the batch."""
+    import summarymixing_b200 as S
+
+    torch.manual_seed(13)
+    m = _perturbed(S.SummaryMixing(256, 4, [256], 256, [256], 256, activation=S.Swish), 13).to(DEV).eval()
+    B, T = 32, 1000
+    x = torch.randn(B, T, 256, device=DEV)
+    lens = torch.randint(300, T + 1, (B,))
+    lens[0] = T
+    mask = (torch.arange(T)[None] < lens[:, None]).to(DEV)
+    dy = torch.randn(B, T, 256, device=DEV)
+
+    def run(xx, mm, dd):
+        for p in m.parameters():
+            p.grad = None
+        xx = xx.clone().requires_grad_(True)
+        m(xx, src_padding_mask=mm).backward(dd)
+        return xx.grad, {k: p.grad.clone() for k, p in m.named_parameters()}
+
+    dx1, g1 = run(x, mask, dy)
+    dx2, g2 = run(x, mask, 2.0 * dy)
+    assert torch.isfinite(dx1).all()
+    assert float((dx2 - 2.0 * dx1).abs().max()) <= 1e-5 * float(dx1.abs().max())
+    for k in g1:
+        assert float((g2[k] - 2.0 * g1[k]).abs().max()) <= 1e-4 * max(1e-6, float(g1[k].abs().max())), k
+    assert float(dx1[~mask].abs().max()) == 0.0
+    dx_solo, _ = run(x[5:6], mask[5:6], dy[5:6])
+    assert float((dx_solo[0] - dx1[5]).abs().max()) <= 1e-5 * max(1.0, float(dx1[5].abs().max()))
