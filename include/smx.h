@@ -245,6 +245,42 @@ SMX_API int smx_summary_mixing_bwd(const smx_cell_weights* w, int dtype, int32_t
                            const uint8_t* padding_mask, const void* dy, void* dx, const smx_cell_grads* grads,
                            void* workspace, size_t workspace_bytes, void* stream);
 
+/* Gradients of the other blocks of ConformerEncoderLayer.forward (Conformer.py:490-548), same conventions as
+ * smx_summary_mixing_bwd: self-contained (forward intermediates recomputed from x in fp32), x / dy / dx in `dtype`,
+ * parameter gradients fp32, overwritten, NULL = not wanted, dropout off.
+ *   smx_layernorm_bwd    nn.LayerNorm (norm1, the encoder's final norm)
+ *   smx_ffn_bwd          y = x + 0.5 * FFN(LN(x)), optionally followed by LN_out (Conformer.py:470-484, 518, 547)
+ *   smx_conv_module_bwd  y = conv_module(x) * mask (Conformer.py:322-338; chunk_size == 0: no Dynamic Chunk Convolution) */
+typedef struct {
+  float* ln_dw;
+  float* ln_db;
+  smx_linear_grad w1;
+  smx_linear_grad w2;
+  float* out_ln_dw;
+  float* out_ln_db;
+} smx_ffn_grads;
+typedef struct {
+  float* ln_dw;
+  float* ln_db;
+  smx_linear_grad bottleneck;
+  float* dw_dw;        /* depthwise weight gradient (D,1,k) */
+  float* dw_db;
+  float* after_ln_dw;
+  float* after_ln_db;
+  smx_linear_grad out;
+} smx_convmod_grads;
+SMX_API size_t smx_layernorm_bwd_workspace_bytes(int dtype, int64_t rows, int32_t D);
+SMX_API int smx_layernorm_bwd(int dtype, int64_t rows, int32_t D, const void* x, const float* w, float eps, const void* dy,
+                      void* dx, float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream);
+SMX_API size_t smx_ffn_bwd_workspace_bytes(const smx_ffn_weights* w, int dtype, int64_t rows, int has_out_ln);
+SMX_API int smx_ffn_bwd(const smx_ffn_weights* w, int act, int dtype, int64_t rows, const void* x, const float* out_ln_w,
+                const float* out_ln_b, float out_ln_eps, const void* dy, void* dx, const smx_ffn_grads* grads,
+                void* workspace, size_t workspace_bytes, void* stream);
+SMX_API size_t smx_conv_module_bwd_workspace_bytes(const smx_convmod_weights* w, int dtype, int32_t B, int32_t T);
+SMX_API int smx_conv_module_bwd(const smx_convmod_weights* w, int act, int dtype, int32_t B, int32_t T, const void* x,
+                        const uint8_t* padding_mask, const void* dy, void* dx, const smx_convmod_grads* grads,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* ConvolutionModule.forward (Conformer.py:166-340): y = conv_module(x) * mask (+ residual if given).
  * chunk_size > 0 selects Dynamic Chunk Convolution (Conformer.py:197-320). */
 SMX_API size_t smx_conv_module_workspace_bytes(const smx_convmod_weights* w, int dtype, int32_t B, int32_t T);

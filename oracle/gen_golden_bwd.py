@@ -1,4 +1,4 @@
-"""Golden GRADIENTS of the SummaryMixing cell from the UNMODIFIED reference (run in the build container).
+"""Golden GRADIENTS of the SummaryMixing cell, the convolution module and the Conformer layer / encoder from the UNMODIFIED reference (run in the build container).
 
     python oracle/gen_golden_bwd.py        # writes tests/golden/bwd/*.npz
 
@@ -25,10 +25,16 @@ sys.path.insert(0, ROOT)
 
 from speechbrain.nnet.activations import Swish  # noqa: E402
 from speechbrain.nnet.summary_mixing import SummaryMixing  # noqa: E402
+from speechbrain.lobes.models.transformer.Conformer import (  # noqa: E402
+    ConformerEncoder,
+    ConformerEncoderLayer,
+    ConvolutionModule,
+)
 from tests import _golden as G  # noqa: E402
 
 ACTS = {"swish": Swish, "gelu": nn.GELU, "relu": nn.ReLU, "leaky_relu": nn.LeakyReLU}
-CASES = ["cell_sm_h4_swish", "cell_sm_h1_gelu", "cell_sm_h4_relu_noln_deep_nomask", "cell_reftest_sm_h4", "cell_sm_h4_gelu"]
+CASES = ["cell_sm_h4_swish", "cell_sm_h1_gelu", "cell_sm_h4_relu_noln_deep_nomask", "cell_reftest_sm_h4", "cell_sm_h4_gelu",
+         "convmod_plain", "convmod_causal", "conformer_layer", "conformer_enc_sm_h4", "conformer_enc_sm_h1_gelu"]
 OUT = os.path.join(ROOT, "tests", "golden", "bwd")
 
 
@@ -37,12 +43,31 @@ def main():
     for i, name in enumerate(CASES):
         fx = G.Fixture(name)
         c = fx.cfg
-        sm = SummaryMixing(c["enc_dim"], c["nhead"], c["local_proj_hid_dim"], c["local_proj_out_dim"], c["summary_hid_dim"],
-                           c["summary_out_dim"], activation=ACTS[c["act"]], mode=c["mode"], use_layernorm=c["use_layernorm"])
+        k = c["kind"]
+        if k == "cell":
+            sm = SummaryMixing(c["enc_dim"], c["nhead"], c["local_proj_hid_dim"], c["local_proj_out_dim"], c["summary_hid_dim"],
+                               c["summary_out_dim"], activation=ACTS[c["act"]], mode=c["mode"], use_layernorm=c["use_layernorm"])
+            run = (lambda m, x: m(x, src_padding_mask=fx.mask)) if fx.mask is not None else (lambda m, x: m(x))
+        elif k == "conv_module":
+            sm = ConvolutionModule(c["input_size"], c["kernel_size"], True, ACTS[c["act"]], 0.0, causal=c["causal"],
+                                   masked_false_or_true=False)
+            run = lambda m, x: m(x, fx.mask.unsqueeze(-1))  # noqa: E731
+        elif k == "conformer_layer":
+            sm = ConformerEncoderLayer(c["d_model"], c["d_ffn"], c["nhead"], c["kernel_size"], activation=ACTS[c["act"]],
+                                       attention_type="SummaryMixing", local_proj_hid_dim=c["local_proj_hid_dim"],
+                                       local_proj_out_dim=c["local_proj_out_dim"], summary_hid_dim=c["summary_hid_dim"],
+                                       mode=c["mode"], use_layernorm=c["use_layernorm"])
+            run = lambda m, x: m(x, src_key_padding_mask=fx.mask)[0]  # noqa: E731
+        else:
+            sm = ConformerEncoder(c["num_layers"], c["d_model"], c["d_ffn"], c["nhead"], c["kernel_size"],
+                                  activation=ACTS[c["act"]], attention_type="SummaryMixing",
+                                  local_proj_hid_dim=c["local_proj_hid_dim"], local_proj_out_dim=c["local_proj_out_dim"],
+                                  summary_hid_dim=c["summary_hid_dim"], mode=c["mode"], use_layernorm=c["use_layernorm"])
+            run = lambda m, x: m(x, src_key_padding_mask=fx.mask)[0]  # noqa: E731
         sm.load_state_dict(fx.sd)
         sm.eval()
         x = fx.x.clone().requires_grad_(True)
-        y = sm(x, src_padding_mask=fx.mask) if fx.mask is not None else sm(x)
+        y = run(sm, x)
         assert float((y.detach() - fx.y).abs().max()) < 1e-6, name
         dy = torch.randn(y.shape, generator=torch.Generator().manual_seed(7000 + i))
         y.backward(dy)

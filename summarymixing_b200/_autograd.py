@@ -1,0 +1,154 @@
+"""autograd nodes over libsmx's backward entry points (smx_layernorm_bwd, smx_ffn_bwd, smx_conv_module_bwd; the cell's
+node lives next to its module in nnet/summary_mixing.py).  Every backward call is self-contained — the library
+recomputes what it needs from the saved input — so a node keeps only its input (and the mask).  Gradients come back in
+fp32 and are cast to the parameter's dtype.  Dropout is not implemented: callers refuse training mode with p > 0."""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _host as H
+from . import _lib as L
+
+
+def wants_grad(module, x) -> bool:
+    """True when the call has to be recorded by autograd: x requires grad, or the module is in training mode with
+    trainable parameters (eval-mode calls on plain inputs stay on the inference path)."""
+    return torch.is_grad_enabled() and (x.requires_grad or (module.training and any(p.requires_grad for p in module.parameters())))
+
+
+def refuse_dropout(module, p: float) -> None:
+    if module.training and p > 0:
+        raise NotImplementedError(
+            "summarymixing_b200: training-mode dropout is not implemented (build the model with dropout=0 or call .eval())")
+
+
+def _new_grads(params, dev):
+    return [torch.empty(p.shape, dtype=torch.float32, device=dev) for p in params]
+
+
+def _cast_out(ctx, first, grads, params):
+    return [g.to(p.dtype) if ctx.needs_input_grad[first + i] else None for i, (g, p) in enumerate(zip(grads, params))]
+
+
+class LayerNormFunction(torch.autograd.Function):
+    """nn.LayerNorm over the last dim: smx_layernorm_fwd / smx_layernorm_bwd."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, eps):
+        from .nnet.containers import layer_norm
+
+        ctx.eps = float(eps)
+        ctx.save_for_backward(x, weight, bias)
+        return layer_norm(x, weight, bias, eps)
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, bias = ctx.saved_tensors
+        dev = x.device
+        xc, dyc = x.contiguous(), dy.contiguous()
+        D = xc.shape[-1]
+        rows = xc.numel() // D
+        wv = H.WeightView()
+        wv.stale((weight,), dev)
+        dw, db = _new_grads((weight, bias), dev)
+        dx = torch.empty_like(xc) if ctx.needs_input_grad[0] else None
+        lib = L.lib()
+        dt = H.dtype_code(xc)
+        with torch.cuda.device(dev):
+            ws = H.workspace(dev, lib.smx_layernorm_bwd_workspace_bytes(dt, rows, D))
+            L.check(lib.smx_layernorm_bwd(dt, rows, D, xc.data_ptr(), wv.ptr(weight, dev), ctx.eps, dyc.data_ptr(),
+                                          H.p_or_none(dx), dw.data_ptr(), db.data_ptr(), ws.data_ptr(), ws.numel(),
+                                          H.stream_ptr(dev)))
+        gw, gb = _cast_out(ctx, 1, (dw, db), (weight, bias))
+        return dx, gw, gb, None
+
+
+class FFNFunction(torch.autograd.Function):
+    """y = x + 0.5 * FFN(LN(x)) (optionally followed by the layer's norm2): smx_ffn_fwd / smx_ffn_bwd.
+    params = [ln.weight, ln.bias, W1, b1, W2, b2] (+ [norm.weight, norm.bias])."""
+
+    @staticmethod
+    def forward(ctx, fw, act, out_norm, x, *params):
+        # fw: L.FFNWeights (kept alive by the owning layer's WeightView); out_norm: (w_ptr, b_ptr, eps) or None
+        dev = x.device
+        xc = x.contiguous()
+        rows = xc.numel() // xc.shape[-1]
+        y = torch.empty_like(xc)
+        lib = L.lib()
+        dt = H.dtype_code(xc)
+        ow, ob, oeps = out_norm if out_norm is not None else (None, None, 0.0)
+        with torch.cuda.device(dev):
+            ws = H.workspace(dev, lib.smx_ffn_workspace_bytes(C.byref(fw), dt, rows))
+            L.check(lib.smx_ffn_fwd(C.byref(fw), act, dt, rows, xc.data_ptr(), ow, ob, oeps, y.data_ptr(), ws.data_ptr(),
+                                    ws.numel(), H.stream_ptr(dev)))
+        ctx.fw, ctx.act, ctx.out_norm, ctx.params = fw, act, out_norm, params
+        ctx.save_for_backward(xc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xc,) = ctx.saved_tensors
+        dev = xc.device
+        dyc = dy.contiguous()
+        rows = xc.numel() // xc.shape[-1]
+        grads = _new_grads(ctx.params, dev)
+        fg = L.FFNGrads()
+        fg.ln_dw, fg.ln_db = grads[0].data_ptr(), grads[1].data_ptr()
+        fg.w1.dw, fg.w1.db = grads[2].data_ptr(), grads[3].data_ptr()
+        fg.w2.dw, fg.w2.db = grads[4].data_ptr(), grads[5].data_ptr()
+        if ctx.out_norm is not None:
+            fg.out_ln_dw, fg.out_ln_db = grads[6].data_ptr(), grads[7].data_ptr()
+        ow, ob, oeps = ctx.out_norm if ctx.out_norm is not None else (None, None, 0.0)
+        dx = torch.empty_like(xc) if ctx.needs_input_grad[3] else None
+        lib = L.lib()
+        dt = H.dtype_code(xc)
+        with torch.cuda.device(dev):
+            ws = H.workspace(dev, lib.smx_ffn_bwd_workspace_bytes(C.byref(ctx.fw), dt, rows, int(ctx.out_norm is not None)))
+            L.check(lib.smx_ffn_bwd(C.byref(ctx.fw), ctx.act, dt, rows, xc.data_ptr(), ow, ob, oeps, dyc.data_ptr(),
+                                    H.p_or_none(dx), C.byref(fg), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+        return (None, None, None, dx, *_cast_out(ctx, 4, grads, ctx.params))
+
+
+class ConvModuleFunction(torch.autograd.Function):
+    """y = conv_module(x) * mask: smx_conv_module_fwd / smx_conv_module_bwd.
+    params = [ln.weight, ln.bias, Wb, bb, dw.weight, dw.bias, after_ln.weight, after_ln.bias, Wo, bo]."""
+
+    @staticmethod
+    def forward(ctx, cw, act, x, m8, *params):
+        dev = x.device
+        xc = x.contiguous()
+        B, T, _ = xc.shape
+        y = torch.empty_like(xc)
+        lib = L.lib()
+        dt = H.dtype_code(xc)
+        with torch.cuda.device(dev):
+            ws = H.workspace(dev, lib.smx_conv_module_workspace_bytes(C.byref(cw), dt, B, T))
+            L.check(lib.smx_conv_module_fwd(C.byref(cw), act, dt, B, T, 0, xc.data_ptr(), H.p_or_none(m8), None, y.data_ptr(),
+                                            ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+        ctx.cw, ctx.act, ctx.params = cw, act, params
+        ctx.save_for_backward(xc, m8)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, m8 = ctx.saved_tensors
+        dev = xc.device
+        dyc = dy.contiguous()
+        B, T, _ = xc.shape
+        grads = _new_grads(ctx.params, dev)
+        cg = L.ConvModGrads()
+        cg.ln_dw, cg.ln_db = grads[0].data_ptr(), grads[1].data_ptr()
+        cg.bottleneck.dw, cg.bottleneck.db = grads[2].data_ptr(), grads[3].data_ptr()
+        cg.dw_dw, cg.dw_db = grads[4].data_ptr(), grads[5].data_ptr()
+        cg.after_ln_dw, cg.after_ln_db = grads[6].data_ptr(), grads[7].data_ptr()
+        cg.out.dw, cg.out.db = grads[8].data_ptr(), grads[9].data_ptr()
+        dx = torch.empty_like(xc) if ctx.needs_input_grad[2] else None
+        lib = L.lib()
+        dt = H.dtype_code(xc)
+        with torch.cuda.device(dev):
+            ws = H.workspace(dev, lib.smx_conv_module_bwd_workspace_bytes(C.byref(ctx.cw), dt, B, T))
+            L.check(lib.smx_conv_module_bwd(C.byref(ctx.cw), ctx.act, dt, B, T, xc.data_ptr(), H.p_or_none(m8), dyc.data_ptr(),
+                                            H.p_or_none(dx), C.byref(cg), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+        return (None, None, dx, None, *_cast_out(ctx, 4, grads, ctx.params))

@@ -51,6 +51,15 @@ class CellGrads(C.Structure):
                 ("local_norm_dw", fp), ("local_norm_db", fp), ("summary_norm_dw", fp), ("summary_norm_db", fp)]
 
 
+class FFNGrads(C.Structure):
+    _fields_ = [("ln_dw", fp), ("ln_db", fp), ("w1", LinearGrad), ("w2", LinearGrad), ("out_ln_dw", fp), ("out_ln_db", fp)]
+
+
+class ConvModGrads(C.Structure):
+    _fields_ = [("ln_dw", fp), ("ln_db", fp), ("bottleneck", LinearGrad), ("dw_dw", fp), ("dw_db", fp), ("after_ln_dw", fp),
+                ("after_ln_db", fp), ("out", LinearGrad)]
+
+
 class FFNWeights(C.Structure):
     _fields_ = [("ln_w", fp), ("ln_b", fp), ("w1", Linear), ("w2", Linear), ("packed", fp)]
 
@@ -107,6 +116,14 @@ _PROTOS = {
     "smx_summary_mixing_bwd_workspace_bytes": (_sz, [C.POINTER(CellWeights), _i, _i, _i]),
     "smx_summary_mixing_bwd": (_i, [C.POINTER(CellWeights), _i, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(CellGrads), _vp, _sz,
                                     _vp]),
+    "smx_layernorm_bwd_workspace_bytes": (_sz, [_i, _i64, _i]),
+    "smx_layernorm_bwd": (_i, [_i, _i64, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "smx_ffn_bwd_workspace_bytes": (_sz, [C.POINTER(FFNWeights), _i, _i64, _i]),
+    "smx_ffn_bwd": (_i, [C.POINTER(FFNWeights), _i, _i, _i64, _vp, _vp, _vp, _f, _vp, _vp, C.POINTER(FFNGrads), _vp, _sz,
+                         _vp]),
+    "smx_conv_module_bwd_workspace_bytes": (_sz, [C.POINTER(ConvModWeights), _i, _i, _i]),
+    "smx_conv_module_bwd": (_i, [C.POINTER(ConvModWeights), _i, _i, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(ConvModGrads),
+                                 _vp, _sz, _vp]),
     "smx_conv_module_workspace_bytes": (_sz, [C.POINTER(ConvModWeights), _i, _i, _i]),
     "smx_conv_module_fwd": (_i, [C.POINTER(ConvModWeights), _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "smx_ffn_workspace_bytes": (_sz, [C.POINTER(FFNWeights), _i, _i64]),
@@ -133,7 +150,7 @@ _PROTOS = {
 
 
 ABI_STRUCTS = [Linear, CellWeights, FFNWeights, ConvModWeights, ConformerLayerWeights, ConvBranchWeights,
-               BranchformerLayerWeights, CellGrads]
+               BranchformerLayerWeights, CellGrads, FFNGrads, ConvModGrads]
 
 
 def exported_symbols():

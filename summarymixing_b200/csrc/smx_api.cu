@@ -74,6 +74,8 @@ size_t smx_struct_size(int which) {
     case 5: return sizeof(smx_convbranch_weights);
     case 6: return sizeof(smx_branchformer_layer_weights);
     case 7: return sizeof(smx_cell_grads);
+    case 8: return sizeof(smx_ffn_grads);
+    case 9: return sizeof(smx_convmod_grads);
     default: return 0;
   }
 }
@@ -204,6 +206,77 @@ int smx_summary_mixing_bwd(const smx_cell_weights* w, int dtype, int32_t B, int3
     return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", dry.peak, workspace_bytes);
   Arena a(workspace, workspace_bytes, false);
   return cell_bwd_generic(w, B, T, x, dtype, padding_mask, dy, dtype, dx, dtype, grads, a, (cudaStream_t)stream);
+}
+
+// ---- LayerNorm / FFN / conv module, backward ------------------------------------------------------
+static float* const kDummy = (float*)(uintptr_t)256;  // sizing runs only: never dereferenced
+size_t smx_layernorm_bwd_workspace_bytes(int dtype, int64_t rows, int32_t D) {
+  if (rows <= 0 || D <= 0) return 0;
+  Arena a(nullptr, 0, true);
+  layernorm_bwd_generic(nullptr, dtype, rows, D, nullptr, 0.f, nullptr, dtype, kDummy, dtype, kDummy, kDummy, a, nullptr);
+  return a.peak;
+}
+int smx_layernorm_bwd(int dtype, int64_t rows, int32_t D, const void* x, const float* w, float eps, const void* dy, void* dx,
+                      float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(dy, "dy"));
+  if (dx) SMX_TRY(check_ptr(dx, "dx"));
+  if (!w) return fail(SMX_ERR_BAD_ARG, "layernorm backward: NULL weight");
+  if (rows <= 0 || D <= 0) return fail(SMX_ERR_BAD_ARG, "layernorm backward: rows and D must be positive");
+  SMX_TRY(check_arch());
+  size_t need = smx_layernorm_bwd_workspace_bytes(dtype, rows, D);
+  if (need > workspace_bytes || (need && !workspace))
+    return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  Arena a(workspace, workspace_bytes, false);
+  return layernorm_bwd_generic(x, dtype, rows, D, w, eps, dy, dtype, dx, dtype, dw, db, a, (cudaStream_t)stream);
+}
+size_t smx_ffn_bwd_workspace_bytes(const smx_ffn_weights* w, int dtype, int64_t rows, int has_out_ln) {
+  if (!w || rows <= 0) return 0;
+  smx_ffn_grads g{kDummy, kDummy, {kDummy, kDummy}, {kDummy, kDummy}, kDummy, kDummy};
+  Arena a(nullptr, 0, true);
+  if (ffn_bwd_generic(w, 0, rows, nullptr, dtype, has_out_ln ? kDummy : nullptr, has_out_ln ? kDummy : nullptr, 0.f, nullptr, dtype,
+                      kDummy, dtype, &g, a, nullptr) != SMX_OK)
+    return 0;
+  return a.peak;
+}
+int smx_ffn_bwd(const smx_ffn_weights* w, int act, int dtype, int64_t rows, const void* x, const float* out_ln_w,
+                const float* out_ln_b, float out_ln_eps, const void* dy, void* dx, const smx_ffn_grads* grads, void* workspace,
+                size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  if (!w || !grads) return fail(SMX_ERR_BAD_ARG, "weights or grads is NULL");
+  if (rows <= 0) return fail(SMX_ERR_BAD_ARG, "rows must be positive");
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(dy, "dy"));
+  if (dx) SMX_TRY(check_ptr(dx, "dx"));
+  SMX_TRY(check_arch());
+  size_t need = smx_ffn_bwd_workspace_bytes(w, dtype, rows, out_ln_w != nullptr);
+  if (need == 0) return SMX_ERR_BAD_ARG;  // message set by the sizing run
+  if (need > workspace_bytes || !workspace)
+    return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  Arena a(workspace, workspace_bytes, false);
+  return ffn_bwd_generic(w, act, rows, x, dtype, out_ln_w, out_ln_b, out_ln_eps, dy, dtype, dx, dtype, grads, a, (cudaStream_t)stream);
+}
+size_t smx_conv_module_bwd_workspace_bytes(const smx_convmod_weights* w, int dtype, int32_t B, int32_t T) {
+  if (!w || B <= 0 || T <= 0) return 0;
+  smx_convmod_grads g{kDummy, kDummy, {kDummy, kDummy}, kDummy, kDummy, kDummy, kDummy, {kDummy, kDummy}};
+  Arena a(nullptr, 0, true);
+  if (convmod_bwd_generic(w, 0, B, T, nullptr, dtype, nullptr, nullptr, dtype, kDummy, dtype, &g, a, nullptr) != SMX_OK) return 0;
+  return a.peak;
+}
+int smx_conv_module_bwd(const smx_convmod_weights* w, int act, int dtype, int32_t B, int32_t T, const void* x,
+                        const uint8_t* padding_mask, const void* dy, void* dx, const smx_convmod_grads* grads, void* workspace,
+                        size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  if (!w || !grads) return fail(SMX_ERR_BAD_ARG, "weights or grads is NULL");
+  SMX_TRY(check_bt(B, T));
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(dy, "dy"));
+  if (dx) SMX_TRY(check_ptr(dx, "dx"));
+  SMX_TRY(check_arch());
+  size_t need = smx_conv_module_bwd_workspace_bytes(w, dtype, B, T);
+  if (need == 0) return SMX_ERR_BAD_ARG;
+  if (need > workspace_bytes || !workspace)
+    return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  Arena a(workspace, workspace_bytes, false);
+  return convmod_bwd_generic(w, act, B, T, x, dtype, padding_mask, dy, dtype, dx, dtype, grads, a, (cudaStream_t)stream);
 }
 
 // ---- ConvolutionModule ---------------------------------------------------------------------------

@@ -317,13 +317,14 @@ int act_bwd(const float* z, const void* da, int da_dt, int64_t rows, int ncols, 
 }
 
 // LayerNorm backward over `rows` rows: g (dy -> dv, in place), parameter gradients into dw / db (either may be NULL)
-int ln_bwd(const float* v, int64_t rows, int D, const float* w, float* g, float* dw, float* db, Arena& ws, cudaStream_t st) {
+int ln_bwd(const float* v, int64_t rows, int D, const float* w, float* g, float* dw, float* db, Arena& ws, cudaStream_t st,
+           float eps = 1e-5f) {
   const size_t m0 = ws.mark();
   float* t = ws.f32((size_t)rows * D);
   if (!t) return fail(SMX_ERR_WORKSPACE, "workspace too small (LayerNorm backward)");
   if (db) SMX_TRY(colsum_all(g, D, rows, D, db, ws, st));  // before g is overwritten
   if (!ws.dry) {
-    ln_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(v, rows, D, w, 1e-5f, g, t);
+    ln_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(v, rows, D, w, eps, g, t);
     count_launch();
     SMX_TRY(check_launch("ln_bwd_kernel"));
   }
@@ -475,5 +476,229 @@ int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int
   ws.release(m0);
   return SMX_OK;
 }
+
+
+// =============================================================================================
+// macaron half-step FFN, LayerNorm and convolution module: backward          Conformer.py:470-484, 322-338
+// =============================================================================================
+namespace {
+
+// dst (fp32) = alpha * src
+__global__ void __launch_bounds__(256) scale_kernel(const void* src, int s_dt, float alpha, int64_t n, float* dst) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) dst[i] = alpha * bw_ld(src, s_dt, i);
+}
+// dst (any dtype) = a + b (* rowmask)
+__global__ void __launch_bounds__(256) add_kernel(const float* a, const float* b, int64_t n, void* dst, int d_dt) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const float v = a[i] + (b ? b[i] : 0.0f);
+    if (d_dt == SMX_BF16) ((__nv_bfloat16*)dst)[i] = __float2bfloat16_rn(v);
+    else ((float*)dst)[i] = v;
+  }
+}
+// dst (fp32) = src * rowmask[row]
+__global__ void __launch_bounds__(256) mask_rows_kernel(const void* src, int s_dt, const uint8_t* rowmask, int ncols, int64_t n, float* dst) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256)
+    dst[i] = bw_ld(src, s_dt, i) * (rowmask ? (float)rowmask[i / ncols] : 1.0f);
+}
+// GLU backward: p = [value | gate] (rows, 2D); dp[:, :D] = dg * sigmoid(gate); dp[:, D:] = dg * value * s * (1 - s)
+__global__ void __launch_bounds__(256) glu_bwd_kernel(const float* p, const float* dg, int64_t rows, int D, float* dp) {
+  const int64_t n = rows * D;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const int64_t r = i / D;
+    const int c = (int)(i % D);
+    const float a = p[r * 2 * D + c], gt = p[r * 2 * D + D + c];
+    const float s = 1.0f / (1.0f + expf(-gt));
+    const float d = dg[i];
+    dp[r * 2 * D + c] = d * s;
+    dp[r * 2 * D + D + c] = d * a * s * (1.0f - s);
+  }
+}
+// depthwise conv, gradient with respect to the input: din[b,t,c] = sum_j w[c,j] * dout[b, t - j + pad, c]
+__global__ void __launch_bounds__(256) dwconv_bwd_data_kernel(const float* dout, const float* w, int B, int T, int C, int k, int pad,
+                                                              float* din) {
+  const int64_t n = (int64_t)B * T * C;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const int c = (int)(i % C);
+    const int t = (int)((i / C) % T);
+    const int b = (int)(i / ((int64_t)C * T));
+    const float* base = dout + (int64_t)b * T * C + c;
+    float acc = 0.0f;
+    for (int j = 0; j < k; ++j) {
+      const int u = t - j + pad;
+      if (u < 0 || u >= T) continue;
+      acc = fmaf(w[(int64_t)c * k + j], base[(int64_t)u * C], acc);
+    }
+    din[i] = acc;
+  }
+}
+// depthwise conv, weight gradient partials: P[slice][c][j] = sum over the slice's utterances and all t of
+// dout[b,t,c] * in[b, t + j - pad, c].  grid (ceil(C/32), k, slices), block 32 x 8 (channels x frame lanes).
+__global__ void __launch_bounds__(256) dwconv_bwd_w_kernel(const float* dout, const float* in, int B, int T, int C, int k, int pad,
+                                                           int utt_per_slice, float* P) {
+  __shared__ float red[8][33];
+  const int cx = threadIdx.x % 32, ry = threadIdx.x / 32;
+  const int c = blockIdx.x * 32 + cx, j = blockIdx.y;
+  const int b0 = blockIdx.z * utt_per_slice;
+  const int b1 = b0 + utt_per_slice < B ? b0 + utt_per_slice : B;
+  float acc = 0.0f;
+  if (c < C) {
+    for (int b = b0; b < b1; ++b) {
+      const float* dob = dout + (int64_t)b * T * C + c;
+      const float* inb = in + (int64_t)b * T * C + c;
+      for (int t = ry; t < T; t += 8) {
+        const int u = t + j - pad;
+        if (u >= 0 && u < T) acc = fmaf(dob[(int64_t)t * C], inb[(int64_t)u * C], acc);
+      }
+    }
+  }
+  red[ry][cx] = acc;
+  __syncthreads();
+  if (ry == 0 && c < C) {
+    float tot = 0.0f;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) tot += red[r][cx];
+    P[((int64_t)blockIdx.z * C + c) * k + j] = tot;
+  }
+}
+
+}  // namespace
+
+#define BW_RUN(expr) do { if (!ws.dry) SMX_TRY(expr); } while (0)
+#define BW_BUF(name, n) float* name = ws.f32((size_t)(n)); if (!name) return fail(SMX_ERR_WORKSPACE, "workspace too small (backward)")
+#define BW_LAUNCH(what, ...) do { if (!ws.dry) { __VA_ARGS__; count_launch(); SMX_TRY(check_launch(what)); } } while (0)
+
+// nn.LayerNorm backward: dx (dtype tag) and fp32 parameter gradients
+int layernorm_bwd_generic(const void* x, int x_dt, int64_t rows, int D, const float* w, float eps, const void* dy, int dy_dt, void* dx,
+                          int dx_dt, float* dw, float* db, Arena& ws, cudaStream_t st) {
+  const size_t m0 = ws.mark();
+  const float* x32 = (const float*)x;
+  if (x_dt != SMX_F32) {
+    BW_BUF(xc, rows * D);
+    BW_RUN(convert(x, x_dt, xc, SMX_F32, rows * D, st));
+    x32 = xc;
+  }
+  BW_BUF(g, rows * D);
+  BW_LAUNCH("scale_kernel", scale_kernel<<<ew_grid(rows * D), 256, 0, st>>>(dy, dy_dt, 1.0f, rows * D, g));
+  SMX_TRY(ln_bwd(x32, rows, D, w, g, dw, db, ws, st, eps));
+  if (dx) BW_LAUNCH("add_kernel", add_kernel<<<ew_grid(rows * D), 256, 0, st>>>(g, nullptr, rows * D, dx, dx_dt));
+  ws.release(m0);
+  return SMX_OK;
+}
+
+// y = x + 0.5 * W2 act(W1 LN(x) + b1) + 0.5 * b2;  y = LN_out(y) when out_ln_w               Conformer.py:470-484, 518, 547
+int ffn_bwd_generic(const smx_ffn_weights* w, int act, int64_t rows, const void* x, int x_dt, const float* oln_w, const float* oln_b,
+                    float oln_eps, const void* dy, int dy_dt, void* dx, int dx_dt, const smx_ffn_grads* g, Arena& ws, cudaStream_t st) {
+  const int D = w->w1.in_dim, F = w->w1.out_dim;
+  if (w->w2.in_dim != F || w->w2.out_dim != D || w->w1.n_split > 1 || w->w2.n_split > 1)
+    return fail(SMX_ERR_BAD_ARG, "ffn backward: inconsistent dims");
+  if (rows > 0x7fffffff) return fail(SMX_ERR_UNSUPPORTED, "ffn backward: more than 2^31 rows");
+  const size_t m0 = ws.mark();
+  const float* x32 = (const float*)x;
+  if (x_dt != SMX_F32) {
+    BW_BUF(xc, rows * D);
+    BW_RUN(convert(x, x_dt, xc, SMX_F32, rows * D, st));
+    x32 = xc;
+  }
+  // forward recomputation
+  BW_BUF(xn, rows * D);
+  BW_RUN(layernorm(x32, SMX_F32, D, w->ln_w, w->ln_b, 1e-5f, SMX_ACT_IDENTITY, xn, SMX_F32, D, rows, D, st));
+  BW_BUF(z1, rows * F);
+  BW_RUN(lin_fwd(w->w1, xn, D, rows, z1, F, true, 0, 0, nullptr, 1, st));
+  BW_BUF(h, rows * F);
+  BW_RUN(act_fwd(z1, rows, F, act, nullptr, h, st));
+  BW_BUF(gy, rows * D);  // gradient with respect to the pre-norm sum x + 0.5 u
+  BW_LAUNCH("scale_kernel", scale_kernel<<<ew_grid(rows * D), 256, 0, st>>>(dy, dy_dt, 1.0f, rows * D, gy));
+  if (oln_w) {
+    BW_BUF(ypre, rows * D);
+    if (!ws.dry) {  // ypre = x + 0.5 * (h W2^T + b2)
+      GemmP p = bw_gemm();
+      p.A = h; p.lda = F; p.C = ypre; p.ldc = D; p.M = (int)rows; p.K = F; p.N = D;
+      p.W = w->w2.w; p.w_sk = 1; p.w_sn = F; p.bias = w->w2.b;
+      p.residual = x32; p.r_dtype = SMX_F32; p.ldr = D; p.alpha = 0.5f;
+      SMX_TRY(gemm(p, st));
+    }
+    SMX_TRY(ln_bwd(ypre, rows, D, oln_w, gy, g->out_ln_dw, g->out_ln_db, ws, st, oln_eps));
+  }
+  BW_BUF(du, rows * D);
+  BW_LAUNCH("scale_kernel", scale_kernel<<<ew_grid(rows * D), 256, 0, st>>>(gy, SMX_F32, 0.5f, rows * D, du));
+  if (g->w2.dw) SMX_TRY(lin_wgrad(w->w2, du, D, h, F, rows, g->w2.dw, 0, 0, ws, st));
+  if (g->w2.db) SMX_TRY(colsum_all(du, D, rows, D, g->w2.db, ws, st));
+  BW_BUF(dh, rows * F);
+  BW_RUN(lin_dgrad(w->w2, du, D, rows, dh, SMX_F32, F, 0, 0, nullptr, st));
+  BW_RUN(act_bwd(z1, dh, SMX_F32, rows, F, act, nullptr, dh, st));
+  if (g->w1.dw) SMX_TRY(lin_wgrad(w->w1, dh, F, xn, D, rows, g->w1.dw, 0, 0, ws, st));
+  if (g->w1.db) SMX_TRY(colsum_all(dh, F, rows, F, g->w1.db, ws, st));
+  float* dxn = du;  // du is dead
+  BW_RUN(lin_dgrad(w->w1, dh, F, rows, dxn, SMX_F32, D, 0, 0, nullptr, st));
+  SMX_TRY(ln_bwd(x32, rows, D, w->ln_w, dxn, g->ln_dw, g->ln_db, ws, st));
+  if (dx) BW_LAUNCH("add_kernel", add_kernel<<<ew_grid(rows * D), 256, 0, st>>>(gy, dxn, rows * D, dx, dx_dt));
+  ws.release(m0);
+  return SMX_OK;
+}
+
+// y = (Linear(act(LN_after(dwconv(GLU(pointwise(LN(x))))))) ) * mask                        Conformer.py:322-338
+int convmod_bwd_generic(const smx_convmod_weights* w, int act, int B, int T, const void* x, int x_dt, const uint8_t* mask, const void* dy,
+                        int dy_dt, void* dx, int dx_dt, const smx_convmod_grads* g, Arena& ws, cudaStream_t st) {
+  const int64_t rows = (int64_t)B * T;
+  const int D = w->bottleneck.in_dim, k = w->kernel_size;
+  if (w->bottleneck.out_dim != 2 * D || w->out.in_dim != D || w->out.out_dim != D || k < 1)
+    return fail(SMX_ERR_BAD_ARG, "conv module backward: inconsistent dims");
+  if (rows > 0x7fffffff) return fail(SMX_ERR_UNSUPPORTED, "conv module backward: more than 2^31 frames");
+  const int pad = w->causal ? (k - 1) : (k - 1) / 2;
+  const size_t m0 = ws.mark();
+  const float* x32 = (const float*)x;
+  if (x_dt != SMX_F32) {
+    BW_BUF(xc, rows * D);
+    BW_RUN(convert(x, x_dt, xc, SMX_F32, rows * D, st));
+    x32 = xc;
+  }
+  // forward recomputation
+  BW_BUF(xn, rows * D);
+  BW_RUN(layernorm(x32, SMX_F32, D, w->ln_w, w->ln_b, 1e-5f, SMX_ACT_IDENTITY, xn, SMX_F32, D, rows, D, st));
+  BW_BUF(p, rows * 2 * D);
+  BW_RUN(lin_fwd(w->bottleneck, xn, D, rows, p, 2 * D, true, 0, 0, nullptr, 1, st));
+  BW_BUF(gl, rows * D);
+  BW_RUN(glu(p, rows, D, gl, st));
+  BW_BUF(c, rows * D);
+  BW_RUN(dwconv(gl, D, w->dw_w, w->dw_b, B, T, D, k, w->causal ? SMX_CONV_CAUSAL : SMX_CONV_SAME_ZERO, 0, c, D, st));
+  BW_BUF(cn, rows * D);
+  BW_RUN(layernorm(c, SMX_F32, D, w->after_ln_w, w->after_ln_b, 1e-5f, SMX_ACT_IDENTITY, cn, SMX_F32, D, rows, D, st));
+  BW_BUF(a, rows * D);
+  BW_RUN(act_fwd(cn, rows, D, act, nullptr, a, st));
+  // backward
+  BW_BUF(dout, rows * D);
+  BW_LAUNCH("mask_rows_kernel", mask_rows_kernel<<<ew_grid(rows * D), 256, 0, st>>>(dy, dy_dt, mask, D, rows * D, dout));
+  if (g->out.dw) SMX_TRY(lin_wgrad(w->out, dout, D, a, D, rows, g->out.dw, 0, 0, ws, st));
+  if (g->out.db) SMX_TRY(colsum_all(dout, D, rows, D, g->out.db, ws, st));
+  float* da = a;  // a is dead
+  BW_RUN(lin_dgrad(w->out, dout, D, rows, da, SMX_F32, D, 0, 0, nullptr, st));
+  BW_RUN(act_bwd(cn, da, SMX_F32, rows, D, act, nullptr, da, st));
+  SMX_TRY(ln_bwd(c, rows, D, w->after_ln_w, da, g->after_ln_dw, g->after_ln_db, ws, st));
+  float* dc = da;
+  if (g->dw_db) SMX_TRY(colsum_all(dc, D, rows, D, g->dw_db, ws, st));
+  if (g->dw_dw) {
+    const int ups = 4, ns = (B + ups - 1) / ups;
+    const size_t m1 = ws.mark();
+    BW_BUF(P, (size_t)ns * D * k);
+    BW_LAUNCH("dwconv_bwd_w_kernel", dwconv_bwd_w_kernel<<<dim3((D + 31) / 32, k, ns), 256, 0, st>>>(dc, gl, B, T, D, k, pad, ups, P));
+    BW_RUN(sum_slices(P, ns, D, k, g->dw_dw, k, st));
+    ws.release(m1);
+  }
+  float* dgl = dout;  // dout is dead
+  BW_LAUNCH("dwconv_bwd_data_kernel", dwconv_bwd_data_kernel<<<ew_grid(rows * D), 256, 0, st>>>(dc, w->dw_w, B, T, D, k, pad, dgl));
+  BW_BUF(dp, rows * 2 * D);
+  BW_LAUNCH("glu_bwd_kernel", glu_bwd_kernel<<<ew_grid(rows * D), 256, 0, st>>>(p, dgl, rows, D, dp));
+  if (g->bottleneck.dw) SMX_TRY(lin_wgrad(w->bottleneck, dp, 2 * D, xn, D, rows, g->bottleneck.dw, 0, 0, ws, st));
+  if (g->bottleneck.db) SMX_TRY(colsum_all(dp, 2 * D, rows, 2 * D, g->bottleneck.db, ws, st));
+  float* dxn = c;  // c is dead (LN_after backward has run)
+  BW_RUN(lin_dgrad(w->bottleneck, dp, 2 * D, rows, dxn, SMX_F32, D, 0, 0, nullptr, st));
+  SMX_TRY(ln_bwd(x32, rows, D, w->ln_w, dxn, g->ln_dw, g->ln_db, ws, st));
+  if (dx) BW_LAUNCH("add_kernel", add_kernel<<<ew_grid(rows * D), 256, 0, st>>>(dxn, nullptr, rows * D, dx, dx_dt));
+  ws.release(m0);
+  return SMX_OK;
+}
+#undef BW_RUN
+#undef BW_BUF
+#undef BW_LAUNCH
 
 }  // namespace smx

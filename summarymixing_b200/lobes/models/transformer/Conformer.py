@@ -15,6 +15,7 @@ import numpy as np
 import torch
 import torch.nn as nn
 
+from .... import _autograd as A
 from .... import _host as H
 from .... import _lib as L
 from ....nnet.activations import Swish
@@ -79,6 +80,12 @@ class ConvolutionModule(nn.Module):
     def params(self):
         return list(self.parameters())
 
+    def grad_params(self):
+        """Parameters in the order smx_convmod_grads lists their gradients."""
+        return [self.layer_norm.weight, self.layer_norm.bias, self.bottleneck[0].weight, self.bottleneck[0].bias,
+                self.conv.weight, self.conv.bias, self.after_conv[0].weight, self.after_conv[0].bias,
+                self.after_conv[2].weight, self.after_conv[2].bias]
+
     def fill(self, cw: L.ConvModWeights, wv: H.WeightView, device) -> None:
         D = self.input_size
         cw.ln_w = wv.ptr(self.layer_norm.weight, device)
@@ -96,7 +103,13 @@ class ConvolutionModule(nn.Module):
     def forward(self, x: torch.Tensor, mask: Optional[torch.Tensor] = None, dynchunktrain_config=None):
         """x: (B,T,D); mask: (B,T,1) or (B,T) in the convention selected by ``masked_false_or_true``."""
         H.require_cuda(x, "ConvolutionModule")
-        H.check_grad_mode(self)
+        grad = A.wants_grad(self, x)
+        if grad:
+            A.refuse_dropout(self, self.after_conv[3].p)
+            if _chunk_size(dynchunktrain_config) > 0:
+                raise NotImplementedError("summarymixing_b200: backward of the Dynamic Chunk Convolution is not implemented")
+        else:
+            H.check_grad_mode(self)
         B, T, D = x.shape
         dev = x.device
         xc = x.contiguous()
@@ -109,6 +122,8 @@ class ConvolutionModule(nn.Module):
             cw = L.ConvModWeights()
             self.fill(cw, self._wv, dev)
             self._wv.struct = cw
+        if grad:
+            return A.ConvModuleFunction.apply(self._wv.struct, self._act_code, xc, m8, *self.grad_params())
         y = torch.empty_like(xc)
         lib = L.lib()
         dt = H.dtype_code(xc)
@@ -218,7 +233,6 @@ class ConformerEncoderLayer(nn.Module):
     ):
         """Returns (x, None) like the reference with SummaryMixing (Conformer.py:527,548)."""
         H.require_cuda(x, "ConformerEncoderLayer")
-        H.check_grad_mode(self)
         B, T, D = x.shape
         dev = x.device
         xc = x.contiguous()
@@ -228,6 +242,11 @@ class ConformerEncoderLayer(nn.Module):
             lw = L.ConformerLayerWeights()
             self.fill(lw, self._wv, dev)
             self._wv.struct = lw
+        if A.wants_grad(self, x):
+            if smask is not None or _chunk_size(dynchunktrain_config) > 0:
+                raise NotImplementedError("summarymixing_b200: backward with sum_mask / dynamic chunk training is not implemented")
+            return self._forward_autograd(xc, mask), None
+        H.check_grad_mode(self)
         y = torch.empty_like(xc)
         lib = L.lib()
         dt = H.dtype_code(xc)
@@ -238,6 +257,28 @@ class ConformerEncoderLayer(nn.Module):
                                                 xc.data_ptr(), H.p_or_none(mask), H.p_or_none(smask), y.data_ptr(),
                                                 ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
         return y, None
+
+
+def _ffn_params(seq: nn.Sequential):
+    ln, pw = seq[0], seq[1]
+    return [ln.weight, ln.bias, pw.ffn[0].weight, pw.ffn[0].bias, pw.ffn[3].weight, pw.ffn[3].bias]
+
+
+def _layer_forward_autograd(self, x, mask):
+    """The layer as a chain of autograd nodes, one per libsmx module call (Conformer.py:518-547, dropout off):
+    FFN half-step -> norm1 -> cell + skip -> conv module + skip -> FFN half-step + norm2."""
+    A.refuse_dropout(self, self.drop.p)
+    lw = self._wv.struct
+    x1 = A.FFNFunction.apply(lw.ffn1, self._act_code, None, x, *_ffn_params(self.ffn_module1))
+    n1 = A.LayerNormFunction.apply(x1, self.norm1.norm.weight, self.norm1.norm.bias, self.norm1.eps)
+    x2 = self.mha_layer(n1, src_padding_mask=mask) + x1
+    x3 = x2 + self.convolution_module(x2, mask)
+    out_norm = (lw.norm2_w, lw.norm2_b, float(self.norm2.eps))
+    return A.FFNFunction.apply(lw.ffn2, self._act_code, out_norm, x3, *_ffn_params(self.ffn_module2),
+                               self.norm2.norm.weight, self.norm2.norm.bias)
+
+
+ConformerEncoderLayer._forward_autograd = _layer_forward_autograd
 
 
 class ConformerEncoder(nn.Module):
@@ -312,6 +353,19 @@ class ConformerEncoder(nn.Module):
         """src: (B,T,d_model).  Returns (output, attention_lst) with attention_lst = [None]*num_layers
         (or (output, hidden_lst, attention_lst) when output_hidden_states), as Conformer.py:821-827."""
         H.require_cuda(src, "ConformerEncoder")
+        if A.wants_grad(self, src):
+            # training path: the layers and the final norm as autograd nodes (Conformer.py:797-821, layerdrop off)
+            if self.training and self.layerdrop_prob > 0:
+                raise NotImplementedError("summarymixing_b200: layerdrop is not implemented (layerdrop_prob must be 0 in training)")
+            out, hidden_lst = src, []
+            for layer in self.layers:
+                out, _ = layer(out, src_mask=src_mask, src_key_padding_mask=src_key_padding_mask,
+                               dynchunktrain_config=dynchunktrain_config)
+                hidden_lst.append(out)
+            out = A.LayerNormFunction.apply(out, self.norm.norm.weight, self.norm.norm.bias, self.norm.eps)
+            if self.output_hidden_states:
+                return out, hidden_lst, [None] * len(self.layers)
+            return out, [None] * len(self.layers)
         H.check_grad_mode(self)  # layerdrop only acts in training (Conformer.py:806-810)
         B, T, D = src.shape
         dev = src.device

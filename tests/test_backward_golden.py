@@ -7,7 +7,6 @@ import numpy as np
 import pytest
 import torch
 
-from oracle import smx_oracle as O
 from tests import _golden as G
 
 BWD_DIR = os.path.join(G.GOLDEN_DIR, "bwd")
@@ -24,17 +23,21 @@ def load_bwd(name):
 
 
 def oracle_grads(fx, dy, dtype=torch.float32):
-    """dx and parameter gradients of the oracle cell on the fixture's input (autograd on the CPU)."""
-    sd = {k: v.to(dtype).clone().requires_grad_(v.is_floating_point()) for k, v in fx.sd.items()}
-    x = fx.x.to(dtype).clone().requires_grad_(True)
-    y = O.summary_mixing(x, sd, mode=fx.cfg["mode"], act=fx.cfg["act"], use_layernorm=fx.cfg["use_layernorm"],
-                         src_padding_mask=fx.mask)
+    """dx and parameter gradients of the oracle on the fixture's input (autograd on the CPU)."""
+    import copy
+
+    from tests.test_oracle_golden import run_oracle
+
+    fx = copy.copy(fx)
+    fx.sd = {k: v.to(dtype).clone().requires_grad_(v.is_floating_point()) for k, v in fx.sd.items()}
+    fx.x = fx.x.to(dtype).clone().requires_grad_(True)
+    y = run_oracle(fx, dtype)
     y.backward(dy.to(dtype))
-    return x.grad, {k: v.grad for k, v in sd.items() if v.grad is not None}
+    return fx.x.grad, {k: v.grad for k, v in fx.sd.items() if v.grad is not None}
 
 
 def test_fixtures_present():
-    assert len(bwd_names()) >= 5
+    assert len(bwd_names()) >= 10
 
 
 @pytest.mark.parametrize("name", bwd_names())
@@ -42,7 +45,7 @@ def test_oracle_autograd_matches_reference_gradients(name):
     fx = G.Fixture(name)
     dy, dx_ref, g_ref = load_bwd(name)
     dx, g = oracle_grads(fx, dy)
-    assert float((dx - dx_ref).abs().max()) <= 1e-5 * max(1.0, float(dx_ref.abs().max()))
+    assert float((dx - dx_ref).abs().max()) <= 2e-5 * max(1.0, float(dx_ref.abs().max()))
     assert set(g_ref) <= set(g)
     for k, v in g_ref.items():
         assert float((g[k] - v).abs().max()) <= 2e-5 * max(1.0, float(v.abs().max())), k

@@ -11,7 +11,7 @@ import torch.nn as nn
 
 from oracle import smx_oracle as O
 from tests import _golden as G
-from tests._build import module_from_fixture
+from tests._build import module_from_fixture, run_module
 from tests.test_backward_golden import bwd_names, load_bwd
 
 pytestmark = pytest.mark.gpu
@@ -29,17 +29,43 @@ def test_backward_matches_reference_gradients(name):
     dy, dx_ref, g_ref = load_bwd(name)
     m = module_from_fixture(fx).to(DEV)
     x = fx.x.to(DEV).requires_grad_(True)
-    mask = None if fx.mask is None else fx.mask.to(DEV)
-    y = m(x, src_padding_mask=mask)
+    y = run_module(m, fx, x, DEV)
     assert y.requires_grad
-    _close(y, fx.y, 1e-4, "forward")
+    enc = fx.cfg["kind"] != "cell"
+    _close(y, fx.y, 5e-4 if enc else 1e-4, "forward")
     y.backward(dy.to(DEV))
-    _close(x.grad, dx_ref, 1e-4, "dx")
+    tol = 3e-4 if enc else 1e-4  # deeper chains: fp32 rounding of more, longer sums
+    _close(x.grad, dx_ref, tol, "dx")
     named = dict(m.named_parameters())
     assert set(g_ref) <= set(named)
     for k, v in g_ref.items():
         assert named[k].grad is not None, k
-        _close(named[k].grad, v, 1e-4, k)
+        _close(named[k].grad, v, tol, k)
+
+
+def test_encoder_training_step_and_eval_path_agree():
+    """Training mode (dropout=0): forward through the autograd chain equals the fused inference call, gradients reach
+    every parameter, and an SGD step changes the output."""
+    import summarymixing_b200 as S
+
+    torch.manual_seed(21)
+    enc = S.ConformerEncoder(2, 64, 128, 4, 31, attention_type="SummaryMixing", local_proj_hid_dim=[64], local_proj_out_dim=64,
+                             summary_hid_dim=[64], dropout=0.0).to(DEV)
+    x = torch.randn(3, 90, 64, device=DEV)
+    mask = (torch.arange(90)[None] < torch.tensor([90, 50, 17])[:, None]).to(DEV)
+    with torch.no_grad():
+        y_eval = enc.eval()(x, src_key_padding_mask=mask)[0]
+    enc.train()
+    y = enc(x, src_key_padding_mask=mask)[0]
+    assert float((y.detach() - y_eval).abs().max()) < 1e-4
+    loss = (y * mask[..., None]).pow(2).mean()
+    loss.backward()
+    assert all(p.grad is not None and torch.isfinite(p.grad).all() for p in enc.parameters())
+    opt = torch.optim.SGD(enc.parameters(), lr=0.05)
+    opt.step()
+    y2 = enc(x, src_key_padding_mask=mask)[0]
+    loss2 = (y2 * mask[..., None]).pow(2).mean()
+    assert float(loss2) < float(loss)
 
 
 def _oracle_grads(m, x, mask, dy, act):
@@ -105,6 +131,9 @@ def test_backward_unsupported_configurations_fail_loudly():
         S.SummaryMixing(64, 4, [64], 64, [64], 64).to(DEV).eval()(x, sum_mask=torch.ones(16, 16, device=DEV))
     with pytest.raises(NotImplementedError, match="dropout"):
         S.SummaryMixing(64, 4, [64], 64, [64], 64).to(DEV).train()(x)
+    with pytest.raises(NotImplementedError, match="dropout"):
+        S.ConformerEncoderLayer(64, 128, 4, attention_type="SummaryMixing", local_proj_hid_dim=[64], local_proj_out_dim=64,
+                                summary_hid_dim=[64], dropout=0.1).to(DEV).train()(x)
 
 
 def test_backward_properties_at_baseline_shape():
