@@ -75,3 +75,53 @@ def test_sharded_forward_equals_unsharded_world2():
         assert shape == (5, 37, 64) or shape[0] == 5
         assert err == 0.0, f"rank {rank}: sharded != unsharded ({err})"
         assert t == 2.0
+
+
+def _grad_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import smx_oracle as O
+        from tests import _golden as G
+
+        fx = G.Fixture("cell_sm_h4_swish")
+        g = torch.Generator().manual_seed(8)
+        B, T, D = 5, 37, fx.cfg["enc_dim"]
+        x = torch.randn(B, T, D, generator=g)
+        lens = torch.tensor([37, 20, 1, 37, 9])
+        mask = torch.arange(T)[None] < lens[:, None]
+
+        def grads(xs, ms):
+            sd = {k: torch.nn.Parameter(v.clone()) for k, v in fx.sd.items()}
+            if xs.shape[0] > 0:
+                y = O.summary_mixing(xs, sd, mode=fx.cfg["mode"], act=fx.cfg["act"], src_padding_mask=ms)
+                (y * ms[..., None]).pow(2).sum().backward()
+            return sd
+
+        full = grads(x, mask)
+        xs, ms = P.shard_batch(x, mask, rank, world)
+        mine = grads(xs, ms)
+        calls = P.allreduce_gradients(list(mine.values()), bucket_bytes=16 << 10)  # small buckets: several collectives
+        err = max(float((mine[k].grad * world - full[k].grad).abs().max() / (1.0 + full[k].grad.abs().max())) for k in full)
+        q.put((rank, err, calls))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_gradient_allreduce_equals_full_batch_gradient_world2():
+    """Data-parallel training plumbing: per-shard gradients averaged by allreduce_gradients x world == the gradient of
+    the whole batch (the loss is a sum over utterances), over several buckets."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_grad_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, calls in res:
+        assert err < 1e-5, f"rank {rank}: averaged shard gradients != full-batch gradient ({err})"
+        assert calls >= 2
