@@ -269,18 +269,16 @@ int lin_wgrad(const smx_linear& L, const float* dZ, int64_t ldz, const float* X,
     }
   } else {
     const int h = L.n_split, a = L.in_dim / h, b = L.out_dim / h;
-    float* P = ws.f32((size_t)ns * a * b);
+    float* P = ws.f32((size_t)ns * h * a * b);  // [slice][head][a][b]
     if (!P) return fail(SMX_ERR_WORKSPACE, "workspace too small (weight gradient)");
-    if (!ws.dry) {
-      for (int hh = 0; hh < h; ++hh) {  // C[i][o] = sum_m X[m, hh*a + i] dZ[m, hh*b + o]
-        GemmP p = bw_gemm();
-        p.A = X + (int64_t)hh * a; p.lda = 1; p.a_sk = ldx; p.a_bs = (int64_t)chunk * ldx;
-        p.W = dZ + (int64_t)hh * b; p.w_sk = ldz; p.w_sn = 1; p.w_bs = (int64_t)chunk * ldz;
-        p.C = P; p.ldc = b; p.c_bs = (int64_t)a * b;
-        p.M = a; p.N = b; p.K = chunk; p.k_total = (int)rows; p.batches = ns;
-        SMX_TRY(gemm(p, st));
-        SMX_TRY(sum_slices(P, ns, a, b, dW + (int64_t)hh * a * b, b, st));
-      }
+    if (!ws.dry) {  // C[head][i][o] = sum_m X[m, head*a + i] dZ[m, head*b + o]: one launch over slices x heads
+      GemmP p = bw_gemm();
+      p.A = X; p.lda = 1; p.a_sk = ldx; p.a_bs = (int64_t)chunk * ldx; p.a_bs2 = a;
+      p.W = dZ; p.w_sk = ldz; p.w_sn = 1; p.w_bs = (int64_t)chunk * ldz; p.w_bs2 = b;
+      p.C = P; p.ldc = b; p.c_bs = (int64_t)h * a * b; p.c_bs2 = (int64_t)a * b;
+      p.M = a; p.N = b; p.K = chunk; p.k_total = (int)rows; p.batches = ns; p.batches2 = h;
+      SMX_TRY(gemm(p, st));
+      SMX_TRY(sum_slices(P, ns, h * a, b, dW, b, st));
     }
   }
   ws.release(m0);

@@ -58,6 +58,8 @@ struct GemmP {
   const void* residual;  int r_dtype;  int64_t ldr;  float alpha; // out = residual + alpha*v
   void* C;  int c_dtype;  int64_t ldc;  int64_t c_bs;
   int M, N, K, batches, act;
+  // optional outer batch level (0 means 1): blockIdx.z = outer * batches + inner; the outer index adds these offsets
+  int batches2;  int64_t a_bs2;  int64_t w_bs2;  int64_t c_bs2;
 };
 int gemm(const GemmP& p, cudaStream_t st);
 int layernorm(const void* x, int x_dtype, int64_t ldx, const float* w, const float* b, float eps, int act,

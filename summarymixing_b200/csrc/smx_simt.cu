@@ -39,12 +39,12 @@ constexpr int BM = 64, BN = 64, BK = 16;
 __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Ws[BK][BN + 4];
-  const int batch = blockIdx.z;
+  const int batch = blockIdx.z % p.batches, outer = blockIdx.z / p.batches;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int tid = threadIdx.x;
   const int tx = tid % 16, ty = tid / 16;
-  const int64_t a_off = (int64_t)batch * p.a_bs;
-  const float* W = p.W + (int64_t)batch * p.w_bs;
+  const int64_t a_off = (int64_t)batch * p.a_bs + (int64_t)outer * p.a_bs2;
+  const float* W = p.W + (int64_t)batch * p.w_bs + (int64_t)outer * p.w_bs2;
   const int64_t ask = p.a_sk ? p.a_sk : 1;
   int K = p.K;
   if (p.k_total > 0) { const int rem = p.k_total - batch * p.K; K = rem < p.K ? rem : p.K; }
@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
   }
 
   const float* bias = p.bias ? p.bias + (int64_t)batch * p.bias_bs : nullptr;
-  const int64_t c_off = (int64_t)batch * p.c_bs;
+  const int64_t c_off = (int64_t)batch * p.c_bs + (int64_t)outer * p.c_bs2;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
     int m = m0 + ty * 4 + i;
@@ -108,9 +108,11 @@ __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
   }
 }
 
+
 int gemm(const GemmP& p, cudaStream_t st) {
   if (p.M <= 0 || p.N <= 0 || p.K <= 0 || p.batches <= 0) return fail(SMX_ERR_BAD_ARG, "gemm: empty problem");
-  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, p.batches);
+  const int nz = p.batches * (p.batches2 > 0 ? p.batches2 : 1);
+  dim3 grid((p.N + BN - 1) / BN, (p.M + BM - 1) / BM, nz);
   if (grid.y > 65535) {  // split rows over several launches
     GemmP q = p;
     const int chunk = 65535 * BM;
