@@ -221,12 +221,13 @@ SMX_API int smx_summary_mixing_fwd(const smx_cell_weights* w, int dtype, int32_t
                            void* workspace, size_t workspace_bytes, void* stream);
 
 /* Gradient of SummaryMixing.forward with respect to x and every parameter — what torch.autograd computes for
- * summary_mixing.py:198-253 (mode "SummaryMixing", whole-utterance mean: sum_mask == None), dropout off.
+ * summary_mixing.py:198-253 (mode "SummaryMixing", whole-utterance mean: sum_mask == None) and :300-324
+ * (mode "SummaryMixing-lite": y and dy are (B,D_s), only grads->summary is written), dropout off.
  * The call is self-contained: it recomputes the forward intermediates from x in fp32 (nothing is saved by
  * smx_summary_mixing_fwd), then back-propagates dy.  x, dy, dx are (B,T,*) in `dtype`; parameter gradients are fp32
  * in the parameters' own layouts (dense (out,in) / ParallelLinear (n_split,in/n_split,out/n_split)), OVERWRITTEN,
  * not accumulated; any gradient pointer may be NULL (not wanted).  dx may be NULL.
- * Other modes and sum_mask != None: SMX_ERR_UNSUPPORTED. */
+ * Modes -fast / -expdecay and sum_mask != None: SMX_ERR_UNSUPPORTED. */
 typedef struct {
   float* dw;
   float* db;

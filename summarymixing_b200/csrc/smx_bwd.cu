@@ -379,10 +379,43 @@ int branch_bwd(const smx_linear* blocks, const smx_linear_grad* g, int n, int ac
 
 int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int x_dt, const uint8_t* mask, const void* dy, int dy_dt,
                      void* dx, int dx_dt, const smx_cell_grads* g, Arena& ws, cudaStream_t st) {
-  if (w->mode != SMX_MODE_FULL)
-    return fail(SMX_ERR_UNSUPPORTED, "smx_summary_mixing_bwd handles mode 'SummaryMixing' only (got mode %d)", w->mode);
+  if (w->mode != SMX_MODE_FULL && w->mode != SMX_MODE_LITE)
+    return fail(SMX_ERR_UNSUPPORTED, "smx_summary_mixing_bwd handles modes 'SummaryMixing' and 'SummaryMixing-lite' (got mode %d)", w->mode);
   const int64_t rows = (int64_t)B * T;
   if (rows > 0x7fffffff) return fail(SMX_ERR_UNSUPPORTED, "cell backward: more than 2^31 frames");
+  if (w->mode == SMX_MODE_LITE) {
+    // y[b] = sum_t (s(x)[b,t] * mask) / count_b  (summary_mixing.py:300-324; y and dy are (B, D_s): the caller owns the
+    // stride-0 expand over T and its gradient).  dS[b,t] = dy[b] / count_b, then the MLP backward of summary_proj.
+    const int D = w->enc_dim, Ds = w->summary_out_dim, nsm = w->n_summary;
+    if (nsm < 1 || nsm > SMX_MAX_BLOCKS || w->summary[0].in_dim != D || w->summary[nsm - 1].out_dim != Ds)
+      return fail(SMX_ERR_BAD_ARG, "cell backward (lite): summary_proj dims");
+    const size_t m0 = ws.mark();
+    const float* x32 = (const float*)x;
+    if (x_dt != SMX_F32) {
+      float* xc = ws.f32((size_t)rows * D);
+      if (!xc) return fail(SMX_ERR_WORKSPACE, "workspace too small (cell backward)");
+      if (!ws.dry) SMX_TRY(convert(x, x_dt, xc, SMX_F32, rows * D, st));
+      x32 = xc;
+    }
+    BranchFwd fs{};
+    SMX_TRY(branch_fwd(w->summary, nsm, w->act, x32, rows, mask, fs, ws, st));
+    float* dy32 = ws.f32((size_t)B * Ds);
+    float* inv = ws.f32((size_t)B);
+    float* dS = ws.f32((size_t)rows * Ds);
+    if (!dy32 || !inv || !dS) return fail(SMX_ERR_WORKSPACE, "workspace too small (cell backward)");
+    if (!ws.dry) {
+      SMX_TRY(convert(dy, dy_dt, dy32, SMX_F32, (int64_t)B * Ds, st));
+      inv_count_kernel<<<B, 32, 0, st>>>(mask, T, inv);
+      count_launch();
+      SMX_TRY(check_launch("inv_count_kernel"));
+      bcast_scale_kernel<<<ew_grid(rows * Ds), 256, 0, st>>>(dy32, inv, T, Ds, rows * Ds, dS);
+      count_launch();
+      SMX_TRY(check_launch("bcast_scale_kernel"));
+    }
+    SMX_TRY(branch_bwd(w->summary, g->summary, nsm, w->act, fs, rows, mask, dS, dx, dx_dt, nullptr, dx != nullptr, ws, st));
+    ws.release(m0);
+    return SMX_OK;
+  }
   const int D = w->enc_dim, Dl = w->local_out_dim, Ds = w->summary_out_dim, Dout = w->merge.out_dim;
   const int nl = w->n_local, nsm = w->n_summary, act = w->act;
   if (nl < 1 || nl > SMX_MAX_BLOCKS || nsm < 1 || nsm > SMX_MAX_BLOCKS) return fail(SMX_ERR_BAD_ARG, "cell backward: block counts");

@@ -166,19 +166,23 @@ class SummaryMixing(nn.Module):
         mask = H.mask_u8(src_padding_mask, B, T, dev)
         smask = H.sum_mask_f32(sum_mask, T, dev)
         if torch.is_grad_enabled() and (x.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
-            if self.mode != "SummaryMixing" or smask is not None:
+            lite = self.mode == "SummaryMixing-lite"  # (lite ignores sum_mask, summary_mixing.py:300-324)
+            if not (lite or (self.mode == "SummaryMixing" and smask is None)):
                 raise NotImplementedError(
-                    "summarymixing_b200: backward is implemented for mode 'SummaryMixing' without sum_mask only; "
-                    "wrap other configurations in torch.no_grad()")
+                    "summarymixing_b200: backward is implemented for modes 'SummaryMixing' (without sum_mask) and "
+                    "'SummaryMixing-lite' only; wrap other configurations in torch.no_grad()")
             if self.training and self.dropout.p > 0:
                 raise NotImplementedError(
                     "summarymixing_b200: training-mode dropout is not implemented (set global_dropout=0 or call .eval())")
-            return _CellFunction.apply(self, x, mask, *self.grad_params())
+            y = _CellFunction.apply(self, x, mask, *self.grad_params())
+            return y.unsqueeze(1).expand(-1, T, -1) if lite else y
         H.check_grad_mode(self)
         return self._forward_impl(x, mask, smask)
 
     def grad_params(self):
         """Parameters in the order smx_cell_grads lists their gradients (mode "SummaryMixing")."""
+        if self.mode == "SummaryMixing-lite":
+            return self.summary_proj.params()
         out = self.local_proj.params() + self.summary_proj.params() + self.summary_local_merging.params()
         if self.use_layernorm:
             out += [self.local_norm.weight, self.local_norm.bias, self.summary_norm.weight, self.summary_norm.bias]
@@ -191,7 +195,7 @@ class SummaryMixing(nn.Module):
             self._wv.struct = cw
         return self._wv.struct
 
-    def _forward_impl(self, x, mask, smask):
+    def _forward_impl(self, x, mask, smask, expand_lite=True):
         B, T, _ = x.shape
         dev = x.device
         xc = x.contiguous()
@@ -206,7 +210,7 @@ class SummaryMixing(nn.Module):
             L.check(lib.smx_summary_mixing_fwd(cw, dt, B, T, xc.data_ptr(), H.p_or_none(mask),
                                                H.p_or_none(smask), None, y.data_ptr(), ws.data_ptr(), ws.numel(),
                                                H.stream_ptr(dev)))
-        if lite:
+        if lite and expand_lite:
             return y.unsqueeze(1).expand(-1, T, -1)
         return y
 
@@ -220,13 +224,16 @@ class SummaryMixing(nn.Module):
         grads = [torch.empty(p.shape, dtype=torch.float32, device=dev) for p in plist]
         cg = L.CellGrads()
         it = iter(grads)
-        for dst, net in ((cg.local, self.local_proj), (cg.summary, self.summary_proj)):
+        lite = self.mode == "SummaryMixing-lite"
+        nets = ((cg.summary, self.summary_proj),) if lite else ((cg.local, self.local_proj), (cg.summary, self.summary_proj))
+        for dst, net in nets:
             for i in range(len(net._linears)):
                 dst[i].dw = next(it).data_ptr()
                 dst[i].db = next(it).data_ptr()
-        cg.merge.dw = next(it).data_ptr()
-        cg.merge.db = next(it).data_ptr()
-        if self.use_layernorm:
+        if not lite:
+            cg.merge.dw = next(it).data_ptr()
+            cg.merge.db = next(it).data_ptr()
+        if self.use_layernorm and not lite:
             cg.local_norm_dw, cg.local_norm_db = next(it).data_ptr(), next(it).data_ptr()
             cg.summary_norm_dw, cg.summary_norm_db = next(it).data_ptr(), next(it).data_ptr()
         dx = torch.empty_like(xc) if want_dx else None
@@ -248,7 +255,7 @@ class _CellFunction(torch.autograd.Function):
     def forward(ctx, module, x, mask, *params):
         ctx.module = module
         ctx.save_for_backward(x, mask)
-        return module._forward_impl(x, mask, None)
+        return module._forward_impl(x, mask, None, expand_lite=False)
 
     @staticmethod
     def backward(ctx, dy):
