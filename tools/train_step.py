@@ -31,6 +31,8 @@ def main():
     ap.add_argument("--T", type=int, default=1000)
     ap.add_argument("--D", type=int, default=256)
     ap.add_argument("--dtype", default="fp32", choices=["fp32", "bf16"])
+    ap.add_argument("--ddp", action="store_true", help="wrap the encoder in torch DistributedDataParallel (what SpeechBrain's "
+                    "Brain does) instead of calling parallel.allreduce_gradients")
     a = ap.parse_args()
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -43,6 +45,9 @@ def main():
     enc = S.ConformerEncoder(a.layers, a.D, 4 * a.D, 4, 31, attention_type="SummaryMixing", local_proj_hid_dim=[a.D],
                              local_proj_out_dim=a.D, summary_hid_dim=[a.D], dropout=0.0).to(dev).train()
     params = list(enc.parameters())
+    model = enc
+    if a.ddp and world > 1:
+        model = torch.nn.parallel.DistributedDataParallel(enc, device_ids=[local])
     opt = torch.optim.SGD(params, lr=0.02)
     g = torch.Generator().manual_seed(100 + rank)  # a different batch on every rank
     dt = torch.float32 if a.dtype == "fp32" else torch.bfloat16
@@ -61,10 +66,10 @@ def main():
             n0 = L.lib().smx_launch_count()
             ev0.record()
         opt.zero_grad(set_to_none=True)
-        y = enc(x, src_key_padding_mask=mask)[0]
+        y = model(x, src_key_padding_mask=mask)[0]
         loss = ((y.float() - target) * mask[..., None]).pow(2).mean()
         loss.backward()
-        calls = P.allreduce_gradients(params)
+        calls = -1 if model is not enc else P.allreduce_gradients(params)  # (-1: DDP's own bucketed all-reduce)
         opt.step()
         losses.append(float(loss.detach()))
     ev1.record()
