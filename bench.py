@@ -387,9 +387,9 @@ def run_smx(args):
                             "bound": "hbm", "achieved": bytes_cell / us / 1e3, "peak": pk["hbm_gbs"], "unit": "GB/s",
                             "frac": bytes_cell / us / 1e3 / pk["hbm_gbs"],
                             # dram__bytes_read+write per cell call from the ncu --set full capture summarised in
-                            # profiles/r01_call80_ncu_layer_summary.csv (pass A 16.54 MB + finalise 0.58 MB + pass B 16.73 MB
-                            # read, 0.30 MB written: most of the 16.4 MB output was still in L2 when the window closed)
-                            "traffic": 34.15e6, "algorithmic_bytes": bytes_cell,
+                            # profiles/r01_call117_ncu_layer_summary.csv (pass A 16.53 MB + finalise 0.58 MB + pass B 16.73 MB
+                            # read, 0.23 MB written: most of the 16.4 MB output was still in L2 when the window closed)
+                            "traffic": 34.08e6, "algorithmic_bytes": bytes_cell,
                             "us_per_call": us, "peak_source": pk["source"] + " (burst copy)",
                             "tensor_tflops": flops_cell / us / 1e6, "tensor_frac": flops_cell / us / 1e6 / pk["bf16_tflops"]}
         flops_ffn = frames * 4 * D * FFN
