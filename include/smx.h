@@ -222,12 +222,13 @@ SMX_API int smx_summary_mixing_fwd(const smx_cell_weights* w, int dtype, int32_t
 
 /* Gradient of SummaryMixing.forward with respect to x and every parameter — what torch.autograd computes for
  * summary_mixing.py:198-253 (mode "SummaryMixing", whole-utterance mean: sum_mask == None) and :300-324
- * (mode "SummaryMixing-lite": y and dy are (B,D_s), only grads->summary is written), dropout off.
+ * (mode "SummaryMixing-lite": y and dy are (B,D_s), only grads->summary is written) and :255-298 (mode
+ * "SummaryMixing-fast": grads->global_proj and grads->merge), dropout off.
  * The call is self-contained: it recomputes the forward intermediates from x in fp32 (nothing is saved by
  * smx_summary_mixing_fwd), then back-propagates dy.  x, dy, dx are (B,T,*) in `dtype`; parameter gradients are fp32
  * in the parameters' own layouts (dense (out,in) / ParallelLinear (n_split,in/n_split,out/n_split)), OVERWRITTEN,
  * not accumulated; any gradient pointer may be NULL (not wanted).  dx may be NULL.
- * Modes -fast / -expdecay and sum_mask != None: SMX_ERR_UNSUPPORTED. */
+ * Mode -expdecay and sum_mask != None: SMX_ERR_UNSUPPORTED. */
 typedef struct {
   float* dw;
   float* db;
@@ -240,6 +241,7 @@ typedef struct {
   float* local_norm_db;
   float* summary_norm_dw;
   float* summary_norm_db;
+  smx_linear_grad global_proj; /* mode "SummaryMixing-fast" (summary_mixing.py:133-140) */
 } smx_cell_grads;
 SMX_API size_t smx_summary_mixing_bwd_workspace_bytes(const smx_cell_weights* w, int dtype, int32_t B, int32_t T);
 SMX_API int smx_summary_mixing_bwd(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x,

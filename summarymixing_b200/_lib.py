@@ -48,7 +48,8 @@ class LinearGrad(C.Structure):
 
 class CellGrads(C.Structure):
     _fields_ = [("local", LinearGrad * SMX_MAX_BLOCKS), ("summary", LinearGrad * SMX_MAX_BLOCKS), ("merge", LinearGrad),
-                ("local_norm_dw", fp), ("local_norm_db", fp), ("summary_norm_dw", fp), ("summary_norm_db", fp)]
+                ("local_norm_dw", fp), ("local_norm_db", fp), ("summary_norm_dw", fp), ("summary_norm_db", fp),
+                ("global_proj", LinearGrad)]
 
 
 class FFNGrads(C.Structure):

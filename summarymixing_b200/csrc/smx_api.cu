@@ -180,6 +180,7 @@ static void all_grads_wanted(smx_cell_grads& g) {
   for (int i = 0; i < SMX_MAX_BLOCKS; ++i) { g.local[i] = {dummy, dummy}; g.summary[i] = {dummy, dummy}; }
   g.merge = {dummy, dummy};
   g.local_norm_dw = g.local_norm_db = g.summary_norm_dw = g.summary_norm_db = dummy;
+  g.global_proj = {dummy, dummy};
 }
 size_t smx_summary_mixing_bwd_workspace_bytes(const smx_cell_weights* w, int dtype, int32_t B, int32_t T) {
   if (!w || B <= 0 || T <= 0) return 0;

@@ -172,11 +172,12 @@ __global__ void inv_count_kernel(const uint8_t* mask, int T, float* inv) {
 }
 
 // dst[(b*T + t)*D + d] = src[b*D + d] * inv[b]   (gradient of the mean, broadcast back over the frames)
-__global__ void __launch_bounds__(256) bcast_scale_kernel(const float* src, const float* inv, int T, int D, int64_t n, float* dst) {
+__global__ void __launch_bounds__(256) bcast_scale_kernel(const float* src, const float* inv, int T, int D, int64_t n, float* dst,
+                                                          int64_t ldd = 0) {
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
     const int64_t row = i / D;
     const int b = (int)(row / T), d = (int)(i % D);
-    dst[i] = src[(int64_t)b * D + d] * inv[b];
+    dst[ldd ? row * ldd + d : i] = src[(int64_t)b * D + d] * inv[b];
   }
 }
 
@@ -379,10 +380,64 @@ int branch_bwd(const smx_linear* blocks, const smx_linear_grad* g, int n, int ac
 
 int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int x_dt, const uint8_t* mask, const void* dy, int dy_dt,
                      void* dx, int dx_dt, const smx_cell_grads* g, Arena& ws, cudaStream_t st) {
-  if (w->mode != SMX_MODE_FULL && w->mode != SMX_MODE_LITE)
-    return fail(SMX_ERR_UNSUPPORTED, "smx_summary_mixing_bwd handles modes 'SummaryMixing' and 'SummaryMixing-lite' (got mode %d)", w->mode);
+  if (w->mode != SMX_MODE_FULL && w->mode != SMX_MODE_LITE && w->mode != SMX_MODE_FAST)
+    return fail(SMX_ERR_UNSUPPORTED, "smx_summary_mixing_bwd does not handle mode %d ('SummaryMixing-expdecay')", w->mode);
   const int64_t rows = (int64_t)B * T;
   if (rows > 0x7fffffff) return fail(SMX_ERR_UNSUPPORTED, "cell backward: more than 2^31 frames");
+  if (w->mode == SMX_MODE_FAST) {
+    // G = act(W_g x + b_g) * mask (rows, 2 D_l); local = G[:, :D_l], S = G[:, D_l:]; mean_b = sum_t S / count_b;
+    // y = act(local Wc[:, :D_l]^T + mean_b Wc[:, D_l:]^T + b_c); no LayerNorms            summary_mixing.py:255-298
+    const int D = w->enc_dim, Dl = w->local_out_dim, Dout = w->merge.out_dim, act = w->act;
+    if (w->global_proj.in_dim != D || w->global_proj.out_dim != 2 * Dl || w->global_proj.n_split > 1 || w->merge.in_dim != 2 * Dl ||
+        w->merge.n_split > 1)
+      return fail(SMX_ERR_BAD_ARG, "cell backward (fast): global_proj must be dense D -> 2*D_l and the merger 2*D_l -> D_s");
+    const size_t m0 = ws.mark();
+#define BWF_BUF(name, n) float* name = ws.f32((size_t)(n)); if (!name) return fail(SMX_ERR_WORKSPACE, "workspace too small (cell backward)")
+    const float* x32 = (const float*)x;
+    if (x_dt != SMX_F32) {
+      BWF_BUF(xc, rows * D);
+      if (!ws.dry) SMX_TRY(convert(x, x_dt, xc, SMX_F32, rows * D, st));
+      x32 = xc;
+    }
+    BranchFwd fg{};
+    SMX_TRY(branch_fwd(&w->global_proj, 1, act, x32, rows, mask, fg, ws, st));
+    const float* G = fg.a[1];
+    BWF_BUF(mean, (size_t)B * Dl);
+    BWF_BUF(cbias, (size_t)B * Dout);
+    BWF_BUF(zc, rows * Dout);
+    BWF_BUF(dcb, (size_t)B * Dout);
+    BWF_BUF(dG, rows * 2 * Dl);
+    BWF_BUF(dmean, (size_t)B * Dl);
+    BWF_BUF(inv, (size_t)B);
+    if (!ws.dry) {
+      SMX_TRY(masked_mean(G + Dl, 2 * Dl, mask, B, T, Dl, mean, SMX_F32, st));
+      SMX_TRY(lin_fwd(w->merge, mean, Dl, B, cbias, Dout, true, Dl, Dl, nullptr, 1, st));
+      SMX_TRY(lin_fwd(w->merge, G, 2 * Dl, rows, zc, Dout, false, 0, Dl, cbias, T, st));
+      SMX_TRY(act_bwd(zc, dy, dy_dt, rows, Dout, act, nullptr, zc, st));  // zc now holds dzc
+      colsum_kernel<<<dim3((Dout + 31) / 32, B), 256, 0, st>>>(zc, Dout, rows, T, Dout, dcb);
+      count_launch();
+      SMX_TRY(check_launch("colsum_kernel"));
+    }
+    if (g->merge.dw) {
+      SMX_TRY(lin_wgrad(w->merge, zc, Dout, G, 2 * Dl, rows, g->merge.dw, 0, Dl, ws, st));
+      SMX_TRY(lin_wgrad(w->merge, dcb, Dout, mean, Dl, B, g->merge.dw, Dl, Dl, ws, st));
+    }
+    if (g->merge.db) SMX_TRY(colsum_all(dcb, Dout, B, Dout, g->merge.db, ws, st));
+    if (!ws.dry) {
+      SMX_TRY(lin_dgrad(w->merge, zc, Dout, rows, dG, SMX_F32, 2 * Dl, 0, Dl, nullptr, st));      // dG[:, :D_l]
+      SMX_TRY(lin_dgrad(w->merge, dcb, Dout, B, dmean, SMX_F32, Dl, Dl, Dl, nullptr, st));
+      inv_count_kernel<<<B, 32, 0, st>>>(mask, T, inv);
+      count_launch();
+      SMX_TRY(check_launch("inv_count_kernel"));
+      bcast_scale_kernel<<<ew_grid(rows * Dl), 256, 0, st>>>(dmean, inv, T, Dl, rows * Dl, dG + Dl, 2 * Dl);  // dG[:, D_l:]
+      count_launch();
+      SMX_TRY(check_launch("bcast_scale_kernel"));
+    }
+    SMX_TRY(branch_bwd(&w->global_proj, &g->global_proj, 1, act, fg, rows, mask, dG, dx, dx_dt, nullptr, dx != nullptr, ws, st));
+#undef BWF_BUF
+    ws.release(m0);
+    return SMX_OK;
+  }
   if (w->mode == SMX_MODE_LITE) {
     // y[b] = sum_t (s(x)[b,t] * mask) / count_b  (summary_mixing.py:300-324; y and dy are (B, D_s): the caller owns the
     // stride-0 expand over T and its gradient).  dS[b,t] = dy[b] / count_b, then the MLP backward of summary_proj.

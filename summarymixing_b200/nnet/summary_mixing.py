@@ -167,10 +167,10 @@ class SummaryMixing(nn.Module):
         smask = H.sum_mask_f32(sum_mask, T, dev)
         if torch.is_grad_enabled() and (x.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
             lite = self.mode == "SummaryMixing-lite"  # (lite ignores sum_mask, summary_mixing.py:300-324)
-            if not (lite or (self.mode == "SummaryMixing" and smask is None)):
+            if not (lite or (self.mode in ("SummaryMixing", "SummaryMixing-fast") and smask is None)):
                 raise NotImplementedError(
-                    "summarymixing_b200: backward is implemented for modes 'SummaryMixing' (without sum_mask) and "
-                    "'SummaryMixing-lite' only; wrap other configurations in torch.no_grad()")
+                    "summarymixing_b200: backward is implemented for modes 'SummaryMixing', 'SummaryMixing-fast' (both without "
+                    "sum_mask) and 'SummaryMixing-lite' only; wrap other configurations in torch.no_grad()")
             if self.training and self.dropout.p > 0:
                 raise NotImplementedError(
                     "summarymixing_b200: training-mode dropout is not implemented (set global_dropout=0 or call .eval())")
@@ -183,6 +183,8 @@ class SummaryMixing(nn.Module):
         """Parameters in the order smx_cell_grads lists their gradients (mode "SummaryMixing")."""
         if self.mode == "SummaryMixing-lite":
             return self.summary_proj.params()
+        if self.mode == "SummaryMixing-fast":
+            return self.global_proj.params() + self.summary_local_merging.params()
         out = self.local_proj.params() + self.summary_proj.params() + self.summary_local_merging.params()
         if self.use_layernorm:
             out += [self.local_norm.weight, self.local_norm.bias, self.summary_norm.weight, self.summary_norm.bias]
@@ -224,8 +226,15 @@ class SummaryMixing(nn.Module):
         grads = [torch.empty(p.shape, dtype=torch.float32, device=dev) for p in plist]
         cg = L.CellGrads()
         it = iter(grads)
-        lite = self.mode == "SummaryMixing-lite"
-        nets = ((cg.summary, self.summary_proj),) if lite else ((cg.local, self.local_proj), (cg.summary, self.summary_proj))
+        lite, fast = self.mode == "SummaryMixing-lite", self.mode == "SummaryMixing-fast"
+        if fast:
+            nets = ()
+            cg.global_proj.dw = next(it).data_ptr()
+            cg.global_proj.db = next(it).data_ptr()
+        elif lite:
+            nets = ((cg.summary, self.summary_proj),)
+        else:
+            nets = ((cg.local, self.local_proj), (cg.summary, self.summary_proj))
         for dst, net in nets:
             for i in range(len(net._linears)):
                 dst[i].dw = next(it).data_ptr()
@@ -233,7 +242,7 @@ class SummaryMixing(nn.Module):
         if not lite:
             cg.merge.dw = next(it).data_ptr()
             cg.merge.db = next(it).data_ptr()
-        if self.use_layernorm and not lite:
+        if self.use_layernorm and not lite and not fast:
             cg.local_norm_dw, cg.local_norm_db = next(it).data_ptr(), next(it).data_ptr()
             cg.summary_norm_dw, cg.summary_norm_db = next(it).data_ptr(), next(it).data_ptr()
         dx = torch.empty_like(xc) if want_dx else None

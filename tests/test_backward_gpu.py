@@ -126,7 +126,7 @@ def test_backward_unsupported_configurations_fail_loudly():
 
     x = torch.randn(2, 16, 64, device=DEV, requires_grad=True)
     with pytest.raises(NotImplementedError, match="backward"):
-        S.SummaryMixing(64, 4, [64], 64, [64], 64, mode="SummaryMixing-fast").to(DEV).eval()(x)
+        S.SummaryMixing(64, 4, [64], 64, [64], 64, mode="SummaryMixing-expdecay").to(DEV).eval()(x)
     with pytest.raises(NotImplementedError, match="backward"):
         S.SummaryMixing(64, 4, [64], 64, [64], 64).to(DEV).eval()(x, sum_mask=torch.ones(16, 16, device=DEV))
     with pytest.raises(NotImplementedError, match="dropout"):
