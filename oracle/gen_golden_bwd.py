@@ -35,7 +35,7 @@ from tests import _golden as G  # noqa: E402
 ACTS = {"swish": Swish, "gelu": nn.GELU, "relu": nn.ReLU, "leaky_relu": nn.LeakyReLU}
 CASES = ["cell_sm_h4_swish", "cell_sm_h1_gelu", "cell_sm_h4_relu_noln_deep_nomask", "cell_reftest_sm_h4", "cell_sm_h4_gelu", "cell_sm_lite_h4_gelu", "cell_sm_lite_h1_gelu",
          "convmod_plain", "convmod_causal", "conformer_layer", "conformer_enc_sm_h4", "conformer_enc_sm_h1_gelu",
-         "cell_sm_fast_h4_swish", "cell_sm_fast_h1_gelu"]
+         "cell_sm_fast_h4_swish", "cell_sm_fast_h1_gelu", "conformer_enc_lite_h4"]
 OUT = os.path.join(ROOT, "tests", "golden", "bwd")
 
 
