@@ -272,6 +272,11 @@ typedef struct {
   float* after_ln_db;
   smx_linear_grad out;
 } smx_convmod_grads;
+/* VanillaNN backward (VanillaNN.py:168-196): grads[i] = gradients of block i, n_blocks entries. */
+SMX_API size_t smx_vanilla_nn_bwd_workspace_bytes(const smx_linear* blocks, int32_t n_blocks, int dtype, int64_t rows);
+SMX_API int smx_vanilla_nn_bwd(const smx_linear* blocks, int32_t n_blocks, int act, int dtype, int64_t rows, const void* x,
+                       const void* dy, void* dx, const smx_linear_grad* grads, void* workspace, size_t workspace_bytes,
+                       void* stream);
 SMX_API size_t smx_layernorm_bwd_workspace_bytes(int dtype, int64_t rows, int32_t D);
 SMX_API int smx_layernorm_bwd(int dtype, int64_t rows, int32_t D, const void* x, const float* w, float eps, const void* dy,
                       void* dx, float* dw, float* db, void* workspace, size_t workspace_bytes, void* stream);

@@ -25,6 +25,7 @@ sys.path.insert(0, ROOT)
 
 from speechbrain.nnet.activations import Swish  # noqa: E402
 from speechbrain.nnet.summary_mixing import SummaryMixing  # noqa: E402
+from speechbrain.lobes.models.VanillaNN import VanillaNN  # noqa: E402
 from speechbrain.lobes.models.transformer.Conformer import (  # noqa: E402
     ConformerEncoder,
     ConformerEncoderLayer,
@@ -35,7 +36,7 @@ from tests import _golden as G  # noqa: E402
 ACTS = {"swish": Swish, "gelu": nn.GELU, "relu": nn.ReLU, "leaky_relu": nn.LeakyReLU}
 CASES = ["cell_sm_h4_swish", "cell_sm_h1_gelu", "cell_sm_h4_relu_noln_deep_nomask", "cell_reftest_sm_h4", "cell_sm_h4_gelu", "cell_sm_lite_h4_gelu", "cell_sm_lite_h1_gelu",
          "convmod_plain", "convmod_causal", "conformer_layer", "conformer_enc_sm_h4", "conformer_enc_sm_h1_gelu",
-         "cell_sm_fast_h4_swish", "cell_sm_fast_h1_gelu", "conformer_enc_lite_h4"]
+         "cell_sm_fast_h4_swish", "cell_sm_fast_h1_gelu", "conformer_enc_lite_h4", "vanilla_split1", "vanilla_split3"]
 OUT = os.path.join(ROOT, "tests", "golden", "bwd")
 
 
@@ -49,6 +50,10 @@ def main():
             sm = SummaryMixing(c["enc_dim"], c["nhead"], c["local_proj_hid_dim"], c["local_proj_out_dim"], c["summary_hid_dim"],
                                c["summary_out_dim"], activation=ACTS[c["act"]], mode=c["mode"], use_layernorm=c["use_layernorm"])
             run = (lambda m, x: m(x, src_padding_mask=fx.mask)) if fx.mask is not None else (lambda m, x: m(x))
+        elif k == "vanilla":
+            sm = VanillaNN(input_shape=[None, None, c["input_size"]], activation=ACTS[c["act"]], dnn_blocks=len(c["dnn_neurons"]),
+                           dnn_neurons=c["dnn_neurons"], n_split=c["n_split"])
+            run = lambda m, x: m(x)  # noqa: E731
         elif k == "conv_module":
             sm = ConvolutionModule(c["input_size"], c["kernel_size"], True, ACTS[c["act"]], 0.0, causal=c["causal"],
                                    masked_false_or_true=False)

@@ -152,3 +152,46 @@ class ConvModuleFunction(torch.autograd.Function):
             L.check(lib.smx_conv_module_bwd(C.byref(ctx.cw), ctx.act, dt, B, T, xc.data_ptr(), H.p_or_none(m8), dyc.data_ptr(),
                                             H.p_or_none(dx), C.byref(cg), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
         return (None, None, dx, None, *_cast_out(ctx, 4, grads, ctx.params))
+
+
+class VanillaNNFunction(torch.autograd.Function):
+    """n x (linear, act) (VanillaNN / ParallelLinear): smx_vanilla_nn_fwd / smx_vanilla_nn_bwd.  params = [W0, b0, W1, b1, ...]."""
+
+    @staticmethod
+    def forward(ctx, blocks, n, act, out_dim, x, *params):
+        xc = x.contiguous()
+        B, T = xc.shape[0], xc.shape[1]
+        xc = xc.reshape(B, T, -1)
+        dev = xc.device
+        y = torch.empty(B, T, out_dim, dtype=xc.dtype, device=dev)
+        lib = L.lib()
+        dt = H.dtype_code(xc)
+        rows = B * T
+        with torch.cuda.device(dev):
+            ws = H.workspace(dev, lib.smx_vanilla_nn_workspace_bytes(blocks, n, dt, rows))
+            L.check(lib.smx_vanilla_nn_fwd(blocks, n, act, dt, rows, xc.data_ptr(), y.data_ptr(), ws.data_ptr(), ws.numel(),
+                                           H.stream_ptr(dev)))
+        ctx.blocks, ctx.n, ctx.act, ctx.params, ctx.x_shape = blocks, n, act, params, x.shape
+        ctx.save_for_backward(xc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xc,) = ctx.saved_tensors
+        dev = xc.device
+        dyc = dy.contiguous()
+        rows = xc.shape[0] * xc.shape[1]
+        grads = _new_grads(ctx.params, dev)
+        lg = (L.LinearGrad * L.SMX_MAX_BLOCKS)()
+        for i in range(ctx.n):
+            lg[i].dw, lg[i].db = grads[2 * i].data_ptr(), grads[2 * i + 1].data_ptr()
+        dx = torch.empty_like(xc) if ctx.needs_input_grad[4] else None
+        lib = L.lib()
+        dt = H.dtype_code(xc)
+        with torch.cuda.device(dev):
+            ws = H.workspace(dev, lib.smx_vanilla_nn_bwd_workspace_bytes(ctx.blocks, ctx.n, dt, rows))
+            L.check(lib.smx_vanilla_nn_bwd(ctx.blocks, ctx.n, ctx.act, dt, rows, xc.data_ptr(), dyc.data_ptr(), H.p_or_none(dx), lg,
+                                           ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+        if dx is not None:
+            dx = dx.reshape(ctx.x_shape)
+        return (None, None, None, None, dx, *_cast_out(ctx, 5, grads, ctx.params))

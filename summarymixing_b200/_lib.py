@@ -117,6 +117,8 @@ _PROTOS = {
     "smx_summary_mixing_bwd_workspace_bytes": (_sz, [C.POINTER(CellWeights), _i, _i, _i]),
     "smx_summary_mixing_bwd": (_i, [C.POINTER(CellWeights), _i, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(CellGrads), _vp, _sz,
                                     _vp]),
+    "smx_vanilla_nn_bwd_workspace_bytes": (_sz, [C.POINTER(Linear), _i, _i, _i64]),
+    "smx_vanilla_nn_bwd": (_i, [C.POINTER(Linear), _i, _i, _i, _i64, _vp, _vp, _vp, C.POINTER(LinearGrad), _vp, _sz, _vp]),
     "smx_layernorm_bwd_workspace_bytes": (_sz, [_i, _i64, _i]),
     "smx_layernorm_bwd": (_i, [_i, _i64, _i, _vp, _vp, _f, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "smx_ffn_bwd_workspace_bytes": (_sz, [C.POINTER(FFNWeights), _i, _i64, _i]),

@@ -211,6 +211,29 @@ int smx_summary_mixing_bwd(const smx_cell_weights* w, int dtype, int32_t B, int3
 
 // ---- LayerNorm / FFN / conv module, backward ------------------------------------------------------
 static float* const kDummy = (float*)(uintptr_t)256;  // sizing runs only: never dereferenced
+size_t smx_vanilla_nn_bwd_workspace_bytes(const smx_linear* blocks, int32_t n_blocks, int dtype, int64_t rows) {
+  if (!blocks || n_blocks < 1 || n_blocks > SMX_MAX_BLOCKS || rows <= 0) return 0;
+  smx_linear_grad g[SMX_MAX_BLOCKS];
+  for (int i = 0; i < SMX_MAX_BLOCKS; ++i) g[i] = {kDummy, kDummy};
+  Arena a(nullptr, 0, true);
+  if (vanilla_bwd_generic(blocks, n_blocks, 0, rows, nullptr, dtype, nullptr, dtype, kDummy, dtype, g, a, nullptr) != SMX_OK) return 0;
+  return a.peak;
+}
+int smx_vanilla_nn_bwd(const smx_linear* blocks, int32_t n_blocks, int act, int dtype, int64_t rows, const void* x, const void* dy,
+                       void* dx, const smx_linear_grad* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  if (!blocks || !grads) return fail(SMX_ERR_BAD_ARG, "blocks or grads is NULL");
+  if (rows <= 0) return fail(SMX_ERR_BAD_ARG, "rows must be positive");
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(dy, "dy"));
+  if (dx) SMX_TRY(check_ptr(dx, "dx"));
+  SMX_TRY(check_arch());
+  Arena dry(nullptr, 0, true);
+  SMX_TRY(vanilla_bwd_generic(blocks, n_blocks, act, rows, x, dtype, dy, dtype, dx, dtype, grads, dry, nullptr));
+  if (dry.peak > workspace_bytes || (dry.peak && !workspace))
+    return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", dry.peak, workspace_bytes);
+  Arena a(workspace, workspace_bytes, false);
+  return vanilla_bwd_generic(blocks, n_blocks, act, rows, x, dtype, dy, dtype, dx, dtype, grads, a, (cudaStream_t)stream);
+}
 size_t smx_layernorm_bwd_workspace_bytes(int dtype, int64_t rows, int32_t D) {
   if (rows <= 0 || D <= 0) return 0;
   Arena a(nullptr, 0, true);

@@ -653,6 +653,31 @@ __global__ void __launch_bounds__(256) dwconv_bwd_w_kernel(const float* dout, co
 #define BW_BUF(name, n) float* name = ws.f32((size_t)(n)); if (!name) return fail(SMX_ERR_WORKSPACE, "workspace too small (backward)")
 #define BW_LAUNCH(what, ...) do { if (!ws.dry) { __VA_ARGS__; count_launch(); SMX_TRY(check_launch(what)); } } while (0)
 
+// VanillaNN backward: n x (linear, act), activation after every block                 VanillaNN.py:168-196
+int vanilla_bwd_generic(const smx_linear* blocks, int n, int act, int64_t rows, const void* x, int x_dt, const void* dy, int dy_dt,
+                        void* dx, int dx_dt, const smx_linear_grad* g, Arena& ws, cudaStream_t st) {
+  if (n < 1 || n > SMX_MAX_BLOCKS) return fail(SMX_ERR_UNSUPPORTED, "VanillaNN with %d blocks (library handles 1..%d)", n, SMX_MAX_BLOCKS);
+  if (rows > 0x7fffffff) return fail(SMX_ERR_UNSUPPORTED, "VanillaNN backward: more than 2^31 rows");
+  for (int i = 0; i < n; ++i)
+    if (blocks[i].n_split > 1 && (blocks[i].in_dim % blocks[i].n_split || blocks[i].out_dim % blocks[i].n_split))
+      return fail(SMX_ERR_BAD_ARG, "input_size and n_neurons must be dividible by n_split!");
+  const size_t m0 = ws.mark();
+  const int D = blocks[0].in_dim, N = blocks[n - 1].out_dim;
+  const float* x32 = (const float*)x;
+  if (x_dt != SMX_F32) {
+    BW_BUF(xc, rows * D);
+    BW_RUN(convert(x, x_dt, xc, SMX_F32, rows * D, st));
+    x32 = xc;
+  }
+  BranchFwd f{};
+  SMX_TRY(branch_fwd(blocks, n, act, x32, rows, nullptr, f, ws, st));
+  BW_BUF(da, rows * N);
+  BW_RUN(convert(dy, dy_dt, da, SMX_F32, rows * N, st));
+  SMX_TRY(branch_bwd(blocks, g, n, act, f, rows, nullptr, da, dx, dx_dt, nullptr, dx != nullptr, ws, st));
+  ws.release(m0);
+  return SMX_OK;
+}
+
 // nn.LayerNorm backward: dx (dtype tag) and fp32 parameter gradients
 int layernorm_bwd_generic(const void* x, int x_dt, int64_t rows, int D, const float* w, float eps, const void* dy, int dy_dt, void* dx,
                           int dx_dt, float* dw, float* db, Arena& ws, cudaStream_t st) {

@@ -87,6 +87,8 @@ int cell_generic(const smx_cell_weights* w, int B, int T, const void* x, int x_d
 // backward of the cell, mode "SummaryMixing" (smx_bwd.cu); recomputes the forward intermediates from x
 int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int x_dt, const uint8_t* mask, const void* dy, int dy_dt,
                      void* dx, int dx_dt, const smx_cell_grads* g, Arena& ws, cudaStream_t st);
+int vanilla_bwd_generic(const smx_linear* blocks, int n, int act, int64_t rows, const void* x, int x_dt, const void* dy, int dy_dt,
+                        void* dx, int dx_dt, const smx_linear_grad* g, Arena& ws, cudaStream_t st);
 int layernorm_bwd_generic(const void* x, int x_dt, int64_t rows, int D, const float* w, float eps, const void* dy, int dy_dt, void* dx,
                           int dx_dt, float* dw, float* db, Arena& ws, cudaStream_t st);
 int ffn_bwd_generic(const smx_ffn_weights* w, int act, int64_t rows, const void* x, int x_dt, const float* oln_w, const float* oln_b,

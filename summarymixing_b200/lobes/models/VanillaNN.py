@@ -172,6 +172,10 @@ class VanillaNN(nn.ModuleDict):
             blk = (L.Linear * L.SMX_MAX_BLOCKS)()
             self.fill(blk, self._wv, dev)
             self._wv.struct = blk
+        from ... import _autograd as A
+
+        if A.wants_grad(self, x):
+            return A.VanillaNNFunction.apply(self._wv.struct, len(self._linears), self._act_code, self.output_size, xc, *self.params())
         y = torch.empty(B, T, self.output_size, dtype=xc.dtype, device=dev)
         _run_vanilla(self._wv.struct, len(self._linears), self._act_code, xc, y)
         return y
