@@ -10,7 +10,9 @@
  *  - extern "C", plain pointers and sizes.  Every pointer except the `_host` entry points' buffers is
  *    a DEVICE pointer.  The library allocates nothing persistent and keeps no pointer after return.
  *  - Enqueue-only on `stream` (a cudaStream_t passed as void*); no host synchronisation; safe to
- *    capture in a CUDA graph.  Re-entrant.
+ *    capture in a CUDA graph.  Re-entrant: no entry point keeps state between calls.  The only process-wide
+ *    state is the smx_debug_set_* switches at the end of this header (atomics; a concurrent call sees the old or the
+ *    new value) and the launch counters.
  *  - Returns SMX_OK (0) or a negative smx_status; never throws, never aborts.  smx_last_error()
  *    returns a thread-local message for the last failure.
  *  - Activations x/y: row-major (B,T,D) contiguous, fp32 (SMX_F32) or bf16 (SMX_BF16), 16-byte aligned.

@@ -24,6 +24,23 @@ def refuse_dropout(module, p: float) -> None:
             "summarymixing_b200: training-mode dropout is not implemented (build the model with dropout=0 or call .eval())")
 
 
+def pin_params(ctx, params) -> None:
+    """Record the parameters' version counters at forward time.  The backward entry points recompute the forward from
+    raw weight pointers (nothing but x is saved), so autograd cannot see a parameter that was modified in between; the
+    node checks it itself and fails like torch does for a saved tensor modified in place."""
+    ctx.param_versions = tuple(p._version for p in params)
+    ctx.pinned_params = tuple(params)
+
+
+def check_params(ctx) -> None:
+    now = tuple(p._version for p in ctx.pinned_params)
+    if now != ctx.param_versions:
+        raise RuntimeError(
+            "summarymixing_b200: a parameter of this module was modified in place between forward and backward "
+            "(optimizer step or load_state_dict with the graph still alive); its backward recomputes the forward from "
+            "the current weights and would return wrong gradients")
+
+
 def _new_grads(params, dev):
     return [torch.empty(p.shape, dtype=torch.float32, device=dev) for p in params]
 
@@ -83,13 +100,15 @@ class FFNFunction(torch.autograd.Function):
             ws = H.workspace(dev, lib.smx_ffn_workspace_bytes(C.byref(fw), dt, rows))
             L.check(lib.smx_ffn_fwd(C.byref(fw), act, dt, rows, xc.data_ptr(), ow, ob, oeps, y.data_ptr(), ws.data_ptr(),
                                     ws.numel(), H.stream_ptr(dev)))
-        ctx.fw, ctx.act, ctx.out_norm, ctx.params = fw, act, out_norm, params
+        ctx.fw, ctx.act, ctx.out_norm, ctx.params = fw, act, out_norm, params  # fw carries its tensors (_keepalive)
+        pin_params(ctx, params)
         ctx.save_for_backward(xc)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         (xc,) = ctx.saved_tensors
+        check_params(ctx)
         dev = xc.device
         dyc = dy.contiguous()
         rows = xc.numel() // xc.shape[-1]
@@ -128,12 +147,14 @@ class ConvModuleFunction(torch.autograd.Function):
             L.check(lib.smx_conv_module_fwd(C.byref(cw), act, dt, B, T, 0, xc.data_ptr(), H.p_or_none(m8), None, y.data_ptr(),
                                             ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
         ctx.cw, ctx.act, ctx.params = cw, act, params
+        pin_params(ctx, params)
         ctx.save_for_backward(xc, m8)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         xc, m8 = ctx.saved_tensors
+        check_params(ctx)
         dev = xc.device
         dyc = dy.contiguous()
         B, T, _ = xc.shape
@@ -172,12 +193,14 @@ class VanillaNNFunction(torch.autograd.Function):
             L.check(lib.smx_vanilla_nn_fwd(blocks, n, act, dt, rows, xc.data_ptr(), y.data_ptr(), ws.data_ptr(), ws.numel(),
                                            H.stream_ptr(dev)))
         ctx.blocks, ctx.n, ctx.act, ctx.params, ctx.x_shape = blocks, n, act, params, x.shape
+        pin_params(ctx, params)
         ctx.save_for_backward(xc)
         return y
 
     @staticmethod
     def backward(ctx, dy):
         (xc,) = ctx.saved_tensors
+        check_params(ctx)
         dev = xc.device
         dyc = dy.contiguous()
         rows = xc.shape[0] * xc.shape[1]

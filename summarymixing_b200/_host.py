@@ -79,7 +79,19 @@ class WeightView:
     def __init__(self):
         self._key = None
         self._keep = []
-        self.struct = None
+        self._struct = None
+
+    @property
+    def struct(self):
+        return self._struct
+
+    @struct.setter
+    def struct(self, value):
+        # the ctypes struct holds raw device pointers into the tensors of _keep (fp32 copies, packed operand images):
+        # whoever holds the struct (an autograd node between forward and backward, a captured graph) holds them too
+        if value is not None:
+            value._keepalive = self._keep
+        self._struct = value
 
     def stale(self, params, device) -> bool:
         key = (str(device),) + tuple((p.data_ptr(), p._version, p.dtype) for p in params)

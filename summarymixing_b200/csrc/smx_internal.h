@@ -4,6 +4,7 @@
 #include <cuda_bf16.h>
 #include <stdint.h>
 #include <stddef.h>
+#include <atomic>
 #include "smx.h"
 
 namespace smx {

@@ -183,7 +183,7 @@ extern "C" SMX_API int smx_debug_set_ffn_cluster(int cluster_size) {
 }
 
 namespace smx {
-static int g_pdl = 1;
+static std::atomic<int> g_pdl{1};
 bool tc_pdl_enabled() { return g_pdl != 0; }
 void tc_set_pdl(int on) { g_pdl = on ? 1 : 0; }
 }  // namespace smx

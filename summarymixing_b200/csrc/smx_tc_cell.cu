@@ -688,7 +688,7 @@ size_t tc_cellf_workspace_bytes(const smx_cell_weights* w, int B, int T) {
   return align_up((size_t)B * tpu * w->summary_out_dim * 4) + align_up((size_t)B * w->merge.out_dim * 4);
 }
 
-static unsigned long long* g_trace = nullptr;  // set by smx_debug_set_trace
+static std::atomic<unsigned long long*> g_trace{nullptr};  // set by smx_debug_set_trace
 void tc_set_trace(void* p) { g_trace = (unsigned long long*)p; }
 
 static int g_num_sms = 0;
@@ -767,7 +767,8 @@ int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
   };
   const unsigned grid = (unsigned)(p.n_tiles < num_sms() ? p.n_tiles : num_sms());
 
-  p.trace = g_trace;
+  unsigned long long* const trace0 = g_trace.load();
+  p.trace = trace0;
   {  // pass A
     p.g[0] = make_gemm(w->summary[0], img_s1, D);
     p.g[1] = make_gemm(w->summary[1], img_s2, w->summary[0].out_dim);
@@ -779,7 +780,7 @@ int tc_cellf_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
     SMX_TRY(launch_cell<0>(p, grid, smem, st));
   }
   SMX_TRY(tc_cell_finalize(w, B, T, colsum, mask, rowbias, st));  // per-utterance mean -> LN_s -> summary share of the combiner
-  if (g_trace) p.trace = g_trace + 512;
+  if (trace0) p.trace = trace0 + 512;
   {  // pass B
     p.g[0] = make_gemm(w->local[0], img_f1, D);
     p.g[1] = make_gemm(w->local[1], img_f2, w->local[0].out_dim);

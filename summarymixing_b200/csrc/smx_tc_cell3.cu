@@ -595,9 +595,9 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
-static unsigned long long* g_trace_c3 = nullptr;  // set by smx_debug_set_trace
+static std::atomic<unsigned long long*> g_trace_c3{nullptr};  // set by smx_debug_set_trace
 void tc_set_trace_cell3(void* p) { g_trace_c3 = (unsigned long long*)p; }
-static int g_cell_ver = 3;  // smx_debug_set_cell_version: 1 = first generation (smx_tc_cell.cu), 3 = this file (default)
+static std::atomic<int> g_cell_ver{3};  // smx_debug_set_cell_version: 1 = first generation (smx_tc_cell.cu), 3 = this file (default)
 void tc_set_cell_version(int v) { g_cell_ver = v == 1 ? 1 : 3; }
 int tc_cell_version() { return g_cell_ver; }
 
@@ -706,7 +706,8 @@ int tc_cell3_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
   if (p.nslots < 2) return fail(SMX_ERR_UNSUPPORTED, "fused cell: tile does not fit shared memory");
   const unsigned grid = (unsigned)(p.n_tiles < c3_sms() ? p.n_tiles : c3_sms());
 
-  p.trace = g_trace_c3;
+  unsigned long long* const trace0 = g_trace_c3.load();
+  p.trace = trace0;
   {  // pass A
     p.g[0] = c3_make_gemm(w->summary[0], D, w->summary[0].n_split); p.g[0].img = (const uint8_t*)img_s1;
     p.g[1] = c3_make_gemm(w->summary[1], w->summary[0].out_dim, w->summary[1].n_split); p.g[1].img = (const uint8_t*)img_s2;
@@ -715,7 +716,7 @@ int tc_cell3_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
     SMX_TRY(launch_cell3<0>(p, grid, smem, st));
   }
   SMX_TRY(tc_cell_finalize(w, B, T, colsum, mask, rowbias, st));  // per-utterance mean -> LN_s -> summary share of the combiner
-  if (g_trace_c3) p.trace = g_trace_c3 + 512;
+  if (trace0) p.trace = trace0 + 512;
   {  // pass B
     p.g[0] = c3_make_gemm(w->local[0], D, w->local[0].n_split); p.g[0].img = (const uint8_t*)img_f1;
     p.g[1] = c3_make_gemm(w->local[1], w->local[0].out_dim, w->local[1].n_split); p.g[1].img = (const uint8_t*)img_f2;
@@ -743,7 +744,7 @@ int tc_glu3_fwd(const smx_linear& L, const void* img_sched, const float* ln_w, c
   p.Dout = D; p.Ds = D;
   p.g[0] = c3_make_gemm(L, D, 1); p.g[0].img = (const uint8_t*)img_sched;
   p.b1 = L.b; p.b2 = L.b + D; p.nb1 = D; p.nb2 = D;
-  p.trace = g_trace_c3;  // (diagnostics) the GLU pass writes its timeline where pass A would
+  p.trace = g_trace_c3.load();  // (diagnostics) the GLU pass writes its timeline where pass A would
   const size_t smem = c3_carve(p, D);
   const unsigned grid = (unsigned)(p.n_tiles < c3_sms() ? p.n_tiles : c3_sms());
   return launch_cell3_act<2, 0>(p, grid, smem, st);  // the GLU pass has no runtime activation (sigmoid gate only)

@@ -343,7 +343,7 @@ bool tc_convf_supported(const smx_convmod_weights* w, int chunk) {
   return true;
 }
 
-static unsigned long long* g_trace3 = nullptr;
+static std::atomic<unsigned long long*> g_trace3{nullptr};
 void tc_set_trace_conv(void* p) { g_trace3 = (unsigned long long*)p; }
 
 static int convf_sms() {

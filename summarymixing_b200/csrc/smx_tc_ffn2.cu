@@ -426,9 +426,9 @@ int tc_ffn2_pack(const smx_ffn_weights* w, void* packed, cudaStream_t st) {
   return tc_pack_linear_nt(w->w2, 0, F, 64, (char*)packed + align_up((size_t)D * F * 2, 1024), st);
 }
 
-static int g_ffn_cluster = 1;  // measured on B200: multicast clusters couple the CTAs' rings and run slower (85/101/120 us for 1/2/4)
+static std::atomic<int> g_ffn_cluster{1};  // measured on B200: multicast clusters couple the CTAs' rings and run slower (85/101/120 us for 1/2/4)
 void tc_set_ffn_cluster(int cl) { g_ffn_cluster = (cl == 4 || cl == 2) ? cl : 1; }
-static unsigned long long* g_trace2 = nullptr;
+static std::atomic<unsigned long long*> g_trace2{nullptr};
 void tc_set_trace_ffn(void* p) { g_trace2 = (unsigned long long*)p; }
 
 static int ffn2_sms() {

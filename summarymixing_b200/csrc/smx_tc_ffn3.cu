@@ -518,8 +518,8 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
 // ---------------------------------------------------------------------------------------------
 // host side (weights packed by tc_ffn2_pack: the images are shared with v2)
 // ---------------------------------------------------------------------------------------------
-static int g_ffn_ver = 3;   // smx_debug_set_ffn_version: 2 = shared-memory hidden (v2), 3 = TMEM hidden, single CTAs (default),
-static int g_ffn_pair = 0;  //                            4 = TMEM hidden + CTA pairs (cta_group::2; bit-identical, measured slower)
+static std::atomic<int> g_ffn_ver{3};   // smx_debug_set_ffn_version: 2 = shared-memory hidden (v2), 3 = TMEM hidden, single CTAs (default),
+static std::atomic<int> g_ffn_pair{0};  //                            4 = TMEM hidden + CTA pairs (cta_group::2; bit-identical, measured slower)
 void tc_set_ffn_version(int v) { g_ffn_ver = v == 2 ? 2 : 3; g_ffn_pair = v == 4 ? 1 : 0; }
 int tc_ffn_version() { return g_ffn_ver; }
 
@@ -555,7 +555,7 @@ bool tc_ffn3_supported(const smx_ffn_weights* w) {
   return D % 64 == 0 && D <= 256;
 }
 
-static unsigned long long* g_trace3f = nullptr;
+static std::atomic<unsigned long long*> g_trace3f{nullptr};
 void tc_set_trace_ffn3(void* p) { g_trace3f = (unsigned long long*)p; }
 
 static int ffn3_sms() {

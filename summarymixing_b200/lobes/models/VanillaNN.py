@@ -34,25 +34,18 @@ class ParallelLinear(torch.nn.Module):
         combine_out_dims: Optional[bool] = True,
     ):
         super().__init__()
-        self.n_split = n_split
-        self.combine_out_dims = combine_out_dims
-
-        if input_shape is None and input_size is None:
-            raise ValueError("Expected one of input_shape or input_size")
-
         if input_size is None:
-            input_size = input_shape[-1]
-            if len(input_shape) == 4:
-                input_size = input_shape[-1] * input_shape[-2]
-
-        if input_size % n_split != 0 or n_neurons % n_split != 0:
-            raise ValueError("input_size and n_neurons must be dividible by n_split!")
-
-        self.split_inp_dim = input_size // n_split
-        self.split_out_dim = n_neurons // n_split
-
-        self.weights = nn.Parameter(torch.empty(self.n_split, self.split_inp_dim, self.split_out_dim))
-        self.biases = nn.Parameter(torch.zeros(self.n_split, self.split_out_dim))
+            if input_shape is None:
+                raise ValueError("Expected one of input_shape or input_size")
+            # a 4-D (B,T,heads,F) shape means the incoming head axis is folded into the feature dim
+            input_size = math.prod(input_shape[2:]) if len(input_shape) == 4 else input_shape[-1]
+        if input_size % n_split or n_neurons % n_split:
+            raise ValueError("input_size and n_neurons must be dividible by n_split!")  # (sic, VanillaNN.py:80)
+        self.n_split, self.combine_out_dims = n_split, combine_out_dims
+        self.split_inp_dim, self.split_out_dim = input_size // n_split, n_neurons // n_split
+        # head m maps input columns [m*in/h, (m+1)*in/h) to output columns [m*out/h, (m+1)*out/h)
+        self.weights = nn.Parameter(torch.empty(n_split, self.split_inp_dim, self.split_out_dim))
+        self.biases = nn.Parameter(torch.zeros(n_split, self.split_out_dim))
         self._reset_parameters()
         self._wv = H.WeightView()
 
@@ -76,8 +69,14 @@ class ParallelLinear(torch.nn.Module):
             blk = (L.Linear * 1)()
             self._fill(blk[0], self._wv, dev)
             self._wv.struct = blk
-        y = torch.empty(B, T, self.n_split * self.split_out_dim, dtype=xc.dtype, device=dev)
-        _run_vanilla(self._wv.struct, 1, L.ACT_IDENTITY, xc, y)
+        from ... import _autograd as A
+
+        if A.wants_grad(self, x):  # one block, no activation, through the VanillaNN node (smx_vanilla_nn_bwd)
+            y = A.VanillaNNFunction.apply(self._wv.struct, 1, L.ACT_IDENTITY, self.n_split * self.split_out_dim, xc,
+                                          self.weights, self.biases)
+        else:
+            y = torch.empty(B, T, self.n_split * self.split_out_dim, dtype=xc.dtype, device=dev)
+            _run_vanilla(self._wv.struct, 1, L.ACT_IDENTITY, xc, y)
         if not self.combine_out_dims:
             y = y.view(B, T, self.n_split, self.split_out_dim)
         return y

@@ -355,17 +355,24 @@ class ConformerEncoder(nn.Module):
         H.require_cuda(src, "ConformerEncoder")
         if A.wants_grad(self, src):
             # training path: the layers and the final norm as autograd nodes (Conformer.py:797-821, layerdrop off)
-            if self.training and self.layerdrop_prob > 0:
-                raise NotImplementedError("summarymixing_b200: layerdrop is not implemented (layerdrop_prob must be 0 in training)")
-            out, hidden_lst = src, []
-            for layer in self.layers:
-                out, _ = layer(out, src_mask=src_mask, src_key_padding_mask=src_key_padding_mask,
-                               dynchunktrain_config=dynchunktrain_config)
+            # layerdrop (Conformer.py:798-810): one uniform draw per layer from the module's numpy generator; a layer
+            # runs unless training and its draw is <= layerdrop_prob; skipped layers leave no entry in either list
+            drop = self.training and self.layerdrop_prob > 0.0
+            keep_probs = self.rng.random(len(self.layers)) if self.layerdrop_prob > 0.0 else None
+            out, hidden_lst, attention_lst = src, [], []
+            for i, layer in enumerate(self.layers):
+                if drop and not keep_probs[i] > self.layerdrop_prob:
+                    continue
+                out, attn = layer(out, src_mask=src_mask, src_key_padding_mask=src_key_padding_mask,
+                                  dynchunktrain_config=dynchunktrain_config)
                 hidden_lst.append(out)
+                attention_lst.append(attn)
             out = A.LayerNormFunction.apply(out, self.norm.norm.weight, self.norm.norm.bias, self.norm.eps)
             if self.output_hidden_states:
-                return out, hidden_lst, [None] * len(self.layers)
-            return out, [None] * len(self.layers)
+                if hidden_lst:
+                    hidden_lst[-1] = out  # the last entry is the normalised output (Conformer.py:823-825)
+                return out, hidden_lst, attention_lst
+            return out, attention_lst
         H.check_grad_mode(self)  # layerdrop only acts in training (Conformer.py:806-810)
         B, T, D = src.shape
         dev = src.device

@@ -11,7 +11,6 @@ from typing import Optional
 
 import ctypes as C
 
-import numpy as np
 import torch
 import torch.nn as nn
 
@@ -39,74 +38,44 @@ class SummaryMixing(nn.Module):
         mode: Optional[str] = "SummaryMixing",
         use_layernorm: Optional[bool] = True,
     ):
-        super(SummaryMixing, self).__init__()
-
+        super().__init__()
         if mode not in L.MODES:
             raise ValueError(
                 "The SummaryMixing mode should either be 'SummaryMixing', 'SummaryMixing-lite', 'SummaryMixing-fast' or 'SummaryMixing-expdecay'"
             )
-
-        self.local_proj_hid_dim = local_proj_hid_dim
-        self.local_proj_out_dim = local_proj_out_dim
-        self.summary_hid_dim = summary_hid_dim
-        self.summary_out_dim = summary_out_dim
-        self.summary_reshaped_dim = int(np.sqrt(summary_out_dim))
-        self.enc_dim = enc_dim
-        self.nhead = nhead
-        self.activation = activation()
-        self.local_dnn_blocks = local_proj_hid_dim + [local_proj_out_dim]
-        self.summary_dnn_blocks = summary_hid_dim + [summary_out_dim]
-        self.mode = mode
+        self.enc_dim, self.nhead, self.mode = enc_dim, nhead, mode
+        self.local_proj_hid_dim, self.local_proj_out_dim = local_proj_hid_dim, local_proj_out_dim
+        self.summary_hid_dim, self.summary_out_dim = summary_hid_dim, summary_out_dim
         self.use_layernorm = use_layernorm
+        self.activation = activation()
         self.dropout = nn.Dropout(global_dropout)
 
-        if self.mode == "SummaryMixing" or self.mode == "SummaryMixing-expdecay":
-            self.local_proj = VanillaNN(
-                input_shape=[None, None, enc_dim],
-                dnn_blocks=len(self.local_dnn_blocks),
-                dnn_neurons=self.local_dnn_blocks,
-                activation=activation,
-                n_split=nhead,
-            )
-            self.summary_local_merging = VanillaNN(
-                input_shape=[None, None, local_proj_out_dim + summary_out_dim],
-                dnn_blocks=1,
-                dnn_neurons=[summary_out_dim],
-                activation=activation,
-            )
+        def mlp(in_dim, widths, heads=1):
+            # VanillaNN over the last dim of a (B,T,in_dim) input: one (linear, activation) pair per width
+            return VanillaNN(input_shape=[None, None, in_dim], dnn_blocks=len(widths), dnn_neurons=list(widths),
+                             activation=activation, n_split=heads)
 
-        if self.mode == "SummaryMixing-fast":
-            self.global_proj = VanillaNN(
-                input_shape=[None, None, enc_dim],
-                dnn_blocks=1,
-                dnn_neurons=self.local_proj_out_dim * 2,
-                activation=activation,
-                n_split=1,
-            )
-            self.summary_local_merging = VanillaNN(
-                input_shape=[None, None, self.local_proj_out_dim * 2],
-                dnn_blocks=1,
-                dnn_neurons=[summary_out_dim],
-                activation=activation,
-            )
+        # Which sub-networks a mode owns (summary_mixing.py:103-161).  Registration order = the reference's, so that
+        # state_dict() and parameters() enumerate identically:
+        #   full / expdecay: local_proj (f), summary_local_merging (combiner over [f ; mean s]), summary_proj (s)
+        #   lite:            summary_proj only
+        #   fast:            global_proj (one dense D -> 2 D_l layer whose halves are f and s), summary_local_merging
+        if mode in ("SummaryMixing", "SummaryMixing-expdecay"):
+            self.local_proj = mlp(enc_dim, local_proj_hid_dim + [local_proj_out_dim], nhead)
+            self.summary_local_merging = mlp(local_proj_out_dim + summary_out_dim, [summary_out_dim])
+        if mode == "SummaryMixing-fast":
+            self.global_proj = mlp(enc_dim, [2 * local_proj_out_dim])
+            self.summary_local_merging = mlp(2 * local_proj_out_dim, [summary_out_dim])
         else:
-            self.summary_proj = VanillaNN(
-                input_shape=[None, None, enc_dim],
-                dnn_blocks=len(self.summary_dnn_blocks),
-                dnn_neurons=self.summary_dnn_blocks,
-                activation=activation,
-                n_split=nhead,
-            )
-
-        if self.mode == "SummaryMixing-expdecay":
-            self.decay_constant = nn.Parameter(data=torch.tensor(0.995), requires_grad=False)
-
-        if self.use_layernorm:
-            # created in every mode, as in the reference (:163-165); unused by lite and fast
+            self.summary_proj = mlp(enc_dim, summary_hid_dim + [summary_out_dim], nhead)
+        if mode == "SummaryMixing-expdecay":
+            self.decay_constant = nn.Parameter(torch.tensor(0.995), requires_grad=False)  # frozen (:158-161)
+        if use_layernorm:
+            # owned in every mode, like the reference (:163-165), although lite and fast never apply them
             self.local_norm = nn.LayerNorm(local_proj_out_dim)
             self.summary_norm = nn.LayerNorm(summary_out_dim)
 
-        self.apply(self._init_parameters)
+        self.apply(self._init_parameters)  # zero the biases of dense layers (:167, 326-328)
         self._act_code = H.act_code(self.activation)
         self._wv = H.WeightView()
 
@@ -216,12 +185,13 @@ class SummaryMixing(nn.Module):
             return y.unsqueeze(1).expand(-1, T, -1)
         return y
 
-    def _backward_impl(self, x, mask, dy, want_dx):
+    def _backward_impl(self, x, mask, dy, want_dx, cw=None):
         """(dx or None, [fp32 gradient per grad_params() entry]) through smx_summary_mixing_bwd."""
         B, T, _ = x.shape
         dev = x.device
         xc, dyc = x.contiguous(), dy.contiguous()
-        cw = self._weights(dev)
+        if cw is None:
+            cw = self._weights(dev)
         plist = self.grad_params()
         grads = [torch.empty(p.shape, dtype=torch.float32, device=dev) for p in plist]
         cg = L.CellGrads()
@@ -262,15 +232,23 @@ class _CellFunction(torch.autograd.Function):
 
     @staticmethod
     def forward(ctx, module, x, mask, *params):
+        from .. import _autograd as A
+
         ctx.module = module
         ctx.save_for_backward(x, mask)
-        return module._forward_impl(x, mask, None, expand_lite=False)
+        y = module._forward_impl(x, mask, None, expand_lite=False)
+        ctx.cw = module._wv.struct  # the weight struct of THIS forward (with the tensors it points into)
+        A.pin_params(ctx, module.params())
+        return y
 
     @staticmethod
     def backward(ctx, dy):
+        from .. import _autograd as A
+
         x, mask = ctx.saved_tensors
+        A.check_params(ctx)
         module = ctx.module
-        dx, grads = module._backward_impl(x, mask, dy, ctx.needs_input_grad[1])
+        dx, grads = module._backward_impl(x, mask, dy, ctx.needs_input_grad[1], cw=ctx.cw)
         plist = module.grad_params()
         out = [g.to(p.dtype) if ctx.needs_input_grad[3 + i] else None for i, (g, p) in enumerate(zip(grads, plist))]
         return (None, dx, None, *out)

@@ -31,13 +31,21 @@ def shard_batch(x: torch.Tensor, mask: Optional[torch.Tensor], rank: int, world:
 
 
 def sharded_forward(fn: Callable, x: torch.Tensor, mask: Optional[torch.Tensor], gather: bool = False,
-                    group=None) -> torch.Tensor:
+                    group=None, out_dim: Optional[int] = None, out_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
     """Run `fn(x_shard, mask_shard) -> (b,T,D')` on this rank's utterances.  With gather=True every rank returns the
-    full (B,T,D') result (all_gather of equal-size padded shards); otherwise only its own shard."""
+    full (B,T,D') result (all_gather of equal-size padded shards); otherwise only its own shard.
+    `out_dim` / `out_dtype`: feature dim and dtype of fn's result when they differ from x's (a cell with
+    summary_out_dim != enc_dim): a rank whose shard is empty never runs fn and needs them to build its (empty) share."""
     world = dist.get_world_size(group) if dist.is_initialized() else 1
     rank = dist.get_rank(group) if dist.is_initialized() else 0
     xs, ms = shard_batch(x, mask, rank, world)
-    y = fn(xs, ms) if xs.shape[0] > 0 else x.new_zeros((0,) + tuple(x.shape[1:]))
+    if xs.shape[0] > 0:
+        y = fn(xs, ms)
+        if out_dim is not None and y.shape[-1] != out_dim:
+            raise ValueError(f"sharded_forward: fn returned feature dim {y.shape[-1]}, out_dim says {out_dim}")
+    else:
+        y = torch.zeros((0,) + tuple(x.shape[1:-1]) + (out_dim if out_dim is not None else x.shape[-1],),
+                        dtype=out_dtype or x.dtype, device=x.device)
     if not gather or world == 1:
         return y
     B = x.shape[0]
