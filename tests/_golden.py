@@ -32,3 +32,33 @@ class Fixture:
         self.mask = torch.from_numpy(z["in.mask"]) if "in.mask" in z.files else None
         self.sum_mask = torch.from_numpy(z["in.sum_mask"]) if "in.sum_mask" in z.files else None
         self.sd = {k[3:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("sd.")}
+
+
+# ---- tile-aligned fixtures (tests/golden/tile/, oracle/gen_golden_tile.py): seed-defined weights and inputs -------------
+TILE_DIR = os.path.join(GOLDEN_DIR, "tile")
+
+
+def tile_names(prefix=""):
+    return [os.path.basename(f)[:-4] for f in sorted(glob.glob(os.path.join(TILE_DIR, prefix + "*.npz")))]
+
+
+class TileFixture:
+    """y32: the reference's fp32 output; y16: the reference module run in bfloat16 (its own bf16-vs-fp32 error is
+    |y16 - y32|); x and the weights are regenerated from the seeds in cfg (oracle/seeded.py)."""
+
+    def __init__(self, name):
+        from oracle.seeded import seeded_input
+
+        z = np.load(os.path.join(TILE_DIR, name + ".npz"))
+        self.name = name
+        self.cfg = json.loads(bytes(z["cfg"]).decode())
+        self.y32 = torch.from_numpy(z["y32"])
+        self.y16 = torch.from_numpy(z["y16"]).view(torch.bfloat16).float()
+        self.mask = torch.from_numpy(z["mask"])
+        c = self.cfg
+        D = c.get("enc_dim") or c.get("d_model") or c.get("input_size")
+        self.x = seeded_input(c["seed_x"], c["B"], c["T"], D)
+
+    def ref_bf16_error(self):
+        d = self.y16 - self.y32
+        return float(d.abs().max()), float(d.norm() / self.y32.norm())
