@@ -354,6 +354,20 @@ int smx_ffn_fwd(const smx_ffn_weights* w, int act, int dtype, int64_t rows, cons
   return ffn_generic(w, act, rows, x, dtype, out_ln_w, out_ln_b, out_ln_eps, y, dtype, a, (cudaStream_t)stream);
 }
 
+// Zeroes `bytes` at the start of the workspace (the fused cell kernels' per-utterance counters, smx_tc_cell4.cu) with ONE
+// memset ahead of the whole kernel chain and hands the area down to tc_cell4_fwd (thread-local); released on scope exit.
+struct PresyncGuard {
+  size_t bytes;
+  int status;
+  PresyncGuard(void* ws, size_t n, bool active, cudaStream_t st) : bytes(n), status(SMX_OK) {
+    if (!active || !ws || n == 0) { tc_cell4_set_presync(nullptr, 0); return; }
+    cudaError_t e = cudaMemsetAsync(ws, 0, n, st);
+    if (e != cudaSuccess) { status = fail(SMX_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e)); return; }
+    tc_cell4_set_presync(ws, n);
+  }
+  ~PresyncGuard() { tc_cell4_set_presync(nullptr, 0); }
+};
+
 // ---- Conformer layer / encoder -------------------------------------------------------------------
 size_t smx_conformer_layer_workspace_bytes(const smx_conformer_layer_weights* w, int dtype, int32_t B, int32_t T,
                                            int has_sum_mask) {
@@ -361,7 +375,7 @@ size_t smx_conformer_layer_workspace_bytes(const smx_conformer_layer_weights* w,
   Arena a(nullptr, 0, true);
   const float* sm = has_sum_mask ? (const float*)(uintptr_t)256 : nullptr;
   conformer_layer_generic(w, dtype, B, T, 0, nullptr, nullptr, sm, nullptr, a, nullptr);
-  return a.peak;
+  return a.peak + tc_cell4_sync_bytes(B);
 }
 int smx_conformer_layer_fwd(const smx_conformer_layer_weights* w, int dtype, int32_t B, int32_t T, int32_t chunk_size,
                             const void* x, const uint8_t* padding_mask, const float* sum_mask, void* y, void* workspace,
@@ -374,7 +388,11 @@ int smx_conformer_layer_fwd(const smx_conformer_layer_weights* w, int dtype, int
   size_t need = smx_conformer_layer_workspace_bytes(w, dtype, B, T, sum_mask != nullptr);
   if (need > workspace_bytes || (need && !workspace))
     return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
-  Arena a(workspace, workspace_bytes, false);
+  // the fused cell's per-utterance counters are zeroed here, ahead of the layer's kernel chain (a memset node right in
+  // front of the cell kernel would cut its programmatic-launch edge to the FFN kernel)
+  PresyncGuard presync(workspace, tc_cell4_sync_bytes(B), dtype == SMX_BF16, (cudaStream_t)stream);
+  if (presync.status != SMX_OK) return presync.status;
+  Arena a((char*)workspace + presync.bytes, workspace_bytes - presync.bytes, false);
   return conformer_layer_generic(w, dtype, B, T, chunk_size, x, padding_mask, sum_mask, y, a, (cudaStream_t)stream);
 }
 
@@ -386,7 +404,7 @@ size_t smx_conformer_encoder_workspace_bytes(const smx_conformer_layer_weights* 
     size_t s = smx_conformer_layer_workspace_bytes(&layers[i], dtype, B, T, has_sum_mask);
     if (s > m) m = s;
   }
-  return m;
+  return m + (size_t)n_layers * tc_cell4_sync_bytes(B);
 }
 int smx_conformer_encoder_fwd(const smx_conformer_layer_weights* layers, int32_t n_layers, const float* final_norm_w,
                               const float* final_norm_b, int dtype, int32_t B, int32_t T, int32_t chunk_size,
@@ -405,10 +423,12 @@ int smx_conformer_encoder_fwd(const smx_conformer_layer_weights* layers, int32_t
   const int D = layers[0].ffn1.w1.in_dim;
   const int64_t rows = (int64_t)B * T;
   const void* cur = x;
+  PresyncGuard presync(workspace, (size_t)n_layers * tc_cell4_sync_bytes(B), dtype == SMX_BF16, st);  // one memset for all layers' counters
+  if (presync.status != SMX_OK) return presync.status;
   for (int i = 0; i < n_layers; ++i) {
     void* out = hidden ? hidden[i] : y;
     if (hidden) SMX_TRY(check_ptr(out, "hidden[i]"));
-    Arena a(workspace, workspace_bytes, false);
+    Arena a((char*)workspace + presync.bytes, workspace_bytes - presync.bytes, false);
     SMX_TRY(conformer_layer_generic(&layers[i], dtype, B, T, chunk_size, cur, padding_mask, sum_mask, out, a, st));
     cur = out;
   }

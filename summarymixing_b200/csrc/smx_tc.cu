@@ -170,6 +170,7 @@ extern "C" SMX_API int smx_debug_tc_gemm(int layout, int32_t M, int32_t N, int32
 extern "C" SMX_API int smx_debug_set_trace(void* device_u64_buffer) {
   tc_set_trace(device_u64_buffer);
   tc_set_trace_cell3(device_u64_buffer);
+  tc_set_trace_cell4(device_u64_buffer);
   tc_set_trace_ffn(device_u64_buffer ? (char*)device_u64_buffer + 4096 : nullptr);  // entries 512..1023
   tc_set_trace_ffn3(device_u64_buffer ? (char*)device_u64_buffer + 4096 : nullptr);
   tc_set_trace_conv(device_u64_buffer ? (char*)device_u64_buffer + 7680 : nullptr); // entries 960..1023

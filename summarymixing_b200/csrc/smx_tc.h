@@ -94,9 +94,23 @@ int tc_cell3_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
                  const uint8_t* mask, const __nv_bfloat16* residual, __nv_bfloat16* y, Arena& ws, cudaStream_t st);
 int tc_glu3_fwd(const smx_linear& L, const void* img_sched, const float* ln_w, const float* ln_b, int64_t rows,
                 const __nv_bfloat16* x, __nv_bfloat16* out, cudaStream_t st);
-void tc_set_cell_version(int v);  // 1 or 3 (diagnostics / A-B timing)
+void tc_set_cell_version(int v);  // 1, 3 or 4 (diagnostics / A-B timing)
 void tc_set_trace_cell3(void* p);
 int tc_cell_version();
+
+// ---- smx_tc_cell4.cu: K-SM v4 (one persistent kernel: x tile by tensor-map TMA, normalised once and resident through both
+// phases, per-utterance counter / flag instead of a kernel boundary, half-width chains ping-ponging in TMEM) --------------
+bool tc_cell4_supported(const smx_cell_weights* w);
+bool tc_cell4_fits(int B, int T);  // at most two tiles per CTA, one CTA per SM
+size_t tc_cell4_packed_bytes(const smx_cell_weights* w);
+int tc_cell4_pack(const smx_cell_weights* w, const void* img_s1, const void* img_s2, const void* img_f1, const void* img_f2,
+                  const void* img_c, void* out, cudaStream_t st);  // inputs: chunk-major images (tc_pack_linear_nt, NT = 64)
+size_t tc_cell4_workspace_bytes(const smx_cell_weights* w, int B, int T);
+size_t tc_cell4_sync_bytes(int B);
+void tc_cell4_set_presync(void* zeroed, size_t bytes);  // (thread-local) counters zeroed ahead of the kernel chain by the caller
+int tc_cell4_fwd(const smx_cell_weights* w, const void* img, int B, int T, const __nv_bfloat16* x, const float* pre_ln_w,
+                 const float* pre_ln_b, const uint8_t* mask, const __nv_bfloat16* residual, __nv_bfloat16* y, Arena& ws, cudaStream_t st);
+void tc_set_trace_cell4(void* p);
 
 // ---- smx_tc_conv.cu: K-CONV, depthwise conv + LN + act + output GEMM + mask/residual, persistent -------
 bool tc_convf_supported(const smx_convmod_weights* w, int chunk);

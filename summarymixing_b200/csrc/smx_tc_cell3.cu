@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
   if (warp == C3_PROD_WARP) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int s = 0; s < C3_MAX_SLOTS; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    tc::mbar_init(&x_full, C3_NPW); tc::mbar_init(&x_free, 1); tc::mbar_init(&x_copied, C3_NPW); tc::mbar_init(&epi_done, C3_NEW);
+    tc::mbar_init(&x_full, C3_NPW); tc::mbar_init(&x_free, 1); tc::mbar_init(&x_copied, C3_NPW * 32); tc::mbar_init(&epi_done, C3_NEW);
     for (int i = 0; i < 3; ++i) tc::mbar_init(&acc_full[i], 1);
     for (int i = 0; i < 2; ++i) tc::mbar_init(&op_full[i], C3_NEW);
     tc::fence_barrier_init();
@@ -299,7 +299,7 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
         tc::cp_async_commit();
         tc::cp_async_wait_all();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&x_copied);
+        tc::mbar_arrive(&x_copied);  // every lane: each thread publishes its own cp.async writes (count = all copying threads)
       } else {
         tc::stage_ln_rows_wide(sX, p.x, p.ldx, row0, nrows, p.D, pw * 4, 4, lane, p.pre_w != nullptr, sPar + 1280, sPar + 1552, sStat);
         tc::fence_proxy_async();
@@ -597,8 +597,8 @@ __global__ void __launch_bounds__(C3_THREADS, 1) cell3_kernel(const Cell3P p) {
 // ---------------------------------------------------------------------------------------------
 static std::atomic<unsigned long long*> g_trace_c3{nullptr};  // set by smx_debug_set_trace
 void tc_set_trace_cell3(void* p) { g_trace_c3 = (unsigned long long*)p; }
-static std::atomic<int> g_cell_ver{3};  // smx_debug_set_cell_version: 1 = first generation (smx_tc_cell.cu), 3 = this file (default)
-void tc_set_cell_version(int v) { g_cell_ver = v == 1 ? 1 : 3; }
+static std::atomic<int> g_cell_ver{4};  // smx_debug_set_cell_version: 1 = first generation (smx_tc_cell.cu), 3 = this file, 4 = smx_tc_cell4.cu (default)
+void tc_set_cell_version(int v) { g_cell_ver = (v == 1 || v == 3) ? v : 4; }
 int tc_cell_version() { return g_cell_ver; }
 
 static bool c3_dim_ok(int d) { return d >= 64 && d <= 256 && d % 64 == 0; }

@@ -41,6 +41,7 @@ bool tc_cell_supported(const smx_cell_weights* w, int has_sum_mask) {
 struct CellLayout {
   size_t local[SMX_MAX_BLOCKS], summary[SMX_MAX_BLOCKS], merge, total;
   size_t local_s[2], summary_s[2], merge_s;  // the same images in schedule order (K-SM v3)
+  size_t v4;                                 // stream-order image + W_cs^T of K-SM v4 (0 bytes when v4 does not apply)
 };
 static CellLayout cell_layout(const smx_cell_weights* w) {
   CellLayout l{};
@@ -52,6 +53,7 @@ static CellLayout cell_layout(const smx_cell_weights* w) {
     for (int i = 0; i < 2; ++i) { l.local_s[i] = off; off += align_up(tc_linear_packed_bytes(w->local[i].in_dim, w->local[i].out_dim)); }
     for (int i = 0; i < 2; ++i) { l.summary_s[i] = off; off += align_up(tc_linear_packed_bytes(w->summary[i].in_dim, w->summary[i].out_dim)); }
     l.merge_s = off; off += align_up(tc_linear_packed_bytes(w->local_out_dim, w->merge.out_dim));
+    l.v4 = off; off += align_up(tc_cell4_packed_bytes(w), 1024);
   }
   l.total = off;
   return l;
@@ -70,7 +72,10 @@ int tc_cell_pack(const smx_cell_weights* w, void* packed, cudaStream_t st) {
       SMX_TRY(tc_cell3_reorder(w->local[i], w->local[i].in_dim, w->local[i].n_split, base + l.local[i], base + l.local_s[i], st));
       SMX_TRY(tc_cell3_reorder(w->summary[i], w->summary[i].in_dim, w->summary[i].n_split, base + l.summary[i], base + l.summary_s[i], st));
     }
-    return tc_cell3_reorder(w->merge, w->local_out_dim, 1, base + l.merge, base + l.merge_s, st);
+    SMX_TRY(tc_cell3_reorder(w->merge, w->local_out_dim, 1, base + l.merge, base + l.merge_s, st));
+    if (tc_cell4_packed_bytes(w))
+      SMX_TRY(tc_cell4_pack(w, base + l.summary[0], base + l.summary[1], base + l.local[0], base + l.local[1], base + l.merge, base + l.v4, st));
+    return SMX_OK;
   }
   for (int i = 0; i < w->n_local; ++i) SMX_TRY(tc_pack_linear(w->local[i], 0, w->local[i].in_dim, 0, base + l.local[i], st));
   for (int i = 0; i < w->n_summary; ++i) SMX_TRY(tc_pack_linear(w->summary[i], 0, w->summary[i].in_dim, 0, base + l.summary[i], st));
@@ -163,7 +168,10 @@ static int cell_ws(const smx_cell_weights* w, int B, int T, Arena& ws, CellWs& o
 }
 size_t tc_cell_workspace_bytes(const smx_cell_weights* w, int B, int T) {
   if (!tc_cell_supported(w, 0)) return 0;
-  if (tc_cellf_supported(w)) return tc_cellf_workspace_bytes(w, B, T);
+  if (tc_cellf_supported(w)) {
+    const size_t a = tc_cellf_workspace_bytes(w, B, T), b = tc_cell4_supported(w) ? tc_cell4_workspace_bytes(w, B, T) : 0;
+    return a > b ? a : b;
+  }
   Arena a(nullptr, 0, true);
   CellWs o;
   cell_ws(w, B, T, a, o);
@@ -197,7 +205,9 @@ int tc_cell_fwd(const smx_cell_weights* w, const void* packed, int B, int T, con
   if (tc_cellf_supported(w)) {
     // v3 moves rows with 256-bit global accesses: 32-byte aligned x / y / residual
     const bool al = ((uintptr_t)x % 32 == 0) && ((uintptr_t)y % 32 == 0) && ((uintptr_t)residual % 32 == 0);
-    if (tc_cell_version() == 3 && tc_cell3_supported(w) && al)
+    if (tc_cell_version() == 4 && tc_cell4_packed_bytes(w) && tc_cell4_fits(B, T) && al)
+      return tc_cell4_fwd(w, pk + l.v4, B, T, x, pre_ln_w, pre_ln_b, mask, residual, y, ws, st);
+    if (tc_cell_version() >= 3 && tc_cell3_supported(w) && al)
       return tc_cell3_fwd(w, pk + l.summary_s[0], pk + l.summary_s[1], pk + l.local_s[0], pk + l.local_s[1], pk + l.merge_s, B, T, x,
                           pre_ln_w, pre_ln_b, mask, residual, y, ws, st);
     return tc_cellf_fwd(w, pk + l.summary[0], pk + l.summary[1], pk + l.local[0], pk + l.local[1], pk + l.merge, B, T, x,
@@ -520,7 +530,7 @@ int tc_convmod_fwd(const smx_convmod_weights* w, const void* packed, int act, in
   if (tc_convf_supported(w, 0)) {
     __nv_bfloat16* gb = (__nv_bfloat16*)ws.take((size_t)rows * D * 2);
     if (!gb) return fail(SMX_ERR_WORKSPACE, "workspace too small (tc conv module)");
-    if (tc_cell_version() == 3 && ((uintptr_t)x % 32 == 0) && ((uintptr_t)gb % 32 == 0))                 // :322-324
+    if (tc_cell_version() >= 3 && ((uintptr_t)x % 32 == 0) && ((uintptr_t)gb % 32 == 0))                // :322-324
       SMX_TRY(tc_glu3_fwd(w->bottleneck, (const char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)) + align_up(tc_linear_packed_bytes(D, D)),
                           w->ln_w, w->ln_b, rows, x, gb, st));
     else
