@@ -27,6 +27,24 @@ sys.path.insert(0, ROOT)
 B, T, D, FFN, HEADS, LAYERS, KSIZE = 32, 1000, 256, 1024, 4, 12, 31
 METRIC = "encoder-fwd frames/sec (B=32,T=1000,D=256)"
 N_ROTATE = 12  # distinct input batches cycled through the timed loop: 12 x 16.4 MB (+ outputs) > 126 MB of L2
+WORKLOAD = ("cfg2: 12-layer SummaryMixing-Conformer encoder forward, D=256 d_ffn=1024 h=4 k=31, "
+            "B=32 x T=1000 padded batch per GPU")
+
+
+def config(world: int):
+    """The `config` object, identical for both arms (--impl smx / reference): what is measured, not how."""
+    return {"workload": WORKLOAD, "batch_per_gpu": B, "seq_len": T, "d_model": D, "layers": LAYERS, "n_gpus": world}
+
+
+def ksm_traffic():
+    """DRAM bytes of one K-SM call from the committed ncu capture (profiles/r02_ksm_traffic.json, written by
+    tools/ncu_traffic.py from `ncu --set full` of tools/ncu_cell_capture.py; includes the trailing evict pass that forces the
+    output's dirty lines out of L2).  None when the file is absent."""
+    p = os.path.join(ROOT, "profiles", "r02_ksm_traffic.json")
+    if not os.path.exists(p):
+        return None
+    with open(p) as f:
+        return json.load(f)
 
 
 def peaks():
@@ -165,9 +183,7 @@ def run_reference(args):
     line = {"metric": METRIC, "value": r["value"], "unit": "frames/s", "n_gpus": args.gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": r["ms_per_step"], "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
-            "config": {"workload": "cfg2: 12-layer SummaryMixing-Conformer encoder forward, D=256 d_ffn=1024 h=4 k=31, "
-                                   "B=32 x T=1000 padded batch per GPU", "frames_per_step": r["frames_per_step"],
-                       "device": "host CPU"},
+            "config": config(args.gpus), "details": {"frames_per_step": r["frames_per_step"], "device": "host CPU"},
             "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": r["value"], "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -191,16 +207,23 @@ def time_module_calls(enc, x, mask, iters: int):
     st = H.stream_ptr(dev)
     rows = B * T
     nb = max(lib.smx_conformer_layer_workspace_bytes(C.byref(lw), L.BF16, B, T, 0),
-             lib.smx_summary_mixing_workspace_bytes(C.byref(lw.cell), L.BF16, B, T, 0),
+             lib.smx_mixing_block_workspace_bytes(C.byref(lw.cell), L.BF16, B, T, 0),
              lib.smx_ffn_workspace_bytes(C.byref(lw.ffn1), L.BF16, rows),
              lib.smx_conv_module_workspace_bytes(C.byref(lw.conv), L.BF16, B, T), 1 << 20)
     ws = torch.empty(nb, dtype=torch.uint8, device=dev)
     xs = [torch.randn(B, T, D, device=dev).to(torch.bfloat16) for _ in range(N_ROTATE)]
     ys = [torch.empty_like(xs[0]) for _ in range(N_ROTATE)]
 
-    def cell(i):
-        L.check(lib.smx_summary_mixing_fwd(C.byref(lw.cell), L.BF16, B, T, xs[i].data_ptr(), m8.data_ptr(), None,
-                                           xs[i].data_ptr(), ys[i].data_ptr(), ws.data_ptr(), ws.numel(), st))
+    # K-SM as it runs inside the layer: y = x + SummaryMixing(norm1(x)) (Conformer.py:520-541), `iters` batches back to back
+    # through smx_mixing_block_fwd_batch (kernels chained by programmatic launch, one counter reset ahead of the chain -- the
+    # way smx_conformer_encoder_fwd runs its layers)
+    xs_p = (C.c_void_p * iters)(*[xs[i % N_ROTATE].data_ptr() for i in range(iters)])
+    ys_p = (C.c_void_p * iters)(*[ys[i % N_ROTATE].data_ptr() for i in range(iters)])
+    ws_cell = torch.empty(nb + iters * (4096 + 8 * B), dtype=torch.uint8, device=dev)
+
+    def cell_batch(n):
+        L.check(lib.smx_mixing_block_fwd_batch(C.byref(lw.cell), lw.norm1_w, lw.norm1_b, L.BF16, B, T, n, xs_p, m8.data_ptr(), ys_p,
+                                               ws_cell.data_ptr(), ws_cell.numel(), st))
 
     def ffn(i):
         L.check(lib.smx_ffn_fwd(C.byref(lw.ffn1), lw.act, L.BF16, rows, xs[i].data_ptr(), None, None, 0.0,
@@ -211,7 +234,16 @@ def time_module_calls(enc, x, mask, iters: int):
                                         xs[i].data_ptr(), ys[i].data_ptr(), ws.data_ptr(), ws.numel(), st))
 
     out = {}
-    for name, fn in (("cell", cell), ("ffn", ffn), ("conv", conv)):
+    cell_batch(3)
+    torch.cuda.synchronize()
+    n0 = lib.smx_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    cell_batch(iters)
+    e1.record()
+    torch.cuda.synchronize()
+    out["cell"] = {"us": 1e3 * e0.elapsed_time(e1) / iters, "launches": int(lib.smx_launch_count() - n0) // iters}
+    for name, fn in (("ffn", ffn), ("conv", conv)):
         for i in range(3):
             fn(i)
         torch.cuda.synchronize()
@@ -290,56 +322,17 @@ def run_smx(args):
         launches, tc_launches = per_step * args.steps, tc_per_step * args.steps
         ms_total = e0.elapsed_time(e1)
 
-        # ---- e2e: same metric through the public module call with HOST buffers (pinned), copies inside the region.
-        # A serving loop: step i's input travels host -> device on a copy stream while step i-1 computes, its result
-        # travels back on a second copy stream; every step's H2D and D2H happen inside the timed region.
+        # ---- e2e: same metric through the package's host-buffer entry point (summarymixing_b200.HostPipeline) with HOST
+        # tensors: every step's H2D (x, mask) and D2H (y) are inside the timed region, overlapped with the neighbouring steps.
         hx = [x.to(torch.bfloat16).pin_memory() for x, _ in host[:4]]
         hm = [m.pin_memory() for _, m in host[:4]]
-        hy = [torch.empty(B, T, D, dtype=torch.bfloat16).pin_memory() for _ in range(4)]
-        copy_stream = torch.cuda.Stream(dev)   # host -> device
-        back_stream = torch.cuda.Stream(dev)   # device -> host (its own stream: an in-order single copy stream would hold
-                                               # the next step's input behind this step's result)
-        main_stream = torch.cuda.current_stream(dev)
-        try:
-            if args.eager:
-                raise RuntimeError("eager requested")
-            gfs = [S.GraphedForward(enc, xs[0], ms[0]) for _ in range(2)]   # one graph per landing buffer
-            xd = [g.static_x for g in gfs]
-            md = [g.static_mask for g in gfs]
-            fwd = [g.replay for g in gfs]
-        except Exception:
-            xd = [torch.empty(B, T, D, dtype=torch.bfloat16, device=dev) for _ in range(2)]
-            md = [torch.empty(B, T, dtype=torch.bool, device=dev) for _ in range(2)]
-            fwd = [(lambda j=j: enc(xd[j], src_key_padding_mask=md[j])[0]) for j in range(2)]
-        in_ready = [torch.cuda.Event() for _ in range(2)]
-        in_free = [torch.cuda.Event() for _ in range(2)]
-        out_ready = [torch.cuda.Event() for _ in range(2)]
-        out_free = [torch.cuda.Event() for _ in range(2)]
-        yd = [torch.empty(B, T, D, dtype=torch.bfloat16, device=dev) for _ in range(2)]  # results wait here for their D2H
+        pipe = S.HostPipeline(enc, B, T, D, device=dev, use_graph=not args.eager)
 
         def e2e_loop(n):
-            for j in range(2):
-                in_free[j].record(main_stream)
-                out_free[j].record(back_stream)
-            for i in range(n):
-                j = i & 1
-                with torch.cuda.stream(copy_stream):
-                    copy_stream.wait_event(in_free[j])          # the forward that read this buffer has finished
-                    xd[j].copy_(hx[i % 4], non_blocking=True)
-                    md[j].copy_(hm[i % 4], non_blocking=True)
-                    in_ready[j].record(copy_stream)
-                main_stream.wait_event(in_ready[j])
-                y = fwd[j]()
-                in_free[j].record(main_stream)
-                main_stream.wait_event(out_free[j])             # the D2H that read this staging buffer has finished
-                yd[j].copy_(y)
-                out_ready[j].record(main_stream)
-                with torch.cuda.stream(back_stream):
-                    back_stream.wait_event(out_ready[j])
-                    hy[i % 4].copy_(yd[j], non_blocking=True)
-                    out_free[j].record(back_stream)
-            main_stream.wait_stream(copy_stream)
-            main_stream.wait_stream(back_stream)                # the last result is on the host when the region ends
+            last = None
+            for last in pipe.run(((hx[i % 4], hm[i % 4]) for i in range(n))):
+                pass
+            return last
 
         e2e_loop(3)
         barrier()
@@ -362,15 +355,17 @@ def run_smx(args):
     line = {"metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": "cfg2: 12-layer SummaryMixing-Conformer encoder forward, D=256 d_ffn=1024 h=4 k=31, "
-                                   "B=32 x T=1000 padded batch per GPU", "frames_per_step": world * B * T,
+            "config": config(world),
+            "details": {"frames_per_step": world * B * T,
                        "parallelism": f"utterance-sharded x{world} (no collective)",
                        "l2": f"inputs rotate over {N_ROTATE} distinct batches ({N_ROTATE * B * T * D * 2 / 1e6:.0f} MB "
                              "of x > 126 MB L2) so no step finds its input in L2",
                        "accumulate": "fp32", "io": "bf16", "launch": mode},
-            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": B * T * D * 2 + B * T,
-                    "d2h_bytes_per_step": B * T * D * 2, "ms_per_step": e2e_ms / args.steps,
-                    "api": "summarymixing_b200.GraphedForward(ConformerEncoder) (CUDA-graph replay of ConformerEncoder.forward); pinned host inputs/outputs, H2D and D2H on their own streams, overlapped with the previous/next step"},
+            "e2e": {"value": e2e_value, "unit": "frames/s", "h2d_bytes_per_step": pipe.h2d_bytes_per_step,
+                    "d2h_bytes_per_step": pipe.d2h_bytes_per_step, "ms_per_step": e2e_ms / args.steps,
+                    "api": "summarymixing_b200.HostPipeline(ConformerEncoder).run(host batches): pinned host inputs/outputs, H2D and "
+                           "D2H on their own streams inside the timed region, overlapped with the previous/next step; forward = "
+                           "CUDA-graph replay of ConformerEncoder.forward"},
             "gpu_launches": launches, "tc_launches": tc_launches, "clocks": clocks}
 
     if rank == 0:
@@ -383,18 +378,28 @@ def run_smx(args):
         bytes_cell = frames * ((D + D) * 2 + 1)
         flops_cell = frames * (4 * 2 * HEADS * hd * hd + 2 * D * D)
         us = mod["cell"]["us"]
-        line["roofline"] = {"kernel": f"smx_summary_mixing_fwd (SummaryMixing cell, {mod['cell']['launches']} launches)",
+        tr = ksm_traffic()
+        traffic = tr["dram_bytes_per_call"] if tr else None
+        line["roofline"] = {"kernel": f"smx_mixing_block_fwd: norm1 + SummaryMixing cell + skip ({mod['cell']['launches']} launch(es); "
+                                      "the unit the fused cell kernel executes inside a layer)",
                             "bound": "hbm", "achieved": bytes_cell / us / 1e3, "peak": pk["hbm_gbs"], "unit": "GB/s",
                             "frac": bytes_cell / us / 1e3 / pk["hbm_gbs"],
-                            # dram__bytes_read+write per cell call from the ncu --set full capture summarised in
-                            # profiles/r01_call117_ncu_layer_summary.csv (pass A 16.53 MB + finalise 0.58 MB + pass B 16.73 MB
-                            # read, 0.23 MB written: most of the 16.4 MB output was still in L2 when the window closed)
-                            "traffic": 34.08e6, "algorithmic_bytes": bytes_cell,
+                            "traffic": traffic, "traffic_ratio": (traffic / bytes_cell) if traffic else None,
+                            "traffic_source": (tr or {}).get("source"), "algorithmic_bytes": bytes_cell,
                             "us_per_call": us, "peak_source": pk["source"] + " (burst copy)",
-                            "tensor_tflops": flops_cell / us / 1e6, "tensor_frac": flops_cell / us / 1e6 / pk["bf16_tflops"]}
+                            "tensor_tflops": flops_cell / us / 1e6, "tensor_frac": flops_cell / us / 1e6 / pk["bf16_tflops"],
+                            # what bounds this kernel in practice: one MUFU.TANH per activation, 5 activations per element,
+                            # 16 MUFU/clk/SM (tools/micro/tmem_bench.cu): frames * 5 * D / (16 * SMs * clock)
+                            "mufu_floor_us": frames * 5 * D / (16 * 148 * 1.965e3)}
         flops_ffn = frames * 4 * D * FFN
         flops_conv = frames * 2 * D * 3 * D
         step_us = ms_step * 1e3
+        # whole step: FLOPs as executed per frame and layer (2 FFNs, cell with block-diagonal MLPs + split combiner, conv module)
+        flops_step = LAYERS * (2 * flops_ffn + flops_cell + flops_conv + frames * 2 * 31 * D)
+        line["roofline_step"] = {"bound": "tensor", "flops": flops_step, "achieved": flops_step / step_us / 1e6,
+                                 "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                                 "frac": flops_step / step_us / 1e6 / pk["bf16_tflops_sustained"],
+                                 "peak_source": pk["source"] + " (sustained cuBLAS bf16)"}
         line["kernels"] = {
             "cell": {"us": us, "launches": mod["cell"]["launches"], "share_of_step": LAYERS * us / step_us},
             "ffn": {"us": mod["ffn"]["us"], "launches": mod["ffn"]["launches"],

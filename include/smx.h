@@ -307,6 +307,23 @@ SMX_API int smx_ffn_fwd(const smx_ffn_weights* w, int act, int dtype, int64_t ro
 
 /* ---- encoder blocks ------------------------------------------------------------------------- */
 
+/* The mixing block of ConformerEncoderLayer.forward: y = x + SummaryMixing(LayerNorm(x)) -- skip = x; x = norm1(x);
+ * x = mha_layer(x, ...); x = x + skip (Conformer.py:520-541).  This is the unit the fused cell kernel executes inside a
+ * layer (norm1 as its prologue, the skip as its epilogue) and the one bench.py reports the K-SM roofline on.
+ * Requires summary_out_dim == enc_dim (the layer passes summary_out_dim=d_model, Conformer.py:446-457). */
+SMX_API size_t smx_mixing_block_workspace_bytes(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, int has_sum_mask);
+SMX_API int smx_mixing_block_fwd(const smx_cell_weights* w, const float* norm_w, const float* norm_b, int dtype, int32_t B, int32_t T,
+                         const void* x, const uint8_t* padding_mask, const float* sum_mask, void* y, void* workspace,
+                         size_t workspace_bytes, void* stream);
+
+/* The same block over n independent padded batches (same B, T; xs[i] -> ys[i]), enqueued back to back: the kernels chain by
+ * programmatic dependent launch and the fused cell's per-utterance counters for all n calls are cleared by one memset ahead of
+ * the chain (as smx_conformer_encoder_fwd does for its layers).  workspace: smx_mixing_block_workspace_bytes() +
+ * n * 4096 + n * 8 * B bytes. */
+SMX_API int smx_mixing_block_fwd_batch(const smx_cell_weights* w, const float* norm_w, const float* norm_b, int dtype, int32_t B,
+                               int32_t T, int32_t n, const void* const* xs, const uint8_t* padding_mask, void* const* ys,
+                               void* workspace, size_t workspace_bytes, void* stream);
+
 /* ConformerEncoderLayer.forward (Conformer.py:490-548). */
 SMX_API size_t smx_conformer_layer_workspace_bytes(const smx_conformer_layer_weights* w, int dtype, int32_t B, int32_t T,
                                            int has_sum_mask);

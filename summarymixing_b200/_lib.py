@@ -131,6 +131,10 @@ _PROTOS = {
     "smx_conv_module_fwd": (_i, [C.POINTER(ConvModWeights), _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "smx_ffn_workspace_bytes": (_sz, [C.POINTER(FFNWeights), _i, _i64]),
     "smx_ffn_fwd": (_i, [C.POINTER(FFNWeights), _i, _i, _i64, _vp, _vp, _vp, _f, _vp, _vp, _sz, _vp]),
+    "smx_mixing_block_workspace_bytes": (_sz, [C.POINTER(CellWeights), _i, _i, _i, _i]),
+    "smx_mixing_block_fwd": (_i, [C.POINTER(CellWeights), _vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
+    "smx_mixing_block_fwd_batch": (_i, [C.POINTER(CellWeights), _vp, _vp, _i, _i, _i, _i, C.POINTER(C.c_void_p), _vp,
+                                        C.POINTER(C.c_void_p), _vp, _sz, _vp]),
     "smx_conformer_layer_workspace_bytes": (_sz, [C.POINTER(ConformerLayerWeights), _i, _i, _i, _i]),
     "smx_conformer_layer_fwd": (_i, [C.POINTER(ConformerLayerWeights), _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "smx_conformer_encoder_workspace_bytes": (_sz, [C.POINTER(ConformerLayerWeights), _i, _i, _i, _i, _i]),

@@ -369,6 +369,53 @@ struct PresyncGuard {
 };
 
 // ---- Conformer layer / encoder -------------------------------------------------------------------
+size_t smx_mixing_block_workspace_bytes(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, int has_sum_mask) {
+  if (!w || B <= 0 || T <= 0) return 0;
+  Arena a(nullptr, 0, true);
+  const float* sm = has_sum_mask ? (const float*)(uintptr_t)256 : nullptr;
+  if (mixing_block_generic(w, kDummy, kDummy, dtype, B, T, nullptr, nullptr, sm, nullptr, a, nullptr) != SMX_OK) return 0;
+  return a.peak + tc_cell4_sync_bytes(B);
+}
+int smx_mixing_block_fwd(const smx_cell_weights* w, const float* norm_w, const float* norm_b, int dtype, int32_t B, int32_t T,
+                         const void* x, const uint8_t* padding_mask, const float* sum_mask, void* y, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  if (!w || !norm_w || !norm_b) return fail(SMX_ERR_BAD_ARG, "weights / norm parameters are NULL");
+  SMX_TRY(check_bt(B, T));
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(y, "y"));
+  SMX_TRY(check_arch());
+  size_t need = smx_mixing_block_workspace_bytes(w, dtype, B, T, sum_mask != nullptr);
+  if (need == 0) return fail(SMX_ERR_BAD_ARG, "mixing block: unsupported configuration (summary_out_dim must equal enc_dim)");
+  if (need > workspace_bytes || !workspace)
+    return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  PresyncGuard presync(workspace, tc_cell4_sync_bytes(B), dtype == SMX_BF16, (cudaStream_t)stream);
+  if (presync.status != SMX_OK) return presync.status;
+  Arena a((char*)workspace + presync.bytes, workspace_bytes - presync.bytes, false);
+  return mixing_block_generic(w, norm_w, norm_b, dtype, B, T, x, padding_mask, sum_mask, y, a, (cudaStream_t)stream);
+}
+
+int smx_mixing_block_fwd_batch(const smx_cell_weights* w, const float* norm_w, const float* norm_b, int dtype, int32_t B, int32_t T,
+                               int32_t n, const void* const* xs, const uint8_t* padding_mask, void* const* ys, void* workspace,
+                               size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  if (!w || !norm_w || !norm_b || !xs || !ys || n <= 0) return fail(SMX_ERR_BAD_ARG, "weights / norm parameters / batch lists are NULL");
+  SMX_TRY(check_bt(B, T));
+  SMX_TRY(check_arch());
+  const size_t one = smx_mixing_block_workspace_bytes(w, dtype, B, T, 0);
+  if (one == 0) return fail(SMX_ERR_BAD_ARG, "mixing block: unsupported configuration (summary_out_dim must equal enc_dim)");
+  const size_t sync_all = (size_t)n * tc_cell4_sync_bytes(B);
+  if (one + sync_all > workspace_bytes || !workspace)
+    return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", one + sync_all, workspace_bytes);
+  PresyncGuard presync(workspace, sync_all, dtype == SMX_BF16, (cudaStream_t)stream);
+  if (presync.status != SMX_OK) return presync.status;
+  for (int i = 0; i < n; ++i) {
+    SMX_TRY(check_ptr(xs[i], "xs[i]")); SMX_TRY(check_ptr(ys[i], "ys[i]"));
+    Arena a((char*)workspace + presync.bytes, workspace_bytes - presync.bytes, false);
+    SMX_TRY(mixing_block_generic(w, norm_w, norm_b, dtype, B, T, xs[i], padding_mask, nullptr, ys[i], a, (cudaStream_t)stream));
+  }
+  return SMX_OK;
+}
+
 size_t smx_conformer_layer_workspace_bytes(const smx_conformer_layer_weights* w, int dtype, int32_t B, int32_t T,
                                            int has_sum_mask) {
   if (!w || B <= 0 || T <= 0) return 0;

@@ -251,6 +251,43 @@ int convmod_generic(const smx_convmod_weights* w, int act, int B, int T, int chu
 // tcgen05 arm when its weights carry a packed image and the configuration is supported, else on the
 // generic arm (which reads/writes bf16 through the dtype tags).
 // ---------------------------------------------------------------------------------------------
+// y = x + SummaryMixing(LayerNorm(x)): the mixing block of the Conformer layer (skip = x; x = norm1(x); x = mha_layer(x);
+// x = x + skip, Conformer.py:520-541).  bf16 with a packed cell: the fused tcgen05 kernel(s) with the LayerNorm as prologue
+// and the skip as epilogue; otherwise LayerNorm + generic cell.
+int mixing_block_generic(const smx_cell_weights* cw, const float* norm_w, const float* norm_b, int dtype, int B, int T, const void* x1,
+                         const uint8_t* mask, const float* sum_mask, void* x2, Arena& ws, cudaStream_t st) {
+  const int64_t rows = (int64_t)B * T;
+  const int D = cw->enc_dim;
+  const int idt = dtype;
+  if (dtype == SMX_BF16 && cw->packed && tc_cell_supported(cw, sum_mask != nullptr)) {
+    if (cw->merge.out_dim != D) return fail(SMX_ERR_BAD_ARG, "mixing block: cell output dim != d_model");
+    return tc_cell_fwd(cw, cw->packed, B, T, (const __nv_bfloat16*)x1, norm_w, norm_b, mask, (const __nv_bfloat16*)x1,
+                       (__nv_bfloat16*)x2, ws, st);
+  }
+  const size_t m1 = ws.mark();
+  float* n1 = ws.f32((size_t)rows * D);
+  if (!n1) return fail(SMX_ERR_WORKSPACE, "workspace too small (mixing block norm1)");
+  if (!ws.dry) SMX_TRY(layernorm(x1, idt, D, norm_w, norm_b, 1e-5f, SMX_ACT_IDENTITY, n1, SMX_F32, D, rows, D, st));
+  if (cw->mode == SMX_MODE_LITE) {
+    if (cw->summary_out_dim != D) return fail(SMX_ERR_BAD_ARG, "mixing block: lite summary_out_dim != d_model");
+    float* mean = ws.f32((size_t)B * D);
+    float* x1f = (idt == SMX_F32) ? (float*)x1 : ws.f32((size_t)rows * D);
+    float* x2f = (idt == SMX_F32) ? (float*)x2 : ws.f32((size_t)rows * D);
+    if (!mean || !x1f || !x2f) return fail(SMX_ERR_WORKSPACE, "workspace too small (mixing block lite)");
+    SMX_TRY(cell_generic(cw, B, T, n1, SMX_F32, mask, sum_mask, nullptr, 0, mean, SMX_F32, D, ws, st));
+    if (!ws.dry) {
+      if (idt != SMX_F32) SMX_TRY(convert(x1, idt, x1f, SMX_F32, rows * D, st));
+      SMX_TRY(add_bcast(x1f, mean, rows, T, D, x2f, st));
+      if (idt != SMX_F32) SMX_TRY(convert(x2f, SMX_F32, x2, idt, rows * D, st));
+    }
+  } else {
+    if (cw->merge.out_dim != D) return fail(SMX_ERR_BAD_ARG, "mixing block: cell output dim != d_model");
+    SMX_TRY(cell_generic(cw, B, T, n1, SMX_F32, mask, sum_mask, x1, idt, x2, idt, D, ws, st));
+  }
+  ws.release(m1);
+  return SMX_OK;
+}
+
 int conformer_layer_generic(const smx_conformer_layer_weights* w, int dtype, int B, int T, int chunk, const void* x,
                             const uint8_t* mask, const float* sum_mask, void* y, Arena& ws, cudaStream_t st) {
   const int64_t rows = (int64_t)B * T;
@@ -268,34 +305,7 @@ int conformer_layer_generic(const smx_conformer_layer_weights* w, int dtype, int
   else
     SMX_TRY(ffn_generic(&w->ffn1, w->act, rows, x, dtype, nullptr, nullptr, 0.f, x1, idt, ws, st));
   // x2 = cell(norm1(x1)) + x1                                                          :520-541
-  if (bf && w->cell.packed && tc_cell_supported(&w->cell, sum_mask != nullptr)) {
-    if (w->cell.merge.out_dim != D) return fail(SMX_ERR_BAD_ARG, "conformer layer: cell output dim != d_model");
-    SMX_TRY(tc_cell_fwd(&w->cell, w->cell.packed, B, T, (const __nv_bfloat16*)x1, w->norm1_w, w->norm1_b, mask,
-                        (const __nv_bfloat16*)x1, (__nv_bfloat16*)x2, ws, st));
-  } else {
-    const size_t m1 = ws.mark();
-    float* n1 = ws.f32((size_t)rows * D);
-    if (!n1) return fail(SMX_ERR_WORKSPACE, "workspace too small (conformer layer norm1)");
-    if (!ws.dry)
-      SMX_TRY(layernorm(x1, idt, D, w->norm1_w, w->norm1_b, 1e-5f, SMX_ACT_IDENTITY, n1, SMX_F32, D, rows, D, st));
-    if (w->cell.mode == SMX_MODE_LITE) {
-      if (w->cell.summary_out_dim != D) return fail(SMX_ERR_BAD_ARG, "conformer layer: lite summary_out_dim != d_model");
-      float* mean = ws.f32((size_t)B * D);
-      float* x1f = (idt == SMX_F32) ? (float*)x1 : ws.f32((size_t)rows * D);
-      float* x2f = (idt == SMX_F32) ? (float*)x2 : ws.f32((size_t)rows * D);
-      if (!mean || !x1f || !x2f) return fail(SMX_ERR_WORKSPACE, "workspace too small (conformer layer lite)");
-      SMX_TRY(cell_generic(&w->cell, B, T, n1, SMX_F32, mask, sum_mask, nullptr, 0, mean, SMX_F32, D, ws, st));
-      if (!ws.dry) {
-        if (idt != SMX_F32) SMX_TRY(convert(x1, idt, x1f, SMX_F32, rows * D, st));
-        SMX_TRY(add_bcast(x1f, mean, rows, T, D, x2f, st));
-        if (idt != SMX_F32) SMX_TRY(convert(x2f, SMX_F32, x2, idt, rows * D, st));
-      }
-    } else {
-      if (w->cell.merge.out_dim != D) return fail(SMX_ERR_BAD_ARG, "conformer layer: cell output dim != d_model");
-      SMX_TRY(cell_generic(&w->cell, B, T, n1, SMX_F32, mask, sum_mask, x1, idt, x2, idt, D, ws, st));
-    }
-    ws.release(m1);
-  }
+  SMX_TRY(mixing_block_generic(&w->cell, w->norm1_w, w->norm1_b, dtype, B, T, x1, mask, sum_mask, x2, ws, st));
   // x3 = x2 + conv_module(x2)*mask   (into x1, which is dead)                           :543-545
   if (bf && w->conv.packed && tc_convmod_supported(&w->conv, chunk))
     SMX_TRY(tc_convmod_fwd(&w->conv, w->conv.packed, w->act, B, T, (const __nv_bfloat16*)x2, mask, (const __nv_bfloat16*)x2,

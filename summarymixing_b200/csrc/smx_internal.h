@@ -101,6 +101,8 @@ int ffn_generic(const smx_ffn_weights* w, int act, int64_t rows, const void* x, 
 int convmod_generic(const smx_convmod_weights* w, int act, int B, int T, int chunk, const void* x, int x_dt,
                     const uint8_t* mask, const void* residual, int r_dt, void* y, int y_dt, Arena& ws,
                     cudaStream_t st);
+int mixing_block_generic(const smx_cell_weights* cw, const float* norm_w, const float* norm_b, int dtype, int B, int T, const void* x1,
+                         const uint8_t* mask, const float* sum_mask, void* x2, Arena& ws, cudaStream_t st);
 int conformer_layer_generic(const smx_conformer_layer_weights* w, int dtype, int B, int T, int chunk, const void* x,
                             const uint8_t* mask, const float* sum_mask, void* y, Arena& ws, cudaStream_t st);
 int branchformer_layer_generic(const smx_branchformer_layer_weights* w, int dtype, int B, int T, const void* x,

@@ -167,6 +167,15 @@ __device__ __forceinline__ void c4_bias_act32(float* v, const float* sB, int act
   }
 }
 
+// One copy of the in-place LayerNorm for both callers (epilogue warps: first tile, 8 rows each; prologue warps: second tile,
+// 4 x 8 rows each).  Code size matters here: every CTA executes the kernel's code at most twice, so instruction fetch is paid in
+// full -- ncu of the first build: 20 % of the stall samples were no_instructions, instruction-cache hit rate 59 %.
+static __device__ __noinline__ void c4_ln_rows(uint8_t* sX, int nrows, int D, int w0, int n_groups, int lane, const float* sW, const float* sB,
+                                               float2* sStat) {
+#pragma unroll 1
+  for (int i = 0; i < n_groups; ++i) tc::rows8_ln(sX, nrows, D, w0 + i, lane, sW, sB, sStat);
+}
+
 template <int ACT>  // ACT >= 0: compile-time smx_act, -1: runtime p.act
 __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_constant__ CUtensorMap tmap_x, const C4P p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -235,16 +244,21 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       };
       int s = 0, issued = 0;
       uint32_t pe = 0;
+#pragma unroll 1
       for (int ph = 0; ph < 2; ++ph) {
+#pragma unroll 1
         for (int t = 0; t < ntl; ++t) {
           const uint8_t* src = p.img + (ph ? p.img_p2_off : 0u);
           const int h0 = ph ? 4 : 0, h1 = ph ? 10 : 4;
+#pragma unroll 1
           for (int h = h0; h < h1; ++h) {
             const int gw = p.hg[h].gw, nun = p.hg[h].n_units, ups = 2 / gw;
             if (h == 8 && p.c0_in_x) {
               // the combiner's first half goes into this tile's X buffer, dead once GEMM 1 of the local branch has read it:
               // all of it is in flight while the epilogue warps are busy with E1 / E2, so the combiner runs at tensor speed
+              C4_TRACE(0, 2 * t);
               tc::mbar_wait(&x_dead[t], 0);
+              C4_TRACE(0, 2 * t + 1);
               tc::mbar_arrive_expect_tx(&c_full[t], p.c0_bytes);
               for (uint32_t o = 0; o < p.c0_bytes; o += C4_SLOT)
                 tc::bulk_g2s(smem + (size_t)t * xtile_bytes + o, src + o, p.c0_bytes - o < C4_SLOT ? p.c0_bytes - o : C4_SLOT, &c_full[t]);
@@ -323,13 +337,16 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       tc::mbar_wait_spin(bar, (pb >> bit) & 1u);
       pb ^= 1u << bit;
     };
+#pragma unroll 1
     for (int ph = 0; ph < 2; ++ph) {
       const int hb = ph ? 4 : 0;
       const int n1h = ph ? p.n1f_h : p.n1s_h;
       const int both = ph ? p.g2f_both : p.g2s_both;
+#pragma unroll 1
       for (int t = 0; t < ntl; ++t) {
         const uint32_t xaddr = sx0 + (uint32_t)t * xtile_bytes;
         if (ph == 0) { tc::mbar_wait(&x_ready[t], 0); }
+#pragma unroll 1
         for (int c = 0; c < 2; ++c) {  // GEMM 1 of both chains
           wait_bit(&x_free[c], c);
           tc::tc_fence_after();
@@ -338,6 +355,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
           commit_to(&acc1_full[c]);
         }
         if (ph == 1 && p.c0_in_x) commit_to(&x_dead[t]);  // both chains' GEMM 1 have read the X tile: its buffer may be reused
+#pragma unroll 1
         for (int c = 0; c < 2; ++c) {  // GEMM 2 of both chains: A = H (Y regions), D = X_c again
           if (c == 0 || !both) wait_bit(&h_full[c], 2 + c);
           if (c == 0 && both) wait_bit(&h_full[1], 3);
@@ -349,11 +367,13 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
         if (ph == 1) {                 // combiner halves: A = L (Y regions), D = X_n
           wait_bit(&l_full, 4);
           tc::tc_fence_after();
+#pragma unroll 1
           for (int n = 0; n < 2; ++n) {
             C4_TRACE(1, ev++);
             if (n == 0 && p.c0_in_x) {  // weights of this half wait in the X buffer
               tc::mbar_wait_spin(&c_full[t], 0);
               tc::tc_fence_after();
+              C4_TRACE(1, 40 + t);
               const C4Half& H = p.hg[8];
               const uint32_t idesc = tc::make_idesc_bf16(128, 64u * H.gw);
               if (tc::elect_one()) {
@@ -387,10 +407,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       const int t0 = (tile % p.tpu) * 128;
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
       tc::mbar_wait(&x_raw[1], 0);
-      if (p.pre_w) {
-#pragma unroll 1
-        for (int i = 0; i < 4; ++i) tc::rows8_ln(smem + xtile_bytes, nrows, p.D, pw * 4 + i, lane, sPar + 1792, sPar + 2064, sStat + 128);
-      }
+      if (p.pre_w) c4_ln_rows(smem + xtile_bytes, nrows, p.D, pw * 4, 4, lane, sPar + 1792, sPar + 2064, sStat + 128);
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&x_ready[1]);
@@ -400,6 +417,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
     float* sPart = sFin + 256;    // [4][256]
     float* sR = sFin + 1280;      // [16]
     const int Ds = p.Ds, Dout = p.Dout;
+#pragma unroll 1
     for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
       if (ftid == 0) c4_spin_until_ge(p.cnt + b, p.tpu);
       tc::named_bar_sync(6, 128);
@@ -407,6 +425,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       float cntf = (float)p.T;
       if (p.mask) {
         float cc = 0.0f;
+#pragma unroll 2
         for (int t = ftid; t < p.T; t += 128) cc += (float)p.mask[(size_t)b * p.T + t];
 #pragma unroll
         for (int o = 16; o; o >>= 1) cc += __shfl_xor_sync(0xffffffffu, cc, o);
@@ -415,10 +434,12 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
         cntf = (sR[0] + sR[1]) + (sR[2] + sR[3]);
       }
       float loc[2] = {0.0f, 0.0f};
+#pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int d = ftid + 128 * j;
         if (d < Ds) {
           float sacc = 0.0f;
+#pragma unroll 4
           for (int i = 0; i < p.tpu; ++i) sacc += __ldcg(p.colsum + ((size_t)b * p.tpu + i) * Ds + d);  // fixed order: deterministic
           loc[j] = sacc / cntf;
         }
@@ -513,13 +534,14 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       const int t0 = (tile % p.tpu) * 128;
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
       tc::mbar_wait(&x_raw[0], 0);
-      if (p.pre_w) tc::rows8_ln(smem, nrows, p.D, warp, lane, sPar + 1792, sPar + 2064, sStat);
+      if (p.pre_w) c4_ln_rows(smem, nrows, p.D, warp, 1, lane, sPar + 1792, sPar + 2064, sStat);
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&x_ready[0]);
     }
     int ev = 0;
     // =============================== phase 1: summary branch ===============================
+#pragma unroll 1
     for (int t = 0; t < ntl; ++t) {
       const int tile = (int)blockIdx.x + t * (int)gridDim.x;
       const int b = tile / p.tpu, t0 = (tile % p.tpu) * 128;
@@ -527,10 +549,11 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
       const float rscale = r < nrows ? (p.mask ? (float)p.mask[row0 + r] : 1.0f) : 0.0f;
       if (warp == 0) C4_TRACE(3, ev++);
-      e1(0, sPar, p.n1s_h);
-      e1(1, sPar, p.n1s_h);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) e1(c, sPar, p.n1s_h);
       if (warp == 0) C4_TRACE(3, ev++);
       // E2': S = act(acc2 + b2) * mask -> column sums of this tile                                summary_mixing.py:221, 229-231
+#pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         wait_bit(&acc2_full[c], 2 + c);
         if (k4 * 32 < p.n2s_h) {
@@ -563,6 +586,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
     tc::pdl_wait();  // the residual is read straight from global memory from here on
     const bool use_ln = p.lnl_w != nullptr;
     const int np2 = p.n2f_h >> 5;  // 32-column pieces per half of the local branch output
+#pragma unroll 1
     for (int t = 0; t < ntl; ++t) {
       const int tile = (int)blockIdx.x + t * (int)gridDim.x;
       const int b = tile / p.tpu, t0 = (tile % p.tpu) * 128;
@@ -571,8 +595,8 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       const bool live = r < nrows;
       const float rscale = live ? (p.mask ? (float)p.mask[row0 + r] : 1.0f) : 0.0f;
       if (warp == 0) C4_TRACE(3, ev++);
-      e1(0, sPar + 512, p.n1f_h);
-      e1(1, sPar + 512, p.n1f_h);
+#pragma unroll 1
+      for (int c = 0; c < 2; ++c) e1(c, sPar + 512, p.n1f_h);
       if (warp == 0) C4_TRACE(3, ev++);
       // E2a: v = act(acc2 + b2) * mask; with LayerNorm: per-thread (mean, M2) of its 32 values, v parked as fp32 in place;
       // without: L = v straight to Y_c                                                             summary_mixing.py:215-218
@@ -580,6 +604,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
         wait_bit(&acc2_full[0], 2);
         wait_bit(&acc2_full[1], 3);
       }
+#pragma unroll 1
       for (int c = 0; c < 2; ++c) {
         if (use_ln) wait_bit(&acc2_full[c], 2 + c);
         if (k4 < np2) {
@@ -615,17 +640,24 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       if (use_ln) {
         // E2b: Chan's merge of the row's 2 np2 partials (32 values each) in fixed order, then L = LN_l(v) -> Y_c
         tc::named_bar_sync(1 + q, 128);
-        float mean = 0.0f, m2 = 0.0f, n = 0.0f;
+        // the row's 2 np2 partials (mean_i, M2_i of 32 values each), in fixed order: mean = avg(mean_i),
+        // M2 = sum M2_i + 32 sum (mean_i - mean)^2  (no divisions: every partial has the same count)
+        const float2* pp = reinterpret_cast<const float2*>(sRed) + r;
+        const float inv_np = np2 == 4 ? 0.125f : 0.25f;
+        float msum = 0.0f, m2 = 0.0f;
+#pragma unroll 1
         for (int c = 0; c < 2; ++c)
-          for (int i = 0; i < np2; ++i) {
-            const float2 pr = reinterpret_cast<const float2*>(sRed)[(c * 4 + i) * 128 + r];
-            const float dl = pr.x - mean, nn = n + 32.0f;
-            mean += dl * (32.0f / nn);
-            m2 += pr.y + dl * dl * (n * 32.0f / nn);
-            n = nn;
-          }
-        const float rstd = rsqrtf(m2 / n + 1e-5f), shift = -mean * rstd;
+#pragma unroll 1
+          for (int i = 0; i < np2; ++i) { const float2 pr = pp[(c * 4 + i) * 128]; msum += pr.x; m2 += pr.y; }
+        const float mean = msum * inv_np;
+        float dev2 = 0.0f;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c)
+#pragma unroll 1
+          for (int i = 0; i < np2; ++i) { const float d = pp[(c * 4 + i) * 128].x - mean; dev2 = fmaf(d, d, dev2); }
+        const float rstd = rsqrtf(fmaf(32.0f, dev2, m2) * (inv_np * (1.0f / 32.0f)) + 1e-5f), shift = -mean * rstd;
         if (warp == 0) C4_TRACE(3, ev++);
+#pragma unroll 1
         for (int c = 0; c < 2; ++c) {
           if (k4 < np2) {
             float v[32];
@@ -678,6 +710,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       if (etid < p.Dout) sRB[etid] = BSC * __ldcg(p.rowbias + (size_t)b * p.Dout + etid);
       tc::named_bar_sync(5, C4_NEW * 32);
       if (warp == 0) C4_TRACE(3, ev++);
+#pragma unroll 1
       for (int n = 0; n < 2; ++n) {
         const int col = n * p.dout_h + k4 * 32;
         wait_bit(&acc3_full[n], 4 + n);

@@ -46,5 +46,7 @@ iss, epi = t[64:128], t[192:256]
 nz = t[t > 0]
 if nz.numel():
     t0 = int(nz.min())
-    print("issuer  :", " ".join(f"{int(v) - t0:6d}" for v in iss if int(v)))
+    print("producer (c0 wait x_dead / issue):", " ".join(f"{int(v) - t0:6d}" for v in t[0:4]))
+    print("issuer after c_full:", " ".join(f"{int(v) - t0:6d}" for v in t[64 + 40:64 + 42]))
+    print("issuer  :", " ".join(f"{int(v) - t0:6d}" for v in iss[:40] if int(v)))
     print("epilogue:", " ".join(f"{int(v) - t0:6d}" for v in epi if int(v)))
