@@ -258,6 +258,66 @@ def time_module_calls(enc, x, mask, iters: int):
     return out
 
 
+def other_configs(dev, steps: int = 5):
+    """Device-resident forward throughput of BASELINE.json configs[2] and [3] at their real model dims, one GPU:
+    cfg3 = conformer_large (conformer_summarymixing.yaml:113-125: 12 layers, D=512, h=8, d_ffn=2048), B=32 x T=1000;
+    cfg4 = Branchformer SummaryMixing-lite (branchformer_summarymixing.yaml:112-127: 18 layers, D=512, csgu 3072), variable-length
+    padded batch, B=16, lengths uniform in [200,3000].  Frames = B*T padded (cfg4 also reports valid frames/s)."""
+    import torch
+
+    import summarymixing_b200 as S
+    from summarymixing_b200 import _lib as L
+
+    out = {}
+    lib = L.lib()
+
+    def timed(model, x, mask, valid_frames):
+        with torch.no_grad():
+            t0 = lib.smx_tc_launch_count()
+            for _ in range(2):
+                model(x, src_key_padding_mask=mask)
+            torch.cuda.synchronize()
+            tc = int(lib.smx_tc_launch_count() - t0) // 2
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(steps):
+                model(x, src_key_padding_mask=mask)
+            e1.record()
+            torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        Bx, Tx = x.shape[0], x.shape[1]
+        return {"ms_per_step": ms, "frames_per_s": Bx * Tx / ms * 1e3, "valid_frames_per_s": valid_frames / ms * 1e3,
+                "batch": Bx, "T": Tx, "tcgen05_launches_per_step": tc, "launch": "eager", "io": "bf16"}
+
+    g = torch.Generator().manual_seed(7)
+    try:
+        torch.manual_seed(3)
+        enc = S.ConformerEncoder(12, 512, 2048, 8, 31, attention_type="SummaryMixing", local_proj_hid_dim=[512], local_proj_out_dim=512,
+                                 summary_hid_dim=[512], mode="SummaryMixing").eval().to(dev)
+        x = torch.randn(32, 1000, 512, generator=g).to(torch.bfloat16).to(dev)
+        lens = torch.randint(500, 1001, (32,), generator=g)
+        lens[0] = 1000
+        mask = (torch.arange(1000)[None] < lens[:, None]).to(dev)
+        out["cfg3_conformer_large_D512"] = timed(enc, x, mask, int(lens.sum()))
+        del enc, x
+    except Exception as exc:  # a secondary line must never take the headline down
+        out["cfg3_conformer_large_D512"] = {"error": repr(exc)[:200]}
+    try:
+        torch.manual_seed(4)
+        enc = S.BranchformerEncoder(18, 512, 1, 31, csgu_linear_units=3072, local_proj_hid_dim=[512], local_proj_out_dim=512,
+                                    summary_hid_dim=[512], summary_out_dim=512, mode="SummaryMixing-lite").eval().to(dev)
+        lens = torch.randint(200, 3001, (16,), generator=g)
+        Tm = int(lens.max())
+        x = torch.randn(16, Tm, 512, generator=g).to(torch.bfloat16).to(dev)
+        mask = (torch.arange(Tm)[None] < lens[:, None]).to(dev)
+        out["cfg4_branchformer_lite_D512"] = timed(enc, x, mask, int(lens.sum()))
+        del enc, x
+    except Exception as exc:
+        out["cfg4_branchformer_lite_D512"] = {"error": repr(exc)[:200]}
+    torch.cuda.empty_cache()
+    return out
+
+
 def run_smx(args):
     import torch
     import torch.distributed as dist
@@ -411,6 +471,8 @@ def run_smx(args):
                      "tflops": flops_conv / mod["conv"]["us"] / 1e6,
                      "frac": flops_conv / mod["conv"]["us"] / 1e6 / pk["bf16_tflops_sustained"]},
         }
+        if world == 1 and not args.no_others:
+            line["other_configs"] = other_configs(dev)
         if world == 1 and not args.no_cpu:
             r = cpu_reference_throughput(enc.state_dict(), budget_s=20.0, steps=2, warmup=1)
             line["cpu_baseline"] = {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -426,6 +488,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="smx", choices=["smx", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-others", action="store_true", help="skip the cfg3 / cfg4 side measurements")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replay (ncu runs)")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -176,6 +176,7 @@ typedef struct {
   int32_t n_merge;                   /* blocks in merge_proj (Branchformer.py:220-226) */
   int32_t act;
   smx_linear merge[SMX_MAX_BLOCKS];
+  const void* packed;                /* bf16 operand images from smx_branchformer_pack(), or NULL (generic arm) */
 } smx_branchformer_layer_weights;
 
 /* ---- library info -------------------------------------------------------------------------- */
@@ -198,6 +199,8 @@ SMX_API size_t smx_cell_packed_bytes(const smx_cell_weights* w);
 SMX_API int smx_cell_pack(const smx_cell_weights* w, void* packed, size_t packed_bytes, void* stream);
 SMX_API size_t smx_ffn_packed_bytes(const smx_ffn_weights* w);
 SMX_API int smx_ffn_pack(const smx_ffn_weights* w, void* packed, size_t packed_bytes, void* stream);
+SMX_API size_t smx_branchformer_packed_bytes(const smx_branchformer_layer_weights* w); /* w->cell.packed must be set first */
+SMX_API int smx_branchformer_pack(const smx_branchformer_layer_weights* w, void* packed, size_t packed_bytes, void* stream);
 SMX_API size_t smx_convmod_packed_bytes(const smx_convmod_weights* w);
 SMX_API int smx_convmod_pack(const smx_convmod_weights* w, void* packed, size_t packed_bytes, void* stream);
 

@@ -85,7 +85,7 @@ class ConvBranchWeights(C.Structure):
 class BranchformerLayerWeights(C.Structure):
     _fields_ = [("norm_mhsa_w", fp), ("norm_mhsa_b", fp), ("norm_conv_w", fp), ("norm_conv_b", fp),
                 ("cell", CellWeights), ("branch", ConvBranchWeights), ("n_merge", C.c_int32), ("act", C.c_int32),
-                ("merge", Linear * SMX_MAX_BLOCKS)]
+                ("merge", Linear * SMX_MAX_BLOCKS), ("packed", C.c_void_p)]
 
 
 class SmxError(RuntimeError):
@@ -107,6 +107,8 @@ _PROTOS = {
     "smx_cell_pack": (_i, [C.POINTER(CellWeights), _vp, _sz, _vp]),
     "smx_ffn_packed_bytes": (_sz, [C.POINTER(FFNWeights)]),
     "smx_ffn_pack": (_i, [C.POINTER(FFNWeights), _vp, _sz, _vp]),
+    "smx_branchformer_packed_bytes": (_sz, [C.POINTER(BranchformerLayerWeights)]),
+    "smx_branchformer_pack": (_i, [C.POINTER(BranchformerLayerWeights), _vp, _sz, _vp]),
     "smx_convmod_packed_bytes": (_sz, [C.POINTER(ConvModWeights)]),
     "smx_convmod_pack": (_i, [C.POINTER(ConvModWeights), _vp, _sz, _vp]),
     "smx_layernorm_fwd": (_i, [_i, _i64, _i, _vp, _vp, _vp, _f, _vp, _vp]),

@@ -102,6 +102,13 @@ int smx_ffn_pack(const smx_ffn_weights* w, void* packed, size_t packed_bytes, vo
   SMX_TRY(check_arch());
   return tc_ffn_pack(w, packed, (cudaStream_t)stream);
 }
+size_t smx_branchformer_packed_bytes(const smx_branchformer_layer_weights* w) { return w ? tc_branchformer_packed_bytes(w) : 0; }
+int smx_branchformer_pack(const smx_branchformer_layer_weights* w, void* packed, size_t packed_bytes, void* stream) {
+  if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");
+  SMX_TRY(check_packed(packed, packed_bytes, tc_branchformer_packed_bytes(w)));
+  SMX_TRY(check_arch());
+  return tc_branchformer_pack(w, packed, (cudaStream_t)stream);
+}
 size_t smx_convmod_packed_bytes(const smx_convmod_weights* w) { return w ? tc_convmod_packed_bytes(w) : 0; }
 int smx_convmod_pack(const smx_convmod_weights* w, void* packed, size_t packed_bytes, void* stream) {
   if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");

@@ -159,8 +159,20 @@ int cell_generic(const smx_cell_weights* w, int B, int T, const void* x, int x_d
     float* rs = ws.f32((size_t)T);
     float* Sm = ws.f32((size_t)rows * Dsum);
     cbias = ws.f32((size_t)rows * Dout);
-    if (!rs || !Sm || !cbias) return fail(SMX_ERR_WORKSPACE, "workspace too small (cell sum_mask)");
+    // Dynamic-chunk masks (TransformerASR.py:85-110) have rows that are single runs of ones: per-frame summaries are then
+    // differences of prefix sums over time, O(T D) per utterance.  The structure is checked on the device; any other mask
+    // (weights, holes, the Laplace matrix of -expdecay) takes the (T,T) @ (T,D) product below instead.
+    const bool try_intervals = (mode != SMX_MODE_EXPDECAY);
+    int* iv = try_intervals ? (int*)ws.take((size_t)(2 * T + 1) * sizeof(int)) : nullptr;
+    void* pws = try_intervals ? ws.take(interval_means_workspace_bytes(B, T, Dsum)) : nullptr;
+    if (!rs || !Sm || !cbias || (try_intervals && (!iv || !pws))) return fail(SMX_ERR_WORKSPACE, "workspace too small (cell sum_mask)");
     if (!ws.dry) {
+      int* not_interval = nullptr;
+      if (try_intervals) {
+        not_interval = iv + 2 * T;
+        SMX_TRY(interval_detect(Mx, T, iv, iv + T, not_interval, st));
+        SMX_TRY(interval_means(S, ld_S, B, T, Dsum, iv, iv + T, not_interval, Sm, pws, st));
+      }
       SMX_TRY(rowsum(Mx, T, T, rs, st));
       GemmP p = base_gemm();  // Sm[b] = (Mx @ S[b]) / rowsum(Mx)   (padding NOT removed from the denominator, :239-246)
       p.A = Mx; p.a_dtype = SMX_F32; p.lda = T; p.a_bs = 0;
@@ -168,6 +180,7 @@ int cell_generic(const smx_cell_weights* w, int B, int T, const void* x, int x_d
       p.rowdiv = rs;
       p.C = Sm; p.c_dtype = SMX_F32; p.ldc = Dsum; p.c_bs = (int64_t)T * Dsum;
       p.M = T; p.N = Dsum; p.K = T; p.batches = B;
+      p.run_if_nonzero = not_interval;  // (NULL for -expdecay: always)
       SMX_TRY(gemm(p, st));
       if (use_ln)
         SMX_TRY(layernorm(Sm, SMX_F32, Dsum, w->summary_norm_w, w->summary_norm_b, 1e-5f, SMX_ACT_IDENTITY, Sm, SMX_F32, Dsum, rows, Dsum, st));
@@ -260,6 +273,16 @@ int mixing_block_generic(const smx_cell_weights* cw, const float* norm_w, const 
   const int D = cw->enc_dim;
   const int idt = dtype;
   if (dtype == SMX_BF16 && cw->packed && tc_cell_supported(cw, sum_mask != nullptr)) {
+    if (cw->mode == SMX_MODE_LITE) {  // the cell returns one row per utterance (:318-322); x2 = x1 + that row
+      if (cw->summary_out_dim != D) return fail(SMX_ERR_BAD_ARG, "mixing block: lite summary_out_dim != d_model");
+      const size_t m1 = ws.mark();
+      __nv_bfloat16* mean = (__nv_bfloat16*)ws.take((size_t)B * D * 2);
+      if (!mean) return fail(SMX_ERR_WORKSPACE, "workspace too small (mixing block lite)");
+      SMX_TRY(tc_cell_fwd(cw, cw->packed, B, T, (const __nv_bfloat16*)x1, norm_w, norm_b, mask, nullptr, mean, ws, st));
+      if (!ws.dry) SMX_TRY(tc_add_bcast((const __nv_bfloat16*)x1, mean, rows, T, D, (__nv_bfloat16*)x2, st));
+      ws.release(m1);
+      return SMX_OK;
+    }
     if (cw->merge.out_dim != D) return fail(SMX_ERR_BAD_ARG, "mixing block: cell output dim != d_model");
     return tc_cell_fwd(cw, cw->packed, B, T, (const __nv_bfloat16*)x1, norm_w, norm_b, mask, (const __nv_bfloat16*)x1,
                        (__nv_bfloat16*)x2, ws, st);
@@ -335,6 +358,8 @@ int branchformer_layer_generic(const smx_branchformer_layer_weights* w, int dtyp
   const int Dcat = Dx1 + D;
   if (w->n_merge < 1 || w->merge[0].in_dim != Dcat)
     return fail(SMX_ERR_BAD_ARG, "merge_proj expects %d inputs but the branches provide %d", w->n_merge < 1 ? -1 : w->merge[0].in_dim, Dcat);
+  if (dtype == SMX_BF16 && w->packed && tc_branchformer_supported(w, sum_mask != nullptr))   // tensor-core arm (smx_tc_branch.cu)
+    return tc_branchformer_layer_fwd(w, B, T, (const __nv_bfloat16*)x, mask, (__nv_bfloat16*)y, ws, st);
   const size_t m0 = ws.mark();
   float* n = ws.f32((size_t)rows * D);
   float* cat = ws.f32((size_t)rows * Dcat);

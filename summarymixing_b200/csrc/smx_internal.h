@@ -61,6 +61,7 @@ struct GemmP {
   int M, N, K, batches, act;
   // optional outer batch level (0 means 1): blockIdx.z = outer * batches + inner; the outer index adds these offsets
   int batches2;  int64_t a_bs2;  int64_t w_bs2;  int64_t c_bs2;
+  const int* run_if_nonzero;                                     // device flag (NULL: always run): the kernel returns at once when *flag == 0
 };
 int gemm(const GemmP& p, cudaStream_t st);
 int layernorm(const void* x, int x_dtype, int64_t ldx, const float* w, const float* b, float eps, int act,
@@ -76,6 +77,14 @@ int broadcast_rows(const float* src, int B, int T, int D, float* dst, int64_t ld
 int add_bcast(const float* a, const float* s, int64_t rows, int div, int D, float* out, cudaStream_t st);
 int laplace(float decay, const float* binary, int T, float* out, cudaStream_t st);
 int rowsum(const float* m, int rows, int cols, float* out, cudaStream_t st);
+// Per-frame summaries for a (T,T) sum mask whose rows are runs of ones (the dynamic-chunk masks of TransformerASR.py:85-110):
+// interval_detect finds every row's [lo, hi) and clears *not_interval... sets it to 1 when some row is not a single run of
+// exact ones; interval_means then gives Sm[b,t,:] = sum_{j in [lo_t, hi_t)} S[b,j,:] / (hi_t - lo_t) from prefix sums over time
+// (fp64 running sums) -- O(T D) per utterance instead of the (T,T) @ (T,D) product.  Both are no-ops once the flag is set.
+int interval_detect(const float* M, int T, int* lo, int* hi, int* not_interval, cudaStream_t st);
+size_t interval_means_workspace_bytes(int B, int T, int D);
+int interval_means(const float* S, int64_t ldS, int B, int T, int D, const int* lo, const int* hi, const int* not_interval, float* Sm,
+                   void* workspace, cudaStream_t st);
 int convert(const void* src, int s_dtype, void* dst, int d_dtype, int64_t n, cudaStream_t st);
 
 // host orchestration of the generic path (smx_generic.cu).  x/y/residual carry their own dtype tags.

@@ -39,6 +39,7 @@ constexpr int BM = 64, BN = 64, BK = 16;
 __global__ void __launch_bounds__(256) gemm_kernel(GemmP p) {
   __shared__ float As[BK][BM + 4];
   __shared__ float Ws[BK][BN + 4];
+  if (p.run_if_nonzero && *p.run_if_nonzero == 0) return;  // (uniform over the grid: the flag was written by an earlier kernel)
   const int batch = blockIdx.z % p.batches, outer = blockIdx.z / p.batches;
   const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
   const int tid = threadIdx.x;
@@ -326,6 +327,84 @@ int laplace(float decay, const float* binary, int T, float* out, cudaStream_t st
   laplace_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(logf(decay), binary, T, out);
   count_launch();
   return check_launch("laplace_kernel");
+}
+
+// ---- chunk-prefix path of the sum-mask summaries ---------------------------------------------------------------------
+__global__ void __launch_bounds__(256) interval_detect_kernel(const float* __restrict__ M, int T, int* __restrict__ lo, int* __restrict__ hi,
+                                                              int* __restrict__ not_interval) {
+  const int row = blockIdx.x * 8 + threadIdx.x / 32, lane = threadIdx.x % 32;
+  if (row >= T) return;
+  int first = T, last = -1, cnt = 0, bad = 0;
+  for (int c = lane; c < T; c += 32) {
+    const float v = M[(int64_t)row * T + c];
+    if (v != 0.0f) {
+      if (v != 1.0f) bad = 1;
+      first = c < first ? c : first;
+      last = c > last ? c : last;
+      ++cnt;
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) {
+    const int f2 = __shfl_xor_sync(0xffffffffu, first, o), l2 = __shfl_xor_sync(0xffffffffu, last, o);
+    first = f2 < first ? f2 : first;
+    last = l2 > last ? l2 : last;
+    cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    bad |= __shfl_xor_sync(0xffffffffu, bad, o);
+  }
+  if (lane == 0) {
+    if (bad || cnt == 0 || cnt != last - first + 1) atomicExch(not_interval, 1);
+    lo[row] = first; hi[row] = last + 1;
+  }
+}
+int interval_detect(const float* M, int T, int* lo, int* hi, int* not_interval, cudaStream_t st) {
+  cudaError_t e = cudaMemsetAsync(not_interval, 0, sizeof(int), st);
+  if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
+  interval_detect_kernel<<<(T + 7) / 8, 256, 0, st>>>(M, T, lo, hi, not_interval);
+  count_launch();
+  return check_launch("interval_detect_kernel");
+}
+// P[b][t][d] = sum_{j < t} S[b][j][d] (exclusive, fp64), one thread per (b, d): coalesced over d
+__global__ void __launch_bounds__(256) prefix_time_kernel(const float* __restrict__ S, int64_t ldS, int B, int T, int D, const int* __restrict__ skip,
+                                                          double* __restrict__ P) {
+  if (*skip) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * D) return;
+  const int b = (int)(i / D), d = (int)(i % D);
+  const float* s = S + (int64_t)b * T * ldS + d;
+  double* p = P + (int64_t)b * (T + 1) * D + d;
+  double acc = 0.0;
+  p[0] = 0.0;
+#pragma unroll 4
+  for (int t = 0; t < T; ++t) {
+    acc += (double)s[(int64_t)t * ldS];
+    p[(int64_t)(t + 1) * D] = acc;
+  }
+}
+__global__ void __launch_bounds__(256) interval_mean_kernel(const double* __restrict__ P, const int* __restrict__ lo, const int* __restrict__ hi, int B,
+                                                            int T, int D, const int* __restrict__ skip, float* __restrict__ Sm) {
+  if (*skip) return;
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)B * T * D) return;
+  const int d = (int)(i % D);
+  const int64_t bt = i / D;
+  const int t = (int)(bt % T), b = (int)(bt / T);
+  const int l = lo[t], h = hi[t];
+  const double* p = P + (int64_t)b * (T + 1) * D + d;
+  // the reference divides by the row sum of the mask: padding is NOT removed from the denominator (summary_mixing.py:239-246)
+  Sm[i] = (float)((p[(int64_t)h * D] - p[(int64_t)l * D]) / (double)(h - l));
+}
+size_t interval_means_workspace_bytes(int B, int T, int D) { return align_up((size_t)B * (T + 1) * D * sizeof(double)); }
+int interval_means(const float* S, int64_t ldS, int B, int T, int D, const int* lo, const int* hi, const int* not_interval, float* Sm,
+                   void* workspace, cudaStream_t st) {
+  double* P = (double*)workspace;
+  const int64_t n1 = (int64_t)B * D, n2 = (int64_t)B * T * D;
+  prefix_time_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(S, ldS, B, T, D, not_interval, P);
+  count_launch();
+  SMX_TRY(check_launch("prefix_time_kernel"));
+  interval_mean_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(P, lo, hi, B, T, D, not_interval, Sm);
+  count_launch();
+  return check_launch("interval_mean_kernel");
 }
 
 __global__ void rowsum_kernel(const float* m, int rows, int cols, float* out) {

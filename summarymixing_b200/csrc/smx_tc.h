@@ -73,6 +73,8 @@ int tc_cell_fwd(const smx_cell_weights* w, const void* packed, int B, int T, con
                 const float* pre_ln_w, const float* pre_ln_b, const uint8_t* mask, const __nv_bfloat16* residual,
                 __nv_bfloat16* y, Arena& ws, cudaStream_t st);
 
+int tc_add_bcast(const __nv_bfloat16* a, const __nv_bfloat16* s, int64_t rows, int T, int D, __nv_bfloat16* out, cudaStream_t st);
+
 // ---- smx_tc_cell.cu: K-SM, the fused persistent cell (two passes) ---------------------------------
 void tc_set_trace(void* p);  // debug timeline buffer (>= 1024 x u64) or NULL
 bool tc_cellf_supported(const smx_cell_weights* w);
@@ -154,4 +156,32 @@ int tc_convmod_fwd(const smx_convmod_weights* w, const void* packed, int act, in
 int tc_dwconv_ln_act(const __nv_bfloat16* g, const float* dw_w, const float* dw_b, const float* ln_w,
                      const float* ln_b, int act, int B, int T, int D, int k, __nv_bfloat16* out, cudaStream_t st);
 
+}  // namespace smx
+
+namespace smx {
+// ---- smx_tc_gemm.cu: K-GEMM (both operands streamed by tensor-map TMA, any K) and the fused CSGU gate ------------------
+struct GemmTc {
+  const __nv_bfloat16* a; int64_t lda; int64_t M;   // A (M, K) bf16 rows, row pitch lda elements
+  int N, K;
+  const __nv_bfloat16* w;                            // W (N, K) bf16 row-major (tc_dense_bf16)
+  const float* bias;                                 // [N] or NULL
+  const float* rowbias; int64_t rowbias_ld; int rows_per_group;   // + rowbias[row / rows_per_group][n] before the activation, or NULL
+  int act;
+  const uint8_t* rowmask;                            // [M] multiplies the activated value, or NULL
+  const __nv_bfloat16* resid; int64_t ldr; float alpha;   // out = resid + alpha * v, or NULL
+  __nv_bfloat16* out; int64_t ldo;
+};
+bool tc_gemm_supported(int K, int N);
+int tc_gemm_launch(const GemmTc& g, cudaStream_t st);
+int tc_dense_bf16(const smx_linear& L, int k_offset, int K, void* out, cudaStream_t st);  // (out_dim, K) bf16 copy of columns [k_offset, +K)
+size_t tc_csgu_workspace_bytes(int64_t rows);
+int tc_csgu_fwd(const __nv_bfloat16* u, int B, int T, int H, const float* ln_w, const float* ln_b, const float* dw_w, const float* dw_b,
+                int kernel_size, int gate_act, __nv_bfloat16* out, int64_t ldo, void* stats_ws, cudaStream_t st);
+
+// ---- smx_tc_branch.cu: BranchformerEncoderLayer on the tensor-core arm ------------------------------------------------
+bool tc_branchformer_supported(const smx_branchformer_layer_weights* w, int has_sum_mask);
+size_t tc_branchformer_packed_bytes(const smx_branchformer_layer_weights* w);
+int tc_branchformer_pack(const smx_branchformer_layer_weights* w, void* packed, cudaStream_t st);
+int tc_branchformer_layer_fwd(const smx_branchformer_layer_weights* w, int B, int T, const __nv_bfloat16* x, const uint8_t* mask,
+                              __nv_bfloat16* y, Arena& ws, cudaStream_t st);
 }  // namespace smx

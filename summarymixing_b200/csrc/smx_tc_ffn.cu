@@ -308,15 +308,26 @@ __global__ void __launch_bounds__(FFN_THREADS, 1) ffn_kernel(const FfnP p) {
 // ---------------------------------------------------------------------------------------------
 static uint32_t ffn_stage_bytes(int D) { return (uint32_t)((D / 64) * kblock_bytes(FFN_HC) + kblock_bytes(D)); }
 
-bool tc_ffn_supported(const smx_ffn_weights* w) {
+static bool ffn_fused_ok(const smx_ffn_weights* w) {
   const int D = w->w1.in_dim, F = w->w1.out_dim;
   if (w->w1.n_split > 1 || w->w2.n_split > 1 || w->w2.in_dim != F || w->w2.out_dim != D) return false;
   if (D % 64 || D < 64 || D > 256 || F % 64 || F < 64) return false;  // acc2 (D cols) + 2x64 acc1 cols fit 512 TMEM cols
   if (!w->w1.w || !w->w1.b || !w->w2.w || !w->w2.b || !w->ln_w || !w->ln_b) return false;
   return true;
 }
+// Wide models (conformer_large: D = 512, d_ffn = 2048, conformer_summarymixing.yaml:113-125): the output tile no longer fits the
+// fused kernels' TMEM budget; two launches instead -- K-LIN (LayerNorm prologue, D -> F, activation) and K-GEMM (F -> D with
+// the scaled residual as epilogue, any K) -- with the hidden activation making one bf16 round trip through memory.
+static bool ffn_wide_ok(const smx_ffn_weights* w) {
+  const int D = w->w1.in_dim, F = w->w1.out_dim;
+  if (w->w1.n_split > 1 || w->w2.n_split > 1 || w->w2.in_dim != F || w->w2.out_dim != D) return false;
+  if (!w->w1.w || !w->w1.b || !w->w2.w || !w->w2.b || !w->ln_w || !w->ln_b) return false;
+  return D > 256 && tc_linear_supported(D, F) && tc_gemm_supported(F, D);
+}
+bool tc_ffn_supported(const smx_ffn_weights* w) { return ffn_fused_ok(w) || ffn_wide_ok(w); }
 size_t tc_ffn_packed_bytes(const smx_ffn_weights* w) {
   if (!tc_ffn_supported(w)) return 0;
+  if (ffn_wide_ok(w)) return align_up(tc_linear_packed_bytes(w->w1.in_dim, w->w1.out_dim), 1024) + align_up((size_t)w->w2.out_dim * w->w2.in_dim * 2, 1024);
   if (tc_ffn3_supported(w)) return tc_ffn3_packed_bytes(w);
   if (tc_ffn2_supported(w)) return tc_ffn2_packed_bytes(w);
   return (size_t)(w->w1.out_dim / FFN_HC) * ffn_stage_bytes(w->w1.in_dim);
@@ -348,6 +359,10 @@ __global__ void ffn_pack_kernel(const float* w1, const float* w2, int D, int F, 
 
 int tc_ffn_pack(const smx_ffn_weights* w, void* packed, cudaStream_t st) {
   if (!tc_ffn_supported(w)) return fail(SMX_ERR_UNSUPPORTED, "ffn configuration not handled by the tensor-core arm");
+  if (ffn_wide_ok(w)) {
+    SMX_TRY(tc_pack_linear(w->w1, 0, w->w1.in_dim, 0, packed, st));
+    return tc_dense_bf16(w->w2, 0, w->w2.in_dim, (char*)packed + align_up(tc_linear_packed_bytes(w->w1.in_dim, w->w1.out_dim), 1024), st);
+  }
   if (tc_ffn3_supported(w)) return tc_ffn3_pack(w, packed, st);
   if (tc_ffn2_supported(w)) return tc_ffn2_pack(w, packed, st);
   const int D = w->w1.in_dim, F = w->w1.out_dim;
@@ -358,10 +373,34 @@ int tc_ffn_pack(const smx_ffn_weights* w, void* packed, cudaStream_t st) {
   return check_launch("ffn_pack_kernel");
 }
 
-size_t tc_ffn_workspace_bytes(const smx_ffn_weights*, int64_t) { return 0; }
+size_t tc_ffn_workspace_bytes(const smx_ffn_weights* w, int64_t rows) {
+  return ffn_wide_ok(w) ? align_up((size_t)rows * w->w1.out_dim * 2) : 0;  // the fused kernels need no scratch
+}
 
 int tc_ffn_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t rows, const __nv_bfloat16* x,
                const float* oln_w, const float* oln_b, float oln_eps, __nv_bfloat16* y, Arena& ws, cudaStream_t st) {
+  if (ffn_wide_ok(w)) {
+    const int D = w->w1.in_dim, F = w->w1.out_dim;
+    const size_t m0 = ws.mark();
+    __nv_bfloat16* h = (__nv_bfloat16*)ws.take((size_t)rows * F * 2);
+    if (!h) return fail(SMX_ERR_WORKSPACE, "workspace too small (wide FFN)");
+    if (!ws.dry) {
+      LinP p{};
+      p.rows = rows; p.T = 1; p.utt_tiles = 0; p.alpha = 1.0f; p.ln_eps = 1e-5f; p.oln_eps = 1e-5f;
+      p.x = x; p.ldx = D; p.K = D; p.N = F; p.wp = (const __nv_bfloat16*)packed; p.bias = w->w1.b;
+      p.ln_w = w->ln_w; p.ln_b = w->ln_b; p.act = act;
+      p.out = h; p.ldo = F;
+      SMX_TRY(tc_linear_launch(p, TC_LIN_PLAIN, st));                                   // Conformer.py:470-473
+      GemmTc g{};
+      g.a = h; g.lda = F; g.M = rows; g.N = D; g.K = F;
+      g.w = (const __nv_bfloat16*)((const char*)packed + align_up(tc_linear_packed_bytes(D, F), 1024));
+      g.bias = w->w2.b; g.act = SMX_ACT_IDENTITY; g.resid = x; g.ldr = D; g.alpha = 0.5f; g.out = y; g.ldo = D;
+      SMX_TRY(tc_gemm_launch(g, st));                                                   // x + 0.5 * ffn(x), :518
+      if (oln_w) SMX_TRY(layernorm(y, SMX_BF16, D, oln_w, oln_b, oln_eps, SMX_ACT_IDENTITY, y, SMX_BF16, D, rows, D, st));  // norm2, :547
+    }
+    ws.release(m0);
+    return SMX_OK;
+  }
   if (ws.dry) return SMX_OK;
   // v3 (hidden activation in tensor memory) moves rows with 256-bit global accesses: 32-byte aligned x / y
   if (tc_ffn_version() == 3 && tc_ffn3_supported(w) && ((uintptr_t)x % 32 == 0) && ((uintptr_t)y % 32 == 0))

@@ -1,0 +1,401 @@
+// tcgen05 arm of libsmx, part 11: K-GEMM, the general linear kernel, and the fused CSGU gate of the Branchformer block.
+//
+//   out[M, N] (bf16) = epilogue( A[M, K] (bf16 rows, any row pitch) @ W[N, K]^T (bf16, nn.Linear layout) )
+//   epilogue: + bias[n] + rowbias[row / rows_per_group][n] -> activation -> * rowmask[row] -> resid + alpha * v
+//
+// Unlike K-LIN (smx_tc_lin.cu: the whole 128 x K activation tile staged in shared memory, K <= 512, LayerNorm prologue),
+// both operands STREAM through one shared-memory ring by tensor-map TMA (cp.async.bulk.tensor.2d, 128-byte swizzle = the
+// UMMA operand image), so K is unbounded: the Branchformer's 1536 -> D and 2D -> D projections (Branchformer.py:78-84,
+// 220-226), the frontend's 640 -> D input projection (TransformerASR.py:353-358).  Persistent over 128 x NT output tiles
+// (tile order n-major so that concurrently running CTAs share a weight panel in L2), two TMEM accumulators: the eight
+// epilogue warps drain tile i while the tensor pipe works on tile i + 1.
+// Warp roles: 0 TMA producer | 1 MMA issuer | 2-9 epilogue (quadrant = warp % 4, column half = (warp - 2) / 4)
+#include <cuda.h>
+
+#include "smx_tc.h"
+#include "smx_tc_common.cuh"
+
+namespace smx {
+
+using tc::kblock_bytes;
+
+constexpr int GM_THREADS = 320;
+constexpr int GM_MAX_STAGES = 8;
+
+struct GemmTcP {
+  int M, N, K, NT, m_tiles, n_tiles;
+  const float* bias;
+  const float* rowbias; int64_t rowbias_ld; int rows_per_group;
+  int act;
+  const uint8_t* rowmask;
+  const __nv_bfloat16* resid; int64_t ldr; float alpha;
+  __nv_bfloat16* out; int64_t ldo;
+  int n_stages; uint32_t stage_bytes; uint32_t tmem_cols;
+};
+
+__device__ __forceinline__ void gm_tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   tc::smem_u32(smem_dst)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(tc::smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void gm_ldg256(const void* p, uint32_t* r) {
+  asm volatile("ld.global.v8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+               : "l"(p));
+}
+__device__ __forceinline__ void gm_stg256(void* p, const uint32_t* r) {
+  asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]),
+               "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
+               : "memory");
+}
+
+__global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
+                                                                const __grid_constant__ CUtensorMap tmW, const GemmTcP p) {
+  extern __shared__ __align__(1024) uint8_t smem[];  // ring stages: [A block 128 x 64 | W block NT x 64]
+  __shared__ __align__(8) uint64_t full_bar[GM_MAX_STAGES], empty_bar[GM_MAX_STAGES], acc_full[2], acc_empty[2];
+  __shared__ uint32_t tmem_base_s;
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
+  const int nkb = p.K >> 6, NT = p.NT;
+  const int n_tiles_total = p.m_tiles * p.n_tiles;
+
+  if (warp == 0) tc::tmem_alloc(&tmem_base_s, p.tmem_cols);
+  if (tid == 32) {
+    for (int s = 0; s < p.n_stages; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc_full[i], 1); tc::mbar_init(&acc_empty[i], 8); }
+    tc::fence_barrier_init();
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  tc::tc_fence_after();
+  tc::pdl_wait();               // A (and the residual) come from the preceding kernel
+  tc::pdl_launch_dependents();
+  const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
+
+  if (warp == 0) {
+    // =============================== TMA producer ===============================
+    if (lane == 0) {
+      int s = 0;
+      uint32_t ph = 0;
+      for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
+        const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+#pragma unroll 1
+        for (int kb = 0; kb < nkb; ++kb) {
+          tc::mbar_wait(&empty_bar[s], ph ^ 1u);
+          tc::mbar_arrive_expect_tx(&full_bar[s], p.stage_bytes);
+          uint8_t* dst = smem + (size_t)s * p.stage_bytes;
+          gm_tma_load_2d(dst, &tmA, kb * 64, mt * 128, &full_bar[s]);          // rows >= M are zero-filled
+          gm_tma_load_2d(dst + kblock_bytes(128), &tmW, kb * 64, nt * NT, &full_bar[s]);
+          if (++s == p.n_stages) { s = 0; ph ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // =============================== MMA issuer ===============================
+    int s = 0;
+    uint32_t ph = 0;
+    const uint32_t s0 = tc::smem_u32(smem);
+    const uint32_t idesc = tc::make_idesc_bf16(128, (uint32_t)NT);
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      tc::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator (first two uses: fresh)
+      tc::tc_fence_after();
+      const uint32_t d_addr = tmem + (uint32_t)buf * (uint32_t)NT;
+#pragma unroll 1
+      for (int kb = 0; kb < nkb; ++kb) {
+        tc::mbar_wait_spin(&full_bar[s], ph);
+        tc::tc_fence_after();
+        if (tc::elect_one()) {
+          const uint32_t a_addr = s0 + (uint32_t)s * p.stage_bytes;
+          const uint64_t ad = tc::make_desc_sw128(a_addr), bd = tc::make_desc_sw128(a_addr + kblock_bytes(128));
+#pragma unroll
+          for (int ks = 0; ks < 4; ++ks) tc::umma_bf16(d_addr, ad + 2u * ks, bd + 2u * ks, idesc, (kb == 0 && ks == 0) ? 0u : 1u);
+          tc::umma_commit(&empty_bar[s]);
+          if (kb == nkb - 1) tc::umma_commit(&acc_full[buf]);
+        }
+        __syncwarp();
+        if (++s == p.n_stages) { s = 0; ph ^= 1u; }
+      }
+    }
+  } else {
+    // =============================== epilogue ===============================
+    const int q = warp & 3, half = (warp - 2) >> 2;
+    const int r = q * 32 + lane;
+    const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
+    const int npc = NT >> 6;  // 32-column pieces per column half (NT = 64: one piece per half)
+    int it = 0;
+    for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+      const int64_t grow = (int64_t)mt * 128 + r;
+      const bool live = grow < p.M;
+      const float rscale = (live && p.rowmask) ? (float)p.rowmask[grow] : 1.0f;
+      const float* rb = (live && p.rowbias) ? p.rowbias + (grow / p.rows_per_group) * p.rowbias_ld : nullptr;
+      tc::mbar_wait(&acc_full[buf], (it >> 1) & 1);
+      tc::tc_fence_after();
+#pragma unroll 1
+      for (int pc = 0; pc < npc; ++pc) {
+        const int col = half * (NT >> 1) + pc * 32;       // column inside the tile
+        const int gcol = nt * NT + col;
+        uint32_t rres[16];
+        if (p.resid && live) { gm_ldg256(p.resid + grow * p.ldr + gcol, rres); gm_ldg256(p.resid + grow * p.ldr + gcol + 16, rres + 8); }
+        float v[32];
+        tc::tmem_ld32(tmem + lane_sel + (uint32_t)buf * (uint32_t)NT + col, v);
+        tc::tmem_ld_wait();
+        if (p.bias) {
+          const float4* bp = reinterpret_cast<const float4*>(p.bias + gcol);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float4 bb = __ldg(bp + j); v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w; }
+        }
+        if (rb) {
+          const float4* bp = reinterpret_cast<const float4*>(rb + gcol);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) { const float4 bb = __ldcg(bp + j); v[4 * j] += bb.x; v[4 * j + 1] += bb.y; v[4 * j + 2] += bb.z; v[4 * j + 3] += bb.w; }
+        }
+        tc::act_apply<32>(p.act, v);
+        if (p.rowmask) {
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] *= rscale;
+        }
+        if (p.resid && live) {
+#pragma unroll
+          for (int i = 0; i < 16; ++i) {
+            const float2 f = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&rres[i]));
+            v[2 * i] = fmaf(p.alpha, v[2 * i], f.x); v[2 * i + 1] = fmaf(p.alpha, v[2 * i + 1], f.y);
+          }
+        }
+        if (live) {
+          uint32_t o[16];
+#pragma unroll
+          for (int i = 0; i < 16; ++i) o[i] = tc::pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          gm_stg256(p.out + grow * p.ldo + gcol, o);
+          gm_stg256(p.out + grow * p.ldo + gcol + 16, o + 8);
+        }
+      }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&acc_empty[buf]);
+    }
+  }
+  tc::tc_fence_before();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, p.tmem_cols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*gm_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                 const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                 CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static gm_encode_fn gm_encoder() {
+  static gm_encode_fn fn = nullptr;
+  static std::atomic<int> state{0};
+  if (state.load() == 0) {
+    void* f = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &qres);
+    if (e == cudaSuccess && qres == cudaDriverEntryPointSuccess && f) { fn = (gm_encode_fn)f; state = 1; }
+    else { (void)cudaGetLastError(); state = 2; }
+  }
+  return state.load() == 1 ? fn : nullptr;
+}
+static int gm_map_2d(CUtensorMap* tm, const void* base, uint64_t cols, uint64_t rows, uint64_t pitch_bytes, uint32_t box_rows) {
+  gm_encode_fn enc = gm_encoder();
+  if (!enc) return fail(SMX_ERR_UNSUPPORTED, "tc gemm: cuTensorMapEncodeTiled is not available");
+  const cuuint64_t gdim[2] = {cols, rows};
+  const cuuint64_t gstr[1] = {pitch_bytes};
+  const cuuint32_t box[2] = {64, box_rows};
+  const cuuint32_t estr[2] = {1, 1};
+  CUresult r = enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(SMX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return SMX_OK;
+}
+
+bool tc_gemm_supported(int K, int N) { return K >= 64 && K % 64 == 0 && N >= 64 && N % 64 == 0; }
+
+static int gm_sms() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev);
+    if (n <= 0) n = 148;
+  }
+  return n;
+}
+
+int tc_gemm_launch(const GemmTc& g, cudaStream_t st) {
+  if (!tc_gemm_supported(g.K, g.N) || g.M <= 0) return fail(SMX_ERR_UNSUPPORTED, "tc gemm: M=%lld N=%d K=%d", (long long)g.M, g.N, g.K);
+  if (g.M > 0x7fffffff) return fail(SMX_ERR_UNSUPPORTED, "tc gemm: too many rows");
+  if (((uintptr_t)g.a % 16) || ((uintptr_t)g.w % 16) || ((uintptr_t)g.out % 32) || (g.lda % 8) || (g.ldo % 16) ||
+      (g.resid && (((uintptr_t)g.resid % 32) || g.ldr % 16)))
+    return fail(SMX_ERR_ALIGNMENT, "tc gemm: operand alignment");
+  GemmTcP p{};
+  p.M = (int)g.M; p.N = g.N; p.K = g.K;
+  p.NT = g.N % 256 == 0 ? 256 : (g.N % 128 == 0 ? 128 : 64);
+  p.m_tiles = (int)((g.M + 127) / 128); p.n_tiles = g.N / p.NT;
+  p.bias = g.bias; p.rowbias = g.rowbias; p.rowbias_ld = g.rowbias_ld; p.rows_per_group = g.rows_per_group > 0 ? g.rows_per_group : 1;
+  p.act = g.act; p.rowmask = g.rowmask; p.resid = g.resid; p.ldr = g.ldr; p.alpha = g.alpha;
+  p.out = g.out; p.ldo = g.ldo;
+  p.stage_bytes = kblock_bytes(128) + (uint32_t)p.NT * 128u;
+  int stages = (int)((227 * 1024 - 2048) / p.stage_bytes);
+  if (stages > GM_MAX_STAGES) stages = GM_MAX_STAGES;
+  p.n_stages = stages;
+  p.tmem_cols = p.NT == 256 ? 512 : (p.NT == 128 ? 256 : 128);
+  CUtensorMap tmA, tmW;
+  SMX_TRY(gm_map_2d(&tmA, g.a, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda * 2, 128));
+  SMX_TRY(gm_map_2d(&tmW, g.w, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.K * 2, (uint32_t)p.NT));
+  const size_t smem = (size_t)stages * p.stage_bytes + 1024;
+  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(gemm_tc_kernel): %s", cudaGetErrorString(e));
+  const int total = p.m_tiles * p.n_tiles;
+  const unsigned grid = (unsigned)(total < gm_sms() ? total : gm_sms());
+  e = launch_pdl(gemm_tc_kernel, dim3(grid), dim3(GM_THREADS), smem, st, 1u, tmA, tmW, p);
+  if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaLaunchKernelEx(gemm_tc_kernel): %s", cudaGetErrorString(e));
+  count_tc_launch();
+  return check_launch("gemm_tc_kernel");
+}
+
+// dense bf16 (N, K) row-major copy of columns [k_offset, k_offset + K) of an smx_linear (block-diagonal weights get their zeros)
+__global__ void dense_bf16_kernel(const float* __restrict__ w, int in_dim, int out_dim, int n_split, int k_offset, int K, int N,
+                                  __nv_bfloat16* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)N * K) return;
+  const int n = (int)(i / K), k = (int)(i % K) + k_offset;
+  float val;
+  if (n_split <= 1) {
+    val = w[(int64_t)n * in_dim + k];
+  } else {
+    const int hi = in_dim / n_split, ho = out_dim / n_split, m = n / ho;
+    val = (k / hi == m) ? w[((int64_t)m * hi + (k - m * hi)) * ho + (n - m * ho)] : 0.0f;
+  }
+  out[i] = __float2bfloat16(val);
+}
+int tc_dense_bf16(const smx_linear& L, int k_offset, int K, void* out, cudaStream_t st) {
+  const int64_t n = (int64_t)L.out_dim * K;
+  dense_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L.w, L.in_dim, L.out_dim, L.n_split, k_offset, K, L.out_dim,
+                                                                 (__nv_bfloat16*)out);
+  count_launch();
+  return check_launch("dense_bf16_kernel");
+}
+
+// =============================================================================================
+// CSGU (speechbrain ConvolutionalSpatialGatingUnit, used by Branchformer.py:78-84), fused:
+//   u (rows, 2H) bf16 = [value | gate];  out (rows, H) = gate_act( dwconv_reflect( LN(gate) ) + b ) * value
+// Pass 1: per-row LayerNorm statistics of the gate half.  Pass 2: a block owns 32 frames x 128 channels of one utterance: the
+// 32 + k - 1 normalised gate rows (reflect padding at the utterance edges) are staged in shared memory once, every thread
+// convolves one channel over 16 frames with its taps in registers.
+// =============================================================================================
+__global__ void __launch_bounds__(256) csgu_stats_kernel(const __nv_bfloat16* __restrict__ u, int64_t rows, int H, float2* __restrict__ stats) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t row = (int64_t)blockIdx.x * 8 + warp;
+  if (row >= rows) return;
+  const __nv_bfloat16* g = u + row * (2 * (int64_t)H) + H;
+  float s = 0.0f, q = 0.0f;
+  const float x0 = __bfloat162float(g[0]);  // shift: no cancellation for rows with a large mean
+  for (int c = lane * 8; c < H; c += 256) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(g + c);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float2 f = __bfloat1622float2(h[e]);
+      const float a = f.x - x0, b = f.y - x0;
+      s += a + b; q = fmaf(a, a, fmaf(b, b, q));
+    }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); q += __shfl_xor_sync(0xffffffffu, q, o); }
+  if (lane == 0) {
+    const float m0 = s / (float)H;
+    const float rstd = rsqrtf(fmaxf(q / (float)H - m0 * m0, 0.0f) + 1e-5f);
+    stats[row] = make_float2(rstd, -(m0 + x0) * rstd);
+  }
+}
+
+constexpr int CS_FR = 32, CS_CH = 128;
+template <int KS>
+__global__ void __launch_bounds__(256) csgu_kernel(const __nv_bfloat16* __restrict__ u, const float2* __restrict__ stats,
+                                                   const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                   const float* __restrict__ dw_w, const float* __restrict__ dw_b, int gate_act, int T,
+                                                   int H, __nv_bfloat16* __restrict__ out, int64_t ldo) {
+  constexpr int PAD = (KS - 1) / 2, NIN = CS_FR + KS - 1;
+  __shared__ float sG[NIN][CS_CH];
+  const int b = blockIdx.z, t0 = blockIdx.x * CS_FR, c0 = blockIdx.y * CS_CH;
+  const int tid = threadIdx.x;
+  const int64_t ubase = (int64_t)b * T;
+  for (int idx = tid; idx < NIN * (CS_CH / 8); idx += 256) {
+    const int row = idx / (CS_CH / 8), ch = (idx % (CS_CH / 8)) * 8;
+    int t = t0 - PAD + row;
+    if (t < 0) t = -t;                       // reflect padding (F.pad(..., mode="reflect")): edge not repeated
+    if (t >= T) t = 2 * (T - 1) - t;
+    float v[8];
+    if (t >= 0 && t < T && c0 + ch < H) {
+      const float2 st = stats[ubase + t];
+      const uint4 raw = *reinterpret_cast<const uint4*>(u + (ubase + t) * (2 * (int64_t)H) + H + c0 + ch);
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float2 f = __bfloat1622float2(h[e]);
+        v[2 * e] = fmaf(fmaf(f.x, st.x, st.y), ln_w[c0 + ch + 2 * e], ln_b[c0 + ch + 2 * e]);
+        v[2 * e + 1] = fmaf(fmaf(f.y, st.x, st.y), ln_w[c0 + ch + 2 * e + 1], ln_b[c0 + ch + 2 * e + 1]);
+      }
+    } else {
+#pragma unroll
+      for (int e = 0; e < 8; ++e) v[e] = 0.0f;
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) sG[row][ch + e] = v[e];
+  }
+  __syncthreads();
+  const int c = tid % CS_CH, fh = tid / CS_CH;  // channel, frame half (16 frames each)
+  if (c0 + c >= H) return;
+  float w[KS];
+#pragma unroll
+  for (int j = 0; j < KS; ++j) w[j] = dw_w[(size_t)(c0 + c) * KS + j];
+  const float bias = dw_b ? dw_b[c0 + c] : 0.0f;
+#pragma unroll 1
+  for (int fb = 0; fb < 2; ++fb) {   // two blocks of 8 frames
+    float a[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) a[o] = bias;
+    const int f0 = fh * 16 + fb * 8;
+#pragma unroll
+    for (int i = 0; i < KS + 7; ++i) {
+      const float x = sG[f0 + i][c];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        const int j = i - o;
+        if (j >= 0 && j < KS) a[o] = fmaf(w[j], x, a[o]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const int t = t0 + f0 + o;
+      if (t < T) {
+        const float val = __bfloat162float(u[(ubase + t) * (2 * (int64_t)H) + c0 + c]);
+        out[(ubase + t) * ldo + c0 + c] = __float2bfloat16(tc::act_fast(gate_act, a[o]) * val);
+      }
+    }
+  }
+}
+
+size_t tc_csgu_workspace_bytes(int64_t rows) { return align_up((size_t)rows * sizeof(float2)); }
+int tc_csgu_fwd(const __nv_bfloat16* u, int B, int T, int H, const float* ln_w, const float* ln_b, const float* dw_w, const float* dw_b,
+                int kernel_size, int gate_act, __nv_bfloat16* out, int64_t ldo, void* stats_ws, cudaStream_t st) {
+  if (kernel_size != 31 || H % 8) return fail(SMX_ERR_UNSUPPORTED, "csgu: kernel_size=%d H=%d", kernel_size, H);
+  if ((kernel_size - 1) / 2 >= T) return fail(SMX_ERR_BAD_ARG, "reflect padding %d needs T > pad (T=%d)", (kernel_size - 1) / 2, T);
+  const int64_t rows = (int64_t)B * T;
+  csgu_stats_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(u, rows, H, (float2*)stats_ws);
+  count_launch();
+  SMX_TRY(check_launch("csgu_stats_kernel"));
+  dim3 grid((T + CS_FR - 1) / CS_FR, (H + CS_CH - 1) / CS_CH, B);
+  csgu_kernel<31><<<grid, 256, 0, st>>>(u, (const float2*)stats_ws, ln_w, ln_b, dw_w, dw_b, gate_act, T, H, out, ldo);
+  count_launch();
+  return check_launch("csgu_kernel");
+}
+
+}  // namespace smx

@@ -25,7 +25,22 @@ static bool mlp_ok(const smx_linear* blk, int n, int in_dim) {
   return true;
 }
 
+// modes "SummaryMixing-lite" (summary_mixing.py:300-324) and "SummaryMixing-fast" (:255-298) on the row-tile linear kernels
+static bool lite_ok(const smx_cell_weights* w) {
+  return mlp_ok(w->summary, w->n_summary, w->enc_dim) && w->summary[w->n_summary - 1].out_dim == w->summary_out_dim &&
+         w->summary_out_dim <= 1024;
+}
+static bool fast_ok(const smx_cell_weights* w) {
+  const smx_linear& g = w->global_proj;
+  const int Dl = w->local_out_dim;
+  if (!g.w || !g.b || g.n_split > 1 || g.in_dim != w->enc_dim || g.out_dim != 2 * Dl) return false;
+  if (!tc_linear_supported(g.in_dim, Dl)) return false;
+  if (w->merge.n_split > 1 || w->merge.in_dim != 2 * Dl || !w->merge.w || !w->merge.b) return false;
+  return tc_linear_supported(Dl, w->merge.out_dim) && Dl <= 1024;
+}
 bool tc_cell_supported(const smx_cell_weights* w, int has_sum_mask) {
+  if (w->mode == SMX_MODE_LITE) return lite_ok(w);             // (lite ignores sum_mask, :300-324)
+  if (w->mode == SMX_MODE_FAST) return !has_sum_mask && fast_ok(w);
   if (w->mode != SMX_MODE_FULL || has_sum_mask) return false;
   if (tc_cellf_supported(w)) return true;  // fused kernels: any n_split (heads not aligned to 64 are packed as dense)
   if (!mlp_ok(w->local, w->n_local, w->enc_dim) || !mlp_ok(w->summary, w->n_summary, w->enc_dim)) return false;
@@ -46,6 +61,18 @@ struct CellLayout {
 static CellLayout cell_layout(const smx_cell_weights* w) {
   CellLayout l{};
   size_t off = 0;
+  if (w->mode == SMX_MODE_LITE) {
+    for (int i = 0; i < w->n_summary; ++i) { l.summary[i] = off; off += align_up(tc_linear_packed_bytes(w->summary[i].in_dim, w->summary[i].out_dim)); }
+    l.total = off;
+    return l;
+  }
+  if (w->mode == SMX_MODE_FAST) {  // [global_proj rows 0..Dl (local half)] [rows Dl..2Dl (summary half)] [merge local part]
+    l.local[0] = off; off += align_up(tc_linear_packed_bytes(w->enc_dim, w->local_out_dim));
+    l.summary[0] = off; off += align_up(tc_linear_packed_bytes(w->enc_dim, w->local_out_dim));
+    l.merge = off; off += align_up(tc_linear_packed_bytes(w->local_out_dim, w->merge.out_dim));
+    l.total = off;
+    return l;
+  }
   for (int i = 0; i < w->n_local; ++i) { l.local[i] = off; off += align_up(tc_linear_packed_bytes(w->local[i].in_dim, w->local[i].out_dim)); }
   for (int i = 0; i < w->n_summary; ++i) { l.summary[i] = off; off += align_up(tc_linear_packed_bytes(w->summary[i].in_dim, w->summary[i].out_dim)); }
   l.merge = off; off += align_up(tc_linear_packed_bytes(w->local_out_dim, w->merge.out_dim));
@@ -64,6 +91,19 @@ int tc_cell_pack(const smx_cell_weights* w, void* packed, cudaStream_t st) {
   if (!tc_cell_supported(w, 0)) return fail(SMX_ERR_UNSUPPORTED, "cell configuration not handled by the tensor-core arm");
   const CellLayout l = cell_layout(w);
   char* base = (char*)packed;
+  if (w->mode == SMX_MODE_LITE) {
+    for (int i = 0; i < w->n_summary; ++i) SMX_TRY(tc_pack_linear(w->summary[i], 0, w->summary[i].in_dim, 0, base + l.summary[i], st));
+    return SMX_OK;
+  }
+  if (w->mode == SMX_MODE_FAST) {
+    smx_linear half = w->global_proj;  // dense (2 D_l, D): rows [0, D_l) feed the local half, rows [D_l, 2 D_l) the summary half
+    half.out_dim = w->local_out_dim;
+    SMX_TRY(tc_pack_linear(half, 0, half.in_dim, 0, base + l.local[0], st));
+    half.w = w->global_proj.w + (size_t)w->local_out_dim * w->global_proj.in_dim;
+    half.b = w->global_proj.b + w->local_out_dim;
+    SMX_TRY(tc_pack_linear(half, 0, half.in_dim, 0, base + l.summary[0], st));
+    return tc_pack_linear(w->merge, 0, w->local_out_dim, 0, base + l.merge, st);  // W_c[:, :D_l]
+  }
   if (tc_cellf_supported(w)) {  // fused persistent cell: 64 x 64 weight blocks
     for (int i = 0; i < 2; ++i) SMX_TRY(tc_pack_linear_nt(w->local[i], 0, w->local[i].in_dim, 64, base + l.local[i], st));
     for (int i = 0; i < 2; ++i) SMX_TRY(tc_pack_linear_nt(w->summary[i], 0, w->summary[i].in_dim, 64, base + l.summary[i], st));
@@ -148,12 +188,74 @@ __global__ void __launch_bounds__(256) cell_finalize_kernel(const float* __restr
   }
 }
 
+// lite mode: y[b] = sum_t s[b,t] mask[b,t] / sum_t mask[b,t] from the per-tile column sums (fixed order)   summary_mixing.py:318-322
+__global__ void __launch_bounds__(256) cell_mean_kernel(const float* __restrict__ colsum, int tiles_per_utt, int T,
+                                                        const uint8_t* __restrict__ mask, int Ds, __nv_bfloat16* __restrict__ y) {
+  __shared__ float red[8];
+  const int b = blockIdx.x, tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  float cnt = (float)T;
+  if (mask) {
+    cnt = 0.0f;
+    for (int t = tid; t < T; t += 256) cnt += (float)mask[(size_t)b * T + t];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+    if (lane == 0) red[warp] = cnt;
+    __syncthreads();
+    cnt = 0.0f;
+    for (int i = 0; i < 8; ++i) cnt += red[i];
+  }
+  for (int d = tid; d < Ds; d += 256) {
+    float s = 0.0f;
+    for (int i = 0; i < tiles_per_utt; ++i) s += colsum[((size_t)b * tiles_per_utt + i) * Ds + d];
+    y[(size_t)b * Ds + d] = __float2bfloat16(s / cnt);
+  }
+}
+
+// out[r, :] = a[r, :] + s[r / T, :]  (bf16; the `x + skip` of a lite cell, whose output is one row per utterance)
+__global__ void __launch_bounds__(256) add_bcast_bf16_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ s, int64_t n8,
+                                                             int T, int D8, __nv_bfloat16* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const int64_t row = i / D8;
+  const int c8 = (int)(i - row * D8);
+  const uint4 av = reinterpret_cast<const uint4*>(a)[i];
+  const uint4 sv = reinterpret_cast<const uint4*>(s)[(row / T) * D8 + c8];
+  const __nv_bfloat162* ah = reinterpret_cast<const __nv_bfloat162*>(&av);
+  const __nv_bfloat162* sh = reinterpret_cast<const __nv_bfloat162*>(&sv);
+  uint32_t o[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const float2 x = __bfloat1622float2(ah[e]), y = __bfloat1622float2(sh[e]);
+    o[e] = tc::pack_bf16x2(x.x + y.x, x.y + y.y);
+  }
+  reinterpret_cast<uint4*>(out)[i] = make_uint4(o[0], o[1], o[2], o[3]);
+}
+int tc_add_bcast(const __nv_bfloat16* a, const __nv_bfloat16* s, int64_t rows, int T, int D, __nv_bfloat16* out, cudaStream_t st) {
+  if (D % 8) return fail(SMX_ERR_UNSUPPORTED, "add_bcast: D=%d", D);
+  const int64_t n8 = rows * (D / 8);
+  add_bcast_bf16_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, st>>>(a, s, n8, T, D / 8, out);
+  count_launch();
+  return check_launch("add_bcast_bf16_kernel");
+}
+
 struct CellWs {
   __nv_bfloat16 *h, *L;
   float *colsum, *rowbias;
 };
 static int cell_ws(const smx_cell_weights* w, int B, int T, Arena& ws, CellWs& o) {
   const int64_t rows = (int64_t)B * T;
+  if (w->mode == SMX_MODE_LITE || w->mode == SMX_MODE_FAST) {
+    const int tpu = (T + 127) / 128;
+    int maxh = 1;
+    for (int i = 0; i + 1 < w->n_summary; ++i) maxh = w->summary[i].out_dim > maxh ? w->summary[i].out_dim : maxh;
+    const int Dsum = w->mode == SMX_MODE_LITE ? w->summary_out_dim : w->local_out_dim;
+    o.h = (__nv_bfloat16*)ws.take((size_t)rows * maxh * 2 * 2);
+    o.L = (__nv_bfloat16*)ws.take(w->mode == SMX_MODE_FAST ? (size_t)rows * w->local_out_dim * 2 : 16);
+    o.colsum = ws.f32((size_t)B * tpu * Dsum);
+    o.rowbias = ws.f32((size_t)B * (w->mode == SMX_MODE_FAST ? w->merge.out_dim : 1));
+    if (!o.h || !o.L || !o.colsum || !o.rowbias) return fail(SMX_ERR_WORKSPACE, "workspace too small (tc cell lite/fast)");
+    return SMX_OK;
+  }
   int maxh = 0;
   for (int i = 0; i + 1 < w->n_local; ++i) maxh = w->local[i].out_dim > maxh ? w->local[i].out_dim : maxh;
   for (int i = 0; i + 1 < w->n_summary; ++i) maxh = w->summary[i].out_dim > maxh ? w->summary[i].out_dim : maxh;
@@ -168,7 +270,7 @@ static int cell_ws(const smx_cell_weights* w, int B, int T, Arena& ws, CellWs& o
 }
 size_t tc_cell_workspace_bytes(const smx_cell_weights* w, int B, int T) {
   if (!tc_cell_supported(w, 0)) return 0;
-  if (tc_cellf_supported(w)) {
+  if (w->mode == SMX_MODE_FULL && tc_cellf_supported(w)) {
     const size_t a = tc_cellf_workspace_bytes(w, B, T), b = tc_cell4_supported(w) ? tc_cell4_workspace_bytes(w, B, T) : 0;
     return a > b ? a : b;
   }
@@ -202,6 +304,78 @@ int tc_cell_fwd(const smx_cell_weights* w, const void* packed, int B, int T, con
   const char* pk = (const char*)packed;
   const size_t m0 = ws.mark();
   if (ws.dry) { ws.take(tc_cell_workspace_bytes(w, B, T)); ws.release(m0); return SMX_OK; }
+  if (w->mode == SMX_MODE_LITE || w->mode == SMX_MODE_FAST) {
+    const bool lite = w->mode == SMX_MODE_LITE;
+    if (lite && residual) return fail(SMX_ERR_BAD_ARG, "lite mode returns (B,D_s): no fused residual");
+    CellWs o;
+    SMX_TRY(cell_ws(w, B, T, ws, o));
+    const int64_t rows = (int64_t)B * T;
+    const int Dl = w->local_out_dim, Ds = w->summary_out_dim, tpu = (T + 127) / 128;
+    if (lite) {
+      // s(x) * mask -> per-tile column sums (fused epilogue of the last block) -> mean over valid frames        :318-322
+      int maxh = 1;
+      for (int i = 0; i + 1 < w->n_summary; ++i) maxh = w->summary[i].out_dim > maxh ? w->summary[i].out_dim : maxh;
+      __nv_bfloat16* hb[2] = {o.h, o.h + (size_t)rows * maxh};
+      const __nv_bfloat16* cur = x; int64_t ld = w->enc_dim;
+      for (int i = 0; i < w->n_summary; ++i) {
+        const bool last = (i == w->n_summary - 1);
+        LinP p = lin_base(B, T);
+        p.x = cur; p.ldx = ld;
+        lin_weight(p, w->summary[i], pk + l.summary[i], w->summary[i].in_dim);
+        p.act = w->act;
+        if (i == 0) { p.ln_w = pre_ln_w; p.ln_b = pre_ln_b; }
+        if (last) {
+          p.rowmask = mask; p.colsum = o.colsum;
+          SMX_TRY(tc_linear_launch(p, TC_LIN_COLSUM, st));
+        } else {
+          p.out = hb[i & 1]; p.ldo = w->summary[i].out_dim;
+          SMX_TRY(tc_linear_launch(p, TC_LIN_PLAIN, st));
+          cur = p.out; ld = p.ldo;
+        }
+      }
+      cell_mean_kernel<<<B, 256, 0, st>>>(o.colsum, tpu, T, mask, Ds, y);
+      count_launch();
+      SMX_TRY(check_launch("cell_mean_kernel"));
+    } else {
+      // G = act(W_g x + b_g) * mask; local = G[:, :D_l] (bf16), summary half -> per-tile column sums             :271-281
+      smx_linear half = w->global_proj;
+      half.out_dim = Dl;
+      {
+        LinP p = lin_base(B, T);
+        p.x = x; p.ldx = w->enc_dim;
+        lin_weight(p, half, pk + l.local[0], w->enc_dim);
+        p.ln_w = pre_ln_w; p.ln_b = pre_ln_b;
+        p.act = w->act; p.rowmask = mask;
+        p.out = o.L; p.ldo = Dl;
+        SMX_TRY(tc_linear_launch(p, TC_LIN_PLAIN, st));
+      }
+      {
+        half.b = w->global_proj.b + Dl;
+        LinP p = lin_base(B, T);
+        p.x = x; p.ldx = w->enc_dim;
+        lin_weight(p, half, pk + l.summary[0], w->enc_dim);
+        p.ln_w = pre_ln_w; p.ln_b = pre_ln_b;
+        p.act = w->act; p.rowmask = mask; p.colsum = o.colsum;
+        SMX_TRY(tc_linear_launch(p, TC_LIN_COLSUM, st));
+      }
+      // mean (no LayerNorm in fast mode) and the summary's share of the combiner: c[b] = W_c[:, D_l:] mean + b_c   :278-281, 296-298
+      cell_finalize_kernel<<<B, 256, 0, st>>>(o.colsum, tpu, T, mask, Dl, Dl, w->merge.out_dim, nullptr, nullptr, w->merge.w, w->merge.b, o.rowbias);
+      count_launch();
+      SMX_TRY(check_launch("cell_finalize_kernel"));
+      LinP p = lin_base(B, T);
+      p.x = o.L; p.ldx = Dl;
+      lin_weight(p, w->merge, pk + l.merge, Dl);
+      p.bias = nullptr;
+      p.head_in = p.head_out = 0;
+      p.rowbias = o.rowbias; p.rowbias_ld = w->merge.out_dim;
+      p.act = w->act;
+      p.resid = residual; p.ldr = w->merge.out_dim;
+      p.out = y; p.ldo = w->merge.out_dim;
+      SMX_TRY(tc_linear_launch(p, TC_LIN_PLAIN, st));
+    }
+    ws.release(m0);
+    return SMX_OK;
+  }
   if (tc_cellf_supported(w)) {
     // v3 moves rows with 256-bit global accesses: 32-byte aligned x / y / residual
     const bool al = ((uintptr_t)x % 32 == 0) && ((uintptr_t)y % 32 == 0) && ((uintptr_t)residual % 32 == 0);

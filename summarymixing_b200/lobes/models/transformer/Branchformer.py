@@ -172,6 +172,7 @@ class BranchformerEncoderLayer(nn.Module):
         self.convolution_branch.fill(lw.branch, wv, device)
         lw.n_merge = self.merge_proj.fill(lw.merge, wv, device)
         lw.act = self._act_code
+        H.pack_tc(wv, device, lw, L.lib().smx_branchformer_packed_bytes, L.lib().smx_branchformer_pack)
 
     def forward(
         self,

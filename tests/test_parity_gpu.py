@@ -202,3 +202,30 @@ def test_baseline_shape_one_layer_against_oracle_sample():
     with torch.no_grad():
         y = layer.to(DEV)(x.to(DEV), src_key_padding_mask=mask.to(DEV))[0]
     assert float((y.cpu() - y_or).abs().max()) < 5e-4
+
+
+def test_sum_mask_chunk_prefix_path_and_general_fallback():
+    """Per-frame summaries with a (T,T) sum mask (summary_mixing.py:235-246).  Dynamic-chunk masks (rows = runs of ones,
+    TransformerASR.py:85-110) take the chunk-prefix-sum path (O(T D)); an arbitrary weighted matrix must still give the
+    reference's (T,T) @ (T,D) result through the fallback product.  fp32 arm vs the oracle at T = 1000."""
+    import summarymixing_b200 as S
+    from oracle import smx_oracle as O
+    from oracle.seeded import fill_module, seeded_input
+
+    B, T, D = 3, 1000, 64
+    m = S.SummaryMixing(D, 4, [D], D, [D], D, activation=S.Swish, mode="SummaryMixing").eval()
+    fill_module(m, 91)
+    x = seeded_input(92, B, T, D)
+    lens = torch.tensor([1000, 731, 40])
+    mask = torch.arange(T)[None] < lens[:, None]
+    chunk = O.chunk_mask(T, 16, 4).float()                       # 16-frame chunks, 4 chunks of left context
+    weighted = torch.rand(T, T, generator=torch.Generator().manual_seed(93)) + 0.1
+    holes = chunk.clone()
+    holes[5, 2] = 0.0                                            # ones with a hole: not an interval -> fallback
+    md = m.to("cuda:0")
+    for name, sm in (("chunk", chunk), ("weighted", weighted), ("holes", holes)):
+        y_or = O.summary_mixing(x, dict(m.cpu().state_dict()), mode="SummaryMixing", act="swish", src_padding_mask=mask, sum_mask=sm)
+        with torch.no_grad():
+            y = md.to("cuda:0")(x.to("cuda:0"), sum_mask=sm.to("cuda:0"), src_padding_mask=mask.to("cuda:0")).cpu()
+        err = float((y - y_or).abs().max())
+        assert err <= 5e-4 * max(1.0, float(y_or.abs().max())), f"sum_mask {name}: {err:.3e}"

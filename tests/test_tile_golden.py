@@ -17,7 +17,7 @@ DEV = "cuda:0"
 ALL = G.tile_names()
 # fixtures whose bf16 path must run on tcgen05 kernels (fused path): everything at D = 256 in mode "SummaryMixing"
 TC_REQUIRED = {"cell_d256_h4_swish", "cell_d256_h1_swish", "cell_d256_h4_gelu", "convmod_d256", "conformer_layer_d256",
-               "conformer_enc_d256_3l"}
+               "conformer_enc_d256_3l", "cell_d256_h4_lite", "cell_d256_h4_fast", "conformer_layer_d512", "branchformer_enc_d512_lite_2l"}
 
 
 def test_tile_fixture_inventory():
