@@ -357,6 +357,51 @@ SMX_API int smx_branchformer_encoder_fwd(const smx_branchformer_layer_weights* l
                                  const void* x, const uint8_t* padding_mask, const float* sum_mask, void* y,
                                  void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- acoustic frontend (the blocks the recipes put in front of the encoder) --------------------------------------------------
+ * The reference configures these by YAML name only (conformer_summarymixing.yaml:145-152, 198-200, 298-330); the classes are
+ * SpeechBrain v1.0's (un-vendored): semantics restated from its published behaviour, "parity unpinned" (oracle/frontend_oracle.py).
+ * All tensors fp32 device memory unless noted. */
+typedef struct {
+  int32_t sample_rate;   /* 16000 */
+  int32_t n_fft;         /* 512 (the implemented size) */
+  int32_t n_mels;        /* 80 */
+  float win_length_ms;   /* 32 */
+  float hop_length_ms;   /* 10 */
+  float f_min;           /* 0 */
+  float f_max;           /* <= 0: sample_rate / 2 */
+  float amin;            /* 1e-10 */
+  float top_db;          /* 80; <= 0: no clamp */
+} smx_fbank_desc;
+/* speechbrain.lobes.features.Fbank (conformer_summarymixing.yaml:326-330): wav (B, n_samples) -> feats (B, T', n_mels) with
+ * T' = smx_fbank_frames() = 1 + n_samples / hop: hamming-window STFT (center, zero padding), power spectrum, triangular mel
+ * filterbank, 10 log10, per-utterance top_db clamp. */
+SMX_API int32_t smx_fbank_frames(const smx_fbank_desc* d, int32_t n_samples);
+SMX_API size_t smx_fbank_workspace_bytes(const smx_fbank_desc* d, int32_t B);
+SMX_API int smx_fbank_fwd(const smx_fbank_desc* d, int32_t B, int32_t n_samples, const float* wav, float* feats, void* workspace,
+                  size_t workspace_bytes, void* stream);
+/* InputNormalization(norm_type="global") at inference (yaml:198-200): y = (x - mean[f]) / std[f]; x, y (rows, F); may alias. */
+SMX_API int smx_input_norm_fwd(int64_t rows, int32_t F, const float* x, const float* mean, const float* std, float* y, void* stream);
+/* SpectrogramDrop (yaml:298-312), in place on x (B, T, F): positions [pos[b][m], pos[b][m] + len[b][m]) along dim (1 = time,
+ * 2 = frequency) are replaced by the mean of the whole tensor (replace_mean != 0) or by zero.  pos / len: device int32 (B, n_masks),
+ * drawn by the caller.  workspace: smx_spec_drop_workspace_bytes(). */
+SMX_API size_t smx_spec_drop_workspace_bytes(void);
+SMX_API int smx_spec_drop_fwd(int32_t B, int32_t T, int32_t F, float* x, int32_t dim, int32_t n_masks, const int32_t* pos, const int32_t* len,
+                      int32_t replace_mean, void* workspace, size_t workspace_bytes, void* stream);
+/* Warping (yaml:315; dim = 1, bicubic, align_corners): frames [0, c) of x (B, T, F) are resampled to w frames, frames [c, T) to
+ * T - w frames; y must not alias x.  c, w in (0, T), drawn by the caller. */
+SMX_API int smx_time_warp_fwd(int32_t B, int32_t T, int32_t F, const float* x, int32_t c, int32_t w, float* y, void* stream);
+/* One block of ConvolutionFrontEnd (yaml:145-152; num_layers_per_block = 1, no residual): Conv2d(kernel, stride, reflect "same")
+ * over (time, frequency) of x (B, T, F, Cin) channels-last -> LayerNorm over (F', Cout) -> LeakyReLU(0.01); y (B, T', F', Cout),
+ * T' = ceil(T / stride), F' = ceil(F / stride).  conv_w (Cout, Cin, k, k), conv_b (Cout), ln_w / ln_b (F', Cout). */
+SMX_API int smx_conv_frontend_block_fwd(int32_t B, int32_t T, int32_t F, int32_t Cin, int32_t Cout, int32_t kernel, int32_t stride,
+                                const float* x, const float* conv_w, const float* conv_b, const float* ln_w, const float* ln_b,
+                                float* y, void* stream);
+/* custom_src_module + positional encoding (TransformerASR.py:353-358, 405-406; Transformer.py:288-339), dropout off:
+ * y (B, T, D) in out_dtype = x (B, T, in_dim) W^T + b + pe[t, :].  T must not exceed max_len (the reference's table, 2500). */
+SMX_API size_t smx_input_proj_workspace_bytes(int32_t B, int32_t T, int32_t D);
+SMX_API int smx_input_proj_fwd(const smx_linear* proj, int32_t B, int32_t T, int32_t max_len, const float* x, int out_dtype, void* y,
+                       void* workspace, size_t workspace_bytes, void* stream);
+
 /* ---- mask builders (TransformerASR.py:50-180) ------------------------------------------------ */
 
 /* padding mask from relative lengths: abs_len = round(wav_len*T); mask[b,t] = t < abs_len[b]

@@ -88,6 +88,11 @@ class BranchformerLayerWeights(C.Structure):
                 ("merge", Linear * SMX_MAX_BLOCKS), ("packed", C.c_void_p)]
 
 
+class FbankDesc(C.Structure):
+    _fields_ = [("sample_rate", C.c_int32), ("n_fft", C.c_int32), ("n_mels", C.c_int32), ("win_length_ms", C.c_float),
+                ("hop_length_ms", C.c_float), ("f_min", C.c_float), ("f_max", C.c_float), ("amin", C.c_float), ("top_db", C.c_float)]
+
+
 class SmxError(RuntimeError):
     def __init__(self, code, msg):
         super().__init__(f"libsmx: {STATUS.get(code, code)}: {msg}")
@@ -147,6 +152,16 @@ _PROTOS = {
     "smx_branchformer_encoder_workspace_bytes": (_sz, [C.POINTER(BranchformerLayerWeights), _i, _i, _i, _i, _i]),
     "smx_branchformer_encoder_fwd": (_i, [C.POINTER(BranchformerLayerWeights), _i, _vp, _vp, _i, _i, _i, _vp, _vp, _vp,
                                           _vp, _vp, _sz, _vp]),
+    "smx_fbank_frames": (C.c_int32, [C.POINTER(FbankDesc), _i]),
+    "smx_fbank_workspace_bytes": (_sz, [C.POINTER(FbankDesc), _i]),
+    "smx_fbank_fwd": (_i, [C.POINTER(FbankDesc), _i, _i, _vp, _vp, _vp, _sz, _vp]),
+    "smx_input_norm_fwd": (_i, [_i64, _i, _vp, _vp, _vp, _vp, _vp]),
+    "smx_spec_drop_workspace_bytes": (_sz, []),
+    "smx_spec_drop_fwd": (_i, [_i, _i, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _sz, _vp]),
+    "smx_time_warp_fwd": (_i, [_i, _i, _i, _vp, _i, _i, _vp, _vp]),
+    "smx_conv_frontend_block_fwd": (_i, [_i, _i, _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _vp, _vp]),
+    "smx_input_proj_workspace_bytes": (_sz, [_i, _i, _i]),
+    "smx_input_proj_fwd": (_i, [C.POINTER(Linear), _i, _i, _i, _vp, _i, _vp, _vp, _sz, _vp]),
     "smx_padding_mask_from_wav_len": (_i, [_vp, _i, _i, _vp, _vp]),
     "smx_chunk_mask": (_i, [_i, _i, _i, _vp, _vp]),
     "smx_debug_tc_gemm": (_i, [_i, _i, _i, _i, _vp, _vp, _vp, _vp, _sz, _vp]),

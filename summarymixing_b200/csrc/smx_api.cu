@@ -550,4 +550,72 @@ int smx_branchformer_encoder_fwd(const smx_branchformer_layer_weights* layers, i
   return layernorm(cur, dtype, D, final_norm_w, final_norm_b, 1e-6f, SMX_ACT_IDENTITY, y, dtype, D, rows, D, st);
 }
 
+// ---- acoustic frontend ---------------------------------------------------------------------------------------------------
+int32_t smx_fbank_frames(const smx_fbank_desc* d, int32_t n_samples) {
+  if (!d || n_samples <= 0) return 0;
+  const int hop = (int)lrintf((float)d->sample_rate / 1000.0f * d->hop_length_ms);
+  return hop > 0 ? fbank_frames(n_samples, hop) : 0;
+}
+size_t smx_fbank_workspace_bytes(const smx_fbank_desc* d, int32_t B) { return (d && B > 0) ? fbank_workspace_bytes(B, d->n_mels) : 0; }
+int smx_fbank_fwd(const smx_fbank_desc* d, int32_t B, int32_t n_samples, const float* wav, float* feats, void* workspace,
+                  size_t workspace_bytes, void* stream) {
+  if (!d || B <= 0 || n_samples <= 0) return fail(SMX_ERR_BAD_ARG, "fbank: NULL descriptor or non-positive size");
+  SMX_TRY(check_ptr(wav, "wav")); SMX_TRY(check_ptr(feats, "feats"));
+  SMX_TRY(check_arch());
+  if (!workspace || workspace_bytes < smx_fbank_workspace_bytes(d, B)) return fail(SMX_ERR_WORKSPACE, "fbank: workspace too small");
+  return fbank_fwd(d, B, n_samples, wav, feats, workspace, (cudaStream_t)stream);
+}
+int smx_input_norm_fwd(int64_t rows, int32_t F, const float* x, const float* mean, const float* std, float* y, void* stream) {
+  if (rows <= 0 || F <= 0 || !mean || !std) return fail(SMX_ERR_BAD_ARG, "input_norm: bad size or NULL statistics");
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(y, "y"));
+  SMX_TRY(check_arch());
+  return input_norm_fwd(rows, F, x, mean, std, y, (cudaStream_t)stream);
+}
+size_t smx_spec_drop_workspace_bytes(void) { return spec_drop_workspace_bytes(); }
+int smx_spec_drop_fwd(int32_t B, int32_t T, int32_t F, float* x, int32_t dim, int32_t n_masks, const int32_t* pos, const int32_t* len,
+                      int32_t replace_mean, void* workspace, size_t workspace_bytes, void* stream) {
+  if (B <= 0 || T <= 0 || F <= 0 || n_masks < 0 || (n_masks && (!pos || !len))) return fail(SMX_ERR_BAD_ARG, "spec_drop: bad arguments");
+  SMX_TRY(check_ptr(x, "x"));
+  SMX_TRY(check_arch());
+  if (!workspace || workspace_bytes < spec_drop_workspace_bytes()) return fail(SMX_ERR_WORKSPACE, "spec_drop: workspace too small");
+  return spec_drop_fwd(B, T, F, x, dim, n_masks, pos, len, replace_mean, workspace, (cudaStream_t)stream);
+}
+int smx_time_warp_fwd(int32_t B, int32_t T, int32_t F, const float* x, int32_t c, int32_t w, float* y, void* stream) {
+  if (B <= 0 || T <= 0 || F <= 0) return fail(SMX_ERR_BAD_ARG, "time_warp: non-positive size");
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(y, "y"));
+  if (x == y) return fail(SMX_ERR_BAD_ARG, "time_warp: y must not alias x");
+  SMX_TRY(check_arch());
+  return time_warp_fwd(B, T, F, x, c, w, y, (cudaStream_t)stream);
+}
+int smx_conv_frontend_block_fwd(int32_t B, int32_t T, int32_t F, int32_t Cin, int32_t Cout, int32_t kernel, int32_t stride,
+                                const float* x, const float* conv_w, const float* conv_b, const float* ln_w, const float* ln_b,
+                                float* y, void* stream) {
+  if (B <= 0 || T <= 0 || F <= 0 || Cin <= 0 || Cout <= 0 || kernel <= 0 || stride <= 0 || !conv_w || !ln_w || !ln_b)
+    return fail(SMX_ERR_BAD_ARG, "conv frontend block: bad arguments");
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(y, "y"));
+  SMX_TRY(check_arch());
+  return conv_block_fwd(B, T, F, Cin, Cout, kernel, stride, x, conv_w, conv_b, ln_w, ln_b, y, (cudaStream_t)stream);
+}
+size_t smx_input_proj_workspace_bytes(int32_t B, int32_t T, int32_t D) {
+  return (B > 0 && T > 0 && D > 0) ? align_up((size_t)B * T * D * 4) + (1 << 16) : 0;
+}
+int smx_input_proj_fwd(const smx_linear* proj, int32_t B, int32_t T, int32_t max_len, const float* x, int out_dtype, void* y,
+                       void* workspace, size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(out_dtype));
+  if (!proj || !proj->w) return fail(SMX_ERR_BAD_ARG, "input_proj: NULL weights");
+  SMX_TRY(check_bt(B, T));
+  if (max_len > 0 && T > max_len)  /* the reference's table has max_len rows: the broadcast add fails there (Transformer.py:339) */
+    return fail(SMX_ERR_BAD_ARG, "input_proj: sequence length %d exceeds the positional table (%d)", T, max_len);
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(y, "y"));
+  SMX_TRY(check_arch());
+  const int D = proj->out_dim;
+  if (!workspace || workspace_bytes < smx_input_proj_workspace_bytes(B, T, D)) return fail(SMX_ERR_WORKSPACE, "input_proj: workspace too small");
+  Arena a(workspace, workspace_bytes, false);
+  float* v = a.f32((size_t)B * T * D);
+  if (!v) return fail(SMX_ERR_WORKSPACE, "input_proj: workspace too small");
+  SMX_TRY(vanilla_generic(proj, 1, SMX_ACT_IDENTITY, x, SMX_F32, proj->in_dim, (int64_t)B * T, nullptr, nullptr, 0, 0, v, SMX_F32, D, a,
+                          (cudaStream_t)stream));
+  return posenc_add(v, B, T, D, y, out_dtype, (cudaStream_t)stream);
+}
+
 }  // extern "C"

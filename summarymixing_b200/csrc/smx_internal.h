@@ -87,6 +87,19 @@ int interval_means(const float* S, int64_t ldS, int B, int T, int D, const int* 
                    void* workspace, cudaStream_t st);
 int convert(const void* src, int s_dtype, void* dst, int d_dtype, int64_t n, cudaStream_t st);
 
+// ---- frontend: smx_frontend.cu -------------------------------------------------------------------
+int fbank_frames(int n_samples, int hop);
+size_t fbank_workspace_bytes(int B, int n_mels);
+int fbank_fwd(const smx_fbank_desc* d, int B, int n_samples, const float* wav, float* feats, void* workspace, cudaStream_t st);
+int input_norm_fwd(int64_t rows, int F, const float* x, const float* mean, const float* stdv, float* y, cudaStream_t st);
+size_t spec_drop_workspace_bytes();
+int spec_drop_fwd(int B, int T, int F, float* x, int dim, int n_masks, const int* pos, const int* len, int replace_mean, void* workspace,
+                  cudaStream_t st);
+int time_warp_fwd(int B, int T, int F, const float* x, int c, int w, float* y, cudaStream_t st);
+int conv_block_fwd(int B, int T, int F, int Cin, int Cout, int ks, int stride, const float* x, const float* cw, const float* cb, const float* lw,
+                   const float* lb, float* y, cudaStream_t st);
+int posenc_add(const float* v, int B, int T, int D, void* y, int y_dt, cudaStream_t st);
+
 // host orchestration of the generic path (smx_generic.cu).  x/y/residual carry their own dtype tags.
 int vanilla_generic(const smx_linear* blocks, int n, int act, const void* x, int x_dt, int64_t ldx, int64_t rows,
                     const uint8_t* rowmask, const void* residual, int r_dt, int64_t ldr, void* y, int y_dt,
