@@ -472,6 +472,22 @@ def run_smx(args):
                      "frac": flops_conv / mod["conv"]["us"] / 1e6 / pk["bf16_tflops_sustained"]},
         }
         if world == 1 and not args.no_others:
+            # the same encoder with fp32 I/O: linears as split-bf16 tensor-core GEMMs (the arm that meets north_star's 1e-3)
+            with torch.no_grad():
+                xf, mf = host[0][0].to(dev), ms[0]
+                for _ in range(2):
+                    enc(xf, src_key_padding_mask=mf)
+                torch.cuda.synchronize()
+                g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                g0.record()
+                for _ in range(5):
+                    enc(xf, src_key_padding_mask=mf)
+                g1.record()
+                torch.cuda.synchronize()
+            ms32 = g0.elapsed_time(g1) / 5
+            line["fp32_arm"] = {"ms_per_step": ms32, "frames_per_s": B * T / ms32 * 1e3, "io": "fp32",
+                                "math": "linears: split-bf16 (bf16x3) tcgen05 GEMMs with fp32 accumulation; everything else fp32 on CUDA cores",
+                                "max_abs_vs_oracle": "<= 1e-3 (tests/test_fullsize_parity_gpu.py prints the measured value)"}
             line["other_configs"] = other_configs(dev)
         if world == 1 and not args.no_cpu:
             r = cpu_reference_throughput(enc.state_dict(), budget_s=20.0, steps=2, warmup=1)

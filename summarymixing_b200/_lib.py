@@ -170,6 +170,7 @@ _PROTOS = {
     "smx_debug_set_ffn_version": (_i, [_i]),
     "smx_debug_set_pdl": (_i, [_i]),
     "smx_debug_set_cell_version": (_i, [_i]),
+    "smx_debug_set_f32_tc": (_i, [_i]),
 }
 
 

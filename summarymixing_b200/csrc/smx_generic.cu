@@ -24,13 +24,45 @@ struct LinOpts {
   bool use_bias = true;
   int k_offset = 0;  // dense only: use input columns [k_offset, k_offset+K) of the weight
   int K = -1;        // dense only: reduced K
+  void* scratch = nullptr; size_t scratch_bytes = 0;  // split_scratch(): lets large fp32 linears run on the tensor cores (split-bf16)
 };
+
+// Scratch for the split-bf16 tensor-core form of the largest of `ls` at `rows` rows (0 bytes when none qualifies); taken from
+// the arena by every module function, so the sizing (dry) runs account for it.
+static void* split_scratch(Arena& ws, int64_t rows, std::initializer_list<const smx_linear*> ls, size_t& bytes) {
+  bytes = 0;
+  for (const smx_linear* l : ls)
+    if (l && l->w && tc_split3_ok(rows, l->in_dim, l->out_dim)) {
+      const size_t b = tc_split3_scratch_bytes(rows, l->in_dim, l->out_dim);
+      bytes = b > bytes ? b : bytes;
+    }
+  return bytes ? ws.take(bytes) : nullptr;
+}
 
 // C = epilogue(A @ L) for one smx_linear (dense nn.Linear or block-diagonal ParallelLinear, VanillaNN.py:99-117)
 static int linear(const smx_linear& L, const void* A, int a_dt, int64_t lda, int64_t rows, void* C, int c_dt,
                   int64_t ldc, const LinOpts& o, cudaStream_t st) {
   if (!L.w) return fail(SMX_ERR_BAD_ARG, "linear: NULL weight");
   if (rows > 0x7fffffff) return fail(SMX_ERR_UNSUPPORTED, "linear: more than 2^31 rows");
+  // fp32 activations, large row counts: the tensor cores with split-bf16 operands (three bf16 MMAs per fp32 product, ~1e-5
+  // relative to the fp32 result; smx_tc_gemm.cu) instead of the CUDA-core GEMM
+  if (o.scratch && a_dt == SMX_F32 && tc_f32_tc_enabled()) {
+    const bool dense = L.n_split <= 1;
+    const int K = dense ? (o.K > 0 ? o.K : L.in_dim - o.k_offset) : L.in_dim;
+    const bool split_ok = dense || (L.in_dim % L.n_split == 0 && L.out_dim % L.n_split == 0 && !o.k_offset && o.K <= 0);
+    const bool al = lda % 4 == 0 && ((uintptr_t)A % 16) == 0 && ((uintptr_t)C % 32) == 0 && ldc % (c_dt == SMX_F32 ? 8 : 16) == 0 &&
+                    (!o.residual || (((uintptr_t)o.residual % 32) == 0 && o.ldr % (o.r_dt == SMX_F32 ? 4 : 16) == 0));
+    if (split_ok && al && tc_split3_ok(rows, K, L.out_dim) && o.scratch_bytes >= tc_split3_scratch_bytes(rows, K, L.out_dim)) {
+      GemmTc g{};
+      g.bias = (o.use_bias && L.b) ? L.b : nullptr;
+      g.rowbias = o.rowbias; g.rowbias_ld = o.rowbias_ld; g.rows_per_group = o.rowbias_div;
+      g.act = o.act; g.rowmask = o.rowmask; g.alpha = o.alpha; g.ldr = o.ldr;
+      if (o.residual) { if (o.r_dt == SMX_F32) g.resid_f32 = (const float*)o.residual; else g.resid = (const __nv_bfloat16*)o.residual; }
+      if (c_dt == SMX_F32) g.out_f32 = (float*)C; else g.out = (__nv_bfloat16*)C;
+      g.ldo = ldc;
+      return tc_linear_split3(L, dense ? o.k_offset : 0, K, (const float*)A, lda, rows, g, o.scratch, st);
+    }
+  }
   GemmP p = base_gemm();
   p.A = A; p.a_dtype = a_dt; p.lda = lda;
   p.C = C; p.c_dtype = c_dt; p.ldc = ldc;
@@ -62,6 +94,8 @@ int vanilla_generic(const smx_linear* blocks, int n, int act, const void* x, int
   if (n < 1 || n > SMX_MAX_BLOCKS)
     return fail(SMX_ERR_UNSUPPORTED, "VanillaNN with %d blocks (library handles 1..%d)", n, SMX_MAX_BLOCKS);
   const size_t m0 = ws.mark();
+  size_t sc_bytes = 0;
+  void* sc = split_scratch(ws, rows, {&blocks[0], n > 1 ? &blocks[1] : nullptr, n > 2 ? &blocks[2] : nullptr, n > 3 ? &blocks[3] : nullptr}, sc_bytes);
   const void* cur = x; int cur_dt = x_dt; int64_t cur_ld = ldx;
   for (int i = 0; i < n; ++i) {
     const bool last = (i == n - 1);
@@ -74,7 +108,7 @@ int vanilla_generic(const smx_linear* blocks, int n, int act, const void* x, int
       out = ws.f32((size_t)rows * blocks[i].out_dim); out_dt = SMX_F32; out_ld = blocks[i].out_dim;
       if (!out) return fail(SMX_ERR_WORKSPACE, "workspace too small (VanillaNN)");
     }
-    LinOpts o; o.act = act;
+    LinOpts o; o.act = act; o.scratch = sc; o.scratch_bytes = sc_bytes;
     if (last) { o.rowmask = rowmask; o.residual = residual; o.r_dt = r_dt; o.ldr = ldr; }
     if (!ws.dry) SMX_TRY(linear(blocks[i], cur, cur_dt, cur_ld, rows, out, out_dt, out_ld, o, st));
     cur = out; cur_dt = out_dt; cur_ld = out_ld;
@@ -189,8 +223,10 @@ int cell_generic(const smx_cell_weights* w, int B, int T, const void* x, int x_d
     }
     cdiv = 1;
   }
+  size_t sc_bytes = 0;
+  void* sc = split_scratch(ws, rows, {&w->merge}, sc_bytes);
   if (!ws.dry) {  // y = act(W_c[:, :D_l] @ local + cbias) (+ residual)      summary_mixing.py:251-253
-    LinOpts o; o.act = w->act; o.use_bias = false; o.K = Dl;
+    LinOpts o; o.act = w->act; o.use_bias = false; o.K = Dl; o.scratch = sc; o.scratch_bytes = sc_bytes;
     o.rowbias = cbias; o.rowbias_ld = Dout; o.rowbias_div = cdiv;
     o.residual = residual; o.r_dt = r_dt; o.ldr = Dout;
     SMX_TRY(linear(w->merge, local, SMX_F32, ld_local, rows, y, y_dt, ldy, o, st));
@@ -209,12 +245,14 @@ int ffn_generic(const smx_ffn_weights* w, int act, int64_t rows, const void* x, 
   const size_t m0 = ws.mark();
   float* t = ws.f32((size_t)rows * D);
   float* h = ws.f32((size_t)rows * F);
+  size_t sc_bytes = 0;
+  void* sc = split_scratch(ws, rows, {&w->w1, &w->w2}, sc_bytes);
   if (!t || !h) return fail(SMX_ERR_WORKSPACE, "workspace too small (ffn)");
   if (!ws.dry) {
     SMX_TRY(layernorm(x, x_dt, D, w->ln_w, w->ln_b, 1e-5f, SMX_ACT_IDENTITY, t, SMX_F32, D, rows, D, st));
-    LinOpts o1; o1.act = act;
+    LinOpts o1; o1.act = act; o1.scratch = sc; o1.scratch_bytes = sc_bytes;
     SMX_TRY(linear(w->w1, t, SMX_F32, D, rows, h, SMX_F32, F, o1, st));
-    LinOpts o2; o2.residual = x; o2.r_dt = x_dt; o2.ldr = D; o2.alpha = 0.5f;
+    LinOpts o2; o2.residual = x; o2.r_dt = x_dt; o2.ldr = D; o2.alpha = 0.5f; o2.scratch = sc; o2.scratch_bytes = sc_bytes;
     if (oln_w) {  // t is free again: reuse it for the pre-norm sum
       SMX_TRY(linear(w->w2, h, SMX_F32, F, rows, t, SMX_F32, D, o2, st));
       SMX_TRY(layernorm(t, SMX_F32, D, oln_w, oln_b, oln_eps, SMX_ACT_IDENTITY, y, y_dt, D, rows, D, st));
@@ -242,16 +280,19 @@ int convmod_generic(const smx_convmod_weights* w, int act, int B, int T, int chu
   float* t = ws.f32((size_t)rows * D);
   float* p = ws.f32((size_t)rows * 2 * D);
   float* g = ws.f32((size_t)rows * D);
+  size_t sc_bytes = 0;
+  void* sc = split_scratch(ws, rows, {&w->bottleneck, &w->out}, sc_bytes);
   if (!t || !p || !g) return fail(SMX_ERR_WORKSPACE, "workspace too small (conv module)");
   if (!ws.dry) {
     SMX_TRY(layernorm(x, x_dt, D, w->ln_w, w->ln_b, 1e-5f, SMX_ACT_IDENTITY, t, SMX_F32, D, rows, D, st));
-    LinOpts o1;
+    LinOpts o1; o1.scratch = sc; o1.scratch_bytes = sc_bytes;
     SMX_TRY(linear(w->bottleneck, t, SMX_F32, D, rows, p, SMX_F32, 2 * D, o1, st));
     SMX_TRY(glu(p, rows, D, g, st));
     const int pad_mode = chunk > 0 ? SMX_CONV_CHUNKED : (w->causal ? SMX_CONV_CAUSAL : SMX_CONV_SAME_ZERO);
     SMX_TRY(dwconv(g, D, w->dw_w, w->dw_b, B, T, D, w->kernel_size, pad_mode, chunk, t, D, st));
     SMX_TRY(layernorm(t, SMX_F32, D, w->after_ln_w, w->after_ln_b, 1e-5f, act, t, SMX_F32, D, rows, D, st));
     LinOpts o2; o2.rowmask = mask; o2.residual = residual; o2.r_dt = r_dt; o2.ldr = D;  // out*mask (:338) then x + out
+    o2.scratch = sc; o2.scratch_bytes = sc_bytes;
     SMX_TRY(linear(w->out, t, SMX_F32, D, rows, y, y_dt, D, o2, st));
   }
   ws.release(m0);
@@ -379,10 +420,12 @@ int branchformer_layer_generic(const smx_branchformer_layer_weights* w, int dtyp
   float* u = ws.f32((size_t)rows * U);
   float* g = ws.f32((size_t)rows * H);
   float* g2 = ws.f32((size_t)rows * H);
+  size_t sc_bytes = 0;
+  void* sc = split_scratch(ws, rows, {&br.pre, &br.post}, sc_bytes);
   if (!u || !g || !g2) return fail(SMX_ERR_WORKSPACE, "workspace too small (convolution branch)");
   if (!ws.dry) {
     SMX_TRY(layernorm(x, dtype, D, w->norm_conv_w, w->norm_conv_b, 1e-5f, SMX_ACT_IDENTITY, n, SMX_F32, D, rows, D, st));
-    LinOpts o1; o1.act = br.act;
+    LinOpts o1; o1.act = br.act; o1.scratch = sc; o1.scratch_bytes = sc_bytes;
     SMX_TRY(linear(br.pre, n, SMX_F32, D, rows, u, SMX_F32, U, o1, st));
     // CSGU: gate half = u[:, H:], LN -> depthwise conv (reflect) -> [linear] -> gate_act -> * u[:, :H]
     SMX_TRY(layernorm(u + H, SMX_F32, U, br.csgu_ln_w, br.csgu_ln_b, 1e-5f, SMX_ACT_IDENTITY, g, SMX_F32, H, rows, H, st));
@@ -395,7 +438,7 @@ int branchformer_layer_generic(const smx_branchformer_layer_weights* w, int dtyp
     }
     float* prod = (gate == g) ? g2 : g;
     SMX_TRY(gate_mul(gate, H, u, U, br.gate_act, rows, H, prod, st));
-    LinOpts o2;
+    LinOpts o2; o2.scratch = sc; o2.scratch_bytes = sc_bytes;
     SMX_TRY(linear(br.post, prod, SMX_F32, H, rows, cat + Dx1, SMX_F32, Dcat, o2, st));
   }
   // y = x + merge_proj(cat)                                                              :279

@@ -194,6 +194,12 @@ extern "C" SMX_API int smx_debug_set_pdl(int on) {
   return SMX_OK;
 }
 
+// fp32 I/O: large linears on the tensor cores with split-bf16 operands (default on) or on the CUDA-core GEMM (exact fp32 products)
+extern "C" SMX_API int smx_debug_set_f32_tc(int on) {
+  tc_set_f32_tc(on);
+  return SMX_OK;
+}
+
 // A-B switch between the fused cell / GLU-pass generations (3: operands in tensor memory, 1: first generation)
 extern "C" SMX_API int smx_debug_set_cell_version(int version) {
   tc_set_cell_version(version);

@@ -170,8 +170,16 @@ struct GemmTc {
   const uint8_t* rowmask;                            // [M] multiplies the activated value, or NULL
   const __nv_bfloat16* resid; int64_t ldr; float alpha;   // out = resid + alpha * v, or NULL
   __nv_bfloat16* out; int64_t ldo;
+  float* out_f32 = nullptr; const float* resid_f32 = nullptr;   // fp32 output / residual instead of out / resid
+  int split3 = 0;                                     // set by tc_linear_split3
 };
 bool tc_gemm_supported(int K, int N);
+// fp32 linears on the tensor cores with split-bf16 operands (smx_tc_gemm.cu)
+size_t tc_split3_scratch_bytes(int64_t rows, int K, int N);
+bool tc_split3_ok(int64_t rows, int K, int N);
+bool tc_f32_tc_enabled();
+void tc_set_f32_tc(int on);
+int tc_linear_split3(const smx_linear& L, int k_offset, int K, const float* A, int64_t lda, int64_t rows, GemmTc g, void* scratch, cudaStream_t st);
 int tc_gemm_launch(const GemmTc& g, cudaStream_t st);
 int tc_dense_bf16(const smx_linear& L, int k_offset, int K, void* out, cudaStream_t st);  // (out_dim, K) bf16 copy of columns [k_offset, +K)
 size_t tc_csgu_workspace_bytes(int64_t rows);

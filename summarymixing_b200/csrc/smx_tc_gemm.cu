@@ -30,6 +30,8 @@ struct GemmTcP {
   const uint8_t* rowmask;
   const __nv_bfloat16* resid; int64_t ldr; float alpha;
   __nv_bfloat16* out; int64_t ldo;
+  float* out_f32; const float* resid_f32;   // fp32 output / residual (split3 arm); out / resid are NULL then
+  int split3;                                // A and W hold [hi | lo] halves of width K: accumulate hi*hi + hi*lo + lo*hi
   int n_stages; uint32_t stage_bytes; uint32_t tmem_cols;
 };
 
@@ -57,7 +59,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
   __shared__ uint32_t tmem_base_s;
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
-  const int nkb = p.K >> 6, NT = p.NT;
+  const int nkb1 = p.K >> 6, NT = p.NT;
+  const int nkb = p.split3 ? 3 * nkb1 : nkb1;  // split3: K-block kb' = (segment, kb): segments (hi,hi) (hi,lo) (lo,hi)
   const int n_tiles_total = p.m_tiles * p.n_tiles;
 
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, p.tmem_cols);
@@ -85,8 +88,9 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
           tc::mbar_wait(&empty_bar[s], ph ^ 1u);
           tc::mbar_arrive_expect_tx(&full_bar[s], p.stage_bytes);
           uint8_t* dst = smem + (size_t)s * p.stage_bytes;
-          gm_tma_load_2d(dst, &tmA, kb * 64, mt * 128, &full_bar[s]);          // rows >= M are zero-filled
-          gm_tma_load_2d(dst + kblock_bytes(128), &tmW, kb * 64, nt * NT, &full_bar[s]);
+          const int seg = kb / nkb1, k1 = kb - seg * nkb1;
+          gm_tma_load_2d(dst, &tmA, k1 * 64 + (seg == 2 ? p.K : 0), mt * 128, &full_bar[s]);          // rows >= M are zero-filled
+          gm_tma_load_2d(dst + kblock_bytes(128), &tmW, k1 * 64 + (seg == 1 ? p.K : 0), nt * NT, &full_bar[s]);
           if (++s == p.n_stages) { s = 0; ph ^= 1u; }
         }
       }
@@ -166,7 +170,20 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
             v[2 * i] = fmaf(p.alpha, v[2 * i], f.x); v[2 * i + 1] = fmaf(p.alpha, v[2 * i + 1], f.y);
           }
         }
-        if (live) {
+        if (p.resid_f32 && live) {
+          const float4* rp = reinterpret_cast<const float4*>(p.resid_f32 + grow * p.ldr + gcol);
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 f = __ldcg(rp + j);
+            v[4 * j] = fmaf(p.alpha, v[4 * j], f.x); v[4 * j + 1] = fmaf(p.alpha, v[4 * j + 1], f.y);
+            v[4 * j + 2] = fmaf(p.alpha, v[4 * j + 2], f.z); v[4 * j + 3] = fmaf(p.alpha, v[4 * j + 3], f.w);
+          }
+        }
+        if (live && p.out_f32) {
+          float* op = p.out_f32 + grow * p.ldo + gcol;
+#pragma unroll
+          for (int j = 0; j < 4; ++j) gm_stg256(op + 8 * j, reinterpret_cast<const uint32_t*>(v + 8 * j));
+        } else if (live) {
           uint32_t o[16];
 #pragma unroll
           for (int i = 0; i < 16; ++i) o[i] = tc::pack_bf16x2(v[2 * i], v[2 * i + 1]);
@@ -231,24 +248,27 @@ static int gm_sms() {
 int tc_gemm_launch(const GemmTc& g, cudaStream_t st) {
   if (!tc_gemm_supported(g.K, g.N) || g.M <= 0) return fail(SMX_ERR_UNSUPPORTED, "tc gemm: M=%lld N=%d K=%d", (long long)g.M, g.N, g.K);
   if (g.M > 0x7fffffff) return fail(SMX_ERR_UNSUPPORTED, "tc gemm: too many rows");
-  if (((uintptr_t)g.a % 16) || ((uintptr_t)g.w % 16) || ((uintptr_t)g.out % 32) || (g.lda % 8) || (g.ldo % 16) ||
-      (g.resid && (((uintptr_t)g.resid % 32) || g.ldr % 16)))
+  if (((uintptr_t)g.a % 16) || ((uintptr_t)g.w % 16) || ((uintptr_t)g.out % 32) || ((uintptr_t)g.out_f32 % 32) || (g.lda % 8) ||
+      (g.ldo % (g.out_f32 ? 8 : 16)) || (g.resid && (((uintptr_t)g.resid % 32) || g.ldr % 16)) ||
+      (g.resid_f32 && (((uintptr_t)g.resid_f32 % 16) || g.ldr % 4)))
     return fail(SMX_ERR_ALIGNMENT, "tc gemm: operand alignment");
+  if ((g.out != nullptr) == (g.out_f32 != nullptr)) return fail(SMX_ERR_BAD_ARG, "tc gemm: exactly one of out / out_f32");
   GemmTcP p{};
   p.M = (int)g.M; p.N = g.N; p.K = g.K;
   p.NT = g.N % 256 == 0 ? 256 : (g.N % 128 == 0 ? 128 : 64);
   p.m_tiles = (int)((g.M + 127) / 128); p.n_tiles = g.N / p.NT;
   p.bias = g.bias; p.rowbias = g.rowbias; p.rowbias_ld = g.rowbias_ld; p.rows_per_group = g.rows_per_group > 0 ? g.rows_per_group : 1;
   p.act = g.act; p.rowmask = g.rowmask; p.resid = g.resid; p.ldr = g.ldr; p.alpha = g.alpha;
-  p.out = g.out; p.ldo = g.ldo;
+  p.out = g.out; p.ldo = g.ldo; p.out_f32 = g.out_f32; p.resid_f32 = g.resid_f32; p.split3 = g.split3;
   p.stage_bytes = kblock_bytes(128) + (uint32_t)p.NT * 128u;
   int stages = (int)((227 * 1024 - 2048) / p.stage_bytes);
   if (stages > GM_MAX_STAGES) stages = GM_MAX_STAGES;
   p.n_stages = stages;
   p.tmem_cols = p.NT == 256 ? 512 : (p.NT == 128 ? 256 : 128);
   CUtensorMap tmA, tmW;
-  SMX_TRY(gm_map_2d(&tmA, g.a, (uint64_t)g.K, (uint64_t)g.M, (uint64_t)g.lda * 2, 128));
-  SMX_TRY(gm_map_2d(&tmW, g.w, (uint64_t)g.K, (uint64_t)g.N, (uint64_t)g.K * 2, (uint32_t)p.NT));
+  const uint64_t kw = g.split3 ? 2 * (uint64_t)g.K : (uint64_t)g.K;  // split3: rows of A and W are [hi | lo], 2K wide
+  SMX_TRY(gm_map_2d(&tmA, g.a, kw, (uint64_t)g.M, (uint64_t)g.lda * 2, 128));
+  SMX_TRY(gm_map_2d(&tmW, g.w, kw, (uint64_t)g.N, kw * 2, (uint32_t)p.NT));
   const size_t smem = (size_t)stages * p.stage_bytes + 1024;
   cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(gemm_tc_kernel): %s", cudaGetErrorString(e));
@@ -281,6 +301,63 @@ int tc_dense_bf16(const smx_linear& L, int k_offset, int K, void* out, cudaStrea
                                                                  (__nv_bfloat16*)out);
   count_launch();
   return check_launch("dense_bf16_kernel");
+}
+
+// ---- fp32 on the tensor cores: split-bf16 ("bf16x3") operands ------------------------------------------------------------------
+// x = hi + lo with hi = bf16(x), lo = bf16(x - hi): x w ~= hi_x hi_w + hi_x lo_w + lo_x hi_w (the dropped lo lo term is 2^-16
+// relative).  Rows are stored [hi | lo] (2K bf16); K-GEMM's split3 mode walks the three (A, W) half pairings as one 3K-long
+// accumulation in fp32, so an fp32 linear costs three bf16 MMAs and stays ~1e-5 relative to the fp32 result.
+__global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int K, __nv_bfloat16* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;  // one thread per 4 consecutive elements
+  const int k4 = K >> 2;
+  if (i >= rows * k4) return;
+  const int64_t r = i / k4;
+  const int c = (int)(i - r * k4) * 4;
+  const float4 v = *reinterpret_cast<const float4*>(x + r * ldx + c);
+  const float f[4] = {v.x, v.y, v.z, v.w};
+  __nv_bfloat16 hi[4], lo[4];
+#pragma unroll
+  for (int e = 0; e < 4; ++e) { hi[e] = __float2bfloat16(f[e]); lo[e] = __float2bfloat16(f[e] - __bfloat162float(hi[e])); }
+  __nv_bfloat16* o = out + r * (2 * (int64_t)K) + c;
+  *reinterpret_cast<uint2*>(o) = *reinterpret_cast<const uint2*>(hi);
+  *reinterpret_cast<uint2*>(o + K) = *reinterpret_cast<const uint2*>(lo);
+}
+// W' (N, 2K) = [hi | lo] of columns [k_offset, k_offset + K) of the dense (N, in_dim) view of an smx_linear
+__global__ void __launch_bounds__(256) split_weight_kernel(const float* __restrict__ w, int in_dim, int out_dim, int n_split, int k_offset, int K, int N,
+                                                           __nv_bfloat16* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)N * K) return;
+  const int n = (int)(i / K), k = (int)(i % K) + k_offset;
+  float val;
+  if (n_split <= 1) {
+    val = w[(int64_t)n * in_dim + k];
+  } else {
+    const int hi_ = in_dim / n_split, ho = out_dim / n_split, m = n / ho;
+    val = (k / hi_ == m) ? w[((int64_t)m * hi_ + (k - m * hi_)) * ho + (n - m * ho)] : 0.0f;
+  }
+  const __nv_bfloat16 h = __float2bfloat16(val);
+  out[(int64_t)n * 2 * K + (k - k_offset)] = h;
+  out[(int64_t)n * 2 * K + K + (k - k_offset)] = __float2bfloat16(val - __bfloat162float(h));
+}
+size_t tc_split3_scratch_bytes(int64_t rows, int K, int N) { return align_up((size_t)rows * 2 * K * 2, 1024) + align_up((size_t)N * 2 * K * 2, 1024); }
+bool tc_split3_ok(int64_t rows, int K, int N) { return rows >= 1024 && tc_gemm_supported(K, N); }
+static std::atomic<int> g_f32_tc{1};
+void tc_set_f32_tc(int on) { g_f32_tc = on ? 1 : 0; }
+bool tc_f32_tc_enabled() { return g_f32_tc.load() != 0; }
+// out = epilogue(A (rows, K) fp32 @ W^T) through the split-bf16 GEMM; g carries the epilogue (a / w / K / split3 are set here)
+int tc_linear_split3(const smx_linear& L, int k_offset, int K, const float* A, int64_t lda, int64_t rows, GemmTc g, void* scratch, cudaStream_t st) {
+  if (lda % 4 || ((uintptr_t)A % 16)) return fail(SMX_ERR_ALIGNMENT, "split3: A alignment");
+  __nv_bfloat16* a2 = (__nv_bfloat16*)scratch;
+  __nv_bfloat16* w2 = (__nv_bfloat16*)((char*)scratch + align_up((size_t)rows * 2 * K * 2, 1024));
+  const int64_t na = rows * (K / 4), nw = (int64_t)L.out_dim * K;
+  split_rows_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(A, lda, rows, K, a2);
+  count_launch();
+  SMX_TRY(check_launch("split_rows_kernel"));
+  split_weight_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(L.w, L.in_dim, L.out_dim, L.n_split, k_offset, K, L.out_dim, w2);
+  count_launch();
+  SMX_TRY(check_launch("split_weight_kernel"));
+  g.a = a2; g.lda = 2 * (int64_t)K; g.M = rows; g.N = L.out_dim; g.K = K; g.w = w2; g.split3 = 1;
+  return tc_gemm_launch(g, st);
 }
 
 // =============================================================================================

@@ -65,12 +65,24 @@ def test_cfg2_encoder_12_layers_bench_shape():
     tc = L.lib().smx_tc_launch_count() - n0
     assert tc >= NL * 5, f"the encoder did not run on the fused tcgen05 kernels ({tc} launches)"
     _compare(f"cfg2 12L B={B} T={T} (bf16 tcgen05 arm, {tc} tcgen05 launches)", y, y32, y16)
-    # the fp32-I/O arm on the same input: north_star's 1e-3 class (fp32 accumulation order only)
+    # the fp32-I/O arm on the same input meets north_star's 1e-3 ON THE TENSOR CORES: its linears run as split-bf16 GEMMs
+    # (hi*hi + hi*lo + lo*hi in fp32 accumulators, smx_tc_gemm.cu); with the switch off every product is an fp32 FMA
+    n0 = L.lib().smx_tc_launch_count()
     with torch.no_grad():
         yf = enc(x.to(DEV), src_key_padding_mask=mask.to(DEV))[0].cpu()
+    tc32 = L.lib().smx_tc_launch_count() - n0
     e32 = float((yf - y32).abs().max())
-    print(f"[cfg2 12L fp32-I/O arm] max-abs {e32:.3e}")
+    try:
+        L.lib().smx_debug_set_f32_tc(0)
+        with torch.no_grad():
+            ye = enc(x.to(DEV), src_key_padding_mask=mask.to(DEV))[0].cpu()
+    finally:
+        L.lib().smx_debug_set_f32_tc(1)
+    ee = float((ye - y32).abs().max())
+    print(f"[cfg2 12L fp32-I/O arm] split-bf16 tensor-core linears ({tc32} tcgen05 launches): max-abs {e32:.3e}; CUDA-core fp32 GEMMs: {ee:.3e}")
+    assert tc32 >= NL * 8, "the fp32 arm's linears did not run on the tensor cores"
     assert e32 <= 1e-3 * max(1.0, float(y32.abs().max()))
+    assert ee <= 1e-4 * max(1.0, float(y32.abs().max()))
 
 
 def test_cfg3_conformer_large_encoder_real_dims():
