@@ -437,7 +437,7 @@ SMX_API int smx_debug_set_pdl(int on);
  * through shared memory).  Same function; diagnostics / A-B timing. */
 SMX_API int smx_debug_set_cell_version(int version);
 
-/* fp32 (SMX_F32) arm: linears with >= 1024 rows and dims that are multiples of 64 run on the tensor cores with split-bf16
+/* fp32 (SMX_F32) arm: linears with >= 128 rows and dims that are multiples of 64 run on the tensor cores with split-bf16
  * operands (x = hi + lo in bf16; hi*hi + hi*lo + lo*hi accumulated in fp32: ~1e-5 relative to the fp32 product); 0 keeps every
  * product on the CUDA-core fp32 GEMM.  Default on.  Diagnostics / A-B. */
 SMX_API int smx_debug_set_f32_tc(int on);

@@ -114,5 +114,26 @@ def main():
     print(f"total {total / 1e6:.2f} MB in {OUT}")
 
 
-if __name__ == "__main__":
+if __name__ == "__main__" and "--mhsa" not in sys.argv:
     main()
+
+
+def mhsa_fixture():
+    """The self-attention Conformer (attention_type='regularMHA', Conformer.py:425-429): the comparison arm of BASELINE.json
+    configs[4].  Pins oracle.conformer_encoder_mhsa; D = 64 toy (the arm is a torch-library baseline, not a product kernel)."""
+    torch.manual_seed(77)
+    enc = ConformerEncoder(2, 64, 128, 4, 31, attention_type="regularMHA").eval()
+    fill_module(enc, 78)
+    x = seeded_input(79, 3, 70, 64)
+    pad = ~lens_mask(70, [70, 41, 12])
+    with torch.no_grad():
+        y = enc(x, src_key_padding_mask=pad)[0]
+    cfg = dict(kind="conformer_encoder_mhsa", num_layers=2, d_model=64, d_ffn=128, nhead=4, kernel_size=31, act="swish", seed_w=78, seed_x=79,
+               B=3, T=70, reference_commit="d1b1f42", torch=torch.__version__)
+    np.savez_compressed(os.path.join(os.path.dirname(OUT), "mhsa", "mhsa_conformer_enc.npz"), y32=y.numpy(), pad=pad.numpy(),
+                        keys=np.array(sorted(enc.state_dict().keys())), cfg=np.frombuffer(json.dumps(cfg).encode(), dtype=np.uint8))
+    print("mhsa_conformer_enc: ok", tuple(y.shape))
+
+
+if __name__ == "__main__" and "--mhsa" in sys.argv:
+    mhsa_fixture()

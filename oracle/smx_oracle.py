@@ -291,6 +291,39 @@ def conformer_encoder(
 
 
 # --------------------------------------------------------------------------------------
+# Self-attention Conformer (the comparison arm of BASELINE.json configs[4])   Conformer.py:425-429, 528-541
+# --------------------------------------------------------------------------------------
+def conformer_layer_mhsa(x: Tensor, sd: SD, prefix: str, nhead: int, act: str = "swish",
+                         key_padding_mask: Optional[Tensor] = None) -> Tensor:
+    """ConformerEncoderLayer.forward with attention_type == 'regularMHA' (Conformer.py:425-429, 518-548): the same layer with
+    SpeechBrain's MultiheadAttention (a wrapper of nn.MultiheadAttention: packed in_proj, out_proj; un-vendored) in place of
+    the SummaryMixing cell.  key_padding_mask (B,T): True = PADDED frame (the MHSA convention, TransformerASR.py:159-162); the
+    convolution module then zeroes padded frames with masked_fill (masked_false_or_true=True, Conformer.py:334-338)."""
+    B, T, D = x.shape
+    x = x + 0.5 * ffn_module(x, sd, prefix + "ffn_module1.", act)
+    skip = x
+    xn = layer_norm(x, _p(sd, prefix + "norm1.norm.weight", x), _p(sd, prefix + "norm1.norm.bias", x))
+    qkv = xn @ _p(sd, prefix + "mha_layer.att.in_proj_weight", x).T + _p(sd, prefix + "mha_layer.att.in_proj_bias", x)
+    q, k, v = (t.reshape(B, T, nhead, D // nhead).transpose(1, 2) for t in qkv.chunk(3, dim=-1))
+    am = None if key_padding_mask is None else (~key_padding_mask)[:, None, None, :]  # True = may attend
+    a = F.scaled_dot_product_attention(q, k, v, attn_mask=am)
+    a = a.transpose(1, 2).reshape(B, T, D)
+    x = a @ _p(sd, prefix + "mha_layer.att.out_proj.weight", x).T + _p(sd, prefix + "mha_layer.att.out_proj.bias", x) + skip
+    conv_mask = None if key_padding_mask is None else key_padding_mask.unsqueeze(-1)
+    x = x + convolution_module(x, sd, prefix + "convolution_module.", act=act, mask=conv_mask, masked_false_or_true=True)
+    y = x + 0.5 * ffn_module(x, sd, prefix + "ffn_module2.", act)
+    return layer_norm(y, _p(sd, prefix + "norm2.norm.weight", x), _p(sd, prefix + "norm2.norm.bias", x))
+
+
+def conformer_encoder_mhsa(x: Tensor, sd: SD, num_layers: int, nhead: int, prefix: str = "", act: str = "swish",
+                           key_padding_mask: Optional[Tensor] = None) -> Tensor:
+    """ConformerEncoder.forward (Conformer.py:797-827) over conformer_layer_mhsa layers; final LN eps=1e-6."""
+    for i in range(num_layers):
+        x = conformer_layer_mhsa(x, sd, f"{prefix}layers.{i}.", nhead, act=act, key_padding_mask=key_padding_mask)
+    return layer_norm(x, _p(sd, prefix + "norm.norm.weight", x), _p(sd, prefix + "norm.norm.bias", x), eps=1e-6)
+
+
+# --------------------------------------------------------------------------------------
 # Branchformer                                                            (Branchformer.py)
 # --------------------------------------------------------------------------------------
 def csgu(x: Tensor, sd: SD, prefix: str, gate_act: str = "identity") -> Tensor:

@@ -14,6 +14,7 @@
 // First-correct implementation on the generic kernels (strided fp32 GEMM of smx_simt.cu + the elementwise / reduction
 // kernels below); not tuned.  Parity: tests/test_backward_gpu.py against torch.autograd of the oracle restatement.
 #include "smx_internal.h"
+#include "smx_tc.h"
 #include <math.h>
 
 namespace smx {
@@ -186,6 +187,27 @@ unsigned ew_grid(int64_t n) {
   return (unsigned)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
 }
 
+// Tensor-core form of the three linear primitives below (recompute, data gradient, weight gradient): split-bf16 operands,
+// fp32 accumulation (smx_tc_gemm.cu), ~1e-5 relative to the fp32 products -- the golden-gradient tolerances hold.  The scratch
+// for the two per-row primitives is reserved once per backward entry point (BwScratch) so that the sizing runs see it.
+thread_local void* t_bw_sc = nullptr;
+thread_local size_t t_bw_sc_bytes = 0;
+struct BwScratch {
+  BwScratch(Arena& ws, int64_t rows, int maxdim) {
+    t_bw_sc = nullptr; t_bw_sc_bytes = 0;
+    if (!tc_f32_tc_enabled() || !tc_split3_ok(rows, 64, 64)) return;
+    const int md = (maxdim + 63) / 64 * 64;
+    t_bw_sc_bytes = tc_split3_scratch_bytes(rows, md, md);
+    t_bw_sc = ws.take(t_bw_sc_bytes);
+    if (!t_bw_sc) t_bw_sc_bytes = 0;
+  }
+  ~BwScratch() { t_bw_sc = nullptr; t_bw_sc_bytes = 0; }
+};
+bool bw_tc_ok(int64_t rows, int K, int N, const void* a, int64_t lda, const void* c, int64_t ldc, bool c_f32) {
+  return t_bw_sc && tc_f32_tc_enabled() && tc_split3_ok(rows, K, N) && t_bw_sc_bytes >= tc_split3_scratch_bytes(rows, K, N) &&
+         lda % 4 == 0 && ((uintptr_t)a % 16) == 0 && ((uintptr_t)c % 32) == 0 && ldc % (c_f32 ? 8 : 16) == 0;
+}
+
 GemmP bw_gemm() {
   GemmP p{};
   p.alpha = 1.0f;
@@ -200,6 +222,17 @@ GemmP bw_gemm() {
 // z = A @ L (+ b): pre-activation of one block (dense columns [k_offset, k_offset + K) when K > 0)
 int lin_fwd(const smx_linear& L, const float* A, int64_t lda, int64_t rows, float* C, int64_t ldc, bool use_bias, int k_offset,
             int K, const float* rowbias, int rowbias_div, cudaStream_t st) {
+  {
+    const bool dense = L.n_split <= 1;
+    const int Kt = dense ? (K > 0 ? K : L.in_dim - k_offset) : L.in_dim;
+    if ((dense || (L.in_dim % L.n_split == 0 && L.out_dim % L.n_split == 0)) && bw_tc_ok(rows, Kt, L.out_dim, A, lda, C, ldc, true)) {
+      GemmTc g{};
+      g.bias = (use_bias && L.b) ? L.b : nullptr;
+      g.rowbias = rowbias; g.rowbias_ld = L.out_dim; g.rows_per_group = rowbias_div > 0 ? rowbias_div : 1;
+      g.act = SMX_ACT_IDENTITY; g.alpha = 1.0f; g.out_f32 = C; g.ldo = ldc;
+      return tc_linear_split3(L, dense ? k_offset : 0, Kt, A, lda, rows, g, t_bw_sc, st);
+    }
+  }
   GemmP p = bw_gemm();
   p.A = A; p.lda = lda; p.C = C; p.ldc = ldc; p.M = (int)rows;
   p.rowbias = rowbias; p.rowbias_ld = L.out_dim; p.rowbias_div = rowbias_div;
@@ -220,6 +253,17 @@ int lin_fwd(const smx_linear& L, const float* A, int64_t lda, int64_t rows, floa
 // dX = dZ @ W (+ residual), the gradient with respect to the block's input (dense: columns [k_offset, k_offset + K))
 int lin_dgrad(const smx_linear& L, const float* dZ, int64_t ldz, int64_t rows, void* dX, int dx_dt, int64_t ldx, int k_offset, int K,
               const float* residual, cudaStream_t st) {
+  {
+    const bool dense = L.n_split <= 1;
+    const int Kin = dense ? (K > 0 ? K : L.in_dim - k_offset) : L.in_dim;
+    if ((dense || (L.in_dim % L.n_split == 0 && L.out_dim % L.n_split == 0)) &&
+        bw_tc_ok(rows, L.out_dim, Kin, dZ, ldz, dX, ldx, dx_dt == SMX_F32) && (!residual || (((uintptr_t)residual % 16) == 0 && ldx % 4 == 0))) {
+      GemmTc g{};
+      g.act = SMX_ACT_IDENTITY; g.alpha = 1.0f; g.resid_f32 = residual; g.ldr = ldx; g.ldo = ldx;
+      if (dx_dt == SMX_F32) g.out_f32 = (float*)dX; else g.out = (__nv_bfloat16*)dX;
+      return tc_dgrad_split3(L, dense ? k_offset : 0, Kin, dZ, ldz, rows, g, t_bw_sc, st);
+    }
+  }
   GemmP p = bw_gemm();
   p.A = dZ; p.lda = ldz; p.C = dX; p.c_dtype = dx_dt; p.ldc = ldx; p.M = (int)rows;
   p.residual = residual; p.r_dtype = SMX_F32; p.ldr = ldx;
@@ -233,6 +277,15 @@ int lin_dgrad(const smx_linear& L, const float* dZ, int64_t ldz, int64_t rows, v
     p.W = L.w; p.w_sk = 1; p.w_sn = b; p.w_bs = (int64_t)a * b;
   }
   return gemm(p, st);
+}
+
+// dW[m][i][o] = T[m a + i][m b + o]: the per-head blocks of the dense (in, out) product, in ParallelLinear's layout
+__global__ void gather_heads_kernel(const float* __restrict__ Tm, int ldt, int h, int a, int b, float* __restrict__ dW) {
+  const int64_t n = (int64_t)h * a * b;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+    const int o = (int)(i % b), ii = (int)((i / b) % a), m = (int)(i / ((int64_t)a * b));
+    dW[i] = Tm[(int64_t)(m * a + ii) * ldt + m * b + o];
+  }
 }
 
 int sum_slices(const float* P, int ns, int nrows, int ncols, float* dst, int64_t ldd, cudaStream_t st) {
@@ -252,6 +305,37 @@ void slice_plan(int64_t rows, int& chunk, int& ns) {
 // dW = X^T dZ in the parameter's own layout; split-K over row slices, then a fixed-order reduction.
 int lin_wgrad(const smx_linear& L, const float* dZ, int64_t ldz, const float* X, int64_t ldx, int64_t rows, float* dW, int k_offset,
               int K, Arena& ws, cudaStream_t st) {
+  if (tc_f32_tc_enabled() && rows >= 128) {
+    // tensor-core form: partial products over row slices by the split-bf16 GEMM (contraction over the rows: both operands are
+    // transposed activations), then the same fixed-order reduction as below
+    const bool dense = L.n_split <= 1;
+    const int Kin = dense ? (K > 0 ? K : L.in_dim - k_offset) : L.in_dim;
+    const int M = dense ? L.out_dim : Kin, N = dense ? Kin : L.out_dim;   // dense: dW (out, in); split: product as (in, out), gathered per head
+    if (M % 64 == 0 && N % 64 == 0 && (dense || (L.in_dim % L.n_split == 0 && L.out_dim % L.n_split == 0))) {
+      const size_t m1 = ws.mark();
+      const int nsl = tc_wgrad_slices(rows);
+      float* P = ws.f32((size_t)nsl * M * N);
+      float* Tm = dense ? nullptr : ws.f32((size_t)M * N);
+      void* sc = ws.take(tc_wgrad_scratch_bytes(rows, M, N));
+      if (!P || !sc || (!dense && !Tm)) return fail(SMX_ERR_WORKSPACE, "workspace too small (weight gradient, tensor-core form)");
+      if (!ws.dry) {
+        int ns2 = 0;
+        if (dense) {
+          SMX_TRY(tc_wgrad_split3(dZ, ldz, M, X, ldx, N, rows, P, &ns2, sc, st));
+          SMX_TRY(sum_slices(P, ns2, M, N, dW + k_offset, L.in_dim, st));
+        } else {
+          SMX_TRY(tc_wgrad_split3(X, ldx, M, dZ, ldz, N, rows, P, &ns2, sc, st));
+          SMX_TRY(sum_slices(P, ns2, M, N, Tm, N, st));
+          const int h = L.n_split, a = L.in_dim / h, b = L.out_dim / h;
+          gather_heads_kernel<<<ew_grid((int64_t)h * a * b), 256, 0, st>>>(Tm, N, h, a, b, dW);
+          count_launch();
+          SMX_TRY(check_launch("gather_heads_kernel"));
+        }
+      }
+      ws.release(m1);
+      return SMX_OK;
+    }
+  }
   int chunk, ns;
   slice_plan(rows, chunk, ns);
   const size_t m0 = ws.mark();
@@ -384,6 +468,17 @@ int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int
     return fail(SMX_ERR_UNSUPPORTED, "smx_summary_mixing_bwd does not handle mode %d ('SummaryMixing-expdecay')", w->mode);
   const int64_t rows = (int64_t)B * T;
   if (rows > 0x7fffffff) return fail(SMX_ERR_UNSUPPORTED, "cell backward: more than 2^31 frames");
+  int maxdim = w->enc_dim;
+  {
+    const smx_linear* ls[2 * SMX_MAX_BLOCKS + 2];
+    int nl = 0;
+    for (int i = 0; i < w->n_local; ++i) ls[nl++] = &w->local[i];
+    for (int i = 0; i < w->n_summary; ++i) ls[nl++] = &w->summary[i];
+    if (w->mode == SMX_MODE_FAST) ls[nl++] = &w->global_proj;
+    if (w->mode != SMX_MODE_LITE) ls[nl++] = &w->merge;
+    for (int i = 0; i < nl; ++i) { maxdim = ls[i]->in_dim > maxdim ? ls[i]->in_dim : maxdim; maxdim = ls[i]->out_dim > maxdim ? ls[i]->out_dim : maxdim; }
+  }
+  BwScratch bw_scratch(ws, rows, maxdim);
   if (w->mode == SMX_MODE_FAST) {
     // G = act(W_g x + b_g) * mask (rows, 2 D_l); local = G[:, :D_l], S = G[:, D_l:]; mean_b = sum_t S / count_b;
     // y = act(local Wc[:, :D_l]^T + mean_b Wc[:, D_l:]^T + b_c); no LayerNorms            summary_mixing.py:255-298
@@ -663,6 +758,9 @@ int vanilla_bwd_generic(const smx_linear* blocks, int n, int act, int64_t rows, 
       return fail(SMX_ERR_BAD_ARG, "input_size and n_neurons must be dividible by n_split!");
   const size_t m0 = ws.mark();
   const int D = blocks[0].in_dim, N = blocks[n - 1].out_dim;
+  int maxdim = D;
+  for (int i = 0; i < n; ++i) maxdim = blocks[i].out_dim > maxdim ? blocks[i].out_dim : maxdim;
+  BwScratch bw_scratch(ws, rows, maxdim);
   const float* x32 = (const float*)x;
   if (x_dt != SMX_F32) {
     BW_BUF(xc, rows * D);
@@ -704,6 +802,7 @@ int ffn_bwd_generic(const smx_ffn_weights* w, int act, int64_t rows, const void*
     return fail(SMX_ERR_BAD_ARG, "ffn backward: inconsistent dims");
   if (rows > 0x7fffffff) return fail(SMX_ERR_UNSUPPORTED, "ffn backward: more than 2^31 rows");
   const size_t m0 = ws.mark();
+  BwScratch bw_scratch(ws, rows, D > F ? D : F);
   const float* x32 = (const float*)x;
   if (x_dt != SMX_F32) {
     BW_BUF(xc, rows * D);
@@ -757,6 +856,7 @@ int convmod_bwd_generic(const smx_convmod_weights* w, int act, int B, int T, con
   if (rows > 0x7fffffff) return fail(SMX_ERR_UNSUPPORTED, "conv module backward: more than 2^31 frames");
   const int pad = w->causal ? (k - 1) : (k - 1) / 2;
   const size_t m0 = ws.mark();
+  BwScratch bw_scratch(ws, rows, 2 * D);
   const float* x32 = (const float*)x;
   if (x_dt != SMX_F32) {
     BW_BUF(xc, rows * D);

@@ -172,6 +172,7 @@ struct GemmTc {
   __nv_bfloat16* out; int64_t ldo;
   float* out_f32 = nullptr; const float* resid_f32 = nullptr;   // fp32 output / residual instead of out / resid
   int split3 = 0;                                     // set by tc_linear_split3
+  int ksplit = 1; int64_t out_split_stride = 0;       // split-K: fp32 partials out_f32 + ks * out_split_stride (summed by the caller)
 };
 bool tc_gemm_supported(int K, int N);
 // fp32 linears on the tensor cores with split-bf16 operands (smx_tc_gemm.cu)
@@ -180,6 +181,11 @@ bool tc_split3_ok(int64_t rows, int K, int N);
 bool tc_f32_tc_enabled();
 void tc_set_f32_tc(int on);
 int tc_linear_split3(const smx_linear& L, int k_offset, int K, const float* A, int64_t lda, int64_t rows, GemmTc g, void* scratch, cudaStream_t st);
+int tc_dgrad_split3(const smx_linear& L, int k_offset, int Kin, const float* dZ, int64_t ldz, int64_t rows, GemmTc g, void* scratch, cudaStream_t st);
+size_t tc_wgrad_scratch_bytes(int64_t rows, int M, int N);
+int tc_wgrad_slices(int64_t rows);
+int tc_wgrad_split3(const float* A, int64_t lda, int M, const float* Bm, int64_t ldb, int N, int64_t rows, float* P, int* ns, void* scratch,
+                    cudaStream_t st);  // P[slice][M][N] = partial sums over row slices of A^T B
 int tc_gemm_launch(const GemmTc& g, cudaStream_t st);
 int tc_dense_bf16(const smx_linear& L, int k_offset, int K, void* out, cudaStream_t st);  // (out_dim, K) bf16 copy of columns [k_offset, +K)
 size_t tc_csgu_workspace_bytes(int64_t rows);

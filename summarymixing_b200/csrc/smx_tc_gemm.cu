@@ -32,6 +32,8 @@ struct GemmTcP {
   __nv_bfloat16* out; int64_t ldo;
   float* out_f32; const float* resid_f32;   // fp32 output / residual (split3 arm); out / resid are NULL then
   int split3;                                // A and W hold [hi | lo] halves of width K: accumulate hi*hi + hi*lo + lo*hi
+  int ksplit, kb_per_split;                  // split-K: slice ks covers K-blocks [ks kb_per_split, ...) and writes out_f32 + ks * out_split_stride
+  int64_t out_split_stride;
   int n_stages; uint32_t stage_bytes; uint32_t tmem_cols;
 };
 
@@ -60,8 +62,9 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
   const int nkb1 = p.K >> 6, NT = p.NT;
-  const int nkb = p.split3 ? 3 * nkb1 : nkb1;  // split3: K-block kb' = (segment, kb): segments (hi,hi) (hi,lo) (lo,hi)
-  const int n_tiles_total = p.m_tiles * p.n_tiles;
+  const int nseg = p.split3 ? 3 : 1;           // split3: iteration = (segment, K-block): segments (hi,hi) (hi,lo) (lo,hi)
+  const int mn_tiles = p.m_tiles * p.n_tiles;
+  const int n_tiles_total = mn_tiles * p.ksplit;
 
   if (warp == 0) tc::tmem_alloc(&tmem_base_s, p.tmem_cols);
   if (tid == 32) {
@@ -82,13 +85,15 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
       int s = 0;
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
-        const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+        const int ks = tile / mn_tiles, t2 = tile - ks * mn_tiles;
+        const int nt = t2 / p.m_tiles, mt = t2 - nt * p.m_tiles;
+        const int kb0 = ks * p.kb_per_split, nloc = min(p.kb_per_split, nkb1 - kb0);
 #pragma unroll 1
-        for (int kb = 0; kb < nkb; ++kb) {
+        for (int kb = 0; kb < nseg * nloc; ++kb) {
           tc::mbar_wait(&empty_bar[s], ph ^ 1u);
           tc::mbar_arrive_expect_tx(&full_bar[s], p.stage_bytes);
           uint8_t* dst = smem + (size_t)s * p.stage_bytes;
-          const int seg = kb / nkb1, k1 = kb - seg * nkb1;
+          const int seg = kb / nloc, k1 = kb0 + kb - seg * nloc;
           gm_tma_load_2d(dst, &tmA, k1 * 64 + (seg == 2 ? p.K : 0), mt * 128, &full_bar[s]);          // rows >= M are zero-filled
           gm_tma_load_2d(dst + kblock_bytes(128), &tmW, k1 * 64 + (seg == 1 ? p.K : 0), nt * NT, &full_bar[s]);
           if (++s == p.n_stages) { s = 0; ph ^= 1u; }
@@ -107,6 +112,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
       tc::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator (first two uses: fresh)
       tc::tc_fence_after();
       const uint32_t d_addr = tmem + (uint32_t)buf * (uint32_t)NT;
+      const int ks = tile / mn_tiles;
+      const int nkb = nseg * min(p.kb_per_split, nkb1 - ks * p.kb_per_split);
 #pragma unroll 1
       for (int kb = 0; kb < nkb; ++kb) {
         tc::mbar_wait_spin(&full_bar[s], ph);
@@ -132,7 +139,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
     int it = 0;
     for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
       const int buf = it & 1;
-      const int nt = tile / p.m_tiles, mt = tile - nt * p.m_tiles;
+      const int ks = tile / mn_tiles, t2 = tile - ks * mn_tiles;
+      const int nt = t2 / p.m_tiles, mt = t2 - nt * p.m_tiles;
       const int64_t grow = (int64_t)mt * 128 + r;
       const bool live = grow < p.M;
       const float rscale = (live && p.rowmask) ? (float)p.rowmask[grow] : 1.0f;
@@ -180,7 +188,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
           }
         }
         if (live && p.out_f32) {
-          float* op = p.out_f32 + grow * p.ldo + gcol;
+          float* op = p.out_f32 + (int64_t)ks * p.out_split_stride + grow * p.ldo + gcol;
 #pragma unroll
           for (int j = 0; j < 4; ++j) gm_stg256(op + 8 * j, reinterpret_cast<const uint32_t*>(v + 8 * j));
         } else if (live) {
@@ -260,6 +268,15 @@ int tc_gemm_launch(const GemmTc& g, cudaStream_t st) {
   p.bias = g.bias; p.rowbias = g.rowbias; p.rowbias_ld = g.rowbias_ld; p.rows_per_group = g.rows_per_group > 0 ? g.rows_per_group : 1;
   p.act = g.act; p.rowmask = g.rowmask; p.resid = g.resid; p.ldr = g.ldr; p.alpha = g.alpha;
   p.out = g.out; p.ldo = g.ldo; p.out_f32 = g.out_f32; p.resid_f32 = g.resid_f32; p.split3 = g.split3;
+  {
+    const int nkb1 = g.K / 64;
+    int want = g.ksplit > 1 ? g.ksplit : 1;
+    if (want > 1 && !g.out_f32) return fail(SMX_ERR_BAD_ARG, "tc gemm: split-K needs fp32 partial outputs");
+    if (want > nkb1) want = nkb1;
+    p.kb_per_split = (nkb1 + want - 1) / want;
+    p.ksplit = (nkb1 + p.kb_per_split - 1) / p.kb_per_split;   // no empty slice
+    p.out_split_stride = g.out_split_stride;
+  }
   p.stage_bytes = kblock_bytes(128) + (uint32_t)p.NT * 128u;
   int stages = (int)((227 * 1024 - 2048) / p.stage_bytes);
   if (stages > GM_MAX_STAGES) stages = GM_MAX_STAGES;
@@ -272,7 +289,7 @@ int tc_gemm_launch(const GemmTc& g, cudaStream_t st) {
   const size_t smem = (size_t)stages * p.stage_bytes + 1024;
   cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(gemm_tc_kernel): %s", cudaGetErrorString(e));
-  const int total = p.m_tiles * p.n_tiles;
+  const int total = p.m_tiles * p.n_tiles * p.ksplit;
   const unsigned grid = (unsigned)(total < gm_sms() ? total : gm_sms());
   e = launch_pdl(gemm_tc_kernel, dim3(grid), dim3(GM_THREADS), smem, st, 1u, tmA, tmW, p);
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaLaunchKernelEx(gemm_tc_kernel): %s", cudaGetErrorString(e));
@@ -340,7 +357,7 @@ __global__ void __launch_bounds__(256) split_weight_kernel(const float* __restri
   out[(int64_t)n * 2 * K + K + (k - k_offset)] = __float2bfloat16(val - __bfloat162float(h));
 }
 size_t tc_split3_scratch_bytes(int64_t rows, int K, int N) { return align_up((size_t)rows * 2 * K * 2, 1024) + align_up((size_t)N * 2 * K * 2, 1024); }
-bool tc_split3_ok(int64_t rows, int K, int N) { return rows >= 1024 && tc_gemm_supported(K, N); }
+bool tc_split3_ok(int64_t rows, int K, int N) { return rows >= 128 && tc_gemm_supported(K, N); }  // (one full row tile: the arithmetic of a row must not depend on how many rows ride along -- utterance sharding)
 static std::atomic<int> g_f32_tc{1};
 void tc_set_f32_tc(int on) { g_f32_tc = on ? 1 : 0; }
 bool tc_f32_tc_enabled() { return g_f32_tc.load() != 0; }
@@ -358,6 +375,97 @@ int tc_linear_split3(const smx_linear& L, int k_offset, int K, const float* A, i
   SMX_TRY(check_launch("split_weight_kernel"));
   g.a = a2; g.lda = 2 * (int64_t)K; g.M = rows; g.N = L.out_dim; g.K = K; g.w = w2; g.split3 = 1;
   return tc_gemm_launch(g, st);
+}
+
+// ---- backward linears on the tensor cores (split-bf16, fp32 accuracy) -----------------------------------------------------------
+// out (C, 2 Kp) = [hi | lo] of x^T for x (rows, C) fp32; Kp = rows rounded up to 64 (zero padded): the operands of a weight gradient
+// dW = dZ^T X are the TRANSPOSED activations, contracted over the rows.
+__global__ void __launch_bounds__(256) split_transpose_kernel(const float* __restrict__ x, int64_t ldx, int64_t rows, int C, int64_t Kp,
+                                                              __nv_bfloat16* __restrict__ out) {
+  __shared__ float tile[32][33];
+  const int64_t r0 = (int64_t)blockIdx.x * 32;
+  const int c0 = blockIdx.y * 32;
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;  // 32 x 8
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int64_t r = r0 + ty + 8 * j;
+    const int c = c0 + tx;
+    tile[ty + 8 * j][tx] = (r < rows && c < C) ? x[r * ldx + c] : 0.0f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const int c = c0 + ty + 8 * j;
+    const int64_t r = r0 + tx;
+    if (c < C && r < Kp) {
+      const float v = tile[tx][ty + 8 * j];
+      const __nv_bfloat16 h = __float2bfloat16(v);
+      out[(int64_t)c * 2 * Kp + r] = h;
+      out[(int64_t)c * 2 * Kp + Kp + r] = __float2bfloat16(v - __bfloat162float(h));
+    }
+  }
+}
+// W'' (Kin, 2 out) = [hi | lo] of the TRANSPOSED dense view: W''[i][o] = W[o][k_offset + i] (data gradient dX = dZ W)
+__global__ void __launch_bounds__(256) split_weight_t_kernel(const float* __restrict__ w, int in_dim, int out_dim, int n_split, int k_offset, int Kin,
+                                                             __nv_bfloat16* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)Kin * out_dim) return;
+  const int i = (int)(idx / out_dim), o = (int)(idx % out_dim), k = i + k_offset;
+  float val;
+  if (n_split <= 1) {
+    val = w[(int64_t)o * in_dim + k];
+  } else {
+    const int hi_ = in_dim / n_split, ho = out_dim / n_split, m = o / ho;
+    val = (k / hi_ == m) ? w[((int64_t)m * hi_ + (k - m * hi_)) * ho + (o - m * ho)] : 0.0f;
+  }
+  const __nv_bfloat16 h = __float2bfloat16(val);
+  out[(int64_t)i * 2 * out_dim + o] = h;
+  out[(int64_t)i * 2 * out_dim + out_dim + o] = __float2bfloat16(val - __bfloat162float(h));
+}
+// dX (rows, Kin) = dZ (rows, out) @ W[:, k_offset : k_offset + Kin]; g carries the output / residual
+int tc_dgrad_split3(const smx_linear& L, int k_offset, int Kin, const float* dZ, int64_t ldz, int64_t rows, GemmTc g, void* scratch, cudaStream_t st) {
+  if (ldz % 4 || ((uintptr_t)dZ % 16)) return fail(SMX_ERR_ALIGNMENT, "split3 dgrad: dZ alignment");
+  const int out = L.out_dim;
+  __nv_bfloat16* a2 = (__nv_bfloat16*)scratch;
+  __nv_bfloat16* w2 = (__nv_bfloat16*)((char*)scratch + align_up((size_t)rows * 2 * out * 2, 1024));
+  const int64_t na = rows * (out / 4), nw = (int64_t)Kin * out;
+  split_rows_kernel<<<(unsigned)((na + 255) / 256), 256, 0, st>>>(dZ, ldz, rows, out, a2);
+  count_launch();
+  SMX_TRY(check_launch("split_rows_kernel"));
+  split_weight_t_kernel<<<(unsigned)((nw + 255) / 256), 256, 0, st>>>(L.w, L.in_dim, L.out_dim, L.n_split, k_offset, Kin, w2);
+  count_launch();
+  SMX_TRY(check_launch("split_weight_t_kernel"));
+  g.a = a2; g.lda = 2 * (int64_t)out; g.M = rows; g.N = Kin; g.K = out; g.w = w2; g.split3 = 1;
+  return tc_gemm_launch(g, st);
+}
+// P (ksplit, M, N) fp32 partials of A^T B over the rows: A (rows, M), B (rows, N); returns the number of slices in *ns
+size_t tc_wgrad_scratch_bytes(int64_t rows, int M, int N) {
+  const int64_t Kp = (rows + 63) / 64 * 64;
+  return align_up((size_t)M * 2 * Kp * 2, 1024) + align_up((size_t)N * 2 * Kp * 2, 1024);
+}
+int tc_wgrad_slices(int64_t rows) { const int64_t nkb = (rows + 63) / 64; return (int)(nkb < 64 ? nkb : 64); }
+int tc_wgrad_split3(const float* A, int64_t lda, int M, const float* Bm, int64_t ldb, int N, int64_t rows, float* P, int* ns, void* scratch,
+                    cudaStream_t st) {
+  const int64_t Kp = (rows + 63) / 64 * 64;
+  if (Kp > 0x7fffffff) return fail(SMX_ERR_UNSUPPORTED, "split3 wgrad: too many rows");
+  __nv_bfloat16* a2 = (__nv_bfloat16*)scratch;
+  __nv_bfloat16* b2 = (__nv_bfloat16*)((char*)scratch + align_up((size_t)M * 2 * Kp * 2, 1024));
+  dim3 ga((unsigned)(Kp / 32), (M + 31) / 32), gb((unsigned)(Kp / 32), (N + 31) / 32);
+  split_transpose_kernel<<<ga, 256, 0, st>>>(A, lda, rows, M, Kp, a2);
+  count_launch();
+  SMX_TRY(check_launch("split_transpose_kernel"));
+  split_transpose_kernel<<<gb, 256, 0, st>>>(Bm, ldb, rows, N, Kp, b2);
+  count_launch();
+  SMX_TRY(check_launch("split_transpose_kernel"));
+  GemmTc g{};
+  g.a = a2; g.lda = 2 * Kp; g.M = M; g.N = N; g.K = (int)Kp; g.w = b2; g.split3 = 1;
+  g.act = SMX_ACT_IDENTITY; g.alpha = 1.0f;
+  g.out_f32 = P; g.ldo = N; g.ksplit = tc_wgrad_slices(rows); g.out_split_stride = (int64_t)M * N;
+  SMX_TRY(tc_gemm_launch(g, st));
+  const int nkb1 = (int)(Kp / 64);
+  const int kbps = (nkb1 + g.ksplit - 1) / g.ksplit;
+  *ns = (nkb1 + kbps - 1) / kbps;
+  return SMX_OK;
 }
 
 // =============================================================================================

@@ -79,3 +79,29 @@ def test_combiner_split_is_exact():
     W, b = sd["summary_local_merging.linear.w.weight"], sd["summary_local_merging.linear.w.bias"]
     y = O.activation("swish", local @ W[:, :64].T + (mu @ W[:, 64:].T + b).unsqueeze(1))
     assert float((y - fx.y.double()).abs().max()) < 5e-6
+
+
+def test_mhsa_comparison_arm_oracle_matches_reference():
+    """oracle.conformer_encoder_mhsa (the self-attention comparison arm of BASELINE.json configs[4], tools/rtf_sweep.py) against
+    the unmodified reference's ConformerEncoder(attention_type='regularMHA') output (fixture by oracle/gen_golden_tile.py --mhsa).
+    The state_dict is rebuilt from the seeded stream with the reference's key names and shapes."""
+    import json
+    import os
+
+    import numpy as np
+
+    from oracle.seeded import seeded_input, seeded_param
+
+    z = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "mhsa", "mhsa_conformer_enc.npz"))
+    cfg = json.loads(bytes(z["cfg"]).decode())
+    D, F, k = cfg["d_model"], cfg["d_ffn"], cfg["kernel_size"]
+    shapes = {"in_proj_weight": (3 * D, D), "in_proj_bias": (3 * D,), "out_proj.weight": (D, D), "out_proj.bias": (D,),
+              "bottleneck.0.weight": (2 * D, D, 1), "bottleneck.0.bias": (2 * D,), "conv.weight": (D, 1, k), "conv.bias": (D,),
+              "after_conv.2.weight": (D, D), "ffn.0.weight": (F, D), "ffn.0.bias": (F,), "ffn.3.weight": (D, F)}
+    sd = {}
+    for key in [str(s) for s in z["keys"]]:
+        shape = next((v for s, v in shapes.items() if key.endswith(s)), (D,))
+        sd[key] = seeded_param(cfg["seed_w"], key, shape)
+    x = seeded_input(cfg["seed_x"], cfg["B"], cfg["T"], D)
+    y = O.conformer_encoder_mhsa(x, sd, cfg["num_layers"], cfg["nhead"], act=cfg["act"], key_padding_mask=torch.from_numpy(z["pad"]))
+    assert float((y - torch.from_numpy(z["y32"])).abs().max()) < 2e-5
