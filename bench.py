@@ -318,6 +318,70 @@ def other_configs(dev, steps: int = 5):
     return out
 
 
+def train_line(dev, world: int, rank: int, steps: int = 3):
+    """One data-parallel TRAINING step of the same encoder (forward + backward through smx_*_bwd + gradient exchange + SGD), every
+    rank on its own B x T batch.  The gradient all-reduce (NCCL over NVLink, flat fp32 buckets) is launched from gradient-ready
+    hooks during backward (summarymixing_b200.parallel.GradientBucketer); `exposed_comm_ms` = step time minus the time of the
+    same step without any exchange.  Called by ALL ranks (collectives inside); times are the max over ranks."""
+    import torch
+    import torch.distributed as dist
+
+    import summarymixing_b200 as S
+    from summarymixing_b200 import parallel as P
+
+    torch.manual_seed(0)
+    enc = S.ConformerEncoder(LAYERS, D, FFN, HEADS, KSIZE, attention_type="SummaryMixing", local_proj_hid_dim=[D], local_proj_out_dim=D,
+                             summary_hid_dim=[D], mode="SummaryMixing", dropout=0.0).to(dev).train()
+    params = list(enc.parameters())
+    opt = torch.optim.SGD(params, lr=0.01)
+    g = torch.Generator().manual_seed(200 + rank)
+    x = torch.randn(B, T, D, generator=g).to(dev).to(torch.bfloat16)
+    lens = torch.randint(T // 2, T + 1, (B,), generator=g)
+    mask = (torch.arange(T)[None] < lens[:, None]).to(dev)
+    target = torch.randn(B, T, D, generator=g).to(dev)
+    bucketer = P.GradientBucketer(params) if world > 1 else None
+
+    def step(exchange: bool):
+        opt.zero_grad(set_to_none=True)
+        y = enc(x, src_key_padding_mask=mask)[0]
+        loss = ((y.float() - target) * mask[..., None]).pow(2).mean()
+        loss.backward()
+        calls = bucketer.finish() if (bucketer and exchange) else 0
+        opt.step()
+        return calls
+
+    def timed(exchange: bool):
+        calls = 0
+        for _ in range(2):
+            calls = step(exchange)
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            step(exchange)
+        e1.record()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        return P.max_over_ranks(e0.elapsed_time(e1) / steps, device=dev), calls
+
+    ms_x, calls = timed(True)
+    if bucketer:
+        bucketer.remove()
+        bucketer = None
+    ms_c, _ = timed(False) if world > 1 else (ms_x, 0)
+    n_par = sum(p.numel() for p in params)
+    del enc, opt
+    torch.cuda.empty_cache()
+    return {"ms_per_step": ms_x, "frames_per_s": world * B * T / ms_x * 1e3, "io": "bf16 activations, fp32 gradients",
+            "backward": "smx_*_bwd: linears (recompute, dgrad, wgrad) as split-bf16 tcgen05 GEMMs, elementwise / reductions on CUDA cores",
+            "allreduce_bytes_per_step": n_par * 4 if world > 1 else 0, "allreduce_calls_per_step": calls,
+            "exchange": "flat fp32 buckets of 32 MB, all-reduce launched from gradient-ready hooks during backward (async NCCL)" if world > 1 else "none (1 GPU)",
+            "compute_only_ms": ms_c, "exposed_comm_ms": max(0.0, ms_x - ms_c), "params": n_par, "steps": steps}
+
+
 def run_smx(args):
     import torch
     import torch.distributed as dist
@@ -404,6 +468,12 @@ def run_smx(args):
         e2e_ms = f0.elapsed_time(f1)
         clocks = sampler.stop() if sampler else None
 
+    train = None
+    if not args.no_train:
+        try:
+            train = train_line(dev, world, rank)
+        except Exception as exc:  # never take the headline down
+            train = {"error": repr(exc)[:200]}
     t = torch.tensor([ms_total, e2e_ms], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -426,7 +496,7 @@ def run_smx(args):
                     "api": "summarymixing_b200.HostPipeline(ConformerEncoder).run(host batches): pinned host inputs/outputs, H2D and "
                            "D2H on their own streams inside the timed region, overlapped with the previous/next step; forward = "
                            "CUDA-graph replay of ConformerEncoder.forward"},
-            "gpu_launches": launches, "tc_launches": tc_launches, "clocks": clocks}
+            "gpu_launches": launches, "tc_launches": tc_launches, "clocks": clocks, "train": train}
 
     if rank == 0:
         with torch.no_grad():
@@ -504,6 +574,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="smx", choices=["smx", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg (profiling runs)")
+    ap.add_argument("--no-train", action="store_true", help="skip the training-step side measurement")
     ap.add_argument("--no-others", action="store_true", help="skip the cfg3 / cfg4 side measurements")
     ap.add_argument("--eager", action="store_true", help="time eager launches instead of CUDA-graph replay (ncu runs)")
     args = ap.parse_args()

@@ -109,3 +109,90 @@ def allreduce_gradients(params, world: Optional[int] = None, bucket_bytes: int =
         calls += 1
         i = j
     return calls
+
+
+class GradientBucketer:
+    """Data-parallel gradient exchange OVERLAPPED with the backward pass (what SpeechBrain's DistributedDataParallel wrapper does
+    for the reference): parameters are grouped into flat fp32 buckets in reverse registration order (the order in
+    which backward produces their gradients); a post-accumulate hook copies each gradient into its bucket, and the moment a
+    bucket is complete its all-reduce is launched asynchronously (NCCL: on the communicator's own stream, under the rest of the
+    backward).  `finish()` waits for the collectives, divides by the world size and hands the averaged gradients back.
+
+        bucketer = GradientBucketer(model.parameters())          # once
+        loss.backward(); bucketer.finish(); optimizer.step()     # every step
+
+    Every rank must build it over the same parameters in the same order.  A parameter that received no gradient in a step counts
+    as zeros (its bucket is completed by finish()).  Results are identical to `allreduce_gradients` (same sums, same order)."""
+
+    def __init__(self, params, bucket_bytes: int = 32 << 20, group=None):
+        self.group = group
+        self.params = [p for p in params if p.requires_grad]
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        self.buckets = []   # (flat, [(param, offset)], )
+        order = list(reversed(self.params))
+        i = 0
+        while i < len(order):
+            j, n = i, 0
+            while j < len(order) and (j == i or (n + order[j].numel()) * 4 <= bucket_bytes):
+                n += order[j].numel()
+                j += 1
+            flat = torch.zeros(n, dtype=torch.float32, device=order[i].device)
+            items, off = [], 0
+            for p in order[i:j]:
+                items.append((p, off))
+                off += p.numel()
+            self.buckets.append({"flat": flat, "items": items, "ready": 0, "work": None, "seen": set()})
+            i = j
+        self._where = {}
+        for bi, b in enumerate(self.buckets):
+            for p, off in b["items"]:
+                self._where[id(p)] = (bi, off)
+        self._handles = [p.register_post_accumulate_grad_hook(self._hook) for p in self.params] if self.world > 1 else []
+        self.calls = 0
+
+    def _launch(self, b):
+        b["work"] = dist.all_reduce(b["flat"], op=dist.ReduceOp.SUM, group=self.group, async_op=True)
+        self.calls += 1
+
+    def _hook(self, p):
+        bi, off = self._where[id(p)]
+        b = self.buckets[bi]
+        if id(p) in b["seen"]:
+            return
+        b["seen"].add(id(p))
+        b["flat"][off:off + p.numel()].copy_(p.grad.reshape(-1))
+        b["ready"] += 1
+        if b["ready"] == len(b["items"]):
+            self._launch(b)
+
+    def finish(self) -> int:
+        """Wait for the bucket all-reduces (launching those whose parameters got no gradient this step), average, write back."""
+        if self.world == 1:
+            return 0
+        for b in self.buckets:
+            if b["work"] is None:
+                for p, off in b["items"]:
+                    if id(p) not in b["seen"]:
+                        if p.grad is None:
+                            b["flat"][off:off + p.numel()].zero_()
+                        else:
+                            b["flat"][off:off + p.numel()].copy_(p.grad.reshape(-1))
+                self._launch(b)
+        for b in self.buckets:
+            b["work"].wait()
+            b["flat"].div_(self.world)
+            for p, off in b["items"]:
+                g = b["flat"][off:off + p.numel()].view_as(p).to(p.dtype)
+                if p.grad is None:
+                    p.grad = g.clone()
+                else:
+                    p.grad.copy_(g)
+            b["ready"], b["work"] = 0, None
+            b["seen"].clear()
+        n, self.calls = self.calls, 0
+        return n
+
+    def remove(self):
+        for h in self._handles:
+            h.remove()
+        self._handles = []

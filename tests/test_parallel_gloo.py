@@ -125,3 +125,54 @@ def test_gradient_allreduce_equals_full_batch_gradient_world2():
     for rank, err, calls in res:
         assert err < 1e-5, f"rank {rank}: averaged shard gradients != full-batch gradient ({err})"
         assert calls >= 2
+
+
+def _bucketer_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import smx_oracle as O
+        from tests import _golden as G
+
+        fx = G.Fixture("cell_sm_h4_swish")
+        g = torch.Generator().manual_seed(9)
+        B, T, D = 5, 37, fx.cfg["enc_dim"]
+        x = torch.randn(B, T, D, generator=g)
+        lens = torch.tensor([37, 20, 1, 37, 9])
+        mask = torch.arange(T)[None] < lens[:, None]
+        xs, ms = P.shard_batch(x, mask, rank, world)
+
+        def run(overlapped):
+            sd = {k: torch.nn.Parameter(v.clone()) for k, v in fx.sd.items()}
+            params = list(sd.values())
+            bk = P.GradientBucketer(params, bucket_bytes=16 << 10) if overlapped else None  # hooks fire during backward
+            y = O.summary_mixing(xs, sd, mode=fx.cfg["mode"], act=fx.cfg["act"], src_padding_mask=ms)
+            (y * ms[..., None]).pow(2).sum().backward()
+            calls = bk.finish() if overlapped else P.allreduce_gradients(params, bucket_bytes=16 << 10)
+            return [p.grad.clone() for p in params], calls
+
+        ga, ca = run(True)
+        gb, cb = run(False)
+        err = max(float((a - b).abs().max()) for a, b in zip(ga, gb))
+        q.put((rank, err, ca, cb))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_overlapped_bucketer_matches_plain_allreduce_world2():
+    """GradientBucketer (bucket all-reduces launched from gradient-ready hooks DURING backward) gives the same averaged
+    gradients as the after-the-fact allreduce_gradients; several buckets, including one completed only by finish()."""
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_bucketer_worker, args=(r, world, port, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for rank, err, ca, cb in res:
+        assert err < 1e-6, f"rank {rank}: overlapped != plain ({err})"
+        assert ca >= 2 and cb >= 2
