@@ -24,6 +24,7 @@
 // Warp roles:  0-15 epilogue | 16-19 LayerNorm of the CTA's second tile, then per-utterance finalisation
 //              | 20 TMA producer (x tiles, weight ring) | 21 MMA issuer
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "smx_tc.h"
 #include "smx_tc_common.cuh"
@@ -38,6 +39,7 @@ constexpr int C4_SLOTS = 4;
 constexpr uint32_t C4_SLOT = 16384, C4_BLOCK = 8192;
 constexpr int C4_MAXU = 8;       // MMA units (one K-block of one column group) per half-GEMM
 constexpr int C4_MAX_TILES = 2;  // tiles resident per CTA
+constexpr int C4_SYNC_STRIDE = 8;  // ints between two utterances' counters / flags: pollers of one do not share a sector with the atomics of another
 
 // One half (column half c) of one GEMM: its units in issue order; the weight blocks lie in the same order in the image.
 struct C4Half {
@@ -60,22 +62,26 @@ struct C4P {
   int c0_in_x;                                // the combiner's first half is prefetched into the (dead) X tile instead of the ring
   uint32_t c0_bytes;
   const float* b_s1; const float* b_s2; const float* b_f1; const float* b_f2;
-  const float* lnl_w; const float* lnl_b;     // local_norm (NULL: no LayerNorm)
+  int use_lnl;                                // local_norm is applied (folded: gamma into the combiner weights, beta into c[b], see E2 / E3)
+  const float* gw;                            // [Dout] gw[n] = sum_k bf16(gamma_k W_c[n,k]) (zeros without LayerNorm)
+  const float* bw;                            // [Dout] bw[n] = sum_k beta_k W_c[n,k], added to c[b] by the finalisation (zeros without)
   int act;
   int Ds, Dl, Dout;
   const float* lns_w; const float* lns_b;     // summary_norm (NULL: none)
   const __nv_bfloat16* wcsT;                  // [Ds][Dout] bf16: W_c[:, D_l:] transposed (k-major)
   const float* bc;
-  float* colsum;                              // [n_tiles][Ds]
+  float* colsum;                              // [n_tiles][4 row quadrants][Ds]
   float* rowbias;                             // [B][Dout]
-  int* cnt; int* flag;                        // [B] each, zero on entry
-  uint32_t off_ring, off_par, off_red, off_stat, off_fin;
-  unsigned long long* trace;                  // debug timeline of CTA 0 (NULL: off)
+  int* cnt; int* flag;                        // [B] each, one 32-byte sector per utterance (index b * C4_SYNC_STRIDE), zero on entry
+  int fin_parts;                              // owner CTAs per utterance (4, 2 or 1): each finalises Dout / fin_parts outputs of c[b]
+  uint32_t off_ring, off_par, off_red, off_stat, off_fin, off_rbw;
+  unsigned long long* trace;                  // debug timeline of CTA trace_cta (NULL: off)
+  int trace_cta;
 };
 
 #define C4_TRACE(role, ev)                                                                       \
   do {                                                                                           \
-    if (p.trace && blockIdx.x == 0 && lane == 0 && (ev) < 64) p.trace[(role) * 64 + (ev)] = clock64(); \
+    if (p.trace && blockIdx.x == p.trace_cta && lane == 0 && (ev) < 64) p.trace[(role) * 64 + (ev)] = clock64(); \
   } while (0)
 
 // ---- small PTX helpers ---------------------------------------------------------------------------------------------
@@ -167,6 +173,27 @@ __device__ __forceinline__ void c4_bias_act32(float* v, const float* sB, int act
   }
 }
 
+// E3: v[j] = act(rs * v[j] + nm * gw[j] + cb[j]) -- the combiner epilogue with the local LayerNorm folded in (rs = 1/std,
+// nm = -mean/std of the row; gw / cb staged pre-halved for a compile-time Swish, like the biases of c4_bias_act32)
+template <int ACT>
+__device__ __forceinline__ void c4_affine_act32(float* v, float rs, float nm, const float* sGw, const float* sCb, int act) {
+  const float4* gp = reinterpret_cast<const float4*>(sGw);
+  const float4* cp = reinterpret_cast<const float4*>(sCb);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const float4 g = gp[j], c = cp[j];
+    const float h0 = fmaf(rs, v[4 * j], fmaf(nm, g.x, c.x)), h1 = fmaf(rs, v[4 * j + 1], fmaf(nm, g.y, c.y));
+    const float h2 = fmaf(rs, v[4 * j + 2], fmaf(nm, g.z, c.z)), h3 = fmaf(rs, v[4 * j + 3], fmaf(nm, g.w, c.w));
+    if (ACT == SMX_ACT_SWISH) {
+      v[4 * j] = fmaf(h0, tc::tanh_approx(h0), h0); v[4 * j + 1] = fmaf(h1, tc::tanh_approx(h1), h1);
+      v[4 * j + 2] = fmaf(h2, tc::tanh_approx(h2), h2); v[4 * j + 3] = fmaf(h3, tc::tanh_approx(h3), h3);
+    } else {
+      v[4 * j] = h0; v[4 * j + 1] = h1; v[4 * j + 2] = h2; v[4 * j + 3] = h3;
+    }
+  }
+  if (ACT != SMX_ACT_SWISH) tc::act_apply<32>(act, v);
+}
+
 // One copy of the in-place LayerNorm for both callers (epilogue warps: first tile, 8 rows each; prologue warps: second tile,
 // 4 x 8 rows each).  Code size matters here: every CTA executes the kernel's code at most twice, so instruction fetch is paid in
 // full -- ncu of the first build: 20 % of the stall samples were no_instructions, instruction-cache hit rate 59 %.
@@ -185,27 +212,30 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
   float* sRed = reinterpret_cast<float*>(smem + p.off_red);   // 2048 floats: phase 1 column partials [4][256]; phase 2 LayerNorm partials [8][128] x (mean, M2)
   float2* sStat = reinterpret_cast<float2*>(smem + p.off_stat);  // [2][128] per-row (1/std, -mean/std) of the norm1 prologue, one set per tile
   float* sFin = reinterpret_cast<float*>(smem + p.off_fin);   // finalisation scratch: mu[256] | partial c [4][256] | red[16]
+  float* sRBw = reinterpret_cast<float*>(smem + p.off_rbw);   // [2 (tile parity)][256]: c[b] (+ the local LayerNorm's beta share) of the tile's utterance
   __shared__ __align__(8) uint64_t full_bar[C4_SLOTS], empty_bar[C4_SLOTS];
   __shared__ __align__(8) uint64_t x_raw[C4_MAX_TILES], x_ready[C4_MAX_TILES];
-  __shared__ __align__(8) uint64_t acc1_full[2], acc2_full[2], acc3_full[2], h_full[2], x_free[2], l_full;
-  __shared__ __align__(8) uint64_t x_dead[C4_MAX_TILES], c_full[C4_MAX_TILES];
+  __shared__ __align__(8) uint64_t acc1_full[2], acc2_full[2], acc3_full[2], h_full[2], x_free[2], l_full[2];
+  __shared__ __align__(8) uint64_t x_dead[C4_MAX_TILES], c_full[C4_MAX_TILES], cb_full;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler (role dispatch below)
   const int act = ACT >= 0 ? ACT : p.act;
+  if (p.trace && tid == 0) p.trace[256 + 4 * blockIdx.x] = tc::global_timer_ns();  // per-CTA wall-clock stamps: start, x ready, end
 
   if (warp == C4_PROD_WARP) tc::tmem_alloc(&tmem_base_s, 512);
   if (tid == 0) {
     for (int s = 0; s < C4_SLOTS; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     tc::mbar_init(&x_raw[0], 1); tc::mbar_init(&x_raw[1], 1);
     tc::mbar_init(&x_ready[0], C4_NEW); tc::mbar_init(&x_ready[1], C4_NPW);
+    tc::mbar_init(&cb_full, 1);
     tc::mbar_init(&x_dead[0], 1); tc::mbar_init(&x_dead[1], 1); tc::mbar_init(&c_full[0], 1); tc::mbar_init(&c_full[1], 1);
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&acc1_full[i], 1); tc::mbar_init(&acc2_full[i], 1); tc::mbar_init(&acc3_full[i], 1);
       tc::mbar_init(&h_full[i], C4_NEW); tc::mbar_init(&x_free[i], C4_NEW);
     }
-    tc::mbar_init(&l_full, C4_NEW);
+    tc::mbar_init(&l_full[0], C4_NEW); tc::mbar_init(&l_full[1], C4_NEW);
     tc::fence_barrier_init();
   }
   constexpr float BSC = ACT == SMX_ACT_SWISH ? 0.5f : 1.0f;  // (c4_bias_act32)
@@ -214,8 +244,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
     sPar[256 + i] = i < 2 * p.n2s_h ? BSC * p.b_s2[i] : 0.0f;
     sPar[512 + i] = i < 2 * p.n1f_h ? BSC * p.b_f1[i] : 0.0f;
     sPar[768 + i] = i < 2 * p.n2f_h ? BSC * p.b_f2[i] : 0.0f;
-    sPar[1024 + i] = (p.lnl_w && i < 2 * p.n2f_h) ? p.lnl_w[i] : 1.0f;
-    sPar[1280 + i] = (p.lnl_b && i < 2 * p.n2f_h) ? p.lnl_b[i] : 0.0f;
+    sPar[1024 + i] = i < p.Dout ? BSC * p.gw[i] : 0.0f;
     if (i < p.D) {  // norm1 parameters, padded layout (tc::ln_pad_index)
       sPar[1792 + tc::ln_pad_index(i, p.D)] = p.pre_w ? p.pre_w[i] : 1.0f;
       sPar[2064 + tc::ln_pad_index(i, p.D)] = p.pre_b ? p.pre_b[i] : 0.0f;
@@ -292,7 +321,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
     //   x_free: E2' / E3 read acc2 / acc3).
     int s = 0;
     uint32_t pf = 0;
-    uint32_t pb = 0x3u;  // parity bits: 0,1 x_free[c] (first wait passes on the fresh barrier) | 2,3 h_full[c] | 4 l_full
+    uint32_t pb = 0x3u;  // parity bits: 0,1 x_free[c] (first wait passes on the fresh barrier) | 2,3 h_full[c] | 4,5 l_full[c]
     const uint32_t sx0 = tc::smem_u32(smem), r0 = tc::smem_u32(sRing);
     int ev = 0;
     auto issue_half = [&](const C4Half& H, int kind, uint32_t d_base, uint32_t xaddr, int a_half_w) {
@@ -365,7 +394,8 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
           commit_to(&acc2_full[c]);
         }
         if (ph == 1) {                 // combiner halves: A = L (Y regions), D = X_n
-          wait_bit(&l_full, 4);
+          wait_bit(&l_full[0], 4);     // (D = X_0 holds chain 0's drained accumulator; K-blocks of L's first half are there)
+          if (!p.c0_in_x) wait_bit(&l_full[1], 5);
           tc::tc_fence_after();
 #pragma unroll 1
           for (int n = 0; n < 2; ++n) {
@@ -376,21 +406,28 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
               C4_TRACE(1, 40 + t);
               const C4Half& H = p.hg[8];
               const uint32_t idesc = tc::make_idesc_bf16(128, 64u * H.gw);
-              if (tc::elect_one()) {
-                uint32_t b_addr = xaddr;
-                for (int u = 0; u < H.n_units; ++u) {
-                  const uint32_t un = H.unit[u];
-                  const uint32_t d_addr = tmem + (un & 0xffu);
-                  const uint32_t kba = (un >> 8) & 7u, first = (un >> 11) & 1u;
-                  const uint64_t bd = tc::make_desc_sw128(b_addr);
-                  const uint32_t col = kba * 64u, hc = col >= (uint32_t)p.n2f_h ? 1u : 0u;
-                  const uint32_t at = tmem + hc * 192u + 128u + ((col - hc * (uint32_t)p.n2f_h) >> 1);
+              // K-blocks in L's first half go out right away (the epilogue warps are still busy with the second half of E2);
+              // the rest once that half has been stored
+              int n_first = 0;  // units whose A K-block lies in L's first half (they come first: units are ordered by K-block)
+              for (int u = 0; u < H.n_units; ++u) n_first += (((H.unit[u] >> 8) & 7u) * 64u < (uint32_t)p.n2f_h) ? 1 : 0;
+#pragma unroll 1
+              for (int part = 0; part < 2; ++part) {
+                if (part == 1) { wait_bit(&l_full[1], 5); tc::tc_fence_after(); }
+                const int u0 = part ? n_first : 0, u1 = part ? (int)H.n_units : n_first;
+                if (tc::elect_one()) {
+                  for (int u = u0; u < u1; ++u) {
+                    const uint32_t un = H.unit[u];
+                    const uint32_t kba = (un >> 8) & 7u, first = (un >> 11) & 1u;
+                    const uint32_t col = kba * 64u, hc = col >= (uint32_t)p.n2f_h ? 1u : 0u;
+                    const uint32_t d_addr = tmem + (un & 0xffu);
+                    const uint64_t bd = tc::make_desc_sw128(xaddr + (uint32_t)u * (uint32_t)H.gw * C4_BLOCK);
+                    const uint32_t at = tmem + hc * 192u + 128u + ((col - hc * (uint32_t)p.n2f_h) >> 1);
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) c4_umma_ts(d_addr, at + 8u * ks, bd + 2u * ks, idesc, (first && ks == 0) ? 0u : 1u);
-                  b_addr += (uint32_t)H.gw * C4_BLOCK;
+                    for (int ks = 0; ks < 4; ++ks) c4_umma_ts(d_addr, at + 8u * ks, bd + 2u * ks, idesc, (first && ks == 0) ? 0u : 1u);
+                  }
                 }
+                __syncwarp();
               }
-              __syncwarp();
             } else {
               issue_half(p.hg[8 + n], 1, tmem + (uint32_t)n * 192u, 0, p.n2f_h);
             }
@@ -412,20 +449,24 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&x_ready[1]);
     }
-    // utterances b = blockIdx.x, blockIdx.x + gridDim.x, ...: wait for all tiles' column sums, then mean -> LN_s -> c[b]
+    // Finalisation of utterance b: mean over valid frames -> LN_s -> c[b] = W_c[:, D_l:] mu + b_c (+ the local LayerNorm's beta
+    // share).  The Dout outputs of an utterance are split over `parts` owner CTAs (CTA index = part * B + b), so that the
+    // weight rows each warp walks are few enough to be in flight at once: the whole job is a handful of L2 round trips and
+    // is done long before the combiner epilogue of the utterance's tiles asks for it.  flag[b] counts finished parts.
     float* sMu = sFin;            // [256]
     float* sPart = sFin + 256;    // [4][256]
     float* sR = sFin + 1280;      // [16]
     const int Ds = p.Ds, Dout = p.Dout;
+    const int parts = p.fin_parts, per_part = Dout / parts;     // outputs per owner CTA: 256, 128 or 64 (a multiple of 8)
 #pragma unroll 1
-    for (int b = blockIdx.x; b < p.B; b += gridDim.x) {
-      if (ftid == 0) c4_spin_until_ge(p.cnt + b, p.tpu);
-      tc::named_bar_sync(6, 128);
-      // number of valid frames (an integer-valued float, like torch.sum(mask) in the reference, summary_mixing.py:229-231)
+    for (int job = blockIdx.x; job < p.B * parts; job += gridDim.x) {
+      const int b = job % p.B, part = job / p.B;
+      // number of valid frames (an integer-valued float, like torch.sum(mask) in the reference, summary_mixing.py:229-231):
+      // independent of the other CTAs, so before the wait
       float cntf = (float)p.T;
       if (p.mask) {
         float cc = 0.0f;
-#pragma unroll 2
+#pragma unroll 8
         for (int t = ftid; t < p.T; t += 128) cc += (float)p.mask[(size_t)b * p.T + t];
 #pragma unroll
         for (int o = 16; o; o >>= 1) cc += __shfl_xor_sync(0xffffffffu, cc, o);
@@ -433,14 +474,19 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
         tc::named_bar_sync(6, 128);
         cntf = (sR[0] + sR[1]) + (sR[2] + sR[3]);
       }
+      if (ftid == 0) c4_spin_until_ge(p.cnt + b * C4_SYNC_STRIDE, p.tpu);
+      tc::named_bar_sync(6, 128);
       float loc[2] = {0.0f, 0.0f};
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
         const int d = ftid + 128 * j;
         if (d < Ds) {
           float sacc = 0.0f;
-#pragma unroll 4
-          for (int i = 0; i < p.tpu; ++i) sacc += __ldcg(p.colsum + ((size_t)b * p.tpu + i) * Ds + d);  // fixed order: deterministic
+#pragma unroll 8
+          for (int i = 0; i < p.tpu; ++i) {  // tiles in order, row quadrants in order: deterministic
+            const float* cs = p.colsum + ((size_t)b * p.tpu + i) * 4 * Ds + d;
+            sacc += (__ldcg(cs) + __ldcg(cs + Ds)) + (__ldcg(cs + 2 * Ds) + __ldcg(cs + 3 * Ds));
+          }
           loc[j] = sacc / cntf;
         }
       }
@@ -467,34 +513,44 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       for (int j = 0; j < 2; ++j)
         if (ftid + 128 * j < Ds) sMu[ftid + 128 * j] = loc[j];
       tc::named_bar_sync(6, 128);
-      // c[b] = W_cs mu + b_c: warp pw takes the k quarter [pw Ds/4, (pw+1) Ds/4), lane l the outputs [8l, 8l+8): one 16-byte load
-      // per k covers a full row of W_cs^T for the warp (coalesced); the four partials meet in shared memory in fixed order
+      // this part's outputs [part per_part, +per_part): warp pw takes the k quarter [pw Ds/4, ...); a 16-byte load covers 8 outputs,
+      // so per_part / 8 lanes cover one row of W_cs^T and a warp instruction walks 32 / (per_part / 8) rows at once
       {
         float acc[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) acc[e] = 0.0f;
+        const int lanes_per_row = per_part >> 3, rows_per_it = 32 / lanes_per_row;
         const int kq = Ds >> 2, k0 = pw * kq;
-        if (lane * 8 < Dout) {
-          const __nv_bfloat16* wp = p.wcsT + (size_t)k0 * Dout + lane * 8;
+        const int lr = lane / lanes_per_row, lc = lane - lr * lanes_per_row;
+        const __nv_bfloat16* wp = p.wcsT + (size_t)(k0 + lr) * Dout + part * per_part + lc * 8;
 #pragma unroll 8
-          for (int k = 0; k < kq; ++k) {
-            const uint4 raw = __ldg(reinterpret_cast<const uint4*>(wp + (size_t)k * Dout));
-            const float m = sMu[k0 + k];
-            const float2 f0 = c4_bf2(raw.x), f1 = c4_bf2(raw.y), f2 = c4_bf2(raw.z), f3 = c4_bf2(raw.w);
-            acc[0] = fmaf(f0.x, m, acc[0]); acc[1] = fmaf(f0.y, m, acc[1]); acc[2] = fmaf(f1.x, m, acc[2]); acc[3] = fmaf(f1.y, m, acc[3]);
-            acc[4] = fmaf(f2.x, m, acc[4]); acc[5] = fmaf(f2.y, m, acc[5]); acc[6] = fmaf(f3.x, m, acc[6]); acc[7] = fmaf(f3.y, m, acc[7]);
-          }
+        for (int k = 0; k < kq; k += rows_per_it) {
+          const uint4 raw = __ldg(reinterpret_cast<const uint4*>(wp + (size_t)k * Dout));
+          const float m = sMu[k0 + k + lr];
+          const float2 f0 = c4_bf2(raw.x), f1 = c4_bf2(raw.y), f2 = c4_bf2(raw.z), f3 = c4_bf2(raw.w);
+          acc[0] = fmaf(f0.x, m, acc[0]); acc[1] = fmaf(f0.y, m, acc[1]); acc[2] = fmaf(f1.x, m, acc[2]); acc[3] = fmaf(f1.y, m, acc[3]);
+          acc[4] = fmaf(f2.x, m, acc[4]); acc[5] = fmaf(f2.y, m, acc[5]); acc[6] = fmaf(f3.x, m, acc[6]); acc[7] = fmaf(f3.y, m, acc[7]);
+        }
+        // lanes with the same lc hold partial sums over different rows: add them in a fixed (butterfly) order
+        for (int o = lanes_per_row; o < 32; o <<= 1) {
 #pragma unroll
-          for (int e = 0; e < 8; ++e) sPart[pw * 256 + lane * 8 + e] = acc[e];
+          for (int e = 0; e < 8; ++e) acc[e] += __shfl_xor_sync(0xffffffffu, acc[e], o);
+        }
+        if (lr == 0) {
+#pragma unroll
+          for (int e = 0; e < 8; ++e) sPart[pw * 256 + lc * 8 + e] = acc[e];
         }
       }
       tc::named_bar_sync(6, 128);
       for (int j = 0; j < 2; ++j) {
         const int n = ftid + 128 * j;
-        if (n < Dout) p.rowbias[(size_t)b * Dout + n] = ((sPart[n] + sPart[256 + n]) + (sPart[512 + n] + sPart[768 + n])) + p.bc[n];
+        if (n < per_part) {
+          const int go = part * per_part + n;
+          p.rowbias[(size_t)b * Dout + go] = ((sPart[n] + sPart[256 + n]) + (sPart[512 + n] + sPart[768 + n])) + (p.bc[go] + p.bw[go]);
+        }
       }
       tc::named_bar_sync(6, 128);  // every thread's share of c[b] is written (and sMu / sPart may be reused)
-      if (ftid == 0) c4_st_release(p.flag + b, 1);  // release at GPU scope, cumulative over the barrier-ordered writes
+      if (ftid == 0) c4_red_release_add(p.flag + b * C4_SYNC_STRIDE, 1);  // release at GPU scope, cumulative over the barrier-ordered writes
     }
   } else {
     // =============================== epilogue ===============================
@@ -502,7 +558,6 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
     const int r = q * 32 + lane;             // row inside the tile
     const int etid = tid;                    // 0..511
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    float* const sRB = sPar + 1536;
     uint32_t pe = 0;  // parity bits: 0,1 acc1_full[c] | 2,3 acc2_full[c] | 4,5 acc3_full[c]
     auto wait_bit = [&](uint64_t* bar, int bit) {
       tc::mbar_wait(bar, (pe >> bit) & 1u);
@@ -534,6 +589,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       const int t0 = (tile % p.tpu) * 128;
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
       tc::mbar_wait(&x_raw[0], 0);
+      if (p.trace && tid == 0) p.trace[256 + 4 * blockIdx.x + 1] = tc::global_timer_ns();
       if (p.pre_w) c4_ln_rows(smem, nrows, p.D, warp, 1, lane, sPar + 1792, sPar + 2064, sStat);
       tc::fence_proxy_async();
       __syncwarp();
@@ -567,24 +623,19 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
             for (int j = 0; j < 32; ++j) v[j] = 0.0f;
           }
           const float tot = c4_column_sums(v, lane);
-          sRed[q * 256 + col + lane] = tot;
+          p.colsum[((size_t)tile * 4 + q) * p.Ds + col + lane] = tot;  // this row quadrant's partial; the finalisation adds the four in fixed order
         }
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&x_free[c]);
         if (warp == 0) C4_TRACE(3, ev++);
       }
-      tc::named_bar_sync(5, C4_NEW * 32);
-      if (etid < p.Ds) {  // fixed-order reduction over the four row quadrants: deterministic
-        p.colsum[(size_t)tile * p.Ds + etid] = (sRed[etid] + sRed[256 + etid]) + (sRed[512 + etid] + sRed[768 + etid]);
-      }
-      tc::named_bar_sync(5, C4_NEW * 32);  // the tile's sums are written (CTA barrier); sRed may be rewritten
-      if (etid == 0) c4_red_release_add(p.cnt + b, 1);  // release at GPU scope, cumulative over the writes ordered before it by the barrier
+      tc::named_bar_sync(5, C4_NEW * 32);  // every warp's partial sums of this tile are written (CTA barrier)
+      if (etid == 0) c4_red_release_add(p.cnt + b * C4_SYNC_STRIDE, 1);  // release at GPU scope, cumulative over the writes ordered before it by the barrier
       if (warp == 0) C4_TRACE(3, ev++);
     }
     // =============================== phase 2: local branch + combiner ===============================
     tc::pdl_wait();  // the residual is read straight from global memory from here on
-    const bool use_ln = p.lnl_w != nullptr;
     const int np2 = p.n2f_h >> 5;  // 32-column pieces per half of the local branch output
 #pragma unroll 1
     for (int t = 0; t < ntl; ++t) {
@@ -598,93 +649,44 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) e1(c, sPar + 512, p.n1f_h);
       if (warp == 0) C4_TRACE(3, ev++);
-      // E2a: v = act(acc2 + b2) * mask; with LayerNorm: per-thread (mean, M2) of its 32 values, v parked as fp32 in place;
-      // without: L = v straight to Y_c                                                             summary_mixing.py:215-218
-      if (!use_ln) {  // L goes straight into Y_c: with a dense second layer GEMM 2 of the OTHER chain still reads H from it
+      // E2: v = act(acc2 + b2) * mask -> packed bf16 into Y_c: the A operand of the combiner is the UN-normalised local branch.
+      // local_norm is applied AFTER the GEMM, algebraically: LN_l(v) W^T = rstd (v (W gamma)^T - mean gw) + W beta with
+      // gw[n] = sum_k gamma_k W[n,k]: gamma is folded into the packed combiner weights, W beta into c[b], and E3 applies the two
+      // per-row scalars (mean, rstd) -- so this epilogue is one pass (no parked fp32 copy, no second read), and the combiner's
+      // first K-blocks can start as soon as half 0 is stored.  Per-thread (sum, sum of squares) of its 32 values go to shared
+      // memory for the row statistics.                                                        summary_mixing.py:215-218
+      if (p.g2f_both) {  // dense second layer: GEMM 2 of chain 1 still reads H from Y_0, where chain 0's L is about to go
         wait_bit(&acc2_full[0], 2);
         wait_bit(&acc2_full[1], 3);
       }
 #pragma unroll 1
       for (int c = 0; c < 2; ++c) {
-        if (use_ln) wait_bit(&acc2_full[c], 2 + c);
+        if (!p.g2f_both) wait_bit(&acc2_full[c], 2 + c);
         if (k4 < np2) {
           float v[32];
-          const uint32_t xa = tmem + lane_sel + (uint32_t)c * 192u + k4 * 32;
-          tc::tmem_ld32(xa, v);
+          tc::tmem_ld32(tmem + lane_sel + (uint32_t)c * 192u + k4 * 32, v);
           tc::tmem_ld_wait();
           c4_bias_act32<ACT>(v, sPar + 768 + c * p.n2f_h + k4 * 32, act);
           if (rscale == 0.0f) {  // (the mask is 0 or 1: a rare branch instead of 32 multiplies)
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.0f;
           }
-          if (use_ln) {
-            // one pass: sum and sum of squares of the 32 values in four independent chains each (fixed association:
-            // deterministic); (mean, M2) of the piece from them -- activations are O(1) with |mean| <~ std, no cancellation issue
+          if (p.use_lnl) {  // four independent chains each (fixed association: deterministic)
             float sa[4] = {0.0f, 0.0f, 0.0f, 0.0f}, qa[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
             for (int j = 0; j < 32; ++j) { sa[j & 3] += v[j]; qa[j & 3] = fmaf(v[j], v[j], qa[j & 3]); }
-            tc::tmem_st32(xa, v);
-            const float s1 = (sa[0] + sa[1]) + (sa[2] + sa[3]), s2 = (qa[0] + qa[1]) + (qa[2] + qa[3]);
-            const float mh = s1 * (1.0f / 32.0f);
-            reinterpret_cast<float2*>(sRed)[(c * 4 + k4) * 128 + r] = make_float2(mh, fmaxf(fmaf(-s1, mh, s2), 0.0f));
-          } else {
-            uint32_t lp[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) lp[i] = tc::pack_bf16x2(v[2 * i], v[2 * i + 1]);
-            c4_st16(tmem + lane_sel + (uint32_t)c * 192u + 128u + k4 * 16, lp);
+            reinterpret_cast<float2*>(sRed)[(c * 4 + k4) * 128 + r] = make_float2((sa[0] + sa[1]) + (sa[2] + sa[3]), (qa[0] + qa[1]) + (qa[2] + qa[3]));
           }
-        }
-      }
-      tc::tmem_st_wait();
-      if (warp == 0) C4_TRACE(3, ev++);
-      if (use_ln) {
-        // E2b: Chan's merge of the row's 2 np2 partials (32 values each) in fixed order, then L = LN_l(v) -> Y_c
-        tc::named_bar_sync(1 + q, 128);
-        // the row's 2 np2 partials (mean_i, M2_i of 32 values each), in fixed order: mean = avg(mean_i),
-        // M2 = sum M2_i + 32 sum (mean_i - mean)^2  (no divisions: every partial has the same count)
-        const float2* pp = reinterpret_cast<const float2*>(sRed) + r;
-        const float inv_np = np2 == 4 ? 0.125f : 0.25f;
-        float msum = 0.0f, m2 = 0.0f;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c)
-#pragma unroll 1
-          for (int i = 0; i < np2; ++i) { const float2 pr = pp[(c * 4 + i) * 128]; msum += pr.x; m2 += pr.y; }
-        const float mean = msum * inv_np;
-        float dev2 = 0.0f;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c)
-#pragma unroll 1
-          for (int i = 0; i < np2; ++i) { const float d = pp[(c * 4 + i) * 128].x - mean; dev2 = fmaf(d, d, dev2); }
-        const float rstd = rsqrtf(fmaf(32.0f, dev2, m2) * (inv_np * (1.0f / 32.0f)) + 1e-5f), shift = -mean * rstd;
-        if (warp == 0) C4_TRACE(3, ev++);
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
-          if (k4 < np2) {
-            float v[32];
-            tc::tmem_ld32(tmem + lane_sel + (uint32_t)c * 192u + k4 * 32, v);
-            tc::tmem_ld_wait();
-            const int col = c * p.n2f_h + k4 * 32;
-            const float4* wp = reinterpret_cast<const float4*>(sPar + 1024 + col);
-            const float4* bp = reinterpret_cast<const float4*>(sPar + 1280 + col);
+          uint32_t lp[16];
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 ww = wp[j], bb = bp[j];
-              v[4 * j] = fmaf(fmaf(v[4 * j], rstd, shift), ww.x, bb.x);
-              v[4 * j + 1] = fmaf(fmaf(v[4 * j + 1], rstd, shift), ww.y, bb.y);
-              v[4 * j + 2] = fmaf(fmaf(v[4 * j + 2], rstd, shift), ww.z, bb.z);
-              v[4 * j + 3] = fmaf(fmaf(v[4 * j + 3], rstd, shift), ww.w, bb.w);
-            }
-            uint32_t lp[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) lp[i] = tc::pack_bf16x2(v[2 * i], v[2 * i + 1]);
-            c4_st16(tmem + lane_sel + (uint32_t)c * 192u + 128u + k4 * 16, lp);
-          }
+          for (int i = 0; i < 16; ++i) lp[i] = tc::pack_bf16x2(v[2 * i], v[2 * i + 1]);
+          c4_st16(tmem + lane_sel + (uint32_t)c * 192u + 128u + k4 * 16, lp);
+          tc::tmem_st_wait();
         }
-        tc::tmem_st_wait();
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&l_full[c]);
       }
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&l_full);
       if (warp == 0) C4_TRACE(3, ev++);
       // E3: y = act(acc3 + c[b]) (+ residual); this thread: row r, output columns [n dout_h + 32 k4, + 32)   summary_mixing.py:251-253, Conformer.py:541
       // The residual of half 0 is requested now, before the wait for c[b] and the combiner; the one of half 1 as soon as half
@@ -704,11 +706,38 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
         }
       };
       if (has_res) load_res(0);
-      // c[b] of this tile's utterance (finalised by its owner CTA's prologue warps long ago, normally)
-      if (etid == 0) c4_spin_until_ge(p.flag + b, 1);
-      tc::named_bar_sync(5, C4_NEW * 32);  // flag seen (acquire by thread 0, CTA barrier: visible to all); every warp is past E3 of the previous tile
-      if (etid < p.Dout) sRB[etid] = BSC * __ldcg(p.rowbias + (size_t)b * p.Dout + etid);
-      tc::named_bar_sync(5, C4_NEW * 32);
+      // c[b] of this tile's utterance (finalised by its owner CTA's prologue warps long ago, normally): every warp fetches the 64
+      // values of its own output columns into its private slice -- no CTA-wide barrier between E2 and E3
+      // ONE poller per CTA (warp 0, lane 0; more pollers hot-spot the flag's L2 line against the other CTAs' atomics): warp 0
+      // stages c[b] for everybody and signals an mbarrier; the other warps sleep on it -- no CTA-wide barrier between E2 and E3
+      float* const sCb = sRBw + (t & 1) * 256;
+      if (warp == 0) {
+        if (lane == 0) c4_spin_until_ge(p.flag + b * C4_SYNC_STRIDE, p.fin_parts);
+        __syncwarp();  // (acquire by lane 0, then warp barrier: the other lanes' loads below are ordered after it; they bypass L1)
+        for (int i = lane; i < (p.Dout >> 2); i += 32) {
+          const float4 cv = __ldcg(reinterpret_cast<const float4*>(p.rowbias + (size_t)b * p.Dout) + i);
+          reinterpret_cast<float4*>(sCb)[i] = make_float4(BSC * cv.x, BSC * cv.y, BSC * cv.z, BSC * cv.w);
+        }
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&cb_full);
+      }
+      tc::mbar_wait(&cb_full, t & 1);
+      // row statistics of the un-normalised local branch (fixed order over the row's 2 np2 partials): mean, 1/std
+      float rs = BSC, nm = 0.0f;
+      if (p.use_lnl) {
+        tc::named_bar_sync(1 + q, 128);  // the quadrant's four warps have published their partials of this tile
+        const float2* pp = reinterpret_cast<const float2*>(sRed) + r;
+        float s1 = 0.0f, s2 = 0.0f;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c)
+#pragma unroll 1
+          for (int i = 0; i < np2; ++i) { const float2 pr = pp[(c * 4 + i) * 128]; s1 += pr.x; s2 += pr.y; }
+        const float inv_n = np2 == 4 ? (1.0f / 256.0f) : (1.0f / 128.0f);
+        const float mean = s1 * inv_n;
+        const float rstd = rsqrtf(fmaxf(fmaf(-mean, mean, s2 * inv_n), 0.0f) + 1e-5f);
+        rs = BSC * rstd; nm = -mean * rstd;
+      }
+      __syncwarp();
       if (warp == 0) C4_TRACE(3, ev++);
 #pragma unroll 1
       for (int n = 0; n < 2; ++n) {
@@ -718,7 +747,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
           float v[32];
           tc::tmem_ld32(tmem + lane_sel + (uint32_t)n * 192u + k4 * 32, v);
           tc::tmem_ld_wait();
-          c4_bias_act32<ACT>(v, sRB + col, act);
+          c4_affine_act32<ACT>(v, rs, nm, sPar + 1024 + col, sCb + col, act);
           if (has_res) {
 #pragma unroll
             for (int i = 0; i < 16; ++i) { const float2 f = c4_bf2(rres[i]); v[2 * i] += f.x; v[2 * i + 1] += f.y; }
@@ -741,6 +770,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
   }
   tc::tc_fence_before();
   __syncthreads();
+  if (p.trace && tid == 0) p.trace[256 + 4 * blockIdx.x + 2] = tc::global_timer_ns();
   if (warp == C4_PROD_WARP) tc::tmem_dealloc(tmem, 512);
 }
 
@@ -752,7 +782,7 @@ void tc_set_trace_cell4(void* p) { g_trace_c4 = (unsigned long long*)p; }
 static thread_local int* g_presync = nullptr;  // pre-zeroed counters handed down by the encoder / layer entry points
 static thread_local size_t g_presync_left = 0;
 void tc_cell4_set_presync(void* p, size_t bytes) { g_presync = (int*)p; g_presync_left = bytes; }
-size_t tc_cell4_sync_bytes(int B) { return align_up((size_t)B * 2 * sizeof(int)); }
+size_t tc_cell4_sync_bytes(int B) { return align_up((size_t)B * 2 * C4_SYNC_STRIDE * sizeof(int)); }
 
 static bool c4_dim_ok(int d) { return d == 128 || d == 256; }
 
@@ -818,16 +848,30 @@ static bool c4_schedule(const smx_cell_weights* w, C4Sched& s) {
   return c4_make_halves(w->local_out_dim, w->merge.out_dim, 1, s.hg + 8, s.blocks + 8, s.nblocks + 8, s.both + 4);
 }
 
-// image layout: [stream-order weight blocks (phase 1 | phase 2)] [W_cs^T bf16]
+// image layout: [stream-order weight blocks (phase 1 | phase 2)] [W_cs^T bf16] [gw f32] [bw f32]
+//               [pack-time scratch: W_c[:, :D_l] * gamma in fp32 | its chunk-major bf16 image]
 static size_t c4_img_bytes(const C4Sched& s) {
   size_t n = 0;
   for (int h = 0; h < 10; ++h) n += (size_t)s.nblocks[h] * C4_BLOCK;
   return n;
 }
+struct C4Image { size_t wcs, gw, bw, wg, wg_img, total; };
+static C4Image c4_image(const smx_cell_weights* w, const C4Sched& s) {
+  C4Image im{};
+  const size_t Dl = w->local_out_dim, Ds = w->summary_out_dim, Do = w->merge.out_dim;
+  size_t off = align_up(c4_img_bytes(s));
+  im.wcs = off; off += align_up(Ds * Do * 2);
+  im.gw = off; off += align_up(Do * 4);
+  im.bw = off; off += align_up(Do * 4);
+  im.wg = off; off += align_up(Do * Dl * 4);
+  im.wg_img = off; off += align_up(Do * Dl * 2, 1024);
+  im.total = off;
+  return im;
+}
 size_t tc_cell4_packed_bytes(const smx_cell_weights* w) {
   C4Sched s;
   if (!tc_cell4_supported(w) || !c4_schedule(w, s)) return 0;
-  return align_up(c4_img_bytes(s)) + align_up((size_t)w->summary_out_dim * w->merge.out_dim * 2);
+  return c4_image(w, s).total;
 }
 
 struct C4Gather { uint16_t src[C4_MAXU * 2]; int n; };
@@ -843,11 +887,46 @@ __global__ void cell4_wcs_kernel(const float* __restrict__ Wc, int Dl, int Ds, i
   const int k = i / Dout, n = i % Dout;
   out[i] = __float2bfloat16(Wc[(size_t)n * (Dl + Ds) + Dl + k]);
 }
+// local_norm folded into the combiner (see E2 / E3 of the kernel): Wg[n][k] = W_c[n][k] gamma[k] (fp32; the combiner's packed
+// weights are its bf16 image), gw[n] = sum_k bf16(Wg[n][k]) -- from the ROUNDED weights, so that subtracting mean * gw cancels the
+// mean's share of the GEMM exactly -- and bw[n] = sum_k beta[k] W_c[n][k].  One warp per output n.
+__global__ void __launch_bounds__(256) cell4_fold_ln_kernel(const float* __restrict__ Wc, int Dl, int ldw, int Dout, const float* __restrict__ gamma,
+                                                            const float* __restrict__ beta, float* __restrict__ Wg, float* __restrict__ gw,
+                                                            float* __restrict__ bw) {
+  const int n = blockIdx.x * 8 + (threadIdx.x >> 5), lane = threadIdx.x & 31;
+  if (n >= Dout) return;
+  float sg = 0.0f, sb = 0.0f;
+  for (int k = lane; k < Dl; k += 32) {
+    const float wv = Wc[(size_t)n * ldw + k];
+    const float g = gamma ? wv * gamma[k] : wv;
+    Wg[(size_t)n * Dl + k] = g;
+    sg += __bfloat162float(__float2bfloat16(g));
+    sb = fmaf(beta ? beta[k] : 0.0f, wv, sb);
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) { sg += __shfl_xor_sync(0xffffffffu, sg, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
+  if (lane == 0) { gw[n] = gamma ? sg : 0.0f; bw[n] = sb; }
+}
 // chunk-major images of the five GEMMs (tc_pack_linear_nt, NT = 64) -> the v4 image
 int tc_cell4_pack(const smx_cell_weights* w, const void* img_s1, const void* img_s2, const void* img_f1, const void* img_f2,
                   const void* img_c, void* out, cudaStream_t st) {
   C4Sched s;
   if (!tc_cell4_supported(w) || !c4_schedule(w, s)) return fail(SMX_ERR_UNSUPPORTED, "cell v4: configuration not handled");
+  const C4Image im = c4_image(w, s);
+  const bool ln = w->use_layernorm != 0;
+  {  // the combiner's local part with local_norm folded in (without LayerNorm: the plain weights, gw = bw = 0)
+    const int Dl = w->local_out_dim, Dout = w->merge.out_dim;
+    float* Wg = (float*)((char*)out + im.wg);
+    cell4_fold_ln_kernel<<<(Dout + 7) / 8, 256, 0, st>>>(w->merge.w, Dl, w->merge.in_dim, Dout, ln ? w->local_norm_w : nullptr,
+                                                       ln ? w->local_norm_b : nullptr, Wg, (float*)((char*)out + im.gw),
+                                                       (float*)((char*)out + im.bw));
+    count_launch();
+    SMX_TRY(check_launch("cell4_fold_ln_kernel"));
+    smx_linear Lg{};
+    Lg.w = Wg; Lg.b = nullptr; Lg.in_dim = Dl; Lg.out_dim = Dout; Lg.n_split = 1;
+    SMX_TRY(tc_pack_linear_nt(Lg, 0, Dl, 64, (char*)out + im.wg_img, st));
+    img_c = (const char*)out + im.wg_img;
+  }
   const void* srcs[5] = {img_s1, img_s2, img_f1, img_f2, img_c};
   char* dst = (char*)out;
   for (int h = 0; h < 10; ++h) {
@@ -859,7 +938,7 @@ int tc_cell4_pack(const smx_cell_weights* w, const void* img_s1, const void* img
     SMX_TRY(check_launch("cell4_gather_kernel"));
     dst += (size_t)g.n * C4_BLOCK;
   }
-  __nv_bfloat16* wcs = (__nv_bfloat16*)((char*)out + align_up(c4_img_bytes(s)));
+  __nv_bfloat16* wcs = (__nv_bfloat16*)((char*)out + im.wcs);
   const int n = w->summary_out_dim * w->merge.out_dim;
   cell4_wcs_kernel<<<(n + 255) / 256, 256, 0, st>>>(w->merge.w, w->local_out_dim, w->summary_out_dim, w->merge.out_dim, wcs);
   count_launch();
@@ -881,7 +960,7 @@ bool tc_cell4_fits(int B, int T) { return (int64_t)B * ((T + 127) / 128) <= (int
 
 size_t tc_cell4_workspace_bytes(const smx_cell_weights* w, int B, int T) {
   const int tpu = (T + 127) / 128;
-  return align_up((size_t)B * tpu * w->summary_out_dim * 4) + align_up((size_t)B * w->merge.out_dim * 4) + tc_cell4_sync_bytes(B);
+  return align_up((size_t)B * tpu * 4 * w->summary_out_dim * 4) + align_up((size_t)B * w->merge.out_dim * 4) + tc_cell4_sync_bytes(B);
 }
 
 typedef CUresult (*c4_encode_fn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -919,9 +998,10 @@ int tc_cell4_fwd(const smx_cell_weights* w, const void* img, int B, int T, const
   const int tpu = (T + 127) / 128;
   const int Ds = w->summary_out_dim, Dl = w->local_out_dim, Dout = w->merge.out_dim, D = w->enc_dim;
   const size_t m0 = ws.mark();
-  float* colsum = ws.f32((size_t)B * tpu * Ds);
+  float* colsum = ws.f32((size_t)B * tpu * 4 * Ds);
   float* rowbias = ws.f32((size_t)B * Dout);
   if (!colsum || !rowbias) return fail(SMX_ERR_WORKSPACE, "workspace too small (cell v4)");
+  const C4Image im = c4_image(w, s);
   int* sync = nullptr;
   const size_t sb = tc_cell4_sync_bytes(B);
   if (g_presync && g_presync_left >= sb) {  // zeroed once per encoder / layer call, ahead of the kernel chain
@@ -960,22 +1040,29 @@ int tc_cell4_fwd(const smx_cell_weights* w, const void* img, int B, int T, const
   p.c0_bytes = (uint32_t)s.nblocks[8] * C4_BLOCK;
   p.c0_in_x = p.c0_bytes <= (uint32_t)(D / 64) * kblock_bytes(128) ? 1 : 0;
   p.b_s1 = w->summary[0].b; p.b_s2 = w->summary[1].b; p.b_f1 = w->local[0].b; p.b_f2 = w->local[1].b;
-  p.lnl_w = w->use_layernorm ? w->local_norm_w : nullptr;
-  p.lnl_b = w->use_layernorm ? w->local_norm_b : nullptr;
+  p.use_lnl = w->use_layernorm ? 1 : 0;
+  p.gw = (const float*)((const char*)img + im.gw);
+  p.bw = (const float*)((const char*)img + im.bw);
   p.act = w->act; p.Ds = Ds; p.Dl = Dl; p.Dout = Dout;
   p.lns_w = w->use_layernorm ? w->summary_norm_w : nullptr;
   p.lns_b = w->use_layernorm ? w->summary_norm_b : nullptr;
-  p.wcsT = (const __nv_bfloat16*)((const char*)img + align_up(c4_img_bytes(s)));
+  p.wcsT = (const __nv_bfloat16*)((const char*)img + im.wcs);
   p.bc = w->merge.b;
-  p.colsum = colsum; p.rowbias = rowbias; p.cnt = sync; p.flag = sync + B;
+  p.colsum = colsum; p.rowbias = rowbias; p.cnt = sync; p.flag = sync + (size_t)B * C4_SYNC_STRIDE;
+  {
+    const int grid_n = p.n_tiles < c4_sms() ? p.n_tiles : c4_sms();
+    p.fin_parts = (grid_n >= 4 * B && Dout % 32 == 0) ? 4 : ((grid_n >= 2 * B && Dout % 16 == 0) ? 2 : 1);
+  }
   const uint32_t xb = (uint32_t)(D / 64) * kblock_bytes(128);
   p.off_ring = C4_MAX_TILES * xb;
   p.off_par = p.off_ring + C4_SLOTS * C4_SLOT;
   p.off_red = p.off_par + 9728;   // 2336 floats of parameters, rounded up
   p.off_stat = p.off_red + 8192;
   p.off_fin = p.off_stat + 2048;
-  const size_t smem = (size_t)p.off_fin + 5248 + 1024;
+  p.off_rbw = p.off_fin + 5248;
+  const size_t smem = (size_t)p.off_rbw + 4096 + 1024;
   p.trace = g_trace_c4.load();
+  if (p.trace) { const char* e = getenv("SMX_TRACE_CTA"); p.trace_cta = e ? atoi(e) : 0; }
   const unsigned grid = (unsigned)(p.n_tiles < c4_sms() ? p.n_tiles : c4_sms());
   int rc;
   switch (p.act) {

@@ -21,7 +21,7 @@ xs = [torch.randn(B, T, D, device=dev).to(torch.bfloat16) for _ in range(8)]  # 
 lens = torch.randint(500, T + 1, (B,))
 lens[0] = T
 mask = (torch.arange(T)[None] < lens[:, None]).to(dev)
-buf = torch.zeros(1024, dtype=torch.int64, device=dev)
+buf = torch.zeros(2048, dtype=torch.int64, device=dev)
 for ver in (4, 3):
     L.lib().smx_debug_set_cell_version(ver)
     with torch.no_grad():
@@ -42,10 +42,19 @@ with torch.no_grad():
     torch.cuda.synchronize()
     L.lib().smx_debug_set_trace(None)
 t = buf.cpu()
+cta = t[256:256 + 4 * 148].view(148, 4)
+st, xr, en = cta[:, 0], cta[:, 1], cta[:, 2]
+ok = st > 0
+if int(ok.sum()):
+    s0 = int(st[ok].min())
+    print(f"per-CTA wall clock (ns since the first CTA started): start max {int(st[ok].max()) - s0}, x tile landed median {int((xr[ok] - s0).median())} "
+          f"max {int(xr[ok].max()) - s0}, end min {int(en[ok].min()) - s0} median {int((en[ok] - s0).median())} max {int(en[ok].max()) - s0}; "
+          f"CTA 0: x {int(xr[0]) - s0} end {int(en[0]) - s0}; two-tile CTAs end median {int((en[:102] - s0).median())}, one-tile {int((en[102:148] - s0).median())}")
 iss, epi = t[64:128], t[192:256]
 nz = t[t > 0]
 if nz.numel():
     t0 = int(nz.min())
+    print("traced CTA:", os.environ.get("SMX_TRACE_CTA", "0"), " clock64 at first event", t0)
     print("producer (c0 wait x_dead / issue):", " ".join(f"{int(v) - t0:6d}" for v in t[0:4]))
     print("issuer after c_full:", " ".join(f"{int(v) - t0:6d}" for v in t[64 + 40:64 + 42]))
     print("issuer  :", " ".join(f"{int(v) - t0:6d}" for v in iss[:40] if int(v)))
