@@ -77,6 +77,8 @@ struct C4P {
   uint32_t off_ring, off_par, off_red, off_stat, off_fin, off_rbw;
   unsigned long long* trace;                  // debug timeline of CTA trace_cta (NULL: off)
   int trace_cta;
+  int trace_slot;                             // per-CTA wall-clock stamps of consecutive calls rotate over four slots of 640 entries
+  int dbg_noweights;                          // timing experiment only (SMX_DBG_C4_NOWEIGHTS=1, wrong results): weight steps after the first ring fill are not copied
 };
 
 #define C4_TRACE(role, ev)                                                                       \
@@ -222,20 +224,41 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
   const int tid = threadIdx.x, lane = tid & 31;
   const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);  // warp-uniform for the compiler (role dispatch below)
   const int act = ACT >= 0 ? ACT : p.act;
-  if (p.trace && tid == 0) p.trace[256 + 4 * blockIdx.x] = tc::global_timer_ns();  // per-CTA wall-clock stamps: start, x ready, end
+  if (p.trace && tid == 0) p.trace[256 + 640 * p.trace_slot + 4 * blockIdx.x] = tc::global_timer_ns();  // per-CTA wall-clock stamps: start, x ready, end
+  if (p.trace && tid == 0 && blockIdx.x == p.trace_cta) { p.trace[60] = clock64(); p.trace[62] = tc::global_timer_ns(); }  // the traced CTA: cycles and wall clock side by side
 
-  if (warp == C4_PROD_WARP) tc::tmem_alloc(&tmem_base_s, 512);
+  // this CTA's tiles: blockIdx.x and blockIdx.x + gridDim.x (the host guarantees n_tiles <= 2 gridDim.x)
+  const int ntl = (int)blockIdx.x + (int)gridDim.x < p.n_tiles ? 2 : 1;
+  if (warp == C4_PROD_WARP) {
+    tc::tmem_alloc(&tmem_base_s, 512);
+    // The x tiles are the first thing on the critical path (HBM latency + the whole grid's 16 MB burst): their TMA loads go out
+    // before anything else of the set-up, on barriers this thread initialises itself.  Programmatic dependent launch: x (and the
+    // residual, the same tensor) come from the preceding kernel, so this is also where that kernel's completion is awaited.
+    if (lane == 0) {
+      tc::mbar_init(&x_raw[0], 1); tc::mbar_init(&x_raw[1], 1);
+      tc::fence_barrier_init();
+      tc::fence_proxy_async();
+      tc::pdl_wait();
+      for (int t = 0; t < ntl; ++t) {
+        const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+        const int b = tile / p.tpu, t0 = (tile % p.tpu) * 128;
+        tc::mbar_arrive_expect_tx(&x_raw[t], xtile_bytes);
+        for (int kb = 0; kb < (p.D >> 6); ++kb)   // box = 64 columns x 128 frames x 1 utterance; frames >= T are zero-filled
+          c4_tma_load_3d(smem + (size_t)t * xtile_bytes + (size_t)kb * kblock_bytes(128), &tmap_x, kb * 64, t0, b, &x_raw[t]);
+      }
+    }
+    __syncwarp();
+  }
   if (tid == 0) {
     for (int s = 0; s < C4_SLOTS; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    tc::mbar_init(&x_raw[0], 1); tc::mbar_init(&x_raw[1], 1);
     tc::mbar_init(&x_ready[0], C4_NEW); tc::mbar_init(&x_ready[1], C4_NPW);
     tc::mbar_init(&cb_full, 1);
     tc::mbar_init(&x_dead[0], 1); tc::mbar_init(&x_dead[1], 1); tc::mbar_init(&c_full[0], 1); tc::mbar_init(&c_full[1], 1);
     for (int i = 0; i < 2; ++i) {
       tc::mbar_init(&acc1_full[i], 1); tc::mbar_init(&acc2_full[i], 1); tc::mbar_init(&acc3_full[i], 1);
-      tc::mbar_init(&h_full[i], C4_NEW); tc::mbar_init(&x_free[i], C4_NEW);
+      tc::mbar_init(&h_full[i], C4_NEW / 2); tc::mbar_init(&x_free[i], C4_NEW / 2);
     }
-    tc::mbar_init(&l_full[0], C4_NEW); tc::mbar_init(&l_full[1], C4_NEW);
+    tc::mbar_init(&l_full[0], C4_NEW / 2); tc::mbar_init(&l_full[1], C4_NEW / 2);
     tc::fence_barrier_init();
   }
   constexpr float BSC = ACT == SMX_ACT_SWISH ? 0.5f : 1.0f;  // (c4_bias_act32)
@@ -253,25 +276,13 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
   tc::tc_fence_before();
   __syncthreads();
   tc::tc_fence_after();
-  // Programmatic dependent launch: x (and the residual, the same tensor) come from the preceding kernel.  Each role waits for
-  // it where it first touches them: the producer after it has put the first weight steps in flight, the epilogue warps
-  // before phase 2 (they see x only through the producer's TMA loads before that).
   tc::pdl_launch_dependents();
   const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
-  // this CTA's tiles: blockIdx.x and blockIdx.x + gridDim.x (the host guarantees n_tiles <= 2 gridDim.x)
-  const int ntl = (int)blockIdx.x + (int)gridDim.x < p.n_tiles ? 2 : 1;
 
   if (warp == C4_PROD_WARP) {
-    // =============================== TMA producer: x tiles, then the weight ring ===============================
+    // =============================== TMA producer: the weight ring (the x tiles are already in flight) ===============================
     if (lane == 0) {
-      auto load_x = [&](int t) {
-        const int tile = (int)blockIdx.x + t * (int)gridDim.x;
-        const int b = tile / p.tpu, t0 = (tile % p.tpu) * 128;
-        tc::mbar_arrive_expect_tx(&x_raw[t], xtile_bytes);
-        for (int kb = 0; kb < (p.D >> 6); ++kb)   // box = 64 columns x 128 frames x 1 utterance; frames >= T are zero-filled
-          c4_tma_load_3d(smem + (size_t)t * xtile_bytes + (size_t)kb * kblock_bytes(128), &tmap_x, kb * 64, t0, b, &x_raw[t]);
-      };
-      int s = 0, issued = 0;
+      int s = 0;
       uint32_t pe = 0;
 #pragma unroll 1
       for (int ph = 0; ph < 2; ++ph) {
@@ -288,6 +299,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
               C4_TRACE(0, 2 * t);
               tc::mbar_wait(&x_dead[t], 0);
               C4_TRACE(0, 2 * t + 1);
+              if (p.dbg_noweights & 1) { tc::mbar_arrive(&c_full[t]); src += p.c0_bytes; continue; }
               tc::mbar_arrive_expect_tx(&c_full[t], p.c0_bytes);
               for (uint32_t o = 0; o < p.c0_bytes; o += C4_SLOT)
                 tc::bulk_g2s(smem + (size_t)t * xtile_bytes + o, src + o, p.c0_bytes - o < C4_SLOT ? p.c0_bytes - o : C4_SLOT, &c_full[t]);
@@ -299,14 +311,13 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
               const uint32_t bytes = (uint32_t)(nu * gw) * C4_BLOCK;
               tc::mbar_wait(&empty_bar[s], ((pe >> s) & 1u) ^ 1u);
               pe ^= 1u << s;
-              tc::mbar_arrive_expect_tx(&full_bar[s], bytes);
-              tc::bulk_g2s(sRing + (size_t)s * C4_SLOT, src, bytes, &full_bar[s]);
+              if ((p.dbg_noweights & 1) && (ph | t | (h - h0)) != 0) tc::mbar_arrive(&full_bar[s]);
+              else {
+                tc::mbar_arrive_expect_tx(&full_bar[s], bytes);
+                tc::bulk_g2s(sRing + (size_t)s * C4_SLOT, src, bytes, &full_bar[s]);
+              }
               src += bytes;
               if (++s == C4_SLOTS) s = 0;
-              // x tiles: the first after the first weight steps (weights do not depend on the preceding kernel), the second
-              // once the ring is full -- the order in which the consumers need them
-              if (++issued == 2) { tc::pdl_wait(); load_x(0); }
-              if (issued == C4_SLOTS && ntl > 1) load_x(1);
             }
           }
         }
@@ -474,7 +485,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
         tc::named_bar_sync(6, 128);
         cntf = (sR[0] + sR[1]) + (sR[2] + sR[3]);
       }
-      if (ftid == 0) c4_spin_until_ge(p.cnt + b * C4_SYNC_STRIDE, p.tpu);
+      if (ftid == 0) c4_spin_until_ge(p.cnt + b * C4_SYNC_STRIDE, 2 * p.tpu);  // each tile's two epilogue groups report separately
       tc::named_bar_sync(6, 128);
       float loc[2] = {0.0f, 0.0f};
 #pragma unroll
@@ -554,33 +565,43 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
     }
   } else {
     // =============================== epilogue ===============================
-    const int q = warp & 3, k4 = warp >> 2;  // TMEM lane quadrant; 32-column piece inside a half
+    // Two groups of eight warps, one per chain (column half): group c runs E1 / E2 / E3 of chain c only, so the two groups drift
+    // apart by about one stage and the fixed latencies of one group's stage (barrier wake-up, tcgen05.ld / st round trips) lie under
+    // the other group's math.  (All sixteen warps on the same half, as in the first build, ran every half-epilogue at 2.3 k cycles
+    // against the MUFU's 1.0 k: tools/micro/mufubench.cu, profiles/r02_notes.md.)  A warp owns 64 columns of its chain: two
+    // 32-column pieces.
+    const int grp = warp >> 3;               // chain / output half of this warp
+    const int q = warp & 3, k2 = (warp >> 2) & 1;  // TMEM lane quadrant; which 64 columns of the half
     const int r = q * 32 + lane;             // row inside the tile
-    const int etid = tid;                    // 0..511
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
-    uint32_t pe = 0;  // parity bits: 0,1 acc1_full[c] | 2,3 acc2_full[c] | 4,5 acc3_full[c]
-    auto wait_bit = [&](uint64_t* bar, int bit) {
-      tc::mbar_wait(bar, (pe >> bit) & 1u);
-      pe ^= 1u << bit;
+    const uint32_t xc = tmem + lane_sel + (uint32_t)grp * 192u;  // this chain's accumulator; its operand region is at + 128
+    const bool tr = (warp & 7) == 0;         // the traced warp of each group (role 3: group 0, role 2: group 1)
+    int it = 0;                              // (phase, tile) counter: acc1_full / acc2_full complete once per step
+    auto wait_acc = [&](uint64_t* bar, uint32_t parity) {
+      tc::mbar_wait(bar, parity);
       tc::tc_fence_after();
     };
     // E1: H = act(acc1 + b1) -> packed bf16 into Y_c                                             VanillaNN.py:168-196
-    auto e1 = [&](int c, const float* sB1, int n1h) {
-      wait_bit(&acc1_full[c], c);
-      if (k4 * 32 < n1h) {
-        float v[32];
-        tc::tmem_ld32(tmem + lane_sel + (uint32_t)c * 192u + k4 * 32, v);
-        tc::tmem_ld_wait();
-        c4_bias_act32<ACT>(v, sB1 + c * n1h + k4 * 32, act);
-        uint32_t hp[16];
+    auto e1 = [&](const float* sB1, int n1h) {
+      wait_acc(&acc1_full[grp], it & 1);
+#pragma unroll 1
+      for (int i = 0; i < 2; ++i) {
+        const int kk = k2 * 2 + i;
+        if (kk * 32 < n1h) {
+          float v[32];
+          tc::tmem_ld32(xc + kk * 32, v);
+          tc::tmem_ld_wait();
+          c4_bias_act32<ACT>(v, sB1 + grp * n1h + kk * 32, act);
+          uint32_t hp[16];
 #pragma unroll
-        for (int i = 0; i < 16; ++i) hp[i] = tc::pack_bf16x2(v[2 * i], v[2 * i + 1]);
-        c4_st16(tmem + lane_sel + (uint32_t)c * 192u + 128u + k4 * 16, hp);
-        tc::tmem_st_wait();
+          for (int j = 0; j < 16; ++j) hp[j] = tc::pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          c4_st16(xc + 128u + kk * 16, hp);
+        }
       }
+      tc::tmem_st_wait();
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&h_full[c]);
+      if (lane == 0) tc::mbar_arrive(&h_full[grp]);
     };
 
     // ---- the CTA's first tile: the 16 epilogue warps normalise it in place (8 rows each) ----
@@ -589,7 +610,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       const int t0 = (tile % p.tpu) * 128;
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
       tc::mbar_wait(&x_raw[0], 0);
-      if (p.trace && tid == 0) p.trace[256 + 4 * blockIdx.x + 1] = tc::global_timer_ns();
+      if (p.trace && tid == 0) p.trace[256 + 640 * p.trace_slot + 4 * blockIdx.x + 1] = tc::global_timer_ns();
       if (p.pre_w) c4_ln_rows(smem, nrows, p.D, warp, 1, lane, sPar + 1792, sPar + 2064, sStat);
       tc::fence_proxy_async();
       __syncwarp();
@@ -598,25 +619,25 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
     int ev = 0;
     // =============================== phase 1: summary branch ===============================
 #pragma unroll 1
-    for (int t = 0; t < ntl; ++t) {
+    for (int t = 0; t < ntl; ++t, ++it) {
       const int tile = (int)blockIdx.x + t * (int)gridDim.x;
       const int b = tile / p.tpu, t0 = (tile % p.tpu) * 128;
       const int64_t row0 = (int64_t)b * p.T + t0;
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
       const float rscale = r < nrows ? (p.mask ? (float)p.mask[row0 + r] : 1.0f) : 0.0f;
-      if (warp == 0) C4_TRACE(3, ev++);
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) e1(c, sPar, p.n1s_h);
-      if (warp == 0) C4_TRACE(3, ev++);
+      if (tr) C4_TRACE(3 - grp, ev++);
+      e1(sPar, p.n1s_h);
+      if (tr) C4_TRACE(3 - grp, ev++);
       // E2': S = act(acc2 + b2) * mask -> column sums of this tile                                summary_mixing.py:221, 229-231
+      wait_acc(&acc2_full[grp], it & 1);
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        wait_bit(&acc2_full[c], 2 + c);
-        if (k4 * 32 < p.n2s_h) {
+      for (int i = 0; i < 2; ++i) {
+        const int kk = k2 * 2 + i;
+        if (kk * 32 < p.n2s_h) {
           float v[32];
-          tc::tmem_ld32(tmem + lane_sel + (uint32_t)c * 192u + k4 * 32, v);
+          tc::tmem_ld32(xc + kk * 32, v);
           tc::tmem_ld_wait();
-          const int col = c * p.n2s_h + k4 * 32;
+          const int col = grp * p.n2s_h + kk * 32;
           c4_bias_act32<ACT>(v, sPar + 256 + col, act);
           if (rscale == 0.0f) {  // padded frame / row past the tile (the mask is 0 or 1: H.mask_u8): rare, so a branch, not 32 multiplies
 #pragma unroll
@@ -625,48 +646,45 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
           const float tot = c4_column_sums(v, lane);
           p.colsum[((size_t)tile * 4 + q) * p.Ds + col + lane] = tot;  // this row quadrant's partial; the finalisation adds the four in fixed order
         }
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&x_free[c]);
-        if (warp == 0) C4_TRACE(3, ev++);
       }
-      tc::named_bar_sync(5, C4_NEW * 32);  // every warp's partial sums of this tile are written (CTA barrier)
-      if (etid == 0) c4_red_release_add(p.cnt + b * C4_SYNC_STRIDE, 1);  // release at GPU scope, cumulative over the writes ordered before it by the barrier
-      if (warp == 0) C4_TRACE(3, ev++);
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&x_free[grp]);
+      if (tr) C4_TRACE(3 - grp, ev++);
+      tc::named_bar_sync(7 + grp, 256);  // the group's partial sums of this tile are written
+      if ((tid & 255) == 0) c4_red_release_add(p.cnt + b * C4_SYNC_STRIDE, 1);  // release at GPU scope, cumulative over the writes ordered before it by the barrier; two per tile
+      if (tr) C4_TRACE(3 - grp, ev++);
     }
     // =============================== phase 2: local branch + combiner ===============================
     tc::pdl_wait();  // the residual is read straight from global memory from here on
     const int np2 = p.n2f_h >> 5;  // 32-column pieces per half of the local branch output
 #pragma unroll 1
-    for (int t = 0; t < ntl; ++t) {
+    for (int t = 0; t < ntl; ++t, ++it) {
       const int tile = (int)blockIdx.x + t * (int)gridDim.x;
       const int b = tile / p.tpu, t0 = (tile % p.tpu) * 128;
       const int64_t row0 = (int64_t)b * p.T + t0;
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
       const bool live = r < nrows;
       const float rscale = live ? (p.mask ? (float)p.mask[row0 + r] : 1.0f) : 0.0f;
-      if (warp == 0) C4_TRACE(3, ev++);
-#pragma unroll 1
-      for (int c = 0; c < 2; ++c) e1(c, sPar + 512, p.n1f_h);
-      if (warp == 0) C4_TRACE(3, ev++);
+      if (tr) C4_TRACE(3 - grp, ev++);
+      e1(sPar + 512, p.n1f_h);
+      if (tr) C4_TRACE(3 - grp, ev++);
       // E2: v = act(acc2 + b2) * mask -> packed bf16 into Y_c: the A operand of the combiner is the UN-normalised local branch.
       // local_norm is applied AFTER the GEMM, algebraically: LN_l(v) W^T = rstd (v (W gamma)^T - mean gw) + W beta with
       // gw[n] = sum_k gamma_k W[n,k]: gamma is folded into the packed combiner weights, W beta into c[b], and E3 applies the two
       // per-row scalars (mean, rstd) -- so this epilogue is one pass (no parked fp32 copy, no second read), and the combiner's
       // first K-blocks can start as soon as half 0 is stored.  Per-thread (sum, sum of squares) of its 32 values go to shared
       // memory for the row statistics.                                                        summary_mixing.py:215-218
-      if (p.g2f_both) {  // dense second layer: GEMM 2 of chain 1 still reads H from Y_0, where chain 0's L is about to go
-        wait_bit(&acc2_full[0], 2);
-        wait_bit(&acc2_full[1], 3);
-      }
+      if (p.g2f_both) wait_acc(&acc2_full[grp ^ 1], it & 1);  // dense second layer: the other chain's GEMM 2 still reads H from this Y_c, where L is about to go
+      wait_acc(&acc2_full[grp], it & 1);
 #pragma unroll 1
-      for (int c = 0; c < 2; ++c) {
-        if (!p.g2f_both) wait_bit(&acc2_full[c], 2 + c);
-        if (k4 < np2) {
+      for (int i = 0; i < 2; ++i) {
+        const int kk = k2 * 2 + i;
+        if (kk < np2) {
           float v[32];
-          tc::tmem_ld32(tmem + lane_sel + (uint32_t)c * 192u + k4 * 32, v);
+          tc::tmem_ld32(xc + kk * 32, v);
           tc::tmem_ld_wait();
-          c4_bias_act32<ACT>(v, sPar + 768 + c * p.n2f_h + k4 * 32, act);
+          c4_bias_act32<ACT>(v, sPar + 768 + grp * p.n2f_h + kk * 32, act);
           if (rscale == 0.0f) {  // (the mask is 0 or 1: a rare branch instead of 32 multiplies)
 #pragma unroll
             for (int j = 0; j < 32; ++j) v[j] = 0.0f;
@@ -675,27 +693,26 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
             float sa[4] = {0.0f, 0.0f, 0.0f, 0.0f}, qa[4] = {0.0f, 0.0f, 0.0f, 0.0f};
 #pragma unroll
             for (int j = 0; j < 32; ++j) { sa[j & 3] += v[j]; qa[j & 3] = fmaf(v[j], v[j], qa[j & 3]); }
-            reinterpret_cast<float2*>(sRed)[(c * 4 + k4) * 128 + r] = make_float2((sa[0] + sa[1]) + (sa[2] + sa[3]), (qa[0] + qa[1]) + (qa[2] + qa[3]));
+            reinterpret_cast<float2*>(sRed)[(grp * 4 + kk) * 128 + r] = make_float2((sa[0] + sa[1]) + (sa[2] + sa[3]), (qa[0] + qa[1]) + (qa[2] + qa[3]));
           }
           uint32_t lp[16];
 #pragma unroll
-          for (int i = 0; i < 16; ++i) lp[i] = tc::pack_bf16x2(v[2 * i], v[2 * i + 1]);
-          c4_st16(tmem + lane_sel + (uint32_t)c * 192u + 128u + k4 * 16, lp);
-          tc::tmem_st_wait();
+          for (int j = 0; j < 16; ++j) lp[j] = tc::pack_bf16x2(v[2 * j], v[2 * j + 1]);
+          c4_st16(xc + 128u + kk * 16, lp);
         }
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&l_full[c]);
       }
-      if (warp == 0) C4_TRACE(3, ev++);
-      // E3: y = act(acc3 + c[b]) (+ residual); this thread: row r, output columns [n dout_h + 32 k4, + 32)   summary_mixing.py:251-253, Conformer.py:541
-      // The residual of half 0 is requested now, before the wait for c[b] and the combiner; the one of half 1 as soon as half
-      // 0's has been consumed (same registers), so neither load latency sits in front of the epilogue math.
-      const bool active = k4 * 32 < p.dout_h;
-      const bool has_res = active && p.resid != nullptr;
+      tc::tmem_st_wait();
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&l_full[grp]);
+      if (tr) C4_TRACE(3 - grp, ev++);
+      // E3: y = act(acc3 + c[b]) (+ residual); this thread: row r, output columns [grp dout_h + 32 kk, + 32)   summary_mixing.py:251-253, Conformer.py:541
+      // The residual of the first piece is requested now, before the wait for c[b] and the combiner; the one of the second piece as
+      // soon as the first has been consumed (same registers), so neither load latency sits in front of the epilogue math.
+      const bool has_res = p.resid != nullptr && !(p.dbg_noweights & 2);
       uint32_t rres[16];
-      auto load_res = [&](int n) {
-        const __nv_bfloat16* src = p.resid + (row0 + r) * p.ldr + n * p.dout_h + k4 * 32;
+      auto load_res = [&](int kk) {
+        const __nv_bfloat16* src = p.resid + (row0 + r) * p.ldr + grp * p.dout_h + kk * 32;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (live) c4_ldg256(src + h * 16, rres + 8 * h);
@@ -705,9 +722,8 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
           }
         }
       };
-      if (has_res) load_res(0);
-      // c[b] of this tile's utterance (finalised by its owner CTA's prologue warps long ago, normally): every warp fetches the 64
-      // values of its own output columns into its private slice -- no CTA-wide barrier between E2 and E3
+      if (has_res && k2 * 64 < p.dout_h) load_res(k2 * 2);
+      // c[b] of this tile's utterance (finalised by its owner CTA's prologue warps long ago, normally).
       // ONE poller per CTA (warp 0, lane 0; more pollers hot-spot the flag's L2 line against the other CTAs' atomics): warp 0
       // stages c[b] for everybody and signals an mbarrier; the other warps sleep on it -- no CTA-wide barrier between E2 and E3
       float* const sCb = sRBw + (t & 1) * 256;
@@ -725,7 +741,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       // row statistics of the un-normalised local branch (fixed order over the row's 2 np2 partials): mean, 1/std
       float rs = BSC, nm = 0.0f;
       if (p.use_lnl) {
-        tc::named_bar_sync(1 + q, 128);  // the quadrant's four warps have published their partials of this tile
+        tc::named_bar_sync(1 + q, 128);  // the quadrant's four warps (two of each group) have published their partials of this tile
         const float2* pp = reinterpret_cast<const float2*>(sRed) + r;
         float s1 = 0.0f, s2 = 0.0f;
 #pragma unroll 1
@@ -738,39 +754,41 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
         rs = BSC * rstd; nm = -mean * rstd;
       }
       __syncwarp();
-      if (warp == 0) C4_TRACE(3, ev++);
+      if (tr) C4_TRACE(3 - grp, ev++);
+      wait_acc(&acc3_full[grp], t & 1);
 #pragma unroll 1
-      for (int n = 0; n < 2; ++n) {
-        const int col = n * p.dout_h + k4 * 32;
-        wait_bit(&acc3_full[n], 4 + n);
-        if (active) {
+      for (int i = 0; i < 2; ++i) {
+        const int kk = k2 * 2 + i;
+        const int col = grp * p.dout_h + kk * 32;
+        if (kk * 32 < p.dout_h) {
           float v[32];
-          tc::tmem_ld32(tmem + lane_sel + (uint32_t)n * 192u + k4 * 32, v);
+          tc::tmem_ld32(xc + kk * 32, v);
           tc::tmem_ld_wait();
           c4_affine_act32<ACT>(v, rs, nm, sPar + 1024 + col, sCb + col, act);
           if (has_res) {
 #pragma unroll
-            for (int i = 0; i < 16; ++i) { const float2 f = c4_bf2(rres[i]); v[2 * i] += f.x; v[2 * i + 1] += f.y; }
-            if (n == 0) load_res(1);
+            for (int j = 0; j < 16; ++j) { const float2 f = c4_bf2(rres[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
+            if (i == 0) load_res(kk + 1);
           }
-          if (live) {
+          if (live && (!(p.dbg_noweights & 4) || v[0] == 12345.678f)) {
             uint32_t o[16];
 #pragma unroll
-            for (int i = 0; i < 16; ++i) o[i] = tc::pack_bf16x2(v[2 * i], v[2 * i + 1]);
+            for (int j = 0; j < 16; ++j) o[j] = tc::pack_bf16x2(v[2 * j], v[2 * j + 1]);
             c4_stg256(p.y + (row0 + r) * p.ldy + col, o);
             c4_stg256(p.y + (row0 + r) * p.ldy + col + 16, o + 8);
           }
         }
-        tc::tc_fence_before();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&x_free[n]);
-        if (warp == 0) C4_TRACE(3, ev++);
       }
+      tc::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&x_free[grp]);
+      if (tr) C4_TRACE(3 - grp, ev++);
     }
   }
   tc::tc_fence_before();
   __syncthreads();
-  if (p.trace && tid == 0) p.trace[256 + 4 * blockIdx.x + 2] = tc::global_timer_ns();
+  if (p.trace && tid == 0) p.trace[256 + 640 * p.trace_slot + 4 * blockIdx.x + 2] = tc::global_timer_ns();
+  if (p.trace && tid == 0 && blockIdx.x == p.trace_cta) { p.trace[61] = clock64(); p.trace[63] = tc::global_timer_ns(); }
   if (warp == C4_PROD_WARP) tc::tmem_dealloc(tmem, 512);
 }
 
@@ -1062,7 +1080,13 @@ int tc_cell4_fwd(const smx_cell_weights* w, const void* img, int B, int T, const
   p.off_rbw = p.off_fin + 5248;
   const size_t smem = (size_t)p.off_rbw + 4096 + 1024;
   p.trace = g_trace_c4.load();
-  if (p.trace) { const char* e = getenv("SMX_TRACE_CTA"); p.trace_cta = e ? atoi(e) : 0; }
+  if (p.trace) {
+    static std::atomic<int> calls{0};
+    const char* e = getenv("SMX_TRACE_CTA");
+    p.trace_cta = e ? atoi(e) : 0;
+    p.trace_slot = calls.fetch_add(1) & 3;
+  }
+  { static const int nw = getenv("SMX_DBG_C4_NOWEIGHTS") ? atoi(getenv("SMX_DBG_C4_NOWEIGHTS")) : 0; p.dbg_noweights = nw; }
   const unsigned grid = (unsigned)(p.n_tiles < c4_sms() ? p.n_tiles : c4_sms());
   int rc;
   switch (p.act) {

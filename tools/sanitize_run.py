@@ -21,7 +21,7 @@ D, B, T = 256, 3, 300
 if len(sys.argv) > 3:
     B, T = int(sys.argv[2]), int(sys.argv[3])
 x = seeded_input(1, B, T, D)
-lens = torch.tensor(([T, T // 2 + 20, 9] + [T - 7 * i for i in range(B)])[:B])
+lens = torch.tensor(([T, T // 2 + 20, 9] + [max(1, T - 7 * i) for i in range(B)])[:B])
 mask = torch.arange(T)[None] < lens[:, None]
 if what in ("conv", "ffn"):
     if what == "conv":
