@@ -42,10 +42,14 @@ constexpr int C4_MAX_TILES = 2;  // tiles resident per CTA
 constexpr int C4_SYNC_STRIDE = 8;  // ints between two utterances' counters / flags: pollers of one do not share a sector with the atomics of another
 
 // One half (column half c) of one GEMM: its units in issue order; the weight blocks lie in the same order in the image.
+// Hand-overs are tracked per QUARTER of a row (quarter Q = 2 c + q, q = which half of the half): a unit names the quarters it has
+// to wait for (its A operand's K range and the accumulator columns it overwrites) and the accumulator quarters that are complete
+// once it has run, so that a head's GEMM 2 starts when that head's H is stored, not the whole half's (see the kernel's issuer).
 struct C4Half {
   uint8_t n_units;
   uint8_t gw;                  // 64-column blocks per unit (1 or 2): MMA N = 64 gw
-  uint16_t unit[C4_MAXU];      // bits 0-7: D column offset inside the half / 1 ... (0..255); bits 8-10: A K-block; bit 11: first
+  uint32_t unit[C4_MAXU];      // bits 0-7: D column offset inside the half (0..255); 8-10: A K-block; 11: first K-block of its columns;
+                               // 12-15: quarters to wait for; 16-19: accumulator quarters complete after this unit
 };
 
 struct C4P {
@@ -205,7 +209,7 @@ static __device__ __noinline__ void c4_ln_rows(uint8_t* sX, int nrows, int D, in
   for (int i = 0; i < n_groups; ++i) tc::rows8_ln(sX, nrows, D, w0 + i, lane, sW, sB, sStat);
 }
 
-template <int ACT>  // ACT >= 0: compile-time smx_act, -1: runtime p.act
+template <int ACT, bool STD>  // ACT >= 0: compile-time smx_act, -1: runtime p.act; STD: the standard cell's compile-time schedule
 __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_constant__ CUtensorMap tmap_x, const C4P p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t xtile_bytes = (uint32_t)(p.D >> 6) * kblock_bytes(128);
@@ -217,7 +221,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
   float* sRBw = reinterpret_cast<float*>(smem + p.off_rbw);   // [2 (tile parity)][256]: c[b] (+ the local LayerNorm's beta share) of the tile's utterance
   __shared__ __align__(8) uint64_t full_bar[C4_SLOTS], empty_bar[C4_SLOTS];
   __shared__ __align__(8) uint64_t x_raw[C4_MAX_TILES], x_ready[C4_MAX_TILES];
-  __shared__ __align__(8) uint64_t acc1_full[2], acc2_full[2], acc3_full[2], h_full[2], x_free[2], l_full[2];
+  __shared__ __align__(8) uint64_t acc1_full[4], acc2_full[4], acc3_full[4], h_full[4], x_free[4], l_full[4];  // per quarter
   __shared__ __align__(8) uint64_t x_dead[C4_MAX_TILES], c_full[C4_MAX_TILES], cb_full;
   __shared__ uint32_t tmem_base_s;
 
@@ -254,11 +258,10 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
     tc::mbar_init(&x_ready[0], C4_NEW); tc::mbar_init(&x_ready[1], C4_NPW);
     tc::mbar_init(&cb_full, 1);
     tc::mbar_init(&x_dead[0], 1); tc::mbar_init(&x_dead[1], 1); tc::mbar_init(&c_full[0], 1); tc::mbar_init(&c_full[1], 1);
-    for (int i = 0; i < 2; ++i) {
+    for (int i = 0; i < 4; ++i) {
       tc::mbar_init(&acc1_full[i], 1); tc::mbar_init(&acc2_full[i], 1); tc::mbar_init(&acc3_full[i], 1);
-      tc::mbar_init(&h_full[i], C4_NEW / 2); tc::mbar_init(&x_free[i], C4_NEW / 2);
+      tc::mbar_init(&h_full[i], C4_NEW / 2); tc::mbar_init(&x_free[i], C4_NEW / 2); tc::mbar_init(&l_full[i], C4_NEW / 2);
     }
-    tc::mbar_init(&l_full[0], C4_NEW / 2); tc::mbar_init(&l_full[1], C4_NEW / 2);
     tc::fence_barrier_init();
   }
   constexpr float BSC = ACT == SMX_ACT_SWISH ? 0.5f : 1.0f;  // (c4_bias_act32)
@@ -325,29 +328,145 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
     }
   } else if (warp == C4_MMA_WARP) {
     // =============================== MMA issuer ===============================
-    // Program per tile -- phase 1: G1(0) G1(1) G2(0) G2(1); phase 2: G1(0) G1(1) G2(0) G2(1) G3(0) G3(1).  The tensor pipe
-    // executes in issue order, which protects every TMEM hand-over that is not covered by a barrier:
-    //   G1(t+1,c) overwrites X_c / follows the combiner that read L from Y_c; G2 / G3 overwrite X_c after the epilogue that
-    //   drained it has arrived on the barrier this warp waited for (h_full: E1 read acc1; l_full: E2 read the parked values;
-    //   x_free: E2' / E3 read acc2 / acc3).
+    if constexpr (STD) {
+      // The standard cell (every GEMM 256 x 256, four heads: smx_tc_cell4_std()): the schedule is a compile-time constant, so
+      // every operand of every MMA is a loop-invariant base plus an immediate.  (The
+      // table-driven issuer below spends ~180 cycles per MMA decoding its units -- 35 k of a CTA's 55 k cycles, the critical
+      // path of the first builds: profiles/r02_notes.md.)  Same program, same hand-over rules as the generic path.
+      {
+        constexpr uint32_t ID64 = tc::make_idesc_bf16(128, 64), ID128 = tc::make_idesc_bf16(128, 128);
+        constexpr uint32_t KB16 = 16384u >> 4;  // one K-block of a 128-row operand image / one ring slot, in descriptor units
+        const uint64_t ring_d = tc::make_desc_sw128(tc::smem_u32(sRing));
+        uint32_t pf = 0;
+        int ev = 0, it = 0;
+        auto ring_wait = [&](int slot) {
+          tc::mbar_wait_spin(&full_bar[slot], (pf >> slot) & 1u);
+          pf ^= 1u << slot;
+        };
+#pragma unroll 1
+        for (int ph = 0; ph < 2; ++ph) {
+#pragma unroll 1
+          for (int t = 0; t < ntl; ++t, ++it) {
+            const uint64_t x_d = tc::make_desc_sw128(tc::smem_u32(smem) + (uint32_t)t * 65536u);
+            if (ph == 0) tc::mbar_wait(&x_ready[t], 0);
+            const uint32_t par = (uint32_t)(it & 1);
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {  // GEMM 1: head Q = 2 c + j reads K-block Q of the X tile
+              C4_TRACE(1, ev++);
+              ring_wait(c);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const int Q = 2 * c + j;
+                tc::mbar_wait_spin(&x_free[Q], par ^ 1u);  // (the very first wait on a fresh barrier passes)
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                  const uint64_t ad = x_d + (uint64_t)(Q * KB16), bd = ring_d + (uint64_t)(c * KB16 + j * (KB16 / 2));
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) tc::umma_bf16(tmem + c * 192 + j * 64, ad + 2 * ks, bd + 2 * ks, ID64, ks ? 1u : 0u);
+                  tc::umma_commit(&acc1_full[Q]);
+                  if (j == 1) tc::umma_commit(&empty_bar[c]);
+                  if (j == 1 && c == 1 && ph == 1) tc::umma_commit(&x_dead[t]);  // both chains' GEMM 1 have read the X tile: its buffer may be reused
+                }
+                __syncwarp();
+              }
+            }
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {  // GEMM 2: A = H of head Q (tensor memory), D = the head's accumulator again
+              C4_TRACE(1, ev++);
+              ring_wait(2 + c);
+#pragma unroll
+              for (int j = 0; j < 2; ++j) {
+                const int Q = 2 * c + j;
+                tc::mbar_wait_spin(&h_full[Q], par);
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                  const uint64_t bd = ring_d + (uint64_t)((2 + c) * KB16 + j * (KB16 / 2));
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) c4_umma_ts(tmem + c * 192 + j * 64, tmem + c * 192 + 128 + j * 32 + 8 * ks, bd + 2 * ks, ID64, ks ? 1u : 0u);
+                  tc::umma_commit(&acc2_full[Q]);
+                  if (j == 1) tc::umma_commit(&empty_bar[2 + c]);
+                }
+                __syncwarp();
+              }
+            }
+            if (ph == 1) {  // combiner: A = L quarter kb, D = output half n (N = 128); half 0's weights wait in the dead X buffer
+              const uint32_t lpar = (uint32_t)(t & 1);
+              C4_TRACE(1, ev++);
+              tc::mbar_wait_spin(&c_full[t], 0);
+#pragma unroll
+              for (int kb = 0; kb < 4; ++kb) {
+                if (kb == 0) { tc::mbar_wait_spin(&l_full[0], lpar); tc::mbar_wait_spin(&l_full[1], lpar); }  // A quarter 0; D = X_0, drained by E2 of quarters 0, 1
+                else if (kb >= 2) tc::mbar_wait_spin(&l_full[kb], lpar);
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                  const uint64_t bd = x_d + (uint64_t)(kb * KB16);
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) c4_umma_ts(tmem, tmem + (kb >> 1) * 192 + 128 + (kb & 1) * 32 + 8 * ks, bd + 2 * ks, ID128, (kb | ks) ? 1u : 0u);
+                  if (kb == 3) { tc::umma_commit(&acc3_full[0]); tc::umma_commit(&acc3_full[1]); }
+                }
+                __syncwarp();
+              }
+              C4_TRACE(1, ev++);
+#pragma unroll
+              for (int kb = 0; kb < 4; ++kb) {  // half 1 through the ring (one 16 KB unit per step); every L quarter has been waited for
+                ring_wait(kb);
+                tc::tc_fence_after();
+                if (tc::elect_one()) {
+                  const uint64_t bd = ring_d + (uint64_t)(kb * KB16);
+#pragma unroll
+                  for (int ks = 0; ks < 4; ++ks) c4_umma_ts(tmem + 192, tmem + (kb >> 1) * 192 + 128 + (kb & 1) * 32 + 8 * ks, bd + 2 * ks, ID128, (kb | ks) ? 1u : 0u);
+                  tc::umma_commit(&empty_bar[kb]);
+                  if (kb == 3) { tc::umma_commit(&acc3_full[2]); tc::umma_commit(&acc3_full[3]); }
+                }
+                __syncwarp();
+              }
+            }
+          }
+        }
+      }
+    } else {
+    // Program per tile -- phase 1: G1(0) G1(1) G2(0) G2(1); phase 2: G1(0) G1(1) G2(0) G2(1) G3(0) G3(1), each a list of units
+    // (C4Half).  Before a unit the warp waits for the quarters the unit names -- G1: x_free (the epilogue that drained those
+    // accumulator columns), G2: h_full (E1 has read acc1 there and stored that part of H), G3: l_full (E2 likewise, L) -- and after
+    // it commits to the accumulator barriers of the quarters it completes.  With block-diagonal layers a head's GEMM 2 therefore
+    // runs while the epilogue warps are still busy with the half's other head, and its result is waiting when they get there.
+    // The tensor pipe executes in issue order, which protects every TMEM hand-over that is not covered by a barrier.
     int s = 0;
     uint32_t pf = 0;
-    uint32_t pb = 0x3u;  // parity bits: 0,1 x_free[c] (first wait passes on the fresh barrier) | 2,3 h_full[c] | 4,5 l_full[c]
     const uint32_t sx0 = tc::smem_u32(smem), r0 = tc::smem_u32(sRing);
     int ev = 0;
-    auto issue_half = [&](const C4Half& H, int kind, uint32_t d_base, uint32_t xaddr, int a_half_w) {
-      // kind 0: A = X tile in shared memory; 1: A = H / L in tensor memory (bf16 pairs; column halves of width a_half_w)
+    long long t_ring = 0, t_hand = 0;  // (trace) cycles this warp spent waiting for weight steps / for the epilogue warps
+    // kind 0: A = X tile in shared memory; 1: A = H / L in tensor memory (bf16 pairs; column halves of width a_half_w).
+    // bx != 0: the half's weight blocks wait at this shared-memory address (behind `bx_bar`) instead of coming through the ring.
+    auto issue_half = [&](const C4Half& H, int kind, uint32_t d_base, uint32_t xaddr, int a_half_w, uint64_t* wait_arr, uint32_t wait_par,
+                          uint64_t* acc_arr, uint32_t bx, uint64_t* bx_bar) {
       const int gw = H.gw, nun = H.n_units, ups = 2 / gw;
       const uint32_t idesc = tc::make_idesc_bf16(128, 64u * gw);
+      uint32_t waited = 0;
+      long long tw0 = 0;
+      if (bx) tc::mbar_wait_spin(bx_bar, 0);
       for (int u0 = 0; u0 < nun; u0 += ups) {
         const int nu = nun - u0 < ups ? nun - u0 : ups;
-        tc::mbar_wait_spin(&full_bar[s], (pf >> s) & 1u);
-        pf ^= 1u << s;
-        tc::tc_fence_after();
-        if (tc::elect_one()) {
-          uint32_t b_addr = r0 + (uint32_t)s * C4_SLOT;
-          for (int u = 0; u < nu; ++u) {
-            const uint32_t un = H.unit[u0 + u];
+        if (!bx) {
+          if (p.trace) tw0 = clock64();
+          tc::mbar_wait_spin(&full_bar[s], (pf >> s) & 1u);
+          pf ^= 1u << s;
+          if (p.trace) t_ring += clock64() - tw0;
+        }
+        uint32_t b_addr = bx ? bx + (uint32_t)u0 * (uint32_t)gw * C4_BLOCK : r0 + (uint32_t)s * C4_SLOT;
+        for (int u = 0; u < nu; ++u) {
+          const uint32_t un = H.unit[u0 + u];
+          uint32_t need = ((un >> 12) & 0xfu) & ~waited;
+          waited |= need;
+          if (p.trace) tw0 = clock64();
+          while (need) {
+            const int Q = __ffs((int)need) - 1;
+            need &= need - 1;
+            tc::mbar_wait_spin(&wait_arr[Q], wait_par);
+          }
+          if (p.trace) t_hand += clock64() - tw0;
+          tc::tc_fence_after();
+          if (tc::elect_one()) {
             const uint32_t d_addr = d_base + (un & 0xffu);
             const uint32_t kba = (un >> 8) & 7u, first = (un >> 11) & 1u;
             const uint64_t bd = tc::make_desc_sw128(b_addr);
@@ -361,92 +480,56 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
 #pragma unroll
               for (int ks = 0; ks < 4; ++ks) c4_umma_ts(d_addr, at + 8u * ks, bd + 2u * ks, idesc, (first && ks == 0) ? 0u : 1u);
             }
-            b_addr += (uint32_t)gw * C4_BLOCK;
+            uint32_t cm = (un >> 16) & 0xfu;
+            while (cm) {
+              const int Q = __ffs((int)cm) - 1;
+              cm &= cm - 1;
+              tc::umma_commit(&acc_arr[Q]);
+            }
+            if (!bx && u == nu - 1) tc::umma_commit(&empty_bar[s]);  // one ring release per step
           }
-          tc::umma_commit(&empty_bar[s]);  // one commit per step
+          __syncwarp();
+          b_addr += (uint32_t)gw * C4_BLOCK;
         }
-        __syncwarp();
-        if (++s == C4_SLOTS) s = 0;
+        if (!bx && ++s == C4_SLOTS) s = 0;
       }
     };
     auto commit_to = [&](uint64_t* bar) {
       if (tc::elect_one()) tc::umma_commit(bar);
       __syncwarp();
     };
-    auto wait_bit = [&](uint64_t* bar, int bit) {
-      tc::mbar_wait_spin(bar, (pb >> bit) & 1u);
-      pb ^= 1u << bit;
-    };
+    int it = 0;  // (phase, tile) step: every hand-over barrier completes once per step
 #pragma unroll 1
     for (int ph = 0; ph < 2; ++ph) {
       const int hb = ph ? 4 : 0;
       const int n1h = ph ? p.n1f_h : p.n1s_h;
-      const int both = ph ? p.g2f_both : p.g2s_both;
 #pragma unroll 1
-      for (int t = 0; t < ntl; ++t) {
+      for (int t = 0; t < ntl; ++t, ++it) {
         const uint32_t xaddr = sx0 + (uint32_t)t * xtile_bytes;
         if (ph == 0) { tc::mbar_wait(&x_ready[t], 0); }
 #pragma unroll 1
-        for (int c = 0; c < 2; ++c) {  // GEMM 1 of both chains
-          wait_bit(&x_free[c], c);
-          tc::tc_fence_after();
+        for (int c = 0; c < 2; ++c) {  // GEMM 1 of both chains (the very first wait on a fresh x_free barrier passes)
           C4_TRACE(1, ev++);
-          issue_half(p.hg[hb + c], 0, tmem + (uint32_t)c * 192u, xaddr, 0);
-          commit_to(&acc1_full[c]);
+          issue_half(p.hg[hb + c], 0, tmem + (uint32_t)c * 192u, xaddr, 0, x_free, (uint32_t)(it & 1) ^ 1u, acc1_full, 0u, nullptr);
         }
         if (ph == 1 && p.c0_in_x) commit_to(&x_dead[t]);  // both chains' GEMM 1 have read the X tile: its buffer may be reused
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {  // GEMM 2 of both chains: A = H (Y regions), D = X_c again
-          if (c == 0 || !both) wait_bit(&h_full[c], 2 + c);
-          if (c == 0 && both) wait_bit(&h_full[1], 3);
-          tc::tc_fence_after();
           C4_TRACE(1, ev++);
-          issue_half(p.hg[hb + 2 + c], 1, tmem + (uint32_t)c * 192u, 0, n1h);
-          commit_to(&acc2_full[c]);
+          issue_half(p.hg[hb + 2 + c], 1, tmem + (uint32_t)c * 192u, 0, n1h, h_full, (uint32_t)(it & 1), acc2_full, 0u, nullptr);
         }
         if (ph == 1) {                 // combiner halves: A = L (Y regions), D = X_n
-          wait_bit(&l_full[0], 4);     // (D = X_0 holds chain 0's drained accumulator; K-blocks of L's first half are there)
-          if (!p.c0_in_x) wait_bit(&l_full[1], 5);
-          tc::tc_fence_after();
 #pragma unroll 1
           for (int n = 0; n < 2; ++n) {
             C4_TRACE(1, ev++);
-            if (n == 0 && p.c0_in_x) {  // weights of this half wait in the X buffer
-              tc::mbar_wait_spin(&c_full[t], 0);
-              tc::tc_fence_after();
-              C4_TRACE(1, 40 + t);
-              const C4Half& H = p.hg[8];
-              const uint32_t idesc = tc::make_idesc_bf16(128, 64u * H.gw);
-              // K-blocks in L's first half go out right away (the epilogue warps are still busy with the second half of E2);
-              // the rest once that half has been stored
-              int n_first = 0;  // units whose A K-block lies in L's first half (they come first: units are ordered by K-block)
-              for (int u = 0; u < H.n_units; ++u) n_first += (((H.unit[u] >> 8) & 7u) * 64u < (uint32_t)p.n2f_h) ? 1 : 0;
-#pragma unroll 1
-              for (int part = 0; part < 2; ++part) {
-                if (part == 1) { wait_bit(&l_full[1], 5); tc::tc_fence_after(); }
-                const int u0 = part ? n_first : 0, u1 = part ? (int)H.n_units : n_first;
-                if (tc::elect_one()) {
-                  for (int u = u0; u < u1; ++u) {
-                    const uint32_t un = H.unit[u];
-                    const uint32_t kba = (un >> 8) & 7u, first = (un >> 11) & 1u;
-                    const uint32_t col = kba * 64u, hc = col >= (uint32_t)p.n2f_h ? 1u : 0u;
-                    const uint32_t d_addr = tmem + (un & 0xffu);
-                    const uint64_t bd = tc::make_desc_sw128(xaddr + (uint32_t)u * (uint32_t)H.gw * C4_BLOCK);
-                    const uint32_t at = tmem + hc * 192u + 128u + ((col - hc * (uint32_t)p.n2f_h) >> 1);
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks) c4_umma_ts(d_addr, at + 8u * ks, bd + 2u * ks, idesc, (first && ks == 0) ? 0u : 1u);
-                  }
-                }
-                __syncwarp();
-              }
-            } else {
-              issue_half(p.hg[8 + n], 1, tmem + (uint32_t)n * 192u, 0, p.n2f_h);
-            }
-            commit_to(&acc3_full[n]);
+            const bool in_x = n == 0 && p.c0_in_x;  // the first half's weights wait in the (dead) X buffer
+            issue_half(p.hg[8 + n], 1, tmem + (uint32_t)n * 192u, 0, p.n2f_h, l_full, (uint32_t)(t & 1), acc3_full, in_x ? xaddr : 0u, &c_full[t]);
           }
         }
       }
     }
+    if (p.trace && blockIdx.x == p.trace_cta && lane == 0) { p.trace[58] = (unsigned long long)t_ring; p.trace[59] = (unsigned long long)t_hand; }
+    }  // generic issuer
   } else if (warp >= C4_PRO_WARP0) {
     // =============================== LayerNorm of the second tile, then per-utterance finalisation ===============================
     const int pw = warp - C4_PRO_WARP0, ftid = pw * 32 + lane;  // 0..127
@@ -566,42 +649,45 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
   } else {
     // =============================== epilogue ===============================
     // Two groups of eight warps, one per chain (column half): group c runs E1 / E2 / E3 of chain c only, so the two groups drift
-    // apart by about one stage and the fixed latencies of one group's stage (barrier wake-up, tcgen05.ld / st round trips) lie under
-    // the other group's math.  (All sixteen warps on the same half, as in the first build, ran every half-epilogue at 2.3 k cycles
-    // against the MUFU's 1.0 k: tools/micro/mufubench.cu, profiles/r02_notes.md.)  A warp owns 64 columns of its chain: two
-    // 32-column pieces.
+    // apart and the fixed latencies of one group's stage (barrier wake-up, tcgen05.ld / st round trips) lie under the other
+    // group's math.  Inside a group the hand-overs are per QUARTER (half of the chain's columns, one head of a four-head layer):
+    // the group works through quarter 0 then quarter 1 of every stage and signals each as it is done, so the tensor pipe
+    // computes quarter 0's next GEMM while the group is busy with quarter 1 (profiles/r02_notes.md: a GEMM hand-over costs ~1.5 k
+    // cycles end to end, about as long as a half-epilogue -- two whole-half chains left the MUFU 40 % busy).
+    // A warp owns a lane quadrant and, per quarter, 32 columns (k2: which 32 of the quarter's up to 64).
     const int grp = warp >> 3;               // chain / output half of this warp
-    const int q = warp & 3, k2 = (warp >> 2) & 1;  // TMEM lane quadrant; which 64 columns of the half
+    const int q = warp & 3, k2 = (warp >> 2) & 1;  // TMEM lane quadrant; which 32 columns of a quarter
     const int r = q * 32 + lane;             // row inside the tile
     const uint32_t lane_sel = (uint32_t)(q * 32) << 16;
     const uint32_t xc = tmem + lane_sel + (uint32_t)grp * 192u;  // this chain's accumulator; its operand region is at + 128
     const bool tr = (warp & 7) == 0;         // the traced warp of each group (role 3: group 0, role 2: group 1)
-    int it = 0;                              // (phase, tile) counter: acc1_full / acc2_full complete once per step
+    int it = 0;                              // (phase, tile) step: acc1_full / acc2_full complete once per step
     auto wait_acc = [&](uint64_t* bar, uint32_t parity) {
       tc::mbar_wait(bar, parity);
       tc::tc_fence_after();
     };
     // E1: H = act(acc1 + b1) -> packed bf16 into Y_c                                             VanillaNN.py:168-196
     auto e1 = [&](const float* sB1, int n1h) {
-      wait_acc(&acc1_full[grp], it & 1);
+      const int qw = n1h >> 1;  // quarter width
 #pragma unroll 1
-      for (int i = 0; i < 2; ++i) {
-        const int kk = k2 * 2 + i;
-        if (kk * 32 < n1h) {
+      for (int qq = 0; qq < 2; ++qq) {
+        wait_acc(&acc1_full[2 * grp + qq], it & 1);
+        const int cc = qq * qw + k2 * 32;  // column inside the half
+        if (k2 * 32 < qw) {
           float v[32];
-          tc::tmem_ld32(xc + kk * 32, v);
+          tc::tmem_ld32(xc + cc, v);
           tc::tmem_ld_wait();
-          c4_bias_act32<ACT>(v, sB1 + grp * n1h + kk * 32, act);
+          c4_bias_act32<ACT>(v, sB1 + grp * n1h + cc, act);
           uint32_t hp[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) hp[j] = tc::pack_bf16x2(v[2 * j], v[2 * j + 1]);
-          c4_st16(xc + 128u + kk * 16, hp);
+          c4_st16(xc + 128u + (cc >> 1), hp);
+          tc::tmem_st_wait();
         }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&h_full[2 * grp + qq]);
       }
-      tc::tmem_st_wait();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&h_full[grp]);
     };
 
     // ---- the CTA's first tile: the 16 epilogue warps normalise it in place (8 rows each) ----
@@ -629,27 +715,30 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       e1(sPar, p.n1s_h);
       if (tr) C4_TRACE(3 - grp, ev++);
       // E2': S = act(acc2 + b2) * mask -> column sums of this tile                                summary_mixing.py:221, 229-231
-      wait_acc(&acc2_full[grp], it & 1);
+      {
+        const int qw = p.n2s_h >> 1;
 #pragma unroll 1
-      for (int i = 0; i < 2; ++i) {
-        const int kk = k2 * 2 + i;
-        if (kk * 32 < p.n2s_h) {
-          float v[32];
-          tc::tmem_ld32(xc + kk * 32, v);
-          tc::tmem_ld_wait();
-          const int col = grp * p.n2s_h + kk * 32;
-          c4_bias_act32<ACT>(v, sPar + 256 + col, act);
-          if (rscale == 0.0f) {  // padded frame / row past the tile (the mask is 0 or 1: H.mask_u8): rare, so a branch, not 32 multiplies
+        for (int qq = 0; qq < 2; ++qq) {
+          wait_acc(&acc2_full[2 * grp + qq], it & 1);
+          const int cc = qq * qw + k2 * 32;
+          if (k2 * 32 < qw) {
+            float v[32];
+            tc::tmem_ld32(xc + cc, v);
+            tc::tmem_ld_wait();
+            const int col = grp * p.n2s_h + cc;
+            c4_bias_act32<ACT>(v, sPar + 256 + col, act);
+            if (rscale == 0.0f) {  // padded frame / row past the tile (the mask is 0 or 1: H.mask_u8): rare, so a branch, not 32 multiplies
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+              for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+            }
+            const float tot = c4_column_sums(v, lane);
+            p.colsum[((size_t)tile * 4 + q) * p.Ds + col + lane] = tot;  // this row quadrant's partial; the finalisation adds the four in fixed order
           }
-          const float tot = c4_column_sums(v, lane);
-          p.colsum[((size_t)tile * 4 + q) * p.Ds + col + lane] = tot;  // this row quadrant's partial; the finalisation adds the four in fixed order
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&x_free[2 * grp + qq]);
         }
       }
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&x_free[grp]);
       if (tr) C4_TRACE(3 - grp, ev++);
       tc::named_bar_sync(7 + grp, 256);  // the group's partial sums of this tile are written
       if ((tid & 255) == 0) c4_red_release_add(p.cnt + b * C4_SYNC_STRIDE, 1);  // release at GPU scope, cumulative over the writes ordered before it by the barrier; two per tile
@@ -673,46 +762,54 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       // local_norm is applied AFTER the GEMM, algebraically: LN_l(v) W^T = rstd (v (W gamma)^T - mean gw) + W beta with
       // gw[n] = sum_k gamma_k W[n,k]: gamma is folded into the packed combiner weights, W beta into c[b], and E3 applies the two
       // per-row scalars (mean, rstd) -- so this epilogue is one pass (no parked fp32 copy, no second read), and the combiner's
-      // first K-blocks can start as soon as half 0 is stored.  Per-thread (sum, sum of squares) of its 32 values go to shared
+      // first K-blocks can start as soon as quarter 0 is stored.  Per-thread (sum, sum of squares) of its 32 values go to shared
       // memory for the row statistics.                                                        summary_mixing.py:215-218
-      if (p.g2f_both) wait_acc(&acc2_full[grp ^ 1], it & 1);  // dense second layer: the other chain's GEMM 2 still reads H from this Y_c, where L is about to go
-      wait_acc(&acc2_full[grp], it & 1);
+      if (p.g2f_both) {  // dense second layer: every unit of GEMM 2 reads all of H, where L is about to go
 #pragma unroll 1
-      for (int i = 0; i < 2; ++i) {
-        const int kk = k2 * 2 + i;
-        if (kk < np2) {
-          float v[32];
-          tc::tmem_ld32(xc + kk * 32, v);
-          tc::tmem_ld_wait();
-          c4_bias_act32<ACT>(v, sPar + 768 + grp * p.n2f_h + kk * 32, act);
-          if (rscale == 0.0f) {  // (the mask is 0 or 1: a rare branch instead of 32 multiplies)
+        for (int Q = 0; Q < 4; ++Q) wait_acc(&acc2_full[Q], it & 1);
+      }
+      {
+        const int qw = p.n2f_h >> 1;
+#pragma unroll 1
+        for (int qq = 0; qq < 2; ++qq) {
+          wait_acc(&acc2_full[2 * grp + qq], it & 1);
+          const int cc = qq * qw + k2 * 32;
+          if (k2 * 32 < qw) {
+            float v[32];
+            tc::tmem_ld32(xc + cc, v);
+            tc::tmem_ld_wait();
+            c4_bias_act32<ACT>(v, sPar + 768 + grp * p.n2f_h + cc, act);
+            if (rscale == 0.0f) {  // (the mask is 0 or 1: a rare branch instead of 32 multiplies)
 #pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+              for (int j = 0; j < 32; ++j) v[j] = 0.0f;
+            }
+            if (p.use_lnl) {  // four independent chains each (fixed association: deterministic)
+              float sa[4] = {0.0f, 0.0f, 0.0f, 0.0f}, qa[4] = {0.0f, 0.0f, 0.0f, 0.0f};
+#pragma unroll
+              for (int j = 0; j < 32; ++j) { sa[j & 3] += v[j]; qa[j & 3] = fmaf(v[j], v[j], qa[j & 3]); }
+              reinterpret_cast<float2*>(sRed)[(grp * 4 + (cc >> 5)) * 128 + r] = make_float2((sa[0] + sa[1]) + (sa[2] + sa[3]), (qa[0] + qa[1]) + (qa[2] + qa[3]));
+            }
+            uint32_t lp[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) lp[j] = tc::pack_bf16x2(v[2 * j], v[2 * j + 1]);
+            c4_st16(xc + 128u + (cc >> 1), lp);
+            tc::tmem_st_wait();
           }
-          if (p.use_lnl) {  // four independent chains each (fixed association: deterministic)
-            float sa[4] = {0.0f, 0.0f, 0.0f, 0.0f}, qa[4] = {0.0f, 0.0f, 0.0f, 0.0f};
-#pragma unroll
-            for (int j = 0; j < 32; ++j) { sa[j & 3] += v[j]; qa[j & 3] = fmaf(v[j], v[j], qa[j & 3]); }
-            reinterpret_cast<float2*>(sRed)[(grp * 4 + kk) * 128 + r] = make_float2((sa[0] + sa[1]) + (sa[2] + sa[3]), (qa[0] + qa[1]) + (qa[2] + qa[3]));
-          }
-          uint32_t lp[16];
-#pragma unroll
-          for (int j = 0; j < 16; ++j) lp[j] = tc::pack_bf16x2(v[2 * j], v[2 * j + 1]);
-          c4_st16(xc + 128u + kk * 16, lp);
+          tc::tc_fence_before();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&l_full[2 * grp + qq]);
         }
       }
-      tc::tmem_st_wait();
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&l_full[grp]);
       if (tr) C4_TRACE(3 - grp, ev++);
-      // E3: y = act(acc3 + c[b]) (+ residual); this thread: row r, output columns [grp dout_h + 32 kk, + 32)   summary_mixing.py:251-253, Conformer.py:541
-      // The residual of the first piece is requested now, before the wait for c[b] and the combiner; the one of the second piece as
+      // E3: y = act(acc3 + c[b]) (+ residual); this thread: row r, 32 output columns of each quarter of half grp   summary_mixing.py:251-253, Conformer.py:541
+      // The residual of the first quarter is requested now, before the wait for c[b] and the combiner; the one of the second as
       // soon as the first has been consumed (same registers), so neither load latency sits in front of the epilogue math.
       const bool has_res = p.resid != nullptr && !(p.dbg_noweights & 2);
+      const int qw3 = p.dout_h >> 1;
+      const bool e3_active = k2 * 32 < qw3;
       uint32_t rres[16];
-      auto load_res = [&](int kk) {
-        const __nv_bfloat16* src = p.resid + (row0 + r) * p.ldr + grp * p.dout_h + kk * 32;
+      auto load_res = [&](int qq) {
+        const __nv_bfloat16* src = p.resid + (row0 + r) * p.ldr + grp * p.dout_h + qq * qw3 + k2 * 32;
 #pragma unroll
         for (int h = 0; h < 2; ++h) {
           if (live) c4_ldg256(src + h * 16, rres + 8 * h);
@@ -722,7 +819,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
           }
         }
       };
-      if (has_res && k2 * 64 < p.dout_h) load_res(k2 * 2);
+      if (has_res && e3_active) load_res(0);
       // c[b] of this tile's utterance (finalised by its owner CTA's prologue warps long ago, normally).
       // ONE poller per CTA (warp 0, lane 0; more pollers hot-spot the flag's L2 line against the other CTAs' atomics): warp 0
       // stages c[b] for everybody and signals an mbarrier; the other warps sleep on it -- no CTA-wide barrier between E2 and E3
@@ -755,20 +852,20 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       }
       __syncwarp();
       if (tr) C4_TRACE(3 - grp, ev++);
-      wait_acc(&acc3_full[grp], t & 1);
 #pragma unroll 1
-      for (int i = 0; i < 2; ++i) {
-        const int kk = k2 * 2 + i;
-        const int col = grp * p.dout_h + kk * 32;
-        if (kk * 32 < p.dout_h) {
+      for (int qq = 0; qq < 2; ++qq) {
+        wait_acc(&acc3_full[2 * grp + qq], t & 1);
+        const int cc = qq * qw3 + k2 * 32;
+        const int col = grp * p.dout_h + cc;
+        if (e3_active) {
           float v[32];
-          tc::tmem_ld32(xc + kk * 32, v);
+          tc::tmem_ld32(xc + cc, v);
           tc::tmem_ld_wait();
           c4_affine_act32<ACT>(v, rs, nm, sPar + 1024 + col, sCb + col, act);
           if (has_res) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) { const float2 f = c4_bf2(rres[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
-            if (i == 0) load_res(kk + 1);
+            if (qq == 0) load_res(1);
           }
           if (live && (!(p.dbg_noweights & 4) || v[0] == 12345.678f)) {
             uint32_t o[16];
@@ -778,10 +875,10 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
             c4_stg256(p.y + (row0 + r) * p.ldy + col + 16, o + 8);
           }
         }
+        tc::tc_fence_before();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&x_free[2 * grp + qq]);
       }
-      tc::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&x_free[grp]);
       if (tr) C4_TRACE(3 - grp, ev++);
     }
   }
@@ -821,7 +918,16 @@ struct C4Sched {
 // GEMM (K -> N), n_split heads.  Block-diagonal (even head count, head dims multiples of 64, a head inside one half): half c
 // walks its heads, one unit per (head, column group, K-block of the head).  Anything else: dense, half c = its N/2 columns,
 // one unit per K-block.  Returns false if a half needs more than C4_MAXU units.
-static bool c4_make_halves(int K, int N, int n_split, C4Half* out, int (*blk)[C4_MAXU * 2], int* nblk, int* both) {
+// quarters (of a `total`-wide row) overlapped by columns [col0, col0 + width)
+static unsigned c4_qmask(int col0, int width, int total) {
+  const int qw = total / 4;
+  unsigned m = 0;
+  for (int Q = 0; Q < 4; ++Q)
+    if (col0 < (Q + 1) * qw && col0 + width > Q * qw) m |= 1u << Q;
+  return m;
+}
+// a_tmem: the A operand is the previous stage's output in tensor memory (its K range has to be waited for as well)
+static bool c4_make_halves(int K, int N, int n_split, int a_tmem, C4Half* out, int (*blk)[C4_MAXU * 2], int* nblk, int* both) {
   const int nkb = K / 64, nc = N / 64, nh = N / 2;
   bool bd = false;
   int cph = 0, kph = 0;
@@ -842,7 +948,9 @@ static bool c4_make_halves(int K, int N, int n_split, C4Half* out, int (*blk)[C4
           for (int kbl = 0; kbl < kph; ++kbl) {
             if (nu >= C4_MAXU) return false;
             const int chunk0 = m * cph + jg * gw, kb = m * kph + kbl;
-            H.unit[nu++] = (uint16_t)((chunk0 * 64 - c * nh) | (kb << 8) | ((kbl == 0 ? 1 : 0) << 11));
+            const unsigned dq = c4_qmask(chunk0 * 64, 64 * gw, N), aq = a_tmem ? c4_qmask(kb * 64, 64, K) : 0u;
+            H.unit[nu++] = (uint32_t)(chunk0 * 64 - c * nh) | ((uint32_t)kb << 8) | ((kbl == 0 ? 1u : 0u) << 11) | ((dq | aq) << 12) |
+                           ((kbl == kph - 1 ? dq : 0u) << 16);
             for (int u = 0; u < gw; ++u) blk[c][nb++] = (chunk0 + u) * nkb + kb;
           }
     } else {
@@ -850,7 +958,8 @@ static bool c4_make_halves(int K, int N, int n_split, C4Half* out, int (*blk)[C4
       H.gw = (uint8_t)gw;
       for (int kb = 0; kb < nkb; ++kb) {
         if (nu >= C4_MAXU) return false;
-        H.unit[nu++] = (uint16_t)(0 | (kb << 8) | ((kb == 0 ? 1 : 0) << 11));
+        const unsigned dq = c4_qmask(c * nh, 64 * gw, N), aq = a_tmem ? c4_qmask(kb * 64, 64, K) : 0u;
+        H.unit[nu++] = ((uint32_t)kb << 8) | ((kb == 0 ? 1u : 0u) << 11) | ((dq | aq) << 12) | ((kb == nkb - 1 ? dq : 0u) << 16);
         for (int u = 0; u < gw; ++u) blk[c][nb++] = (c * gw + u) * nkb + kb;
       }
     }
@@ -862,8 +971,8 @@ static bool c4_make_halves(int K, int N, int n_split, C4Half* out, int (*blk)[C4
 static bool c4_schedule(const smx_cell_weights* w, C4Sched& s) {
   const smx_linear* L[4] = {&w->summary[0], &w->summary[1], &w->local[0], &w->local[1]};
   for (int g = 0; g < 4; ++g)
-    if (!c4_make_halves(L[g]->in_dim, L[g]->out_dim, L[g]->n_split, s.hg + 2 * g, s.blocks + 2 * g, s.nblocks + 2 * g, s.both + g)) return false;
-  return c4_make_halves(w->local_out_dim, w->merge.out_dim, 1, s.hg + 8, s.blocks + 8, s.nblocks + 8, s.both + 4);
+    if (!c4_make_halves(L[g]->in_dim, L[g]->out_dim, L[g]->n_split, g & 1, s.hg + 2 * g, s.blocks + 2 * g, s.nblocks + 2 * g, s.both + g)) return false;
+  return c4_make_halves(w->local_out_dim, w->merge.out_dim, 1, 1, s.hg + 8, s.blocks + 8, s.nblocks + 8, s.both + 4);
 }
 
 // image layout: [stream-order weight blocks (phase 1 | phase 2)] [W_cs^T bf16] [gw f32] [bw f32]
@@ -997,14 +1106,19 @@ static c4_encode_fn c4_encoder() {
   return state.load() == 1 ? fn : nullptr;
 }
 
-template <int ACT>
-static int launch_cell4_act(const CUtensorMap& tm, const C4P& p, unsigned grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(cell4_kernel<ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+template <int ACT, bool STD>
+static int launch_cell4_as(const CUtensorMap& tm, const C4P& p, unsigned grid, size_t smem, cudaStream_t st) {
+  cudaError_t e = cudaFuncSetAttribute(cell4_kernel<ACT, STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(cell4_kernel): %s", cudaGetErrorString(e));
-  e = launch_pdl(cell4_kernel<ACT>, dim3(grid), dim3(C4_THREADS), smem, st, 1u, tm, p);
+  e = launch_pdl(cell4_kernel<ACT, STD>, dim3(grid), dim3(C4_THREADS), smem, st, 1u, tm, p);
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaLaunchKernelEx(cell4_kernel): %s", cudaGetErrorString(e));
   count_tc_launch();
   return check_launch("cell4_kernel");
+}
+
+template <int ACT>
+static int launch_cell4_act(const CUtensorMap& tm, const C4P& p, unsigned grid, size_t smem, cudaStream_t st, bool std_cell) {
+  return std_cell ? launch_cell4_as<ACT, true>(tm, p, grid, smem, st) : launch_cell4_as<ACT, false>(tm, p, grid, smem, st);
 }
 
 int tc_cell4_fwd(const smx_cell_weights* w, const void* img, int B, int T, const __nv_bfloat16* x, const float* pre_ln_w,
@@ -1089,11 +1203,17 @@ int tc_cell4_fwd(const smx_cell_weights* w, const void* img, int B, int T, const
   { static const int nw = getenv("SMX_DBG_C4_NOWEIGHTS") ? atoi(getenv("SMX_DBG_C4_NOWEIGHTS")) : 0; p.dbg_noweights = nw; }
   const unsigned grid = (unsigned)(p.n_tiles < c4_sms() ? p.n_tiles : c4_sms());
   int rc;
+  // the standard cell: every GEMM 256 x 256, the four MLP layers block-diagonal over four heads of 64, combiner half in the X buffer
+  bool std_cell = D == 256 && Ds == 256 && Dl == 256 && Dout == 256 && p.c0_in_x && !getenv("SMX_C4_GENERIC");
+  for (int g = 0; g < 4; ++g) {
+    const smx_linear* Lg = g == 0 ? &w->summary[0] : g == 1 ? &w->summary[1] : g == 2 ? &w->local[0] : &w->local[1];
+    std_cell = std_cell && Lg->in_dim == 256 && Lg->out_dim == 256 && Lg->n_split == 4 && s.both[g] == 0;
+  }
   switch (p.act) {
-    case SMX_ACT_SWISH: rc = launch_cell4_act<SMX_ACT_SWISH>(tm, p, grid, smem, st); break;
-    case SMX_ACT_GELU: rc = launch_cell4_act<SMX_ACT_GELU>(tm, p, grid, smem, st); break;
-    case SMX_ACT_RELU: rc = launch_cell4_act<SMX_ACT_RELU>(tm, p, grid, smem, st); break;
-    default: rc = launch_cell4_act<-1>(tm, p, grid, smem, st); break;
+    case SMX_ACT_SWISH: rc = launch_cell4_act<SMX_ACT_SWISH>(tm, p, grid, smem, st, std_cell); break;
+    case SMX_ACT_GELU: rc = launch_cell4_act<SMX_ACT_GELU>(tm, p, grid, smem, st, std_cell); break;
+    case SMX_ACT_RELU: rc = launch_cell4_act<SMX_ACT_RELU>(tm, p, grid, smem, st, std_cell); break;
+    default: rc = launch_cell4_act<-1>(tm, p, grid, smem, st, false); break;
   }
   ws.release(m0);
   return rc;

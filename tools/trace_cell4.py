@@ -58,8 +58,9 @@ if int(ok.sum()):
           f"max {int(xr[ok].max()) - s0}, end min {int(en[ok].min()) - s0} median {int((en[ok] - s0).median())} max {int(en[ok].max()) - s0}; "
           f"CTA 0: x {int(xr[0]) - s0} end {int(en[0]) - s0}; two-tile CTAs end median {int((en[:102] - s0).median())}, one-tile {int((en[102:148] - s0).median())}")
 iss, epi = t[64:128], t[192:256]
-print(f"traced CTA, single call: {int(t[61] - t[60])} cycles in {int(t[63] - t[62])} ns = {float(t[61] - t[60]) / max(1, int(t[63] - t[62])):.3f} GHz")
-t[60:64] = 0
+print(f"traced CTA, single call: {int(t[61] - t[60])} cycles in {int(t[63] - t[62])} ns = {float(t[61] - t[60]) / max(1, int(t[63] - t[62])):.3f} GHz; "
+      f"issuer waited {int(t[58])} cycles for weight steps, {int(t[59])} for epilogue hand-overs")
+t[58:64] = 0
 nz = t[:256][t[:256] > 0]
 if nz.numel():
     t0 = int(nz.min())
@@ -107,8 +108,9 @@ if rows:
     print("chained calls (last four of twelve), ns since the first of them started: [first CTA start, median start, last start | x landed median, max | end min, median, max]")
     for r_ in rows:
         print("   ", " ".join(f"{v - z:7d}" for v in r_))
-print(f"traced CTA, last chained call: {int(t[61] - t[60])} cycles in {int(t[63] - t[62])} ns = {float(t[61] - t[60]) / max(1, int(t[63] - t[62])):.3f} GHz")
-t[60:64] = 0
+print(f"traced CTA, last chained call: {int(t[61] - t[60])} cycles in {int(t[63] - t[62])} ns = {float(t[61] - t[60]) / max(1, int(t[63] - t[62])):.3f} GHz; "
+      f"issuer waited {int(t[58])} cycles for weight steps, {int(t[59])} for epilogue hand-overs")
+t[58:64] = 0
 nz = t[:256][t[:256] > 0]
 if nz.numel():
     t0 = int(nz.min())
