@@ -63,8 +63,7 @@ struct C4P {
   C4Half hg[10];
   int n1s_h, n2s_h, n1f_h, n2f_h, dout_h;     // half widths of the five GEMM outputs
   int g2s_both, g2f_both;                     // GEMM 2 of a chain needs BOTH halves of H (dense second layer)
-  int c0_in_x;                                // the combiner's first half is prefetched into the (dead) X tile instead of the ring
-  uint32_t c0_bytes;
+  int res_in_x;                               // the residual tile is re-loaded (TMA) into the X buffer once GEMM 1 of the local branch has read it
   const float* b_s1; const float* b_s2; const float* b_f1; const float* b_f2;
   int use_lnl;                                // local_norm is applied (folded: gamma into the combiner weights, beta into c[b], see E2 / E3)
   const float* gw;                            // [Dout] gw[n] = sum_k bf16(gamma_k W_c[n,k]) (zeros without LayerNorm)
@@ -98,6 +97,13 @@ __device__ __forceinline__ void c4_tma_load_3d(void* smem_dst, const CUtensorMap
       "l"(tmap), "r"(c0), "r"(c1), "r"(c2), "r"(tc::smem_u32(bar))
       : "memory");
 }
+__device__ __forceinline__ void c4_tma_store_3d(const CUtensorMap* tmap, const void* smem_src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.tile.bulk_group [%0, {%1, %2, %3}], [%4];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(c2),
+               "r"(tc::smem_u32(smem_src))
+               : "memory");
+}
+__device__ __forceinline__ void c4_bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void c4_bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
 __device__ __forceinline__ void c4_umma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -210,7 +216,8 @@ static __device__ __noinline__ void c4_ln_rows(uint8_t* sX, int nrows, int D, in
 }
 
 template <int ACT, bool STD>  // ACT >= 0: compile-time smx_act, -1: runtime p.act; STD: the standard cell's compile-time schedule
-__global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_constant__ CUtensorMap tmap_x, const C4P p) {
+__global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_r,
+                                                              const __grid_constant__ CUtensorMap tmap_y, const C4P p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   const uint32_t xtile_bytes = (uint32_t)(p.D >> 6) * kblock_bytes(128);
   uint8_t* sRing = smem + p.off_ring;
@@ -222,7 +229,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
   __shared__ __align__(8) uint64_t full_bar[C4_SLOTS], empty_bar[C4_SLOTS];
   __shared__ __align__(8) uint64_t x_raw[C4_MAX_TILES], x_ready[C4_MAX_TILES];
   __shared__ __align__(8) uint64_t acc1_full[4], acc2_full[4], acc3_full[4], h_full[4], x_free[4], l_full[4];  // per quarter
-  __shared__ __align__(8) uint64_t x_dead[C4_MAX_TILES], c_full[C4_MAX_TILES], cb_full;
+  __shared__ __align__(8) uint64_t x_dead[C4_MAX_TILES], r_full[C4_MAX_TILES], cb_full;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -257,7 +264,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
     for (int s = 0; s < C4_SLOTS; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     tc::mbar_init(&x_ready[0], C4_NEW); tc::mbar_init(&x_ready[1], C4_NPW);
     tc::mbar_init(&cb_full, 1);
-    tc::mbar_init(&x_dead[0], 1); tc::mbar_init(&x_dead[1], 1); tc::mbar_init(&c_full[0], 1); tc::mbar_init(&c_full[1], 1);
+    tc::mbar_init(&x_dead[0], 1); tc::mbar_init(&x_dead[1], 1); tc::mbar_init(&r_full[0], 1); tc::mbar_init(&r_full[1], 1);
     for (int i = 0; i < 4; ++i) {
       tc::mbar_init(&acc1_full[i], 1); tc::mbar_init(&acc2_full[i], 1); tc::mbar_init(&acc3_full[i], 1);
       tc::mbar_init(&h_full[i], C4_NEW / 2); tc::mbar_init(&x_free[i], C4_NEW / 2); tc::mbar_init(&l_full[i], C4_NEW / 2);
@@ -296,18 +303,17 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
 #pragma unroll 1
           for (int h = h0; h < h1; ++h) {
             const int gw = p.hg[h].gw, nun = p.hg[h].n_units, ups = 2 / gw;
-            if (h == 8 && p.c0_in_x) {
-              // the combiner's first half goes into this tile's X buffer, dead once GEMM 1 of the local branch has read it:
-              // all of it is in flight while the epilogue warps are busy with E1 / E2, so the combiner runs at tensor speed
+            if (h == 8 && p.res_in_x) {
+              // the residual rows of this tile go (back) into its X buffer, dead once GEMM 1 of the local branch has read it: the
+              // combiner epilogue then finds them in shared memory and writes its result over them -- no per-thread global access
               C4_TRACE(0, 2 * t);
               tc::mbar_wait(&x_dead[t], 0);
               C4_TRACE(0, 2 * t + 1);
-              if (p.dbg_noweights & 1) { tc::mbar_arrive(&c_full[t]); src += p.c0_bytes; continue; }
-              tc::mbar_arrive_expect_tx(&c_full[t], p.c0_bytes);
-              for (uint32_t o = 0; o < p.c0_bytes; o += C4_SLOT)
-                tc::bulk_g2s(smem + (size_t)t * xtile_bytes + o, src + o, p.c0_bytes - o < C4_SLOT ? p.c0_bytes - o : C4_SLOT, &c_full[t]);
-              src += p.c0_bytes;
-              continue;
+              const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+              const int b = tile / p.tpu, t0 = (tile % p.tpu) * 128;
+              tc::mbar_arrive_expect_tx(&r_full[t], xtile_bytes);
+              for (int kb = 0; kb < (p.D >> 6); ++kb)
+                c4_tma_load_3d(smem + (size_t)t * xtile_bytes + (size_t)kb * kblock_bytes(128), &tmap_r, kb * 64, t0, b, &r_full[t]);
             }
             for (int u0 = 0; u0 < nun; u0 += ups) {
               const int nu = nun - u0 < ups ? nun - u0 : ups;
@@ -365,7 +371,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
                   for (int ks = 0; ks < 4; ++ks) tc::umma_bf16(tmem + c * 192 + j * 64, ad + 2 * ks, bd + 2 * ks, ID64, ks ? 1u : 0u);
                   tc::umma_commit(&acc1_full[Q]);
                   if (j == 1) tc::umma_commit(&empty_bar[c]);
-                  if (j == 1 && c == 1 && ph == 1) tc::umma_commit(&x_dead[t]);  // both chains' GEMM 1 have read the X tile: its buffer may be reused
+                  if (j == 1 && c == 1 && ph == 1) tc::umma_commit(&x_dead[t]);  // both chains' GEMM 1 have read the X tile: its buffer may be reused (residual)
                 }
                 __syncwarp();
               }
@@ -389,36 +395,29 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
                 __syncwarp();
               }
             }
-            if (ph == 1) {  // combiner: A = L quarter kb, D = output half n (N = 128); half 0's weights wait in the dead X buffer
+            if (ph == 1) {  // combiner: A = L quarter kb, D = output half n (N = 128), one 16 KB unit per ring step
               const uint32_t lpar = (uint32_t)(t & 1);
-              C4_TRACE(1, ev++);
-              tc::mbar_wait_spin(&c_full[t], 0);
 #pragma unroll
-              for (int kb = 0; kb < 4; ++kb) {
-                if (kb == 0) { tc::mbar_wait_spin(&l_full[0], lpar); tc::mbar_wait_spin(&l_full[1], lpar); }  // A quarter 0; D = X_0, drained by E2 of quarters 0, 1
-                else if (kb >= 2) tc::mbar_wait_spin(&l_full[kb], lpar);
-                tc::tc_fence_after();
-                if (tc::elect_one()) {
-                  const uint64_t bd = x_d + (uint64_t)(kb * KB16);
+              for (int n = 0; n < 2; ++n) {
+                C4_TRACE(1, ev++);
 #pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) c4_umma_ts(tmem, tmem + (kb >> 1) * 192 + 128 + (kb & 1) * 32 + 8 * ks, bd + 2 * ks, ID128, (kb | ks) ? 1u : 0u);
-                  if (kb == 3) { tc::umma_commit(&acc3_full[0]); tc::umma_commit(&acc3_full[1]); }
+                for (int kb = 0; kb < 4; ++kb) {
+                  ring_wait(kb);
+                  if (n == 0) {  // half 1 finds every L quarter waited for
+                    if (kb == 0) { tc::mbar_wait_spin(&l_full[0], lpar); tc::mbar_wait_spin(&l_full[1], lpar); }  // A quarter 0; D = X_0, drained by E2 of quarters 0, 1
+                    else if (kb >= 2) tc::mbar_wait_spin(&l_full[kb], lpar);
+                  }
+                  tc::tc_fence_after();
+                  if (tc::elect_one()) {
+                    const uint64_t bd = ring_d + (uint64_t)(kb * KB16);
+#pragma unroll
+                    for (int ks = 0; ks < 4; ++ks)
+                      c4_umma_ts(tmem + n * 192, tmem + (kb >> 1) * 192 + 128 + (kb & 1) * 32 + 8 * ks, bd + 2 * ks, ID128, (kb | ks) ? 1u : 0u);
+                    tc::umma_commit(&empty_bar[kb]);
+                    if (kb == 3) { tc::umma_commit(&acc3_full[2 * n]); tc::umma_commit(&acc3_full[2 * n + 1]); }
+                  }
+                  __syncwarp();
                 }
-                __syncwarp();
-              }
-              C4_TRACE(1, ev++);
-#pragma unroll
-              for (int kb = 0; kb < 4; ++kb) {  // half 1 through the ring (one 16 KB unit per step); every L quarter has been waited for
-                ring_wait(kb);
-                tc::tc_fence_after();
-                if (tc::elect_one()) {
-                  const uint64_t bd = ring_d + (uint64_t)(kb * KB16);
-#pragma unroll
-                  for (int ks = 0; ks < 4; ++ks) c4_umma_ts(tmem + 192, tmem + (kb >> 1) * 192 + 128 + (kb & 1) * 32 + 8 * ks, bd + 2 * ks, ID128, (kb | ks) ? 1u : 0u);
-                  tc::umma_commit(&empty_bar[kb]);
-                  if (kb == 3) { tc::umma_commit(&acc3_full[2]); tc::umma_commit(&acc3_full[3]); }
-                }
-                __syncwarp();
               }
             }
           }
@@ -512,7 +511,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
           C4_TRACE(1, ev++);
           issue_half(p.hg[hb + c], 0, tmem + (uint32_t)c * 192u, xaddr, 0, x_free, (uint32_t)(it & 1) ^ 1u, acc1_full, 0u, nullptr);
         }
-        if (ph == 1 && p.c0_in_x) commit_to(&x_dead[t]);  // both chains' GEMM 1 have read the X tile: its buffer may be reused
+        if (ph == 1 && p.res_in_x) commit_to(&x_dead[t]);  // both chains' GEMM 1 have read the X tile: its buffer may be reused (residual)
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {  // GEMM 2 of both chains: A = H (Y regions), D = X_c again
           C4_TRACE(1, ev++);
@@ -522,8 +521,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
 #pragma unroll 1
           for (int n = 0; n < 2; ++n) {
             C4_TRACE(1, ev++);
-            const bool in_x = n == 0 && p.c0_in_x;  // the first half's weights wait in the (dead) X buffer
-            issue_half(p.hg[8 + n], 1, tmem + (uint32_t)n * 192u, 0, p.n2f_h, l_full, (uint32_t)(t & 1), acc3_full, in_x ? xaddr : 0u, &c_full[t]);
+            issue_half(p.hg[8 + n], 1, tmem + (uint32_t)n * 192u, 0, p.n2f_h, l_full, (uint32_t)(t & 1), acc3_full, 0u, nullptr);
           }
         }
       }
@@ -804,22 +802,10 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       // E3: y = act(acc3 + c[b]) (+ residual); this thread: row r, 32 output columns of each quarter of half grp   summary_mixing.py:251-253, Conformer.py:541
       // The residual of the first quarter is requested now, before the wait for c[b] and the combiner; the one of the second as
       // soon as the first has been consumed (same registers), so neither load latency sits in front of the epilogue math.
-      const bool has_res = p.resid != nullptr && !(p.dbg_noweights & 2);
+      const bool has_res = p.res_in_x && !(p.dbg_noweights & 2);
       const int qw3 = p.dout_h >> 1;
       const bool e3_active = k2 * 32 < qw3;
-      uint32_t rres[16];
-      auto load_res = [&](int qq) {
-        const __nv_bfloat16* src = p.resid + (row0 + r) * p.ldr + grp * p.dout_h + qq * qw3 + k2 * 32;
-#pragma unroll
-        for (int h = 0; h < 2; ++h) {
-          if (live) c4_ldg256(src + h * 16, rres + 8 * h);
-          else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) rres[8 * h + e] = 0u;
-          }
-        }
-      };
-      if (has_res && e3_active) load_res(0);
+      uint8_t* const xt = smem + (size_t)t * xtile_bytes;  // residual rows in (TMA, 128-byte swizzle), result rows out (TMA store)
       // c[b] of this tile's utterance (finalised by its owner CTA's prologue warps long ago, normally).
       // ONE poller per CTA (warp 0, lane 0; more pollers hot-spot the flag's L2 line against the other CTAs' atomics): warp 0
       // stages c[b] for everybody and signals an mbarrier; the other warps sleep on it -- no CTA-wide barrier between E2 and E3
@@ -862,25 +848,44 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
           tc::tmem_ld32(xc + cc, v);
           tc::tmem_ld_wait();
           c4_affine_act32<ACT>(v, rs, nm, sPar + 1024 + col, sCb + col, act);
+          // this thread's 64 bytes of row r: four 16-byte chunks of K-block col / 64, swizzled like the TMA wrote / will read them
+          uint8_t* const rowp = xt + (size_t)(col >> 6) * kblock_bytes(128) + r * 128;
+          const int ch0 = (col & 63) >> 3;
           if (has_res) {
+            if (qq == 0) tc::mbar_wait(&r_full[t], 0);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) { const float2 f = c4_bf2(rres[j]); v[2 * j] += f.x; v[2 * j + 1] += f.y; }
-            if (qq == 0) load_res(1);
+            for (int h = 0; h < 4; ++h) {
+              const uint4 rv = *reinterpret_cast<const uint4*>(rowp + (((ch0 + h) ^ (r & 7)) << 4));
+              const float2 f0 = c4_bf2(rv.x), f1 = c4_bf2(rv.y), f2 = c4_bf2(rv.z), f3 = c4_bf2(rv.w);
+              v[8 * h] += f0.x; v[8 * h + 1] += f0.y; v[8 * h + 2] += f1.x; v[8 * h + 3] += f1.y;
+              v[8 * h + 4] += f2.x; v[8 * h + 5] += f2.y; v[8 * h + 6] += f3.x; v[8 * h + 7] += f3.y;
+            }
           }
-          if (live && (!(p.dbg_noweights & 4) || v[0] == 12345.678f)) {
-            uint32_t o[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) o[j] = tc::pack_bf16x2(v[2 * j], v[2 * j + 1]);
-            c4_stg256(p.y + (row0 + r) * p.ldy + col, o);
-            c4_stg256(p.y + (row0 + r) * p.ldy + col + 16, o + 8);
+          for (int h = 0; h < 4; ++h) {
+            uint4 o;
+            o.x = tc::pack_bf16x2(v[8 * h], v[8 * h + 1]); o.y = tc::pack_bf16x2(v[8 * h + 2], v[8 * h + 3]);
+            o.z = tc::pack_bf16x2(v[8 * h + 4], v[8 * h + 5]); o.w = tc::pack_bf16x2(v[8 * h + 6], v[8 * h + 7]);
+            *reinterpret_cast<uint4*>(rowp + (((ch0 + h) ^ (r & 7)) << 4)) = o;
           }
         }
         tc::tc_fence_before();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&x_free[2 * grp + qq]);
       }
+      // this group's half of the output tile lies in the X buffer: one bulk tensor store per 64-column block (rows >= T are clipped)
+      tc::fence_proxy_async();
+      tc::named_bar_sync(7 + grp, 256);
+      if ((tid & 255) == 0 && !(p.dbg_noweights & 4)) {
+        for (int kb = 0; kb < (p.dout_h >> 6); ++kb) {
+          const int kba = grp * (p.dout_h >> 6) + kb;
+          c4_tma_store_3d(&tmap_y, xt + (size_t)kba * kblock_bytes(128), kba * 64, t0, b);
+        }
+        c4_bulk_commit();
+      }
       if (tr) C4_TRACE(3 - grp, ev++);
     }
+    if ((tid & 255) == 0) c4_bulk_wait_read0();  // the stores have read their shared-memory source before the CTA retires
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -905,6 +910,7 @@ bool tc_cell4_supported(const smx_cell_weights* w) {
   if (!tc_cell3_supported(w)) return false;
   if (!c4_dim_ok(w->enc_dim) || !c4_dim_ok(w->local_out_dim) || !c4_dim_ok(w->summary_out_dim) || !c4_dim_ok(w->merge.out_dim)) return false;
   if (!c4_dim_ok(w->local[0].out_dim) || !c4_dim_ok(w->summary[0].out_dim)) return false;
+  if (w->merge.out_dim > w->enc_dim) return false;  // the output tile is staged in the (dead) X buffer for its bulk tensor store
   return true;
 }
 
@@ -1107,18 +1113,19 @@ static c4_encode_fn c4_encoder() {
 }
 
 template <int ACT, bool STD>
-static int launch_cell4_as(const CUtensorMap& tm, const C4P& p, unsigned grid, size_t smem, cudaStream_t st) {
+static int launch_cell4_as(const CUtensorMap& tm, const CUtensorMap& tr, const CUtensorMap& ty, const C4P& p, unsigned grid, size_t smem, cudaStream_t st) {
   cudaError_t e = cudaFuncSetAttribute(cell4_kernel<ACT, STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(cell4_kernel): %s", cudaGetErrorString(e));
-  e = launch_pdl(cell4_kernel<ACT, STD>, dim3(grid), dim3(C4_THREADS), smem, st, 1u, tm, p);
+  e = launch_pdl(cell4_kernel<ACT, STD>, dim3(grid), dim3(C4_THREADS), smem, st, 1u, tm, tr, ty, p);
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaLaunchKernelEx(cell4_kernel): %s", cudaGetErrorString(e));
   count_tc_launch();
   return check_launch("cell4_kernel");
 }
 
 template <int ACT>
-static int launch_cell4_act(const CUtensorMap& tm, const C4P& p, unsigned grid, size_t smem, cudaStream_t st, bool std_cell) {
-  return std_cell ? launch_cell4_as<ACT, true>(tm, p, grid, smem, st) : launch_cell4_as<ACT, false>(tm, p, grid, smem, st);
+static int launch_cell4_act(const CUtensorMap& tm, const CUtensorMap& tr, const CUtensorMap& ty, const C4P& p, unsigned grid, size_t smem,
+                            cudaStream_t st, bool std_cell) {
+  return std_cell ? launch_cell4_as<ACT, true>(tm, tr, ty, p, grid, smem, st) : launch_cell4_as<ACT, false>(tm, tr, ty, p, grid, smem, st);
 }
 
 int tc_cell4_fwd(const smx_cell_weights* w, const void* img, int B, int T, const __nv_bfloat16* x, const float* pre_ln_w,
@@ -1147,16 +1154,19 @@ int tc_cell4_fwd(const smx_cell_weights* w, const void* img, int B, int T, const
     if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaMemsetAsync: %s", cudaGetErrorString(e));
   }
 
-  CUtensorMap tm;
-  {
-    const cuuint64_t gdim[3] = {(cuuint64_t)D, (cuuint64_t)T, (cuuint64_t)B};
-    const cuuint64_t gstr[2] = {(cuuint64_t)D * 2, (cuuint64_t)T * D * 2};
+  // x (GEMM operand tiles), the residual and y (both through the X buffer in the combiner epilogue) as (columns, frames, utterances)
+  // tensors, box = one 64-column block of a 128-frame tile, 128-byte swizzle: the UMMA operand image as is
+  CUtensorMap tm, tr, ty;
+  auto encode = [&](CUtensorMap* m, const void* base, int cols, int64_t ld) -> bool {
+    const cuuint64_t gdim[3] = {(cuuint64_t)cols, (cuuint64_t)T, (cuuint64_t)B};
+    const cuuint64_t gstr[2] = {(cuuint64_t)ld * 2, (cuuint64_t)T * ld * 2};
     const cuuint32_t box[3] = {64, 128, 1};
     const cuuint32_t estr[3] = {1, 1, 1};
-    CUresult r = enc(&tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)x, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    if (r != CUDA_SUCCESS) return fail(SMX_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
-  }
+    return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)base, gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+               CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+  };
+  if (!encode(&tm, x, D, D) || !encode(&ty, y, Dout, Dout) || !encode(&tr, residual ? (const void*)residual : (const void*)x, residual ? Dout : D, residual ? Dout : D))
+    return fail(SMX_ERR_CUDA, "cuTensorMapEncodeTiled failed");
 
   C4P p{};
   p.pre_w = pre_ln_w; p.pre_b = pre_ln_b; p.mask = mask;
@@ -1169,8 +1179,7 @@ int tc_cell4_fwd(const smx_cell_weights* w, const void* img, int B, int T, const
   for (int h = 0; h < 10; ++h) p.hg[h] = s.hg[h];
   p.n1s_h = w->summary[0].out_dim / 2; p.n2s_h = Ds / 2; p.n1f_h = w->local[0].out_dim / 2; p.n2f_h = Dl / 2; p.dout_h = Dout / 2;
   p.g2s_both = s.both[1]; p.g2f_both = s.both[3];
-  p.c0_bytes = (uint32_t)s.nblocks[8] * C4_BLOCK;
-  p.c0_in_x = p.c0_bytes <= (uint32_t)(D / 64) * kblock_bytes(128) ? 1 : 0;
+  p.res_in_x = residual != nullptr && Dout <= D ? 1 : 0;  // (the output tile must fit the X buffer; it does: the residual has the input's width)
   p.b_s1 = w->summary[0].b; p.b_s2 = w->summary[1].b; p.b_f1 = w->local[0].b; p.b_f2 = w->local[1].b;
   p.use_lnl = w->use_layernorm ? 1 : 0;
   p.gw = (const float*)((const char*)img + im.gw);
@@ -1204,16 +1213,16 @@ int tc_cell4_fwd(const smx_cell_weights* w, const void* img, int B, int T, const
   const unsigned grid = (unsigned)(p.n_tiles < c4_sms() ? p.n_tiles : c4_sms());
   int rc;
   // the standard cell: every GEMM 256 x 256, the four MLP layers block-diagonal over four heads of 64, combiner half in the X buffer
-  bool std_cell = D == 256 && Ds == 256 && Dl == 256 && Dout == 256 && p.c0_in_x && !getenv("SMX_C4_GENERIC");
+  bool std_cell = D == 256 && Ds == 256 && Dl == 256 && Dout == 256 && !getenv("SMX_C4_GENERIC");
   for (int g = 0; g < 4; ++g) {
     const smx_linear* Lg = g == 0 ? &w->summary[0] : g == 1 ? &w->summary[1] : g == 2 ? &w->local[0] : &w->local[1];
     std_cell = std_cell && Lg->in_dim == 256 && Lg->out_dim == 256 && Lg->n_split == 4 && s.both[g] == 0;
   }
   switch (p.act) {
-    case SMX_ACT_SWISH: rc = launch_cell4_act<SMX_ACT_SWISH>(tm, p, grid, smem, st, std_cell); break;
-    case SMX_ACT_GELU: rc = launch_cell4_act<SMX_ACT_GELU>(tm, p, grid, smem, st, std_cell); break;
-    case SMX_ACT_RELU: rc = launch_cell4_act<SMX_ACT_RELU>(tm, p, grid, smem, st, std_cell); break;
-    default: rc = launch_cell4_act<-1>(tm, p, grid, smem, st, false); break;
+    case SMX_ACT_SWISH: rc = launch_cell4_act<SMX_ACT_SWISH>(tm, tr, ty, p, grid, smem, st, std_cell); break;
+    case SMX_ACT_GELU: rc = launch_cell4_act<SMX_ACT_GELU>(tm, tr, ty, p, grid, smem, st, std_cell); break;
+    case SMX_ACT_RELU: rc = launch_cell4_act<SMX_ACT_RELU>(tm, tr, ty, p, grid, smem, st, std_cell); break;
+    default: rc = launch_cell4_act<-1>(tm, tr, ty, p, grid, smem, st, false); break;
   }
   ws.release(m0);
   return rc;
