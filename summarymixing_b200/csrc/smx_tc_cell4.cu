@@ -23,6 +23,7 @@
 // combiner's half c), Y_c = [192 c + 128, 192 c + 192) bf16 operand (H, then L).
 // Warp roles:  0-15 epilogue | 16-19 LayerNorm of the CTA's second tile, then per-utterance finalisation
 //              | 20 TMA producer (x tiles, weight ring) | 21 MMA issuer
+//              | 22 service warp: publishes a tile's column sums (GPU-scope release), fetches c[b] ahead of the combiner epilogue
 #include <cuda.h>
 #include <stdlib.h>
 
@@ -33,8 +34,8 @@ namespace smx {
 
 using tc::kblock_bytes;
 
-constexpr int C4_NEW = 16, C4_PRO_WARP0 = 16, C4_NPW = 4, C4_PROD_WARP = 20, C4_MMA_WARP = 21;
-constexpr int C4_THREADS = 22 * 32;
+constexpr int C4_NEW = 16, C4_PRO_WARP0 = 16, C4_NPW = 4, C4_PROD_WARP = 20, C4_MMA_WARP = 21, C4_SVC_WARP = 22;
+constexpr int C4_THREADS = 23 * 32;
 constexpr int C4_SLOTS = 4;
 constexpr uint32_t C4_SLOT = 16384, C4_BLOCK = 8192;
 constexpr int C4_MAXU = 8;       // MMA units (one K-block of one column group) per half-GEMM
@@ -229,7 +230,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
   __shared__ __align__(8) uint64_t full_bar[C4_SLOTS], empty_bar[C4_SLOTS];
   __shared__ __align__(8) uint64_t x_raw[C4_MAX_TILES], x_ready[C4_MAX_TILES];
   __shared__ __align__(8) uint64_t acc1_full[4], acc2_full[4], acc3_full[4], h_full[4], x_free[4], l_full[4];  // per quarter
-  __shared__ __align__(8) uint64_t x_dead[C4_MAX_TILES], r_full[C4_MAX_TILES], cb_full;
+  __shared__ __align__(8) uint64_t x_dead[C4_MAX_TILES], r_full[C4_MAX_TILES], cb_full[C4_MAX_TILES], pub_bar;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -263,7 +264,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
   if (tid == 0) {
     for (int s = 0; s < C4_SLOTS; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     tc::mbar_init(&x_ready[0], C4_NEW); tc::mbar_init(&x_ready[1], C4_NPW);
-    tc::mbar_init(&cb_full, 1);
+    tc::mbar_init(&cb_full[0], 1); tc::mbar_init(&cb_full[1], 1); tc::mbar_init(&pub_bar, C4_NEW);
     tc::mbar_init(&x_dead[0], 1); tc::mbar_init(&x_dead[1], 1); tc::mbar_init(&r_full[0], 1); tc::mbar_init(&r_full[1], 1);
     for (int i = 0; i < 4; ++i) {
       tc::mbar_init(&acc1_full[i], 1); tc::mbar_init(&acc2_full[i], 1); tc::mbar_init(&acc3_full[i], 1);
@@ -528,6 +529,34 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
     }
     if (p.trace && blockIdx.x == p.trace_cta && lane == 0) { p.trace[58] = (unsigned long long)t_ring; p.trace[59] = (unsigned long long)t_hand; }
     }  // generic issuer
+  } else if (warp == C4_SVC_WARP) {
+    // =============================== service warp ===============================
+    // Keeps two latencies off the epilogue warps' path.  Phase 1: when the sixteen epilogue warps have written a tile's column
+    // sums (pub_bar, CTA scope) it performs the GPU-scope release-add on the utterance's counter (the release is cumulative over
+    // the writes it has observed through the barrier); the epilogue warps go straight on to the next tile instead of waiting
+    // ~1.2 k cycles for their stores to be acknowledged.  Phase 2: it polls the utterance's flag (ONE poller per CTA: more
+    // hot-spot the flag's L2 line against the other CTAs' atomics) and stages c[b] in shared memory before the combiner
+    // epilogue of the tile asks for it (an L2 round trip of ~1.5 k cycles sat between E2 and E3 of every tile).
+#pragma unroll 1
+    for (int t = 0; t < ntl; ++t) {
+      const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+      tc::mbar_wait(&pub_bar, t & 1);
+      if (lane == 0) c4_red_release_add(p.cnt + (tile / p.tpu) * C4_SYNC_STRIDE, 1);
+    }
+#pragma unroll 1
+    for (int t = 0; t < ntl; ++t) {
+      const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+      const int b = tile / p.tpu;
+      float* const sCb = sRBw + t * 256;
+      if (lane == 0) c4_spin_until_ge(p.flag + b * C4_SYNC_STRIDE, p.fin_parts);
+      __syncwarp();  // (acquire by lane 0, then warp barrier: the other lanes' loads below are ordered after it; they bypass L1)
+      for (int i = lane; i < (p.Dout >> 2); i += 32) {
+        const float4 cv = __ldcg(reinterpret_cast<const float4*>(p.rowbias + (size_t)b * p.Dout) + i);
+        reinterpret_cast<float4*>(sCb)[i] = make_float4(BSC * cv.x, BSC * cv.y, BSC * cv.z, BSC * cv.w);
+      }
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&cb_full[t]);
+    }
   } else if (warp >= C4_PRO_WARP0) {
     // =============================== LayerNorm of the second tile, then per-utterance finalisation ===============================
     const int pw = warp - C4_PRO_WARP0, ftid = pw * 32 + lane;  // 0..127
@@ -566,7 +595,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
         tc::named_bar_sync(6, 128);
         cntf = (sR[0] + sR[1]) + (sR[2] + sR[3]);
       }
-      if (ftid == 0) c4_spin_until_ge(p.cnt + b * C4_SYNC_STRIDE, 2 * p.tpu);  // each tile's two epilogue groups report separately
+      if (ftid == 0) c4_spin_until_ge(p.cnt + b * C4_SYNC_STRIDE, p.tpu);
       tc::named_bar_sync(6, 128);
       float loc[2] = {0.0f, 0.0f};
 #pragma unroll
@@ -738,8 +767,8 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
         }
       }
       if (tr) C4_TRACE(3 - grp, ev++);
-      tc::named_bar_sync(7 + grp, 256);  // the group's partial sums of this tile are written
-      if ((tid & 255) == 0) c4_red_release_add(p.cnt + b * C4_SYNC_STRIDE, 1);  // release at GPU scope, cumulative over the writes ordered before it by the barrier; two per tile
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&pub_bar);  // this warp's partial sums of the tile are written: the service warp publishes the tile
       if (tr) C4_TRACE(3 - grp, ev++);
     }
     // =============================== phase 2: local branch + combiner ===============================
@@ -806,21 +835,9 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       const int qw3 = p.dout_h >> 1;
       const bool e3_active = k2 * 32 < qw3;
       uint8_t* const xt = smem + (size_t)t * xtile_bytes;  // residual rows in (TMA, 128-byte swizzle), result rows out (TMA store)
-      // c[b] of this tile's utterance (finalised by its owner CTA's prologue warps long ago, normally).
-      // ONE poller per CTA (warp 0, lane 0; more pollers hot-spot the flag's L2 line against the other CTAs' atomics): warp 0
-      // stages c[b] for everybody and signals an mbarrier; the other warps sleep on it -- no CTA-wide barrier between E2 and E3
-      float* const sCb = sRBw + (t & 1) * 256;
-      if (warp == 0) {
-        if (lane == 0) c4_spin_until_ge(p.flag + b * C4_SYNC_STRIDE, p.fin_parts);
-        __syncwarp();  // (acquire by lane 0, then warp barrier: the other lanes' loads below are ordered after it; they bypass L1)
-        for (int i = lane; i < (p.Dout >> 2); i += 32) {
-          const float4 cv = __ldcg(reinterpret_cast<const float4*>(p.rowbias + (size_t)b * p.Dout) + i);
-          reinterpret_cast<float4*>(sCb)[i] = make_float4(BSC * cv.x, BSC * cv.y, BSC * cv.z, BSC * cv.w);
-        }
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&cb_full);
-      }
-      tc::mbar_wait(&cb_full, t & 1);
+      // c[b] of this tile's utterance, staged by the service warp (finalised by its owner CTA's prologue warps long ago, normally)
+      float* const sCb = sRBw + t * 256;
+      tc::mbar_wait(&cb_full[t], 0);
       // row statistics of the un-normalised local branch (fixed order over the row's 2 np2 partials): mean, 1/std
       float rs = BSC, nm = 0.0f;
       if (p.use_lnl) {
