@@ -133,6 +133,8 @@ int tc_ffn2_pack(const smx_ffn_weights* w, void* packed, cudaStream_t st);
 int tc_ffn2_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t rows, const __nv_bfloat16* x,
                 const float* oln_w, const float* oln_b, float oln_eps, __nv_bfloat16* y, cudaStream_t st);
 // smx_tc_ffn3.cu: K-FFN v3, hidden activation resident in tensor memory (preferred; same packed images as v2)
+// W gamma (fp32), gw[n] = sum_k bf16(W[n,k] gamma_k), bw[n] = sum_k beta_k W[n,k]  (smx_tc_cell4.cu; gamma / beta NULL = no LayerNorm)
+int tc_fold_ln(const float* W, int K, int ldw, int N, const float* gamma, const float* beta, float* Wg, float* gw, float* bw, cudaStream_t st);
 bool tc_ffn3_supported(const smx_ffn_weights* w);
 size_t tc_ffn3_packed_bytes(const smx_ffn_weights* w);  // v2 images + the same blocks in ring-step order
 int tc_ffn3_pack(const smx_ffn_weights* w, void* packed, cudaStream_t st);

@@ -1057,6 +1057,12 @@ __global__ void __launch_bounds__(256) cell4_fold_ln_kernel(const float* __restr
   for (int o = 16; o; o >>= 1) { sg += __shfl_xor_sync(0xffffffffu, sg, o); sb += __shfl_xor_sync(0xffffffffu, sb, o); }
   if (lane == 0) { gw[n] = gamma ? sg : 0.0f; bw[n] = sb; }
 }
+// LayerNorm folded into the linear that follows it (shared with K-FFN's pack): W [N][ldw] (first K columns), gamma / beta NULL = none
+int tc_fold_ln(const float* W, int K, int ldw, int N, const float* gamma, const float* beta, float* Wg, float* gw, float* bw, cudaStream_t st) {
+  cell4_fold_ln_kernel<<<(N + 7) / 8, 256, 0, st>>>(W, K, ldw, N, gamma, beta, Wg, gw, bw);
+  count_launch();
+  return check_launch("cell4_fold_ln_kernel");
+}
 // chunk-major images of the five GEMMs (tc_pack_linear_nt, NT = 64) -> the v4 image
 int tc_cell4_pack(const smx_cell_weights* w, const void* img_s1, const void* img_s2, const void* img_f1, const void* img_f2,
                   const void* img_c, void* out, cudaStream_t st) {

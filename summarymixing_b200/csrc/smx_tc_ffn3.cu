@@ -37,7 +37,9 @@ struct Ffn3P {
   const __nv_bfloat16* x; __nv_bfloat16* y; int64_t rows;
   int D, F, n_tiles;
   const uint8_t* w1; const uint8_t* w2;   // v3 images of 64 x 64 blocks in step order: w1 [F/128][D/64][2], w2 [F/64][D/64]
-  const float* ln_w; const float* ln_b; const float* b1; const float* b2;
+  const float* b1; const float* b2;        // b1: first-layer bias with the LayerNorm's beta share folded in (tc_ffn3_pack)
+  const float* gw1;                        // [F] gw1[n] = sum_k bf16(gamma_k W1[n,k]): the mean's share of GEMM 1 (zeros without LayerNorm)
+  int has_ln;
   const float* oln_w; const float* oln_b; float oln_eps;
   int act;
   unsigned long long* trace;
@@ -100,9 +102,9 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
   uint8_t* sRing = smem + p.off_ring;
   float* sPar = reinterpret_cast<float*>(smem + p.off_par);  // [b1 (F) | b2 | oln_w | oln_b | ln_w | ln_b (256 each)]
   float* sRed = reinterpret_cast<float*>(smem + p.off_red);  // [4 column quarters][128 rows][2]: per-thread (mean, M2)
-  float2* sStat = reinterpret_cast<float2*>(smem + p.off_red + 4096);  // per-row (1/std, -mean/std) of the prologue LayerNorm
+  float2* sStat = reinterpret_cast<float2*>(smem + p.off_red + 4096);  // [2 (tile parity)][128] per-row (1/std, -mean/std) of the input LayerNorm
   __shared__ __align__(8) uint64_t full_bar[F3_STAGES], peer_full[F3_STAGES], empty_bar[F3_STAGES];
-  __shared__ __align__(8) uint64_t x_full, x_free, x_copied, acc1_full[2], h_full[2], acc2_full, epi_done;
+  __shared__ __align__(8) uint64_t x_full, x_free, stat_full, acc1_full[2], h_full[2], acc2_full, epi_done;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -124,17 +126,17 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
   if (warp == F3_PROD_WARP) { if (CL2) tc::tmem_alloc2(&tmem_base_s, 512); else tc::tmem_alloc(&tmem_base_s, 512); }
   if (tid == 0) {
     for (int s = 0; s < F3_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&peer_full[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    tc::mbar_init(&x_full, F3_NPW * NCTA); tc::mbar_init(&x_free, 1); tc::mbar_init(&x_copied, F3_NPW * 32); tc::mbar_init(&acc2_full, 1); tc::mbar_init(&epi_done, F3_NEW * NCTA);
+    tc::mbar_init(&x_full, F3_NPW * NCTA); tc::mbar_init(&x_free, 1); tc::mbar_init(&stat_full, F3_NPW); tc::mbar_init(&acc2_full, 1); tc::mbar_init(&epi_done, F3_NEW * NCTA);
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc1_full[i], 1); tc::mbar_init(&h_full[i], F3_NEW * NCTA); }
     tc::fence_barrier_init();
   }
   for (int i = tid; i < p.F; i += F3_THREADS) sPar[i] = p.b1[i];
-  float* sB2 = sPar + p.F; float* sOw = sB2 + 256; float* sOb = sOw + 256; float* sLw = sOb + 256; float* sLb = sLw + 272;
+  float* sB2 = sPar + p.F; float* sOw = sB2 + 256; float* sOb = sOw + 256; float* sGw = sOb + 256;
+  for (int i = tid; i < p.F; i += F3_THREADS) sGw[i] = p.gw1[i];
   for (int i = tid; i < 256; i += F3_THREADS) {
     sB2[i] = i < D ? p.b2[i] : 0.0f;
     sOw[i] = (OLN && i < D) ? p.oln_w[i] : 1.0f;
     sOb[i] = (OLN && i < D) ? p.oln_b[i] : 0.0f;
-    if (i < D) { sLw[tc::ln_pad_index(i, D)] = p.ln_w[i]; sLb[tc::ln_pad_index(i, D)] = p.ln_b[i]; }  // padded layout
   }
   tc::tc_fence_before();
   __syncthreads();
@@ -337,10 +339,13 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
     }
     }
   } else if (warp >= F3_PRO_WARP0) {
-    // =============================== prologue: x tile -> A operand image (copy only) ===============================
-    // The copy of tile t+1 starts as soon as the last GEMM1 of tile t has released X; the LayerNorm is left to the 16
-    // epilogue warps, which run it in 2 k cycles right after the final epilogue of tile t (four prologue warps competing
-    // with the busy epilogue warps took 20 k and sat on the critical path between two tiles).
+    // =============================== prologue: x tile -> A operand image, row statistics ===============================
+    // The input LayerNorm is NOT applied to the tile: gamma is folded into the packed W1, beta into b1 (tc_ffn3_pack), and the
+    // first epilogue applies the two per-row scalars -- LN(x) W1^T = rstd (x (W1 gamma)^T - mean gw1) + W1 beta.  GEMM 1 of a tile
+    // therefore starts as soon as its rows have landed (under the final epilogue of the previous tile), and the raw bf16 rows
+    // are exact GEMM operands (the normalised rows were rounded to bf16 once more).  The statistics (one thread per row, one
+    // pass shifted by the row's first element) are only needed by the first epilogue, some 3 k cycles later.
+    // The copy of tile t+1 starts as soon as the last GEMM1 of tile t has released X.
     const int pw = warp - F3_PRO_WARP0;
     int it = 0;
     for (int base = first_base; base < p.n_tiles; base += base_step, ++it) {
@@ -349,12 +354,40 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
       if (it > 0) tc::mbar_wait(&x_free, (it - 1) & 1);
       if (pw == 0) F3_TRACE(2, it, 0);
 #pragma unroll 1
-      for (int i = 0; i < 4; ++i) tc::rows8_copy(sX, p.x, D, row0, nrows, D, pw * 4 + i, lane);
+      for (int i = 0; i < 4; ++i) tc::rows8_copy(sX, p.x, D, row0, nrows, D, pw * 4 + i, lane);  // this warp: rows [32 pw, 32 pw + 32)
       tc::cp_async_commit();
       tc::cp_async_wait_all();
+      tc::fence_proxy_async();
       __syncwarp();
-      tc::mbar_arrive(&x_copied);  // every lane: each thread publishes its own cp.async writes
+      if (lane == 0) arrive_leader(&x_full);
       if (pw == 0) F3_TRACE(2, it, 1);
+      float rs = 1.0f, nm = 0.0f;
+      if (p.has_ln) {
+        const int row = pw * 32 + lane;  // copied by this warp
+        const uint8_t* rp = sX + row * 128;
+        const float x0 = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(rp + ((row & 7) << 4)));  // element 0 (chunk 0 lies at chunk position row & 7)
+        float2 s1 = make_float2(0.0f, 0.0f), s2 = make_float2(0.0f, 0.0f);
+        const float2 sh = make_float2(-x0, -x0);
+#pragma unroll 1
+        for (int kb = 0; kb < nkbD; ++kb) {
+#pragma unroll
+          for (int ch = 0; ch < 8; ++ch) {
+            const uint4 raw = *reinterpret_cast<const uint4*>(rp + (size_t)kb * kblock_bytes(128) + ((ch ^ (row & 7)) << 4));
+            float2 v[4];
+            tc::unpack_bf16x8_pairs(raw, v);
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { const float2 d = tc::add2(v[e], sh); s1 = tc::add2(s1, d); s2 = tc::fma2(d, d, s2); }
+          }
+        }
+        const float inv = 1.0f / (float)D;
+        const float m1 = (s1.x + s1.y) * inv;
+        const float var = fmaxf((s2.x + s2.y) * inv - m1 * m1, 0.0f);
+        rs = rsqrtf(var + 1e-5f);
+        nm = -(x0 + m1) * rs;
+      }
+      sStat[(it & 1) * 128 + pw * 32 + lane] = make_float2(rs, nm);
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&stat_full);
     }
   } else {
     // =============================== epilogue ===============================
@@ -367,12 +400,10 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
       const uint32_t par = it & 1;
       const int64_t row0 = (int64_t)(base + (int)crank) * 128;
       const int nrows = p.rows - row0 < 128 ? (int)(p.rows - row0) : 128;
-      // the tile has been copied into the operand image: LayerNorm in place, 8 rows per warp
-      tc::mbar_wait(&x_copied, par);
-      tc::rows8_ln(sX, nrows, D, warp, lane, sLw, sLb, sStat);
-      tc::fence_proxy_async();
-      tc::named_bar_sync(5, F3_NEW * 32);
-      if (warp < F3_NPW && lane == 0) arrive_leader(&x_full);
+      // this row's LayerNorm scalars (the prologue warps computed them while GEMM 1 of the first chunks ran)
+      tc::mbar_wait(&stat_full, par);
+      const float2 rst = sStat[par * 128 + r];
+      const float rs = rst.x, nm = rst.y;
       for (int j = 0; j < nj; ++j) {
         const int bsel = j & 1;
         tc::mbar_wait(&acc1_full[bsel], (ph_a1f >> bsel) & 1u);
@@ -386,8 +417,13 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
         // before any of them writes
         tc::named_bar_sync(1 + q, 128);
         const float4* bp = reinterpret_cast<const float4*>(sPar + chunk_of(j) * F3_HC + k * 32);
+        const float4* gp = reinterpret_cast<const float4*>(sGw + chunk_of(j) * F3_HC + k * 32);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { const float4 bb = bp[i]; v[4 * i] += bb.x; v[4 * i + 1] += bb.y; v[4 * i + 2] += bb.z; v[4 * i + 3] += bb.w; }
+        for (int i = 0; i < 8; ++i) {  // LN(x) W1^T + b1 = rstd acc + (-mean rstd) gw1 + b1'
+          const float4 bb = bp[i], gg = gp[i];
+          v[4 * i] = fmaf(rs, v[4 * i], fmaf(nm, gg.x, bb.x)); v[4 * i + 1] = fmaf(rs, v[4 * i + 1], fmaf(nm, gg.y, bb.y));
+          v[4 * i + 2] = fmaf(rs, v[4 * i + 2], fmaf(nm, gg.z, bb.z)); v[4 * i + 3] = fmaf(rs, v[4 * i + 3], fmaf(nm, gg.w, bb.w));
+        }
         tc::act_apply<32>(act, v);
         uint32_t hp[16];
 #pragma unroll
@@ -538,13 +574,44 @@ __global__ void ffn3_reorder_kernel(const uint4* w1v2, const uint4* w2v2, uint4*
   }
   for (int i = threadIdx.x; i < 512; i += blockDim.x) dst[i] = src[i];
 }
-size_t tc_ffn3_packed_bytes(const smx_ffn_weights* w) { return 2 * tc_ffn2_packed_bytes(w); }
+// image: [v2 W1 | v2 W2 (the v2 kernel's)] [v3 W1, LayerNorm folded | v3 W2 (step order)] [gw1 f32 F] [b1' f32 F]
+//        [pack-time scratch: v2-order image of the folded W1 | W1 gamma in fp32]
+struct Ffn3Image { size_t img, gw, b1, s_img, s_wg, total; };
+static Ffn3Image ffn3_image(const smx_ffn_weights* w) {
+  Ffn3Image im{};
+  const size_t D = w->w1.in_dim, F = w->w1.out_dim;
+  im.img = align_up(D * F * 2, 1024);
+  size_t off = 4 * im.img;
+  im.gw = off; off += align_up(F * 4, 1024);
+  im.b1 = off; off += align_up(F * 4, 1024);
+  im.s_img = off; off += im.img;
+  im.s_wg = off; off += align_up(D * F * 4, 1024);
+  im.total = off;
+  return im;
+}
+__global__ void ffn3_bias_kernel(const float* __restrict__ b1, const float* __restrict__ bw, float* __restrict__ out, int F) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < F) out[i] = (b1 ? b1[i] : 0.0f) + bw[i];
+}
+size_t tc_ffn3_packed_bytes(const smx_ffn_weights* w) { return ffn3_image(w).total; }
 int tc_ffn3_pack(const smx_ffn_weights* w, void* packed, cudaStream_t st) {
   SMX_TRY(tc_ffn2_pack(w, packed, st));
   const int D = w->w1.in_dim, F = w->w1.out_dim, nkbD = D / 64, nkbF = F / 64;
-  const size_t img = align_up((size_t)D * F * 2, 1024);
-  const uint8_t* b = (const uint8_t*)packed;
-  ffn3_reorder_kernel<<<2 * nkbD * nkbF, 128, 0, st>>>((const uint4*)b, (const uint4*)(b + img), (uint4*)(b + 2 * img), (uint4*)(b + 3 * img), nkbD, nkbF);
+  const Ffn3Image im = ffn3_image(w);
+  uint8_t* b = (uint8_t*)packed;
+  // the input LayerNorm folded into the first layer (see the kernel's prologue): W1 gamma -> image, gw1, b1' = b1 + W1 beta
+  float* Wg = (float*)(b + im.s_wg);
+  float* gw = (float*)(b + im.gw);
+  float* b1f = (float*)(b + im.b1);
+  SMX_TRY(tc_fold_ln(w->w1.w, D, D, F, w->ln_w, w->ln_b, Wg, gw, b1f, st));  // (b1f holds W1 beta for a moment)
+  ffn3_bias_kernel<<<(F + 255) / 256, 256, 0, st>>>(w->w1.b, b1f, b1f, F);
+  count_launch();
+  SMX_TRY(check_launch("ffn3_bias_kernel"));
+  smx_linear Lg{};
+  Lg.w = Wg; Lg.b = nullptr; Lg.in_dim = D; Lg.out_dim = F; Lg.n_split = 1;
+  SMX_TRY(tc_pack_linear_nt(Lg, 0, D, 64, b + im.s_img, st));
+  ffn3_reorder_kernel<<<2 * nkbD * nkbF, 128, 0, st>>>((const uint4*)(b + im.s_img), (const uint4*)(b + im.img), (uint4*)(b + 2 * im.img),
+                                                      (uint4*)(b + 3 * im.img), nkbD, nkbF);
   count_launch();
   return check_launch("ffn3_reorder_kernel");
 }
@@ -596,15 +663,17 @@ int tc_ffn3_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t r
   p.n_tiles = (int)((rows + 127) / 128);
   p.w1 = (const uint8_t*)packed + 2 * align_up((size_t)D * F * 2, 1024);  // the v3 images follow the v2 images
   p.w2 = p.w1 + align_up((size_t)D * F * 2, 1024);
-  p.ln_w = w->ln_w; p.ln_b = w->ln_b; p.b1 = w->w1.b; p.b2 = w->w2.b;
+  const Ffn3Image im = ffn3_image(w);
+  p.b1 = (const float*)((const uint8_t*)packed + im.b1); p.gw1 = (const float*)((const uint8_t*)packed + im.gw); p.b2 = w->w2.b;
+  p.has_ln = w->ln_w != nullptr ? 1 : 0;
   p.oln_w = oln_w; p.oln_b = oln_b; p.oln_eps = oln_eps;
   p.act = act;
   const int nc = D / 64;
   p.trace = g_trace3f;
   p.off_ring = (uint32_t)nc * kblock_bytes(128);
   p.off_par = p.off_ring + F3_RING_BYTES;
-  p.off_red = p.off_par + (uint32_t)align_up((size_t)(F + 1280 + 32) * 4, 1024);
-  const size_t smem = (size_t)p.off_red + 4096 + 1024;
+  p.off_red = p.off_par + (uint32_t)align_up((size_t)(2 * F + 768 + 32) * 4, 1024);
+  const size_t smem = (size_t)p.off_red + 4096 + 2048;
   if (smem > 227 * 1024 - 1024) return fail(SMX_ERR_UNSUPPORTED, "ffn: tile does not fit shared memory");
   // CTA pairs when the weight steps split evenly over two CTAs (D a multiple of 128) and there is more than one tile
   p.cl2 = (g_ffn_pair && D % 128 == 0 && p.n_tiles >= 2) ? 1 : 0;

@@ -6,7 +6,7 @@ mkdir -p gpurun_out
 echo "== quick"; for args in "cell" "cell 32 1000" "cell 50 300"; do timeout 180 python tools/sanitize_run.py $args 2>&1 | tail -2; done
 echo "== trace"; timeout 300 python tools/trace_cell4.py 2>&1 | tail -9
 if [ "$2" = "full" ]; then
-echo "== pytest"; timeout 1500 python -m pytest tests/test_tc_path_gpu.py tests/test_tile_golden.py tests/test_fullsize_parity_gpu.py -m gpu -q -x --no-header -s 2>&1 | grep "^\[\|passed\|failed\|Error\|assert" | head -40
+echo "== pytest"; timeout 1500 python -m pytest tests/test_tc_path_gpu.py tests/test_tile_golden.py tests/test_fullsize_parity_gpu.py tests/test_tc_blocks_gpu.py -m gpu -q -x --no-header -s 2>&1 | grep "^\[\|passed\|failed\|Error\|assert" | head -40
 fi
 echo "== bench"; timeout 900 python bench.py --steps 20 --warmup 5 --no-cpu --no-others 2>&1 | tail -1 > gpurun_out/${tag}_bench.json; python - <<PY
 import json

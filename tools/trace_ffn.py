@@ -15,11 +15,12 @@ layer = S.ConformerEncoderLayer(D, 1024, 4, 31, attention_type="SummaryMixing", 
                                 local_proj_out_dim=D, summary_hid_dim=[D]).eval().to(dev)
 x = torch.randn(B, T, D, device=dev).to(torch.bfloat16)
 mask = torch.ones(B, T, dtype=torch.bool, device=dev)
-buf = torch.zeros(1024, dtype=torch.int64, device=dev)
+buf = torch.zeros(4096, dtype=torch.int64, device=dev)
 with torch.no_grad():
     for _ in range(3):
         layer(x, src_key_padding_mask=mask)
     torch.cuda.synchronize()
+    L.lib().smx_debug_set_cell_version(3)  # (the one-kernel cell's own trace stamps would overlap the FFN's slots)
     L.lib().smx_debug_set_trace(buf.data_ptr())
     layer(x, src_key_padding_mask=mask)
     torch.cuda.synchronize()
