@@ -1,5 +1,6 @@
 // Declarations of the tcgen05 (bf16 tensor-core) arm of libsmx.
 #pragma once
+#include <cuda.h>
 #include <utility>
 #include "smx_internal.h"
 
@@ -133,6 +134,9 @@ int tc_ffn2_pack(const smx_ffn_weights* w, void* packed, cudaStream_t st);
 int tc_ffn2_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t rows, const __nv_bfloat16* x,
                 const float* oln_w, const float* oln_b, float oln_eps, __nv_bfloat16* y, cudaStream_t st);
 // smx_tc_ffn3.cu: K-FFN v3, hidden activation resident in tensor memory (preferred; same packed images as v2)
+// bf16 tensor map (cuTensorMapEncodeTiled through the runtime's driver entry point; smx_tc_cell4.cu): rank 2 or 3, dims / box
+// innermost first, strides in bytes for dims 1.., 128-byte swizzle (box[0] = 64 columns: one UMMA K-block).  false: unavailable / rejected
+bool tc_encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
 // W gamma (fp32), gw[n] = sum_k bf16(W[n,k] gamma_k), bw[n] = sum_k beta_k W[n,k]  (smx_tc_cell4.cu; gamma / beta NULL = no LayerNorm)
 int tc_fold_ln(const float* W, int K, int ldw, int N, const float* gamma, const float* beta, float* Wg, float* gw, float* bw, cudaStream_t st);
 bool tc_ffn3_supported(const smx_ffn_weights* w);

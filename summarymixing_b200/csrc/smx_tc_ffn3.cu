@@ -93,10 +93,16 @@ __device__ __forceinline__ void f3_stg256(void* p, const uint32_t* r) {
                "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7])
                : "memory");
 }
+__device__ __forceinline__ void f3_tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
+  asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   tc::smem_u32(smem_dst)),
+               "l"(tmap), "r"(c0), "r"(c1), "r"(tc::smem_u32(bar))
+               : "memory");
+}
 __device__ __forceinline__ float2 f3_bf2(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u)); }
 
 template <bool OLN, int ACT, bool CL2>  // ACT >= 0: compile-time activation (smx_act); -1: runtime p.act; CL2: CTA pairs
-__global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
+__global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Ffn3P p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sX = smem;
   uint8_t* sRing = smem + p.off_ring;
@@ -104,7 +110,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
   float* sRed = reinterpret_cast<float*>(smem + p.off_red);  // [4 column quarters][128 rows][2]: per-thread (mean, M2)
   float2* sStat = reinterpret_cast<float2*>(smem + p.off_red + 4096);  // [2 (tile parity)][128] per-row (1/std, -mean/std) of the input LayerNorm
   __shared__ __align__(8) uint64_t full_bar[F3_STAGES], peer_full[F3_STAGES], empty_bar[F3_STAGES];
-  __shared__ __align__(8) uint64_t x_full, x_free, stat_full, acc1_full[2], h_full[2], acc2_full, epi_done;
+  __shared__ __align__(8) uint64_t x_full, x_free, x_landed, stat_full, acc1_full[2], h_full[2], acc2_full, epi_done;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -126,7 +132,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
   if (warp == F3_PROD_WARP) { if (CL2) tc::tmem_alloc2(&tmem_base_s, 512); else tc::tmem_alloc(&tmem_base_s, 512); }
   if (tid == 0) {
     for (int s = 0; s < F3_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&peer_full[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    tc::mbar_init(&x_full, F3_NPW * NCTA); tc::mbar_init(&x_free, 1); tc::mbar_init(&stat_full, F3_NPW); tc::mbar_init(&acc2_full, 1); tc::mbar_init(&epi_done, F3_NEW * NCTA);
+    tc::mbar_init(&x_full, F3_NPW * NCTA); tc::mbar_init(&x_free, 1); tc::mbar_init(&stat_full, F3_NPW); tc::mbar_init(&x_landed, 1); tc::mbar_init(&acc2_full, 1); tc::mbar_init(&epi_done, F3_NEW * NCTA);
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc1_full[i], 1); tc::mbar_init(&h_full[i], F3_NEW * NCTA); }
     tc::fence_barrier_init();
   }
@@ -353,12 +359,14 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const Ffn3P p) {
       const int nrows = p.rows - row0 < 128 ? (int)(p.rows - row0) : 128;
       if (it > 0) tc::mbar_wait(&x_free, (it - 1) & 1);
       if (pw == 0) F3_TRACE(2, it, 0);
-#pragma unroll 1
-      for (int i = 0; i < 4; ++i) tc::rows8_copy(sX, p.x, D, row0, nrows, D, pw * 4 + i, lane);  // this warp: rows [32 pw, 32 pw + 32)
-      tc::cp_async_commit();
-      tc::cp_async_wait_all();
-      tc::fence_proxy_async();
-      __syncwarp();
+      // the tile arrives by tensor-map TMA (one 64-column box per K-block, 128-byte swizzle: the operand image as is; rows past
+      // the end are zero-filled) -- four bulk copies instead of 4096 16-byte cp.async competing with the epilogue warps for
+      // issue slots and the load/store queue (the copy of a CTA's second tile took 9.7 k cycles that way)
+      if (pw == 0 && lane == 0) {
+        tc::mbar_arrive_expect_tx(&x_landed, (uint32_t)nkbD * kblock_bytes(128));
+        for (int kb = 0; kb < nkbD; ++kb) f3_tma_load_2d(sX + (size_t)kb * kblock_bytes(128), &tmap_x, kb * 64, (int)row0, &x_landed);
+      }
+      tc::mbar_wait(&x_landed, it & 1);
       if (lane == 0) arrive_leader(&x_full);
       if (pw == 0) F3_TRACE(2, it, 1);
       float rs = 1.0f, nm = 0.0f;
@@ -637,12 +645,12 @@ static int ffn3_sms() {
 }
 
 template <bool OLN, bool CL2>
-static int launch_ffn3(const Ffn3P& p, unsigned grid, size_t smem, cudaStream_t st) {
+static int launch_ffn3(const CUtensorMap& tm, const Ffn3P& p, unsigned grid, size_t smem, cudaStream_t st) {
   cudaError_t e;
 #define SMX_FFN3_LAUNCH(A)                                                                                   \
   e = cudaFuncSetAttribute(ffn3_kernel<OLN, A, CL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(ffn3_kernel): %s", cudaGetErrorString(e)); \
-  e = launch_pdl(ffn3_kernel<OLN, A, CL2>, dim3(grid), dim3(F3_THREADS), smem, st, CL2 ? 2u : 1u, p);         \
+  e = launch_pdl(ffn3_kernel<OLN, A, CL2>, dim3(grid), dim3(F3_THREADS), smem, st, CL2 ? 2u : 1u, tm, p);     \
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaLaunchKernelEx(ffn3_kernel): %s", cudaGetErrorString(e));
   switch (p.act) {
     case SMX_ACT_SWISH: SMX_FFN3_LAUNCH(SMX_ACT_SWISH); break;
@@ -675,15 +683,21 @@ int tc_ffn3_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t r
   p.off_red = p.off_par + (uint32_t)align_up((size_t)(2 * F + 768 + 32) * 4, 1024);
   const size_t smem = (size_t)p.off_red + 4096 + 2048;
   if (smem > 227 * 1024 - 1024) return fail(SMX_ERR_UNSUPPORTED, "ffn: tile does not fit shared memory");
+  CUtensorMap tm;
+  {
+    const uint64_t dims[2] = {(uint64_t)D, (uint64_t)rows}, strides[1] = {(uint64_t)D * 2};
+    const uint32_t box[2] = {64, 128};
+    if (!tc_encode_tmap_bf16(&tm, x, 2, dims, strides, box)) return fail(SMX_ERR_CUDA, "ffn: cuTensorMapEncodeTiled failed");
+  }
   // CTA pairs when the weight steps split evenly over two CTAs (D a multiple of 128) and there is more than one tile
   p.cl2 = (g_ffn_pair && D % 128 == 0 && p.n_tiles >= 2) ? 1 : 0;
   if (p.cl2) {
     const int n_pairs = (p.n_tiles + 1) / 2, max_pairs = ffn3_sms() / 2;
     const unsigned grid = 2u * (unsigned)(n_pairs < max_pairs ? n_pairs : max_pairs);
-    return oln_w ? launch_ffn3<true, true>(p, grid, smem, st) : launch_ffn3<false, true>(p, grid, smem, st);
+    return oln_w ? launch_ffn3<true, true>(tm, p, grid, smem, st) : launch_ffn3<false, true>(tm, p, grid, smem, st);
   }
   const unsigned grid = (unsigned)(p.n_tiles < ffn3_sms() ? p.n_tiles : ffn3_sms());
-  return oln_w ? launch_ffn3<true, false>(p, grid, smem, st) : launch_ffn3<false, false>(p, grid, smem, st);
+  return oln_w ? launch_ffn3<true, false>(tm, p, grid, smem, st) : launch_ffn3<false, false>(tm, p, grid, smem, st);
 }
 
 }  // namespace smx
