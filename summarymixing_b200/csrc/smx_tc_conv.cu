@@ -176,8 +176,18 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
     const int c0 = pr * 2;                      // this thread's channel pair
     const int wig = (tid % pairs) >> 5;         // warp index inside its frame-block group
     float2 w2[K];  // taps of both channels
+    {
+      // The D x K taps pass through shared memory (the A-operand buffer, idle until the first tile's convolution has been
+      // computed): one coalesced sweep by all compute threads, then every thread picks up its 2 K values.  (Read straight from
+      // global memory -- 62 scalar loads per thread, 124 bytes apart between lanes -- they kept the load/store queue
+      // throttled for a quarter of the kernel's stall samples: profiles/r02_notes.md.)
+      float* sTap = reinterpret_cast<float*>(sA);
+      for (int i = tid; i < D * K; i += CV_CT) sTap[i] = p.dw_w[i];
+      tc::named_bar_sync(1, CV_CT);
 #pragma unroll
-    for (int j = 0; j < K; ++j) w2[j] = make_float2(p.dw_w[(size_t)c0 * K + j], p.dw_w[(size_t)(c0 + 1) * K + j]);
+      for (int j = 0; j < K; ++j) w2[j] = make_float2(sTap[c0 * K + j], sTap[(c0 + 1) * K + j]);
+      tc::named_bar_sync(1, CV_CT);  // before the first A-operand rows are written
+    }
     const float2 bias2 = make_float2(p.dw_b ? p.dw_b[c0] : 0.0f, p.dw_b ? p.dw_b[c0 + 1] : 0.0f);
     tc::pdl_wait();  // g / residual come from the preceding kernels (the taps above are parameters)
     const float2 lw2 = make_float2(sPar[256 + c0], sPar[256 + c0 + 1]), lb2 = make_float2(sPar[512 + c0], sPar[512 + c0 + 1]);
