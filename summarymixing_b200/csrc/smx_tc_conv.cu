@@ -182,7 +182,13 @@ __global__ void __launch_bounds__(CV_THREADS, 1) conv_kernel(const ConvFP p) {
       // global memory -- 62 scalar loads per thread, 124 bytes apart between lanes -- they kept the load/store queue
       // throttled for a quarter of the kernel's stall samples: profiles/r02_notes.md.)
       float* sTap = reinterpret_cast<float*>(sA);
-      for (int i = tid; i < D * K; i += CV_CT) sTap[i] = p.dw_w[i];
+      if ((reinterpret_cast<uintptr_t>(p.dw_w) & 15) == 0 && (D * K) % 4 == 0) {  // all chunks in flight at once
+        for (int i = tid; i < D * K / 4; i += CV_CT) tc::cp_async16(sTap + 4 * i, p.dw_w + 4 * i, 16u);
+        tc::cp_async_commit();
+        tc::cp_async_wait_all();
+      } else {
+        for (int i = tid; i < D * K; i += CV_CT) sTap[i] = p.dw_w[i];
+      }
       tc::named_bar_sync(1, CV_CT);
 #pragma unroll
       for (int j = 0; j < K; ++j) w2[j] = make_float2(sTap[c0 * K + j], sTap[(c0 + 1) * K + j]);
