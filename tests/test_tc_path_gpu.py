@@ -316,6 +316,43 @@ def test_cuda_graph_replay_matches_eager():
             assert torch.equal(y, eager[i])
 
 
+def test_host_pipeline_serves_host_batches():
+    """summarymixing_b200.HostPipeline is the package's host-buffer entry point (what bench.py's `e2e` number is measured
+    through): pageable and pinned HOST batches in, pinned host results out, copies on their own streams around graph replays.
+    Every result equals the module's forward on the same batch, bit for bit, in order; device tensors and wrong shapes are
+    refused loudly, and the modules themselves keep refusing host tensors (no CPU path)."""
+    torch.manual_seed(73)
+    D, B, T = 256, 6, 400
+    m = S.ConformerEncoder(2, D, 1024, 4, 31, attention_type="SummaryMixing", local_proj_hid_dim=[D],
+                           local_proj_out_dim=D, summary_hid_dim=[D]).eval().to(DEV)
+    g = torch.Generator().manual_seed(74)
+    batches = []
+    for i in range(5):
+        x = torch.randn(B, T, D, generator=g).to(torch.bfloat16)
+        lens = torch.randint(50, T + 1, (B,), generator=g)
+        mask = torch.arange(T)[None] < lens[:, None]
+        if i % 2:  # every other batch already pinned: taken as is, the others are staged through the pipeline's own buffers
+            x, mask = x.pin_memory(), mask.pin_memory()
+        batches.append((x, mask))
+    with torch.no_grad():
+        want = [m(x.to(DEV), src_key_padding_mask=k.to(DEV))[0].cpu() for x, k in batches]
+    pipe = S.HostPipeline(m, B, T, D, device=DEV)
+    assert pipe.h2d_bytes_per_step == B * T * D * 2 + B * T and pipe.d2h_bytes_per_step == B * T * D * 2
+    t0 = L.lib().smx_tc_launch_count()
+    got = [y.clone() for y in pipe.run(batches)]
+    assert len(got) == len(want)
+    for y, w in zip(got, want):
+        assert not y.is_cuda and torch.equal(y, w)
+    if pipe.graphs is None:  # eager launches: the kernels of 5 forwards were enqueued by this call
+        assert L.lib().smx_tc_launch_count() - t0 == 5 * 2 * 5
+    with pytest.raises(RuntimeError, match="HOST tensors"):
+        list(pipe.run([(batches[0][0].to(DEV), batches[0][1].to(DEV))]))
+    with pytest.raises(RuntimeError, match="was built for"):
+        list(pipe.run([(batches[0][0][:, :100], batches[0][1][:, :100])]))
+    with pytest.raises(Exception):
+        m(batches[0][0], src_key_padding_mask=batches[0][1])
+
+
 def test_16_byte_aligned_buffers_take_the_fallback_kernels():
     """The newest kernels move rows with 256-bit accesses and need 32-byte aligned activations; buffers that are only
     16-byte aligned (the C ABI's stated minimum) must still give the same answer through the fallbacks: first-generation
