@@ -95,6 +95,12 @@ int tc_cell3_reorder(const smx_linear& L, int K, int n_split, const void* img_ch
 int tc_cell3_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_s2, const void* img_f1, const void* img_f2,
                  const void* img_c, int B, int T, const __nv_bfloat16* x, const float* pre_ln_w, const float* pre_ln_b,
                  const uint8_t* mask, const __nv_bfloat16* residual, __nv_bfloat16* y, Arena& ws, cudaStream_t st);
+// smx_tc_glu4.cu: K-GLU v4 (D = 256, <= 2 row tiles per CTA): both tiles resident, one pass over the weights, LayerNorm folded
+bool tc_glu4_supported(const smx_convmod_weights* w);
+bool tc_glu4_fits(int64_t rows);
+size_t tc_glu4_packed_bytes(const smx_convmod_weights* w);
+int tc_glu4_pack(const smx_convmod_weights* w, void* out, cudaStream_t st);
+int tc_glu4_fwd(const smx_convmod_weights* w, const void* img, int64_t rows, const __nv_bfloat16* x, __nv_bfloat16* g, cudaStream_t st);
 int tc_glu3_fwd(const smx_linear& L, const void* img_sched, const float* ln_w, const float* ln_b, int64_t rows,
                 const __nv_bfloat16* x, __nv_bfloat16* out, cudaStream_t st);
 void tc_set_cell_version(int v);  // 1, 3 or 4 (diagnostics / A-B timing)

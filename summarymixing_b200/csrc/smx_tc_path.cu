@@ -481,8 +481,10 @@ bool tc_convmod_supported(const smx_convmod_weights* w, int chunk) {
 size_t tc_convmod_packed_bytes(const smx_convmod_weights* w) {
   if (!tc_convmod_supported(w, 0)) return 0;
   const int D = w->bottleneck.in_dim;
-  return 2 * align_up(tc_linear_packed_bytes(D, 2 * D)) + 2 * align_up(tc_linear_packed_bytes(D, D));  // [GLU][out][GLU, out in schedule order]
+  return 2 * align_up(tc_linear_packed_bytes(D, 2 * D)) + 2 * align_up(tc_linear_packed_bytes(D, D))  // [GLU][out][GLU, out in schedule order]
+         + (tc_convf_supported(w, 0) ? tc_glu4_packed_bytes(w) : 0);                                    // [K-GLU v4 image]
 }
+static size_t convmod_glu4_offset(int D) { return 2 * align_up(tc_linear_packed_bytes(D, 2 * D)) + 2 * align_up(tc_linear_packed_bytes(D, D)); }
 int tc_convmod_pack(const smx_convmod_weights* w, void* packed, cudaStream_t st) {
   if (!tc_convmod_supported(w, 0)) return fail(SMX_ERR_UNSUPPORTED, "conv module not handled by the tensor-core arm");
   const int D = w->bottleneck.in_dim;
@@ -491,8 +493,10 @@ int tc_convmod_pack(const smx_convmod_weights* w, void* packed, cudaStream_t st)
     SMX_TRY(tc_pack_linear_nt(w->out, 0, D, 64, (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)), st));
     char* sched = (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)) + align_up(tc_linear_packed_bytes(D, D));
     SMX_TRY(tc_cell3_reorder(w->bottleneck, D, 1, packed, sched, st));
-    return tc_cell3_reorder(w->out, D, 1, (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)),
-                            sched + align_up(tc_linear_packed_bytes(D, 2 * D)), st);
+    SMX_TRY(tc_cell3_reorder(w->out, D, 1, (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)),
+                             sched + align_up(tc_linear_packed_bytes(D, 2 * D)), st));
+    if (tc_glu4_supported(w)) SMX_TRY(tc_glu4_pack(w, (char*)packed + convmod_glu4_offset(D), st));
+    return SMX_OK;
   }
   SMX_TRY(tc_pack_linear(w->bottleneck, 0, D, 1, packed, st));
   SMX_TRY(tc_pack_linear(w->out, 0, D, 0, (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)), st));
@@ -704,7 +708,9 @@ int tc_convmod_fwd(const smx_convmod_weights* w, const void* packed, int act, in
   if (tc_convf_supported(w, 0)) {
     __nv_bfloat16* gb = (__nv_bfloat16*)ws.take((size_t)rows * D * 2);
     if (!gb) return fail(SMX_ERR_WORKSPACE, "workspace too small (tc conv module)");
-    if (tc_cell_version() >= 3 && ((uintptr_t)x % 32 == 0) && ((uintptr_t)gb % 32 == 0))                // :322-324
+    if (tc_cell_version() >= 4 && tc_glu4_supported(w) && tc_glu4_fits(rows) && ((uintptr_t)x % 32 == 0) && ((uintptr_t)gb % 32 == 0))  // :322-324
+      SMX_TRY(tc_glu4_fwd(w, (const char*)packed + convmod_glu4_offset(D), rows, x, gb, st));
+    else if (tc_cell_version() >= 3 && ((uintptr_t)x % 32 == 0) && ((uintptr_t)gb % 32 == 0))
       SMX_TRY(tc_glu3_fwd(w->bottleneck, (const char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)) + align_up(tc_linear_packed_bytes(D, D)),
                           w->ln_w, w->ln_b, rows, x, gb, st));
     else
