@@ -132,7 +132,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
   if (warp == F3_PROD_WARP) { if (CL2) tc::tmem_alloc2(&tmem_base_s, 512); else tc::tmem_alloc(&tmem_base_s, 512); }
   if (tid == 0) {
     for (int s = 0; s < F3_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&peer_full[s], 1); tc::mbar_init(&empty_bar[s], 1); }
-    tc::mbar_init(&x_full, F3_NPW * NCTA); tc::mbar_init(&x_free, 1); tc::mbar_init(&stat_full, F3_NPW); tc::mbar_init(&x_landed, 1); tc::mbar_init(&acc2_full, 1); tc::mbar_init(&epi_done, F3_NEW * NCTA);
+    tc::mbar_init(&x_full, F3_NPW * NCTA); tc::mbar_init(&x_free, 1); tc::mbar_init(&stat_full, F3_NPW * 32); tc::mbar_init(&x_landed, 1); tc::mbar_init(&acc2_full, 1); tc::mbar_init(&epi_done, F3_NEW * NCTA);
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc1_full[i], 1); tc::mbar_init(&h_full[i], F3_NEW * NCTA); }
     tc::fence_barrier_init();
   }
@@ -394,8 +394,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
         nm = -(x0 + m1) * rs;
       }
       sStat[(it & 1) * 128 + pw * 32 + lane] = make_float2(rs, nm);
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&stat_full);
+      tc::mbar_arrive(&stat_full);  // every thread publishes its own row (release / acquire through the barrier)
     }
   } else {
     // =============================== epilogue ===============================

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(G4_THREADS, 1) glu4_kernel(const __grid_consta
   if (tid == 0) {
     for (int s = 0; s < G4_SLOTS; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     for (int t = 0; t < 2; ++t) {
-      tc::mbar_init(&stat_full[t], 4);
+      tc::mbar_init(&stat_full[t], 128);
       for (int u = 0; u < 2; ++u) { tc::mbar_init(&acc_full[t][u], 1); tc::mbar_init(&acc_free[t][u], 8); }
     }
     tc::fence_barrier_init();
@@ -192,8 +192,7 @@ __global__ void __launch_bounds__(G4_THREADS, 1) glu4_kernel(const __grid_consta
         nm = -(x0 + m1) * rs;
       }
       sStat[t * 128 + pw * 32 + lane] = make_float2(rs, nm);
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&stat_full[t]);
+      tc::mbar_arrive(&stat_full[t]);  // every thread publishes its own row (release / acquire through the barrier)
     }
   } else {
     // =============================== epilogue: group t (eight warps) owns tile t ===============================
