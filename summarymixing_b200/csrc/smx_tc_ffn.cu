@@ -316,18 +316,20 @@ static bool ffn_fused_ok(const smx_ffn_weights* w) {
   return true;
 }
 // Wide models (conformer_large: D = 512, d_ffn = 2048, conformer_summarymixing.yaml:113-125): the output tile no longer fits the
-// fused kernels' TMEM budget; two launches instead -- K-LIN (LayerNorm prologue, D -> F, activation) and K-GEMM (F -> D with
-// the scaled residual as epilogue, any K) -- with the hidden activation making one bf16 round trip through memory.
+// fused kernels' TMEM budget; three launches instead -- the input LayerNorm, K-GEMM (D -> F, activation) and K-GEMM (F -> D with
+// the scaled residual as epilogue) -- with the normalised rows and the hidden activation making one bf16 round trip through
+// memory.  (The first GEMM used to be K-LIN with its LayerNorm prologue: 546 us at B=32, T=1000 against 70 us for the same
+// FLOPs on K-GEMM, whose operands stream by TMA under double-buffered accumulators: profiles/r02_notes.md.)
 static bool ffn_wide_ok(const smx_ffn_weights* w) {
   const int D = w->w1.in_dim, F = w->w1.out_dim;
   if (w->w1.n_split > 1 || w->w2.n_split > 1 || w->w2.in_dim != F || w->w2.out_dim != D) return false;
   if (!w->w1.w || !w->w1.b || !w->w2.w || !w->w2.b || !w->ln_w || !w->ln_b) return false;
-  return D > 256 && tc_linear_supported(D, F) && tc_gemm_supported(F, D);
+  return D > 256 && tc_gemm_supported(D, F) && tc_gemm_supported(F, D);
 }
 bool tc_ffn_supported(const smx_ffn_weights* w) { return ffn_fused_ok(w) || ffn_wide_ok(w); }
 size_t tc_ffn_packed_bytes(const smx_ffn_weights* w) {
   if (!tc_ffn_supported(w)) return 0;
-  if (ffn_wide_ok(w)) return align_up(tc_linear_packed_bytes(w->w1.in_dim, w->w1.out_dim), 1024) + align_up((size_t)w->w2.out_dim * w->w2.in_dim * 2, 1024);
+  if (ffn_wide_ok(w)) return 2 * align_up((size_t)w->w2.out_dim * w->w2.in_dim * 2, 1024);  // dense bf16 W1 | W2
   if (tc_ffn3_supported(w)) return tc_ffn3_packed_bytes(w);
   if (tc_ffn2_supported(w)) return tc_ffn2_packed_bytes(w);
   return (size_t)(w->w1.out_dim / FFN_HC) * ffn_stage_bytes(w->w1.in_dim);
@@ -360,8 +362,8 @@ __global__ void ffn_pack_kernel(const float* w1, const float* w2, int D, int F, 
 int tc_ffn_pack(const smx_ffn_weights* w, void* packed, cudaStream_t st) {
   if (!tc_ffn_supported(w)) return fail(SMX_ERR_UNSUPPORTED, "ffn configuration not handled by the tensor-core arm");
   if (ffn_wide_ok(w)) {
-    SMX_TRY(tc_pack_linear(w->w1, 0, w->w1.in_dim, 0, packed, st));
-    return tc_dense_bf16(w->w2, 0, w->w2.in_dim, (char*)packed + align_up(tc_linear_packed_bytes(w->w1.in_dim, w->w1.out_dim), 1024), st);
+    SMX_TRY(tc_dense_bf16(w->w1, 0, w->w1.in_dim, packed, st));
+    return tc_dense_bf16(w->w2, 0, w->w2.in_dim, (char*)packed + align_up((size_t)w->w1.out_dim * w->w1.in_dim * 2, 1024), st);
   }
   if (tc_ffn3_supported(w)) return tc_ffn3_pack(w, packed, st);
   if (tc_ffn2_supported(w)) return tc_ffn2_pack(w, packed, st);
@@ -374,7 +376,7 @@ int tc_ffn_pack(const smx_ffn_weights* w, void* packed, cudaStream_t st) {
 }
 
 size_t tc_ffn_workspace_bytes(const smx_ffn_weights* w, int64_t rows) {
-  return ffn_wide_ok(w) ? align_up((size_t)rows * w->w1.out_dim * 2) : 0;  // the fused kernels need no scratch
+  return ffn_wide_ok(w) ? align_up((size_t)rows * w->w1.out_dim * 2) + align_up((size_t)rows * w->w1.in_dim * 2) : 0;  // the fused kernels need no scratch
 }
 
 int tc_ffn_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t rows, const __nv_bfloat16* x,
@@ -383,17 +385,18 @@ int tc_ffn_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t ro
     const int D = w->w1.in_dim, F = w->w1.out_dim;
     const size_t m0 = ws.mark();
     __nv_bfloat16* h = (__nv_bfloat16*)ws.take((size_t)rows * F * 2);
-    if (!h) return fail(SMX_ERR_WORKSPACE, "workspace too small (wide FFN)");
+    __nv_bfloat16* xn = (__nv_bfloat16*)ws.take((size_t)rows * D * 2);
+    if (!h || !xn) return fail(SMX_ERR_WORKSPACE, "workspace too small (wide FFN)");
     if (!ws.dry) {
-      LinP p{};
-      p.rows = rows; p.T = 1; p.utt_tiles = 0; p.alpha = 1.0f; p.ln_eps = 1e-5f; p.oln_eps = 1e-5f;
-      p.x = x; p.ldx = D; p.K = D; p.N = F; p.wp = (const __nv_bfloat16*)packed; p.bias = w->w1.b;
-      p.ln_w = w->ln_w; p.ln_b = w->ln_b; p.act = act;
-      p.out = h; p.ldo = F;
-      SMX_TRY(tc_linear_launch(p, TC_LIN_PLAIN, st));                                   // Conformer.py:470-473
+      SMX_TRY(layernorm(x, SMX_BF16, D, w->ln_w, w->ln_b, 1e-5f, SMX_ACT_IDENTITY, xn, SMX_BF16, D, rows, D, st));  // Conformer.py:470
+      GemmTc g1{};
+      g1.a = xn; g1.lda = D; g1.M = rows; g1.N = F; g1.K = D;
+      g1.w = (const __nv_bfloat16*)packed;
+      g1.bias = w->w1.b; g1.act = act; g1.alpha = 1.0f; g1.out = h; g1.ldo = F;
+      SMX_TRY(tc_gemm_launch(g1, st));                                                  // :471-473
       GemmTc g{};
       g.a = h; g.lda = F; g.M = rows; g.N = D; g.K = F;
-      g.w = (const __nv_bfloat16*)((const char*)packed + align_up(tc_linear_packed_bytes(D, F), 1024));
+      g.w = (const __nv_bfloat16*)((const char*)packed + align_up((size_t)F * D * 2, 1024));
       g.bias = w->w2.b; g.act = SMX_ACT_IDENTITY; g.resid = x; g.ldr = D; g.alpha = 0.5f; g.out = y; g.ldo = D;
       SMX_TRY(tc_gemm_launch(g, st));                                                   // x + 0.5 * ffn(x), :518
       if (oln_w) SMX_TRY(layernorm(y, SMX_BF16, D, oln_w, oln_b, oln_eps, SMX_ACT_IDENTITY, y, SMX_BF16, D, rows, D, st));  // norm2, :547

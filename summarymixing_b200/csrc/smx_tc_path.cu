@@ -57,7 +57,18 @@ struct CellLayout {
   size_t local[SMX_MAX_BLOCKS], summary[SMX_MAX_BLOCKS], merge, total;
   size_t local_s[2], summary_s[2], merge_s;  // the same images in schedule order (K-SM v3)
   size_t v4;                                 // stream-order image + W_cs^T of K-SM v4 (0 bytes when v4 does not apply)
+  size_t local_d[SMX_MAX_BLOCKS], summary_d[SMX_MAX_BLOCKS], merge_d;  // dense (out, in) bf16 copies for K-GEMM (unfused full mode; 0 = not used)
+  int gemm;                                  // the unfused full-mode cell runs its plain linears on K-GEMM
 };
+// Unfused full-mode cells (conformer_large: D = 512) run every linear that needs no column-sum epilogue on K-GEMM (operands by
+// TMA, double-buffered accumulators; block-diagonal weights as dense with zero blocks): K-LIN took 160-180 us per 512 x 512
+// linear at B=32, T=1000, K-GEMM takes ~25 (profiles/r02_notes.md).
+static bool cell_gemm_ok(const smx_cell_weights* w) {
+  if (w->mode != SMX_MODE_FULL || tc_cellf_supported(w)) return false;
+  for (int i = 0; i < w->n_local; ++i) if (!tc_gemm_supported(w->local[i].in_dim, w->local[i].out_dim)) return false;
+  for (int i = 0; i + 1 < w->n_summary; ++i) if (!tc_gemm_supported(w->summary[i].in_dim, w->summary[i].out_dim)) return false;
+  return tc_gemm_supported(w->local_out_dim, w->merge.out_dim);
+}
 static CellLayout cell_layout(const smx_cell_weights* w) {
   CellLayout l{};
   size_t off = 0;
@@ -81,6 +92,12 @@ static CellLayout cell_layout(const smx_cell_weights* w) {
     for (int i = 0; i < 2; ++i) { l.summary_s[i] = off; off += align_up(tc_linear_packed_bytes(w->summary[i].in_dim, w->summary[i].out_dim)); }
     l.merge_s = off; off += align_up(tc_linear_packed_bytes(w->local_out_dim, w->merge.out_dim));
     l.v4 = off; off += align_up(tc_cell4_packed_bytes(w), 1024);
+  }
+  if (cell_gemm_ok(w)) {
+    l.gemm = 1;
+    for (int i = 0; i < w->n_local; ++i) { l.local_d[i] = off; off += align_up((size_t)w->local[i].in_dim * w->local[i].out_dim * 2, 1024); }
+    for (int i = 0; i + 1 < w->n_summary; ++i) { l.summary_d[i] = off; off += align_up((size_t)w->summary[i].in_dim * w->summary[i].out_dim * 2, 1024); }
+    l.merge_d = off; off += align_up((size_t)w->local_out_dim * w->merge.out_dim * 2, 1024);
   }
   l.total = off;
   return l;
@@ -120,6 +137,11 @@ int tc_cell_pack(const smx_cell_weights* w, void* packed, cudaStream_t st) {
   for (int i = 0; i < w->n_local; ++i) SMX_TRY(tc_pack_linear(w->local[i], 0, w->local[i].in_dim, 0, base + l.local[i], st));
   for (int i = 0; i < w->n_summary; ++i) SMX_TRY(tc_pack_linear(w->summary[i], 0, w->summary[i].in_dim, 0, base + l.summary[i], st));
   SMX_TRY(tc_pack_linear(w->merge, 0, w->local_out_dim, 0, base + l.merge, st));  // W_c[:, :D_l]
+  if (l.gemm) {
+    for (int i = 0; i < w->n_local; ++i) SMX_TRY(tc_dense_bf16(w->local[i], 0, w->local[i].in_dim, base + l.local_d[i], st));
+    for (int i = 0; i + 1 < w->n_summary; ++i) SMX_TRY(tc_dense_bf16(w->summary[i], 0, w->summary[i].in_dim, base + l.summary_d[i], st));
+    SMX_TRY(tc_dense_bf16(w->merge, 0, w->local_out_dim, base + l.merge_d, st));  // W_c[:, :D_l]
+  }
   return SMX_OK;
 }
 
@@ -178,7 +200,9 @@ __global__ void __launch_bounds__(256) cell_finalize_kernel(const float* __restr
     __syncthreads();
   }
   const int ldw = Dl + Ds;
-  for (int n = warp; n < Dout; n += 8) {  // one warp per output, lanes along k: coalesced weight rows
+  // one warp per output, lanes along k: coalesced weight rows; the outputs are split over gridDim.y blocks per utterance (each
+  // repeats the cheap mean / LayerNorm above): 32 blocks alone left the 512 x 512 GEMV at 111 us
+  for (int n = warp + 8 * blockIdx.y; n < Dout; n += 8 * gridDim.y) {
     const float* wr = Wc + (size_t)n * ldw + Dl;
     float acc = 0.0f;
     for (int k = lane; k < Ds; k += 32) acc = fmaf(wr[k], mu[k], acc);
@@ -239,7 +263,7 @@ int tc_add_bcast(const __nv_bfloat16* a, const __nv_bfloat16* s, int64_t rows, i
 }
 
 struct CellWs {
-  __nv_bfloat16 *h, *L;
+  __nv_bfloat16 *h, *L, *xn;
   float *colsum, *rowbias;
 };
 static int cell_ws(const smx_cell_weights* w, int B, int T, Arena& ws, CellWs& o) {
@@ -265,7 +289,8 @@ static int cell_ws(const smx_cell_weights* w, int B, int T, Arena& ws, CellWs& o
   o.L = (__nv_bfloat16*)ws.take((size_t)rows * w->local_out_dim * 2);
   o.colsum = ws.f32((size_t)B * tpu * w->summary_out_dim);
   o.rowbias = ws.f32((size_t)B * w->merge.out_dim);
-  if (!o.h || !o.L || !o.colsum || !o.rowbias) return fail(SMX_ERR_WORKSPACE, "workspace too small (tc cell)");
+  o.xn = cell_gemm_ok(w) ? (__nv_bfloat16*)ws.take((size_t)rows * w->enc_dim * 2) : nullptr;  // norm1(x), shared by both branches
+  if (!o.h || !o.L || !o.colsum || !o.rowbias || (cell_gemm_ok(w) && !o.xn)) return fail(SMX_ERR_WORKSPACE, "workspace too small (tc cell)");
   return SMX_OK;
 }
 size_t tc_cell_workspace_bytes(const smx_cell_weights* w, int B, int T) {
@@ -359,7 +384,7 @@ int tc_cell_fwd(const smx_cell_weights* w, const void* packed, int B, int T, con
         SMX_TRY(tc_linear_launch(p, TC_LIN_COLSUM, st));
       }
       // mean (no LayerNorm in fast mode) and the summary's share of the combiner: c[b] = W_c[:, D_l:] mean + b_c   :278-281, 296-298
-      cell_finalize_kernel<<<B, 256, 0, st>>>(o.colsum, tpu, T, mask, Dl, Dl, w->merge.out_dim, nullptr, nullptr, w->merge.w, w->merge.b, o.rowbias);
+      cell_finalize_kernel<<<dim3(B, 8), 256, 0, st>>>(o.colsum, tpu, T, mask, Dl, Dl, w->merge.out_dim, nullptr, nullptr, w->merge.w, w->merge.b, o.rowbias);
       count_launch();
       SMX_TRY(check_launch("cell_finalize_kernel"));
       LinP p = lin_base(B, T);
@@ -395,17 +420,42 @@ int tc_cell_fwd(const smx_cell_weights* w, const void* packed, int B, int T, con
   for (int i = 0; i + 1 < w->n_summary; ++i) maxh = w->summary[i].out_dim > maxh ? w->summary[i].out_dim : maxh;
   __nv_bfloat16* hb[2] = {o.h, o.h + (size_t)rows * maxh};
   const int Dl = w->local_out_dim, Ds = w->summary_out_dim, Dout = w->merge.out_dim;
+  const bool use_gemm = l.gemm != 0;
+  auto gemm_lin = [&](const smx_linear& L, const void* wd, int K, const __nv_bfloat16* a, int64_t lda, int act_code, const uint8_t* rowmask,
+                      const float* rowbias, const __nv_bfloat16* resid, bool with_bias, __nv_bfloat16* out) -> int {
+    GemmTc g{};
+    g.a = a; g.lda = lda; g.M = rows; g.N = L.out_dim; g.K = K;
+    g.w = (const __nv_bfloat16*)wd;
+    g.bias = with_bias ? L.b : nullptr;
+    g.rowbias = rowbias; g.rowbias_ld = L.out_dim; g.rows_per_group = T;
+    g.act = act_code; g.rowmask = rowmask;
+    g.resid = resid; g.ldr = L.out_dim; g.alpha = 1.0f;
+    g.out = out; g.ldo = L.out_dim;
+    return tc_gemm_launch(g, st);
+  };
+  const __nv_bfloat16* x_in = x;      // input of the first block of both branches
+  bool ln_in_kernel = true;           // ... normalised by the K-LIN prologue (else: already normalised)
+  if (use_gemm && pre_ln_w) {
+    SMX_TRY(layernorm(x, SMX_BF16, w->enc_dim, pre_ln_w, pre_ln_b, 1e-5f, SMX_ACT_IDENTITY, o.xn, SMX_BF16, w->enc_dim, rows, w->enc_dim, st));
+    x_in = o.xn;
+    ln_in_kernel = false;
+  }
 
   // ---- s(): summary branch -> masked column sums per tile                               :221, 229-231
   {
-    const __nv_bfloat16* cur = x; int64_t ld = w->enc_dim;
+    const __nv_bfloat16* cur = x_in; int64_t ld = w->enc_dim;
     for (int i = 0; i < w->n_summary; ++i) {
       const bool last = (i == w->n_summary - 1);
+      if (use_gemm && !last) {
+        SMX_TRY(gemm_lin(w->summary[i], pk + l.summary_d[i], w->summary[i].in_dim, cur, ld, w->act, nullptr, nullptr, nullptr, true, hb[i & 1]));
+        cur = hb[i & 1]; ld = w->summary[i].out_dim;
+        continue;
+      }
       LinP p = lin_base(B, T);
       p.x = cur; p.ldx = ld;
       lin_weight(p, w->summary[i], pk + l.summary[i], w->summary[i].in_dim);
       p.act = w->act;
-      if (i == 0) { p.ln_w = pre_ln_w; p.ln_b = pre_ln_b; }
+      if (i == 0 && ln_in_kernel) { p.ln_w = pre_ln_w; p.ln_b = pre_ln_b; }
       if (last) {
         p.rowmask = mask; p.colsum = o.colsum;
         SMX_TRY(tc_linear_launch(p, TC_LIN_COLSUM, st));
@@ -417,21 +467,29 @@ int tc_cell_fwd(const smx_cell_weights* w, const void* packed, int B, int T, con
     }
   }
   // ---- mean, LN_s, summary share of the combiner                                        :229-233, 248-253
-  cell_finalize_kernel<<<B, 256, 0, st>>>(o.colsum, (T + 127) / 128, T, mask, Ds, Dl, Dout,
+  cell_finalize_kernel<<<dim3(B, 8), 256, 0, st>>>(o.colsum, (T + 127) / 128, T, mask, Ds, Dl, Dout,
                                           w->use_layernorm ? w->summary_norm_w : nullptr,
                                           w->use_layernorm ? w->summary_norm_b : nullptr, w->merge.w, w->merge.b, o.rowbias);
   count_launch();
   SMX_TRY(check_launch("cell_finalize_kernel"));
   // ---- f(): local branch -> mask -> LN_l                                                :215-218
   {
-    const __nv_bfloat16* cur = x; int64_t ld = w->enc_dim;
+    const __nv_bfloat16* cur = x_in; int64_t ld = w->enc_dim;
     for (int i = 0; i < w->n_local; ++i) {
       const bool last = (i == w->n_local - 1);
+      if (use_gemm) {
+        __nv_bfloat16* dst = last ? o.L : hb[i & 1];
+        SMX_TRY(gemm_lin(w->local[i], pk + l.local_d[i], w->local[i].in_dim, cur, ld, w->act, last ? mask : nullptr, nullptr, nullptr, true, dst));
+        if (last && w->use_layernorm)
+          SMX_TRY(layernorm(o.L, SMX_BF16, Dl, w->local_norm_w, w->local_norm_b, 1e-5f, SMX_ACT_IDENTITY, o.L, SMX_BF16, Dl, rows, Dl, st));
+        cur = dst; ld = w->local[i].out_dim;
+        continue;
+      }
       LinP p = lin_base(B, T);
       p.x = cur; p.ldx = ld;
       lin_weight(p, w->local[i], pk + l.local[i], w->local[i].in_dim);
       p.act = w->act;
-      if (i == 0) { p.ln_w = pre_ln_w; p.ln_b = pre_ln_b; }
+      if (i == 0 && ln_in_kernel) { p.ln_w = pre_ln_w; p.ln_b = pre_ln_b; }
       if (last) {
         p.rowmask = mask; p.out = o.L; p.ldo = Dl;
         if (w->use_layernorm && Dl <= 256) {
@@ -450,7 +508,10 @@ int tc_cell_fwd(const smx_cell_weights* w, const void* packed, int B, int T, con
     }
   }
   // ---- combiner: y = act(W_c[:, :D_l] @ local + c[b]) (+ residual)                         :251-253
-  {
+  if (use_gemm) {
+    smx_linear mc = w->merge;  // (b_c is inside c[b])
+    SMX_TRY(gemm_lin(mc, pk + l.merge_d, Dl, o.L, Dl, w->act, nullptr, o.rowbias, residual, false, y));
+  } else {
     LinP p = lin_base(B, T);
     p.x = o.L; p.ldx = Dl;
     lin_weight(p, w->merge, pk + l.merge, Dl);
