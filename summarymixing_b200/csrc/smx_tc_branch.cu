@@ -23,7 +23,7 @@ static BranchLayout branch_layout(const smx_branchformer_layer_weights* w) {
   const smx_convbranch_weights& br = w->branch;
   const int D = br.pre.in_dim, U = br.pre.out_dim, H = U / 2, Dx1 = branch_dx1(w);
   size_t off = 0;
-  l.pre = off; off += align_up(tc_linear_packed_bytes(D, U), 1024);
+  l.pre = off; off += align_up((size_t)U * D * 2, 1024);   // dense (U, D) bf16 for K-GEMM
   l.post = off; off += align_up((size_t)D * H * 2, 1024);
   l.m0a = off; off += align_up((size_t)w->merge[0].out_dim * Dx1 * 2, 1024);   // first merge block, columns of x1 (kept for the full cell: dense cat GEMM uses m[0])
   l.m0b = off; off += align_up((size_t)w->merge[0].out_dim * D * 2, 1024);     // first merge block, columns of x2
@@ -39,7 +39,7 @@ bool tc_branchformer_supported(const smx_branchformer_layer_weights* w, int has_
   if (!br.pre.w || !br.pre.b || !br.post.w || !br.post.b || br.pre.n_split > 1 || br.post.n_split > 1) return false;
   if (br.csgu_linear.w) return false;                        // use_linear_after_conv: not on this arm
   if (br.kernel_size != 31 || H % 64) return false;
-  if (!tc_linear_supported(D, U) || !tc_gemm_supported(H, D)) return false;
+  if (!tc_gemm_supported(D, U) || !tc_gemm_supported(H, D)) return false;
   if (!w->cell.packed || !tc_cell_supported(&w->cell, has_sum_mask)) return false;
   if (w->cell.mode != SMX_MODE_LITE && w->cell.mode != SMX_MODE_FULL && w->cell.mode != SMX_MODE_FAST) return false;
   const int Dx1 = branch_dx1(w);
@@ -62,7 +62,7 @@ int tc_branchformer_pack(const smx_branchformer_layer_weights* w, void* packed, 
   const smx_convbranch_weights& br = w->branch;
   const int D = br.pre.in_dim, Dx1 = branch_dx1(w);
   char* base = (char*)packed;
-  SMX_TRY(tc_pack_linear(br.pre, 0, D, 0, base + l.pre, st));
+  SMX_TRY(tc_dense_bf16(br.pre, 0, D, base + l.pre, st));
   SMX_TRY(tc_dense_bf16(br.post, 0, br.post.in_dim, base + l.post, st));
   SMX_TRY(tc_dense_bf16(w->merge[0], 0, Dx1, base + l.m0a, st));
   SMX_TRY(tc_dense_bf16(w->merge[0], Dx1, D, base + l.m0b, st));
@@ -78,7 +78,7 @@ __global__ void __launch_bounds__(256) branch_rowbias_kernel(const __nv_bfloat16
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int k = threadIdx.x; k < Dx1; k += 256) sx[k] = __bfloat162float(x1[(size_t)b * Dx1 + k]);
   __syncthreads();
-  for (int n = warp; n < N; n += 8) {
+  for (int n = warp + 8 * blockIdx.y; n < N; n += 8 * gridDim.y) {  // (outputs split over gridDim.y blocks per utterance)
     const float* wr = W + (size_t)n * ldw;
     float acc = 0.0f;
     for (int k = lane; k < Dx1; k += 32) acc = fmaf(wr[k], sx[k], acc);
@@ -111,15 +111,15 @@ int tc_branchformer_layer_fwd(const smx_branchformer_layer_weights* w, int B, in
   SMX_TRY(tc_cell_fwd(&w->cell, w->cell.packed, B, T, x, w->norm_mhsa_w, w->norm_mhsa_b, mask, nullptr, x1, ws, st));
   if (ws.dry) { ws.release(m0); return SMX_OK; }
   // branch 2: u = act(LN_conv(x) W_pre^T + b)   (no mask on this branch, :276)                    :292, 86-90
+  // (LayerNorm as its own pass into the idle merge buffer, then K-GEMM: the K-LIN kernel with its LayerNorm prologue took 543 us
+  // for this D -> 3072 projection at B=32, T=1000, K-GEMM takes ~100)
   {
-    LinP p{};
-    p.rows = rows; p.T = T; p.utt_tiles = 0; p.alpha = 1.0f; p.ln_eps = 1e-5f; p.oln_eps = 1e-5f;
-    p.x = x; p.ldx = D;
-    p.K = D; p.N = U; p.wp = (const __nv_bfloat16*)(pk + l.pre); p.bias = br.pre.b;
-    p.ln_w = w->norm_conv_w; p.ln_b = w->norm_conv_b;
-    p.act = br.act;
-    p.out = u; p.ldo = U;
-    SMX_TRY(tc_linear_launch(p, TC_LIN_PLAIN, st));
+    __nv_bfloat16* xn = hb;
+    SMX_TRY(layernorm(x, SMX_BF16, D, w->norm_conv_w, w->norm_conv_b, 1e-5f, SMX_ACT_IDENTITY, xn, SMX_BF16, D, rows, D, st));
+    GemmTc gp{};
+    gp.a = xn; gp.lda = D; gp.M = rows; gp.N = U; gp.K = D; gp.w = (const __nv_bfloat16*)(pk + l.pre); gp.bias = br.pre.b;
+    gp.act = br.act; gp.alpha = 1.0f; gp.out = u; gp.ldo = U;
+    SMX_TRY(tc_gemm_launch(gp, st));
   }
   SMX_TRY(tc_csgu_fwd(u, B, T, H, br.csgu_ln_w, br.csgu_ln_b, br.csgu_dw_w, br.csgu_dw_b, br.kernel_size, br.gate_act, g, H, stats, st));
   __nv_bfloat16* x2 = lite ? cat : cat + Dx1;
@@ -135,7 +135,7 @@ int tc_branchformer_layer_fwd(const smx_branchformer_layer_weights* w, int B, in
   GemmTc gm{};
   gm.M = rows; gm.alpha = 1.0f; gm.act = w->act;
   if (lite) {
-    branch_rowbias_kernel<<<B, 256, 0, st>>>(x1, Dx1, w->merge[0].w, w->merge[0].in_dim, w->merge[0].b, w->merge[0].out_dim, rowbias);
+    branch_rowbias_kernel<<<dim3(B, 8), 256, 0, st>>>(x1, Dx1, w->merge[0].w, w->merge[0].in_dim, w->merge[0].b, w->merge[0].out_dim, rowbias);
     count_launch();
     SMX_TRY(check_launch("branch_rowbias_kernel"));
     gm.a = x2; gm.lda = ldx2; gm.K = D; gm.w = (const __nv_bfloat16*)(pk + l.m0b);

@@ -66,14 +66,23 @@ struct CellLayout {
 static bool cell_gemm_ok(const smx_cell_weights* w) {
   if (w->mode != SMX_MODE_FULL || tc_cellf_supported(w)) return false;
   for (int i = 0; i < w->n_local; ++i) if (!tc_gemm_supported(w->local[i].in_dim, w->local[i].out_dim)) return false;
-  for (int i = 0; i + 1 < w->n_summary; ++i) if (!tc_gemm_supported(w->summary[i].in_dim, w->summary[i].out_dim)) return false;
+  for (int i = 0; i < w->n_summary; ++i) if (!tc_gemm_supported(w->summary[i].in_dim, w->summary[i].out_dim)) return false;
   return tc_gemm_supported(w->local_out_dim, w->merge.out_dim);
+}
+static bool lite_gemm_ok(const smx_cell_weights* w) {
+  if (w->mode != SMX_MODE_LITE || w->n_summary < 2 || w->enc_dim <= 256) return false;
+  for (int i = 0; i < w->n_summary; ++i) if (!tc_gemm_supported(w->summary[i].in_dim, w->summary[i].out_dim)) return false;
+  return true;
 }
 static CellLayout cell_layout(const smx_cell_weights* w) {
   CellLayout l{};
   size_t off = 0;
   if (w->mode == SMX_MODE_LITE) {
     for (int i = 0; i < w->n_summary; ++i) { l.summary[i] = off; off += align_up(tc_linear_packed_bytes(w->summary[i].in_dim, w->summary[i].out_dim)); }
+    if (lite_gemm_ok(w)) {  // every block but the last (column-sum epilogue) on K-GEMM
+      l.gemm = 1;
+      for (int i = 0; i < w->n_summary; ++i) { l.summary_d[i] = off; off += align_up((size_t)w->summary[i].in_dim * w->summary[i].out_dim * 2, 1024); }
+    }
     l.total = off;
     return l;
   }
@@ -96,7 +105,7 @@ static CellLayout cell_layout(const smx_cell_weights* w) {
   if (cell_gemm_ok(w)) {
     l.gemm = 1;
     for (int i = 0; i < w->n_local; ++i) { l.local_d[i] = off; off += align_up((size_t)w->local[i].in_dim * w->local[i].out_dim * 2, 1024); }
-    for (int i = 0; i + 1 < w->n_summary; ++i) { l.summary_d[i] = off; off += align_up((size_t)w->summary[i].in_dim * w->summary[i].out_dim * 2, 1024); }
+    for (int i = 0; i < w->n_summary; ++i) { l.summary_d[i] = off; off += align_up((size_t)w->summary[i].in_dim * w->summary[i].out_dim * 2, 1024); }
     l.merge_d = off; off += align_up((size_t)w->local_out_dim * w->merge.out_dim * 2, 1024);
   }
   l.total = off;
@@ -110,6 +119,7 @@ int tc_cell_pack(const smx_cell_weights* w, void* packed, cudaStream_t st) {
   char* base = (char*)packed;
   if (w->mode == SMX_MODE_LITE) {
     for (int i = 0; i < w->n_summary; ++i) SMX_TRY(tc_pack_linear(w->summary[i], 0, w->summary[i].in_dim, 0, base + l.summary[i], st));
+    if (l.gemm) for (int i = 0; i < w->n_summary; ++i) SMX_TRY(tc_dense_bf16(w->summary[i], 0, w->summary[i].in_dim, base + l.summary_d[i], st));
     return SMX_OK;
   }
   if (w->mode == SMX_MODE_FAST) {
@@ -139,7 +149,7 @@ int tc_cell_pack(const smx_cell_weights* w, void* packed, cudaStream_t st) {
   SMX_TRY(tc_pack_linear(w->merge, 0, w->local_out_dim, 0, base + l.merge, st));  // W_c[:, :D_l]
   if (l.gemm) {
     for (int i = 0; i < w->n_local; ++i) SMX_TRY(tc_dense_bf16(w->local[i], 0, w->local[i].in_dim, base + l.local_d[i], st));
-    for (int i = 0; i + 1 < w->n_summary; ++i) SMX_TRY(tc_dense_bf16(w->summary[i], 0, w->summary[i].in_dim, base + l.summary_d[i], st));
+    for (int i = 0; i < w->n_summary; ++i) SMX_TRY(tc_dense_bf16(w->summary[i], 0, w->summary[i].in_dim, base + l.summary_d[i], st));
     SMX_TRY(tc_dense_bf16(w->merge, 0, w->local_out_dim, base + l.merge_d, st));  // W_c[:, :D_l]
   }
   return SMX_OK;
@@ -262,6 +272,25 @@ int tc_add_bcast(const __nv_bfloat16* a, const __nv_bfloat16* s, int64_t rows, i
   return check_launch("add_bcast_bf16_kernel");
 }
 
+// per-tile column sums of S (B, T, Ds) bf16 (already masked): out[b][tile][d] = sum over the tile's frames, in frame order
+// (the K-GEMM arm of the unfused cells: K-LIN's fused column-sum epilogue cost 165 us for a 512 x 512 block, K-GEMM + this ~40)
+__global__ void __launch_bounds__(256) colsum_tiles_kernel(const __nv_bfloat16* __restrict__ S, int T, int Ds, int tpu, float* __restrict__ out) {
+  const int b = blockIdx.y, tile = blockIdx.x, t0 = tile * 128;
+  const int nrows = T - t0 < 128 ? T - t0 : 128;
+  for (int d2 = threadIdx.x; d2 < Ds / 2; d2 += 256) {
+    const __nv_bfloat162* p = reinterpret_cast<const __nv_bfloat162*>(S + ((size_t)b * T + t0) * Ds) + d2;
+    float2 acc = make_float2(0.0f, 0.0f);
+    for (int r = 0; r < nrows; ++r) { const float2 v = __bfloat1622float2(p[(size_t)r * (Ds / 2)]); acc.x += v.x; acc.y += v.y; }
+    *reinterpret_cast<float2*>(out + ((size_t)b * tpu + tile) * Ds + 2 * d2) = acc;
+  }
+}
+static int colsum_tiles(const __nv_bfloat16* S, int B, int T, int Ds, float* out, cudaStream_t st) {
+  const int tpu = (T + 127) / 128;
+  colsum_tiles_kernel<<<dim3(tpu, B), 256, 0, st>>>(S, T, Ds, tpu, out);
+  count_launch();
+  return check_launch("colsum_tiles_kernel");
+}
+
 struct CellWs {
   __nv_bfloat16 *h, *L, *xn;
   float *colsum, *rowbias;
@@ -272,17 +301,20 @@ static int cell_ws(const smx_cell_weights* w, int B, int T, Arena& ws, CellWs& o
     const int tpu = (T + 127) / 128;
     int maxh = 1;
     for (int i = 0; i + 1 < w->n_summary; ++i) maxh = w->summary[i].out_dim > maxh ? w->summary[i].out_dim : maxh;
+    if (lite_gemm_ok(w)) maxh = w->summary_out_dim > maxh ? w->summary_out_dim : maxh;  // S itself makes a round trip on the K-GEMM arm
     const int Dsum = w->mode == SMX_MODE_LITE ? w->summary_out_dim : w->local_out_dim;
     o.h = (__nv_bfloat16*)ws.take((size_t)rows * maxh * 2 * 2);
     o.L = (__nv_bfloat16*)ws.take(w->mode == SMX_MODE_FAST ? (size_t)rows * w->local_out_dim * 2 : 16);
     o.colsum = ws.f32((size_t)B * tpu * Dsum);
     o.rowbias = ws.f32((size_t)B * (w->mode == SMX_MODE_FAST ? w->merge.out_dim : 1));
-    if (!o.h || !o.L || !o.colsum || !o.rowbias) return fail(SMX_ERR_WORKSPACE, "workspace too small (tc cell lite/fast)");
+    o.xn = lite_gemm_ok(w) ? (__nv_bfloat16*)ws.take((size_t)rows * w->enc_dim * 2) : nullptr;
+    if (!o.h || !o.L || !o.colsum || !o.rowbias || (lite_gemm_ok(w) && !o.xn)) return fail(SMX_ERR_WORKSPACE, "workspace too small (tc cell lite/fast)");
     return SMX_OK;
   }
   int maxh = 0;
   for (int i = 0; i + 1 < w->n_local; ++i) maxh = w->local[i].out_dim > maxh ? w->local[i].out_dim : maxh;
   for (int i = 0; i + 1 < w->n_summary; ++i) maxh = w->summary[i].out_dim > maxh ? w->summary[i].out_dim : maxh;
+  if (cell_gemm_ok(w)) maxh = w->summary_out_dim > maxh ? w->summary_out_dim : maxh;  // S itself makes a round trip on the K-GEMM arm
   const int tpu = (T + 127) / 128;
   // two hidden buffers (ping-pong through the MLP chain) + L
   o.h = (__nv_bfloat16*)ws.take((size_t)rows * (maxh > 0 ? maxh : 1) * 2 * 2);
@@ -340,15 +372,33 @@ int tc_cell_fwd(const smx_cell_weights* w, const void* packed, int B, int T, con
       // s(x) * mask -> per-tile column sums (fused epilogue of the last block) -> mean over valid frames        :318-322
       int maxh = 1;
       for (int i = 0; i + 1 < w->n_summary; ++i) maxh = w->summary[i].out_dim > maxh ? w->summary[i].out_dim : maxh;
+      if (l.gemm) maxh = Ds > maxh ? Ds : maxh;
       __nv_bfloat16* hb[2] = {o.h, o.h + (size_t)rows * maxh};
       const __nv_bfloat16* cur = x; int64_t ld = w->enc_dim;
+      bool ln_in_kernel = true;
+      if (l.gemm && pre_ln_w) {  // LayerNorm as its own pass, then K-GEMM for every block but the last
+        SMX_TRY(layernorm(x, SMX_BF16, w->enc_dim, pre_ln_w, pre_ln_b, 1e-5f, SMX_ACT_IDENTITY, o.xn, SMX_BF16, w->enc_dim, rows, w->enc_dim, st));
+        cur = o.xn;
+        ln_in_kernel = false;
+      }
       for (int i = 0; i < w->n_summary; ++i) {
         const bool last = (i == w->n_summary - 1);
+        if (l.gemm) {
+          GemmTc g{};
+          g.a = cur; g.lda = ld; g.M = rows; g.N = w->summary[i].out_dim; g.K = w->summary[i].in_dim;
+          g.w = (const __nv_bfloat16*)(pk + l.summary_d[i]); g.bias = w->summary[i].b; g.act = w->act; g.alpha = 1.0f;
+          g.rowmask = last ? mask : nullptr;
+          g.out = hb[i & 1]; g.ldo = g.N;
+          SMX_TRY(tc_gemm_launch(g, st));
+          cur = g.out; ld = g.ldo;
+          if (last) SMX_TRY(colsum_tiles(cur, B, T, Ds, o.colsum, st));
+          continue;
+        }
         LinP p = lin_base(B, T);
         p.x = cur; p.ldx = ld;
         lin_weight(p, w->summary[i], pk + l.summary[i], w->summary[i].in_dim);
         p.act = w->act;
-        if (i == 0) { p.ln_w = pre_ln_w; p.ln_b = pre_ln_b; }
+        if (i == 0 && ln_in_kernel) { p.ln_w = pre_ln_w; p.ln_b = pre_ln_b; }
         if (last) {
           p.rowmask = mask; p.colsum = o.colsum;
           SMX_TRY(tc_linear_launch(p, TC_LIN_COLSUM, st));
@@ -418,6 +468,7 @@ int tc_cell_fwd(const smx_cell_weights* w, const void* packed, int B, int T, con
   int maxh = 1;
   for (int i = 0; i + 1 < w->n_local; ++i) maxh = w->local[i].out_dim > maxh ? w->local[i].out_dim : maxh;
   for (int i = 0; i + 1 < w->n_summary; ++i) maxh = w->summary[i].out_dim > maxh ? w->summary[i].out_dim : maxh;
+  if (l.gemm) maxh = w->summary_out_dim > maxh ? w->summary_out_dim : maxh;
   __nv_bfloat16* hb[2] = {o.h, o.h + (size_t)rows * maxh};
   const int Dl = w->local_out_dim, Ds = w->summary_out_dim, Dout = w->merge.out_dim;
   const bool use_gemm = l.gemm != 0;
@@ -446,9 +497,10 @@ int tc_cell_fwd(const smx_cell_weights* w, const void* packed, int B, int T, con
     const __nv_bfloat16* cur = x_in; int64_t ld = w->enc_dim;
     for (int i = 0; i < w->n_summary; ++i) {
       const bool last = (i == w->n_summary - 1);
-      if (use_gemm && !last) {
-        SMX_TRY(gemm_lin(w->summary[i], pk + l.summary_d[i], w->summary[i].in_dim, cur, ld, w->act, nullptr, nullptr, nullptr, true, hb[i & 1]));
+      if (use_gemm) {
+        SMX_TRY(gemm_lin(w->summary[i], pk + l.summary_d[i], w->summary[i].in_dim, cur, ld, w->act, last ? mask : nullptr, nullptr, nullptr, true, hb[i & 1]));
         cur = hb[i & 1]; ld = w->summary[i].out_dim;
+        if (last) SMX_TRY(colsum_tiles(cur, B, T, Ds, o.colsum, st));
         continue;
       }
       LinP p = lin_base(B, T);
