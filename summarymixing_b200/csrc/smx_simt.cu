@@ -164,9 +164,70 @@ __global__ void __launch_bounds__(256) ln_kernel(const void* x, int x_dt, int64_
   }
 }
 
+// bf16 -> bf16 rows of D = 256 NCH elements: one warp per row, the row held in registers (128-bit loads and stores, one pass over
+// memory; two-pass statistics like the generic kernel).  The generic kernel's 2-byte accesses and three passes ran at 1.7 TB/s
+// (38 us for 32 000 x 512), a fifth of the D = 512 layers' time.
+template <int NCH>
+__global__ void __launch_bounds__(256) ln_bf16_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                                                           const float* __restrict__ b, float eps, int act, __nv_bfloat16* __restrict__ y,
+                                                           int64_t ldy, int64_t rows) {
+  const int64_t row = (int64_t)blockIdx.x * 8 + threadIdx.x / 32;
+  const int lane = threadIdx.x % 32;
+  if (row >= rows) return;
+  float v[NCH][8];
+  float s = 0.0f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const uint4 raw = *reinterpret_cast<const uint4*>(x + row * ldx + (c * 32 + lane) * 8);
+    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[c][2 * e] = f.x; v[c][2 * e + 1] = f.y; s += f.x + f.y; }
+  }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+  const float mean = s / (float)(NCH * 256);
+  float q = 0.0f;
+#pragma unroll
+  for (int c = 0; c < NCH; ++c)
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { const float d = v[c][e] - mean; q = fmaf(d, d, q); }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+  const float rstd = 1.0f / sqrtf(q / (float)(NCH * 256) + eps);
+#pragma unroll
+  for (int c = 0; c < NCH; ++c) {
+    const int col = (c * 32 + lane) * 8;
+    const float4 w0 = *reinterpret_cast<const float4*>(w + col), w1 = *reinterpret_cast<const float4*>(w + col + 4);
+    const float4 b0 = *reinterpret_cast<const float4*>(b + col), b1 = *reinterpret_cast<const float4*>(b + col + 4);
+    const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+    float o[8];
+#pragma unroll
+    for (int e = 0; e < 8; ++e) o[e] = apply_act(act, (v[c][e] - mean) * rstd * ww[e] + bb[e]);
+    uint4 out;
+    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&out);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) ho[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+    *reinterpret_cast<uint4*>(y + row * ldy + col) = out;
+  }
+}
+
 int layernorm(const void* x, int x_dtype, int64_t ldx, const float* w, const float* b, float eps, int act, void* y,
               int y_dtype, int64_t ldy, int64_t rows, int D, cudaStream_t st) {
   if (rows <= 0 || D <= 0) return fail(SMX_ERR_BAD_ARG, "layernorm: empty problem");
+  if (x_dtype == SMX_BF16 && y_dtype == SMX_BF16 && D % 256 == 0 && D <= 1024 && ldx % 8 == 0 && ldy % 8 == 0 &&
+      ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)w % 16 == 0) && ((uintptr_t)b % 16 == 0)) {
+    const unsigned grid = (unsigned)((rows + 7) / 8);
+    const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
+    __nv_bfloat16* yb = (__nv_bfloat16*)y;
+    switch (D / 256) {
+      case 1: ln_bf16_rows_kernel<1><<<grid, 256, 0, st>>>(xb, ldx, w, b, eps, act, yb, ldy, rows); break;
+      case 2: ln_bf16_rows_kernel<2><<<grid, 256, 0, st>>>(xb, ldx, w, b, eps, act, yb, ldy, rows); break;
+      case 3: ln_bf16_rows_kernel<3><<<grid, 256, 0, st>>>(xb, ldx, w, b, eps, act, yb, ldy, rows); break;
+      default: ln_bf16_rows_kernel<4><<<grid, 256, 0, st>>>(xb, ldx, w, b, eps, act, yb, ldy, rows); break;
+    }
+    count_launch();
+    return check_launch("ln_bf16_rows_kernel");
+  }
   ln_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(x, x_dtype, ldx, w, b, eps, act, y, y_dtype, ldy, rows, D);
   count_launch();
   return check_launch("ln_kernel");

@@ -509,9 +509,14 @@ __global__ void __launch_bounds__(256) csgu_kernel(const __nv_bfloat16* __restri
                                                    int H, __nv_bfloat16* __restrict__ out, int64_t ldo) {
   constexpr int PAD = (KS - 1) / 2, NIN = CS_FR + KS - 1;
   __shared__ float sG[NIN][CS_CH];
+  __shared__ float sW[CS_CH * KS];  // this block's taps, fetched with coalesced loads (per-thread rows 4 KS bytes apart throttled the load/store queue)
   const int b = blockIdx.z, t0 = blockIdx.x * CS_FR, c0 = blockIdx.y * CS_CH;
   const int tid = threadIdx.x;
   const int64_t ubase = (int64_t)b * T;
+  {
+    const int nch = H - c0 < CS_CH ? H - c0 : CS_CH;
+    for (int i = tid; i < nch * KS; i += 256) sW[i] = dw_w[(size_t)c0 * KS + i];
+  }
   for (int idx = tid; idx < NIN * (CS_CH / 8); idx += 256) {
     const int row = idx / (CS_CH / 8), ch = (idx % (CS_CH / 8)) * 8;
     int t = t0 - PAD + row;
@@ -540,7 +545,7 @@ __global__ void __launch_bounds__(256) csgu_kernel(const __nv_bfloat16* __restri
   if (c0 + c >= H) return;
   float w[KS];
 #pragma unroll
-  for (int j = 0; j < KS; ++j) w[j] = dw_w[(size_t)(c0 + c) * KS + j];
+  for (int j = 0; j < KS; ++j) w[j] = sW[c * KS + j];
   const float bias = dw_b ? dw_b[c0 + c] : 0.0f;
 #pragma unroll 1
   for (int fb = 0; fb < 2; ++fb) {   // two blocks of 8 frames

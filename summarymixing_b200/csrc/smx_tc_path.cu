@@ -725,13 +725,17 @@ __global__ void __launch_bounds__(256) dwconv_tiled_kernel(const __nv_bfloat16* 
     if (u >= 0 && u < T) val = *reinterpret_cast<const uint4*>(g + ((size_t)b * T + u) * D + ch * 8);
     *reinterpret_cast<uint4*>(sIn + (size_t)row * D + ch * 8) = val;
   }
+  // the D x K taps pass through the (still unused) output tile with coalesced loads: read per thread straight from global
+  // memory -- rows 4 K bytes apart between lanes -- they throttle the load/store queue (profiles/r02_notes.md)
+  for (int i = tid; i < D * K; i += 256) sOut[i] = dw_w[i];
   __syncthreads();
   {
     const int pairs = D / 2, pr = tid % pairs, fb0 = tid / pairs, nfbp = 256 / pairs;
     const int c0 = pr * 2;
     float w0[K], w1[K];
 #pragma unroll
-    for (int j = 0; j < K; ++j) { w0[j] = dw_w[(size_t)c0 * K + j]; w1[j] = dw_w[(size_t)(c0 + 1) * K + j]; }
+    for (int j = 0; j < K; ++j) { w0[j] = sOut[c0 * K + j]; w1[j] = sOut[(c0 + 1) * K + j]; }
+    __syncthreads();  // every thread holds its taps before the first output rows are written
     const float b0 = dw_b ? dw_b[c0] : 0.0f, b1 = dw_b ? dw_b[c0 + 1] : 0.0f;
     for (int fb = fb0; fb < DWT_FRAMES / 8; fb += nfbp) {
       float a0[8], a1[8];
