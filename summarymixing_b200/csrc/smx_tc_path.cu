@@ -613,6 +613,8 @@ int tc_convmod_pack(const smx_convmod_weights* w, void* packed, cudaStream_t st)
   }
   SMX_TRY(tc_pack_linear(w->bottleneck, 0, D, 1, packed, st));
   SMX_TRY(tc_pack_linear(w->out, 0, D, 0, (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)), st));
+  if (tc_gemm_supported(D, D))  // dense copy of the output linear for K-GEMM (in the area the fused path uses for its schedule-order images)
+    SMX_TRY(tc_dense_bf16(w->out, 0, D, (char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)) + align_up(tc_linear_packed_bytes(D, D)), st));
   return SMX_OK;
 }
 size_t tc_convmod_workspace_bytes(const smx_convmod_weights* w, int B, int T) {
@@ -851,7 +853,13 @@ int tc_convmod_fwd(const smx_convmod_weights* w, const void* packed, int act, in
   }
   // depthwise conv -> LN -> act                                                           :325, :331-332
   SMX_TRY(tc_dwconv_ln_act(g, w->dw_w, w->dw_b, w->after_ln_w, w->after_ln_b, act, B, T, D, w->kernel_size, c, st));
-  {  // Linear D -> D, * mask, + residual                                                  :332-338, :543
+  if (tc_gemm_supported(D, D)) {  // Linear D -> D, * mask, + residual on K-GEMM                            :332-338, :543
+    GemmTc gm{};
+    gm.a = c; gm.lda = D; gm.M = rows; gm.N = D; gm.K = D;
+    gm.w = (const __nv_bfloat16*)((const char*)packed + align_up(tc_linear_packed_bytes(D, 2 * D)) + align_up(tc_linear_packed_bytes(D, D)));
+    gm.bias = w->out.b; gm.act = SMX_ACT_IDENTITY; gm.rowmask = mask; gm.resid = residual; gm.ldr = D; gm.alpha = 1.0f; gm.out = y; gm.ldo = D;
+    SMX_TRY(tc_gemm_launch(gm, st));
+  } else {  // Linear D -> D, * mask, + residual                                           :332-338, :543
     LinP p = lin_base(B, T);
     p.utt_tiles = 0;
     p.x = c; p.ldx = D;
