@@ -1,6 +1,7 @@
-"""One encoder of BASELINE configs[2] / [3] dims with a few layers, run a few times (for ncu launch lists):
+"""One encoder of BASELINE configs[1] / [2] / [3] dims with a few layers, run a few times eagerly (for ncu launch lists: the
+last 5 x launches-per-forward launches of the process are the five timed forwards):
 
-    python tools/cfg_layer_run.py cfg3|cfg4 [layers] [B] [T]
+    python tools/cfg_layer_run.py cfg2|cfg3|cfg4 [layers] [B] [T]
 """
 import os
 import sys
@@ -16,13 +17,17 @@ B = int(sys.argv[3]) if len(sys.argv) > 3 else 32
 T = int(sys.argv[4]) if len(sys.argv) > 4 else 1000
 dev = "cuda:0"
 torch.manual_seed(3)
-if what == "cfg3":
+Dm = 256 if what == "cfg2" else 512
+if what == "cfg2":
+    enc = S.ConformerEncoder(NL, 256, 1024, 4, 31, attention_type="SummaryMixing", local_proj_hid_dim=[256], local_proj_out_dim=256,
+                             summary_hid_dim=[256], mode="SummaryMixing").eval().to(dev)
+elif what == "cfg3":
     enc = S.ConformerEncoder(NL, 512, 2048, 8, 31, attention_type="SummaryMixing", local_proj_hid_dim=[512], local_proj_out_dim=512,
                              summary_hid_dim=[512], mode="SummaryMixing").eval().to(dev)
 else:
     enc = S.BranchformerEncoder(NL, 512, 8, attention_type="SummaryMixing", csgu_linear_units=3072, local_proj_hid_dim=[512],
                                 local_proj_out_dim=512, summary_hid_dim=[512], summary_out_dim=512, mode="SummaryMixing-lite").eval().to(dev)
-x = torch.randn(B, T, 512, device=dev).to(torch.bfloat16)
+x = torch.randn(B, T, Dm, device=dev).to(torch.bfloat16)
 lens = torch.randint(T // 2, T + 1, (B,))
 lens[0] = T
 mask = (torch.arange(T)[None] < lens[:, None]).to(dev)

@@ -1,16 +1,21 @@
-"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel count, mean, share."""
+"""Summarise an `ncu --metrics gpu__time_duration.sum --csv` launch list: per-kernel count, mean, share.
+
+    python tools/ncu_launch_summary.py launches.csv [last N launches only]"""
 import collections
 import csv
 import sys
 
 
-def main(path):
+def main(path, last=0):
     rows = list(csv.reader(open(path)))
     hdr = next(i for i, r in enumerate(rows) if r and r[0] == "ID")
     h = rows[hdr]
     ki, vi = h.index("Kernel Name"), h.index("Metric Value")
     d = collections.defaultdict(list)
-    for r in rows[hdr + 1:]:
+    body = [r for r in rows[hdr + 1:] if len(r) > vi]
+    if last:  # only the last `last` launches (the timed steps: everything before is weight packing and warm-up)
+        body = body[-last:]
+    for r in body:
         if len(r) > vi:
             try:
                 d[r[ki].split("(")[0][:70]].append(float(r[vi].replace(",", "")))
@@ -23,4 +28,4 @@ def main(path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    main(sys.argv[1], int(sys.argv[2]) if len(sys.argv) > 2 else 0)
