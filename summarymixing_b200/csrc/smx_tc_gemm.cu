@@ -11,6 +11,7 @@
 // epilogue warps drain tile i while the tensor pipe works on tile i + 1.
 // Warp roles: 0 TMA producer | 1 MMA issuer | 2-9 epilogue (quadrant = warp % 4, column half = (warp - 2) / 4)
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "smx_tc.h"
 #include "smx_tc_common.cuh"
@@ -573,6 +574,121 @@ __global__ void __launch_bounds__(256) csgu_kernel(const __nv_bfloat16* __restri
   }
 }
 
+
+// ---- CSGU gate, second generation: 128 frames x 256 channels per block (halo overhead 158 / 128 instead of 62 / 32), normalised
+// gate rows staged as fp32 pairs, a thread owns one channel PAIR and blocks of eight frames: taps and accumulators in registers,
+// one packed fma.rn.f32x2 per tap and frame for both channels (the depthwise phase of K-CONV, smx_tc_conv.cu).  The first
+// generation (32 x 128 tiles, scalar FMAs) ran at 13 % of the fp32 rate: 329 us for 32 000 x 1536 -- a third of a
+// Branchformer-lite layer (profiles/r02_notes.md).
+constexpr int CS2_FR = 128, CS2_CH = 256, CS2_THREADS = 384;
+__device__ __forceinline__ float2 cs2_fma2(float2 a, float2 b, float2 c) {
+  unsigned long long d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(d)
+      : "l"(*reinterpret_cast<unsigned long long*>(&a)), "l"(*reinterpret_cast<unsigned long long*>(&b)),
+        "l"(*reinterpret_cast<unsigned long long*>(&c)));
+  return *reinterpret_cast<float2*>(&d);
+}
+template <int KS>
+__global__ void __launch_bounds__(CS2_THREADS, 1) csgu2_kernel(const __nv_bfloat16* __restrict__ u, const float2* __restrict__ stats,
+                                                               const float* __restrict__ ln_w, const float* __restrict__ ln_b,
+                                                               const float* __restrict__ dw_w, const float* __restrict__ dw_b, int gate_act,
+                                                               int T, int H, __nv_bfloat16* __restrict__ out, int64_t ldo) {
+  constexpr int PAD = (KS - 1) / 2, NIN = CS2_FR + KS - 1;
+  extern __shared__ __align__(16) uint8_t cs2_smem[];
+  float* sG = reinterpret_cast<float*>(cs2_smem);                 // [NIN][CS2_CH] normalised gate rows
+  float* sW = sG + (size_t)NIN * CS2_CH;                          // [CS2_CH][KS] taps, then (ln_w | ln_b) of the block's channels
+  float* sLw = sW + CS2_CH * KS;
+  float* sLb = sLw + CS2_CH;
+  const int b = blockIdx.z, t0 = blockIdx.x * CS2_FR, c0 = blockIdx.y * CS2_CH;
+  const int tid = threadIdx.x;
+  const int nch = H - c0 < CS2_CH ? H - c0 : CS2_CH;             // channels of this block (a multiple of 8)
+  const int64_t ubase = (int64_t)b * T;
+  for (int i = tid; i < nch * KS; i += CS2_THREADS) sW[i] = dw_w[(size_t)c0 * KS + i];
+  for (int i = tid; i < CS2_CH; i += CS2_THREADS) { sLw[i] = i < nch ? ln_w[c0 + i] : 0.0f; sLb[i] = i < nch ? ln_b[c0 + i] : 0.0f; }
+  __syncthreads();
+  // stage LN(gate) for frames [t0 - PAD, t0 + 128 + PAD) with reflect padding (F.pad(..., mode="reflect"): the edge is not repeated);
+  // four chunks per thread and round, all loads issued before the first is used (one block per SM: nothing else hides the latency)
+  for (int base = 0; base < NIN * (CS2_CH / 8); base += 4 * CS2_THREADS) {
+    uint4 raw[4];
+    float2 st[4];
+    bool ok[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx = base + k * CS2_THREADS + tid;
+      const int row = idx / (CS2_CH / 8), ch = (idx % (CS2_CH / 8)) * 8;
+      int t = t0 - PAD + row;
+      if (t < 0) t = -t;
+      if (t >= T) t = 2 * (T - 1) - t;
+      ok[k] = idx < NIN * (CS2_CH / 8) && t >= 0 && t < T && ch < nch;
+      if (ok[k]) {
+        st[k] = stats[ubase + t];
+        raw[k] = *reinterpret_cast<const uint4*>(u + (ubase + t) * (2 * (int64_t)H) + H + c0 + ch);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx = base + k * CS2_THREADS + tid;
+      if (idx >= NIN * (CS2_CH / 8)) continue;
+      const int row = idx / (CS2_CH / 8), ch = (idx % (CS2_CH / 8)) * 8;
+      float v[8];
+      if (ok[k]) {
+        const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[k]);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float2 f = __bfloat1622float2(h[e]);
+          v[2 * e] = fmaf(fmaf(f.x, st[k].x, st[k].y), sLw[ch + 2 * e], sLb[ch + 2 * e]);
+          v[2 * e + 1] = fmaf(fmaf(f.y, st[k].x, st[k].y), sLw[ch + 2 * e + 1], sLb[ch + 2 * e + 1]);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 8; ++e) v[e] = 0.0f;
+      }
+      float4* dst = reinterpret_cast<float4*>(sG + (size_t)row * CS2_CH + ch);
+      dst[0] = make_float4(v[0], v[1], v[2], v[3]);
+      dst[1] = make_float4(v[4], v[5], v[6], v[7]);
+    }
+  }
+  __syncthreads();
+  constexpr int pairs = CS2_CH / 2, nfbp = CS2_THREADS / pairs;  // 128 channel pairs, 3 frame-block groups
+  const int pr = tid % pairs, fb0 = tid / pairs, cc = pr * 2;
+  if (cc >= nch) return;
+  float2 w2[KS];
+#pragma unroll
+  for (int j = 0; j < KS; ++j) w2[j] = make_float2(sW[cc * KS + j], sW[(cc + 1) * KS + j]);
+  const float2 bias2 = make_float2(dw_b ? dw_b[c0 + cc] : 0.0f, dw_b ? dw_b[c0 + cc + 1] : 0.0f);
+#pragma unroll 1
+  for (int fb = fb0; fb < CS2_FR / 8; fb += nfbp) {
+    if (t0 + fb * 8 >= T) break;
+    float2 a[8];
+    uint32_t valr[8];  // the value half of the block's eight frames, requested before the convolution: the loads land under the FMAs
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      a[o] = bias2;
+      const int t = t0 + fb * 8 + o;
+      valr[o] = t < T ? *reinterpret_cast<const uint32_t*>(u + (ubase + t) * (2 * (int64_t)H) + c0 + cc) : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < KS + 7; ++i) {
+      const float2 x = *reinterpret_cast<const float2*>(sG + (size_t)(fb * 8 + i) * CS2_CH + cc);
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        const int j = i - o;
+        if (j >= 0 && j < KS) a[o] = cs2_fma2(w2[j], x, a[o]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const int t = t0 + fb * 8 + o;
+      if (t < T) {
+        const float2 val = __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&valr[o]));
+        *reinterpret_cast<__nv_bfloat162*>(out + (ubase + t) * ldo + c0 + cc) =
+            __floats2bfloat162_rn(tc::act_fast(gate_act, a[o].x) * val.x, tc::act_fast(gate_act, a[o].y) * val.y);
+      }
+    }
+  }
+}
+
 size_t tc_csgu_workspace_bytes(int64_t rows) { return align_up((size_t)rows * sizeof(float2)); }
 int tc_csgu_fwd(const __nv_bfloat16* u, int B, int T, int H, const float* ln_w, const float* ln_b, const float* dw_w, const float* dw_b,
                 int kernel_size, int gate_act, __nv_bfloat16* out, int64_t ldo, void* stats_ws, cudaStream_t st) {
@@ -582,6 +698,16 @@ int tc_csgu_fwd(const __nv_bfloat16* u, int B, int T, int H, const float* ln_w, 
   csgu_stats_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(u, rows, H, (float2*)stats_ws);
   count_launch();
   SMX_TRY(check_launch("csgu_stats_kernel"));
+  if (H % 8 == 0 && ldo % 2 == 0 && !getenv("SMX_CSGU_V1")) {
+    constexpr int NIN = CS2_FR + 30;
+    const size_t smem = ((size_t)NIN * CS2_CH + (size_t)CS2_CH * 31 + 2 * CS2_CH) * sizeof(float);
+    cudaError_t e = cudaFuncSetAttribute(csgu2_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(csgu2_kernel): %s", cudaGetErrorString(e));
+    dim3 grid2((T + CS2_FR - 1) / CS2_FR, (H + CS2_CH - 1) / CS2_CH, B);
+    csgu2_kernel<31><<<grid2, CS2_THREADS, smem, st>>>(u, (const float2*)stats_ws, ln_w, ln_b, dw_w, dw_b, gate_act, T, H, out, ldo);
+    count_launch();
+    return check_launch("csgu2_kernel");
+  }
   dim3 grid((T + CS_FR - 1) / CS_FR, (H + CS_CH - 1) / CS_CH, B);
   csgu_kernel<31><<<grid, 256, 0, st>>>(u, (const float2*)stats_ws, ln_w, ln_b, dw_w, dw_b, gate_act, T, H, out, ldo);
   count_launch();
