@@ -353,6 +353,33 @@ def test_host_pipeline_serves_host_batches():
         m(batches[0][0], src_key_padding_mask=batches[0][1])
 
 
+@pytest.mark.parametrize("B,T,launches", [(1, 16, 5), (2, 127, 5), (1, 129, 5), (5, 257, 5), (37, 300, 5), (148, 256, 5), (149, 256, 6), (40, 1000, 6)])
+def test_layer_edge_shapes_and_resident_kernel_limits(B, T, launches):
+    """Edge shapes of the D = 256 layer on the tensor-core arm against the fp32-math arm of the same library: fewer rows than one
+    tile (TMA boxes larger than the tensor), ragged last tiles, exactly two tiles per CTA (148 x 256 frames = 296 tiles) and one
+    tile more -- where the one-kernel cell and K-GLU v4 (<= two resident tiles per CTA) hand over to their multi-pass fallbacks
+    (the cell then takes two tensor-core launches)."""
+    torch.manual_seed(5)
+    D = 256
+    layer = S.ConformerEncoderLayer(D, 1024, 4, 31, attention_type="SummaryMixing", local_proj_hid_dim=[D], local_proj_out_dim=D,
+                                    summary_hid_dim=[D]).eval().to(DEV)
+    g = torch.Generator().manual_seed(B * 1000 + T)
+    x = torch.randn(B, T, D, generator=g)
+    lens = torch.randint(max(1, T // 2), T + 1, (B,), generator=g)
+    lens[0] = T
+    mask = (torch.arange(T)[None] < lens[:, None]).to(DEV)
+    with torch.no_grad():
+        y32 = layer(x.to(DEV), src_key_padding_mask=mask)[0]
+        t0 = L.lib().smx_tc_launch_count()
+        y16 = layer(x.to(torch.bfloat16).to(DEV), src_key_padding_mask=mask)[0].float()
+        n = L.lib().smx_tc_launch_count() - t0
+    torch.cuda.synchronize()
+    valid = mask.unsqueeze(-1)
+    rel = float(((y16 - y32) * valid).norm() / (y32 * valid).norm())
+    assert n == launches, n
+    assert torch.isfinite(y16).all() and rel < 1e-2, rel
+
+
 def test_16_byte_aligned_buffers_take_the_fallback_kernels():
     """The newest kernels move rows with 256-bit accesses and need 32-byte aligned activations; buffers that are only
     16-byte aligned (the C ABI's stated minimum) must still give the same answer through the fallbacks: first-generation
