@@ -171,43 +171,53 @@ template <int NCH>
 __global__ void __launch_bounds__(256) ln_bf16_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ w,
                                                            const float* __restrict__ b, float eps, int act, __nv_bfloat16* __restrict__ y,
                                                            int64_t ldy, int64_t rows) {
-  const int64_t row = (int64_t)blockIdx.x * 8 + threadIdx.x / 32;
+  constexpr int RPW = 2;  // rows per warp: both rows' loads are in flight before the first reduction
+  const int64_t row0 = ((int64_t)blockIdx.x * 8 + threadIdx.x / 32) * RPW;
   const int lane = threadIdx.x % 32;
-  if (row >= rows) return;
-  float v[NCH][8];
-  float s = 0.0f;
+  if (row0 >= rows) return;
+  uint4 raw[RPW][NCH];
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const uint4 raw = *reinterpret_cast<const uint4*>(x + row * ldx + (c * 32 + lane) * 8);
-    const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw);
+  for (int r = 0; r < RPW; ++r)
 #pragma unroll
-    for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[c][2 * e] = f.x; v[c][2 * e + 1] = f.y; s += f.x + f.y; }
-  }
+    for (int c = 0; c < NCH; ++c)
+      raw[r][c] = row0 + r < rows ? *reinterpret_cast<const uint4*>(x + (row0 + r) * ldx + (c * 32 + lane) * 8) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-  for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-  const float mean = s / (float)(NCH * 256);
-  float q = 0.0f;
+  for (int r = 0; r < RPW; ++r) {
+    if (row0 + r >= rows) break;
+    float v[NCH][8];
+    float s = 0.0f;
 #pragma unroll
-  for (int c = 0; c < NCH; ++c)
+    for (int c = 0; c < NCH; ++c) {
+      const __nv_bfloat162* h = reinterpret_cast<const __nv_bfloat162*>(&raw[r][c]);
 #pragma unroll
-    for (int e = 0; e < 8; ++e) { const float d = v[c][e] - mean; q = fmaf(d, d, q); }
+      for (int e = 0; e < 4; ++e) { const float2 f = __bfloat1622float2(h[e]); v[c][2 * e] = f.x; v[c][2 * e + 1] = f.y; s += f.x + f.y; }
+    }
 #pragma unroll
-  for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
-  const float rstd = 1.0f / sqrtf(q / (float)(NCH * 256) + eps);
+    for (int o = 16; o; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    const float mean = s / (float)(NCH * 256);
+    float q = 0.0f;
 #pragma unroll
-  for (int c = 0; c < NCH; ++c) {
-    const int col = (c * 32 + lane) * 8;
-    const float4 w0 = *reinterpret_cast<const float4*>(w + col), w1 = *reinterpret_cast<const float4*>(w + col + 4);
-    const float4 b0 = *reinterpret_cast<const float4*>(b + col), b1 = *reinterpret_cast<const float4*>(b + col + 4);
-    const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
-    float o[8];
+    for (int c = 0; c < NCH; ++c)
 #pragma unroll
-    for (int e = 0; e < 8; ++e) o[e] = apply_act(act, (v[c][e] - mean) * rstd * ww[e] + bb[e]);
-    uint4 out;
-    __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&out);
+      for (int e = 0; e < 8; ++e) { const float d = v[c][e] - mean; q = fmaf(d, d, q); }
 #pragma unroll
-    for (int e = 0; e < 4; ++e) ho[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
-    *reinterpret_cast<uint4*>(y + row * ldy + col) = out;
+    for (int o = 16; o; o >>= 1) q += __shfl_xor_sync(0xffffffffu, q, o);
+    const float rstd = 1.0f / sqrtf(q / (float)(NCH * 256) + eps);
+#pragma unroll
+    for (int c = 0; c < NCH; ++c) {
+      const int col = (c * 32 + lane) * 8;
+      const float4 w0 = *reinterpret_cast<const float4*>(w + col), w1 = *reinterpret_cast<const float4*>(w + col + 4);
+      const float4 b0 = *reinterpret_cast<const float4*>(b + col), b1 = *reinterpret_cast<const float4*>(b + col + 4);
+      const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float o[8];
+#pragma unroll
+      for (int e = 0; e < 8; ++e) o[e] = apply_act(act, (v[c][e] - mean) * rstd * ww[e] + bb[e]);
+      uint4 out;
+      __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&out);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) ho[e] = __floats2bfloat162_rn(o[2 * e], o[2 * e + 1]);
+      *reinterpret_cast<uint4*>(y + (row0 + r) * ldy + col) = out;
+    }
   }
 }
 
@@ -216,7 +226,7 @@ int layernorm(const void* x, int x_dtype, int64_t ldx, const float* w, const flo
   if (rows <= 0 || D <= 0) return fail(SMX_ERR_BAD_ARG, "layernorm: empty problem");
   if (x_dtype == SMX_BF16 && y_dtype == SMX_BF16 && D % 256 == 0 && D <= 1024 && ldx % 8 == 0 && ldy % 8 == 0 &&
       ((uintptr_t)x % 16 == 0) && ((uintptr_t)y % 16 == 0) && ((uintptr_t)w % 16 == 0) && ((uintptr_t)b % 16 == 0)) {
-    const unsigned grid = (unsigned)((rows + 7) / 8);
+    const unsigned grid = (unsigned)((rows + 15) / 16);  // 8 warps x 2 rows per block
     const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
     __nv_bfloat16* yb = (__nv_bfloat16*)y;
     switch (D / 256) {
