@@ -110,6 +110,8 @@ typedef struct {
   const void* packed;      /* bf16 operand image from smx_cell_pack(), or NULL (generic arm) */
   float decay_constant;    /* EXPDECAY (summary_mixing.py:158-161) */
   int32_t _pad;
+  const float* prenorm_w;  /* set by smx_cell_pack_prenorm(): the LayerNorm in front of the cell whose gamma / beta are folded */
+  const float* prenorm_b;  /* into `packed`; NULL = none.  Used only by calls that pass exactly these pointers as the pre-norm */
 } smx_cell_weights;
 
 /* ffn_module{1,2}: LayerNorm + PositionalwiseFeedForward (Conformer.py:470-484). */
@@ -197,6 +199,12 @@ SMX_API uint64_t smx_tc_launch_count(void);
  * fp32-math arm runs.  Pack once per weight set; `packed` must be 1024-byte aligned device memory. */
 SMX_API size_t smx_cell_packed_bytes(const smx_cell_weights* w);
 SMX_API int smx_cell_pack(const smx_cell_weights* w, void* packed, size_t packed_bytes, void* stream);
+/* Optional, after smx_cell_pack() and with w->packed set: folds the LayerNorm that precedes the cell in a Conformer layer (norm1,
+ * Conformer.py:520) into the image of the one-kernel cell -- gamma into the first blocks' weights, beta into their biases; the
+ * kernel then feeds the raw rows to the tensor cores and applies the two per-row statistics in its first epilogue.  Sets
+ * w->prenorm_w / w->prenorm_b (a no-op that leaves them NULL for configurations that kernel does not take).  smx_mixing_block_fwd /
+ * smx_conformer_layer_fwd use the folded image when called with exactly these norm parameters, the plain one otherwise. */
+SMX_API int smx_cell_pack_prenorm(smx_cell_weights* w, const float* norm_w, const float* norm_b, void* stream);
 SMX_API size_t smx_ffn_packed_bytes(const smx_ffn_weights* w);
 SMX_API int smx_ffn_pack(const smx_ffn_weights* w, void* packed, size_t packed_bytes, void* stream);
 SMX_API size_t smx_branchformer_packed_bytes(const smx_branchformer_layer_weights* w); /* w->cell.packed must be set first */

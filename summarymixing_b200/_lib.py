@@ -39,7 +39,7 @@ class CellWeights(C.Structure):
                 ("n_summary", C.c_int32), ("local", Linear * SMX_MAX_BLOCKS), ("summary", Linear * SMX_MAX_BLOCKS),
                 ("global_proj", Linear), ("merge", Linear), ("local_norm_w", fp), ("local_norm_b", fp),
                 ("summary_norm_w", fp), ("summary_norm_b", fp), ("packed", fp), ("decay_constant", C.c_float),
-                ("_pad", C.c_int32)]
+                ("_pad", C.c_int32), ("prenorm_w", fp), ("prenorm_b", fp)]
 
 
 class LinearGrad(C.Structure):
@@ -110,6 +110,7 @@ _PROTOS = {
     "smx_struct_size": (_sz, [_i]),
     "smx_cell_packed_bytes": (_sz, [C.POINTER(CellWeights)]),
     "smx_cell_pack": (_i, [C.POINTER(CellWeights), _vp, _sz, _vp]),
+    "smx_cell_pack_prenorm": (_i, [C.POINTER(CellWeights), fp, fp, _vp]),
     "smx_ffn_packed_bytes": (_sz, [C.POINTER(FFNWeights)]),
     "smx_ffn_pack": (_i, [C.POINTER(FFNWeights), _vp, _sz, _vp]),
     "smx_branchformer_packed_bytes": (_sz, [C.POINTER(BranchformerLayerWeights)]),

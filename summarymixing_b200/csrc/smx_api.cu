@@ -95,6 +95,11 @@ int smx_cell_pack(const smx_cell_weights* w, void* packed, size_t packed_bytes, 
   SMX_TRY(check_arch());
   return tc_cell_pack(w, packed, (cudaStream_t)stream);
 }
+int smx_cell_pack_prenorm(smx_cell_weights* w, const float* norm_w, const float* norm_b, void* stream) {
+  if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");
+  SMX_TRY(check_arch());
+  return tc_cell_pack_prenorm(w, norm_w, norm_b, (cudaStream_t)stream);
+}
 size_t smx_ffn_packed_bytes(const smx_ffn_weights* w) { return w ? tc_ffn_packed_bytes(w) : 0; }
 int smx_ffn_pack(const smx_ffn_weights* w, void* packed, size_t packed_bytes, void* stream) {
   if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");

@@ -96,6 +96,9 @@ int tc_cell3_fwd(const smx_cell_weights* w, const void* img_s1, const void* img_
                  const void* img_c, int B, int T, const __nv_bfloat16* x, const float* pre_ln_w, const float* pre_ln_b,
                  const uint8_t* mask, const __nv_bfloat16* residual, __nv_bfloat16* y, Arena& ws, cudaStream_t st);
 // smx_tc_glu4.cu: K-GLU v4 (D = 256, <= 2 row tiles per CTA): both tiles resident, one pass over the weights, LayerNorm folded
+bool tc_cell4_prenorm_ok(const smx_cell_weights* w);
+int tc_cell4_pack_prenorm(const smx_cell_weights* w, void* img, const float* norm_w, const float* norm_b, cudaStream_t st);
+int tc_cell_pack_prenorm(smx_cell_weights* w, const float* norm_w, const float* norm_b, cudaStream_t st);
 bool tc_glu4_supported(const smx_convmod_weights* w);
 bool tc_glu4_fits(int64_t rows);
 size_t tc_glu4_packed_bytes(const smx_convmod_weights* w);

@@ -64,7 +64,9 @@ struct C4P {
   C4Half hg[10];
   int n1s_h, n2s_h, n1f_h, n2f_h, dout_h;     // half widths of the five GEMM outputs
   int g2s_both, g2f_both;                     // GEMM 2 of a chain needs BOTH halves of H (dense second layer)
-  int res_in_x;                               // the residual tile is re-loaded (TMA) into the X buffer once GEMM 1 of the local branch has read it
+  int res_in_x;                               // 1: the residual tile is re-loaded (TMA) into the X buffer once GEMM 1 of the local branch has
+                                              // read it; 2: it is there already (FOLD: the X tile holds the raw rows, and the residual is x)
+  const float* gw1s; const float* gw1f;       // FOLD: gw[n] = sum_k bf16(gamma_k W[n,k]) of the first summary / local block (norm1 folded)
   const float* b_s1; const float* b_s2; const float* b_f1; const float* b_f2;
   int use_lnl;                                // local_norm is applied (folded: gamma into the combiner weights, beta into c[b], see E2 / E3)
   const float* gw;                            // [Dout] gw[n] = sum_k bf16(gamma_k W_c[n,k]) (zeros without LayerNorm)
@@ -216,7 +218,38 @@ static __device__ __noinline__ void c4_ln_rows(uint8_t* sX, int nrows, int D, in
   for (int i = 0; i < n_groups; ++i) tc::rows8_ln(sX, nrows, D, w0 + i, lane, sW, sB, sStat);
 }
 
-template <int ACT, bool STD>  // ACT >= 0: compile-time smx_act, -1: runtime p.act; STD: the standard cell's compile-time schedule
+// FOLD: norm1 is not applied to the tile.  gamma is folded into the packed first-block weights, beta into their biases
+// (tc_cell4_pack_prenorm), and E1 applies the two per-row scalars: LN(x) W^T = rstd (x (W gamma)^T - mean gw) + W beta.  Row
+// statistics of eight rows per call, four lanes per row (one K-block each; a quarter-warp covers eight different rows, so that the
+// 128-bit shared-memory reads are conflict-free under the swizzle), one pass shifted by the row's first element.
+static __device__ __noinline__ void c4_stats_rows8(const uint8_t* sX, int nkb, int w8, int lane, float2* sStat) {
+  const int row = w8 * 8 + (lane & 7), part = lane >> 3;
+  const uint8_t* rp = sX + row * 128;
+  const float x0 = __bfloat162float(*reinterpret_cast<const __nv_bfloat16*>(rp + ((row & 7) << 4)));
+  float2 s1 = make_float2(0.0f, 0.0f), s2 = make_float2(0.0f, 0.0f);
+  const float2 sh = make_float2(-x0, -x0);
+  for (int kb = part; kb < nkb; kb += 4) {
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+      const uint4 raw = *reinterpret_cast<const uint4*>(rp + (size_t)kb * kblock_bytes(128) + ((ch ^ (row & 7)) << 4));
+      float2 v[4];
+      tc::unpack_bf16x8_pairs(raw, v);
+#pragma unroll
+      for (int e = 0; e < 4; ++e) { const float2 d = tc::add2(v[e], sh); s1 = tc::add2(s1, d); s2 = tc::fma2(d, d, s2); }
+    }
+  }
+  float a = s1.x + s1.y, q = s2.x + s2.y;
+  a += __shfl_xor_sync(0xffffffffu, a, 8); q += __shfl_xor_sync(0xffffffffu, q, 8);
+  a += __shfl_xor_sync(0xffffffffu, a, 16); q += __shfl_xor_sync(0xffffffffu, q, 16);
+  if (part == 0) {
+    const float inv = 1.0f / (float)(nkb * 64);
+    const float m1 = a * inv;
+    const float rstd = rsqrtf(fmaxf(q * inv - m1 * m1, 0.0f) + 1e-5f);
+    sStat[row] = make_float2(rstd, -(x0 + m1) * rstd);
+  }
+}
+
+template <int ACT, bool STD, bool FOLD>  // ACT >= 0: compile-time smx_act, -1: runtime p.act; STD: the standard cell's compile-time schedule; FOLD: norm1 folded
 __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_r,
                                                               const __grid_constant__ CUtensorMap tmap_y, const C4P p) {
   extern __shared__ __align__(1024) uint8_t smem[];
@@ -230,7 +263,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
   __shared__ __align__(8) uint64_t full_bar[C4_SLOTS], empty_bar[C4_SLOTS];
   __shared__ __align__(8) uint64_t x_raw[C4_MAX_TILES], x_ready[C4_MAX_TILES];
   __shared__ __align__(8) uint64_t acc1_full[4], acc2_full[4], acc3_full[4], h_full[4], x_free[4], l_full[4];  // per quarter
-  __shared__ __align__(8) uint64_t x_dead[C4_MAX_TILES], r_full[C4_MAX_TILES], cb_full[C4_MAX_TILES], pub_bar;
+  __shared__ __align__(8) uint64_t x_dead[C4_MAX_TILES], r_full[C4_MAX_TILES], cb_full[C4_MAX_TILES], pub_bar, stat1_ready;
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -241,6 +274,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
 
   // this CTA's tiles: blockIdx.x and blockIdx.x + gridDim.x (the host guarantees n_tiles <= 2 gridDim.x)
   const int ntl = (int)blockIdx.x + (int)gridDim.x < p.n_tiles ? 2 : 1;
+  int n_early = 0;  // (producer thread) weight steps already issued by the set-up
   if (warp == C4_PROD_WARP) {
     tc::tmem_alloc(&tmem_base_s, 512);
     // The x tiles are the first thing on the critical path (HBM latency + the whole grid's 16 MB burst): their TMA loads go out
@@ -248,8 +282,25 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
     // residual, the same tensor) come from the preceding kernel, so this is also where that kernel's completion is awaited.
     if (lane == 0) {
       tc::mbar_init(&x_raw[0], 1); tc::mbar_init(&x_raw[1], 1);
+      for (int s = 0; s < C4_SLOTS; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
       tc::fence_barrier_init();
       tc::fence_proxy_async();
+      // the first ring fill does not depend on the preceding kernel: it goes out before the wait for it (with norm1 folded the
+      // first MMAs are gated by these weights, no longer by a LayerNorm pass over the tile)
+      {
+        const uint8_t* src = p.img;
+        for (int h = 0; h < 4 && n_early < C4_SLOTS; ++h) {
+          const int gw = p.hg[h].gw, nun = p.hg[h].n_units, ups = 2 / gw;
+          for (int u0 = 0; u0 < nun && n_early < C4_SLOTS; u0 += ups) {
+            const int nu = nun - u0 < ups ? nun - u0 : ups;
+            const uint32_t bytes = (uint32_t)(nu * gw) * C4_BLOCK;
+            tc::mbar_arrive_expect_tx(&full_bar[n_early], bytes);
+            tc::bulk_g2s(sRing + (size_t)n_early * C4_SLOT, src, bytes, &full_bar[n_early]);
+            src += bytes;
+            ++n_early;
+          }
+        }
+      }
       tc::pdl_wait();
       for (int t = 0; t < ntl; ++t) {
         const int tile = (int)blockIdx.x + t * (int)gridDim.x;
@@ -262,9 +313,8 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
     __syncwarp();
   }
   if (tid == 0) {
-    for (int s = 0; s < C4_SLOTS; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     tc::mbar_init(&x_ready[0], C4_NEW); tc::mbar_init(&x_ready[1], C4_NPW);
-    tc::mbar_init(&cb_full[0], 1); tc::mbar_init(&cb_full[1], 1); tc::mbar_init(&pub_bar, C4_NEW);
+    tc::mbar_init(&cb_full[0], 1); tc::mbar_init(&cb_full[1], 1); tc::mbar_init(&pub_bar, C4_NEW); tc::mbar_init(&stat1_ready, C4_NPW * 32);
     tc::mbar_init(&x_dead[0], 1); tc::mbar_init(&x_dead[1], 1); tc::mbar_init(&r_full[0], 1); tc::mbar_init(&r_full[1], 1);
     for (int i = 0; i < 4; ++i) {
       tc::mbar_init(&acc1_full[i], 1); tc::mbar_init(&acc2_full[i], 1); tc::mbar_init(&acc3_full[i], 1);
@@ -279,7 +329,10 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
     sPar[512 + i] = i < 2 * p.n1f_h ? BSC * p.b_f1[i] : 0.0f;
     sPar[768 + i] = i < 2 * p.n2f_h ? BSC * p.b_f2[i] : 0.0f;
     sPar[1024 + i] = i < p.Dout ? BSC * p.gw[i] : 0.0f;
-    if (i < p.D) {  // norm1 parameters, padded layout (tc::ln_pad_index)
+    if (FOLD) {  // the mean's share of the first blocks (c4_affine_act32 in E1)
+      sPar[1792 + i] = i < 2 * p.n1s_h ? BSC * p.gw1s[i] : 0.0f;
+      sPar[2064 + i] = i < 2 * p.n1f_h ? BSC * p.gw1f[i] : 0.0f;
+    } else if (i < p.D) {  // norm1 parameters, padded layout (tc::ln_pad_index)
       sPar[1792 + tc::ln_pad_index(i, p.D)] = p.pre_w ? p.pre_w[i] : 1.0f;
       sPar[2064 + tc::ln_pad_index(i, p.D)] = p.pre_b ? p.pre_b[i] : 0.0f;
     }
@@ -304,7 +357,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
 #pragma unroll 1
           for (int h = h0; h < h1; ++h) {
             const int gw = p.hg[h].gw, nun = p.hg[h].n_units, ups = 2 / gw;
-            if (h == 8 && p.res_in_x) {
+            if (h == 8 && p.res_in_x == 1) {
               // the residual rows of this tile go (back) into its X buffer, dead once GEMM 1 of the local branch has read it: the
               // combiner epilogue then finds them in shared memory and writes its result over them -- no per-thread global access
               C4_TRACE(0, 2 * t);
@@ -319,6 +372,13 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
             for (int u0 = 0; u0 < nun; u0 += ups) {
               const int nu = nun - u0 < ups ? nun - u0 : ups;
               const uint32_t bytes = (uint32_t)(nu * gw) * C4_BLOCK;
+              if (n_early > 0) {  // issued by the set-up: only the bookkeeping
+                --n_early;
+                pe ^= 1u << s;
+                src += bytes;
+                if (++s == C4_SLOTS) s = 0;
+                continue;
+              }
               tc::mbar_wait(&empty_bar[s], ((pe >> s) & 1u) ^ 1u);
               pe ^= 1u << s;
               if ((p.dbg_noweights & 1) && (ph | t | (h - h0)) != 0) tc::mbar_arrive(&full_bar[s]);
@@ -372,7 +432,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
                   for (int ks = 0; ks < 4; ++ks) tc::umma_bf16(tmem + c * 192 + j * 64, ad + 2 * ks, bd + 2 * ks, ID64, ks ? 1u : 0u);
                   tc::umma_commit(&acc1_full[Q]);
                   if (j == 1) tc::umma_commit(&empty_bar[c]);
-                  if (j == 1 && c == 1 && ph == 1) tc::umma_commit(&x_dead[t]);  // both chains' GEMM 1 have read the X tile: its buffer may be reused (residual)
+                  if (j == 1 && c == 1 && ph == 1 && p.res_in_x == 1) tc::umma_commit(&x_dead[t]);  // both chains' GEMM 1 have read the X tile: its buffer may be reused (residual)
                 }
                 __syncwarp();
               }
@@ -512,7 +572,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
           C4_TRACE(1, ev++);
           issue_half(p.hg[hb + c], 0, tmem + (uint32_t)c * 192u, xaddr, 0, x_free, (uint32_t)(it & 1) ^ 1u, acc1_full, 0u, nullptr);
         }
-        if (ph == 1 && p.res_in_x) commit_to(&x_dead[t]);  // both chains' GEMM 1 have read the X tile: its buffer may be reused (residual)
+        if (ph == 1 && p.res_in_x == 1) commit_to(&x_dead[t]);  // both chains' GEMM 1 have read the X tile: its buffer may be reused (residual)
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {  // GEMM 2 of both chains: A = H (Y regions), D = X_c again
           C4_TRACE(1, ev++);
@@ -565,10 +625,17 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       const int t0 = (tile % p.tpu) * 128;
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
       tc::mbar_wait(&x_raw[1], 0);
-      if (p.pre_w) c4_ln_rows(smem + xtile_bytes, nrows, p.D, pw * 4, 4, lane, sPar + 1792, sPar + 2064, sStat + 128);
-      tc::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&x_ready[1]);
+      if (FOLD) {  // the raw rows are the operand: GEMM 1 may start at once; only E1 needs the statistics
+        if (lane == 0) tc::mbar_arrive(&x_ready[1]);
+#pragma unroll 1
+        for (int i = 0; i < 4; ++i) c4_stats_rows8(smem + xtile_bytes, p.D >> 6, pw * 4 + i, lane, sStat + 128);
+        tc::mbar_arrive(&stat1_ready);  // every thread: its own rows' statistics are written
+      } else {
+        if (p.pre_w) c4_ln_rows(smem + xtile_bytes, nrows, p.D, pw * 4, 4, lane, sPar + 1792, sPar + 2064, sStat + 128);
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&x_ready[1]);
+      }
     }
     // Finalisation of utterance b: mean over valid frames -> LN_s -> c[b] = W_c[:, D_l:] mu + b_c (+ the local LayerNorm's beta
     // share).  The Dout outputs of an utterance are split over `parts` owner CTAs (CTA index = part * B + b), so that the
@@ -694,7 +761,8 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       tc::tc_fence_after();
     };
     // E1: H = act(acc1 + b1) -> packed bf16 into Y_c                                             VanillaNN.py:168-196
-    auto e1 = [&](const float* sB1, int n1h) {
+    float2 rst = make_float2(1.0f, 0.0f);  // FOLD: this row's (rstd, -mean rstd) of norm1, set per tile
+    auto e1 = [&](const float* sB1, const float* sG1, int n1h) {
       const int qw = n1h >> 1;  // quarter width
 #pragma unroll 1
       for (int qq = 0; qq < 2; ++qq) {
@@ -704,7 +772,8 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
           float v[32];
           tc::tmem_ld32(xc + cc, v);
           tc::tmem_ld_wait();
-          c4_bias_act32<ACT>(v, sB1 + grp * n1h + cc, act);
+          if (FOLD) c4_affine_act32<ACT>(v, BSC * rst.x, rst.y, sG1 + grp * n1h + cc, sB1 + grp * n1h + cc, act);
+          else c4_bias_act32<ACT>(v, sB1 + grp * n1h + cc, act);
           uint32_t hp[16];
 #pragma unroll
           for (int j = 0; j < 16; ++j) hp[j] = tc::pack_bf16x2(v[2 * j], v[2 * j + 1]);
@@ -717,6 +786,16 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       }
     };
 
+    // this thread's mask bytes of both tiles, requested before anything waits (the mask is an input of the whole encoder, not of
+    // the preceding kernel): the loads' latency used to sit in front of the first epilogue of every tile
+    float rmask[C4_MAX_TILES];
+#pragma unroll
+    for (int t = 0; t < C4_MAX_TILES; ++t) {
+      const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+      const int t0 = (tile % p.tpu) * 128;
+      const bool in = t < ntl && t0 + r < p.T;
+      rmask[t] = in ? (p.mask ? (float)p.mask[(int64_t)(tile / p.tpu) * p.T + t0 + r] : 1.0f) : 0.0f;
+    }
     // ---- the CTA's first tile: the 16 epilogue warps normalise it in place (8 rows each) ----
     {
       const int tile = (int)blockIdx.x;
@@ -724,10 +803,17 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
       tc::mbar_wait(&x_raw[0], 0);
       if (p.trace && tid == 0) p.trace[256 + 640 * p.trace_slot + 4 * blockIdx.x + 1] = tc::global_timer_ns();
-      if (p.pre_w) c4_ln_rows(smem, nrows, p.D, warp, 1, lane, sPar + 1792, sPar + 2064, sStat);
-      tc::fence_proxy_async();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&x_ready[0]);
+      if (FOLD) {
+        if (lane == 0) tc::mbar_arrive(&x_ready[0]);
+        c4_stats_rows8(smem, p.D >> 6, q * 4 + (warp >> 2), lane, sStat);  // eight of this lane quadrant's 32 rows
+        tc::named_bar_sync(1 + q, 128);  // the quadrant's four warps have written its rows' statistics
+      } else {
+        if (p.pre_w) c4_ln_rows(smem, nrows, p.D, warp, 1, lane, sPar + 1792, sPar + 2064, sStat);
+        tc::fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&x_ready[0]);
+      }
+      (void)nrows;
     }
     int ev = 0;
     // =============================== phase 1: summary branch ===============================
@@ -737,9 +823,14 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       const int b = tile / p.tpu, t0 = (tile % p.tpu) * 128;
       const int64_t row0 = (int64_t)b * p.T + t0;
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
-      const float rscale = r < nrows ? (p.mask ? (float)p.mask[row0 + r] : 1.0f) : 0.0f;
+      const float rscale = rmask[t];
+      (void)nrows;
       if (tr) C4_TRACE(3 - grp, ev++);
-      e1(sPar, p.n1s_h);
+      if (FOLD) {
+        if (t == 1) tc::mbar_wait(&stat1_ready, 0);
+        rst = sStat[t * 128 + r];
+      }
+      e1(sPar, sPar + 1792, p.n1s_h);
       if (tr) C4_TRACE(3 - grp, ev++);
       // E2': S = act(acc2 + b2) * mask -> column sums of this tile                                summary_mixing.py:221, 229-231
       {
@@ -781,9 +872,10 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
       const int64_t row0 = (int64_t)b * p.T + t0;
       const int nrows = p.T - t0 < 128 ? p.T - t0 : 128;
       const bool live = r < nrows;
-      const float rscale = live ? (p.mask ? (float)p.mask[row0 + r] : 1.0f) : 0.0f;
+      const float rscale = rmask[t];
       if (tr) C4_TRACE(3 - grp, ev++);
-      e1(sPar + 512, p.n1f_h);
+      if (FOLD) rst = sStat[t * 128 + r];
+      e1(sPar + 512, sPar + 2064, p.n1f_h);
       if (tr) C4_TRACE(3 - grp, ev++);
       // E2: v = act(acc2 + b2) * mask -> packed bf16 into Y_c: the A operand of the combiner is the UN-normalised local branch.
       // local_norm is applied AFTER the GEMM, algebraically: LN_l(v) W^T = rstd (v (W gamma)^T - mean gw) + W beta with
@@ -869,7 +961,7 @@ __global__ void __launch_bounds__(C4_THREADS, 1) cell4_kernel(const __grid_const
           uint8_t* const rowp = xt + (size_t)(col >> 6) * kblock_bytes(128) + r * 128;
           const int ch0 = (col & 63) >> 3;
           if (has_res) {
-            if (qq == 0) tc::mbar_wait(&r_full[t], 0);
+            if (qq == 0 && p.res_in_x == 1) tc::mbar_wait(&r_full[t], 0);
 #pragma unroll
             for (int h = 0; h < 4; ++h) {
               const uint4 rv = *reinterpret_cast<const uint4*>(rowp + (((ch0 + h) ^ (r & 7)) << 4));
@@ -1005,7 +1097,7 @@ static size_t c4_img_bytes(const C4Sched& s) {
   for (int h = 0; h < 10; ++h) n += (size_t)s.nblocks[h] * C4_BLOCK;
   return n;
 }
-struct C4Image { size_t wcs, gw, bw, wg, wg_img, total; };
+struct C4Image { size_t wcs, gw, bw, wg, wg_img, stream2, gw1s, gw1f, b1s, b1f, total; };
 static C4Image c4_image(const smx_cell_weights* w, const C4Sched& s) {
   C4Image im{};
   const size_t Dl = w->local_out_dim, Ds = w->summary_out_dim, Do = w->merge.out_dim;
@@ -1013,8 +1105,14 @@ static C4Image c4_image(const smx_cell_weights* w, const C4Sched& s) {
   im.wcs = off; off += align_up(Ds * Do * 2);
   im.gw = off; off += align_up(Do * 4);
   im.bw = off; off += align_up(Do * 4);
-  im.wg = off; off += align_up(Do * Dl * 4);
-  im.wg_img = off; off += align_up(Do * Dl * 2, 1024);
+  size_t big = Do * Dl;  // pack-time scratch also serves the norm1 fold of the first summary / local block
+  if ((size_t)w->summary[0].in_dim * w->summary[0].out_dim > big) big = (size_t)w->summary[0].in_dim * w->summary[0].out_dim;
+  if ((size_t)w->local[0].in_dim * w->local[0].out_dim > big) big = (size_t)w->local[0].in_dim * w->local[0].out_dim;
+  im.wg = off; off += align_up(big * 4);
+  im.wg_img = off; off += align_up(big * 2, 1024);
+  // norm1 folded (tc_cell4_pack_prenorm): a second stream image whose first blocks carry gamma, their gw and folded biases
+  im.stream2 = off; off += align_up(c4_img_bytes(s), 1024);
+  im.gw1s = off; off += 1024; im.gw1f = off; off += 1024; im.b1s = off; off += 1024; im.b1f = off; off += 1024;
   im.total = off;
   return im;
 }
@@ -1101,6 +1199,79 @@ int tc_cell4_pack(const smx_cell_weights* w, const void* img_s1, const void* img
   return check_launch("cell4_wcs_kernel");
 }
 
+// ---- norm1 folded into the first block of both branches -----------------------------------------------------------------
+// ParallelLinear layout (h, in/h, out/h): Wg[m][i][j] = W[m][i][j] gamma[m ih + i]; gw[n] = sum_i bf16(Wg[m][i][j]); bw[n] = sum_i beta[m ih + i] W[m][i][j]
+__global__ void cell4_fold_ln_heads_kernel(const float* __restrict__ W, int h, int ih, int oh, const float* __restrict__ gamma,
+                                           const float* __restrict__ beta, float* __restrict__ Wg, float* __restrict__ gw, float* __restrict__ bw) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  if (n >= h * oh) return;
+  const int m = n / oh, j = n - m * oh;
+  float sg = 0.0f, sb = 0.0f;
+  for (int i = 0; i < ih; ++i) {
+    const size_t at = ((size_t)m * ih + i) * oh + j;
+    const float wv = W[at], g = wv * gamma[m * ih + i];
+    Wg[at] = g;
+    sg += __bfloat162float(__float2bfloat16(g));
+    sb = fmaf(beta[m * ih + i], wv, sb);
+  }
+  gw[n] = sg; bw[n] = sb;
+}
+__global__ void cell4_add_bias_kernel(const float* __restrict__ b, float* __restrict__ bw, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) bw[i] += b ? b[i] : 0.0f;
+}
+bool tc_cell4_prenorm_ok(const smx_cell_weights* w) {
+  if (!tc_cell4_packed_bytes(w)) return false;
+  const smx_linear* L[2] = {&w->summary[0], &w->local[0]};
+  for (int g = 0; g < 2; ++g)
+    if (L[g]->in_dim != w->enc_dim || L[g]->out_dim > 256 || !L[g]->w) return false;
+  return true;
+}
+// img: the v4 image written by tc_cell4_pack (same stream, earlier): adds the folded stream image, gw and biases
+int tc_cell4_pack_prenorm(const smx_cell_weights* w, void* img, const float* norm_w, const float* norm_b, cudaStream_t st) {
+  C4Sched s;
+  if (!tc_cell4_prenorm_ok(w) || !c4_schedule(w, s)) return fail(SMX_ERR_UNSUPPORTED, "cell v4: norm fold not handled");
+  const C4Image im = c4_image(w, s);
+  char* base = (char*)img;
+  size_t off[11];
+  off[0] = 0;
+  for (int h = 0; h < 10; ++h) off[h + 1] = off[h] + (size_t)s.nblocks[h] * C4_BLOCK;
+  // everything but the first blocks is the plain stream
+  cudaError_t e = cudaMemcpyAsync(base + im.stream2, base, off[10], cudaMemcpyDeviceToDevice, st);
+  if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaMemcpyAsync: %s", cudaGetErrorString(e));
+  float* Wg = (float*)(base + im.wg);
+  for (int br = 0; br < 2; ++br) {
+    const smx_linear& L = br == 0 ? w->summary[0] : w->local[0];
+    float* gw = (float*)(base + (br == 0 ? im.gw1s : im.gw1f));
+    float* b1 = (float*)(base + (br == 0 ? im.b1s : im.b1f));
+    const int N = L.out_dim, K = L.in_dim;
+    if (L.n_split > 1) {
+      const int h = L.n_split, ih = K / h, oh = N / h;
+      cell4_fold_ln_heads_kernel<<<(N + 127) / 128, 128, 0, st>>>(L.w, h, ih, oh, norm_w, norm_b, Wg, gw, b1);
+      count_launch();
+      SMX_TRY(check_launch("cell4_fold_ln_heads_kernel"));
+    } else {
+      SMX_TRY(tc_fold_ln(L.w, K, K, N, norm_w, norm_b, Wg, gw, b1, st));
+    }
+    cell4_add_bias_kernel<<<(N + 127) / 128, 128, 0, st>>>(L.b, b1, N);
+    count_launch();
+    SMX_TRY(check_launch("cell4_add_bias_kernel"));
+    smx_linear Lg = L;
+    Lg.w = Wg; Lg.b = nullptr;
+    SMX_TRY(tc_pack_linear_nt(Lg, 0, K, 64, base + im.wg_img, st));
+    for (int c = 0; c < 2; ++c) {
+      const int hh = (br == 0 ? 0 : 4) + c;
+      C4Gather g{};
+      g.n = s.nblocks[hh];
+      for (int i = 0; i < g.n; ++i) g.src[i] = (uint16_t)s.blocks[hh][i];
+      cell4_gather_kernel<<<g.n, 128, 0, st>>>((const uint4*)(base + im.wg_img), (uint4*)(base + im.stream2 + off[hh]), g);
+      count_launch();
+      SMX_TRY(check_launch("cell4_gather_kernel"));
+    }
+  }
+  return SMX_OK;
+}
+
 static int c4_sms() {
   static int n = 0;
   if (n == 0) {
@@ -1146,11 +1317,11 @@ bool tc_encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint6
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
-template <int ACT, bool STD>
+template <int ACT, bool STD, bool FOLD>
 static int launch_cell4_as(const CUtensorMap& tm, const CUtensorMap& tr, const CUtensorMap& ty, const C4P& p, unsigned grid, size_t smem, cudaStream_t st) {
-  cudaError_t e = cudaFuncSetAttribute(cell4_kernel<ACT, STD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = cudaFuncSetAttribute(cell4_kernel<ACT, STD, FOLD>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(cell4_kernel): %s", cudaGetErrorString(e));
-  e = launch_pdl(cell4_kernel<ACT, STD>, dim3(grid), dim3(C4_THREADS), smem, st, 1u, tm, tr, ty, p);
+  e = launch_pdl(cell4_kernel<ACT, STD, FOLD>, dim3(grid), dim3(C4_THREADS), smem, st, 1u, tm, tr, ty, p);
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaLaunchKernelEx(cell4_kernel): %s", cudaGetErrorString(e));
   count_tc_launch();
   return check_launch("cell4_kernel");
@@ -1158,8 +1329,9 @@ static int launch_cell4_as(const CUtensorMap& tm, const CUtensorMap& tr, const C
 
 template <int ACT>
 static int launch_cell4_act(const CUtensorMap& tm, const CUtensorMap& tr, const CUtensorMap& ty, const C4P& p, unsigned grid, size_t smem,
-                            cudaStream_t st, bool std_cell) {
-  return std_cell ? launch_cell4_as<ACT, true>(tm, tr, ty, p, grid, smem, st) : launch_cell4_as<ACT, false>(tm, tr, ty, p, grid, smem, st);
+                            cudaStream_t st, bool std_cell, bool fold) {
+  if (std_cell && fold) return launch_cell4_as<ACT, true, true>(tm, tr, ty, p, grid, smem, st);
+  return std_cell ? launch_cell4_as<ACT, true, false>(tm, tr, ty, p, grid, smem, st) : launch_cell4_as<ACT, false, false>(tm, tr, ty, p, grid, smem, st);
 }
 
 int tc_cell4_fwd(const smx_cell_weights* w, const void* img, int B, int T, const __nv_bfloat16* x, const float* pre_ln_w,
@@ -1202,19 +1374,31 @@ int tc_cell4_fwd(const smx_cell_weights* w, const void* img, int B, int T, const
   if (!encode(&tm, x, D, D) || !encode(&ty, y, Dout, Dout) || !encode(&tr, residual ? (const void*)residual : (const void*)x, residual ? Dout : D, residual ? Dout : D))
     return fail(SMX_ERR_CUDA, "cuTensorMapEncodeTiled failed");
 
+  // the standard cell: every GEMM 256 x 256, the four MLP layers block-diagonal over four heads of 64 (compile-time MMA schedule)
+  bool std_cell = D == 256 && Ds == 256 && Dl == 256 && Dout == 256 && !getenv("SMX_C4_GENERIC");
+  for (int g = 0; g < 4; ++g) {
+    const smx_linear* Lg = g == 0 ? &w->summary[0] : g == 1 ? &w->summary[1] : g == 2 ? &w->local[0] : &w->local[1];
+    std_cell = std_cell && Lg->in_dim == 256 && Lg->out_dim == 256 && Lg->n_split == 4 && s.both[g] == 0;
+  }
+  // norm1 folded into the first blocks: the image was packed for exactly these LayerNorm parameters (smx_cell_pack_prenorm)
+  const bool fold = std_cell && pre_ln_w && pre_ln_b && w->prenorm_w == pre_ln_w && w->prenorm_b == pre_ln_b && !getenv("SMX_C4_NOFOLD");
   C4P p{};
   p.pre_w = pre_ln_w; p.pre_b = pre_ln_b; p.mask = mask;
   p.resid = residual; p.ldr = Dout; p.y = y; p.ldy = Dout;
   p.B = B; p.T = T; p.tpu = tpu; p.n_tiles = B * tpu; p.D = D;
-  p.img = (const uint8_t*)img;
+  p.img = (const uint8_t*)img + (fold ? im.stream2 : 0);
   size_t p1 = 0;
   for (int h = 0; h < 4; ++h) p1 += (size_t)s.nblocks[h] * C4_BLOCK;
   p.img_p2_off = (uint32_t)p1;
   for (int h = 0; h < 10; ++h) p.hg[h] = s.hg[h];
   p.n1s_h = w->summary[0].out_dim / 2; p.n2s_h = Ds / 2; p.n1f_h = w->local[0].out_dim / 2; p.n2f_h = Dl / 2; p.dout_h = Dout / 2;
   p.g2s_both = s.both[1]; p.g2f_both = s.both[3];
-  p.res_in_x = residual != nullptr && Dout <= D ? 1 : 0;  // (the output tile must fit the X buffer; it does: the residual has the input's width)
-  p.b_s1 = w->summary[0].b; p.b_s2 = w->summary[1].b; p.b_f1 = w->local[0].b; p.b_f2 = w->local[1].b;
+  // 1: the residual tile is re-loaded into the X buffer; 2: it is there already (folded norm1: X holds the raw rows; residual == x)
+  p.res_in_x = residual != nullptr && Dout <= D ? ((fold && (const void*)residual == (const void*)x && Dout == D) ? 2 : 1) : 0;
+  p.b_s1 = fold ? (const float*)((const char*)img + im.b1s) : w->summary[0].b;
+  p.b_f1 = fold ? (const float*)((const char*)img + im.b1f) : w->local[0].b;
+  p.b_s2 = w->summary[1].b; p.b_f2 = w->local[1].b;
+  p.gw1s = (const float*)((const char*)img + im.gw1s); p.gw1f = (const float*)((const char*)img + im.gw1f);
   p.use_lnl = w->use_layernorm ? 1 : 0;
   p.gw = (const float*)((const char*)img + im.gw);
   p.bw = (const float*)((const char*)img + im.bw);
@@ -1246,17 +1430,11 @@ int tc_cell4_fwd(const smx_cell_weights* w, const void* img, int B, int T, const
   { static const int nw = getenv("SMX_DBG_C4_NOWEIGHTS") ? atoi(getenv("SMX_DBG_C4_NOWEIGHTS")) : 0; p.dbg_noweights = nw; }
   const unsigned grid = (unsigned)(p.n_tiles < c4_sms() ? p.n_tiles : c4_sms());
   int rc;
-  // the standard cell: every GEMM 256 x 256, the four MLP layers block-diagonal over four heads of 64, combiner half in the X buffer
-  bool std_cell = D == 256 && Ds == 256 && Dl == 256 && Dout == 256 && !getenv("SMX_C4_GENERIC");
-  for (int g = 0; g < 4; ++g) {
-    const smx_linear* Lg = g == 0 ? &w->summary[0] : g == 1 ? &w->summary[1] : g == 2 ? &w->local[0] : &w->local[1];
-    std_cell = std_cell && Lg->in_dim == 256 && Lg->out_dim == 256 && Lg->n_split == 4 && s.both[g] == 0;
-  }
   switch (p.act) {
-    case SMX_ACT_SWISH: rc = launch_cell4_act<SMX_ACT_SWISH>(tm, tr, ty, p, grid, smem, st, std_cell); break;
-    case SMX_ACT_GELU: rc = launch_cell4_act<SMX_ACT_GELU>(tm, tr, ty, p, grid, smem, st, std_cell); break;
-    case SMX_ACT_RELU: rc = launch_cell4_act<SMX_ACT_RELU>(tm, tr, ty, p, grid, smem, st, std_cell); break;
-    default: rc = launch_cell4_act<-1>(tm, tr, ty, p, grid, smem, st, false); break;
+    case SMX_ACT_SWISH: rc = launch_cell4_act<SMX_ACT_SWISH>(tm, tr, ty, p, grid, smem, st, std_cell, fold); break;
+    case SMX_ACT_GELU: rc = launch_cell4_act<SMX_ACT_GELU>(tm, tr, ty, p, grid, smem, st, std_cell, fold); break;
+    case SMX_ACT_RELU: rc = launch_cell4_act<SMX_ACT_RELU>(tm, tr, ty, p, grid, smem, st, std_cell, fold); break;
+    default: rc = launch_cell4_act<-1>(tm, tr, ty, p, grid, smem, st, false, false); break;
   }
   ws.release(m0);
   return rc;

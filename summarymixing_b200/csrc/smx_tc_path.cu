@@ -155,6 +155,19 @@ int tc_cell_pack(const smx_cell_weights* w, void* packed, cudaStream_t st) {
   return SMX_OK;
 }
 
+// The LayerNorm in front of the cell (Conformer.py:520: norm1) folded into the packed image of the one-kernel cell: a no-op for
+// configurations that kernel does not take.  Records the folded parameters in the weights struct; the forward uses the folded
+// image only when it is called with exactly these parameters.
+int tc_cell_pack_prenorm(smx_cell_weights* w, const float* norm_w, const float* norm_b, cudaStream_t st) {
+  w->prenorm_w = nullptr; w->prenorm_b = nullptr;
+  if (!w->packed || !norm_w || !norm_b || w->mode != SMX_MODE_FULL || !tc_cell_supported(w, 0) || !tc_cellf_supported(w) || !tc_cell4_prenorm_ok(w))
+    return SMX_OK;
+  const CellLayout l = cell_layout(w);
+  SMX_TRY(tc_cell4_pack_prenorm(w, (char*)w->packed + l.v4, norm_w, norm_b, st));
+  w->prenorm_w = norm_w; w->prenorm_b = norm_b;
+  return SMX_OK;
+}
+
 // per-utterance finalisation: mean over time, LayerNorm, and the summary's share of the combiner
 //   c[b] = W_c[:, D_l:] @ LN_s( sum_t s[b,t] / sum_t mask[b,t] ) + b_c          summary_mixing.py:229-231,248-253
 __global__ void __launch_bounds__(256) cell_finalize_kernel(const float* __restrict__ colsum, int tiles_per_utt, int T,

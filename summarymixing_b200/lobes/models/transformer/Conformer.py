@@ -220,6 +220,9 @@ class ConformerEncoderLayer(nn.Module):
         lw.norm2_w = wv.ptr(self.norm2.norm.weight, device)
         lw.norm2_b = wv.ptr(self.norm2.norm.bias, device)
         self.mha_layer.fill(lw.cell, wv, device)
+        # norm1 folded into the cell's packed image (the one-kernel cell feeds the raw rows to the tensor cores); a no-op elsewhere
+        with torch.cuda.device(device):
+            L.check(L.lib().smx_cell_pack_prenorm(C.byref(lw.cell), lw.norm1_w, lw.norm1_b, H.stream_ptr(device)))
         self.convolution_module.fill(lw.conv, wv, device)
         lw.act = self._act_code
 
