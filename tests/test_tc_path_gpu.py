@@ -380,6 +380,40 @@ def test_layer_edge_shapes_and_resident_kernel_limits(B, T, launches):
     assert torch.isfinite(y16).all() and rel < 1e-2, rel
 
 
+def test_folded_norm1_agrees_with_the_in_place_layernorm():
+    """smx_cell_pack_prenorm folds the layer's norm1 into the one-kernel cell's image (gamma into the first blocks' weights,
+    statistics-only pass, row scalars in the first epilogue).  The layer records the folded parameters in its cell struct, the
+    folded and the unfolded kernel (SMX_C4_NOFOLD=1: in-place LayerNorm of the tile) agree to bf16 rounding, and both stay
+    within the module-level bound of the oracle."""
+    import os
+
+    torch.manual_seed(91)
+    D, B, T = 256, 9, 700
+    m = S.ConformerEncoderLayer(D, 1024, 4, 31, attention_type="SummaryMixing", local_proj_hid_dim=[D], local_proj_out_dim=D,
+                                summary_hid_dim=[D]).eval()
+    _perturb(m, 91)
+    g = torch.Generator().manual_seed(92)
+    x = torch.randn(B, T, D, generator=g).to(torch.bfloat16)
+    lens = torch.randint(200, T + 1, (B,), generator=g)
+    lens[0] = T
+    mask = torch.arange(T)[None] < lens[:, None]
+    y_or = O.conformer_layer(x.float(), dict(m.state_dict()), "", act="swish", src_key_padding_mask=mask)
+    m = m.to(DEV)
+    with torch.no_grad():
+        y_fold = m(x.to(DEV), src_key_padding_mask=mask.to(DEV))[0].float().cpu()
+        lw = m._wv.struct
+        assert lw.cell.prenorm_w == lw.norm1_w and lw.cell.prenorm_b == lw.norm1_b and lw.cell.prenorm_w
+        os.environ["SMX_C4_NOFOLD"] = "1"
+        try:
+            y_plain = m(x.to(DEV), src_key_padding_mask=mask.to(DEV))[0].float().cpu()
+        finally:
+            del os.environ["SMX_C4_NOFOLD"]
+    rel = float((y_fold - y_plain).norm() / y_plain.norm())
+    assert 0.0 < rel < 5e-3, rel  # different kernels (not bit-equal), same function
+    _check(y_fold, y_or, "layer, norm1 folded", abs_tol=4e-2, rel_tol=2e-2)
+    _check(y_plain, y_or, "layer, norm1 in place", abs_tol=4e-2, rel_tol=2e-2)
+
+
 def test_16_byte_aligned_buffers_take_the_fallback_kernels():
     """The newest kernels move rows with 256-bit accesses and need 32-byte aligned activations; buffers that are only
     16-byte aligned (the C ABI's stated minimum) must still give the same answer through the fallbacks: first-generation
