@@ -146,6 +146,9 @@ int tc_ffn2_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t r
 // bf16 tensor map (cuTensorMapEncodeTiled through the runtime's driver entry point; smx_tc_cell4.cu): rank 2 or 3, dims / box
 // innermost first, strides in bytes for dims 1.., 128-byte swizzle (box[0] = 64 columns: one UMMA K-block).  false: unavailable / rejected
 bool tc_encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box);
+// a packed operand image (8 KB blocks of 64 rows x 128 bytes, already in the 128-byte-swizzled UMMA layout) as a [64 * n_blocks][64] bf16
+// tensor without swizzle, box = one block: lets cp.async.bulk.tensor (with .cta_group::2: completion on the pair leader's barrier) copy blocks as they are
+bool tc_encode_tmap_image(CUtensorMap* m, const void* image, uint64_t n_blocks);
 // W gamma (fp32), gw[n] = sum_k bf16(W[n,k] gamma_k), bw[n] = sum_k beta_k W[n,k]  (smx_tc_cell4.cu; gamma / beta NULL = no LayerNorm)
 int tc_fold_ln(const float* W, int K, int ldw, int N, const float* gamma, const float* beta, float* Wg, float* gw, float* bw, cudaStream_t st);
 bool tc_ffn3_supported(const smx_ffn_weights* w);

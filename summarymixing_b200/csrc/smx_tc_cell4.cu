@@ -1306,15 +1306,23 @@ static c4_encode_fn c4_encoder() {
   return state.load() == 1 ? fn : nullptr;
 }
 
-bool tc_encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+static bool c4_encode(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box, CUtensorMapSwizzle swz) {
   c4_encode_fn enc = c4_encoder();
   if (!enc || rank < 2 || rank > 3) return false;
   cuuint64_t gdim[3], gstr[2];
   cuuint32_t bx[3], estr[3] = {1, 1, 1};
   for (int i = 0; i < rank; ++i) { gdim[i] = dims[i]; bx[i] = box[i]; }
   for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_bytes[i];
-  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, (void*)base, gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+  return enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, (void*)base, gdim, gstr, bx, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, swz,
              CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+bool tc_encode_tmap_bf16(CUtensorMap* m, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes, const uint32_t* box) {
+  return c4_encode(m, base, rank, dims, strides_bytes, box, CU_TENSOR_MAP_SWIZZLE_128B);
+}
+bool tc_encode_tmap_image(CUtensorMap* m, const void* image, uint64_t n_blocks) {
+  const uint64_t dims[2] = {64, n_blocks * 64}, strides[1] = {128};
+  const uint32_t box[2] = {64, 64};
+  return c4_encode(m, image, 2, dims, strides, box, CU_TENSOR_MAP_SWIZZLE_NONE);
 }
 
 template <int ACT, bool STD, bool FOLD>

@@ -311,6 +311,16 @@ __device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) 
       "r"(cta)
       : "memory");
 }
+// The same arrival WITHOUT memory ordering: for hand-overs whose payload lives in tensor memory only (ordered by tcgen05.wait +
+// tcgen05.fence::before_thread_sync on the arriving side).  The release form above is lowered to MEMBAR.ALL.GPU + ERRBAR per arrive.
+__device__ __forceinline__ void mbar_arrive_remote_relaxed(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n\t.reg .b32 ra;\n\t"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+      "mbarrier.arrive.relaxed.cluster.shared::cluster.b64 _, [ra];\n\t}" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
 // bounded wait with acquire at cluster scope (the arrivals may come from the peer CTA)
 __device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
   asm volatile(

@@ -45,6 +45,7 @@ struct Ffn3P {
   unsigned long long* trace;
   uint32_t off_ring, off_par, off_red;
   int cl2;                                 // 1: CTA pairs (cta_group::2)
+  uint32_t ring_bytes;                     // pair mode: bytes of the weight ring in use (the rest of the 128 KB region stages the output tile)
 };
 
 #define F3_TRACE(role, it, ev)                                                                                \
@@ -99,17 +100,32 @@ __device__ __forceinline__ void f3_tma_load_2d(void* smem_dst, const CUtensorMap
                "l"(tmap), "r"(c0), "r"(c1), "r"(tc::smem_u32(bar))
                : "memory");
 }
+// One 64 x 64 block of a packed weight image into this CTA's ring, completion (complete_tx) on the barrier at the same offset in
+// the PAIR LEADER's shared memory (.cta_group::2: the mbarrier may live in either CTA of the pair) -- the leader's issuer learns
+// that both halves of a step have landed from its own barrier, without a relay through the peer's warps.
+__device__ __forceinline__ void f3_tma_block_pair(uint32_t smem_dst, const CUtensorMap* tmap, int block, uint32_t leader_bar) {
+  asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+                   smem_dst),
+               "l"(tmap), "r"(0), "r"(block * 64), "r"(leader_bar)
+               : "memory");
+}
+__device__ __forceinline__ uint32_t f3_leader_addr(const void* p) {  // the same shared-memory offset in CTA 0 of the cluster
+  uint32_t ra;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(tc::smem_u32(p)), "r"(0u));
+  return ra;
+}
 __device__ __forceinline__ float2 f3_bf2(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u)); }
 
 template <bool OLN, int ACT, bool CL2>  // ACT >= 0: compile-time activation (smx_act); -1: runtime p.act; CL2: CTA pairs
-__global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_constant__ CUtensorMap tmap_x, const Ffn3P p) {
+__global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
+                                                              const __grid_constant__ CUtensorMap tmap_w2, const Ffn3P p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sX = smem;
   uint8_t* sRing = smem + p.off_ring;
   float* sPar = reinterpret_cast<float*>(smem + p.off_par);  // [b1 (F) | b2 | oln_w | oln_b | ln_w | ln_b (256 each)]
   float* sRed = reinterpret_cast<float*>(smem + p.off_red);  // [4 column quarters][128 rows][2]: per-thread (mean, M2)
   float2* sStat = reinterpret_cast<float2*>(smem + p.off_red + 4096);  // [2 (tile parity)][128] per-row (1/std, -mean/std) of the input LayerNorm
-  __shared__ __align__(8) uint64_t full_bar[F3_STAGES], peer_full[F3_STAGES], empty_bar[F3_STAGES];
+  __shared__ __align__(8) uint64_t full_bar[F3_STAGES], empty_bar[F3_STAGES];
   __shared__ __align__(8) uint64_t x_full, x_free, x_landed, stat_full, acc1_full[2], h_full[2], acc2_full, epi_done;
   __shared__ uint32_t tmem_base_s;
 
@@ -121,8 +137,8 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
   // the leader (rank 0) with cta_group::2 and spans both SMs: M = 256 (each CTA its own A operand and accumulators), each
   // CTA streams only HALF of every weight step (N/2 rows of B) from L2 into its own ring -- half the L2 requests and
   // shared-memory fill per SM, and the 16-slot ring covers two hidden chunks instead of one.  Cross-CTA protocol:
-  //   leader <- both CTAs : x_full, h_full, epi_done (arrivals from the peer are remote mbarrier arrives), peer_full[s]
-  //                         (the peer's otherwise idle MMA warp relays "my half of step s has landed")
+  //   leader <- both CTAs : x_full, h_full, epi_done (arrivals from the peer are remote mbarrier arrives), full_bar[s] (the peer's
+  //                         weight copies are cp.async.bulk.tensor with .cta_group::2 and complete on the leader's barrier)
   //   leader -> both CTAs : empty_bar[s], acc1_full, acc2_full, x_free (tcgen05.commit multicast to the pair)
   constexpr uint32_t NCTA = CL2 ? 2u : 1u;
   const uint32_t crank = CL2 ? tc::cluster_ctarank() : 0u;
@@ -131,7 +147,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
   tc::pdl_launch_dependents();  // the next kernel may start taking over SMs as CTAs of this grid leave them
   if (warp == F3_PROD_WARP) { if (CL2) tc::tmem_alloc2(&tmem_base_s, 512); else tc::tmem_alloc(&tmem_base_s, 512); }
   if (tid == 0) {
-    for (int s = 0; s < F3_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&peer_full[s], 1); tc::mbar_init(&empty_bar[s], 1); }
+    for (int s = 0; s < F3_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     tc::mbar_init(&x_full, F3_NPW * NCTA); tc::mbar_init(&x_free, 1); tc::mbar_init(&stat_full, F3_NPW * 32); tc::mbar_init(&x_landed, 1); tc::mbar_init(&acc2_full, 1); tc::mbar_init(&epi_done, F3_NEW * NCTA);
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc1_full[i], 1); tc::mbar_init(&h_full[i], F3_NEW * NCTA); }
     tc::fence_barrier_init();
@@ -162,13 +178,15 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
   // step order (tc_ffn3_pack), so a step is one contiguous run of 8 KB blocks.
   const int ng1 = (nkbD + 1) / 2;
   const uint32_t slot_bytes = CL2 ? 16384u : 32768u;
-  const int nslots = (int)(F3_RING_BYTES / slot_bytes);
+  const int nslots = (int)((CL2 ? p.ring_bytes : F3_RING_BYTES) / slot_bytes);
   // Every CTA walks the hidden chunks in the same order: a row's result does not depend on which CTA / tile computes it
   // (bit-exact batch invariance).  A per-CTA rotation of the order, meant to spread L2 requests, measured no gain
   // (replicating the weight images showed there is no hot-line effect to avoid).
   auto chunk_of = [&](int j) { return j; };
   // barriers owned by the leader: an arrival from the peer CTA is a remote arrive
   auto arrive_leader = [&](uint64_t* bar) { if (CL2) tc::mbar_arrive_remote(bar, 0); else tc::mbar_arrive(bar); };
+  // hand-overs of tensor-memory contents only (hidden chunks, the drained output accumulator): no memory fence
+  auto arrive_leader_tmem = [&](uint64_t* bar) { if (CL2) tc::mbar_arrive_remote_relaxed(bar, 0); else tc::mbar_arrive(bar); };
 
   if (warp == F3_PROD_WARP) {
     // =============================== weight producer ===============================
@@ -178,14 +196,17 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
       uint32_t pe = 0;
       long long tw_empty = 0, t_tile0 = 0;
       const bool tracing = p.trace != nullptr && blockIdx.x == 0;
+      // bytes: what the step's full barrier has to see -- in a pair BOTH halves, counted on the leader's barrier only (the peer's
+      // copies complete there; a copy that lands before the leader has armed the phase only drives the transaction count negative)
       auto next_slot = [&](uint32_t bytes) -> uint8_t* {  // wait until the slot is free, arm its full barrier
         const long long c0t = tracing ? clock64() : 0;
         tc::mbar_wait(&empty_bar[s], ((pe >> s) & 1u) ^ 1u);  // suspending wait: a polling producer floods the SM sub-partition's shared-memory queue
         pe ^= 1u << s;
         if (tracing) tw_empty += clock64() - c0t;
-        tc::mbar_arrive_expect_tx(&full_bar[s], bytes);
+        if (leader) tc::mbar_arrive_expect_tx(&full_bar[s], bytes);
         return sRing + (size_t)s * slot_bytes;
       };
+      const uint32_t full0 = CL2 ? f3_leader_addr(&full_bar[0]) : 0u;  // the leader's full_bar[0] in the cluster window
       auto load_g1 = [&](int j) {
         const int c = chunk_of(j);
         for (int h = 0; h < ng1; ++h) {
@@ -195,8 +216,9 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
             uint8_t* dst = next_slot((uint32_t)nk * 2u * F3_BLOCK);
             tc::bulk_g2s(dst, src, (uint32_t)nk * 2u * F3_BLOCK, &full_bar[s]);
           } else {  // this CTA's 64 of the 128 rows of every K-block
-            uint8_t* dst = next_slot((uint32_t)nk * F3_BLOCK);
-            for (int kbl = 0; kbl < nk; ++kbl) tc::bulk_g2s(dst + (size_t)kbl * F3_BLOCK, src + (size_t)(kbl * 2 + (int)crank) * F3_BLOCK, F3_BLOCK, &full_bar[s]);
+            const uint32_t dst = tc::smem_u32(next_slot((uint32_t)nk * 2u * F3_BLOCK));
+            for (int kbl = 0; kbl < nk; ++kbl)
+              f3_tma_block_pair(dst + (uint32_t)kbl * F3_BLOCK, &tmap_w1, (c * nkbD + 2 * h + kbl) * 2 + (int)crank, full0 + 8u * (uint32_t)s);
           }
           if (++s == nslots) s = 0;
         }
@@ -205,9 +227,14 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
         const int c = chunk_of(j);
         for (int u = 0; u < 2; ++u) {
           const uint8_t* src = p.w2 + (size_t)((2 * c + u) * nkbD) * F3_BLOCK;  // blocks [kb of F][n-chunk]
-          const uint32_t bytes = (uint32_t)nkbD * F3_BLOCK / NCTA;              // this CTA's share of the D rows
+          const uint32_t bytes = (uint32_t)nkbD * F3_BLOCK;
           uint8_t* dst = next_slot(bytes);
-          tc::bulk_g2s(dst, src + (size_t)crank * bytes, bytes, &full_bar[s]);
+          if (!CL2) tc::bulk_g2s(dst, src, bytes, &full_bar[s]);
+          else {  // this CTA's half of the D rows
+            const int nb = nkbD / 2;
+            for (int b = 0; b < nb; ++b)
+              f3_tma_block_pair(tc::smem_u32(dst) + (uint32_t)b * F3_BLOCK, &tmap_w2, (2 * c + u) * nkbD + (int)crank * nb + b, full0 + 8u * (uint32_t)s);
+          }
           if (++s == nslots) s = 0;
         }
       };
@@ -232,22 +259,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
     // overwrites acc1[j&1] (and with it H[j&1]), runs after G2(j) has read H[j&1]; G2(j) itself is issued only after
     // the epilogue has loaded acc1[j&1] and stored H[j&1] (h_full).  No separate "accumulator drained" barrier.
     if (CL2 && !leader) {
-      // Peer CTA: this warp has no MMAs to issue.  One lane relays "my half of the step has landed" to the leader in a
-      // loop that is as short as it can be (the ring is a plain cyclic sequence of slots: no schedule knowledge needed):
-      // wait for the local full barrier, arrive on the leader's peer_full barrier of the same slot.
-      if (lane == 0) {
-        int n_mine = 0;
-        for (int base = first_base; base < p.n_tiles; base += base_step) ++n_mine;
-        const int total = n_mine * nj * (ng1 + 2);
-        int s = 0;
-        uint32_t pf = 0;
-        for (int st = 0; st < total; ++st) {
-          tc::mbar_wait_spin(&full_bar[s], (pf >> s) & 1u);
-          tc::mbar_arrive_remote(&peer_full[s], 0);
-          pf ^= 1u << s;
-          if (++s == nslots) s = 0;
-        }
-      }
+      // Peer CTA: this warp has no MMAs to issue (and nothing to relay: the peer's weight copies complete on the leader's barriers)
     } else {
     int s = 0;
     uint32_t pf = 0;
@@ -261,7 +273,6 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
     auto ring_next = [&]() -> uint32_t {  // wait for the next step (both halves); returns its shared-memory address
       const long long c0 = tracing ? clock64() : 0;
       tc::mbar_wait_spin(&full_bar[s], (pf >> s) & 1u);
-      if (CL2) tc::mbar_wait_spin_cluster(&peer_full[s], (pf >> s) & 1u);
       if (tracing) tw_ring += clock64() - c0;
       pf ^= 1u << s;
       tc::tc_fence_after();
@@ -310,7 +321,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
           long long c0 = tracing ? clock64() : 0;
           if (j == 0 && it > 0) { if (CL2) tc::mbar_wait_cluster(&epi_done, par ^ 1); else tc::mbar_wait(&epi_done, par ^ 1); }  // acc2 drained
           if (tracing) { const long long c1 = clock64(); tw_epi += c1 - c0; c0 = c1; }
-          if (CL2) tc::mbar_wait_spin_cluster(&h_full[bsel], (ph_hf >> bsel) & 1u); else tc::mbar_wait_spin(&h_full[bsel], (ph_hf >> bsel) & 1u);
+          tc::mbar_wait_spin(&h_full[bsel], (ph_hf >> bsel) & 1u);  // (tensor-memory payload: no cluster-scope acquire, which costs an L1 invalidate per wait)
           if (tracing) tw_h += clock64() - c0;
           ph_hf ^= 1u << bsel;
         }
@@ -439,7 +450,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
         tc::tmem_st_wait();
         tc::tc_fence_before();
         __syncwarp();
-        if (lane == 0) arrive_leader(&h_full[bsel]);
+        if (lane == 0) arrive_leader_tmem(&h_full[bsel]);
         if (warp == 0 && j < 4) F3_TRACE(3, it, 2 * j + 1);
       }
       // ---- final: y = x + 0.5*(acc2 + b2)  [-> LN_out]; this thread: row r, output columns [64k, 64k + 64), in four
@@ -548,7 +559,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
       }
       tc::tc_fence_before();
       __syncwarp();
-      if (lane == 0) arrive_leader(&epi_done);
+      if (lane == 0) arrive_leader_tmem(&epi_done);
       if (warp == 0) F3_TRACE(3, it, 11);
     }
   }
@@ -644,12 +655,12 @@ static int ffn3_sms() {
 }
 
 template <bool OLN, bool CL2>
-static int launch_ffn3(const CUtensorMap& tm, const Ffn3P& p, unsigned grid, size_t smem, cudaStream_t st) {
+static int launch_ffn3(const CUtensorMap& tm, const CUtensorMap& tw1, const CUtensorMap& tw2, const Ffn3P& p, unsigned grid, size_t smem, cudaStream_t st) {
   cudaError_t e;
 #define SMX_FFN3_LAUNCH(A)                                                                                   \
   e = cudaFuncSetAttribute(ffn3_kernel<OLN, A, CL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(ffn3_kernel): %s", cudaGetErrorString(e)); \
-  e = launch_pdl(ffn3_kernel<OLN, A, CL2>, dim3(grid), dim3(F3_THREADS), smem, st, CL2 ? 2u : 1u, tm, p);     \
+  e = launch_pdl(ffn3_kernel<OLN, A, CL2>, dim3(grid), dim3(F3_THREADS), smem, st, CL2 ? 2u : 1u, tm, tw1, tw2, p);     \
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaLaunchKernelEx(ffn3_kernel): %s", cudaGetErrorString(e));
   switch (p.act) {
     case SMX_ACT_SWISH: SMX_FFN3_LAUNCH(SMX_ACT_SWISH); break;
@@ -690,13 +701,17 @@ int tc_ffn3_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t r
   }
   // CTA pairs when the weight steps split evenly over two CTAs (D a multiple of 128) and there is more than one tile
   p.cl2 = (g_ffn_pair && D % 128 == 0 && p.n_tiles >= 2) ? 1 : 0;
+  p.ring_bytes = getenv("SMX_F3_RING") ? (uint32_t)atoi(getenv("SMX_F3_RING")) : 65536u;
+  CUtensorMap tw1 = tm, tw2 = tm;  // weight images as block tensors (pair mode only: the peer's copies complete on the leader's barriers)
+  if (p.cl2 && !(tc_encode_tmap_image(&tw1, p.w1, (uint64_t)D * F / 4096) && tc_encode_tmap_image(&tw2, p.w2, (uint64_t)D * F / 4096)))
+    return fail(SMX_ERR_CUDA, "ffn: cuTensorMapEncodeTiled (weight images) failed");
   if (p.cl2) {
     const int n_pairs = (p.n_tiles + 1) / 2, max_pairs = ffn3_sms() / 2;
     const unsigned grid = 2u * (unsigned)(n_pairs < max_pairs ? n_pairs : max_pairs);
-    return oln_w ? launch_ffn3<true, true>(tm, p, grid, smem, st) : launch_ffn3<false, true>(tm, p, grid, smem, st);
+    return oln_w ? launch_ffn3<true, true>(tm, tw1, tw2, p, grid, smem, st) : launch_ffn3<false, true>(tm, tw1, tw2, p, grid, smem, st);
   }
   const unsigned grid = (unsigned)(p.n_tiles < ffn3_sms() ? p.n_tiles : ffn3_sms());
-  return oln_w ? launch_ffn3<true, false>(tm, p, grid, smem, st) : launch_ffn3<false, false>(tm, p, grid, smem, st);
+  return oln_w ? launch_ffn3<true, false>(tm, tw1, tw2, p, grid, smem, st) : launch_ffn3<false, false>(tm, tw1, tw2, p, grid, smem, st);
 }
 
 }  // namespace smx

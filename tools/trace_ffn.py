@@ -20,6 +20,9 @@ with torch.no_grad():
     for _ in range(3):
         layer(x, src_key_padding_mask=mask)
     torch.cuda.synchronize()
+    if os.environ.get('SMX_FFN_VER'):
+        L.lib().smx_debug_set_ffn_version(int(os.environ['SMX_FFN_VER']))
+        layer(x, src_key_padding_mask=mask)
     L.lib().smx_debug_set_cell_version(3)  # (the one-kernel cell's own trace stamps would overlap the FFN's slots)
     L.lib().smx_debug_set_trace(buf.data_ptr())
     layer(x, src_key_padding_mask=mask)
