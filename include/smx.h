@@ -433,9 +433,10 @@ SMX_API int smx_debug_set_trace(void* device_u64_buffer);
 /* Thread-block cluster size (1, 2 or 4) of the persistent FFN kernel: CTAs of a cluster multicast weight blocks
  * to each other.  Tuning / diagnostics. */
 SMX_API int smx_debug_set_ffn_cluster(int cluster_size);
-/* Fused FFN kernel generation: 3 (default; hidden activation resident in tensor memory, one CTA per tile), 4 (the same
- * with CTA pairs: cta_group::2 MMAs, each CTA streams half of every weight step) or 2 (hidden activation staged through
- * shared memory).  All compute the same function; diagnostics / A-B timing. */
+/* Fused FFN kernel generation: 4 (default where D is a multiple of 128 and there are at least two row tiles: hidden activation
+ * resident in tensor memory, CTA pairs with cta_group::2 MMAs, each CTA streams half of every weight step, final epilogue staged
+ * through shared memory), 3 (the same on single CTAs; bit-identical results; what other shapes run) or 2 (hidden activation
+ * staged through shared memory).  All compute the same function; diagnostics / A-B timing. */
 SMX_API int smx_debug_set_ffn_version(int version);
 /* Programmatic dependent launch of the fused kernels (default on): a kernel's set-up overlaps the tail of its
  * predecessor; results are identical.  Diagnostics / A-B timing. */

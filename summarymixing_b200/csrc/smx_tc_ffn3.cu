@@ -114,11 +114,14 @@ __device__ __forceinline__ uint32_t f3_leader_addr(const void* p) {  // the same
   asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(ra) : "r"(tc::smem_u32(p)), "r"(0u));
   return ra;
 }
+__device__ __forceinline__ void f3_tma_store_2d(const CUtensorMap* tmap, uint32_t smem_src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.tile.bulk_group [%0, {%1, %2}], [%3];" ::"l"(tmap), "r"(c0), "r"(c1), "r"(smem_src) : "memory");
+}
 __device__ __forceinline__ float2 f3_bf2(uint32_t u) { return __bfloat1622float2(*reinterpret_cast<const __nv_bfloat162*>(&u)); }
 
 template <bool OLN, int ACT, bool CL2>  // ACT >= 0: compile-time activation (smx_act); -1: runtime p.act; CL2: CTA pairs
 __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_constant__ CUtensorMap tmap_x, const __grid_constant__ CUtensorMap tmap_w1,
-                                                              const __grid_constant__ CUtensorMap tmap_w2, const Ffn3P p) {
+                                                              const __grid_constant__ CUtensorMap tmap_w2, const __grid_constant__ CUtensorMap tmap_y, const Ffn3P p) {
   extern __shared__ __align__(1024) uint8_t smem[];
   uint8_t* sX = smem;
   uint8_t* sRing = smem + p.off_ring;
@@ -127,6 +130,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
   float2* sStat = reinterpret_cast<float2*>(smem + p.off_red + 4096);  // [2 (tile parity)][128] per-row (1/std, -mean/std) of the input LayerNorm
   __shared__ __align__(8) uint64_t full_bar[F3_STAGES], empty_bar[F3_STAGES];
   __shared__ __align__(8) uint64_t x_full, x_free, x_landed, stat_full, acc1_full[2], h_full[2], acc2_full, epi_done;
+  __shared__ __align__(8) uint64_t res_full[4];  // pair mode: the residual's 64-column block k has landed in the staging tile
   __shared__ uint32_t tmem_base_s;
 
   const int tid = threadIdx.x, lane = tid & 31;
@@ -150,6 +154,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
     for (int s = 0; s < F3_STAGES; ++s) { tc::mbar_init(&full_bar[s], 1); tc::mbar_init(&empty_bar[s], 1); }
     tc::mbar_init(&x_full, F3_NPW * NCTA); tc::mbar_init(&x_free, 1); tc::mbar_init(&stat_full, F3_NPW * 32); tc::mbar_init(&x_landed, 1); tc::mbar_init(&acc2_full, 1); tc::mbar_init(&epi_done, F3_NEW * NCTA);
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&acc1_full[i], 1); tc::mbar_init(&h_full[i], F3_NEW * NCTA); }
+    for (int i = 0; i < 4; ++i) tc::mbar_init(&res_full[i], 1);
     tc::fence_barrier_init();
   }
   for (int i = tid; i < p.F; i += F3_THREADS) sPar[i] = p.b1[i];
@@ -418,6 +423,21 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
       const uint32_t par = it & 1;
       const int64_t row0 = (int64_t)(base + (int)crank) * 128;
       const int nrows = p.rows - row0 < 128 ? (int)(p.rows - row0) : 128;
+      // Pair mode: the final epilogue goes through a staging tile in shared memory (the half of the ring region the pair does not
+      // need: each CTA streams half of every weight step).  The residual's 64-column block k is fetched into it by tensor-map TMA,
+      // the four warps of column quarter k add the accumulator in place and one of them stores the block with a bulk tensor store
+      // (rows past the end are clipped): LDS/STS.128 that are conflict-free under the 128-byte swizzle and whole lines on the
+      // way out, instead of per-thread row accesses with lanes 512 bytes apart.  Block k's owner (warp 4k, lane 0) issues the
+      // loads: for the first tile at once, for a later tile after the first hidden chunks (by then the previous tile's store has
+      // long read the block: the wait costs nothing).
+      uint8_t* const sStage = sRing + 65536;
+      const bool stage_owner = CL2 && q == 0 && lane == 0 && k * 64 < D;
+      auto fetch_residual = [&]() {
+        tc::bulk_wait_read0();
+        tc::mbar_arrive_expect_tx(&res_full[k], kblock_bytes(128));
+        f3_tma_load_2d(sStage + (size_t)k * kblock_bytes(128), &tmap_x, k * 64, (int)row0, &res_full[k]);
+      };
+      if (stage_owner && it == 0) fetch_residual();
       // this row's LayerNorm scalars (the prologue warps computed them while GEMM 1 of the first chunks ran)
       tc::mbar_wait(&stat_full, par);
       const float2 rst = sStat[par * 128 + r];
@@ -452,13 +472,15 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
         __syncwarp();
         if (lane == 0) arrive_leader_tmem(&h_full[bsel]);
         if (warp == 0 && j < 4) F3_TRACE(3, it, 2 * j + 1);
+        if (stage_owner && it > 0 && j == 1) fetch_residual();
       }
       // ---- final: y = x + 0.5*(acc2 + b2)  [-> LN_out]; this thread: row r, output columns [64k, 64k + 64), in four
       // pieces of 16 columns (one 256-bit residual load and one 256-bit store each)
       const bool active = k * 64 < D;
       const bool live = r < nrows;
-      uint32_t rres[32];  // the residual (bf16 pairs), fetched while the last GEMMs run
-      if (active) {
+      uint32_t rres[CL2 ? 1 : 32];  // the residual (bf16 pairs), fetched while the last GEMMs run (pair mode: read from the staging tile)
+      uint8_t* const srow = sStage + (size_t)k * kblock_bytes(128) + r * 128;  // this thread's 128 bytes of staging block k
+      if (!CL2 && active) {
 #pragma unroll
         for (int h = 0; h < 4; ++h) {
           if (live) f3_ldg256(p.x + (row0 + r) * D + k * 64 + h * 16, rres + 8 * h);
@@ -468,6 +490,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
           }
         }
       }
+      if (CL2 && active) tc::mbar_wait(&res_full[k], par);
       tc::mbar_wait(&acc2_full, par);
       tc::tc_fence_after();
       if (warp == 0) F3_TRACE(3, it, 10);
@@ -482,10 +505,19 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
           if (h + 1 < 4) f3_tmem_ld16(t_acc2 + lane_sel + col + 16, vbuf[(h + 1) & 1]);
           float* v = vbuf[h & 1];
           const float4* bp = reinterpret_cast<const float4*>(sB2 + col);
+          uint32_t rr[8];
+          if (CL2) {
+            const uint4 r0 = *reinterpret_cast<const uint4*>(srow + (((2 * h) ^ (r & 7)) << 4));
+            const uint4 r1 = *reinterpret_cast<const uint4*>(srow + (((2 * h + 1) ^ (r & 7)) << 4));
+            rr[0] = r0.x; rr[1] = r0.y; rr[2] = r0.z; rr[3] = r0.w; rr[4] = r1.x; rr[5] = r1.y; rr[6] = r1.z; rr[7] = r1.w;
+          } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) rr[e] = rres[(CL2 ? 0 : h * 8) + (CL2 ? 0 : e)];
+          }
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             const float4 bb = bp[i];
-            const float2 ra = f3_bf2(rres[h * 8 + 2 * i]), rb = f3_bf2(rres[h * 8 + 2 * i + 1]);
+            const float2 ra = f3_bf2(rr[2 * i]), rb = f3_bf2(rr[2 * i + 1]);
             v[4 * i] = fmaf(0.5f, v[4 * i] + bb.x, ra.x);
             v[4 * i + 1] = fmaf(0.5f, v[4 * i + 1] + bb.y, ra.y);
             v[4 * i + 2] = fmaf(0.5f, v[4 * i + 2] + bb.z, rb.x);
@@ -508,11 +540,14 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
               m2_t += qh + dl * dl * (na * 16.0f / (na + 16.0f));
             }
             f3_tmem_st16f(t_acc2 + lane_sel + col, v);  // park the pre-norm values for the normalisation pass
-          } else if (live) {
+          } else if (CL2 || live) {
             uint32_t o[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) o[i] = tc::pack_bf16x2(v[2 * i], v[2 * i + 1]);
-            f3_stg256(p.y + (row0 + r) * D + col, o);
+            if (CL2) {
+              *reinterpret_cast<uint4*>(srow + (((2 * h) ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+              *reinterpret_cast<uint4*>(srow + (((2 * h + 1) ^ (r & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+            } else f3_stg256(p.y + (row0 + r) * D + col, o);
           }
         }
       }
@@ -547,11 +582,14 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
               v[4 * i + 2] = fmaf(fmaf(v[4 * i + 2], rstd, shift), ww.z, bb.z);
               v[4 * i + 3] = fmaf(fmaf(v[4 * i + 3], rstd, shift), ww.w, bb.w);
             }
-            if (live) {
+            if (CL2 || live) {
               uint32_t o[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i) o[i] = tc::pack_bf16x2(v[2 * i], v[2 * i + 1]);
-              f3_stg256(p.y + (row0 + r) * D + col, o);
+              if (CL2) {
+                *reinterpret_cast<uint4*>(srow + (((2 * h) ^ (r & 7)) << 4)) = make_uint4(o[0], o[1], o[2], o[3]);
+                *reinterpret_cast<uint4*>(srow + (((2 * h + 1) ^ (r & 7)) << 4)) = make_uint4(o[4], o[5], o[6], o[7]);
+              } else f3_stg256(p.y + (row0 + r) * D + col, o);
             }
           }
         }
@@ -560,9 +598,15 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
       tc::tc_fence_before();
       __syncwarp();
       if (lane == 0) arrive_leader_tmem(&epi_done);
+      if (CL2 && active) {  // block k of the output tile is complete in the staging tile: one bulk tensor store
+        tc::fence_proxy_async();
+        tc::named_bar_sync(5 + k, 128);
+        if (stage_owner) { f3_tma_store_2d(&tmap_y, tc::smem_u32(sStage + (size_t)k * kblock_bytes(128)), k * 64, (int)row0); tc::bulk_commit(); }
+      }
       if (warp == 0) F3_TRACE(3, it, 11);
     }
   }
+  if (CL2 && warp < F3_NEW && (warp & 3) == 0 && lane == 0) tc::bulk_wait_read0();  // the stores have read the staging tile before the CTA retires
   tc::tc_fence_before();
   __syncthreads();
   if (CL2) tc::cluster_sync();  // no CTA leaves (or frees tensor memory) while the pair's MMAs, multicast commits or remote arrives may still land
@@ -572,9 +616,9 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
 // ---------------------------------------------------------------------------------------------
 // host side (weights packed by tc_ffn2_pack: the images are shared with v2)
 // ---------------------------------------------------------------------------------------------
-static std::atomic<int> g_ffn_ver{3};   // smx_debug_set_ffn_version: 2 = shared-memory hidden (v2), 3 = TMEM hidden, single CTAs (default),
-static std::atomic<int> g_ffn_pair{0};  //                            4 = TMEM hidden + CTA pairs (cta_group::2; bit-identical, measured slower)
-void tc_set_ffn_version(int v) { g_ffn_ver = v == 2 ? 2 : 3; g_ffn_pair = v == 4 ? 1 : 0; }
+static std::atomic<int> g_ffn_ver{3};   // smx_debug_set_ffn_version: 2 = shared-memory hidden (v2), 3 = TMEM hidden, single CTAs,
+static std::atomic<int> g_ffn_pair{1};  //                            4 = TMEM hidden + CTA pairs (cta_group::2; bit-identical to 3; default where it applies)
+void tc_set_ffn_version(int v) { g_ffn_ver = v == 2 ? 2 : 3; g_ffn_pair = v == 4 ? 1 : 0; }  // 4 also restores the default
 int tc_ffn_version() { return g_ffn_ver; }
 
 // v3 images = the v2 images with their 8 KB blocks reordered into ring-step order:
@@ -655,12 +699,12 @@ static int ffn3_sms() {
 }
 
 template <bool OLN, bool CL2>
-static int launch_ffn3(const CUtensorMap& tm, const CUtensorMap& tw1, const CUtensorMap& tw2, const Ffn3P& p, unsigned grid, size_t smem, cudaStream_t st) {
+static int launch_ffn3(const CUtensorMap& tm, const CUtensorMap& tw1, const CUtensorMap& tw2, const CUtensorMap& ty, const Ffn3P& p, unsigned grid, size_t smem, cudaStream_t st) {
   cudaError_t e;
 #define SMX_FFN3_LAUNCH(A)                                                                                   \
   e = cudaFuncSetAttribute(ffn3_kernel<OLN, A, CL2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); \
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(ffn3_kernel): %s", cudaGetErrorString(e)); \
-  e = launch_pdl(ffn3_kernel<OLN, A, CL2>, dim3(grid), dim3(F3_THREADS), smem, st, CL2 ? 2u : 1u, tm, tw1, tw2, p);     \
+  e = launch_pdl(ffn3_kernel<OLN, A, CL2>, dim3(grid), dim3(F3_THREADS), smem, st, CL2 ? 2u : 1u, tm, tw1, tw2, ty, p);     \
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaLaunchKernelEx(ffn3_kernel): %s", cudaGetErrorString(e));
   switch (p.act) {
     case SMX_ACT_SWISH: SMX_FFN3_LAUNCH(SMX_ACT_SWISH); break;
@@ -701,17 +745,23 @@ int tc_ffn3_fwd(const smx_ffn_weights* w, const void* packed, int act, int64_t r
   }
   // CTA pairs when the weight steps split evenly over two CTAs (D a multiple of 128) and there is more than one tile
   p.cl2 = (g_ffn_pair && D % 128 == 0 && p.n_tiles >= 2) ? 1 : 0;
-  p.ring_bytes = getenv("SMX_F3_RING") ? (uint32_t)atoi(getenv("SMX_F3_RING")) : 65536u;
+  p.ring_bytes = 65536u;
   CUtensorMap tw1 = tm, tw2 = tm;  // weight images as block tensors (pair mode only: the peer's copies complete on the leader's barriers)
+  CUtensorMap ty = tm;
+  if (p.cl2) {
+    const uint64_t dims[2] = {(uint64_t)D, (uint64_t)rows}, strides[1] = {(uint64_t)D * 2};
+    const uint32_t box[2] = {64, 128};
+    if (!tc_encode_tmap_bf16(&ty, y, 2, dims, strides, box)) return fail(SMX_ERR_CUDA, "ffn: cuTensorMapEncodeTiled (y) failed");
+  }
   if (p.cl2 && !(tc_encode_tmap_image(&tw1, p.w1, (uint64_t)D * F / 4096) && tc_encode_tmap_image(&tw2, p.w2, (uint64_t)D * F / 4096)))
     return fail(SMX_ERR_CUDA, "ffn: cuTensorMapEncodeTiled (weight images) failed");
   if (p.cl2) {
     const int n_pairs = (p.n_tiles + 1) / 2, max_pairs = ffn3_sms() / 2;
     const unsigned grid = 2u * (unsigned)(n_pairs < max_pairs ? n_pairs : max_pairs);
-    return oln_w ? launch_ffn3<true, true>(tm, tw1, tw2, p, grid, smem, st) : launch_ffn3<false, true>(tm, tw1, tw2, p, grid, smem, st);
+    return oln_w ? launch_ffn3<true, true>(tm, tw1, tw2, ty, p, grid, smem, st) : launch_ffn3<false, true>(tm, tw1, tw2, ty, p, grid, smem, st);
   }
   const unsigned grid = (unsigned)(p.n_tiles < ffn3_sms() ? p.n_tiles : ffn3_sms());
-  return oln_w ? launch_ffn3<true, false>(tm, tw1, tw2, p, grid, smem, st) : launch_ffn3<false, false>(tm, tw1, tw2, p, grid, smem, st);
+  return oln_w ? launch_ffn3<true, false>(tm, tw1, tw2, ty, p, grid, smem, st) : launch_ffn3<false, false>(tm, tw1, tw2, ty, p, grid, smem, st);
 }
 
 }  // namespace smx

@@ -195,7 +195,7 @@ def test_ffn_kernel_generations_agree(version):
             y = m.to(DEV)(x.to(DEV), src_key_padding_mask=mask.to(DEV))[0]
         torch.cuda.synchronize()
     finally:
-        L.lib().smx_debug_set_ffn_version(3)
+        L.lib().smx_debug_set_ffn_version(4)  # the default
     _check(y, y_or, f"conformer layer, FFN generation {version}", abs_tol=4e-2, rel_tol=2e-2)
 
 
