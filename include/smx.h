@@ -246,6 +246,17 @@ typedef struct {
   float* dw;
   float* db;
 } smx_linear_grad;
+/* Training-mode dropout (torch.nn.Dropout semantics: an element is zeroed with probability p, the others scaled by 1/(1-p)).  The
+ * masks are counter-based: Philox4x32-10 keyed by `seed`, counter = (element index / 4, site), word = element index % 4, an
+ * element is dropped when its word < p * 2^32 -- a function of (seed, site, element index) only, so the backward call that
+ * receives the same smx_dropout regenerates the forward's masks (nothing is stored).  Sites: FFN 0 = inside
+ * PositionalwiseFeedForward, after the activation, over (rows, d_ffn); FFN 1 = the nn.Dropout after the block, over (rows, D)
+ * (Conformer.py:470-484); cell 0 = on cat([local, summary]) over (B*T, D_l + D_s) (summary_mixing.py:252, :297); conv module
+ * 0 = the nn.Dropout ending after_conv, over (B*T, D) (Conformer.py:163).  torch's own random stream is NOT reproduced. */
+typedef struct {
+  float p;       /* [0, 1); 0 = no dropout */
+  uint64_t seed; /* drawn by the caller once per module call */
+} smx_dropout;
 typedef struct {
   smx_linear_grad local[SMX_MAX_BLOCKS];
   smx_linear_grad summary[SMX_MAX_BLOCKS];
@@ -301,6 +312,35 @@ SMX_API size_t smx_conv_module_bwd_workspace_bytes(const smx_convmod_weights* w,
 SMX_API int smx_conv_module_bwd(const smx_convmod_weights* w, int act, int dtype, int32_t B, int32_t T, const void* x,
                         const uint8_t* padding_mask, const void* dy, void* dx, const smx_convmod_grads* grads,
                         void* workspace, size_t workspace_bytes, void* stream);
+
+/* Training-mode forward and backward WITH dropout (the smx_*_fwd entry points are the inference path: dropout is the identity
+ * there).  Same contracts as smx_*_bwd: self-contained calls on the fp32-math arm (linears as split-bf16 tcgen05 GEMMs), the
+ * *_train_bwd call recomputes the forward -- including the masks -- from x and the same smx_dropout.  drop == NULL or p == 0:
+ * the same function as the inference forward / smx_*_bwd.  workspace: the matching smx_*_train_workspace_bytes() (covers both).
+ * smx_ffn_train_fwd: y = x + 0.5 * drop1(W2 drop0(act(W1 LN(x) + b1)) + b2) [-> out LayerNorm];
+ * smx_conv_module_train_fwd: y = drop0(conv_module(x)) * mask; smx_summary_mixing_train_fwd: modes "SummaryMixing" and
+ * "SummaryMixing-fast", y = act(Wc drop0(cat[local, summary]) + bc) ("-lite" has no dropout: use the plain entry points). */
+SMX_API size_t smx_ffn_train_workspace_bytes(const smx_ffn_weights* w, int dtype, int64_t rows, int has_out_ln);
+SMX_API int smx_ffn_train_fwd(const smx_ffn_weights* w, int act, int dtype, int64_t rows, const void* x, const float* out_ln_w,
+                const float* out_ln_b, float out_ln_eps, const smx_dropout* drop, void* y, void* workspace, size_t workspace_bytes,
+                void* stream);
+SMX_API int smx_ffn_train_bwd(const smx_ffn_weights* w, int act, int dtype, int64_t rows, const void* x, const float* out_ln_w,
+                const float* out_ln_b, float out_ln_eps, const smx_dropout* drop, const void* dy, void* dx,
+                const smx_ffn_grads* grads, void* workspace, size_t workspace_bytes, void* stream);
+SMX_API size_t smx_conv_module_train_workspace_bytes(const smx_convmod_weights* w, int dtype, int32_t B, int32_t T);
+SMX_API int smx_conv_module_train_fwd(const smx_convmod_weights* w, int act, int dtype, int32_t B, int32_t T, const void* x,
+                const uint8_t* padding_mask, const smx_dropout* drop, void* y, void* workspace, size_t workspace_bytes, void* stream);
+SMX_API int smx_conv_module_train_bwd(const smx_convmod_weights* w, int act, int dtype, int32_t B, int32_t T, const void* x,
+                const uint8_t* padding_mask, const smx_dropout* drop, const void* dy, void* dx, const smx_convmod_grads* grads,
+                void* workspace, size_t workspace_bytes, void* stream);
+SMX_API size_t smx_summary_mixing_train_workspace_bytes(const smx_cell_weights* w, int dtype, int32_t B, int32_t T);
+SMX_API int smx_summary_mixing_train_fwd(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x,
+                const uint8_t* padding_mask, const smx_dropout* drop, void* y, void* workspace, size_t workspace_bytes, void* stream);
+SMX_API int smx_summary_mixing_train_bwd(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x,
+                const uint8_t* padding_mask, const smx_dropout* drop, const void* dy, void* dx, const smx_cell_grads* grads,
+                void* workspace, size_t workspace_bytes, void* stream);
+/* keep[e] = 1 when element e of `site` survives under `drop` (the mask the calls above apply); n elements, device pointer. */
+SMX_API int smx_dropout_keep_mask(const smx_dropout* drop, int32_t site, int64_t n, uint8_t* keep, void* stream);
 
 /* ConvolutionModule.forward (Conformer.py:166-340): y = conv_module(x) * mask (+ residual if given).
  * chunk_size > 0 selects Dynamic Chunk Convolution (Conformer.py:197-320). */

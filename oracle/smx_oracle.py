@@ -122,8 +122,10 @@ def summary_mixing(
     use_layernorm: bool = True,
     src_padding_mask: Optional[Tensor] = None,
     sum_mask: Optional[Tensor] = None,
+    drop=None,
 ) -> Tensor:
-    """SummaryMixing.forward, eval mode (dropout = identity).
+    """SummaryMixing.forward; eval mode (dropout = identity) unless ``drop`` is given: drop(key, tensor) stands in for
+    self.dropout on the concatenation (:252, :297), key = prefix + "cat" (oracle/dropout.py).
 
     mask prep summary_mixing.py:183-189; full/expdecay :198-253; fast :255-298; lite :300-324.
     ``src_padding_mask`` (B,T): 1/True = valid frame (TransformerASR.py:159-162,348-349)."""
@@ -150,6 +152,8 @@ def summary_mixing(
         if use_layernorm:
             summ = layer_norm(summ, _p(sd, prefix + "summary_norm.weight", x), _p(sd, prefix + "summary_norm.bias", x))
         cat = torch.cat([local, summ], dim=-1)  # :251-253
+        if drop is not None:
+            cat = drop(prefix + "cat", cat)  # :252
         return vanilla_nn(cat, sd, prefix + "summary_local_merging.", act)
 
     if mode == "SummaryMixing-fast":
@@ -162,6 +166,8 @@ def summary_mixing(
         else:
             summ = torch.matmul(sum_mask, s) / sum_mask.sum(dim=1).unsqueeze(-1)  # :292-294
         cat = torch.cat([local, summ], dim=-1)
+        if drop is not None:
+            cat = drop(prefix + "cat", cat)  # :297
         return vanilla_nn(cat, sd, prefix + "summary_local_merging.", act)  # :296-298
 
     if mode == "SummaryMixing-lite":
@@ -187,8 +193,9 @@ def convolution_module(
     causal: bool = False,
     masked_false_or_true: bool = False,
     chunk_size: Optional[int] = None,
+    drop=None,
 ) -> Tensor:
-    """ConvolutionModule.forward, Conformer.py:166-340 (dilation 1).  Non-chunked :322-332, chunked
+    """ConvolutionModule.forward, Conformer.py:166-340 (dilation 1); ``drop`` (training mode): the nn.Dropout ending after_conv (:163), key prefix + "out".  Non-chunked :322-332, chunked
     (Dynamic Chunk Convolution) :197-320, output masking :334-338.  ``mask`` is (B,T,1)."""
     cw = _p(sd, prefix + "conv.weight", x)  # (D,1,k)
     D, _, k = cw.shape
@@ -217,6 +224,8 @@ def convolution_module(
     out = layer_norm(out, _p(sd, prefix + "after_conv.0.weight", x), _p(sd, prefix + "after_conv.0.bias", x))
     out = activation(act, out)
     out = out @ _p(sd, prefix + "after_conv.2.weight", x).T + _p(sd, prefix + "after_conv.2.bias", x)
+    if drop is not None:
+        out = drop(prefix + "out", out)  # after_conv[3]
     if chunk_size is not None:
         out = out.reshape(B, -1, D)  # :313-316
         if frp > 0:
@@ -229,13 +238,16 @@ def convolution_module(
     return out
 
 
-def ffn_module(x: Tensor, sd: SD, prefix: str, act: str) -> Tensor:
+def ffn_module(x: Tensor, sd: SD, prefix: str, act: str, drop=None) -> Tensor:
     """ffn_module{1,2} = Sequential(LayerNorm, PositionalwiseFeedForward, Dropout), Conformer.py:470-484;
     PWFF (SpeechBrain, unpinned) = Linear(D,d_ffn) -> act -> Dropout -> Linear(d_ffn,D)."""
     h = layer_norm(x, _p(sd, prefix + "0.weight", x), _p(sd, prefix + "0.bias", x))
     h = h @ _p(sd, prefix + "1.ffn.0.weight", x).T + _p(sd, prefix + "1.ffn.0.bias", x)
     h = activation(act, h)
-    return h @ _p(sd, prefix + "1.ffn.3.weight", x).T + _p(sd, prefix + "1.ffn.3.bias", x)
+    if drop is not None:
+        h = drop(prefix + "inner", h)  # PositionalwiseFeedForward's dropout
+    out = h @ _p(sd, prefix + "1.ffn.3.weight", x).T + _p(sd, prefix + "1.ffn.3.bias", x)
+    return drop(prefix + "outer", out) if drop is not None else out  # ffn_module[2]
 
 
 def conformer_layer(
@@ -249,22 +261,23 @@ def conformer_layer(
     src_key_padding_mask: Optional[Tensor] = None,
     causal: bool = False,
     chunk_size: Optional[int] = None,
+    drop=None,
 ) -> Tensor:
-    """ConformerEncoderLayer.forward with attention_type == 'SummaryMixing', Conformer.py:490-548."""
+    """ConformerEncoderLayer.forward with attention_type == 'SummaryMixing', Conformer.py:490-548 (``drop``: training mode)."""
     conv_mask = None if src_key_padding_mask is None else src_key_padding_mask.unsqueeze(-1)  # :514-516
-    x = x + 0.5 * ffn_module(x, sd, prefix + "ffn_module1.", act)  # :518
+    x = x + 0.5 * ffn_module(x, sd, prefix + "ffn_module1.", act, drop)  # :518
     skip = x
     x = layer_norm(x, _p(sd, prefix + "norm1.norm.weight", x), _p(sd, prefix + "norm1.norm.bias", x))  # :521
     x = summary_mixing(
         x, sd, prefix + "mha_layer.", mode=mode, act=act, use_layernorm=use_layernorm,
-        src_padding_mask=src_key_padding_mask, sum_mask=src_mask,
+        src_padding_mask=src_key_padding_mask, sum_mask=src_mask, drop=drop,
     )  # :524-526
     x = x + skip  # :541
     x = x + convolution_module(
         x, sd, prefix + "convolution_module.", act=act, mask=conv_mask, causal=causal,
-        masked_false_or_true=False, chunk_size=chunk_size,
+        masked_false_or_true=False, chunk_size=chunk_size, drop=drop,
     )  # :543-545
-    y = x + 0.5 * ffn_module(x, sd, prefix + "ffn_module2.", act)
+    y = x + 0.5 * ffn_module(x, sd, prefix + "ffn_module2.", act, drop)
     return layer_norm(y, _p(sd, prefix + "norm2.norm.weight", x), _p(sd, prefix + "norm2.norm.bias", x))  # :547
 
 
@@ -280,12 +293,13 @@ def conformer_encoder(
     src_key_padding_mask: Optional[Tensor] = None,
     causal: bool = False,
     chunk_size: Optional[int] = None,
+    drop=None,
 ) -> Tensor:
-    """ConformerEncoder.forward, eval mode (no layerdrop), Conformer.py:797-827; final LN eps=1e-6 (:759)."""
+    """ConformerEncoder.forward (no layerdrop; ``drop``: training-mode dropout hook), Conformer.py:797-827; final LN eps=1e-6 (:759)."""
     for i in range(num_layers):
         x = conformer_layer(
             x, sd, f"{prefix}layers.{i}.", act=act, mode=mode, use_layernorm=use_layernorm,
-            src_mask=src_mask, src_key_padding_mask=src_key_padding_mask, causal=causal, chunk_size=chunk_size,
+            src_mask=src_mask, src_key_padding_mask=src_key_padding_mask, causal=causal, chunk_size=chunk_size, drop=drop,
         )
     return layer_norm(x, _p(sd, prefix + "norm.norm.weight", x), _p(sd, prefix + "norm.norm.bias", x), eps=1e-6)
 

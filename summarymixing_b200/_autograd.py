@@ -1,7 +1,9 @@
 """autograd nodes over libsmx's backward entry points (smx_layernorm_bwd, smx_ffn_bwd, smx_conv_module_bwd; the cell's
 node lives next to its module in nnet/summary_mixing.py).  Every backward call is self-contained — the library
 recomputes what it needs from the saved input — so a node keeps only its input (and the mask).  Gradients come back in
-fp32 and are cast to the parameter's dtype.  Dropout is not implemented: callers refuse training mode with p > 0."""
+fp32 and are cast to the parameter's dtype.  Training-mode dropout: a node called with p > 0 draws one seed from torch's
+CPU generator (torch.manual_seed applies), runs smx_*_train_fwd and hands the same (p, seed) to smx_*_train_bwd, which
+regenerates the counter-based masks (include/smx.h, smx_dropout)."""
 from __future__ import annotations
 
 import ctypes as C
@@ -18,10 +20,20 @@ def wants_grad(module, x) -> bool:
     return torch.is_grad_enabled() and (x.requires_grad or (module.training and any(p.requires_grad for p in module.parameters())))
 
 
-def refuse_dropout(module, p: float) -> None:
-    if module.training and p > 0:
-        raise NotImplementedError(
-            "summarymixing_b200: training-mode dropout is not implemented (build the model with dropout=0 or call .eval())")
+def new_dropout(module, p: float):
+    """smx_dropout for one module call: None outside training mode or with p == 0 (dropout is then the identity)."""
+    if not (module.training and p > 0):
+        return None
+    if p >= 1:
+        raise ValueError("summarymixing_b200: dropout p must be < 1")
+    return L.Dropout(float(p), int(torch.randint(0, 2 ** 62, (1,)).item()))
+
+
+def same_p(*ps) -> float:
+    """The one dropout probability a fused module call applies at all of its sites (the reference builds them from one argument)."""
+    if any(p != ps[0] for p in ps):
+        raise NotImplementedError(f"summarymixing_b200: one dropout probability per module call, got {ps}")
+    return ps[0]
 
 
 def pin_params(ctx, params) -> None:
@@ -87,8 +99,8 @@ class FFNFunction(torch.autograd.Function):
     params = [ln.weight, ln.bias, W1, b1, W2, b2] (+ [norm.weight, norm.bias])."""
 
     @staticmethod
-    def forward(ctx, fw, act, out_norm, x, *params):
-        # fw: L.FFNWeights (kept alive by the owning layer's WeightView); out_norm: (w_ptr, b_ptr, eps) or None
+    def forward(ctx, fw, act, out_norm, drop, x, *params):
+        # fw: L.FFNWeights (kept alive by the owning layer's WeightView); out_norm: (w_ptr, b_ptr, eps) or None; drop: L.Dropout or None
         dev = x.device
         xc = x.contiguous()
         rows = xc.numel() // xc.shape[-1]
@@ -97,9 +109,15 @@ class FFNFunction(torch.autograd.Function):
         dt = H.dtype_code(xc)
         ow, ob, oeps = out_norm if out_norm is not None else (None, None, 0.0)
         with torch.cuda.device(dev):
-            ws = H.workspace(dev, lib.smx_ffn_workspace_bytes(C.byref(fw), dt, rows))
-            L.check(lib.smx_ffn_fwd(C.byref(fw), act, dt, rows, xc.data_ptr(), ow, ob, oeps, y.data_ptr(), ws.data_ptr(),
-                                    ws.numel(), H.stream_ptr(dev)))
+            if drop is None:
+                ws = H.workspace(dev, lib.smx_ffn_workspace_bytes(C.byref(fw), dt, rows))
+                L.check(lib.smx_ffn_fwd(C.byref(fw), act, dt, rows, xc.data_ptr(), ow, ob, oeps, y.data_ptr(), ws.data_ptr(),
+                                        ws.numel(), H.stream_ptr(dev)))
+            else:
+                ws = H.workspace(dev, lib.smx_ffn_train_workspace_bytes(C.byref(fw), dt, rows, int(out_norm is not None)))
+                L.check(lib.smx_ffn_train_fwd(C.byref(fw), act, dt, rows, xc.data_ptr(), ow, ob, oeps, C.byref(drop), y.data_ptr(),
+                                              ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+        ctx.drop = drop
         ctx.fw, ctx.act, ctx.out_norm, ctx.params = fw, act, out_norm, params  # fw carries its tensors (_keepalive)
         pin_params(ctx, params)
         ctx.save_for_backward(xc)
@@ -120,14 +138,19 @@ class FFNFunction(torch.autograd.Function):
         if ctx.out_norm is not None:
             fg.out_ln_dw, fg.out_ln_db = grads[6].data_ptr(), grads[7].data_ptr()
         ow, ob, oeps = ctx.out_norm if ctx.out_norm is not None else (None, None, 0.0)
-        dx = torch.empty_like(xc) if ctx.needs_input_grad[3] else None
+        dx = torch.empty_like(xc) if ctx.needs_input_grad[4] else None
         lib = L.lib()
         dt = H.dtype_code(xc)
         with torch.cuda.device(dev):
-            ws = H.workspace(dev, lib.smx_ffn_bwd_workspace_bytes(C.byref(ctx.fw), dt, rows, int(ctx.out_norm is not None)))
-            L.check(lib.smx_ffn_bwd(C.byref(ctx.fw), ctx.act, dt, rows, xc.data_ptr(), ow, ob, oeps, dyc.data_ptr(),
-                                    H.p_or_none(dx), C.byref(fg), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
-        return (None, None, None, dx, *_cast_out(ctx, 4, grads, ctx.params))
+            if ctx.drop is None:
+                ws = H.workspace(dev, lib.smx_ffn_bwd_workspace_bytes(C.byref(ctx.fw), dt, rows, int(ctx.out_norm is not None)))
+                L.check(lib.smx_ffn_bwd(C.byref(ctx.fw), ctx.act, dt, rows, xc.data_ptr(), ow, ob, oeps, dyc.data_ptr(),
+                                        H.p_or_none(dx), C.byref(fg), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+            else:
+                ws = H.workspace(dev, lib.smx_ffn_train_workspace_bytes(C.byref(ctx.fw), dt, rows, int(ctx.out_norm is not None)))
+                L.check(lib.smx_ffn_train_bwd(C.byref(ctx.fw), ctx.act, dt, rows, xc.data_ptr(), ow, ob, oeps, C.byref(ctx.drop),
+                                              dyc.data_ptr(), H.p_or_none(dx), C.byref(fg), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+        return (None, None, None, None, dx, *_cast_out(ctx, 5, grads, ctx.params))
 
 
 class ConvModuleFunction(torch.autograd.Function):
@@ -135,7 +158,7 @@ class ConvModuleFunction(torch.autograd.Function):
     params = [ln.weight, ln.bias, Wb, bb, dw.weight, dw.bias, after_ln.weight, after_ln.bias, Wo, bo]."""
 
     @staticmethod
-    def forward(ctx, cw, act, x, m8, *params):
+    def forward(ctx, cw, act, drop, x, m8, *params):
         dev = x.device
         xc = x.contiguous()
         B, T, _ = xc.shape
@@ -143,9 +166,15 @@ class ConvModuleFunction(torch.autograd.Function):
         lib = L.lib()
         dt = H.dtype_code(xc)
         with torch.cuda.device(dev):
-            ws = H.workspace(dev, lib.smx_conv_module_workspace_bytes(C.byref(cw), dt, B, T))
-            L.check(lib.smx_conv_module_fwd(C.byref(cw), act, dt, B, T, 0, xc.data_ptr(), H.p_or_none(m8), None, y.data_ptr(),
-                                            ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+            if drop is None:
+                ws = H.workspace(dev, lib.smx_conv_module_workspace_bytes(C.byref(cw), dt, B, T))
+                L.check(lib.smx_conv_module_fwd(C.byref(cw), act, dt, B, T, 0, xc.data_ptr(), H.p_or_none(m8), None, y.data_ptr(),
+                                                ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+            else:
+                ws = H.workspace(dev, lib.smx_conv_module_train_workspace_bytes(C.byref(cw), dt, B, T))
+                L.check(lib.smx_conv_module_train_fwd(C.byref(cw), act, dt, B, T, xc.data_ptr(), H.p_or_none(m8), C.byref(drop),
+                                                      y.data_ptr(), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+        ctx.drop = drop
         ctx.cw, ctx.act, ctx.params = cw, act, params
         pin_params(ctx, params)
         ctx.save_for_backward(xc, m8)
@@ -165,14 +194,19 @@ class ConvModuleFunction(torch.autograd.Function):
         cg.dw_dw, cg.dw_db = grads[4].data_ptr(), grads[5].data_ptr()
         cg.after_ln_dw, cg.after_ln_db = grads[6].data_ptr(), grads[7].data_ptr()
         cg.out.dw, cg.out.db = grads[8].data_ptr(), grads[9].data_ptr()
-        dx = torch.empty_like(xc) if ctx.needs_input_grad[2] else None
+        dx = torch.empty_like(xc) if ctx.needs_input_grad[3] else None
         lib = L.lib()
         dt = H.dtype_code(xc)
         with torch.cuda.device(dev):
             ws = H.workspace(dev, lib.smx_conv_module_bwd_workspace_bytes(C.byref(ctx.cw), dt, B, T))
-            L.check(lib.smx_conv_module_bwd(C.byref(ctx.cw), ctx.act, dt, B, T, xc.data_ptr(), H.p_or_none(m8), dyc.data_ptr(),
-                                            H.p_or_none(dx), C.byref(cg), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
-        return (None, None, dx, None, *_cast_out(ctx, 4, grads, ctx.params))
+            if ctx.drop is None:
+                L.check(lib.smx_conv_module_bwd(C.byref(ctx.cw), ctx.act, dt, B, T, xc.data_ptr(), H.p_or_none(m8), dyc.data_ptr(),
+                                                H.p_or_none(dx), C.byref(cg), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+            else:
+                L.check(lib.smx_conv_module_train_bwd(C.byref(ctx.cw), ctx.act, dt, B, T, xc.data_ptr(), H.p_or_none(m8), C.byref(ctx.drop),
+                                                      dyc.data_ptr(), H.p_or_none(dx), C.byref(cg), ws.data_ptr(), ws.numel(),
+                                                      H.stream_ptr(dev)))
+        return (None, None, None, dx, None, *_cast_out(ctx, 5, grads, ctx.params))
 
 
 class VanillaNNFunction(torch.autograd.Function):

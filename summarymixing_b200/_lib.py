@@ -56,6 +56,11 @@ class FFNGrads(C.Structure):
     _fields_ = [("ln_dw", fp), ("ln_db", fp), ("w1", LinearGrad), ("w2", LinearGrad), ("out_ln_dw", fp), ("out_ln_db", fp)]
 
 
+class Dropout(C.Structure):
+    """smx_dropout: p and the seed of the counter-based masks (include/smx.h)."""
+    _fields_ = [("p", C.c_float), ("seed", C.c_uint64)]
+
+
 class ConvModGrads(C.Structure):
     _fields_ = [("ln_dw", fp), ("ln_db", fp), ("bottleneck", LinearGrad), ("dw_dw", fp), ("dw_db", fp), ("after_ln_dw", fp),
                 ("after_ln_db", fp), ("out", LinearGrad)]
@@ -135,6 +140,19 @@ _PROTOS = {
     "smx_conv_module_bwd_workspace_bytes": (_sz, [C.POINTER(ConvModWeights), _i, _i, _i]),
     "smx_conv_module_bwd": (_i, [C.POINTER(ConvModWeights), _i, _i, _i, _i, _vp, _vp, _vp, _vp, C.POINTER(ConvModGrads),
                                  _vp, _sz, _vp]),
+    "smx_ffn_train_workspace_bytes": (_sz, [C.POINTER(FFNWeights), _i, C.c_int64, _i]),
+    "smx_ffn_train_fwd": (_i, [C.POINTER(FFNWeights), _i, _i, C.c_int64, _vp, _vp, _vp, C.c_float, C.POINTER(Dropout), _vp, _vp, _sz, _vp]),
+    "smx_ffn_train_bwd": (_i, [C.POINTER(FFNWeights), _i, _i, C.c_int64, _vp, _vp, _vp, C.c_float, C.POINTER(Dropout), _vp, _vp,
+                               C.POINTER(FFNGrads), _vp, _sz, _vp]),
+    "smx_conv_module_train_workspace_bytes": (_sz, [C.POINTER(ConvModWeights), _i, _i, _i]),
+    "smx_conv_module_train_fwd": (_i, [C.POINTER(ConvModWeights), _i, _i, _i, _i, _vp, _vp, C.POINTER(Dropout), _vp, _vp, _sz, _vp]),
+    "smx_conv_module_train_bwd": (_i, [C.POINTER(ConvModWeights), _i, _i, _i, _i, _vp, _vp, C.POINTER(Dropout), _vp, _vp,
+                                       C.POINTER(ConvModGrads), _vp, _sz, _vp]),
+    "smx_summary_mixing_train_workspace_bytes": (_sz, [C.POINTER(CellWeights), _i, _i, _i]),
+    "smx_summary_mixing_train_fwd": (_i, [C.POINTER(CellWeights), _i, _i, _i, _vp, _vp, C.POINTER(Dropout), _vp, _vp, _sz, _vp]),
+    "smx_summary_mixing_train_bwd": (_i, [C.POINTER(CellWeights), _i, _i, _i, _vp, _vp, C.POINTER(Dropout), _vp, _vp,
+                                          C.POINTER(CellGrads), _vp, _sz, _vp]),
+    "smx_dropout_keep_mask": (_i, [C.POINTER(Dropout), _i, C.c_int64, _vp, _vp]),
     "smx_conv_module_workspace_bytes": (_sz, [C.POINTER(ConvModWeights), _i, _i, _i]),
     "smx_conv_module_fwd": (_i, [C.POINTER(ConvModWeights), _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "smx_ffn_workspace_bytes": (_sz, [C.POINTER(FFNWeights), _i, _i64]),

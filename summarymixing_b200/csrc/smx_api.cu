@@ -315,6 +315,125 @@ int smx_conv_module_bwd(const smx_convmod_weights* w, int act, int dtype, int32_
   return convmod_bwd_generic(w, act, B, T, x, dtype, padding_mask, dy, dtype, dx, dtype, grads, a, (cudaStream_t)stream);
 }
 
+// ---- training-mode forward / backward with dropout ------------------------------------------------
+static int check_drop(const smx_dropout* d) {
+  if (d && !(d->p >= 0.0f && d->p < 1.0f)) return fail(SMX_ERR_BAD_ARG, "dropout p must be in [0, 1), got %g", (double)d->p);
+  return SMX_OK;
+}
+static const smx_dropout kSizingDrop{0.5f, 0};  // sizing runs take the dropout branches (the larger workspace)
+size_t smx_ffn_train_workspace_bytes(const smx_ffn_weights* w, int dtype, int64_t rows, int has_out_ln) {
+  if (!w || rows <= 0) return 0;
+  smx_ffn_grads g{kDummy, kDummy, {kDummy, kDummy}, {kDummy, kDummy}, kDummy, kDummy};
+  Arena a(nullptr, 0, true), b(nullptr, 0, true);
+  float* const oln = has_out_ln ? kDummy : nullptr;
+  if (ffn_bwd_generic(w, 0, rows, nullptr, dtype, oln, oln, 0.f, nullptr, dtype, kDummy, dtype, &g, a, nullptr, &kSizingDrop) != SMX_OK) return 0;
+  if (ffn_bwd_generic(w, 0, rows, nullptr, dtype, oln, oln, 0.f, nullptr, dtype, nullptr, dtype, &g, b, nullptr, &kSizingDrop, kDummy, dtype) != SMX_OK) return 0;
+  return a.peak > b.peak ? a.peak : b.peak;
+}
+static int ffn_train(const smx_ffn_weights* w, int act, int dtype, int64_t rows, const void* x, const float* out_ln_w, const float* out_ln_b,
+                     float out_ln_eps, const smx_dropout* drop, const void* dy, void* dx, const smx_ffn_grads* grads, void* y, void* workspace,
+                     size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");
+  if (rows <= 0) return fail(SMX_ERR_BAD_ARG, "rows must be positive");
+  SMX_TRY(check_drop(drop));
+  SMX_TRY(check_ptr(x, "x"));
+  if (y) SMX_TRY(check_ptr(y, "y")); else { if (!grads) return fail(SMX_ERR_BAD_ARG, "grads is NULL"); SMX_TRY(check_ptr(dy, "dy")); }
+  if (dx) SMX_TRY(check_ptr(dx, "dx"));
+  SMX_TRY(check_arch());
+  const size_t need = smx_ffn_train_workspace_bytes(w, dtype, rows, out_ln_w != nullptr);
+  if (need == 0) return SMX_ERR_BAD_ARG;
+  if (need > workspace_bytes || !workspace) return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  Arena a(workspace, workspace_bytes, false);
+  smx_ffn_grads none{};
+  return ffn_bwd_generic(w, act, rows, x, dtype, out_ln_w, out_ln_b, out_ln_eps, dy, dtype, dx, dtype, grads ? grads : &none, a, (cudaStream_t)stream,
+                         drop, y, dtype);
+}
+int smx_ffn_train_fwd(const smx_ffn_weights* w, int act, int dtype, int64_t rows, const void* x, const float* out_ln_w, const float* out_ln_b,
+                      float out_ln_eps, const smx_dropout* drop, void* y, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!y) return fail(SMX_ERR_BAD_ARG, "y is NULL");
+  return ffn_train(w, act, dtype, rows, x, out_ln_w, out_ln_b, out_ln_eps, drop, nullptr, nullptr, nullptr, y, workspace, workspace_bytes, stream);
+}
+int smx_ffn_train_bwd(const smx_ffn_weights* w, int act, int dtype, int64_t rows, const void* x, const float* out_ln_w, const float* out_ln_b,
+                      float out_ln_eps, const smx_dropout* drop, const void* dy, void* dx, const smx_ffn_grads* grads, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  return ffn_train(w, act, dtype, rows, x, out_ln_w, out_ln_b, out_ln_eps, drop, dy, dx, grads, nullptr, workspace, workspace_bytes, stream);
+}
+size_t smx_conv_module_train_workspace_bytes(const smx_convmod_weights* w, int dtype, int32_t B, int32_t T) {
+  return smx_conv_module_bwd_workspace_bytes(w, dtype, B, T);  // the forward-only run uses a prefix of the backward's buffers
+}
+static int convmod_train(const smx_convmod_weights* w, int act, int dtype, int32_t B, int32_t T, const void* x, const uint8_t* padding_mask,
+                         const smx_dropout* drop, const void* dy, void* dx, const smx_convmod_grads* grads, void* y, void* workspace,
+                         size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");
+  SMX_TRY(check_bt(B, T));
+  SMX_TRY(check_drop(drop));
+  SMX_TRY(check_ptr(x, "x"));
+  if (y) SMX_TRY(check_ptr(y, "y")); else { if (!grads) return fail(SMX_ERR_BAD_ARG, "grads is NULL"); SMX_TRY(check_ptr(dy, "dy")); }
+  if (dx) SMX_TRY(check_ptr(dx, "dx"));
+  SMX_TRY(check_arch());
+  const size_t need = smx_conv_module_train_workspace_bytes(w, dtype, B, T);
+  if (need == 0) return SMX_ERR_BAD_ARG;
+  if (need > workspace_bytes || !workspace) return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  Arena a(workspace, workspace_bytes, false);
+  smx_convmod_grads none{};
+  return convmod_bwd_generic(w, act, B, T, x, dtype, padding_mask, dy, dtype, dx, dtype, grads ? grads : &none, a, (cudaStream_t)stream, drop, y, dtype);
+}
+int smx_conv_module_train_fwd(const smx_convmod_weights* w, int act, int dtype, int32_t B, int32_t T, const void* x, const uint8_t* padding_mask,
+                              const smx_dropout* drop, void* y, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!y) return fail(SMX_ERR_BAD_ARG, "y is NULL");
+  return convmod_train(w, act, dtype, B, T, x, padding_mask, drop, nullptr, nullptr, nullptr, y, workspace, workspace_bytes, stream);
+}
+int smx_conv_module_train_bwd(const smx_convmod_weights* w, int act, int dtype, int32_t B, int32_t T, const void* x, const uint8_t* padding_mask,
+                              const smx_dropout* drop, const void* dy, void* dx, const smx_convmod_grads* grads, void* workspace,
+                              size_t workspace_bytes, void* stream) {
+  return convmod_train(w, act, dtype, B, T, x, padding_mask, drop, dy, dx, grads, nullptr, workspace, workspace_bytes, stream);
+}
+size_t smx_summary_mixing_train_workspace_bytes(const smx_cell_weights* w, int dtype, int32_t B, int32_t T) {
+  if (!w || B <= 0 || T <= 0) return 0;
+  smx_cell_grads g;
+  all_grads_wanted(g);
+  Arena a(nullptr, 0, true);
+  if (cell_bwd_generic(w, B, T, nullptr, dtype, nullptr, nullptr, dtype, (void*)(uintptr_t)256, dtype, &g, a, nullptr, &kSizingDrop) != SMX_OK) return 0;
+  return a.peak;
+}
+static int cell_train(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x, const uint8_t* padding_mask,
+                      const smx_dropout* drop, const void* dy, void* dx, const smx_cell_grads* grads, void* y, void* workspace,
+                      size_t workspace_bytes, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");
+  SMX_TRY(check_bt(B, T));
+  SMX_TRY(check_drop(drop));
+  SMX_TRY(check_ptr(x, "x"));
+  if (y) SMX_TRY(check_ptr(y, "y")); else { if (!grads) return fail(SMX_ERR_BAD_ARG, "grads is NULL"); SMX_TRY(check_ptr(dy, "dy")); }
+  if (dx) SMX_TRY(check_ptr(dx, "dx"));
+  SMX_TRY(check_arch());
+  const size_t need = smx_summary_mixing_train_workspace_bytes(w, dtype, B, T);
+  if (need == 0) return SMX_ERR_BAD_ARG;
+  if (need > workspace_bytes || !workspace) return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  Arena a(workspace, workspace_bytes, false);
+  smx_cell_grads none{};
+  return cell_bwd_generic(w, B, T, x, dtype, padding_mask, dy, dtype, dx, dtype, grads ? grads : &none, a, (cudaStream_t)stream, drop, y, dtype);
+}
+int smx_summary_mixing_train_fwd(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x, const uint8_t* padding_mask,
+                                 const smx_dropout* drop, void* y, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!y) return fail(SMX_ERR_BAD_ARG, "y is NULL");
+  return cell_train(w, dtype, B, T, x, padding_mask, drop, nullptr, nullptr, nullptr, y, workspace, workspace_bytes, stream);
+}
+int smx_summary_mixing_train_bwd(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x, const uint8_t* padding_mask,
+                                 const smx_dropout* drop, const void* dy, void* dx, const smx_cell_grads* grads, void* workspace,
+                                 size_t workspace_bytes, void* stream) {
+  return cell_train(w, dtype, B, T, x, padding_mask, drop, dy, dx, grads, nullptr, workspace, workspace_bytes, stream);
+}
+int smx_dropout_keep_mask(const smx_dropout* drop, int32_t site, int64_t n, uint8_t* keep, void* stream) {
+  SMX_TRY(check_drop(drop));
+  if (n < 0 || site < 0) return fail(SMX_ERR_BAD_ARG, "n and site must be non-negative");
+  if (n > 0) SMX_TRY(check_ptr(keep, "keep"));
+  SMX_TRY(check_arch());
+  return dropout_keep_mask(drop, site, n, keep, (cudaStream_t)stream);
+}
+
 // ---- ConvolutionModule ---------------------------------------------------------------------------
 size_t smx_conv_module_workspace_bytes(const smx_convmod_weights* w, int dtype, int32_t B, int32_t T) {
   if (!w || B <= 0 || T <= 0) return 0;

@@ -74,6 +74,64 @@ __device__ __forceinline__ float bw_dact(int act, float x) {
   }
 }
 
+// ---- training-mode dropout: counter-based masks (Philox4x32-10), a function of (seed, site, element index) only, so that the
+// backward regenerates the forward's mask.  Element e of site s: counter (e / 4 [64 bit], s, 0), key = seed, word e % 4;
+// dropped when word < p * 2^32, kept values scaled by 1 / (1 - p) (torch.nn.Dropout's semantics; its random stream is not matched).
+__device__ __forceinline__ uint4 philox4x32_10(uint4 c, uint2 k) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+    const uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+    c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+    k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+  }
+  return c;
+}
+__device__ __forceinline__ uint4 drop_words(uint64_t seed, uint32_t site, int64_t quad) {
+  return philox4x32_10(make_uint4((uint32_t)quad, (uint32_t)((uint64_t)quad >> 32), site, 0u), make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+}
+// buf[e] = keep(e) ? buf[e] * scale : 0, in place (fp32, contiguous; one Philox call per four elements)
+__global__ void __launch_bounds__(256) dropout_kernel(float* buf, int64_t n, uint64_t seed, uint32_t site, uint32_t thresh, float scale) {
+  const int64_t quad = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e0 = quad * 4;
+  if (e0 >= n) return;
+  const uint4 r = drop_words(seed, site, quad);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (e0 + i < n) buf[e0 + i] = w[i] >= thresh ? buf[e0 + i] * scale : 0.0f;
+}
+__global__ void __launch_bounds__(256) dropout_mask_kernel(uint8_t* keep, int64_t n, uint64_t seed, uint32_t site, uint32_t thresh) {
+  const int64_t quad = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e0 = quad * 4;
+  if (e0 >= n) return;
+  const uint4 r = drop_words(seed, site, quad);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (e0 + i < n) keep[e0 + i] = w[i] >= thresh ? 1 : 0;
+}
+// cat[row] = [ L[row, 0:Dl) | mu[row / T, 0:Ds) ]: the combiner's input written out (needed only when dropout acts on it)
+__global__ void __launch_bounds__(256) concat_bcast_kernel(const float* L, int64_t ldl, const float* mu, int T, int Dl, int Ds, int64_t n, float* cat) {
+  const int W = Dl + Ds;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const int64_t row = i / W;
+    const int c = (int)(i - row * W);
+    cat[i] = c < Dl ? L[row * ldl + c] : mu[(row / T) * Ds + (c - Dl)];
+  }
+}
+__global__ void __launch_bounds__(256) take_cols_kernel(const float* src, int64_t lds, int ncols, int64_t n, float* dst, int64_t ldd) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const int64_t row = i / ncols;
+    const int c = (int)(i - row * ncols);
+    dst[row * ldd + c] = src[row * lds + c];
+  }
+}
+// y = x + alpha * u
+__global__ void __launch_bounds__(256) axpy_kernel(const float* x, const float* u, float alpha, int64_t n, float* y) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) y[i] = fmaf(alpha, u[i], x[i]);
+}
+
 // out = act(z) (* rowmask[row])
 __global__ void __launch_bounds__(256) act_fwd_kernel(const float* z, int64_t n, int ncols, int act, const uint8_t* rowmask,
                                                       float* out) {
@@ -185,6 +243,23 @@ __global__ void __launch_bounds__(256) bcast_scale_kernel(const float* src, cons
 unsigned ew_grid(int64_t n) {
   int64_t g = (n + 255) / 256;
   return (unsigned)(g < 1 ? 1 : (g > 148 * 16 ? 148 * 16 : g));
+}
+
+struct Drop { bool on; uint64_t seed; uint32_t thresh; float scale; };
+Drop make_drop(const smx_dropout* d) {
+  Drop r{false, 0, 0, 1.0f};
+  if (d && d->p > 0.0f) {
+    const double t = (double)d->p * 4294967296.0;
+    r.on = true; r.seed = d->seed; r.thresh = t >= 4294967295.0 ? 4294967295u : (uint32_t)t; r.scale = 1.0f / (1.0f - d->p);
+  }
+  return r;
+}
+int dropout_inplace(float* buf, int64_t n, const Drop& d, uint32_t site, cudaStream_t st) {
+  if (!d.on || n <= 0) return SMX_OK;
+  const int64_t quads = (n + 3) / 4;
+  dropout_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(buf, n, d.seed, site, d.thresh, d.scale);
+  count_launch();
+  return check_launch("dropout_kernel");
 }
 
 // Tensor-core form of the three linear primitives below (recompute, data gradient, weight gradient): split-bf16 operands,
@@ -463,7 +538,13 @@ int branch_bwd(const smx_linear* blocks, const smx_linear_grad* g, int n, int ac
 }  // namespace
 
 int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int x_dt, const uint8_t* mask, const void* dy, int dy_dt,
-                     void* dx, int dx_dt, const smx_cell_grads* g, Arena& ws, cudaStream_t st) {
+                     void* dx, int dx_dt, const smx_cell_grads* g, Arena& ws, cudaStream_t st, const smx_dropout* drop, void* y_fwd, int y_dt) {
+  // drop (p > 0): dropout on the combiner's input cat = [local | summary] (summary_mixing.py:252, :297) -- the concatenation is
+  // then written out per frame (the per-utterance bias shortcut no longer holds: every frame draws its own mask over the summary).
+  // y_fwd: training-mode FORWARD only (same recomputation, result written to y_fwd, no gradients).
+  const Drop dr = make_drop(drop);
+  if ((dr.on || y_fwd) && w->mode == SMX_MODE_LITE && y_fwd)
+    return fail(SMX_ERR_UNSUPPORTED, "cell training forward: mode 'SummaryMixing-lite' has no dropout (use smx_summary_mixing_fwd)");
   if (w->mode != SMX_MODE_FULL && w->mode != SMX_MODE_LITE && w->mode != SMX_MODE_FAST)
     return fail(SMX_ERR_UNSUPPORTED, "smx_summary_mixing_bwd does not handle mode %d ('SummaryMixing-expdecay')", w->mode);
   const int64_t rows = (int64_t)B * T;
@@ -504,6 +585,49 @@ int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int
     BWF_BUF(dG, rows * 2 * Dl);
     BWF_BUF(dmean, (size_t)B * Dl);
     BWF_BUF(inv, (size_t)B);
+    if (dr.on || y_fwd) {
+      // written-out combiner: cat = dropout([G[:, :D_l] | mean_b]), zc = cat Wc^T + b_c
+      BWF_BUF(cat, rows * 2 * Dl);
+      if (!ws.dry) {
+        SMX_TRY(masked_mean(G + Dl, 2 * Dl, mask, B, T, Dl, mean, SMX_F32, st));
+        concat_bcast_kernel<<<ew_grid(rows * 2 * Dl), 256, 0, st>>>(G, 2 * Dl, mean, T, Dl, Dl, rows * 2 * Dl, cat);
+        count_launch();
+        SMX_TRY(check_launch("concat_bcast_kernel"));
+        SMX_TRY(dropout_inplace(cat, rows * 2 * Dl, dr, 0, st));
+        SMX_TRY(lin_fwd(w->merge, cat, 2 * Dl, rows, zc, Dout, true, 0, 0, nullptr, 1, st));
+      }
+      if (y_fwd) {
+        if (!ws.dry) {
+          SMX_TRY(act_fwd(zc, rows, Dout, act, nullptr, zc, st));
+          SMX_TRY(convert(zc, SMX_F32, y_fwd, y_dt, rows * Dout, st));
+        }
+        ws.release(m0);
+        return SMX_OK;
+      }
+      if (!ws.dry) SMX_TRY(act_bwd(zc, dy, dy_dt, rows, Dout, act, nullptr, zc, st));  // zc now holds dzc
+      if (g->merge.dw) SMX_TRY(lin_wgrad(w->merge, zc, Dout, cat, 2 * Dl, rows, g->merge.dw, 0, 0, ws, st));
+      if (g->merge.db) SMX_TRY(colsum_all(zc, Dout, rows, Dout, g->merge.db, ws, st));
+      float* dcat = cat;  // cat is dead
+      if (!ws.dry) {
+        SMX_TRY(lin_dgrad(w->merge, zc, Dout, rows, dcat, SMX_F32, 2 * Dl, 0, 0, nullptr, st));
+        SMX_TRY(dropout_inplace(dcat, rows * 2 * Dl, dr, 0, st));
+        take_cols_kernel<<<ew_grid(rows * Dl), 256, 0, st>>>(dcat, 2 * Dl, Dl, rows * Dl, dG, 2 * Dl);  // dG[:, :D_l]
+        count_launch();
+        SMX_TRY(check_launch("take_cols_kernel"));
+        colsum_kernel<<<dim3((Dl + 31) / 32, B), 256, 0, st>>>(dcat + Dl, 2 * Dl, rows, T, Dl, dmean);  // d mean_b = sum_t dcat[b,t,D_l:]
+        count_launch();
+        SMX_TRY(check_launch("colsum_kernel"));
+        inv_count_kernel<<<B, 32, 0, st>>>(mask, T, inv);
+        count_launch();
+        SMX_TRY(check_launch("inv_count_kernel"));
+        bcast_scale_kernel<<<ew_grid(rows * Dl), 256, 0, st>>>(dmean, inv, T, Dl, rows * Dl, dG + Dl, 2 * Dl);  // dG[:, D_l:]
+        count_launch();
+        SMX_TRY(check_launch("bcast_scale_kernel"));
+      }
+      SMX_TRY(branch_bwd(&w->global_proj, &g->global_proj, 1, act, fg, rows, mask, dG, dx, dx_dt, nullptr, dx != nullptr, ws, st));
+      ws.release(m0);
+      return SMX_OK;
+    }
     if (!ws.dry) {
       SMX_TRY(masked_mean(G + Dl, 2 * Dl, mask, B, T, Dl, mean, SMX_F32, st));
       SMX_TRY(lin_fwd(w->merge, mean, Dl, B, cbias, Dout, true, Dl, Dl, nullptr, 1, st));
@@ -606,13 +730,48 @@ int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int
     BW_RUN(layernorm(mean, SMX_F32, Ds, w->summary_norm_w, w->summary_norm_b, 1e-5f, SMX_ACT_IDENTITY, mub, SMX_F32, Ds, B, Ds, st));
     mu = mub;
   }
+  BW_BUF(zc, rows * Dout);
+  BW_BUF(dL, rows * Dl);
+  BW_BUF(dmu, (size_t)B * Ds);
+  float* dzc = zc;
+  if (dr.on || y_fwd) {
+    // written-out combiner: cat = dropout([L | mu_b]), zc = cat Wc^T + b_c
+    BW_BUF(cat, rows * (Dl + Ds));
+    if (!ws.dry) {
+      concat_bcast_kernel<<<ew_grid(rows * (Dl + Ds)), 256, 0, st>>>(Lmat, Dl, mu, T, Dl, Ds, rows * (Dl + Ds), cat);
+      count_launch();
+      SMX_TRY(check_launch("concat_bcast_kernel"));
+      SMX_TRY(dropout_inplace(cat, rows * (Dl + Ds), dr, 0, st));
+      SMX_TRY(lin_fwd(w->merge, cat, Dl + Ds, rows, zc, Dout, true, 0, 0, nullptr, 1, st));
+    }
+    if (y_fwd) {
+      if (!ws.dry) {
+        SMX_TRY(act_fwd(zc, rows, Dout, act, nullptr, zc, st));
+        SMX_TRY(convert(zc, SMX_F32, y_fwd, y_dt, rows * Dout, st));
+      }
+      ws.release(m0);
+      return SMX_OK;
+    }
+    BW_RUN(act_bwd(zc, dy, dy_dt, rows, Dout, act, nullptr, dzc, st));
+    if (g->merge.dw) SMX_TRY(lin_wgrad(w->merge, dzc, Dout, cat, Dl + Ds, rows, g->merge.dw, 0, 0, ws, st));
+    if (g->merge.db) SMX_TRY(colsum_all(dzc, Dout, rows, Dout, g->merge.db, ws, st));
+    float* dcat = cat;  // cat is dead
+    if (!ws.dry) {
+      SMX_TRY(lin_dgrad(w->merge, dzc, Dout, rows, dcat, SMX_F32, Dl + Ds, 0, 0, nullptr, st));
+      SMX_TRY(dropout_inplace(dcat, rows * (Dl + Ds), dr, 0, st));
+      take_cols_kernel<<<ew_grid(rows * Dl), 256, 0, st>>>(dcat, Dl + Ds, Dl, rows * Dl, dL, Dl);
+      count_launch();
+      SMX_TRY(check_launch("take_cols_kernel"));
+      colsum_kernel<<<dim3((Ds + 31) / 32, B), 256, 0, st>>>(dcat + Dl, Dl + Ds, rows, T, Ds, dmu);  // d mu_b = sum_t dcat[b,t,D_l:]
+      count_launch();
+      SMX_TRY(check_launch("colsum_kernel"));
+    }
+  } else {
   BW_BUF(cbias, (size_t)B * Dout);
   BW_RUN(lin_fwd(w->merge, mu, Ds, B, cbias, Dout, true, Dl, Ds, nullptr, 1, st));
-  BW_BUF(zc, rows * Dout);
   BW_RUN(lin_fwd(w->merge, Lmat, Dl, rows, zc, Dout, false, 0, Dl, cbias, T, st));
 
   // ---- combiner ----
-  float* dzc = zc;
   BW_RUN(act_bwd(zc, dy, dy_dt, rows, Dout, act, nullptr, dzc, st));
   BW_BUF(dcb, (size_t)B * Dout);
   if (!ws.dry) {  // per-utterance column sums
@@ -625,10 +784,9 @@ int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int
     SMX_TRY(lin_wgrad(w->merge, dcb, Dout, mu, Ds, B, g->merge.dw, Dl, Ds, ws, st));
   }
   if (g->merge.db) SMX_TRY(colsum_all(dcb, Dout, B, Dout, g->merge.db, ws, st));
-  BW_BUF(dL, rows * Dl);
   BW_RUN(lin_dgrad(w->merge, dzc, Dout, rows, dL, SMX_F32, Dl, 0, Dl, nullptr, st));
-  BW_BUF(dmu, (size_t)B * Ds);
   BW_RUN(lin_dgrad(w->merge, dcb, Dout, B, dmu, SMX_F32, Ds, Dl, Ds, nullptr, st));
+  }
 
   // ---- summary branch: LN_s, mean, MLP ----
   if (use_ln) SMX_TRY(ln_bwd(mean, B, Ds, w->summary_norm_w, dmu, g->summary_norm_dw, g->summary_norm_db, ws, st));
@@ -796,7 +954,11 @@ int layernorm_bwd_generic(const void* x, int x_dt, int64_t rows, int D, const fl
 
 // y = x + 0.5 * W2 act(W1 LN(x) + b1) + 0.5 * b2;  y = LN_out(y) when out_ln_w               Conformer.py:470-484, 518, 547
 int ffn_bwd_generic(const smx_ffn_weights* w, int act, int64_t rows, const void* x, int x_dt, const float* oln_w, const float* oln_b,
-                    float oln_eps, const void* dy, int dy_dt, void* dx, int dx_dt, const smx_ffn_grads* g, Arena& ws, cudaStream_t st) {
+                    float oln_eps, const void* dy, int dy_dt, void* dx, int dx_dt, const smx_ffn_grads* g, Arena& ws, cudaStream_t st,
+                    const smx_dropout* drop, void* y_fwd, int y_dt) {
+  // drop (p > 0): site 0 = the dropout inside PositionalwiseFeedForward (after the activation), site 1 = the nn.Dropout that follows
+  // the block in ffn_module (Conformer.py:470-484).  y_fwd: training-mode FORWARD only.
+  const Drop dr = make_drop(drop);
   const int D = w->w1.in_dim, F = w->w1.out_dim;
   if (w->w2.in_dim != F || w->w2.out_dim != D || w->w1.n_split > 1 || w->w2.n_split > 1)
     return fail(SMX_ERR_BAD_ARG, "ffn backward: inconsistent dims");
@@ -816,9 +978,26 @@ int ffn_bwd_generic(const smx_ffn_weights* w, int act, int64_t rows, const void*
   BW_RUN(lin_fwd(w->w1, xn, D, rows, z1, F, true, 0, 0, nullptr, 1, st));
   BW_BUF(h, rows * F);
   BW_RUN(act_fwd(z1, rows, F, act, nullptr, h, st));
+  BW_RUN(dropout_inplace(h, rows * F, dr, 0, st));
+  float* ypre_d = nullptr;  // x + 0.5 * dropout(h W2^T + b2), written out when dropout acts on u or only the forward is wanted
+  if (y_fwd || (oln_w && dr.on)) {
+    BW_BUF(u, rows * D);
+    BW_RUN(lin_fwd(w->w2, h, F, rows, u, D, true, 0, 0, nullptr, 1, st));
+    BW_RUN(dropout_inplace(u, rows * D, dr, 1, st));
+    BW_LAUNCH("axpy_kernel", axpy_kernel<<<ew_grid(rows * D), 256, 0, st>>>(x32, u, 0.5f, rows * D, u));
+    ypre_d = u;
+    if (y_fwd) {
+      if (oln_w) BW_RUN(layernorm(u, SMX_F32, D, oln_w, oln_b, oln_eps, SMX_ACT_IDENTITY, y_fwd, y_dt, D, rows, D, st));
+      else BW_RUN(convert(u, SMX_F32, y_fwd, y_dt, rows * D, st));
+      ws.release(m0);
+      return SMX_OK;
+    }
+  }
   BW_BUF(gy, rows * D);  // gradient with respect to the pre-norm sum x + 0.5 u
   BW_LAUNCH("scale_kernel", scale_kernel<<<ew_grid(rows * D), 256, 0, st>>>(dy, dy_dt, 1.0f, rows * D, gy));
-  if (oln_w) {
+  if (oln_w && ypre_d) {
+    SMX_TRY(ln_bwd(ypre_d, rows, D, oln_w, gy, g->out_ln_dw, g->out_ln_db, ws, st, oln_eps));
+  } else if (oln_w) {
     BW_BUF(ypre, rows * D);
     if (!ws.dry) {  // ypre = x + 0.5 * (h W2^T + b2)
       GemmP p = bw_gemm();
@@ -831,10 +1010,12 @@ int ffn_bwd_generic(const smx_ffn_weights* w, int act, int64_t rows, const void*
   }
   BW_BUF(du, rows * D);
   BW_LAUNCH("scale_kernel", scale_kernel<<<ew_grid(rows * D), 256, 0, st>>>(gy, SMX_F32, 0.5f, rows * D, du));
+  BW_RUN(dropout_inplace(du, rows * D, dr, 1, st));
   if (g->w2.dw) SMX_TRY(lin_wgrad(w->w2, du, D, h, F, rows, g->w2.dw, 0, 0, ws, st));
   if (g->w2.db) SMX_TRY(colsum_all(du, D, rows, D, g->w2.db, ws, st));
   BW_BUF(dh, rows * F);
   BW_RUN(lin_dgrad(w->w2, du, D, rows, dh, SMX_F32, F, 0, 0, nullptr, st));
+  BW_RUN(dropout_inplace(dh, rows * F, dr, 0, st));
   BW_RUN(act_bwd(z1, dh, SMX_F32, rows, F, act, nullptr, dh, st));
   if (g->w1.dw) SMX_TRY(lin_wgrad(w->w1, dh, F, xn, D, rows, g->w1.dw, 0, 0, ws, st));
   if (g->w1.db) SMX_TRY(colsum_all(dh, F, rows, F, g->w1.db, ws, st));
@@ -848,7 +1029,11 @@ int ffn_bwd_generic(const smx_ffn_weights* w, int act, int64_t rows, const void*
 
 // y = (Linear(act(LN_after(dwconv(GLU(pointwise(LN(x))))))) ) * mask                        Conformer.py:322-338
 int convmod_bwd_generic(const smx_convmod_weights* w, int act, int B, int T, const void* x, int x_dt, const uint8_t* mask, const void* dy,
-                        int dy_dt, void* dx, int dx_dt, const smx_convmod_grads* g, Arena& ws, cudaStream_t st) {
+                        int dy_dt, void* dx, int dx_dt, const smx_convmod_grads* g, Arena& ws, cudaStream_t st, const smx_dropout* drop,
+                        void* y_fwd, int y_dt) {
+  // drop (p > 0): site 0 = the nn.Dropout that ends after_conv, before the padding mask (Conformer.py:163, :334-337).
+  // y_fwd: training-mode FORWARD only.
+  const Drop dr = make_drop(drop);
   const int64_t rows = (int64_t)B * T;
   const int D = w->bottleneck.in_dim, k = w->kernel_size;
   if (w->bottleneck.out_dim != 2 * D || w->out.in_dim != D || w->out.out_dim != D || k < 1)
@@ -876,9 +1061,18 @@ int convmod_bwd_generic(const smx_convmod_weights* w, int act, int B, int T, con
   BW_RUN(layernorm(c, SMX_F32, D, w->after_ln_w, w->after_ln_b, 1e-5f, SMX_ACT_IDENTITY, cn, SMX_F32, D, rows, D, st));
   BW_BUF(a, rows * D);
   BW_RUN(act_fwd(cn, rows, D, act, nullptr, a, st));
-  // backward
   BW_BUF(dout, rows * D);
+  if (y_fwd) {
+    BW_RUN(lin_fwd(w->out, a, D, rows, dout, D, true, 0, 0, nullptr, 1, st));
+    BW_RUN(dropout_inplace(dout, rows * D, dr, 0, st));
+    BW_LAUNCH("mask_rows_kernel", mask_rows_kernel<<<ew_grid(rows * D), 256, 0, st>>>(dout, SMX_F32, mask, D, rows * D, dout));
+    BW_RUN(convert(dout, SMX_F32, y_fwd, y_dt, rows * D, st));
+    ws.release(m0);
+    return SMX_OK;
+  }
+  // backward
   BW_LAUNCH("mask_rows_kernel", mask_rows_kernel<<<ew_grid(rows * D), 256, 0, st>>>(dy, dy_dt, mask, D, rows * D, dout));
+  BW_RUN(dropout_inplace(dout, rows * D, dr, 0, st));
   if (g->out.dw) SMX_TRY(lin_wgrad(w->out, dout, D, a, D, rows, g->out.dw, 0, 0, ws, st));
   if (g->out.db) SMX_TRY(colsum_all(dout, D, rows, D, g->out.db, ws, st));
   float* da = a;  // a is dead
@@ -911,5 +1105,14 @@ int convmod_bwd_generic(const smx_convmod_weights* w, int act, int B, int T, con
 #undef BW_RUN
 #undef BW_BUF
 #undef BW_LAUNCH
+
+int dropout_keep_mask(const smx_dropout* drop, int site, int64_t n, uint8_t* keep, cudaStream_t st) {
+  const Drop dr = make_drop(drop);
+  if (n <= 0) return SMX_OK;
+  const int64_t quads = (n + 3) / 4;
+  dropout_mask_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(keep, n, dr.seed, (uint32_t)site, dr.on ? dr.thresh : 0u);
+  count_launch();
+  return check_launch("dropout_mask_kernel");
+}
 
 }  // namespace smx

@@ -105,7 +105,6 @@ class ConvolutionModule(nn.Module):
         H.require_cuda(x, "ConvolutionModule")
         grad = A.wants_grad(self, x)
         if grad:
-            A.refuse_dropout(self, self.after_conv[3].p)
             if _chunk_size(dynchunktrain_config) > 0:
                 raise NotImplementedError("summarymixing_b200: backward of the Dynamic Chunk Convolution is not implemented")
         else:
@@ -123,7 +122,8 @@ class ConvolutionModule(nn.Module):
             self.fill(cw, self._wv, dev)
             self._wv.struct = cw
         if grad:
-            return A.ConvModuleFunction.apply(self._wv.struct, self._act_code, xc, m8, *self.grad_params())
+            return A.ConvModuleFunction.apply(self._wv.struct, self._act_code, A.new_dropout(self, self.after_conv[3].p), xc, m8,
+                                              *self.grad_params())
         y = torch.empty_like(xc)
         lib = L.lib()
         dt = H.dtype_code(xc)
@@ -268,16 +268,19 @@ def _ffn_params(seq: nn.Sequential):
 
 
 def _layer_forward_autograd(self, x, mask):
-    """The layer as a chain of autograd nodes, one per libsmx module call (Conformer.py:518-547, dropout off):
-    FFN half-step -> norm1 -> cell + skip -> conv module + skip -> FFN half-step + norm2."""
-    A.refuse_dropout(self, self.drop.p)
+    """The layer as a chain of autograd nodes, one per libsmx module call (Conformer.py:518-547):
+    FFN half-step -> norm1 -> cell + skip -> conv module + skip -> FFN half-step + norm2.  In training mode every node
+    applies its dropout sites (FFN: inside PositionalwiseFeedForward and after it; cell: on the concatenation; conv module: its
+    last stage); ``self.drop`` is not on the SummaryMixing path of the reference's forward."""
     lw = self._wv.struct
-    x1 = A.FFNFunction.apply(lw.ffn1, self._act_code, None, x, *_ffn_params(self.ffn_module1))
+    d1 = A.new_dropout(self, A.same_p(self.ffn_module1[1].ffn[2].p, self.ffn_module1[2].p))
+    d2 = A.new_dropout(self, A.same_p(self.ffn_module2[1].ffn[2].p, self.ffn_module2[2].p))
+    x1 = A.FFNFunction.apply(lw.ffn1, self._act_code, None, d1, x, *_ffn_params(self.ffn_module1))
     n1 = A.LayerNormFunction.apply(x1, self.norm1.norm.weight, self.norm1.norm.bias, self.norm1.eps)
     x2 = self.mha_layer(n1, src_padding_mask=mask) + x1
     x3 = x2 + self.convolution_module(x2, mask)
     out_norm = (lw.norm2_w, lw.norm2_b, float(self.norm2.eps))
-    return A.FFNFunction.apply(lw.ffn2, self._act_code, out_norm, x3, *_ffn_params(self.ffn_module2),
+    return A.FFNFunction.apply(lw.ffn2, self._act_code, out_norm, d2, x3, *_ffn_params(self.ffn_module2),
                                self.norm2.norm.weight, self.norm2.norm.bias)
 
 

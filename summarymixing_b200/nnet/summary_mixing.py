@@ -3,7 +3,8 @@
 Constructor signature, mode validation, sub-module names and state_dict keys follow summary_mixing.py:78-167;
 ``forward(x, sum_mask=None, src_padding_mask=None)`` follows :169-196.  The arithmetic runs in libsmx
 (smx_summary_mixing_fwd).  Differences, deliberate: the default mask is built on x's device (the reference
-allocates it on the CPU, :186, which breaks on GPU), and dropout is identity (inference path).
+allocates it on the CPU, :186, which breaks on GPU); dropout is the identity on the inference path and applied by the
+training path (smx_summary_mixing_train_fwd / _bwd).
 """
 from __future__ import annotations
 
@@ -140,10 +141,10 @@ class SummaryMixing(nn.Module):
                 raise NotImplementedError(
                     "summarymixing_b200: backward is implemented for modes 'SummaryMixing', 'SummaryMixing-fast' (both without "
                     "sum_mask) and 'SummaryMixing-lite' only; wrap other configurations in torch.no_grad()")
-            if self.training and self.dropout.p > 0:
-                raise NotImplementedError(
-                    "summarymixing_b200: training-mode dropout is not implemented (set global_dropout=0 or call .eval())")
-            y = _CellFunction.apply(self, x, mask, *self.grad_params())
+            from .. import _autograd as A
+
+            drop = None if lite else A.new_dropout(self, self.dropout.p)  # (lite has no dropout, summary_mixing.py:300-324)
+            y = _CellFunction.apply(self, x, mask, drop, *self.grad_params())
             return y.unsqueeze(1).expand(-1, T, -1) if lite else y
         H.check_grad_mode(self)
         return self._forward_impl(x, mask, smask)
@@ -185,7 +186,22 @@ class SummaryMixing(nn.Module):
             return y.unsqueeze(1).expand(-1, T, -1)
         return y
 
-    def _backward_impl(self, x, mask, dy, want_dx, cw=None):
+    def _train_forward_impl(self, x, mask, drop):
+        """Training-mode forward with dropout on the concatenation: smx_summary_mixing_train_fwd."""
+        B, T, _ = x.shape
+        dev = x.device
+        xc = x.contiguous()
+        cw = self._weights(dev)
+        y = torch.empty((B, T, self.summary_out_dim), dtype=x.dtype, device=dev)
+        lib = L.lib()
+        dt = H.dtype_code(xc)
+        with torch.cuda.device(dev):
+            ws = H.workspace(dev, lib.smx_summary_mixing_train_workspace_bytes(cw, dt, B, T))
+            L.check(lib.smx_summary_mixing_train_fwd(cw, dt, B, T, xc.data_ptr(), H.p_or_none(mask), C.byref(drop), y.data_ptr(),
+                                                     ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+        return y
+
+    def _backward_impl(self, x, mask, dy, want_dx, cw=None, drop=None):
         """(dx or None, [fp32 gradient per grad_params() entry]) through smx_summary_mixing_bwd."""
         B, T, _ = x.shape
         dev = x.device
@@ -219,10 +235,15 @@ class SummaryMixing(nn.Module):
         lib = L.lib()
         dt = H.dtype_code(xc)
         with torch.cuda.device(dev):
-            nbytes = lib.smx_summary_mixing_bwd_workspace_bytes(cw, dt, B, T)
-            ws = H.workspace(dev, nbytes)
-            L.check(lib.smx_summary_mixing_bwd(cw, dt, B, T, xc.data_ptr(), H.p_or_none(mask), dyc.data_ptr(),
-                                               H.p_or_none(dx), C.byref(cg), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+            if drop is None:
+                nbytes = lib.smx_summary_mixing_bwd_workspace_bytes(cw, dt, B, T)
+                ws = H.workspace(dev, nbytes)
+                L.check(lib.smx_summary_mixing_bwd(cw, dt, B, T, xc.data_ptr(), H.p_or_none(mask), dyc.data_ptr(),
+                                                   H.p_or_none(dx), C.byref(cg), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+            else:
+                ws = H.workspace(dev, lib.smx_summary_mixing_train_workspace_bytes(cw, dt, B, T))
+                L.check(lib.smx_summary_mixing_train_bwd(cw, dt, B, T, xc.data_ptr(), H.p_or_none(mask), C.byref(drop), dyc.data_ptr(),
+                                                         H.p_or_none(dx), C.byref(cg), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
         return dx, grads
 
 
@@ -231,12 +252,13 @@ class _CellFunction(torch.autograd.Function):
     the intermediates from x, so only x and the mask are kept)."""
 
     @staticmethod
-    def forward(ctx, module, x, mask, *params):
+    def forward(ctx, module, x, mask, drop, *params):
         from .. import _autograd as A
 
         ctx.module = module
+        ctx.drop = drop
         ctx.save_for_backward(x, mask)
-        y = module._forward_impl(x, mask, None, expand_lite=False)
+        y = module._forward_impl(x, mask, None, expand_lite=False) if drop is None else module._train_forward_impl(x, mask, drop)
         ctx.cw = module._wv.struct  # the weight struct of THIS forward (with the tensors it points into)
         A.pin_params(ctx, module.params())
         return y
@@ -248,7 +270,7 @@ class _CellFunction(torch.autograd.Function):
         x, mask = ctx.saved_tensors
         A.check_params(ctx)
         module = ctx.module
-        dx, grads = module._backward_impl(x, mask, dy, ctx.needs_input_grad[1], cw=ctx.cw)
+        dx, grads = module._backward_impl(x, mask, dy, ctx.needs_input_grad[1], cw=ctx.cw, drop=ctx.drop)
         plist = module.grad_params()
-        out = [g.to(p.dtype) if ctx.needs_input_grad[3 + i] else None for i, (g, p) in enumerate(zip(grads, plist))]
-        return (None, dx, None, *out)
+        out = [g.to(p.dtype) if ctx.needs_input_grad[4 + i] else None for i, (g, p) in enumerate(zip(grads, plist))]
+        return (None, dx, None, None, *out)

@@ -129,11 +129,7 @@ def test_backward_unsupported_configurations_fail_loudly():
         S.SummaryMixing(64, 4, [64], 64, [64], 64, mode="SummaryMixing-expdecay").to(DEV).eval()(x)
     with pytest.raises(NotImplementedError, match="backward"):
         S.SummaryMixing(64, 4, [64], 64, [64], 64).to(DEV).eval()(x, sum_mask=torch.ones(16, 16, device=DEV))
-    with pytest.raises(NotImplementedError, match="dropout"):
-        S.SummaryMixing(64, 4, [64], 64, [64], 64).to(DEV).train()(x)
-    with pytest.raises(NotImplementedError, match="dropout"):
-        S.ConformerEncoderLayer(64, 128, 4, attention_type="SummaryMixing", local_proj_hid_dim=[64], local_proj_out_dim=64,
-                                summary_hid_dim=[64], dropout=0.1).to(DEV).train()(x)
+    # (training-mode dropout is implemented: tests/test_dropout_gpu.py)
 
 
 def test_backward_properties_at_baseline_shape():
