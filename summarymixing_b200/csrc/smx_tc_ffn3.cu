@@ -7,7 +7,7 @@
 // One CTA per SM walks 128-row tiles; the hidden dimension is processed in 128-wide chunks.  Differences from v2
 // (smx_tc_ffn2.cu), each aimed at what the v2 timelines and ncu captures showed (profiles/r01_notes.md):
 //   * GEMM1 (K = D, N = 128) fills one of two fp32 TMEM accumulators; the epilogue warps add b1, activate and write the
-//     chunk back as packed bf16 INTO THE SAME TMEM COLUMNS (the first 64 of the 128): GEMM2 takes it from there as its
+//     chunk back as packed bf16 INTO THE SAME TMEM COLUMNS (each warp over the first half of its own 32): GEMM2 takes it from there as its
 //     A operand (tcgen05.mma with A in tensor memory).  The hidden activation costs no shared-memory write, no
 //     shared-memory operand read and no shared-memory space -- v2 was bound by shared-memory bandwidth plus the L2
 //     latency its 64 KB weight ring could not cover.
@@ -171,7 +171,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
   tc::tc_fence_after();
   tc::pdl_wait();  // the producer of x has completed (everything above touched only parameters)
   const uint32_t tmem = __shfl_sync(0xffffffffu, tmem_base_s, 0);
-  const uint32_t t_acc2 = tmem, t_acc1 = tmem + 256;  // acc1 buffers at +256 and +384; the bf16 chunk H[b] overlays acc1[b][0:64]
+  const uint32_t t_acc2 = tmem, t_acc1 = tmem + 256;  // acc1 buffers at +256 and +384; the bf16 chunk H[b] overlays acc1[b] (16 of every 32 columns)
   // tile walk: CTA (or pair) g takes tile groups g, g + n_groups, ...; in a pair, rank r takes the r-th tile of the group
   // (both CTAs run the same number of iterations: the protocol is collective; a tile past the end has nrows <= 0)
   const int first_base = CL2 ? (int)tc::cluster_id_x() * 2 : (int)blockIdx.x;
@@ -331,15 +331,15 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
           ph_hf ^= 1u << bsel;
         }
         tc::tc_fence_after();
-        const uint32_t a_tmem = t_acc1 + bsel * F3_HC;  // H[bsel]: K = 128 bf16 in 64 columns
+        const uint32_t a_tmem = t_acc1 + bsel * F3_HC;  // H[bsel]: K = 128 bf16 in 4 x 16 columns (the first half of every epilogue warp's 32)
         for (int u = 0; u < 2; ++u) {  // acc2 += H[j][:, K-block u] @ W2[:, K-block 2j+u]^T
           const uint32_t b_addr = ring_next();
           if (leader && tc::elect_one()) {
 #pragma unroll
             for (int ks = 0; ks < 4; ++ks) {
               const uint32_t acc = (j == 0 && u == 0 && ks == 0) ? 0u : 1u;
-              if (CL2) tc::umma2_bf16_ts(t_acc2, a_tmem + (u * 4 + ks) * 8, tc::make_desc_sw128(b_addr + ks * 32), idesc2, acc);
-              else f3_umma_ts(t_acc2, a_tmem + (u * 4 + ks) * 8, tc::make_desc_sw128(b_addr + ks * 32), idesc2, acc);
+              if (CL2) tc::umma2_bf16_ts(t_acc2, a_tmem + (u * 2 + (ks >> 1)) * 32 + (ks & 1) * 8, tc::make_desc_sw128(b_addr + ks * 32), idesc2, acc);
+              else f3_umma_ts(t_acc2, a_tmem + (u * 2 + (ks >> 1)) * 32 + (ks & 1) * 8, tc::make_desc_sw128(b_addr + ks * 32), idesc2, acc);
             }
           }
           __syncwarp();
@@ -451,9 +451,9 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
         float v[32];
         tc::tmem_ld32(t_acc1 + lane_sel + bsel * F3_HC + k * 32, v);
         tc::tmem_ld_wait();
-        // H[bsel] overlays the first 64 columns of acc1[bsel]: every warp of this lane quadrant must hold its columns
-        // before any of them writes
-        tc::named_bar_sync(1 + q, 128);
+        // H[bsel] overlays acc1[bsel]: this warp writes its 32 activations (16 packed columns) over the FIRST HALF OF ITS OWN 32
+        // accumulator columns, which it has just loaded -- no other warp reads or writes them, so no barrier between the warps of
+        // a lane quadrant is needed.  GEMM 2 takes K-slice s (16 hidden units, 8 columns) from columns 32 (s / 2) + 8 (s % 2).
         const float4* bp = reinterpret_cast<const float4*>(sPar + chunk_of(j) * F3_HC + k * 32);
         const float4* gp = reinterpret_cast<const float4*>(sGw + chunk_of(j) * F3_HC + k * 32);
 #pragma unroll
@@ -466,7 +466,7 @@ __global__ void __launch_bounds__(F3_THREADS, 1) ffn3_kernel(const __grid_consta
         uint32_t hp[16];
 #pragma unroll
         for (int i = 0; i < 16; ++i) hp[i] = tc::pack_bf16x2(v[2 * i], v[2 * i + 1]);
-        f3_tmem_st16(t_acc1 + lane_sel + bsel * F3_HC + k * 16, hp);
+        f3_tmem_st16(t_acc1 + lane_sel + bsel * F3_HC + k * 32, hp);
         tc::tmem_st_wait();
         tc::tc_fence_before();
         __syncwarp();
