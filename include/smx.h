@@ -186,7 +186,8 @@ SMX_API int smx_version(void);
 SMX_API const char* smx_last_error(void);
 /* sizeof() of the ABI structs as compiled (0 smx_linear, 1 smx_cell_weights, 2 smx_ffn_weights,
  * 3 smx_convmod_weights, 4 smx_conformer_layer_weights, 5 smx_convbranch_weights,
- * 6 smx_branchformer_layer_weights) so a binding can verify its mirror of this header. */
+ * 6 smx_branchformer_layer_weights, 7 smx_cell_grads, 8 smx_ffn_grads, 9 smx_convmod_grads, 10 smx_convbranch_grads) so a
+ * binding can verify its mirror of this header. */
 SMX_API size_t smx_struct_size(int which);
 /* number of kernels this library has launched in the calling process (bench.py's gpu_launches) */
 SMX_API uint64_t smx_launch_count(void);
@@ -339,6 +340,30 @@ SMX_API int smx_summary_mixing_train_fwd(const smx_cell_weights* w, int dtype, i
 SMX_API int smx_summary_mixing_train_bwd(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x,
                 const uint8_t* padding_mask, const smx_dropout* drop, const void* dy, void* dx, const smx_cell_grads* grads,
                 void* workspace, size_t workspace_bytes, void* stream);
+/* ConvolutionBranch (Branchformer.py:86-97: pre_channel_proj -> activation -> CSGU -> post_channel_proj; the CSGU is SpeechBrain's
+ * ConvolutionalSpatialGatingUnit: split halves, LayerNorm + reflect-padded depthwise conv [+ linear] + gate activation on the second
+ * half, product with the first, dropout).  x is the branch's input (the layer applies norm_conv before, Branchformer.py:292-293; no
+ * padding mask, :276).  smx_conv_branch_train_fwd is the module's forward on the fp32-math arm (drop == NULL or p == 0: the
+ * inference function; site 0 = the CSGU's dropout on the product); smx_conv_branch_train_bwd is self-contained like the other
+ * smx_*_bwd calls (recomputes the forward from x, regenerates the mask).  workspace: smx_conv_branch_train_workspace_bytes(). */
+typedef struct {
+  smx_linear_grad pre;
+  smx_linear_grad post;
+  float* csgu_ln_dw;
+  float* csgu_ln_db;
+  float* csgu_dw_dw;   /* depthwise weight gradient (U/2,1,k) */
+  float* csgu_dw_db;
+  smx_linear_grad csgu_linear; /* used when the branch has use_linear_after_conv */
+} smx_convbranch_grads;
+SMX_API size_t smx_conv_branch_train_workspace_bytes(const smx_convbranch_weights* w, int dtype, int32_t B, int32_t T);
+SMX_API int smx_conv_branch_train_fwd(const smx_convbranch_weights* w, int dtype, int32_t B, int32_t T, const void* x,
+                const smx_dropout* drop, void* y, void* workspace, size_t workspace_bytes, void* stream);
+SMX_API int smx_conv_branch_train_bwd(const smx_convbranch_weights* w, int dtype, int32_t B, int32_t T, const void* x,
+                const smx_dropout* drop, const void* dy, void* dx, const smx_convbranch_grads* grads, void* workspace,
+                size_t workspace_bytes, void* stream);
+/* y = x * keep(site) / (1 - p): one nn.Dropout call of the layer surface (Branchformer.py:279, :294, :334) with the counter-based
+ * mask; its own backward (dx = the same function of dy).  n elements; x and y may alias. */
+SMX_API int smx_dropout_apply(const smx_dropout* drop, int32_t site, int dtype, int64_t n, const void* x, void* y, void* stream);
 /* keep[e] = 1 when element e of `site` survives under `drop` (the mask the calls above apply); n elements, device pointer. */
 SMX_API int smx_dropout_keep_mask(const smx_dropout* drop, int32_t site, int64_t n, uint8_t* keep, void* stream);
 

@@ -1,4 +1,4 @@
-"""Golden GRADIENTS of the SummaryMixing cell, the convolution module and the Conformer layer / encoder from the UNMODIFIED reference (run in the build container).
+"""Golden GRADIENTS of the SummaryMixing cell, the convolution module, the Conformer layer / encoder and the Branchformer encoder from the UNMODIFIED reference (run in the build container).
 
     python oracle/gen_golden_bwd.py        # writes tests/golden/bwd/*.npz
 
@@ -26,6 +26,7 @@ sys.path.insert(0, ROOT)
 from speechbrain.nnet.activations import Swish  # noqa: E402
 from speechbrain.nnet.summary_mixing import SummaryMixing  # noqa: E402
 from speechbrain.lobes.models.VanillaNN import VanillaNN  # noqa: E402
+from speechbrain.lobes.models.transformer.Branchformer import BranchformerEncoder  # noqa: E402
 from speechbrain.lobes.models.transformer.Conformer import (  # noqa: E402
     ConformerEncoder,
     ConformerEncoderLayer,
@@ -36,13 +37,16 @@ from tests import _golden as G  # noqa: E402
 ACTS = {"swish": Swish, "gelu": nn.GELU, "relu": nn.ReLU, "leaky_relu": nn.LeakyReLU}
 CASES = ["cell_sm_h4_swish", "cell_sm_h1_gelu", "cell_sm_h4_relu_noln_deep_nomask", "cell_reftest_sm_h4", "cell_sm_h4_gelu", "cell_sm_lite_h4_gelu", "cell_sm_lite_h1_gelu",
          "convmod_plain", "convmod_causal", "conformer_layer", "conformer_enc_sm_h4", "conformer_enc_sm_h1_gelu",
-         "cell_sm_fast_h4_swish", "cell_sm_fast_h1_gelu", "conformer_enc_lite_h4", "vanilla_split1", "vanilla_split3"]
+         "cell_sm_fast_h4_swish", "cell_sm_fast_h1_gelu", "conformer_enc_lite_h4", "vanilla_split1", "vanilla_split3",
+         "branchformer_enc_lite", "branchformer_enc_full"]
 OUT = os.path.join(ROOT, "tests", "golden", "bwd")
 
 
 def main():
     os.makedirs(OUT, exist_ok=True)
     for i, name in enumerate(CASES):
+        if "--all" not in sys.argv and os.path.exists(os.path.join(OUT, name + ".npz")):
+            continue
         fx = G.Fixture(name)
         c = fx.cfg
         k = c["kind"]
@@ -63,6 +67,11 @@ def main():
                                        attention_type="SummaryMixing", local_proj_hid_dim=c["local_proj_hid_dim"],
                                        local_proj_out_dim=c["local_proj_out_dim"], summary_hid_dim=c["summary_hid_dim"],
                                        mode=c["mode"], use_layernorm=c["use_layernorm"])
+            run = lambda m, x: m(x, src_key_padding_mask=fx.mask)[0]  # noqa: E731
+        elif k == "branchformer_encoder":
+            sm = BranchformerEncoder(c["num_layers"], c["d_model"], c["nhead"], c["kernel_size"], csgu_linear_units=c["csgu_linear_units"],
+                                     local_proj_hid_dim=c["local_proj_hid_dim"], local_proj_out_dim=c["local_proj_out_dim"],
+                                     summary_hid_dim=c["summary_hid_dim"], summary_out_dim=c["summary_out_dim"], mode=c["mode"])
             run = lambda m, x: m(x, src_key_padding_mask=fx.mask)[0]  # noqa: E731
         else:
             sm = ConformerEncoder(c["num_layers"], c["d_model"], c["d_ffn"], c["nhead"], c["kernel_size"],

@@ -340,9 +340,10 @@ def conformer_encoder_mhsa(x: Tensor, sd: SD, num_layers: int, nhead: int, prefi
 # --------------------------------------------------------------------------------------
 # Branchformer                                                            (Branchformer.py)
 # --------------------------------------------------------------------------------------
-def csgu(x: Tensor, sd: SD, prefix: str, gate_act: str = "identity") -> Tensor:
+def csgu(x: Tensor, sd: SD, prefix: str, gate_act: str = "identity", drop=None) -> Tensor:
     """SpeechBrain ConvolutionalSpatialGatingUnit (UNPINNED, see module docstring): split halves,
-    LN the gate half, depthwise conv 'same' with reflect padding, optional linear, gate act, multiply."""
+    LN the gate half, depthwise conv 'same' with reflect padding, optional linear, gate act, multiply, dropout
+    (``drop``: training mode, key prefix + "out")."""
     x1, x2 = x.chunk(2, dim=-1)
     x2 = layer_norm(x2, _p(sd, prefix + "norm.norm.weight", x), _p(sd, prefix + "norm.norm.bias", x))
     cw = _p(sd, prefix + "conv.conv.weight", x)
@@ -353,13 +354,14 @@ def csgu(x: Tensor, sd: SD, prefix: str, gate_act: str = "identity") -> Tensor:
     if prefix + "linear.weight" in sd:
         x2 = x2 @ _p(sd, prefix + "linear.weight", x).T + _p(sd, prefix + "linear.bias", x)
     x2 = activation(gate_act, x2)
-    return x2 * x1
+    out = x2 * x1
+    return drop(prefix + "out", out) if drop is not None else out
 
 
-def convolution_branch(x: Tensor, sd: SD, prefix: str, act: str = "gelu", gate_act: str = "identity") -> Tensor:
-    """ConvolutionBranch.forward, Branchformer.py:86-97."""
+def convolution_branch(x: Tensor, sd: SD, prefix: str, act: str = "gelu", gate_act: str = "identity", drop=None) -> Tensor:
+    """ConvolutionBranch.forward, Branchformer.py:86-97 (``drop``: the CSGU's dropout in training mode)."""
     x = activation(act, x @ _p(sd, prefix + "pre_channel_proj.weight", x).T + _p(sd, prefix + "pre_channel_proj.bias", x))
-    x = csgu(x, sd, prefix + "csgu.", gate_act)
+    x = csgu(x, sd, prefix + "csgu.", gate_act, drop)
     return x @ _p(sd, prefix + "post_channel_proj.weight", x).T + _p(sd, prefix + "post_channel_proj.bias", x)
 
 
@@ -372,17 +374,24 @@ def branchformer_layer(
     mode: str = "SummaryMixing",
     src_mask: Optional[Tensor] = None,
     src_key_padding_mask: Optional[Tensor] = None,
+    drop=None,
 ) -> Tensor:
-    """BranchformerEncoderLayer.forward with attention_type == 'SummaryMixing', Branchformer.py:243-334."""
+    """BranchformerEncoderLayer.forward with attention_type == 'SummaryMixing', Branchformer.py:243-334.  ``drop`` (training mode):
+    drop(key, tensor) stands in for self.dropout after each branch (keys prefix + "x1", prefix + "x2": :334, :294), after merge_proj
+    (prefix + "merge": :279) and for the CSGU's own dropout (prefix + "convolution_branch.csgu.out"); the cell's dropout
+    (prefix + "mha_layer.cat") as in summary_mixing()."""
     x1 = layer_norm(x, _p(sd, prefix + "norm_mhsa.norm.weight", x), _p(sd, prefix + "norm_mhsa.norm.bias", x))  # :317
     x1 = summary_mixing(
         x1, sd, prefix + "mha_layer.", mode=mode, act=act, use_layernorm=True,
-        src_padding_mask=src_key_padding_mask, sum_mask=src_mask,
+        src_padding_mask=src_key_padding_mask, sum_mask=src_mask, drop=drop if mode != "SummaryMixing-lite" else None,
     )  # :320-322
     x2 = layer_norm(x, _p(sd, prefix + "norm_conv.norm.weight", x), _p(sd, prefix + "norm_conv.norm.bias", x))  # :292
-    x2 = convolution_branch(x2, sd, prefix + "convolution_branch.", act=act, gate_act=gate_act)  # :293 (no mask, :276)
+    x2 = convolution_branch(x2, sd, prefix + "convolution_branch.", act=act, gate_act=gate_act, drop=drop)  # :293 (no mask, :276)
+    if drop is not None:
+        x1 = drop(prefix + "x1", x1.contiguous())  # :334
+        x2 = drop(prefix + "x2", x2)  # :294
     merged = vanilla_nn(torch.cat([x1, x2], dim=-1), sd, prefix + "merge_proj.", act)  # :279, :220-226
-    return x + merged
+    return x + (drop(prefix + "merge", merged) if drop is not None else merged)
 
 
 def branchformer_encoder(
@@ -395,12 +404,13 @@ def branchformer_encoder(
     mode: str = "SummaryMixing",
     src_mask: Optional[Tensor] = None,
     src_key_padding_mask: Optional[Tensor] = None,
+    drop=None,
 ) -> Tensor:
-    """BranchformerEncoder.forward, Branchformer.py:479-491; final LN eps=1e-6 (:444)."""
+    """BranchformerEncoder.forward, Branchformer.py:479-491; final LN eps=1e-6 (:444); ``drop``: training-mode dropout hook."""
     for i in range(num_layers):
         x = branchformer_layer(
             x, sd, f"{prefix}layers.{i}.", act=act, gate_act=gate_act, mode=mode,
-            src_mask=src_mask, src_key_padding_mask=src_key_padding_mask,
+            src_mask=src_mask, src_key_padding_mask=src_key_padding_mask, drop=drop,
         )
     return layer_norm(x, _p(sd, prefix + "norm.norm.weight", x), _p(sd, prefix + "norm.norm.bias", x), eps=1e-6)
 

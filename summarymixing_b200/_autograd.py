@@ -252,3 +252,81 @@ class VanillaNNFunction(torch.autograd.Function):
         if dx is not None:
             dx = dx.reshape(ctx.x_shape)
         return (None, None, None, None, dx, *_cast_out(ctx, 5, grads, ctx.params))
+
+
+class ConvBranchFunction(torch.autograd.Function):
+    """ConvolutionBranch (Branchformer.py:86-97): smx_conv_branch_train_fwd / smx_conv_branch_train_bwd.
+    params = [pre.weight, pre.bias, post.weight, post.bias, csgu.norm.weight, csgu.norm.bias, csgu.conv.weight, csgu.conv.bias]
+    (+ [csgu.linear.weight, csgu.linear.bias])."""
+
+    @staticmethod
+    def forward(ctx, bw, drop, x, *params):
+        dev = x.device
+        xc = x.contiguous()
+        B, T, _ = xc.shape
+        y = torch.empty_like(xc)
+        lib = L.lib()
+        dt = H.dtype_code(xc)
+        with torch.cuda.device(dev):
+            ws = H.workspace(dev, lib.smx_conv_branch_train_workspace_bytes(C.byref(bw), dt, B, T))
+            L.check(lib.smx_conv_branch_train_fwd(C.byref(bw), dt, B, T, xc.data_ptr(), C.byref(drop) if drop is not None else None,
+                                                  y.data_ptr(), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+        ctx.bw, ctx.drop, ctx.params = bw, drop, params
+        pin_params(ctx, params)
+        ctx.save_for_backward(xc)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (xc,) = ctx.saved_tensors
+        check_params(ctx)
+        dev = xc.device
+        dyc = dy.contiguous()
+        B, T, _ = xc.shape
+        grads = _new_grads(ctx.params, dev)
+        bg = L.ConvBranchGrads()
+        bg.pre.dw, bg.pre.db = grads[0].data_ptr(), grads[1].data_ptr()
+        bg.post.dw, bg.post.db = grads[2].data_ptr(), grads[3].data_ptr()
+        bg.csgu_ln_dw, bg.csgu_ln_db = grads[4].data_ptr(), grads[5].data_ptr()
+        bg.csgu_dw_dw, bg.csgu_dw_db = grads[6].data_ptr(), grads[7].data_ptr()
+        if len(grads) > 8:
+            bg.csgu_linear.dw, bg.csgu_linear.db = grads[8].data_ptr(), grads[9].data_ptr()
+        dx = torch.empty_like(xc) if ctx.needs_input_grad[2] else None
+        lib = L.lib()
+        dt = H.dtype_code(xc)
+        with torch.cuda.device(dev):
+            ws = H.workspace(dev, lib.smx_conv_branch_train_workspace_bytes(C.byref(ctx.bw), dt, B, T))
+            L.check(lib.smx_conv_branch_train_bwd(C.byref(ctx.bw), dt, B, T, xc.data_ptr(),
+                                                  C.byref(ctx.drop) if ctx.drop is not None else None, dyc.data_ptr(), H.p_or_none(dx),
+                                                  C.byref(bg), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+        return (None, None, dx, *_cast_out(ctx, 3, grads, ctx.params))
+
+
+class DropoutFunction(torch.autograd.Function):
+    """One nn.Dropout call of a layer's forward with libsmx's counter-based mask (smx_dropout_apply): y = x * keep(site) / (1 - p);
+    the backward applies the same mask to dy."""
+
+    @staticmethod
+    def forward(ctx, drop, site, x):
+        xc = x.contiguous()
+        y = torch.empty_like(xc)
+        dev = xc.device
+        with torch.cuda.device(dev):
+            L.check(L.lib().smx_dropout_apply(C.byref(drop), site, H.dtype_code(xc), xc.numel(), xc.data_ptr(), y.data_ptr(), H.stream_ptr(dev)))
+        ctx.drop, ctx.site = drop, site
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        dyc = dy.contiguous()
+        dx = torch.empty_like(dyc)
+        dev = dyc.device
+        with torch.cuda.device(dev):
+            L.check(L.lib().smx_dropout_apply(C.byref(ctx.drop), ctx.site, H.dtype_code(dyc), dyc.numel(), dyc.data_ptr(), dx.data_ptr(),
+                                              H.stream_ptr(dev)))
+        return None, None, dx
+
+
+def dropout(drop, site: int, x):
+    """x when drop is None (eval mode or p == 0), else DropoutFunction."""
+    return x if drop is None else DropoutFunction.apply(drop, site, x)

@@ -66,6 +66,11 @@ class ConvModGrads(C.Structure):
                 ("after_ln_db", fp), ("out", LinearGrad)]
 
 
+class ConvBranchGrads(C.Structure):
+    _fields_ = [("pre", LinearGrad), ("post", LinearGrad), ("csgu_ln_dw", fp), ("csgu_ln_db", fp), ("csgu_dw_dw", fp),
+                ("csgu_dw_db", fp), ("csgu_linear", LinearGrad)]
+
+
 class FFNWeights(C.Structure):
     _fields_ = [("ln_w", fp), ("ln_b", fp), ("w1", Linear), ("w2", Linear), ("packed", fp)]
 
@@ -153,6 +158,11 @@ _PROTOS = {
     "smx_summary_mixing_train_bwd": (_i, [C.POINTER(CellWeights), _i, _i, _i, _vp, _vp, C.POINTER(Dropout), _vp, _vp,
                                           C.POINTER(CellGrads), _vp, _sz, _vp]),
     "smx_dropout_keep_mask": (_i, [C.POINTER(Dropout), _i, C.c_int64, _vp, _vp]),
+    "smx_dropout_apply": (_i, [C.POINTER(Dropout), _i, _i, C.c_int64, _vp, _vp, _vp]),
+    "smx_conv_branch_train_workspace_bytes": (_sz, [C.POINTER(ConvBranchWeights), _i, _i, _i]),
+    "smx_conv_branch_train_fwd": (_i, [C.POINTER(ConvBranchWeights), _i, _i, _i, _vp, C.POINTER(Dropout), _vp, _vp, _sz, _vp]),
+    "smx_conv_branch_train_bwd": (_i, [C.POINTER(ConvBranchWeights), _i, _i, _i, _vp, C.POINTER(Dropout), _vp, _vp,
+                                       C.POINTER(ConvBranchGrads), _vp, _sz, _vp]),
     "smx_conv_module_workspace_bytes": (_sz, [C.POINTER(ConvModWeights), _i, _i, _i]),
     "smx_conv_module_fwd": (_i, [C.POINTER(ConvModWeights), _i, _i, _i, _i, _i, _vp, _vp, _vp, _vp, _vp, _sz, _vp]),
     "smx_ffn_workspace_bytes": (_sz, [C.POINTER(FFNWeights), _i, _i64]),
@@ -194,7 +204,7 @@ _PROTOS = {
 
 
 ABI_STRUCTS = [Linear, CellWeights, FFNWeights, ConvModWeights, ConformerLayerWeights, ConvBranchWeights,
-               BranchformerLayerWeights, CellGrads, FFNGrads, ConvModGrads]
+               BranchformerLayerWeights, CellGrads, FFNGrads, ConvModGrads, ConvBranchGrads]
 
 
 def exported_symbols():

@@ -76,6 +76,7 @@ size_t smx_struct_size(int which) {
     case 7: return sizeof(smx_cell_grads);
     case 8: return sizeof(smx_ffn_grads);
     case 9: return sizeof(smx_convmod_grads);
+    case 10: return sizeof(smx_convbranch_grads);
     default: return 0;
   }
 }
@@ -389,6 +390,55 @@ int smx_conv_module_train_bwd(const smx_convmod_weights* w, int act, int dtype, 
                               const smx_dropout* drop, const void* dy, void* dx, const smx_convmod_grads* grads, void* workspace,
                               size_t workspace_bytes, void* stream) {
   return convmod_train(w, act, dtype, B, T, x, padding_mask, drop, dy, dx, grads, nullptr, workspace, workspace_bytes, stream);
+}
+size_t smx_conv_branch_train_workspace_bytes(const smx_convbranch_weights* w, int dtype, int32_t B, int32_t T) {
+  if (!w || B <= 0 || T <= 0) return 0;
+  smx_convbranch_grads g{{kDummy, kDummy}, {kDummy, kDummy}, kDummy, kDummy, kDummy, kDummy, {kDummy, kDummy}};
+  Arena a(nullptr, 0, true), b(nullptr, 0, true);
+  if (convbranch_bwd_generic(w, B, T, nullptr, dtype, nullptr, dtype, kDummy, dtype, &g, a, nullptr, &kSizingDrop) != SMX_OK) return 0;
+  if (convbranch_bwd_generic(w, B, T, nullptr, dtype, nullptr, dtype, nullptr, dtype, &g, b, nullptr, &kSizingDrop, kDummy, dtype) != SMX_OK) return 0;
+  return a.peak > b.peak ? a.peak : b.peak;
+}
+static int convbranch_train(const smx_convbranch_weights* w, int dtype, int32_t B, int32_t T, const void* x, const smx_dropout* drop,
+                            const void* dy, void* dx, const smx_convbranch_grads* grads, void* y, void* workspace, size_t workspace_bytes,
+                            void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");
+  SMX_TRY(check_bt(B, T));
+  SMX_TRY(check_drop(drop));
+  SMX_TRY(check_ptr(x, "x"));
+  if (y) SMX_TRY(check_ptr(y, "y")); else { if (!grads) return fail(SMX_ERR_BAD_ARG, "grads is NULL"); SMX_TRY(check_ptr(dy, "dy")); }
+  if (dx) SMX_TRY(check_ptr(dx, "dx"));
+  SMX_TRY(check_arch());
+  const size_t need = smx_conv_branch_train_workspace_bytes(w, dtype, B, T);
+  if (need == 0) {  // the sizing run failed: repeat it for its message (bad dims, T too short for the reflect padding)
+    Arena a(nullptr, 0, true);
+    smx_convbranch_grads none{};
+    const int rc = convbranch_bwd_generic(w, B, T, nullptr, dtype, nullptr, dtype, nullptr, dtype, &none, a, nullptr, nullptr, kDummy, dtype);
+    return rc != SMX_OK ? rc : SMX_ERR_BAD_ARG;
+  }
+  if (need > workspace_bytes || !workspace) return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  Arena a(workspace, workspace_bytes, false);
+  smx_convbranch_grads none{};
+  return convbranch_bwd_generic(w, B, T, x, dtype, dy, dtype, dx, dtype, grads ? grads : &none, a, (cudaStream_t)stream, drop, y, dtype);
+}
+int smx_conv_branch_train_fwd(const smx_convbranch_weights* w, int dtype, int32_t B, int32_t T, const void* x, const smx_dropout* drop, void* y,
+                              void* workspace, size_t workspace_bytes, void* stream) {
+  if (!y) return fail(SMX_ERR_BAD_ARG, "y is NULL");
+  return convbranch_train(w, dtype, B, T, x, drop, nullptr, nullptr, nullptr, y, workspace, workspace_bytes, stream);
+}
+int smx_conv_branch_train_bwd(const smx_convbranch_weights* w, int dtype, int32_t B, int32_t T, const void* x, const smx_dropout* drop,
+                              const void* dy, void* dx, const smx_convbranch_grads* grads, void* workspace, size_t workspace_bytes, void* stream) {
+  return convbranch_train(w, dtype, B, T, x, drop, dy, dx, grads, nullptr, workspace, workspace_bytes, stream);
+}
+int smx_dropout_apply(const smx_dropout* drop, int32_t site, int dtype, int64_t n, const void* x, void* y, void* stream) {
+  SMX_TRY(check_dtype(dtype));
+  SMX_TRY(check_drop(drop));
+  if (n < 0) return fail(SMX_ERR_BAD_ARG, "n must be non-negative");
+  if (n == 0) return SMX_OK;
+  SMX_TRY(check_ptr(x, "x")); SMX_TRY(check_ptr(y, "y"));
+  SMX_TRY(check_arch());
+  return dropout_apply(drop, site, dtype, n, x, y, (cudaStream_t)stream);
 }
 size_t smx_summary_mixing_train_workspace_bytes(const smx_cell_weights* w, int dtype, int32_t B, int32_t T) {
   if (!w || B <= 0 || T <= 0) return 0;

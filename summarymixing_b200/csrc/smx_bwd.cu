@@ -186,12 +186,12 @@ __global__ void __launch_bounds__(256) sum_slices_kernel(const float* P, int ns,
 // LayerNorm backward, one warp per row.  v: the LayerNorm input; g (in): dy, (out): dv;  t (out): dy * xhat (its column
 // sums are the weight gradient; the column sums of dy, taken BEFORE this kernel, are the bias gradient).
 __global__ void __launch_bounds__(256) ln_bwd_kernel(const float* v, int64_t rows, int D, const float* w, float eps, float* g,
-                                                     float* t) {
+                                                     float* t, int64_t ldv, int64_t ldg) {
   const int64_t row = (int64_t)blockIdx.x * 8 + threadIdx.x / 32;
   const int lane = threadIdx.x % 32;
   if (row >= rows) return;
-  const float* vr = v + row * D;
-  float* gr = g + row * D;
+  const float* vr = v + row * ldv;
+  float* gr = g + row * ldg;
   float* tr = t + row * D;
   float s = 0.0f;
   for (int c = lane; c < D; c += 32) s += vr[c];
@@ -476,13 +476,15 @@ int act_bwd(const float* z, const void* da, int da_dt, int64_t rows, int ncols, 
 
 // LayerNorm backward over `rows` rows: g (dy -> dv, in place), parameter gradients into dw / db (either may be NULL)
 int ln_bwd(const float* v, int64_t rows, int D, const float* w, float* g, float* dw, float* db, Arena& ws, cudaStream_t st,
-           float eps = 1e-5f) {
+           float eps = 1e-5f, int64_t ldv = 0, int64_t ldg = 0) {
+  if (ldv == 0) ldv = D;
+  if (ldg == 0) ldg = D;
   const size_t m0 = ws.mark();
   float* t = ws.f32((size_t)rows * D);
   if (!t) return fail(SMX_ERR_WORKSPACE, "workspace too small (LayerNorm backward)");
-  if (db) SMX_TRY(colsum_all(g, D, rows, D, db, ws, st));  // before g is overwritten
+  if (db) SMX_TRY(colsum_all(g, ldg, rows, D, db, ws, st));  // before g is overwritten
   if (!ws.dry) {
-    ln_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(v, rows, D, w, eps, g, t);
+    ln_bwd_kernel<<<(unsigned)((rows + 7) / 8), 256, 0, st>>>(v, rows, D, w, eps, g, t, ldv, ldg);
     count_launch();
     SMX_TRY(check_launch("ln_bwd_kernel"));
   }
@@ -852,9 +854,39 @@ __global__ void __launch_bounds__(256) glu_bwd_kernel(const float* p, const floa
     dp[r * 2 * D + D + c] = d * a * s * (1.0f - s);
   }
 }
-// depthwise conv, gradient with respect to the input: din[b,t,c] = sum_j w[c,j] * dout[b, t - j + pad, c]
+// CSGU gate backward (u = [value | gate-half input], gp = gate pre-activation, dprod = gradient of value * gate_act(gp)):
+// du[:, :H] = dprod * gate_act(gp);  dg = dprod * value * gate_act'(gp)
+__global__ void __launch_bounds__(256) csgu_gate_bwd_kernel(const float* dprod, const float* gp, const float* u, int U, int H, int gate_act,
+                                                            int64_t n, float* du, float* dg) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const int64_t row = i / H;
+    const int c = (int)(i - row * H);
+    const float d = dprod[i], z = gp[i];
+    du[row * U + c] = d * bw_act(gate_act, z);
+    dg[i] = d * u[row * U + c] * bw_dact(gate_act, z);
+  }
+}
+// y[e] = keep(e) ? x[e] * scale : 0 in the I/O dtype (x and y may alias)
+__global__ void __launch_bounds__(256) dropout_apply_kernel(const void* x, void* y, int dt, int64_t n, uint64_t seed, uint32_t site, uint32_t thresh,
+                                                            float scale) {
+  const int64_t quad = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t e0 = quad * 4;
+  if (e0 >= n) return;
+  const uint4 r = drop_words(seed, site, quad);
+  const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+    if (e0 + i < n) {
+      const float v = w[i] >= thresh ? bw_ld(x, dt, e0 + i) * scale : 0.0f;
+      if (dt == SMX_BF16) ((__nv_bfloat16*)y)[e0 + i] = __float2bfloat16_rn(v);
+      else ((float*)y)[e0 + i] = v;
+    }
+}
+// depthwise conv, gradient with respect to the input: din[b,t,c] = sum_j w[c,j] * dout[b, t - j + pad, c]; reflect != 0: the input
+// was reflect-padded (frame -s and frame T-1+s read frames s and T-1-s: those taps' gradients land there too; T > pad).
+// din has row stride ldo.
 __global__ void __launch_bounds__(256) dwconv_bwd_data_kernel(const float* dout, const float* w, int B, int T, int C, int k, int pad,
-                                                              float* din) {
+                                                              int reflect, float* din, int64_t ldo) {
   const int64_t n = (int64_t)B * T * C;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
     const int c = (int)(i % C);
@@ -863,17 +895,23 @@ __global__ void __launch_bounds__(256) dwconv_bwd_data_kernel(const float* dout,
     const float* base = dout + (int64_t)b * T * C + c;
     float acc = 0.0f;
     for (int j = 0; j < k; ++j) {
+      const float wj = w[(int64_t)c * k + j];
       const int u = t - j + pad;
-      if (u < 0 || u >= T) continue;
-      acc = fmaf(w[(int64_t)c * k + j], base[(int64_t)u * C], acc);
+      if (u >= 0 && u < T) acc = fmaf(wj, base[(int64_t)u * C], acc);
+      if (reflect) {
+        const int ul = pad - j - t;                   // output frame whose tap j read padded frame -t
+        if (t >= 1 && ul >= 0 && ul < T) acc = fmaf(wj, base[(int64_t)ul * C], acc);
+        const int ur = 2 * (T - 1) - t - j + pad;     // ... read padded frame 2(T-1) - t
+        if (t <= T - 2 && ur >= 0 && ur < T) acc = fmaf(wj, base[(int64_t)ur * C], acc);
+      }
     }
-    din[i] = acc;
+    din[((int64_t)b * T + t) * ldo + c] = acc;
   }
 }
 // depthwise conv, weight gradient partials: P[slice][c][j] = sum over the slice's utterances and all t of
 // dout[b,t,c] * in[b, t + j - pad, c].  grid (ceil(C/32), k, slices), block 32 x 8 (channels x frame lanes).
 __global__ void __launch_bounds__(256) dwconv_bwd_w_kernel(const float* dout, const float* in, int B, int T, int C, int k, int pad,
-                                                           int utt_per_slice, float* P) {
+                                                           int utt_per_slice, float* P, int reflect = 0) {
   __shared__ float red[8][33];
   const int cx = threadIdx.x % 32, ry = threadIdx.x / 32;
   const int c = blockIdx.x * 32 + cx, j = blockIdx.y;
@@ -885,7 +923,8 @@ __global__ void __launch_bounds__(256) dwconv_bwd_w_kernel(const float* dout, co
       const float* dob = dout + (int64_t)b * T * C + c;
       const float* inb = in + (int64_t)b * T * C + c;
       for (int t = ry; t < T; t += 8) {
-        const int u = t + j - pad;
+        int u = t + j - pad;
+        if (reflect) u = u < 0 ? -u : (u >= T ? 2 * (T - 1) - u : u);
         if (u >= 0 && u < T) acc = fmaf(dob[(int64_t)t * C], inb[(int64_t)u * C], acc);
       }
     }
@@ -1090,7 +1129,7 @@ int convmod_bwd_generic(const smx_convmod_weights* w, int act, int B, int T, con
     ws.release(m1);
   }
   float* dgl = dout;  // dout is dead
-  BW_LAUNCH("dwconv_bwd_data_kernel", dwconv_bwd_data_kernel<<<ew_grid(rows * D), 256, 0, st>>>(dc, w->dw_w, B, T, D, k, pad, dgl));
+  BW_LAUNCH("dwconv_bwd_data_kernel", dwconv_bwd_data_kernel<<<ew_grid(rows * D), 256, 0, st>>>(dc, w->dw_w, B, T, D, k, pad, 0, dgl, D));
   BW_BUF(dp, rows * 2 * D);
   BW_LAUNCH("glu_bwd_kernel", glu_bwd_kernel<<<ew_grid(rows * D), 256, 0, st>>>(p, dgl, rows, D, dp));
   if (g->bottleneck.dw) SMX_TRY(lin_wgrad(w->bottleneck, dp, 2 * D, xn, D, rows, g->bottleneck.dw, 0, 0, ws, st));
@@ -1099,6 +1138,95 @@ int convmod_bwd_generic(const smx_convmod_weights* w, int act, int B, int T, con
   BW_RUN(lin_dgrad(w->bottleneck, dp, 2 * D, rows, dxn, SMX_F32, D, 0, 0, nullptr, st));
   SMX_TRY(ln_bwd(x32, rows, D, w->ln_w, dxn, g->ln_dw, g->ln_db, ws, st));
   if (dx) BW_LAUNCH("add_kernel", add_kernel<<<ew_grid(rows * D), 256, 0, st>>>(dxn, nullptr, rows * D, dx, dx_dt));
+  ws.release(m0);
+  return SMX_OK;
+}
+
+// ConvolutionBranch: y = post( drop0( value * gate_act( [lin]( dwconv_reflect( LN(gate half) ) ) ) ) ),  [value | gate half] = act(pre(x))
+// (Branchformer.py:86-97 + SpeechBrain's ConvolutionalSpatialGatingUnit).  y_fwd: forward only; else the backward from dy.
+int convbranch_bwd_generic(const smx_convbranch_weights* w, int B, int T, const void* x, int x_dt, const void* dy, int dy_dt, void* dx,
+                           int dx_dt, const smx_convbranch_grads* g, Arena& ws, cudaStream_t st, const smx_dropout* drop, void* y_fwd,
+                           int y_dt) {
+  const Drop dr = make_drop(drop);
+  const int64_t rows = (int64_t)B * T;
+  const int D = w->pre.in_dim, U = w->pre.out_dim, H = U / 2, k = w->kernel_size;
+  if (U % 2) return fail(SMX_ERR_BAD_ARG, "Input size must be divisible by 2!");
+  if (w->post.in_dim != H || w->post.out_dim != D || k < 1 || (k % 2) == 0) return fail(SMX_ERR_BAD_ARG, "convolution branch: inconsistent dims");
+  if (w->csgu_linear.w && (w->csgu_linear.in_dim != H || w->csgu_linear.out_dim != H)) return fail(SMX_ERR_BAD_ARG, "convolution branch: csgu linear dims");
+  const int pad = (k - 1) / 2;
+  if (T <= pad) return fail(SMX_ERR_UNSUPPORTED, "convolution branch: reflect padding needs T > (kernel_size - 1) / 2 (T = %d)", T);
+  if (rows > 0x7fffffff) return fail(SMX_ERR_UNSUPPORTED, "convolution branch: more than 2^31 frames");
+  const size_t m0 = ws.mark();
+  BwScratch bw_scratch(ws, rows, U);
+  const float* x32 = (const float*)x;
+  if (x_dt != SMX_F32) {
+    BW_BUF(xc, rows * D);
+    BW_RUN(convert(x, x_dt, xc, SMX_F32, rows * D, st));
+    x32 = xc;
+  }
+  // forward recomputation
+  BW_BUF(z, rows * U);
+  BW_RUN(lin_fwd(w->pre, x32, D, rows, z, U, true, 0, 0, nullptr, 1, st));
+  BW_BUF(u, rows * U);
+  BW_RUN(act_fwd(z, rows, U, w->act, nullptr, u, st));
+  BW_BUF(gl, rows * H);
+  BW_RUN(layernorm(u + H, SMX_F32, U, w->csgu_ln_w, w->csgu_ln_b, 1e-5f, SMX_ACT_IDENTITY, gl, SMX_F32, H, rows, H, st));
+  BW_BUF(gc, rows * H);
+  BW_RUN(dwconv(gl, H, w->csgu_dw_w, w->csgu_dw_b, B, T, H, k, SMX_CONV_SAME_REFLECT, 0, gc, H, st));
+  float* gp = gc;  // gate pre-activation
+  if (w->csgu_linear.w) {
+    BW_BUF(gpl, rows * H);
+    BW_RUN(lin_fwd(w->csgu_linear, gc, H, rows, gpl, H, true, 0, 0, nullptr, 1, st));
+    gp = gpl;
+  }
+  BW_BUF(prod, rows * H);
+  BW_RUN(gate_mul(gp, H, u, U, w->gate_act, rows, H, prod, st));
+  BW_RUN(dropout_inplace(prod, rows * H, dr, 0, st));
+  if (y_fwd) {
+    if (y_dt == SMX_F32 && ((uintptr_t)y_fwd % 32) == 0) {
+      BW_RUN(lin_fwd(w->post, prod, H, rows, (float*)y_fwd, D, true, 0, 0, nullptr, 1, st));
+    } else {
+      BW_BUF(yo, rows * D);
+      BW_RUN(lin_fwd(w->post, prod, H, rows, yo, D, true, 0, 0, nullptr, 1, st));
+      BW_RUN(convert(yo, SMX_F32, y_fwd, y_dt, rows * D, st));
+    }
+    ws.release(m0);
+    return SMX_OK;
+  }
+  // backward
+  BW_BUF(dy32, rows * D);
+  BW_LAUNCH("scale_kernel", scale_kernel<<<ew_grid(rows * D), 256, 0, st>>>(dy, dy_dt, 1.0f, rows * D, dy32));
+  if (g->post.dw) SMX_TRY(lin_wgrad(w->post, dy32, D, prod, H, rows, g->post.dw, 0, 0, ws, st));
+  if (g->post.db) SMX_TRY(colsum_all(dy32, D, rows, D, g->post.db, ws, st));
+  float* dprod = prod;  // prod is dead
+  BW_RUN(lin_dgrad(w->post, dy32, D, rows, dprod, SMX_F32, H, 0, 0, nullptr, st));
+  BW_RUN(dropout_inplace(dprod, rows * H, dr, 0, st));
+  BW_BUF(du, rows * U);
+  BW_BUF(dg, rows * H);
+  BW_LAUNCH("csgu_gate_bwd_kernel", csgu_gate_bwd_kernel<<<ew_grid(rows * H), 256, 0, st>>>(dprod, gp, u, U, H, w->gate_act, rows * H, du, dg));
+  float* dgc = dg;
+  if (w->csgu_linear.w) {
+    if (g->csgu_linear.dw) SMX_TRY(lin_wgrad(w->csgu_linear, dg, H, gc, H, rows, g->csgu_linear.dw, 0, 0, ws, st));
+    if (g->csgu_linear.db) SMX_TRY(colsum_all(dg, H, rows, H, g->csgu_linear.db, ws, st));
+    dgc = dprod;  // dprod is dead
+    BW_RUN(lin_dgrad(w->csgu_linear, dg, H, rows, dgc, SMX_F32, H, 0, 0, nullptr, st));
+  }
+  if (g->csgu_dw_db) SMX_TRY(colsum_all(dgc, H, rows, H, g->csgu_dw_db, ws, st));
+  if (g->csgu_dw_dw) {
+    const int ups = 4, ns = (B + ups - 1) / ups;
+    const size_t m1 = ws.mark();
+    BW_BUF(P, (size_t)ns * H * k);
+    BW_LAUNCH("dwconv_bwd_w_kernel", dwconv_bwd_w_kernel<<<dim3((H + 31) / 32, k, ns), 256, 0, st>>>(dgc, gl, B, T, H, k, pad, ups, P, 1));
+    BW_RUN(sum_slices(P, ns, H, k, g->csgu_dw_dw, k, st));
+    ws.release(m1);
+  }
+  // d(LN output) straight into the gate half of du, then the LayerNorm backward in place there (input: the gate half of u)
+  BW_LAUNCH("dwconv_bwd_data_kernel", dwconv_bwd_data_kernel<<<ew_grid(rows * H), 256, 0, st>>>(dgc, w->csgu_dw_w, B, T, H, k, pad, 1, du + H, U));
+  SMX_TRY(ln_bwd(u + H, rows, H, w->csgu_ln_w, du + H, g->csgu_ln_dw, g->csgu_ln_db, ws, st, 1e-5f, U, U));
+  BW_RUN(act_bwd(z, du, SMX_F32, rows, U, w->act, nullptr, du, st));
+  if (g->pre.dw) SMX_TRY(lin_wgrad(w->pre, du, U, x32, D, rows, g->pre.dw, 0, 0, ws, st));
+  if (g->pre.db) SMX_TRY(colsum_all(du, U, rows, U, g->pre.db, ws, st));
+  if (dx) BW_RUN(lin_dgrad(w->pre, du, U, rows, dx, dx_dt, D, 0, 0, nullptr, st));
   ws.release(m0);
   return SMX_OK;
 }
@@ -1113,6 +1241,15 @@ int dropout_keep_mask(const smx_dropout* drop, int site, int64_t n, uint8_t* kee
   dropout_mask_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(keep, n, dr.seed, (uint32_t)site, dr.on ? dr.thresh : 0u);
   count_launch();
   return check_launch("dropout_mask_kernel");
+}
+
+int dropout_apply(const smx_dropout* drop, int site, int dt, int64_t n, const void* x, void* y, cudaStream_t st) {
+  const Drop dr = make_drop(drop);
+  if (n <= 0) return SMX_OK;
+  const int64_t quads = (n + 3) / 4;
+  dropout_apply_kernel<<<(unsigned)((quads + 255) / 256), 256, 0, st>>>(x, y, dt, n, dr.seed, (uint32_t)site, dr.on ? dr.thresh : 0u, dr.on ? dr.scale : 1.0f);
+  count_launch();
+  return check_launch("dropout_apply_kernel");
 }
 
 }  // namespace smx

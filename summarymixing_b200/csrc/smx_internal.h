@@ -118,6 +118,10 @@ int layernorm_bwd_generic(const void* x, int x_dt, int64_t rows, int D, const fl
 int ffn_bwd_generic(const smx_ffn_weights* w, int act, int64_t rows, const void* x, int x_dt, const float* oln_w, const float* oln_b,
                     float oln_eps, const void* dy, int dy_dt, void* dx, int dx_dt, const smx_ffn_grads* g, Arena& ws, cudaStream_t st,
                     const smx_dropout* drop = nullptr, void* y_fwd = nullptr, int y_dt = 0);
+int convbranch_bwd_generic(const smx_convbranch_weights* w, int B, int T, const void* x, int x_dt, const void* dy, int dy_dt, void* dx,
+                           int dx_dt, const smx_convbranch_grads* g, Arena& ws, cudaStream_t st, const smx_dropout* drop = nullptr,
+                           void* y_fwd = nullptr, int y_dt = 0);
+int dropout_apply(const smx_dropout* drop, int site, int dt, int64_t n, const void* x, void* y, cudaStream_t st);
 int convmod_bwd_generic(const smx_convmod_weights* w, int act, int B, int T, const void* x, int x_dt, const uint8_t* mask, const void* dy,
                         int dy_dt, void* dx, int dx_dt, const smx_convmod_grads* g, Arena& ws, cudaStream_t st,
                         const smx_dropout* drop = nullptr, void* y_fwd = nullptr, int y_dt = 0);

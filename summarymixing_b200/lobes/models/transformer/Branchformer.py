@@ -13,6 +13,7 @@ from typing import Optional
 import torch
 import torch.nn as nn
 
+from .... import _autograd as A
 from .... import _host as H
 from .... import _lib as L
 from ....nnet.containers import LayerNorm
@@ -81,6 +82,35 @@ class ConvolutionBranch(nn.Module):
         )
         self._act_code = H.act_code(self.activation)
         self._gate_code = H.act_code(self.csgu.activation)
+        self._wv = H.WeightView()
+
+    def grad_params(self):
+        """Parameters in the order smx_convbranch_grads lists their gradients."""
+        out = [self.pre_channel_proj.weight, self.pre_channel_proj.bias, self.post_channel_proj.weight, self.post_channel_proj.bias,
+               self.csgu.norm.norm.weight, self.csgu.norm.norm.bias, self.csgu.conv.conv.weight, self.csgu.conv.conv.bias]
+        if self.csgu.use_linear_after_conv:
+            out += [self.csgu.linear.weight, self.csgu.linear.bias]
+        return out
+
+    def forward(self, x):
+        """(B,T,input_size) -> (B,T,input_size), Branchformer.py:86-97.  Runs on the fp32-math arm (linears as split-bf16 tensor-core
+        GEMMs); recorded by autograd (smx_conv_branch_train_bwd) when x requires grad or in training mode, where the CSGU's dropout
+        applies.  Inside a BranchformerEncoderLayer's inference forward the branch is part of the layer's fused path instead."""
+        H.require_cuda(x, "ConvolutionBranch")
+        dev = x.device
+        if self._wv.stale(list(self.parameters()), dev):
+            bw = L.ConvBranchWeights()
+            self.fill(bw, self._wv, dev)
+            self._wv.struct = bw
+        return self.run(self._wv.struct, x)
+
+    def run(self, bw: L.ConvBranchWeights, x):
+        """The branch on a filled weights struct (its own, or the one inside the owning layer's struct)."""
+        drop = A.new_dropout(self, self.csgu.dropout.p)
+        if A.wants_grad(self, x):
+            return A.ConvBranchFunction.apply(bw, drop, x, *self.grad_params())
+        with torch.no_grad():
+            return A.ConvBranchFunction.apply(bw, drop, x, *self.grad_params())
 
     def fill(self, bw: L.ConvBranchWeights, wv: H.WeightView, device) -> None:
         pre, post = self.pre_channel_proj, self.post_channel_proj
@@ -182,7 +212,6 @@ class BranchformerEncoderLayer(nn.Module):
         pos_embs: Optional[torch.Tensor] = None,
     ):
         H.require_cuda(x, "BranchformerEncoderLayer")
-        H.check_grad_mode(self)
         B, T, D = x.shape
         dev = x.device
         xc = x.contiguous()
@@ -192,6 +221,11 @@ class BranchformerEncoderLayer(nn.Module):
             lw = L.BranchformerLayerWeights()
             self.fill(lw, self._wv, dev)
             self._wv.struct = lw
+        if A.wants_grad(self, x):
+            if smask is not None and self.mode != "SummaryMixing-lite":
+                raise NotImplementedError("summarymixing_b200: backward with sum_mask is not implemented")
+            return self._forward_autograd(xc, mask), None
+        H.check_grad_mode(self)
         y = torch.empty_like(xc)
         lib = L.lib()
         dt = H.dtype_code(xc)
@@ -202,6 +236,22 @@ class BranchformerEncoderLayer(nn.Module):
                                                    H.p_or_none(smask), y.data_ptr(), ws.data_ptr(), ws.numel(),
                                                    H.stream_ptr(dev)))
         return y, None
+
+
+def _branchformer_layer_forward_autograd(self, x, mask):
+    """The layer as a chain of autograd nodes (Branchformer.py:262-334): norm_mhsa -> cell -> dropout | norm_conv -> convolution
+    branch -> dropout | merge_proj(cat) -> dropout -> + x.  In training mode the three nn.Dropout calls of the layer use one
+    smx_dropout (sites 1, 2, 3: counter-based masks, regenerated by the backward) and the CSGU's dropout another (site 0)."""
+    drop = A.new_dropout(self, self.dropout.p)
+    x1 = self.mha_layer(self.norm_mhsa(x), src_padding_mask=mask)                       # :317-322
+    x1 = A.dropout(drop, 1, x1)                                                          # :334
+    x2 = self.convolution_branch.run(self._wv.struct.branch, self.norm_conv(x))          # :292-293 (no mask, :276)
+    x2 = A.dropout(drop, 2, x2)                                                          # :294
+    merged = self.merge_proj(torch.cat([x1, x2], dim=-1))                                # :279, :220-226
+    return x + A.dropout(drop, 3, merged)
+
+
+BranchformerEncoderLayer._forward_autograd = _branchformer_layer_forward_autograd
 
 
 class BranchformerEncoder(nn.Module):
@@ -269,13 +319,18 @@ class BranchformerEncoder(nn.Module):
     ):
         assert dynchunktrain_config is None, "Dynamic Chunk Training unsupported for this encoder"
         H.require_cuda(src, "BranchformerEncoder")
-        H.check_grad_mode(self)
         B, T, D = src.shape
         dev = src.device
         xc = src.contiguous()
         mask = H.mask_u8(src_key_padding_mask, B, T, dev)
         smask = H.sum_mask_f32(src_mask, T, dev)
         n = len(self.layers)
+        if A.wants_grad(self, src):  # training / differentiable path: the layers' autograd chains, then the final norm (:479-491)
+            out = xc
+            for layer in self.layers:
+                out, _ = layer(out, src_mask=src_mask, src_key_padding_mask=mask)
+            return self.norm(out), [None] * n
+        H.check_grad_mode(self)
         if self._wv.stale(self.params(), dev):
             arr = (L.BranchformerLayerWeights * n)()
             for i, layer in enumerate(self.layers):

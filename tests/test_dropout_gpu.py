@@ -166,3 +166,84 @@ def test_dropout_bf16_io_and_keep_rate():
     keep = torch.empty(B * T * 512, dtype=torch.uint8, device=DEV)
     L.check(L.lib().smx_dropout_keep_mask(C.byref(L.Dropout(p, s[2])), 0, keep.numel(), keep.data_ptr(), None))
     assert abs(float(keep.float().mean()) - (1 - p)) < 2e-3
+
+
+def _csgu_live(enc, seed):
+    """The CSGU's depthwise weights are ~1e-6 at initialisation (upstream): give the convolution something to do."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for n, prm in enc.named_parameters():
+            if "csgu.conv.conv.weight" in n:
+                prm.add_(0.2 * torch.randn(prm.shape, generator=g))
+    return enc
+
+
+@pytest.mark.parametrize("mode", ["SummaryMixing", "SummaryMixing-lite"])
+def test_branchformer_encoder_trains_with_dropout(mode):
+    """Two Branchformer layers at the recipes' dropout 0.1 (branchformer_summarymixing.yaml): forward and every gradient against the
+    oracle under the same masks.  Seeds are drawn per layer call in the order layer (its three nn.Dropout calls are sites 1, 2, 3),
+    cell (mode "SummaryMixing" only: the reference builds the cell with its default global_dropout = 0.1), convolution branch."""
+    torch.manual_seed(8)
+    p, nl, lite = 0.1, 2, mode == "SummaryMixing-lite"
+    enc = S.BranchformerEncoder(nl, 64, 1, 31, csgu_linear_units=192, local_proj_hid_dim=[64], local_proj_out_dim=64, summary_hid_dim=[64],
+                                summary_out_dim=64, mode=mode, dropout=p)
+    enc = _csgu_live(_perturbed(enc, 8), 9).to(DEV).train()
+    B, T = 3, 70
+    x = torch.randn(B, T, 64, device=DEV, requires_grad=True)
+    mask = (torch.arange(T)[None] < torch.tensor([T, 41, 16])[:, None]).to(DEV)
+    dy = torch.randn(B, T, 64, device=DEV)
+    per = 2 if lite else 3
+    s = _seeds(45, per * nl)
+    y = enc(x, src_key_padding_mask=mask)[0]
+    y.backward(dy)
+    sites = {}
+    for i in range(nl):
+        pre, si = f"layers.{i}.", s[per * i:per * (i + 1)]
+        sites.update({pre + "x1": (si[0], 1), pre + "x2": (si[0], 2), pre + "merge": (si[0], 3),
+                      pre + "convolution_branch.csgu.out": (si[-1], 0)})
+        if not lite:
+            sites[pre + "mha_layer.cat"] = (si[1], 0)
+    hook = OD.Hook(p, sites)
+    y_or, dx_or, g_or = _oracle(lambda xo, sd: O.branchformer_encoder(xo, sd, nl, act="gelu", mode=mode, src_key_padding_mask=mask.cpu(),
+                                                                      drop=hook), enc, x, dy)
+    assert sorted(hook.used) == sorted(sites)
+    _close(y, y_or, 5e-4, "forward")
+    _close(x.grad, dx_or, 5e-4, "dx")
+    for k, prm in enc.named_parameters():
+        if g_or[k] is None:  # "-lite" keeps the unused projections of the cell
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, k
+            continue
+        assert prm.grad is not None and torch.isfinite(prm.grad).all(), k
+        _close(prm.grad, g_or[k], 5e-4, k)
+    y2 = enc(x.detach(), src_key_padding_mask=mask)[0]
+    assert float((y2.detach() - y.detach()).abs().max()) > 1e-3
+
+
+def test_convolution_branch_standalone_and_use_linear_after_conv():
+    """ConvolutionBranch.forward on its own (Branchformer.py:86-97) with the optional linear after the convolution and a gate
+    activation: eval forward, and forward + gradients in training mode with the CSGU's dropout, against the oracle."""
+    torch.manual_seed(10)
+    p = 0.2
+    m = S.ConvolutionBranch(64, linear_units=128, kernel_size=15, activation=nn.GELU, gate_activation=nn.Tanh, dropout=p, use_linear_after_conv=True)
+    m = _csgu_live(_perturbed(m, 10), 11).to(DEV)
+    B, T = 2, 45
+    x = torch.randn(B, T, 64, device=DEV, requires_grad=True)
+    dy = torch.randn(B, T, 64, device=DEV)
+    with torch.no_grad():
+        y_eval = m.eval()(x.detach())
+    y_plain = O.convolution_branch(x.detach().cpu(), {k: v.detach().cpu() for k, v in m.state_dict().items()}, "", act="gelu", gate_act="tanh")
+    _close(y_eval, y_plain, 1e-4, "eval forward")
+    m.train()
+    (s0,) = _seeds(46, 1)
+    y = m(x)
+    y.backward(dy)
+    hook = OD.Hook(p, {"csgu.out": (s0, 0)})
+    y_or, dx_or, g_or = _oracle(lambda xo, sd: O.convolution_branch(xo, sd, "", act="gelu", gate_act="tanh", drop=hook), m, x, dy)
+    assert hook.used == ["csgu.out"]
+    _close(y, y_or, 1e-4, "forward")
+    _close(x.grad, dx_or, 2e-4, "dx")
+    for k, prm in m.named_parameters():
+        _close(prm.grad, g_or[k], 2e-4, k)
+    # T too short for the reflect padding: a loud error like torch's
+    with pytest.raises(Exception):
+        m(torch.randn(1, 7, 64, device=DEV))
