@@ -882,6 +882,80 @@ __global__ void __launch_bounds__(256) dropout_apply_kernel(const void* x, void*
       else ((float*)y)[e0 + i] = v;
     }
 }
+// reflect-padded depthwise conv, data gradient, the part the zero-padded form misses: frames s <= pad and s >= T-1-pad also collect the
+// taps that read their mirror images (padded frame -s and padded frame 2(T-1)-s).  din += ...; one thread per (utterance, boundary frame, channel).
+__global__ void __launch_bounds__(256) dwconv_reflect_fix_kernel(const float* dout, const float* w, int B, int T, int C, int k, int pad, float* din,
+                                                                 int64_t ldo) {
+  const int nb = T <= 2 * pad + 2 ? T : 2 * pad + 2;
+  const int64_t n = (int64_t)B * nb * C;
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
+    const int c = (int)(i % C);
+    const int r = (int)((i / C) % nb);
+    const int b = (int)(i / ((int64_t)C * nb));
+    const int t = T <= 2 * pad + 2 ? r : (r <= pad ? r : T - 1 - (r - pad - 1));
+    const float* base = dout + (int64_t)b * T * C + c;
+    float acc = 0.0f;
+    for (int j = 0; j < k; ++j) {
+      const float wj = w[(int64_t)c * k + j];
+      const int ul = pad - j - t;
+      if (t >= 1 && ul >= 0 && ul < T) acc = fmaf(wj, base[(int64_t)ul * C], acc);
+      const int ur = 2 * (T - 1) - t - j + pad;
+      if (t <= T - 2 && ur >= 0 && ur < T) acc = fmaf(wj, base[(int64_t)ur * C], acc);
+    }
+    din[((int64_t)b * T + t) * ldo + c] += acc;
+  }
+}
+// depthwise conv, weight gradient, register-window form: a thread owns one channel and K accumulators, a warp a strip of 64 frames of one
+// utterance (blocks of eight frames: 8 dout values against K + 7 input frames), a CTA eight consecutive strips; the warps' sums are
+// added in fixed order through shared memory: P[slice = (utterance, 512-frame span)][c][j].
+template <int K>
+__global__ void __launch_bounds__(256) dwconv_wgrad_win_kernel(const float* __restrict__ dout, const float* __restrict__ in, int B, int T, int C,
+                                                               int pad, int reflect, int spans, float* __restrict__ P) {
+  __shared__ float red[8][K][33];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int ncg = (C + 31) / 32;
+  const int cg = blockIdx.x % ncg;
+  const int slice = blockIdx.x / ncg;
+  const int b = slice / spans, span = slice % spans;
+  const int c = cg * 32 + lane;
+  float acc[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) acc[j] = 0.0f;
+  if (c < C) {
+    const float* dob = dout + (int64_t)b * T * C + c;
+    const float* inb = in + (int64_t)b * T * C + c;
+    const int ts = span * 512 + warp * 64;
+#pragma unroll 1
+    for (int blk = 0; blk < 8; ++blk) {
+      const int t0 = ts + blk * 8;
+      if (t0 >= T) break;
+      float d[8];
+#pragma unroll
+      for (int o = 0; o < 8; ++o) d[o] = t0 + o < T ? dob[(int64_t)(t0 + o) * C] : 0.0f;
+#pragma unroll
+      for (int i = 0; i < K + 7; ++i) {
+        int u = t0 + i - pad;
+        if (reflect) u = u < 0 ? -u : (u >= T ? 2 * (T - 1) - u : u);
+        const float x = (u >= 0 && u < T) ? inb[(int64_t)u * C] : 0.0f;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) {
+          const int j = i - o;
+          if (j >= 0 && j < K) acc[j] = fmaf(d[o], x, acc[j]);
+        }
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < K; ++j) red[warp][j][lane] = acc[j];
+  __syncthreads();
+  for (int e = threadIdx.x; e < 32 * K; e += 256) {
+    const int l = e / K, j = e - l * K;   // consecutive threads -> consecutive j of one channel: P rows are contiguous
+    float tot = 0.0f;
+#pragma unroll
+    for (int wv = 0; wv < 8; ++wv) tot += red[wv][j][l];
+    if (cg * 32 + l < C) P[((int64_t)slice * C + cg * 32 + l) * K + j] = tot;
+  }
+}
 // depthwise conv, gradient with respect to the input: din[b,t,c] = sum_j w[c,j] * dout[b, t - j + pad, c]; reflect != 0: the input
 // was reflect-padded (frame -s and frame T-1+s read frames s and T-1-s: those taps' gradients land there too; T > pad).
 // din has row stride ldo.
@@ -940,6 +1014,53 @@ __global__ void __launch_bounds__(256) dwconv_bwd_w_kernel(const float* dout, co
 }
 
 }  // namespace
+
+// din (row stride ldo) = gradient of the depthwise conv input; dw (C,1,k) = its weight gradient.  Register-window kernels for the
+// common kernel sizes (k = 31, 15), the per-element kernels otherwise.
+int dwconv_bwd_data(const float* dout, const float* w, int B, int T, int C, int k, int pad, int reflect, float* din, int64_t ldo,
+                    cudaStream_t st) {
+  int status = SMX_OK;
+  if (dwconv_window(dout, C, w, nullptr, B, T, C, k, k - 1 - pad, 0, 1, din, ldo, st, &status)) {
+    SMX_TRY(status);
+    if (reflect) {
+      const int nb = T <= 2 * pad + 2 ? T : 2 * pad + 2;
+      dwconv_reflect_fix_kernel<<<ew_grid((int64_t)B * nb * C), 256, 0, st>>>(dout, w, B, T, C, k, pad, din, ldo);
+      count_launch();
+      SMX_TRY(check_launch("dwconv_reflect_fix_kernel"));
+    }
+    return SMX_OK;
+  }
+  dwconv_bwd_data_kernel<<<ew_grid((int64_t)B * T * C), 256, 0, st>>>(dout, w, B, T, C, k, pad, reflect, din, ldo);
+  count_launch();
+  return check_launch("dwconv_bwd_data_kernel");
+}
+int dwconv_wgrad(const float* dout, const float* in, int B, int T, int C, int k, int pad, int reflect, float* dw, Arena& ws, cudaStream_t st) {
+  const size_t m0 = ws.mark();
+  if (k == 31 || k == 15) {
+    const int spans = (T + 511) / 512, ns = B * spans, ncg = (C + 31) / 32;
+    float* P = ws.f32((size_t)ns * C * k);
+    if (!P) return fail(SMX_ERR_WORKSPACE, "workspace too small (depthwise weight gradient)");
+    if (!ws.dry) {
+      if (k == 31) dwconv_wgrad_win_kernel<31><<<(unsigned)(ns * ncg), 256, 0, st>>>(dout, in, B, T, C, pad, reflect, spans, P);
+      else dwconv_wgrad_win_kernel<15><<<(unsigned)(ns * ncg), 256, 0, st>>>(dout, in, B, T, C, pad, reflect, spans, P);
+      count_launch();
+      SMX_TRY(check_launch("dwconv_wgrad_win_kernel"));
+      SMX_TRY(sum_slices(P, ns, C, k, dw, k, st));
+    }
+  } else {
+    const int ups = 4, ns = (B + ups - 1) / ups;
+    float* P = ws.f32((size_t)ns * C * k);
+    if (!P) return fail(SMX_ERR_WORKSPACE, "workspace too small (depthwise weight gradient)");
+    if (!ws.dry) {
+      dwconv_bwd_w_kernel<<<dim3((C + 31) / 32, k, ns), 256, 0, st>>>(dout, in, B, T, C, k, pad, ups, P, reflect);
+      count_launch();
+      SMX_TRY(check_launch("dwconv_bwd_w_kernel"));
+      SMX_TRY(sum_slices(P, ns, C, k, dw, k, st));
+    }
+  }
+  ws.release(m0);
+  return SMX_OK;
+}
 
 #define BW_RUN(expr) do { if (!ws.dry) SMX_TRY(expr); } while (0)
 #define BW_BUF(name, n) float* name = ws.f32((size_t)(n)); if (!name) return fail(SMX_ERR_WORKSPACE, "workspace too small (backward)")
@@ -1038,7 +1159,12 @@ int ffn_bwd_generic(const smx_ffn_weights* w, int act, int64_t rows, const void*
     SMX_TRY(ln_bwd(ypre_d, rows, D, oln_w, gy, g->out_ln_dw, g->out_ln_db, ws, st, oln_eps));
   } else if (oln_w) {
     BW_BUF(ypre, rows * D);
-    if (!ws.dry) {  // ypre = x + 0.5 * (h W2^T + b2)
+    if (!ws.dry && bw_tc_ok(rows, F, D, h, F, ypre, D, true) && ((uintptr_t)x32 % 16) == 0) {  // ypre = x + 0.5 * (h W2^T + b2), split-bf16 tensor-core GEMM
+      GemmTc gt{};
+      gt.bias = w->w2.b; gt.act = SMX_ACT_IDENTITY; gt.alpha = 0.5f; gt.resid_f32 = x32; gt.ldr = D; gt.out_f32 = ypre; gt.ldo = D;
+      gt.rows_per_group = 1;
+      SMX_TRY(tc_linear_split3(w->w2, 0, F, h, F, rows, gt, t_bw_sc, st));
+    } else if (!ws.dry) {
       GemmP p = bw_gemm();
       p.A = h; p.lda = F; p.C = ypre; p.ldc = D; p.M = (int)rows; p.K = F; p.N = D;
       p.W = w->w2.w; p.w_sk = 1; p.w_sn = F; p.bias = w->w2.b;
@@ -1120,16 +1246,9 @@ int convmod_bwd_generic(const smx_convmod_weights* w, int act, int B, int T, con
   SMX_TRY(ln_bwd(c, rows, D, w->after_ln_w, da, g->after_ln_dw, g->after_ln_db, ws, st));
   float* dc = da;
   if (g->dw_db) SMX_TRY(colsum_all(dc, D, rows, D, g->dw_db, ws, st));
-  if (g->dw_dw) {
-    const int ups = 4, ns = (B + ups - 1) / ups;
-    const size_t m1 = ws.mark();
-    BW_BUF(P, (size_t)ns * D * k);
-    BW_LAUNCH("dwconv_bwd_w_kernel", dwconv_bwd_w_kernel<<<dim3((D + 31) / 32, k, ns), 256, 0, st>>>(dc, gl, B, T, D, k, pad, ups, P));
-    BW_RUN(sum_slices(P, ns, D, k, g->dw_dw, k, st));
-    ws.release(m1);
-  }
+  if (g->dw_dw) SMX_TRY(dwconv_wgrad(dc, gl, B, T, D, k, pad, 0, g->dw_dw, ws, st));
   float* dgl = dout;  // dout is dead
-  BW_LAUNCH("dwconv_bwd_data_kernel", dwconv_bwd_data_kernel<<<ew_grid(rows * D), 256, 0, st>>>(dc, w->dw_w, B, T, D, k, pad, 0, dgl, D));
+  BW_RUN(dwconv_bwd_data(dc, w->dw_w, B, T, D, k, pad, 0, dgl, D, st));
   BW_BUF(dp, rows * 2 * D);
   BW_LAUNCH("glu_bwd_kernel", glu_bwd_kernel<<<ew_grid(rows * D), 256, 0, st>>>(p, dgl, rows, D, dp));
   if (g->bottleneck.dw) SMX_TRY(lin_wgrad(w->bottleneck, dp, 2 * D, xn, D, rows, g->bottleneck.dw, 0, 0, ws, st));
@@ -1212,16 +1331,9 @@ int convbranch_bwd_generic(const smx_convbranch_weights* w, int B, int T, const 
     BW_RUN(lin_dgrad(w->csgu_linear, dg, H, rows, dgc, SMX_F32, H, 0, 0, nullptr, st));
   }
   if (g->csgu_dw_db) SMX_TRY(colsum_all(dgc, H, rows, H, g->csgu_dw_db, ws, st));
-  if (g->csgu_dw_dw) {
-    const int ups = 4, ns = (B + ups - 1) / ups;
-    const size_t m1 = ws.mark();
-    BW_BUF(P, (size_t)ns * H * k);
-    BW_LAUNCH("dwconv_bwd_w_kernel", dwconv_bwd_w_kernel<<<dim3((H + 31) / 32, k, ns), 256, 0, st>>>(dgc, gl, B, T, H, k, pad, ups, P, 1));
-    BW_RUN(sum_slices(P, ns, H, k, g->csgu_dw_dw, k, st));
-    ws.release(m1);
-  }
+  if (g->csgu_dw_dw) SMX_TRY(dwconv_wgrad(dgc, gl, B, T, H, k, pad, 1, g->csgu_dw_dw, ws, st));
   // d(LN output) straight into the gate half of du, then the LayerNorm backward in place there (input: the gate half of u)
-  BW_LAUNCH("dwconv_bwd_data_kernel", dwconv_bwd_data_kernel<<<ew_grid(rows * H), 256, 0, st>>>(dgc, w->csgu_dw_w, B, T, H, k, pad, 1, du + H, U));
+  BW_RUN(dwconv_bwd_data(dgc, w->csgu_dw_w, B, T, H, k, pad, 1, du + H, U, st));
   SMX_TRY(ln_bwd(u + H, rows, H, w->csgu_ln_w, du + H, g->csgu_ln_dw, g->csgu_ln_db, ws, st, 1e-5f, U, U));
   BW_RUN(act_bwd(z, du, SMX_F32, rows, U, w->act, nullptr, du, st));
   if (g->pre.dw) SMX_TRY(lin_wgrad(w->pre, du, U, x32, D, rows, g->pre.dw, 0, 0, ws, st));

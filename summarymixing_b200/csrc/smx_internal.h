@@ -71,6 +71,8 @@ int masked_mean(const float* s, int64_t lds, const uint8_t* mask, int B, int T, 
 int glu(const float* p, int64_t rows, int D, float* out, cudaStream_t st);
 int dwconv(const float* in, int64_t ldin, const float* w, const float* b, int B, int T, int C, int k, int pad_mode,
            int chunk, float* out, int64_t ldout, cudaStream_t st);
+bool dwconv_window(const float* in, int64_t ldin, const float* w, const float* b, int B, int T, int C, int k, int pad, int reflect, int flip,
+                   float* out, int64_t ldout, cudaStream_t st, int* status);
 int gate_mul(const float* gate, int64_t ldg, const float* other, int64_t ldo, int gate_act, int64_t rows, int C,
              float* out, cudaStream_t st);
 int broadcast_rows(const float* src, int B, int T, int D, float* dst, int64_t lddst, cudaStream_t st);

@@ -2,6 +2,8 @@
 // Every tensor carries a runtime dtype tag (fp32 or bf16 storage); arithmetic is fp32 throughout.
 // These kernels handle every shape and mode the reference accepts; the tcgen05 arm (smx_tc_*.cu)
 // takes over for the bf16 shapes it supports.
+#include <cstdio>
+#include <cstdlib>
 #include "smx_internal.h"
 #include <math.h>
 
@@ -326,11 +328,81 @@ __global__ void dwconv_kernel(const float* in, int64_t ldin, const float* w, con
   }
   out[((int64_t)b * T + t) * ldout + c] = acc;
 }
+// Register-window form for the common kernel sizes: a thread owns one channel (its K taps in registers) and blocks of eight
+// consecutive frames (8 accumulators, K + 7 loads per 8 K FMAs; lanes = 32 consecutive channels: coalesced rows).  A warp walks
+// four frame blocks of one utterance.  flip: taps reversed (the data gradient of a zero-padded convolution is the correlation with
+// the reversed taps and pad' = K - 1 - pad).  reflect: frames outside [0, T) read their mirror image, else zero.
+template <int K>
+__global__ void __launch_bounds__(256) dwconv_win_kernel(const float* __restrict__ in, int64_t ldin, const float* __restrict__ w,
+                                                         const float* __restrict__ bias, int B, int T, int C, int pad, int reflect, int flip,
+                                                         float* __restrict__ out, int64_t ldout, int strips) {
+  const int lane = threadIdx.x & 31;
+  const int64_t wg = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+  const int ncg = (C + 31) / 32;
+  const int cg = (int)(wg % ncg);
+  const int strip = (int)((wg / ncg) % strips);
+  const int b = (int)(wg / ((int64_t)ncg * strips));
+  const int c = cg * 32 + lane;
+  if (b >= B || c >= C) return;
+  float wt[K];
+#pragma unroll
+  for (int j = 0; j < K; ++j) wt[j] = w[(int64_t)c * K + (flip ? K - 1 - j : j)];
+  const float bv = bias ? bias[c] : 0.0f;
+  const float* base = in + (int64_t)b * T * ldin + c;
+  float* obase = out + (int64_t)b * T * ldout + c;
+#pragma unroll 1
+  for (int blk = 0; blk < 4; ++blk) {
+    const int t0 = strip * 32 + blk * 8;
+    if (t0 >= T) break;
+    float a[8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) a[o] = bv;
+#pragma unroll
+    for (int i = 0; i < K + 7; ++i) {
+      int u = t0 + i - pad;
+      if (reflect) u = u < 0 ? -u : (u >= T ? 2 * (T - 1) - u : u);
+      const float x = (u >= 0 && u < T) ? base[(int64_t)u * ldin] : 0.0f;
+#pragma unroll
+      for (int o = 0; o < 8; ++o) {
+        const int j = i - o;
+        if (j >= 0 && j < K) a[o] = fmaf(wt[j], x, a[o]);
+      }
+    }
+#pragma unroll
+    for (int o = 0; o < 8; ++o)
+      if (t0 + o < T) obase[(int64_t)(t0 + o) * ldout] = a[o];
+  }
+}
+template <int K>
+static int launch_dwconv_win(const float* in, int64_t ldin, const float* w, const float* b, int B, int T, int C, int pad, int reflect, int flip,
+                             float* out, int64_t ldout, cudaStream_t st) {
+  const int strips = (T + 31) / 32, ncg = (C + 31) / 32;
+  const int64_t warps = (int64_t)B * strips * ncg;
+  dwconv_win_kernel<K><<<(unsigned)((warps + 7) / 8), 256, 0, st>>>(in, ldin, w, b, B, T, C, pad, reflect, flip, out, ldout, strips);
+  count_launch();
+  return check_launch("dwconv_win_kernel");
+}
+// out[b,t,c] = bias[c] + sum_j w[c, flip ? k-1-j : j] * in[b, t + j - pad, c] with zero or mirrored frames outside [0, T); false when
+// this kernel size has no register-window instance (the caller keeps its generic kernel)
+bool dwconv_window(const float* in, int64_t ldin, const float* w, const float* b, int B, int T, int C, int k, int pad, int reflect, int flip,
+                   float* out, int64_t ldout, cudaStream_t st, int* status) {
+  switch (k) {
+    case 31: *status = launch_dwconv_win<31>(in, ldin, w, b, B, T, C, pad, reflect, flip, out, ldout, st); return true;
+    case 15: *status = launch_dwconv_win<15>(in, ldin, w, b, B, T, C, pad, reflect, flip, out, ldout, st); return true;
+    default: return false;
+  }
+}
+
 int dwconv(const float* in, int64_t ldin, const float* w, const float* b, int B, int T, int C, int k, int pad_mode,
            int chunk, float* out, int64_t ldout, cudaStream_t st) {
   if (pad_mode == SMX_CONV_SAME_REFLECT && (k - 1) / 2 >= T)
     return fail(SMX_ERR_BAD_ARG, "reflect padding %d needs T > pad (T=%d)", (k - 1) / 2, T);
   if (pad_mode == SMX_CONV_CHUNKED && chunk <= 0) return fail(SMX_ERR_BAD_ARG, "chunked conv needs chunk_size > 0");
+  if (pad_mode != SMX_CONV_CHUNKED) {
+    int status = SMX_OK;
+    const int pad = (pad_mode == SMX_CONV_CAUSAL) ? (k - 1) : (k - 1) / 2;
+    if (dwconv_window(in, ldin, w, b, B, T, C, k, pad, pad_mode == SMX_CONV_SAME_REFLECT, 0, out, ldout, st, &status)) return status;
+  }
   int64_t n = (int64_t)B * T * C;
   dwconv_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(in, ldin, w, b, B, T, C, k, pad_mode, chunk, out, ldout);
   count_launch();

@@ -12,6 +12,7 @@ import argparse
 import json
 import os
 import sys
+import time
 
 import torch
 import torch.distributed as dist
@@ -55,7 +56,7 @@ def main():
     lens = torch.randint(a.T // 2, a.T + 1, (a.B,), generator=g)
     mask = (torch.arange(a.T)[None] < lens[:, None]).to(dev)
     target = torch.randn(a.B, a.T, a.D, generator=g).to(dev)
-    losses, calls = [], 0
+    losses, calls, host_ms = [], 0, 0.0
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     n0 = L.lib().smx_launch_count()
     for i in range(a.warmup + a.steps):
@@ -65,12 +66,15 @@ def main():
             torch.cuda.synchronize()
             n0 = L.lib().smx_launch_count()
             ev0.record()
+        h0 = time.perf_counter()
         opt.zero_grad(set_to_none=True)
         y = model(x, src_key_padding_mask=mask)[0]
         loss = ((y.float() - target) * mask[..., None]).pow(2).mean()
         loss.backward()
         calls = -1 if model is not enc else P.allreduce_gradients(params)  # (-1: DDP's own bucketed all-reduce)
         opt.step()
+        if i >= a.warmup:
+            host_ms += (time.perf_counter() - h0) * 1e3   # host time to ENQUEUE the step (the loss read-back below waits for the GPU)
         losses.append(float(loss.detach()))
     ev1.record()
     if world > 1:
@@ -86,7 +90,7 @@ def main():
         dist.all_reduce(hi, op=dist.ReduceOp.MAX)
     if rank == 0:
         print(json.dumps({"what": "encoder training step (fwd + bwd + grad all-reduce + SGD)", "n_gpus": world, "io": a.dtype,
-                          "layers": a.layers, "B_per_gpu": a.B, "T": a.T, "D": a.D, "ms_per_step": ms,
+                          "layers": a.layers, "B_per_gpu": a.B, "T": a.T, "D": a.D, "ms_per_step": ms, "host_enqueue_ms_per_step": host_ms / a.steps,
                           "frames_per_s": world * a.B * a.T / (ms * 1e-3), "libsmx_launches_per_step": int(launches),
                           "allreduce_calls_per_step": calls, "params": sum(p.numel() for p in params),
                           "loss_first": losses[0], "loss_last": losses[-1],

@@ -26,7 +26,7 @@ def fwd_split(n):
 streams = [torch.cuda.Stream(dev) for _ in range(4)]
 with torch.no_grad():
     y1 = enc(x, src_key_padding_mask=m)[0]
-    for n in (1, 2, 4):
+    for n in [int(a) for a in sys.argv[1:]] or (1, 2, 4):
         for _ in range(3):
             fwd_split(n)
         torch.cuda.synchronize()
