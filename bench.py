@@ -318,6 +318,54 @@ def other_configs(dev, steps: int = 5):
     return out
 
 
+def branchformer_train_line(dev, steps: int = 3):
+    """Training step of the Branchformer SummaryMixing-lite encoder at the recipe's model dims and dropout
+    (branchformer_summarymixing.yaml: 18 layers, D=512, csgu 3072, dropout 0.1), B=8 x T=1000 per GPU, no gradient exchange:
+    forward through the layers' autograd chains (smx_conv_branch_train_fwd, the cell, merge_proj, counter-based dropout masks),
+    backward through smx_conv_branch_train_bwd / smx_summary_mixing_bwd / smx_vanilla_nn_bwd, SGD."""
+    import torch
+
+    import summarymixing_b200 as S
+
+    try:
+        torch.manual_seed(5)
+        Bb, Tb, Db = 8, 1000, 512
+        enc = S.BranchformerEncoder(18, Db, 1, 31, csgu_linear_units=3072, local_proj_hid_dim=[512], local_proj_out_dim=512,
+                                    summary_hid_dim=[512], summary_out_dim=512, mode="SummaryMixing-lite", dropout=0.1).to(dev).train()
+        opt = torch.optim.SGD(enc.parameters(), lr=0.01)
+        g = torch.Generator().manual_seed(300)
+        x = torch.randn(Bb, Tb, Db, generator=g).to(dev).to(torch.bfloat16)
+        lens = torch.randint(Tb // 2, Tb + 1, (Bb,), generator=g)
+        mask = (torch.arange(Tb)[None] < lens[:, None]).to(dev)
+        target = torch.randn(Bb, Tb, Db, generator=g).to(dev)
+
+        def step():
+            opt.zero_grad(set_to_none=True)
+            y = enc(x, src_key_padding_mask=mask)[0]
+            loss = ((y.float() - target) * mask[..., None]).pow(2).mean()
+            loss.backward()
+            opt.step()
+            return loss
+
+        l0 = float(step())
+        step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            l1 = step()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / steps
+        out = {"ms_per_step": ms, "frames_per_s": Bb * Tb / ms * 1e3, "batch": Bb, "T": Tb, "layers": 18, "dropout": 0.1,
+               "loss_first": l0, "loss_last": float(l1), "io": "bf16 activations, fp32 gradients"}
+        del enc, opt
+    except Exception as exc:  # a secondary line must never take the headline down
+        out = {"error": repr(exc)[:200]}
+    torch.cuda.empty_cache()
+    return out
+
+
 def train_line(dev, world: int, rank: int, steps: int = 3):
     """One data-parallel TRAINING step of the same encoder (forward + backward through smx_*_bwd + gradient exchange + SGD), every
     rank on its own B x T batch.  The gradient all-reduce (NCCL over NVLink, flat fp32 buckets) is launched from gradient-ready
@@ -375,7 +423,8 @@ def train_line(dev, world: int, rank: int, steps: int = 3):
     n_par = sum(p.numel() for p in params)
     del enc, opt
     torch.cuda.empty_cache()
-    return {"ms_per_step": ms_x, "frames_per_s": world * B * T / ms_x * 1e3, "io": "bf16 activations, fp32 gradients",
+    branch = branchformer_train_line(dev, steps)
+    return {"branchformer_lite_D512": branch, "ms_per_step": ms_x, "frames_per_s": world * B * T / ms_x * 1e3, "io": "bf16 activations, fp32 gradients",
             "backward": "smx_*_bwd: linears (recompute, dgrad, wgrad) as split-bf16 tcgen05 GEMMs, elementwise / reductions on CUDA cores",
             "allreduce_bytes_per_step": n_par * 4 if world > 1 else 0, "allreduce_calls_per_step": calls,
             "exchange": "flat fp32 buckets of 32 MB, all-reduce launched from gradient-ready hooks during backward (async NCCL)" if world > 1 else "none (1 GPU)",

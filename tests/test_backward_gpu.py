@@ -20,7 +20,7 @@ DEV = "cuda:0"
 
 def _close(a, b, rel, what):
     err = float((a.detach().cpu().double() - b.double()).abs().max())
-    assert err <= rel * max(1.0, float(b.abs().max())), f"{what}: max-abs {err:.3e}"
+    assert err <= rel * max(1.0, float(b.abs().max())), f"{what}: max-abs {err:.3e} (reference max {float(b.abs().max()):.3e})"
 
 
 @pytest.mark.parametrize("name", bwd_names())
@@ -162,3 +162,60 @@ def test_backward_properties_at_baseline_shape():
     assert float(dx1[~mask].abs().max()) == 0.0
     dx_solo, _ = run(x[5:6], mask[5:6], dy[5:6])
     assert float((dx_solo[0] - dx1[5]).abs().max()) <= 1e-5 * max(1.0, float(dx1[5].abs().max()))
+
+
+def test_branchformer_layer_backward_at_recipe_dims_bf16_io():
+    """One BranchformerEncoderLayer at the shipped recipe's dims (branchformer_summarymixing.yaml: D=512, csgu 3072, k=31,
+    SummaryMixing-lite), bf16 activations, dropout 0: forward and gradients against torch.autograd of the oracle fed the same
+    bf16-rounded input.  The gradients that travel between the layer's autograd nodes are bf16 like the activations (2^-8 relative
+    rounding each): fp32 parameter gradients within 1e-2 of their scale (the lite cell's weight gradient is driven by B = 2 such
+    rounded vectors), dx within 2^-6 of its scale (x feeds the residual and both branches: three rounded contributions, added and
+    rounded again by autograd)."""
+    import summarymixing_b200 as S
+
+    torch.manual_seed(31)
+    m = S.BranchformerEncoderLayer(512, 1, 31, csgu_linear_units=3072, local_proj_hid_dim=[512], local_proj_out_dim=512, summary_hid_dim=[512],
+                                   summary_out_dim=512, mode="SummaryMixing-lite", dropout=0.0)
+    m = _perturbed(m, 31)
+    with torch.no_grad():
+        m.convolution_branch.csgu.conv.conv.weight.add_(0.1 * torch.randn(m.convolution_branch.csgu.conv.conv.weight.shape))
+    m = m.to(DEV).train()
+    B, T = 2, 300
+    x = torch.randn(B, T, 512, device=DEV).bfloat16().requires_grad_(True)
+    mask = (torch.arange(T)[None] < torch.tensor([T, 171])[:, None]).to(DEV)
+    dy = torch.randn(B, T, 512, device=DEV).bfloat16()
+    y = m(x, src_key_padding_mask=mask)[0]
+    assert y.dtype == torch.bfloat16 and y.requires_grad
+    y.backward(dy)
+    sd = {k: v.detach().cpu().float().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    xo = x.detach().cpu().float().clone().requires_grad_(True)
+    yo = O.branchformer_layer(xo, sd, "", act="gelu", mode="SummaryMixing-lite", src_key_padding_mask=mask.cpu())
+    yo.backward(dy.detach().cpu().float())
+    _close(y.float(), yo.detach(), 2 ** -7, "forward (bf16)")
+    _close(x.grad.float(), xo.grad, 2 ** -6, "dx (bf16)")
+    for k, p in m.named_parameters():
+        if sd[k].grad is None:
+            continue
+        assert p.grad is not None and p.grad.dtype == torch.float32, k
+        _close(p.grad, sd[k].grad, 1e-2, k)
+
+
+def test_branchformer_backward_properties():
+    """Utterance independence and padded-frame behaviour of the Branchformer layer's backward at D=256: an utterance's dx does not
+    depend on the other utterances; with mode "SummaryMixing" a sum_mask is refused loudly (no backward through it)."""
+    import summarymixing_b200 as S
+
+    torch.manual_seed(32)
+    m = _perturbed(S.BranchformerEncoderLayer(256, 4, 31, csgu_linear_units=512, local_proj_hid_dim=[256], local_proj_out_dim=256,
+                                              summary_hid_dim=[256], summary_out_dim=256, mode="SummaryMixing", dropout=0.0), 32).to(DEV).eval()
+    B, T = 4, 200
+    x = torch.randn(B, T, 256, device=DEV)
+    mask = (torch.arange(T)[None] < torch.tensor([T, 150, 64, 199])[:, None]).to(DEV)
+    dy = torch.randn(B, T, 256, device=DEV)
+    xa = x.clone().requires_grad_(True)
+    m(xa, src_key_padding_mask=mask)[0].backward(dy)
+    xb = x[1:3].clone().requires_grad_(True)
+    m(xb, src_key_padding_mask=mask[1:3])[0].backward(dy[1:3])
+    _close(xa.grad[1:3], xb.grad.cpu(), 1e-5, "dx of a sub-batch")
+    with pytest.raises(NotImplementedError, match="sum_mask"):
+        m(x.clone().requires_grad_(True), src_mask=torch.ones(T, T, device=DEV), src_key_padding_mask=mask)
