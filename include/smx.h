@@ -340,6 +340,24 @@ SMX_API int smx_summary_mixing_train_fwd(const smx_cell_weights* w, int dtype, i
 SMX_API int smx_summary_mixing_train_bwd(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x,
                 const uint8_t* padding_mask, const smx_dropout* drop, const void* dy, void* dx, const smx_cell_grads* grads,
                 void* workspace, size_t workspace_bytes, void* stream);
+/* Dynamic Chunk Training (TransformerASR.py:85-110 builds the masks): the same training-mode calls with the chunk structure.
+ * smx_summary_mixing_masked_train_*: sum_mask is the (T,T) fp32 src_mask (summary_mixing.py:235-246, :292-294; modes
+ * "SummaryMixing" and "-fast"; NULL = the functions above; "-lite" ignores it); smx_conv_module_dcc_train_*: chunk_size > 0 selects
+ * Dynamic Chunk Convolution (Conformer.py:197-320; 0 = the functions above).  drop may be NULL.  workspace:
+ * smx_summary_mixing_masked_train_workspace_bytes() / smx_conv_module_train_workspace_bytes(). */
+SMX_API size_t smx_summary_mixing_masked_train_workspace_bytes(const smx_cell_weights* w, int dtype, int32_t B, int32_t T);
+SMX_API int smx_summary_mixing_masked_train_fwd(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x,
+                const uint8_t* padding_mask, const float* sum_mask, const smx_dropout* drop, void* y, void* workspace,
+                size_t workspace_bytes, void* stream);
+SMX_API int smx_summary_mixing_masked_train_bwd(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x,
+                const uint8_t* padding_mask, const float* sum_mask, const smx_dropout* drop, const void* dy, void* dx,
+                const smx_cell_grads* grads, void* workspace, size_t workspace_bytes, void* stream);
+SMX_API int smx_conv_module_dcc_train_fwd(const smx_convmod_weights* w, int act, int dtype, int32_t B, int32_t T, int32_t chunk_size,
+                const void* x, const uint8_t* padding_mask, const smx_dropout* drop, void* y, void* workspace, size_t workspace_bytes,
+                void* stream);
+SMX_API int smx_conv_module_dcc_train_bwd(const smx_convmod_weights* w, int act, int dtype, int32_t B, int32_t T, int32_t chunk_size,
+                const void* x, const uint8_t* padding_mask, const smx_dropout* drop, const void* dy, void* dx,
+                const smx_convmod_grads* grads, void* workspace, size_t workspace_bytes, void* stream);
 /* ConvolutionBranch (Branchformer.py:86-97: pre_channel_proj -> activation -> CSGU -> post_channel_proj; the CSGU is SpeechBrain's
  * ConvolutionalSpatialGatingUnit: split halves, LayerNorm + reflect-padded depthwise conv [+ linear] + gate activation on the second
  * half, product with the first, dropout).  x is the branch's input (the layer applies norm_conv before, Branchformer.py:292-293; no

@@ -32,13 +32,15 @@ from speechbrain.lobes.models.transformer.Conformer import (  # noqa: E402
     ConformerEncoderLayer,
     ConvolutionModule,
 )
+from speechbrain.utils.dynamic_chunk_training import DynChunkTrainConfig  # noqa: E402
 from tests import _golden as G  # noqa: E402
 
 ACTS = {"swish": Swish, "gelu": nn.GELU, "relu": nn.ReLU, "leaky_relu": nn.LeakyReLU}
 CASES = ["cell_sm_h4_swish", "cell_sm_h1_gelu", "cell_sm_h4_relu_noln_deep_nomask", "cell_reftest_sm_h4", "cell_sm_h4_gelu", "cell_sm_lite_h4_gelu", "cell_sm_lite_h1_gelu",
          "convmod_plain", "convmod_causal", "conformer_layer", "conformer_enc_sm_h4", "conformer_enc_sm_h1_gelu",
          "cell_sm_fast_h4_swish", "cell_sm_fast_h1_gelu", "conformer_enc_lite_h4", "vanilla_split1", "vanilla_split3",
-         "branchformer_enc_lite", "branchformer_enc_full"]
+         "branchformer_enc_lite", "branchformer_enc_full",
+         "cell_sm_h4_swish_summask", "cell_sm_fast_h4_swish_summask", "convmod_dcconv", "conformer_enc_fast_noln_dynchunk"]
 OUT = os.path.join(ROOT, "tests", "golden", "bwd")
 
 
@@ -53,7 +55,7 @@ def main():
         if k == "cell":
             sm = SummaryMixing(c["enc_dim"], c["nhead"], c["local_proj_hid_dim"], c["local_proj_out_dim"], c["summary_hid_dim"],
                                c["summary_out_dim"], activation=ACTS[c["act"]], mode=c["mode"], use_layernorm=c["use_layernorm"])
-            run = (lambda m, x: m(x, src_padding_mask=fx.mask)) if fx.mask is not None else (lambda m, x: m(x))
+            run = (lambda m, x: m(x, sum_mask=fx.sum_mask, src_padding_mask=fx.mask)) if fx.mask is not None else (lambda m, x: m(x))
         elif k == "vanilla":
             sm = VanillaNN(input_shape=[None, None, c["input_size"]], activation=ACTS[c["act"]], dnn_blocks=len(c["dnn_neurons"]),
                            dnn_neurons=c["dnn_neurons"], n_split=c["n_split"])
@@ -61,7 +63,8 @@ def main():
         elif k == "conv_module":
             sm = ConvolutionModule(c["input_size"], c["kernel_size"], True, ACTS[c["act"]], 0.0, causal=c["causal"],
                                    masked_false_or_true=False)
-            run = lambda m, x: m(x, fx.mask.unsqueeze(-1))  # noqa: E731
+            dcc = DynChunkTrainConfig(c["chunk_size"]) if c.get("chunk_size") else None
+            run = lambda m, x: m(x, fx.mask.unsqueeze(-1), dynchunktrain_config=dcc)  # noqa: E731
         elif k == "conformer_layer":
             sm = ConformerEncoderLayer(c["d_model"], c["d_ffn"], c["nhead"], c["kernel_size"], activation=ACTS[c["act"]],
                                        attention_type="SummaryMixing", local_proj_hid_dim=c["local_proj_hid_dim"],
@@ -78,7 +81,8 @@ def main():
                                   activation=ACTS[c["act"]], attention_type="SummaryMixing",
                                   local_proj_hid_dim=c["local_proj_hid_dim"], local_proj_out_dim=c["local_proj_out_dim"],
                                   summary_hid_dim=c["summary_hid_dim"], mode=c["mode"], use_layernorm=c["use_layernorm"])
-            run = lambda m, x: m(x, src_key_padding_mask=fx.mask)[0]  # noqa: E731
+            dce = DynChunkTrainConfig(c["chunk_size"]) if c.get("chunk_size") else None
+            run = lambda m, x: m(x, src_mask=fx.sum_mask, src_key_padding_mask=fx.mask, dynchunktrain_config=dce)[0]  # noqa: E731
         sm.load_state_dict(fx.sd)
         sm.eval()
         x = fx.x.clone().requires_grad_(True)

@@ -154,11 +154,11 @@ class FFNFunction(torch.autograd.Function):
 
 
 class ConvModuleFunction(torch.autograd.Function):
-    """y = conv_module(x) * mask: smx_conv_module_fwd / smx_conv_module_bwd.
-    params = [ln.weight, ln.bias, Wb, bb, dw.weight, dw.bias, after_ln.weight, after_ln.bias, Wo, bo]."""
+    """y = conv_module(x) * mask: smx_conv_module_fwd / smx_conv_module_bwd (chunk > 0: Dynamic Chunk Convolution,
+    smx_conv_module_dcc_train_bwd).  params = [ln.weight, ln.bias, Wb, bb, dw.weight, dw.bias, after_ln.weight, after_ln.bias, Wo, bo]."""
 
     @staticmethod
-    def forward(ctx, cw, act, drop, x, m8, *params):
+    def forward(ctx, cw, act, drop, x, m8, chunk, *params):
         dev = x.device
         xc = x.contiguous()
         B, T, _ = xc.shape
@@ -168,13 +168,13 @@ class ConvModuleFunction(torch.autograd.Function):
         with torch.cuda.device(dev):
             if drop is None:
                 ws = H.workspace(dev, lib.smx_conv_module_workspace_bytes(C.byref(cw), dt, B, T))
-                L.check(lib.smx_conv_module_fwd(C.byref(cw), act, dt, B, T, 0, xc.data_ptr(), H.p_or_none(m8), None, y.data_ptr(),
+                L.check(lib.smx_conv_module_fwd(C.byref(cw), act, dt, B, T, chunk, xc.data_ptr(), H.p_or_none(m8), None, y.data_ptr(),
                                                 ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
             else:
                 ws = H.workspace(dev, lib.smx_conv_module_train_workspace_bytes(C.byref(cw), dt, B, T))
-                L.check(lib.smx_conv_module_train_fwd(C.byref(cw), act, dt, B, T, xc.data_ptr(), H.p_or_none(m8), C.byref(drop),
-                                                      y.data_ptr(), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
-        ctx.drop = drop
+                L.check(lib.smx_conv_module_dcc_train_fwd(C.byref(cw), act, dt, B, T, chunk, xc.data_ptr(), H.p_or_none(m8), C.byref(drop),
+                                                          y.data_ptr(), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+        ctx.drop, ctx.chunk = drop, chunk
         ctx.cw, ctx.act, ctx.params = cw, act, params
         pin_params(ctx, params)
         ctx.save_for_backward(xc, m8)
@@ -199,14 +199,14 @@ class ConvModuleFunction(torch.autograd.Function):
         dt = H.dtype_code(xc)
         with torch.cuda.device(dev):
             ws = H.workspace(dev, lib.smx_conv_module_bwd_workspace_bytes(C.byref(ctx.cw), dt, B, T))
-            if ctx.drop is None:
+            if ctx.drop is None and ctx.chunk == 0:
                 L.check(lib.smx_conv_module_bwd(C.byref(ctx.cw), ctx.act, dt, B, T, xc.data_ptr(), H.p_or_none(m8), dyc.data_ptr(),
                                                 H.p_or_none(dx), C.byref(cg), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
             else:
-                L.check(lib.smx_conv_module_train_bwd(C.byref(ctx.cw), ctx.act, dt, B, T, xc.data_ptr(), H.p_or_none(m8), C.byref(ctx.drop),
-                                                      dyc.data_ptr(), H.p_or_none(dx), C.byref(cg), ws.data_ptr(), ws.numel(),
-                                                      H.stream_ptr(dev)))
-        return (None, None, None, dx, None, *_cast_out(ctx, 5, grads, ctx.params))
+                L.check(lib.smx_conv_module_dcc_train_bwd(C.byref(ctx.cw), ctx.act, dt, B, T, ctx.chunk, xc.data_ptr(), H.p_or_none(m8),
+                                                          C.byref(ctx.drop) if ctx.drop is not None else None, dyc.data_ptr(),
+                                                          H.p_or_none(dx), C.byref(cg), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+        return (None, None, None, dx, None, None, *_cast_out(ctx, 6, grads, ctx.params))
 
 
 class VanillaNNFunction(torch.autograd.Function):

@@ -159,6 +159,13 @@ _PROTOS = {
                                           C.POINTER(CellGrads), _vp, _sz, _vp]),
     "smx_dropout_keep_mask": (_i, [C.POINTER(Dropout), _i, C.c_int64, _vp, _vp]),
     "smx_dropout_apply": (_i, [C.POINTER(Dropout), _i, _i, C.c_int64, _vp, _vp, _vp]),
+    "smx_summary_mixing_masked_train_workspace_bytes": (_sz, [C.POINTER(CellWeights), _i, _i, _i]),
+    "smx_summary_mixing_masked_train_fwd": (_i, [C.POINTER(CellWeights), _i, _i, _i, _vp, _vp, _vp, C.POINTER(Dropout), _vp, _vp, _sz, _vp]),
+    "smx_summary_mixing_masked_train_bwd": (_i, [C.POINTER(CellWeights), _i, _i, _i, _vp, _vp, _vp, C.POINTER(Dropout), _vp, _vp,
+                                                 C.POINTER(CellGrads), _vp, _sz, _vp]),
+    "smx_conv_module_dcc_train_fwd": (_i, [C.POINTER(ConvModWeights), _i, _i, _i, _i, _i, _vp, _vp, C.POINTER(Dropout), _vp, _vp, _sz, _vp]),
+    "smx_conv_module_dcc_train_bwd": (_i, [C.POINTER(ConvModWeights), _i, _i, _i, _i, _i, _vp, _vp, C.POINTER(Dropout), _vp, _vp,
+                                           C.POINTER(ConvModGrads), _vp, _sz, _vp]),
     "smx_conv_branch_train_workspace_bytes": (_sz, [C.POINTER(ConvBranchWeights), _i, _i, _i]),
     "smx_conv_branch_train_fwd": (_i, [C.POINTER(ConvBranchWeights), _i, _i, _i, _vp, C.POINTER(Dropout), _vp, _vp, _sz, _vp]),
     "smx_conv_branch_train_bwd": (_i, [C.POINTER(ConvBranchWeights), _i, _i, _i, _vp, C.POINTER(Dropout), _vp, _vp,

@@ -365,7 +365,8 @@ size_t smx_conv_module_train_workspace_bytes(const smx_convmod_weights* w, int d
 }
 static int convmod_train(const smx_convmod_weights* w, int act, int dtype, int32_t B, int32_t T, const void* x, const uint8_t* padding_mask,
                          const smx_dropout* drop, const void* dy, void* dx, const smx_convmod_grads* grads, void* y, void* workspace,
-                         size_t workspace_bytes, void* stream) {
+                         size_t workspace_bytes, void* stream, int chunk = 0) {
+  if (chunk < 0) return fail(SMX_ERR_BAD_ARG, "chunk_size must be non-negative");
   SMX_TRY(check_dtype(dtype));
   if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");
   SMX_TRY(check_bt(B, T));
@@ -379,7 +380,17 @@ static int convmod_train(const smx_convmod_weights* w, int act, int dtype, int32
   if (need > workspace_bytes || !workspace) return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
   Arena a(workspace, workspace_bytes, false);
   smx_convmod_grads none{};
-  return convmod_bwd_generic(w, act, B, T, x, dtype, padding_mask, dy, dtype, dx, dtype, grads ? grads : &none, a, (cudaStream_t)stream, drop, y, dtype);
+  return convmod_bwd_generic(w, act, B, T, x, dtype, padding_mask, dy, dtype, dx, dtype, grads ? grads : &none, a, (cudaStream_t)stream, drop, y, dtype, chunk);
+}
+int smx_conv_module_dcc_train_fwd(const smx_convmod_weights* w, int act, int dtype, int32_t B, int32_t T, int32_t chunk_size, const void* x,
+                                  const uint8_t* padding_mask, const smx_dropout* drop, void* y, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!y) return fail(SMX_ERR_BAD_ARG, "y is NULL");
+  return convmod_train(w, act, dtype, B, T, x, padding_mask, drop, nullptr, nullptr, nullptr, y, workspace, workspace_bytes, stream, chunk_size);
+}
+int smx_conv_module_dcc_train_bwd(const smx_convmod_weights* w, int act, int dtype, int32_t B, int32_t T, int32_t chunk_size, const void* x,
+                                  const uint8_t* padding_mask, const smx_dropout* drop, const void* dy, void* dx, const smx_convmod_grads* grads,
+                                  void* workspace, size_t workspace_bytes, void* stream) {
+  return convmod_train(w, act, dtype, B, T, x, padding_mask, drop, dy, dx, grads, nullptr, workspace, workspace_bytes, stream, chunk_size);
 }
 int smx_conv_module_train_fwd(const smx_convmod_weights* w, int act, int dtype, int32_t B, int32_t T, const void* x, const uint8_t* padding_mask,
                               const smx_dropout* drop, void* y, void* workspace, size_t workspace_bytes, void* stream) {
@@ -448,9 +459,19 @@ size_t smx_summary_mixing_train_workspace_bytes(const smx_cell_weights* w, int d
   if (cell_bwd_generic(w, B, T, nullptr, dtype, nullptr, nullptr, dtype, (void*)(uintptr_t)256, dtype, &g, a, nullptr, &kSizingDrop) != SMX_OK) return 0;
   return a.peak;
 }
+size_t smx_summary_mixing_masked_train_workspace_bytes(const smx_cell_weights* w, int dtype, int32_t B, int32_t T) {
+  if (!w || B <= 0 || T <= 0) return 0;
+  smx_cell_grads g;
+  all_grads_wanted(g);
+  Arena a(nullptr, 0, true);
+  if (cell_bwd_generic(w, B, T, nullptr, dtype, nullptr, nullptr, dtype, (void*)(uintptr_t)256, dtype, &g, a, nullptr, &kSizingDrop, nullptr, 0,
+                       (const float*)(uintptr_t)256) != SMX_OK) return 0;
+  const size_t plain = smx_summary_mixing_train_workspace_bytes(w, dtype, B, T);
+  return a.peak > plain ? a.peak : plain;
+}
 static int cell_train(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x, const uint8_t* padding_mask,
                       const smx_dropout* drop, const void* dy, void* dx, const smx_cell_grads* grads, void* y, void* workspace,
-                      size_t workspace_bytes, void* stream) {
+                      size_t workspace_bytes, void* stream, const float* sum_mask = nullptr) {
   SMX_TRY(check_dtype(dtype));
   if (!w) return fail(SMX_ERR_BAD_ARG, "weights is NULL");
   SMX_TRY(check_bt(B, T));
@@ -459,12 +480,24 @@ static int cell_train(const smx_cell_weights* w, int dtype, int32_t B, int32_t T
   if (y) SMX_TRY(check_ptr(y, "y")); else { if (!grads) return fail(SMX_ERR_BAD_ARG, "grads is NULL"); SMX_TRY(check_ptr(dy, "dy")); }
   if (dx) SMX_TRY(check_ptr(dx, "dx"));
   SMX_TRY(check_arch());
-  const size_t need = smx_summary_mixing_train_workspace_bytes(w, dtype, B, T);
+  if (sum_mask && w->mode == SMX_MODE_LITE) sum_mask = nullptr;  // (lite ignores sum_mask, summary_mixing.py:300-324)
+  if (sum_mask) SMX_TRY(check_ptr(sum_mask, "sum_mask"));
+  const size_t need = sum_mask ? smx_summary_mixing_masked_train_workspace_bytes(w, dtype, B, T) : smx_summary_mixing_train_workspace_bytes(w, dtype, B, T);
   if (need == 0) return SMX_ERR_BAD_ARG;
   if (need > workspace_bytes || !workspace) return fail(SMX_ERR_WORKSPACE, "workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
   Arena a(workspace, workspace_bytes, false);
   smx_cell_grads none{};
-  return cell_bwd_generic(w, B, T, x, dtype, padding_mask, dy, dtype, dx, dtype, grads ? grads : &none, a, (cudaStream_t)stream, drop, y, dtype);
+  return cell_bwd_generic(w, B, T, x, dtype, padding_mask, dy, dtype, dx, dtype, grads ? grads : &none, a, (cudaStream_t)stream, drop, y, dtype, sum_mask);
+}
+int smx_summary_mixing_masked_train_fwd(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x, const uint8_t* padding_mask,
+                                        const float* sum_mask, const smx_dropout* drop, void* y, void* workspace, size_t workspace_bytes, void* stream) {
+  if (!y) return fail(SMX_ERR_BAD_ARG, "y is NULL");
+  return cell_train(w, dtype, B, T, x, padding_mask, drop, nullptr, nullptr, nullptr, y, workspace, workspace_bytes, stream, sum_mask);
+}
+int smx_summary_mixing_masked_train_bwd(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x, const uint8_t* padding_mask,
+                                        const float* sum_mask, const smx_dropout* drop, const void* dy, void* dx, const smx_cell_grads* grads,
+                                        void* workspace, size_t workspace_bytes, void* stream) {
+  return cell_train(w, dtype, B, T, x, padding_mask, drop, dy, dx, grads, nullptr, workspace, workspace_bytes, stream, sum_mask);
 }
 int smx_summary_mixing_train_fwd(const smx_cell_weights* w, int dtype, int32_t B, int32_t T, const void* x, const uint8_t* padding_mask,
                                  const smx_dropout* drop, void* y, void* workspace, size_t workspace_bytes, void* stream) {

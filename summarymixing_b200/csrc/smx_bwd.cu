@@ -537,10 +537,42 @@ int branch_bwd(const smx_linear* blocks, const smx_linear_grad* g, int n, int ac
   return SMX_OK;
 }
 
+// per-frame summaries under a (T,T) sum mask (Dynamic Chunk Training, summary_mixing.py:235-246, :292-294):
+// Sf[b] = (M @ S[b]) / rowsum(M) -- the denominator keeps padded frames, like the reference -- and the gradient
+// dS[b] = M^T @ (dSf[b] / rowsum(M)[:, None]) (dSf is scaled in place; dS has row stride ldd).  O(T^2 D) products on the CUDA-core GEMM.
+__global__ void __launch_bounds__(256) div_rows_kernel(float* v, const float* rs, int T, int D, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) v[i] = v[i] / rs[(i / D) % T];
+}
+int summask_fwd(const float* M, float* rs, const float* S, int64_t ldS, int B, int T, int Ds, float* Sf, cudaStream_t st) {
+  SMX_TRY(rowsum(M, T, T, rs, st));
+  GemmP p = bw_gemm();
+  p.A = M; p.lda = T; p.a_bs = 0;
+  p.W = S; p.w_sk = ldS; p.w_sn = 1; p.w_bs = (int64_t)T * ldS;
+  p.rowdiv = rs;
+  p.C = Sf; p.ldc = Ds; p.c_bs = (int64_t)T * Ds;
+  p.M = T; p.N = Ds; p.K = T; p.batches = B;
+  return gemm(p, st);
+}
+int summask_bwd(const float* M, const float* rs, float* dSf, int B, int T, int Ds, float* dS, int64_t ldd, cudaStream_t st) {
+  const int64_t n = (int64_t)B * T * Ds;
+  div_rows_kernel<<<ew_grid(n), 256, 0, st>>>(dSf, rs, T, Ds, n);
+  count_launch();
+  SMX_TRY(check_launch("div_rows_kernel"));
+  GemmP p = bw_gemm();
+  p.A = M; p.lda = 1; p.a_sk = T; p.a_bs = 0;   // A[m][k] = M[k][m]
+  p.W = dSf; p.w_sk = Ds; p.w_sn = 1; p.w_bs = (int64_t)T * Ds;
+  p.C = dS; p.ldc = ldd; p.c_bs = (int64_t)T * ldd;
+  p.M = T; p.N = Ds; p.K = T; p.batches = B;
+  return gemm(p, st);
+}
+
 }  // namespace
 
 int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int x_dt, const uint8_t* mask, const void* dy, int dy_dt,
-                     void* dx, int dx_dt, const smx_cell_grads* g, Arena& ws, cudaStream_t st, const smx_dropout* drop, void* y_fwd, int y_dt) {
+                     void* dx, int dx_dt, const smx_cell_grads* g, Arena& ws, cudaStream_t st, const smx_dropout* drop, void* y_fwd, int y_dt,
+                     const float* sum_mask) {
+  // sum_mask ((T,T) fp32, modes "SummaryMixing" / "-fast"; "-lite" ignores it like the reference): per-frame summaries
+  // (M @ S) / rowsum(M) instead of the utterance mean; the combiner then runs on the written-out concatenation.
   // drop (p > 0): dropout on the combiner's input cat = [local | summary] (summary_mixing.py:252, :297) -- the concatenation is
   // then written out per frame (the per-utterance bias shortcut no longer holds: every frame draws its own mask over the summary).
   // y_fwd: training-mode FORWARD only (same recomputation, result written to y_fwd, no gradients).
@@ -587,12 +619,18 @@ int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int
     BWF_BUF(dG, rows * 2 * Dl);
     BWF_BUF(dmean, (size_t)B * Dl);
     BWF_BUF(inv, (size_t)B);
-    if (dr.on || y_fwd) {
-      // written-out combiner: cat = dropout([G[:, :D_l] | mean_b]), zc = cat Wc^T + b_c
+    if (dr.on || y_fwd || sum_mask) {
+      // written-out combiner: cat = dropout([G[:, :D_l] | mean_b]) (sum_mask: [G[:, :D_l] | Sf], per-frame summaries), zc = cat Wc^T + b_c
       BWF_BUF(cat, rows * 2 * Dl);
+      float* rsm = nullptr; float* Sf = nullptr;
+      if (sum_mask) {
+        rsm = ws.f32((size_t)T); Sf = ws.f32((size_t)rows * Dl);
+        if (!rsm || !Sf) return fail(SMX_ERR_WORKSPACE, "workspace too small (cell backward, sum_mask)");
+      }
       if (!ws.dry) {
-        SMX_TRY(masked_mean(G + Dl, 2 * Dl, mask, B, T, Dl, mean, SMX_F32, st));
-        concat_bcast_kernel<<<ew_grid(rows * 2 * Dl), 256, 0, st>>>(G, 2 * Dl, mean, T, Dl, Dl, rows * 2 * Dl, cat);
+        if (sum_mask) SMX_TRY(summask_fwd(sum_mask, rsm, G + Dl, 2 * Dl, B, T, Dl, Sf, st));
+        else SMX_TRY(masked_mean(G + Dl, 2 * Dl, mask, B, T, Dl, mean, SMX_F32, st));
+        concat_bcast_kernel<<<ew_grid(rows * 2 * Dl), 256, 0, st>>>(G, 2 * Dl, sum_mask ? Sf : mean, sum_mask ? 1 : T, Dl, Dl, rows * 2 * Dl, cat);
         count_launch();
         SMX_TRY(check_launch("concat_bcast_kernel"));
         SMX_TRY(dropout_inplace(cat, rows * 2 * Dl, dr, 0, st));
@@ -616,6 +654,12 @@ int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int
         take_cols_kernel<<<ew_grid(rows * Dl), 256, 0, st>>>(dcat, 2 * Dl, Dl, rows * Dl, dG, 2 * Dl);  // dG[:, :D_l]
         count_launch();
         SMX_TRY(check_launch("take_cols_kernel"));
+        if (sum_mask) {  // dG[:, D_l:] = M^T (dcat[:, D_l:] / rowsum)
+          take_cols_kernel<<<ew_grid(rows * Dl), 256, 0, st>>>(dcat + Dl, 2 * Dl, Dl, rows * Dl, Sf, Dl);  // (Sf is dead)
+          count_launch();
+          SMX_TRY(check_launch("take_cols_kernel"));
+          SMX_TRY(summask_bwd(sum_mask, rsm, Sf, B, T, Dl, dG + Dl, 2 * Dl, st));
+        } else {
         colsum_kernel<<<dim3((Dl + 31) / 32, B), 256, 0, st>>>(dcat + Dl, 2 * Dl, rows, T, Dl, dmean);  // d mean_b = sum_t dcat[b,t,D_l:]
         count_launch();
         SMX_TRY(check_launch("colsum_kernel"));
@@ -625,6 +669,7 @@ int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int
         bcast_scale_kernel<<<ew_grid(rows * Dl), 256, 0, st>>>(dmean, inv, T, Dl, rows * Dl, dG + Dl, 2 * Dl);  // dG[:, D_l:]
         count_launch();
         SMX_TRY(check_launch("bcast_scale_kernel"));
+        }
       }
       SMX_TRY(branch_bwd(&w->global_proj, &g->global_proj, 1, act, fg, rows, mask, dG, dx, dx_dt, nullptr, dx != nullptr, ws, st));
       ws.release(m0);
@@ -724,23 +769,32 @@ int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int
     BW_RUN(layernorm(Lm, SMX_F32, Dl, w->local_norm_w, w->local_norm_b, 1e-5f, SMX_ACT_IDENTITY, Lb, SMX_F32, Dl, rows, Dl, st));
     Lmat = Lb;
   }
-  BW_BUF(mean, (size_t)B * Ds);
-  BW_RUN(masked_mean(Sm, Ds, mask, B, T, Ds, mean, SMX_F32, st));
+  // the summary: one row per utterance (the masked mean), or one per frame under a sum mask
+  const int64_t srows = sum_mask ? rows : B;
+  float* rsm = nullptr;
+  BW_BUF(mean, (size_t)srows * Ds);
+  if (sum_mask) {
+    rsm = ws.f32((size_t)T);
+    if (!rsm) return fail(SMX_ERR_WORKSPACE, "workspace too small (cell backward, sum_mask)");
+    BW_RUN(summask_fwd(sum_mask, rsm, Sm, Ds, B, T, Ds, mean, st));
+  } else {
+    BW_RUN(masked_mean(Sm, Ds, mask, B, T, Ds, mean, SMX_F32, st));
+  }
   const float* mu = mean;
   if (use_ln) {
-    BW_BUF(mub, (size_t)B * Ds);
-    BW_RUN(layernorm(mean, SMX_F32, Ds, w->summary_norm_w, w->summary_norm_b, 1e-5f, SMX_ACT_IDENTITY, mub, SMX_F32, Ds, B, Ds, st));
+    BW_BUF(mub, (size_t)srows * Ds);
+    BW_RUN(layernorm(mean, SMX_F32, Ds, w->summary_norm_w, w->summary_norm_b, 1e-5f, SMX_ACT_IDENTITY, mub, SMX_F32, Ds, srows, Ds, st));
     mu = mub;
   }
   BW_BUF(zc, rows * Dout);
   BW_BUF(dL, rows * Dl);
-  BW_BUF(dmu, (size_t)B * Ds);
+  BW_BUF(dmu, (size_t)srows * Ds);
   float* dzc = zc;
-  if (dr.on || y_fwd) {
-    // written-out combiner: cat = dropout([L | mu_b]), zc = cat Wc^T + b_c
+  if (dr.on || y_fwd || sum_mask) {
+    // written-out combiner: cat = dropout([L | mu_b]) (sum_mask: mu per frame), zc = cat Wc^T + b_c
     BW_BUF(cat, rows * (Dl + Ds));
     if (!ws.dry) {
-      concat_bcast_kernel<<<ew_grid(rows * (Dl + Ds)), 256, 0, st>>>(Lmat, Dl, mu, T, Dl, Ds, rows * (Dl + Ds), cat);
+      concat_bcast_kernel<<<ew_grid(rows * (Dl + Ds)), 256, 0, st>>>(Lmat, Dl, mu, sum_mask ? 1 : T, Dl, Ds, rows * (Dl + Ds), cat);
       count_launch();
       SMX_TRY(check_launch("concat_bcast_kernel"));
       SMX_TRY(dropout_inplace(cat, rows * (Dl + Ds), dr, 0, st));
@@ -764,9 +818,15 @@ int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int
       take_cols_kernel<<<ew_grid(rows * Dl), 256, 0, st>>>(dcat, Dl + Ds, Dl, rows * Dl, dL, Dl);
       count_launch();
       SMX_TRY(check_launch("take_cols_kernel"));
+      if (sum_mask) {  // d mu[b,t] = dcat[b,t,D_l:]
+        take_cols_kernel<<<ew_grid(rows * Ds), 256, 0, st>>>(dcat + Dl, Dl + Ds, Ds, rows * Ds, dmu, Ds);
+        count_launch();
+        SMX_TRY(check_launch("take_cols_kernel"));
+      } else {
       colsum_kernel<<<dim3((Ds + 31) / 32, B), 256, 0, st>>>(dcat + Dl, Dl + Ds, rows, T, Ds, dmu);  // d mu_b = sum_t dcat[b,t,D_l:]
       count_launch();
       SMX_TRY(check_launch("colsum_kernel"));
+      }
     }
   } else {
   BW_BUF(cbias, (size_t)B * Dout);
@@ -791,10 +851,12 @@ int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int
   }
 
   // ---- summary branch: LN_s, mean, MLP ----
-  if (use_ln) SMX_TRY(ln_bwd(mean, B, Ds, w->summary_norm_w, dmu, g->summary_norm_dw, g->summary_norm_db, ws, st));
+  if (use_ln) SMX_TRY(ln_bwd(mean, srows, Ds, w->summary_norm_w, dmu, g->summary_norm_dw, g->summary_norm_db, ws, st));
   BW_BUF(inv, (size_t)B);
   BW_BUF(dS, rows * Ds);
-  if (!ws.dry) {
+  if (sum_mask) {
+    BW_RUN(summask_bwd(sum_mask, rsm, dmu, B, T, Ds, dS, Ds, st));
+  } else if (!ws.dry) {
     inv_count_kernel<<<B, 32, 0, st>>>(mask, T, inv);
     count_launch();
     SMX_TRY(check_launch("inv_count_kernel"));
@@ -960,7 +1022,7 @@ __global__ void __launch_bounds__(256) dwconv_wgrad_win_kernel(const float* __re
 // was reflect-padded (frame -s and frame T-1+s read frames s and T-1-s: those taps' gradients land there too; T > pad).
 // din has row stride ldo.
 __global__ void __launch_bounds__(256) dwconv_bwd_data_kernel(const float* dout, const float* w, int B, int T, int C, int k, int pad,
-                                                              int reflect, float* din, int64_t ldo) {
+                                                              int reflect, float* din, int64_t ldo, int chunk = 0) {
   const int64_t n = (int64_t)B * T * C;
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) {
     const int c = (int)(i % C);
@@ -970,8 +1032,9 @@ __global__ void __launch_bounds__(256) dwconv_bwd_data_kernel(const float* dout,
     float acc = 0.0f;
     for (int j = 0; j < k; ++j) {
       const float wj = w[(int64_t)c * k + j];
-      const int u = t - j + pad;
-      if (u >= 0 && u < T) acc = fmaf(wj, base[(int64_t)u * C], acc);
+      const int u = t - j + pad;   // the output frame whose tap j read input frame t
+      // chunk > 0 (Dynamic Chunk Convolution): output u sees input frames below the end of ITS chunk only, i.e. t's chunk <= u's chunk
+      if (u >= 0 && u < T && (chunk <= 0 || u >= (t / chunk) * chunk)) acc = fmaf(wj, base[(int64_t)u * C], acc);
       if (reflect) {
         const int ul = pad - j - t;                   // output frame whose tap j read padded frame -t
         if (t >= 1 && ul >= 0 && ul < T) acc = fmaf(wj, base[(int64_t)ul * C], acc);
@@ -985,7 +1048,7 @@ __global__ void __launch_bounds__(256) dwconv_bwd_data_kernel(const float* dout,
 // depthwise conv, weight gradient partials: P[slice][c][j] = sum over the slice's utterances and all t of
 // dout[b,t,c] * in[b, t + j - pad, c].  grid (ceil(C/32), k, slices), block 32 x 8 (channels x frame lanes).
 __global__ void __launch_bounds__(256) dwconv_bwd_w_kernel(const float* dout, const float* in, int B, int T, int C, int k, int pad,
-                                                           int utt_per_slice, float* P, int reflect = 0) {
+                                                           int utt_per_slice, float* P, int reflect = 0, int chunk = 0) {
   __shared__ float red[8][33];
   const int cx = threadIdx.x % 32, ry = threadIdx.x / 32;
   const int c = blockIdx.x * 32 + cx, j = blockIdx.y;
@@ -999,7 +1062,7 @@ __global__ void __launch_bounds__(256) dwconv_bwd_w_kernel(const float* dout, co
       for (int t = ry; t < T; t += 8) {
         int u = t + j - pad;
         if (reflect) u = u < 0 ? -u : (u >= T ? 2 * (T - 1) - u : u);
-        if (u >= 0 && u < T) acc = fmaf(dob[(int64_t)t * C], inb[(int64_t)u * C], acc);
+        if (u >= 0 && u < T && (chunk <= 0 || u < (t / chunk + 1) * chunk)) acc = fmaf(dob[(int64_t)t * C], inb[(int64_t)u * C], acc);
       }
     }
   }
@@ -1018,9 +1081,9 @@ __global__ void __launch_bounds__(256) dwconv_bwd_w_kernel(const float* dout, co
 // din (row stride ldo) = gradient of the depthwise conv input; dw (C,1,k) = its weight gradient.  Register-window kernels for the
 // common kernel sizes (k = 31, 15), the per-element kernels otherwise.
 int dwconv_bwd_data(const float* dout, const float* w, int B, int T, int C, int k, int pad, int reflect, float* din, int64_t ldo,
-                    cudaStream_t st) {
+                    cudaStream_t st, int chunk = 0) {
   int status = SMX_OK;
-  if (dwconv_window(dout, C, w, nullptr, B, T, C, k, k - 1 - pad, 0, 1, din, ldo, st, &status)) {
+  if (chunk <= 0 && dwconv_window(dout, C, w, nullptr, B, T, C, k, k - 1 - pad, 0, 1, din, ldo, st, &status)) {
     SMX_TRY(status);
     if (reflect) {
       const int nb = T <= 2 * pad + 2 ? T : 2 * pad + 2;
@@ -1030,13 +1093,14 @@ int dwconv_bwd_data(const float* dout, const float* w, int B, int T, int C, int 
     }
     return SMX_OK;
   }
-  dwconv_bwd_data_kernel<<<ew_grid((int64_t)B * T * C), 256, 0, st>>>(dout, w, B, T, C, k, pad, reflect, din, ldo);
+  dwconv_bwd_data_kernel<<<ew_grid((int64_t)B * T * C), 256, 0, st>>>(dout, w, B, T, C, k, pad, reflect, din, ldo, chunk);
   count_launch();
   return check_launch("dwconv_bwd_data_kernel");
 }
-int dwconv_wgrad(const float* dout, const float* in, int B, int T, int C, int k, int pad, int reflect, float* dw, Arena& ws, cudaStream_t st) {
+int dwconv_wgrad(const float* dout, const float* in, int B, int T, int C, int k, int pad, int reflect, float* dw, Arena& ws, cudaStream_t st,
+                 int chunk = 0) {
   const size_t m0 = ws.mark();
-  if (k == 31 || k == 15) {
+  if (chunk <= 0 && (k == 31 || k == 15)) {
     const int spans = (T + 511) / 512, ns = B * spans, ncg = (C + 31) / 32;
     float* P = ws.f32((size_t)ns * C * k);
     if (!P) return fail(SMX_ERR_WORKSPACE, "workspace too small (depthwise weight gradient)");
@@ -1052,7 +1116,7 @@ int dwconv_wgrad(const float* dout, const float* in, int B, int T, int C, int k,
     float* P = ws.f32((size_t)ns * C * k);
     if (!P) return fail(SMX_ERR_WORKSPACE, "workspace too small (depthwise weight gradient)");
     if (!ws.dry) {
-      dwconv_bwd_w_kernel<<<dim3((C + 31) / 32, k, ns), 256, 0, st>>>(dout, in, B, T, C, k, pad, ups, P, reflect);
+      dwconv_bwd_w_kernel<<<dim3((C + 31) / 32, k, ns), 256, 0, st>>>(dout, in, B, T, C, k, pad, ups, P, reflect, chunk);
       count_launch();
       SMX_TRY(check_launch("dwconv_bwd_w_kernel"));
       SMX_TRY(sum_slices(P, ns, C, k, dw, k, st));
@@ -1195,7 +1259,8 @@ int ffn_bwd_generic(const smx_ffn_weights* w, int act, int64_t rows, const void*
 // y = (Linear(act(LN_after(dwconv(GLU(pointwise(LN(x))))))) ) * mask                        Conformer.py:322-338
 int convmod_bwd_generic(const smx_convmod_weights* w, int act, int B, int T, const void* x, int x_dt, const uint8_t* mask, const void* dy,
                         int dy_dt, void* dx, int dx_dt, const smx_convmod_grads* g, Arena& ws, cudaStream_t st, const smx_dropout* drop,
-                        void* y_fwd, int y_dt) {
+                        void* y_fwd, int y_dt, int chunk) {
+  // chunk > 0: Dynamic Chunk Convolution (Conformer.py:197-320): a frame sees the past and the frames of its own chunk only.
   // drop (p > 0): site 0 = the nn.Dropout that ends after_conv, before the padding mask (Conformer.py:163, :334-337).
   // y_fwd: training-mode FORWARD only.
   const Drop dr = make_drop(drop);
@@ -1205,6 +1270,7 @@ int convmod_bwd_generic(const smx_convmod_weights* w, int act, int B, int T, con
     return fail(SMX_ERR_BAD_ARG, "conv module backward: inconsistent dims");
   if (rows > 0x7fffffff) return fail(SMX_ERR_UNSUPPORTED, "conv module backward: more than 2^31 frames");
   const int pad = w->causal ? (k - 1) : (k - 1) / 2;
+  if (chunk > 0 && w->causal) return fail(SMX_ERR_BAD_ARG, "Chunked convolution not supported with causal padding");
   const size_t m0 = ws.mark();
   BwScratch bw_scratch(ws, rows, 2 * D);
   const float* x32 = (const float*)x;
@@ -1221,7 +1287,7 @@ int convmod_bwd_generic(const smx_convmod_weights* w, int act, int B, int T, con
   BW_BUF(gl, rows * D);
   BW_RUN(glu(p, rows, D, gl, st));
   BW_BUF(c, rows * D);
-  BW_RUN(dwconv(gl, D, w->dw_w, w->dw_b, B, T, D, k, w->causal ? SMX_CONV_CAUSAL : SMX_CONV_SAME_ZERO, 0, c, D, st));
+  BW_RUN(dwconv(gl, D, w->dw_w, w->dw_b, B, T, D, k, chunk > 0 ? SMX_CONV_CHUNKED : (w->causal ? SMX_CONV_CAUSAL : SMX_CONV_SAME_ZERO), chunk, c, D, st));
   BW_BUF(cn, rows * D);
   BW_RUN(layernorm(c, SMX_F32, D, w->after_ln_w, w->after_ln_b, 1e-5f, SMX_ACT_IDENTITY, cn, SMX_F32, D, rows, D, st));
   BW_BUF(a, rows * D);
@@ -1246,9 +1312,9 @@ int convmod_bwd_generic(const smx_convmod_weights* w, int act, int B, int T, con
   SMX_TRY(ln_bwd(c, rows, D, w->after_ln_w, da, g->after_ln_dw, g->after_ln_db, ws, st));
   float* dc = da;
   if (g->dw_db) SMX_TRY(colsum_all(dc, D, rows, D, g->dw_db, ws, st));
-  if (g->dw_dw) SMX_TRY(dwconv_wgrad(dc, gl, B, T, D, k, pad, 0, g->dw_dw, ws, st));
+  if (g->dw_dw) SMX_TRY(dwconv_wgrad(dc, gl, B, T, D, k, pad, 0, g->dw_dw, ws, st, chunk));
   float* dgl = dout;  // dout is dead
-  BW_RUN(dwconv_bwd_data(dc, w->dw_w, B, T, D, k, pad, 0, dgl, D, st));
+  BW_RUN(dwconv_bwd_data(dc, w->dw_w, B, T, D, k, pad, 0, dgl, D, st, chunk));
   BW_BUF(dp, rows * 2 * D);
   BW_LAUNCH("glu_bwd_kernel", glu_bwd_kernel<<<ew_grid(rows * D), 256, 0, st>>>(p, dgl, rows, D, dp));
   if (g->bottleneck.dw) SMX_TRY(lin_wgrad(w->bottleneck, dp, 2 * D, xn, D, rows, g->bottleneck.dw, 0, 0, ws, st));

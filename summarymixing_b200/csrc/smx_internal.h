@@ -112,7 +112,8 @@ int cell_generic(const smx_cell_weights* w, int B, int T, const void* x, int x_d
 // backward of the cell, mode "SummaryMixing" (smx_bwd.cu); recomputes the forward intermediates from x
 int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int x_dt, const uint8_t* mask, const void* dy, int dy_dt,
                      void* dx, int dx_dt, const smx_cell_grads* g, Arena& ws, cudaStream_t st, const smx_dropout* drop = nullptr,
-                     void* y_fwd = nullptr, int y_dt = 0);  // drop: training-mode dropout; y_fwd: forward only (smx_*_train_fwd)
+                     void* y_fwd = nullptr, int y_dt = 0,   // drop: training-mode dropout; y_fwd: forward only (smx_*_train_fwd)
+                     const float* sum_mask = nullptr);      // (T,T) fp32: Dynamic Chunk Training (per-frame summaries)
 int vanilla_bwd_generic(const smx_linear* blocks, int n, int act, int64_t rows, const void* x, int x_dt, const void* dy, int dy_dt,
                         void* dx, int dx_dt, const smx_linear_grad* g, Arena& ws, cudaStream_t st);
 int layernorm_bwd_generic(const void* x, int x_dt, int64_t rows, int D, const float* w, float eps, const void* dy, int dy_dt, void* dx,
@@ -126,7 +127,7 @@ int convbranch_bwd_generic(const smx_convbranch_weights* w, int B, int T, const 
 int dropout_apply(const smx_dropout* drop, int site, int dt, int64_t n, const void* x, void* y, cudaStream_t st);
 int convmod_bwd_generic(const smx_convmod_weights* w, int act, int B, int T, const void* x, int x_dt, const uint8_t* mask, const void* dy,
                         int dy_dt, void* dx, int dx_dt, const smx_convmod_grads* g, Arena& ws, cudaStream_t st,
-                        const smx_dropout* drop = nullptr, void* y_fwd = nullptr, int y_dt = 0);
+                        const smx_dropout* drop = nullptr, void* y_fwd = nullptr, int y_dt = 0, int chunk = 0);
 int dropout_keep_mask(const smx_dropout* drop, int site, int64_t n, uint8_t* keep, cudaStream_t st);
 int ffn_generic(const smx_ffn_weights* w, int act, int64_t rows, const void* x, int x_dt, const float* oln_w,
                 const float* oln_b, float oln_eps, void* y, int y_dt, Arena& ws, cudaStream_t st);

@@ -222,9 +222,7 @@ class BranchformerEncoderLayer(nn.Module):
             self.fill(lw, self._wv, dev)
             self._wv.struct = lw
         if A.wants_grad(self, x):
-            if smask is not None and self.mode != "SummaryMixing-lite":
-                raise NotImplementedError("summarymixing_b200: backward with sum_mask is not implemented")
-            return self._forward_autograd(xc, mask), None
+            return self._forward_autograd(xc, mask, smask), None
         H.check_grad_mode(self)
         y = torch.empty_like(xc)
         lib = L.lib()
@@ -238,12 +236,12 @@ class BranchformerEncoderLayer(nn.Module):
         return y, None
 
 
-def _branchformer_layer_forward_autograd(self, x, mask):
+def _branchformer_layer_forward_autograd(self, x, mask, smask=None):
     """The layer as a chain of autograd nodes (Branchformer.py:262-334): norm_mhsa -> cell -> dropout | norm_conv -> convolution
     branch -> dropout | merge_proj(cat) -> dropout -> + x.  In training mode the three nn.Dropout calls of the layer use one
     smx_dropout (sites 1, 2, 3: counter-based masks, regenerated by the backward) and the CSGU's dropout another (site 0)."""
     drop = A.new_dropout(self, self.dropout.p)
-    x1 = self.mha_layer(self.norm_mhsa(x), src_padding_mask=mask)                       # :317-322
+    x1 = self.mha_layer(self.norm_mhsa(x), sum_mask=smask, src_padding_mask=mask)       # :317-322
     x1 = A.dropout(drop, 1, x1)                                                          # :334
     x2 = self.convolution_branch.run(self._wv.struct.branch, self.norm_conv(x))          # :292-293 (no mask, :276)
     x2 = A.dropout(drop, 2, x2)                                                          # :294

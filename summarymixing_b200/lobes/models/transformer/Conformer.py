@@ -104,10 +104,7 @@ class ConvolutionModule(nn.Module):
         """x: (B,T,D); mask: (B,T,1) or (B,T) in the convention selected by ``masked_false_or_true``."""
         H.require_cuda(x, "ConvolutionModule")
         grad = A.wants_grad(self, x)
-        if grad:
-            if _chunk_size(dynchunktrain_config) > 0:
-                raise NotImplementedError("summarymixing_b200: backward of the Dynamic Chunk Convolution is not implemented")
-        else:
+        if not grad:
             H.check_grad_mode(self)
         B, T, D = x.shape
         dev = x.device
@@ -123,7 +120,7 @@ class ConvolutionModule(nn.Module):
             self._wv.struct = cw
         if grad:
             return A.ConvModuleFunction.apply(self._wv.struct, self._act_code, A.new_dropout(self, self.after_conv[3].p), xc, m8,
-                                              *self.grad_params())
+                                              _chunk_size(dynchunktrain_config), *self.grad_params())
         y = torch.empty_like(xc)
         lib = L.lib()
         dt = H.dtype_code(xc)
@@ -246,9 +243,7 @@ class ConformerEncoderLayer(nn.Module):
             self.fill(lw, self._wv, dev)
             self._wv.struct = lw
         if A.wants_grad(self, x):
-            if smask is not None or _chunk_size(dynchunktrain_config) > 0:
-                raise NotImplementedError("summarymixing_b200: backward with sum_mask / dynamic chunk training is not implemented")
-            return self._forward_autograd(xc, mask), None
+            return self._forward_autograd(xc, mask, smask, dynchunktrain_config), None
         H.check_grad_mode(self)
         y = torch.empty_like(xc)
         lib = L.lib()
@@ -267,7 +262,7 @@ def _ffn_params(seq: nn.Sequential):
     return [ln.weight, ln.bias, pw.ffn[0].weight, pw.ffn[0].bias, pw.ffn[3].weight, pw.ffn[3].bias]
 
 
-def _layer_forward_autograd(self, x, mask):
+def _layer_forward_autograd(self, x, mask, smask=None, dynchunktrain_config=None):
     """The layer as a chain of autograd nodes, one per libsmx module call (Conformer.py:518-547):
     FFN half-step -> norm1 -> cell + skip -> conv module + skip -> FFN half-step + norm2.  In training mode every node
     applies its dropout sites (FFN: inside PositionalwiseFeedForward and after it; cell: on the concatenation; conv module: its
@@ -277,8 +272,8 @@ def _layer_forward_autograd(self, x, mask):
     d2 = A.new_dropout(self, A.same_p(self.ffn_module2[1].ffn[2].p, self.ffn_module2[2].p))
     x1 = A.FFNFunction.apply(lw.ffn1, self._act_code, None, d1, x, *_ffn_params(self.ffn_module1))
     n1 = A.LayerNormFunction.apply(x1, self.norm1.norm.weight, self.norm1.norm.bias, self.norm1.eps)
-    x2 = self.mha_layer(n1, src_padding_mask=mask) + x1
-    x3 = x2 + self.convolution_module(x2, mask)
+    x2 = self.mha_layer(n1, sum_mask=smask, src_padding_mask=mask) + x1            # (Dynamic Chunk Training: src_mask, :522-527)
+    x3 = x2 + self.convolution_module(x2, mask, dynchunktrain_config=dynchunktrain_config)   # (:543-545)
     out_norm = (lw.norm2_w, lw.norm2_b, float(self.norm2.eps))
     return A.FFNFunction.apply(lw.ffn2, self._act_code, out_norm, d2, x3, *_ffn_params(self.ffn_module2),
                                self.norm2.norm.weight, self.norm2.norm.bias)

@@ -126,8 +126,8 @@ class SummaryMixing(nn.Module):
         """x: (B,T,enc_dim); sum_mask: (T,T) or None; src_padding_mask: (B,T), 1/True = valid frame.
         Returns (B,T,summary_out_dim) in x's dtype (lite: a stride-0 expand over T, as the reference, :322).
 
-        Differentiable (smx_summary_mixing_bwd) for mode "SummaryMixing" without sum_mask when x requires grad, or in
-        training mode with global_dropout == 0; everything else is the inference path."""
+        Differentiable (smx_summary_mixing_bwd and its training-mode / sum_mask forms) for modes "SummaryMixing", "-fast" and
+        "-lite" when x requires grad or in training mode (dropout on the concatenation applied); "-expdecay" is inference only."""
         H.require_cuda(x, "SummaryMixing")
         if x.dim() != 3 or x.shape[-1] != self.enc_dim:
             raise RuntimeError(f"SummaryMixing expects (B,T,{self.enc_dim}), got {tuple(x.shape)}")
@@ -137,14 +137,14 @@ class SummaryMixing(nn.Module):
         smask = H.sum_mask_f32(sum_mask, T, dev)
         if torch.is_grad_enabled() and (x.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
             lite = self.mode == "SummaryMixing-lite"  # (lite ignores sum_mask, summary_mixing.py:300-324)
-            if not (lite or (self.mode in ("SummaryMixing", "SummaryMixing-fast") and smask is None)):
+            if not (lite or self.mode in ("SummaryMixing", "SummaryMixing-fast")):
                 raise NotImplementedError(
-                    "summarymixing_b200: backward is implemented for modes 'SummaryMixing', 'SummaryMixing-fast' (both without "
-                    "sum_mask) and 'SummaryMixing-lite' only; wrap other configurations in torch.no_grad()")
+                    "summarymixing_b200: backward is implemented for modes 'SummaryMixing', 'SummaryMixing-fast' and "
+                    "'SummaryMixing-lite' only; wrap other configurations in torch.no_grad()")
             from .. import _autograd as A
 
             drop = None if lite else A.new_dropout(self, self.dropout.p)  # (lite has no dropout, summary_mixing.py:300-324)
-            y = _CellFunction.apply(self, x, mask, drop, *self.grad_params())
+            y = _CellFunction.apply(self, x, mask, None if lite else smask, drop, *self.grad_params())
             return y.unsqueeze(1).expand(-1, T, -1) if lite else y
         H.check_grad_mode(self)
         return self._forward_impl(x, mask, smask)
@@ -186,8 +186,8 @@ class SummaryMixing(nn.Module):
             return y.unsqueeze(1).expand(-1, T, -1)
         return y
 
-    def _train_forward_impl(self, x, mask, drop):
-        """Training-mode forward with dropout on the concatenation: smx_summary_mixing_train_fwd."""
+    def _train_forward_impl(self, x, mask, drop, smask=None):
+        """Training-mode forward with dropout on the concatenation: smx_summary_mixing_train_fwd (sum_mask: the masked form)."""
         B, T, _ = x.shape
         dev = x.device
         xc = x.contiguous()
@@ -196,12 +196,17 @@ class SummaryMixing(nn.Module):
         lib = L.lib()
         dt = H.dtype_code(xc)
         with torch.cuda.device(dev):
-            ws = H.workspace(dev, lib.smx_summary_mixing_train_workspace_bytes(cw, dt, B, T))
-            L.check(lib.smx_summary_mixing_train_fwd(cw, dt, B, T, xc.data_ptr(), H.p_or_none(mask), C.byref(drop), y.data_ptr(),
-                                                     ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+            if smask is None:
+                ws = H.workspace(dev, lib.smx_summary_mixing_train_workspace_bytes(cw, dt, B, T))
+                L.check(lib.smx_summary_mixing_train_fwd(cw, dt, B, T, xc.data_ptr(), H.p_or_none(mask), C.byref(drop), y.data_ptr(),
+                                                         ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+            else:
+                ws = H.workspace(dev, lib.smx_summary_mixing_masked_train_workspace_bytes(cw, dt, B, T))
+                L.check(lib.smx_summary_mixing_masked_train_fwd(cw, dt, B, T, xc.data_ptr(), H.p_or_none(mask), smask.data_ptr(), C.byref(drop),
+                                                                y.data_ptr(), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
         return y
 
-    def _backward_impl(self, x, mask, dy, want_dx, cw=None, drop=None):
+    def _backward_impl(self, x, mask, dy, want_dx, cw=None, drop=None, smask=None):
         """(dx or None, [fp32 gradient per grad_params() entry]) through smx_summary_mixing_bwd."""
         B, T, _ = x.shape
         dev = x.device
@@ -235,7 +240,12 @@ class SummaryMixing(nn.Module):
         lib = L.lib()
         dt = H.dtype_code(xc)
         with torch.cuda.device(dev):
-            if drop is None:
+            if smask is not None:
+                ws = H.workspace(dev, lib.smx_summary_mixing_masked_train_workspace_bytes(cw, dt, B, T))
+                L.check(lib.smx_summary_mixing_masked_train_bwd(cw, dt, B, T, xc.data_ptr(), H.p_or_none(mask), smask.data_ptr(),
+                                                                C.byref(drop) if drop is not None else None, dyc.data_ptr(), H.p_or_none(dx),
+                                                                C.byref(cg), ws.data_ptr(), ws.numel(), H.stream_ptr(dev)))
+            elif drop is None:
                 nbytes = lib.smx_summary_mixing_bwd_workspace_bytes(cw, dt, B, T)
                 ws = H.workspace(dev, nbytes)
                 L.check(lib.smx_summary_mixing_bwd(cw, dt, B, T, xc.data_ptr(), H.p_or_none(mask), dyc.data_ptr(),
@@ -252,13 +262,13 @@ class _CellFunction(torch.autograd.Function):
     the intermediates from x, so only x and the mask are kept)."""
 
     @staticmethod
-    def forward(ctx, module, x, mask, drop, *params):
+    def forward(ctx, module, x, mask, smask, drop, *params):
         from .. import _autograd as A
 
         ctx.module = module
         ctx.drop = drop
-        ctx.save_for_backward(x, mask)
-        y = module._forward_impl(x, mask, None, expand_lite=False) if drop is None else module._train_forward_impl(x, mask, drop)
+        ctx.save_for_backward(x, mask, smask)
+        y = module._forward_impl(x, mask, smask, expand_lite=False) if drop is None else module._train_forward_impl(x, mask, drop, smask)
         ctx.cw = module._wv.struct  # the weight struct of THIS forward (with the tensors it points into)
         A.pin_params(ctx, module.params())
         return y
@@ -267,10 +277,10 @@ class _CellFunction(torch.autograd.Function):
     def backward(ctx, dy):
         from .. import _autograd as A
 
-        x, mask = ctx.saved_tensors
+        x, mask, smask = ctx.saved_tensors
         A.check_params(ctx)
         module = ctx.module
-        dx, grads = module._backward_impl(x, mask, dy, ctx.needs_input_grad[1], cw=ctx.cw, drop=ctx.drop)
+        dx, grads = module._backward_impl(x, mask, dy, ctx.needs_input_grad[1], cw=ctx.cw, drop=ctx.drop, smask=smask)
         plist = module.grad_params()
-        out = [g.to(p.dtype) if ctx.needs_input_grad[4 + i] else None for i, (g, p) in enumerate(zip(grads, plist))]
-        return (None, dx, None, None, *out)
+        out = [g.to(p.dtype) if ctx.needs_input_grad[5 + i] else None for i, (g, p) in enumerate(zip(grads, plist))]
+        return (None, dx, None, None, None, *out)

@@ -127,9 +127,8 @@ def test_backward_unsupported_configurations_fail_loudly():
     x = torch.randn(2, 16, 64, device=DEV, requires_grad=True)
     with pytest.raises(NotImplementedError, match="backward"):
         S.SummaryMixing(64, 4, [64], 64, [64], 64, mode="SummaryMixing-expdecay").to(DEV).eval()(x)
-    with pytest.raises(NotImplementedError, match="backward"):
-        S.SummaryMixing(64, 4, [64], 64, [64], 64).to(DEV).eval()(x, sum_mask=torch.ones(16, 16, device=DEV))
-    # (training-mode dropout is implemented: tests/test_dropout_gpu.py)
+    # (training-mode dropout and the sum_mask / Dynamic Chunk Convolution backward are implemented: tests/test_dropout_gpu.py and the
+    #  *_summask / convmod_dcconv / *_dynchunk gradient fixtures above)
 
 
 def test_backward_properties_at_baseline_shape():
@@ -200,9 +199,9 @@ def test_branchformer_layer_backward_at_recipe_dims_bf16_io():
         _close(p.grad, sd[k].grad, 1e-2, k)
 
 
-def test_branchformer_backward_properties():
+def test_branchformer_backward_properties_and_sum_mask():
     """Utterance independence and padded-frame behaviour of the Branchformer layer's backward at D=256: an utterance's dx does not
-    depend on the other utterances; with mode "SummaryMixing" a sum_mask is refused loudly (no backward through it)."""
+    depend on the other utterances; with a (chunked) sum_mask forward and gradients follow the oracle."""
     import summarymixing_b200 as S
 
     torch.manual_seed(32)
@@ -217,5 +216,18 @@ def test_branchformer_backward_properties():
     xb = x[1:3].clone().requires_grad_(True)
     m(xb, src_key_padding_mask=mask[1:3])[0].backward(dy[1:3])
     _close(xa.grad[1:3], xb.grad.cpu(), 1e-5, "dx of a sub-batch")
-    with pytest.raises(NotImplementedError, match="sum_mask"):
-        m(x.clone().requires_grad_(True), src_mask=torch.ones(T, T, device=DEV), src_key_padding_mask=mask)
+    chunk = 32
+    smask = (torch.arange(T)[None, :] // chunk <= torch.arange(T)[:, None] // chunk).float()   # a frame sees its own and earlier chunks
+    m.zero_grad(set_to_none=True)   # (the two backward calls above accumulated into the parameters' .grad)
+    xc = x.clone().requires_grad_(True)
+    y = m(xc, src_mask=smask.to(DEV), src_key_padding_mask=mask)[0]
+    y.backward(dy)
+    sd = {k: v.detach().cpu().float().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    xo = x.detach().cpu().clone().requires_grad_(True)
+    yo = O.branchformer_layer(xo, sd, "", act="gelu", mode="SummaryMixing", src_mask=smask, src_key_padding_mask=mask.cpu())
+    yo.backward(dy.cpu())
+    _close(y, yo.detach(), 3e-4, "forward with sum_mask")
+    _close(xc.grad, xo.grad, 3e-4, "dx with sum_mask")
+    for k, p in m.named_parameters():
+        if sd[k].grad is not None:
+            _close(p.grad, sd[k].grad, 3e-4, k)

@@ -247,3 +247,32 @@ def test_convolution_branch_standalone_and_use_linear_after_conv():
     # T too short for the reflect padding: a loud error like torch's
     with pytest.raises(Exception):
         m(torch.randn(1, 7, 64, device=DEV))
+
+
+@pytest.mark.parametrize("mode", ["SummaryMixing", "SummaryMixing-fast"])
+def test_cell_dropout_with_sum_mask(mode):
+    """Dynamic Chunk Training with dropout: per-frame summaries under a chunked sum_mask, dropout on the written-out concatenation
+    (smx_summary_mixing_masked_train_fwd / _bwd) against the oracle under the same mask."""
+    torch.manual_seed(13)
+    p = 0.2
+    m = _perturbed(S.SummaryMixing(64, 4, [64], 64, [64], 64, activation=nn.GELU, global_dropout=p, mode=mode, use_layernorm=(mode == "SummaryMixing")), 13)
+    m = m.to(DEV).train()
+    B, T, chunk = 3, 77, 16
+    x = torch.randn(B, T, 64, device=DEV, requires_grad=True)
+    mask = (torch.arange(T)[None] < torch.tensor([T, 40, 21])[:, None]).to(DEV)
+    smask = (torch.arange(T)[None, :] // chunk <= torch.arange(T)[:, None] // chunk).float()
+    dy = torch.randn(B, T, 64, device=DEV)
+    (s0,) = _seeds(47, 1)
+    y = m(x, sum_mask=smask.to(DEV), src_padding_mask=mask)
+    y.backward(dy)
+    hook = OD.Hook(p, {"cat": (s0, 0)})
+    y_or, dx_or, g_or = _oracle(lambda xo, sd: O.summary_mixing(xo, sd, mode=mode, act="gelu", use_layernorm=(mode == "SummaryMixing"),
+                                                                src_padding_mask=mask.cpu(), sum_mask=smask, drop=hook), m, x, dy)
+    assert hook.used == ["cat"]
+    _close(y, y_or, 1e-4, "forward")
+    _close(x.grad, dx_or, 1e-4, "dx")
+    for k, prm in m.named_parameters():
+        if g_or[k] is None:
+            assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, k
+            continue
+        _close(prm.grad, g_or[k], 1e-4, k)
