@@ -40,7 +40,8 @@ CASES = ["cell_sm_h4_swish", "cell_sm_h1_gelu", "cell_sm_h4_relu_noln_deep_nomas
          "convmod_plain", "convmod_causal", "conformer_layer", "conformer_enc_sm_h4", "conformer_enc_sm_h1_gelu",
          "cell_sm_fast_h4_swish", "cell_sm_fast_h1_gelu", "conformer_enc_lite_h4", "vanilla_split1", "vanilla_split3",
          "branchformer_enc_lite", "branchformer_enc_full",
-         "cell_sm_h4_swish_summask", "cell_sm_fast_h4_swish_summask", "convmod_dcconv", "conformer_enc_fast_noln_dynchunk"]
+         "cell_sm_h4_swish_summask", "cell_sm_fast_h4_swish_summask", "convmod_dcconv", "conformer_enc_fast_noln_dynchunk",
+         "cell_sm_expdecay_h4_gelu", "cell_sm_expdecay_h1_gelu"]
 OUT = os.path.join(ROOT, "tests", "golden", "bwd")
 
 

@@ -579,8 +579,8 @@ int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int
   const Drop dr = make_drop(drop);
   if ((dr.on || y_fwd) && w->mode == SMX_MODE_LITE && y_fwd)
     return fail(SMX_ERR_UNSUPPORTED, "cell training forward: mode 'SummaryMixing-lite' has no dropout (use smx_summary_mixing_fwd)");
-  if (w->mode != SMX_MODE_FULL && w->mode != SMX_MODE_LITE && w->mode != SMX_MODE_FAST)
-    return fail(SMX_ERR_UNSUPPORTED, "smx_summary_mixing_bwd does not handle mode %d ('SummaryMixing-expdecay')", w->mode);
+  if (w->mode != SMX_MODE_FULL && w->mode != SMX_MODE_LITE && w->mode != SMX_MODE_FAST && w->mode != SMX_MODE_EXPDECAY)
+    return fail(SMX_ERR_UNSUPPORTED, "smx_summary_mixing_bwd: unknown mode %d", w->mode);
   const int64_t rows = (int64_t)B * T;
   if (rows > 0x7fffffff) return fail(SMX_ERR_UNSUPPORTED, "cell backward: more than 2^31 frames");
   int maxdim = w->enc_dim;
@@ -751,6 +751,13 @@ int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int
 #define BW_RUN(expr) do { if (!ws.dry) SMX_TRY(expr); } while (0)
 #define BW_BUF(name, n) float* name = ws.f32((size_t)(n)); if (!name) return fail(SMX_ERR_WORKSPACE, "workspace too small (cell backward)")
 
+  // "SummaryMixing-expdecay" (summary_mixing.py:223-224): the sum mask is the Laplace-shaped weight matrix decay^|t - t'| (times the
+  // caller's binary mask, if any); decay_constant is not trainable (requires_grad=False, :159-161), so this is the sum_mask path
+  if (w->mode == SMX_MODE_EXPDECAY) {
+    BW_BUF(lap, (size_t)T * T);
+    BW_RUN(laplace(w->decay_constant, sum_mask, T, lap, st));
+    sum_mask = lap;
+  }
   // ---- forward recomputation ----
   const float* x32 = (const float*)x;
   if (x_dt != SMX_F32) {

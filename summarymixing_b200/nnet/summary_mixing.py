@@ -126,8 +126,8 @@ class SummaryMixing(nn.Module):
         """x: (B,T,enc_dim); sum_mask: (T,T) or None; src_padding_mask: (B,T), 1/True = valid frame.
         Returns (B,T,summary_out_dim) in x's dtype (lite: a stride-0 expand over T, as the reference, :322).
 
-        Differentiable (smx_summary_mixing_bwd and its training-mode / sum_mask forms) for modes "SummaryMixing", "-fast" and
-        "-lite" when x requires grad or in training mode (dropout on the concatenation applied); "-expdecay" is inference only."""
+        Differentiable (smx_summary_mixing_bwd and its training-mode / sum_mask forms) in all four modes when x requires grad or in
+        training mode (dropout on the concatenation applied; "-expdecay": decay_constant is not trainable, as in the reference)."""
         H.require_cuda(x, "SummaryMixing")
         if x.dim() != 3 or x.shape[-1] != self.enc_dim:
             raise RuntimeError(f"SummaryMixing expects (B,T,{self.enc_dim}), got {tuple(x.shape)}")
@@ -137,10 +137,6 @@ class SummaryMixing(nn.Module):
         smask = H.sum_mask_f32(sum_mask, T, dev)
         if torch.is_grad_enabled() and (x.requires_grad or (self.training and any(p.requires_grad for p in self.parameters()))):
             lite = self.mode == "SummaryMixing-lite"  # (lite ignores sum_mask, summary_mixing.py:300-324)
-            if not (lite or self.mode in ("SummaryMixing", "SummaryMixing-fast")):
-                raise NotImplementedError(
-                    "summarymixing_b200: backward is implemented for modes 'SummaryMixing', 'SummaryMixing-fast' and "
-                    "'SummaryMixing-lite' only; wrap other configurations in torch.no_grad()")
             from .. import _autograd as A
 
             drop = None if lite else A.new_dropout(self, self.dropout.p)  # (lite has no dropout, summary_mixing.py:300-324)

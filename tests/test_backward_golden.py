@@ -37,7 +37,7 @@ def oracle_grads(fx, dy, dtype=torch.float32):
 
 
 def test_fixtures_present():
-    assert len(bwd_names()) >= 23
+    assert len(bwd_names()) >= 25
 
 
 @pytest.mark.parametrize("name", bwd_names())

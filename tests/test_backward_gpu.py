@@ -121,16 +121,6 @@ def test_backward_bf16_io():
         _close(p.grad, g[k], 1e-3, k)
 
 
-def test_backward_unsupported_configurations_fail_loudly():
-    import summarymixing_b200 as S
-
-    x = torch.randn(2, 16, 64, device=DEV, requires_grad=True)
-    with pytest.raises(NotImplementedError, match="backward"):
-        S.SummaryMixing(64, 4, [64], 64, [64], 64, mode="SummaryMixing-expdecay").to(DEV).eval()(x)
-    # (training-mode dropout and the sum_mask / Dynamic Chunk Convolution backward are implemented: tests/test_dropout_gpu.py and the
-    #  *_summask / convmod_dcconv / *_dynchunk gradient fixtures above)
-
-
 def test_backward_properties_at_baseline_shape():
     """B=32, T=1000, D=256, h=4 (BASELINE configs[1] cell): the backward is linear in dy, padded frames receive no
     gradient, and an utterance's dx does not depend on the other utterances in the batch."""

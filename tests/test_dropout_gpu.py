@@ -249,13 +249,14 @@ def test_convolution_branch_standalone_and_use_linear_after_conv():
         m(torch.randn(1, 7, 64, device=DEV))
 
 
-@pytest.mark.parametrize("mode", ["SummaryMixing", "SummaryMixing-fast"])
+@pytest.mark.parametrize("mode", ["SummaryMixing", "SummaryMixing-fast", "SummaryMixing-expdecay"])
 def test_cell_dropout_with_sum_mask(mode):
     """Dynamic Chunk Training with dropout: per-frame summaries under a chunked sum_mask, dropout on the written-out concatenation
-    (smx_summary_mixing_masked_train_fwd / _bwd) against the oracle under the same mask."""
+    (smx_summary_mixing_masked_train_fwd / _bwd) against the oracle under the same mask; "-expdecay": the Laplace weights times the
+    chunk mask (summary_mixing.py:223-224)."""
     torch.manual_seed(13)
     p = 0.2
-    m = _perturbed(S.SummaryMixing(64, 4, [64], 64, [64], 64, activation=nn.GELU, global_dropout=p, mode=mode, use_layernorm=(mode == "SummaryMixing")), 13)
+    m = _perturbed(S.SummaryMixing(64, 4, [64], 64, [64], 64, activation=nn.GELU, global_dropout=p, mode=mode, use_layernorm=(mode != "SummaryMixing-fast")), 13)
     m = m.to(DEV).train()
     B, T, chunk = 3, 77, 16
     x = torch.randn(B, T, 64, device=DEV, requires_grad=True)
@@ -266,12 +267,14 @@ def test_cell_dropout_with_sum_mask(mode):
     y = m(x, sum_mask=smask.to(DEV), src_padding_mask=mask)
     y.backward(dy)
     hook = OD.Hook(p, {"cat": (s0, 0)})
-    y_or, dx_or, g_or = _oracle(lambda xo, sd: O.summary_mixing(xo, sd, mode=mode, act="gelu", use_layernorm=(mode == "SummaryMixing"),
+    y_or, dx_or, g_or = _oracle(lambda xo, sd: O.summary_mixing(xo, sd, mode=mode, act="gelu", use_layernorm=(mode != "SummaryMixing-fast"),
                                                                 src_padding_mask=mask.cpu(), sum_mask=smask, drop=hook), m, x, dy)
     assert hook.used == ["cat"]
     _close(y, y_or, 1e-4, "forward")
     _close(x.grad, dx_or, 1e-4, "dx")
     for k, prm in m.named_parameters():
+        if not prm.requires_grad:  # decay_constant of "-expdecay" (requires_grad=False in the reference, summary_mixing.py:159-161)
+            continue
         if g_or[k] is None:
             assert prm.grad is None or float(prm.grad.abs().max()) == 0.0, k
             continue
