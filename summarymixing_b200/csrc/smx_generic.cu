@@ -97,6 +97,13 @@ int vanilla_generic(const smx_linear* blocks, int n, int act, const void* x, int
   size_t sc_bytes = 0;
   void* sc = split_scratch(ws, rows, {&blocks[0], n > 1 ? &blocks[1] : nullptr, n > 2 ? &blocks[2] : nullptr, n > 3 ? &blocks[3] : nullptr}, sc_bytes);
   const void* cur = x; int cur_dt = x_dt; int64_t cur_ld = ldx;
+  if (x_dt != SMX_F32 && sc && tc_f32_tc_enabled() && ldx == blocks[0].in_dim && tc_split3_ok(rows, blocks[0].in_dim, blocks[0].out_dim)) {
+    // bf16 rows: one conversion pass puts the first block on the split-bf16 tensor-core GEMM too (the CUDA-core GEMM reads bf16 directly)
+    float* xf = ws.f32((size_t)rows * blocks[0].in_dim);
+    if (!xf) return fail(SMX_ERR_WORKSPACE, "workspace too small (VanillaNN)");
+    if (!ws.dry) SMX_TRY(convert(x, x_dt, xf, SMX_F32, rows * blocks[0].in_dim, st));
+    cur = xf; cur_dt = SMX_F32;
+  }
   for (int i = 0; i < n; ++i) {
     const bool last = (i == n - 1);
     if (i > 0 && blocks[i].in_dim != blocks[i - 1].out_dim)
