@@ -543,7 +543,26 @@ int branch_bwd(const smx_linear* blocks, const smx_linear_grad* g, int n, int ac
 __global__ void __launch_bounds__(256) div_rows_kernel(float* v, const float* rs, int T, int D, int64_t n) {
   for (int64_t i = (int64_t)blockIdx.x * 256 + threadIdx.x; i < n; i += (int64_t)gridDim.x * 256) v[i] = v[i] / rs[(i / D) % T];
 }
-int summask_fwd(const float* M, float* rs, const float* S, int64_t ldS, int B, int T, int Ds, float* Sf, cudaStream_t st) {
+// iv (4 T + 1 ints: lo, hi, tlo, thi, flag) + pws (interval_means_workspace_bytes): the prefix-sum form for masks whose rows are runs of
+// ones (the dynamic-chunk masks, TransformerASR.py:85-110), O(T D) per utterance; the structure is checked on the device and any other
+// mask (weights, holes, the Laplace matrix) takes the (T,T) products.  iv == NULL: products only.
+struct SumMaskWs { int* iv; void* pws; };
+SumMaskWs summask_ws(Arena& ws, int B, int T, int D, bool try_intervals) {
+  SumMaskWs r{nullptr, nullptr};
+  if (try_intervals) {
+    r.iv = (int*)ws.take((size_t)(4 * T + 1) * sizeof(int));
+    r.pws = ws.take(interval_means_workspace_bytes(B, T, D));
+    if (!r.iv || !r.pws) r = SumMaskWs{nullptr, nullptr};
+  }
+  return r;
+}
+int summask_fwd(const float* M, float* rs, const float* S, int64_t ldS, int B, int T, int Ds, float* Sf, const SumMaskWs& sw, cudaStream_t st) {
+  int* flag = nullptr;
+  if (sw.iv) {
+    flag = sw.iv + 4 * T;
+    SMX_TRY(interval_detect(M, T, sw.iv, sw.iv + T, flag, st));
+    SMX_TRY(interval_means(S, ldS, B, T, Ds, sw.iv, sw.iv + T, flag, Sf, sw.pws, st));
+  }
   SMX_TRY(rowsum(M, T, T, rs, st));
   GemmP p = bw_gemm();
   p.A = M; p.lda = T; p.a_bs = 0;
@@ -551,18 +570,26 @@ int summask_fwd(const float* M, float* rs, const float* S, int64_t ldS, int B, i
   p.rowdiv = rs;
   p.C = Sf; p.ldc = Ds; p.c_bs = (int64_t)T * Ds;
   p.M = T; p.N = Ds; p.K = T; p.batches = B;
+  p.run_if_nonzero = flag;
   return gemm(p, st);
 }
-int summask_bwd(const float* M, const float* rs, float* dSf, int B, int T, int Ds, float* dS, int64_t ldd, cudaStream_t st) {
+int summask_bwd(const float* M, const float* rs, float* dSf, int B, int T, int Ds, float* dS, int64_t ldd, const SumMaskWs& sw, cudaStream_t st) {
   const int64_t n = (int64_t)B * T * Ds;
   div_rows_kernel<<<ew_grid(n), 256, 0, st>>>(dSf, rs, T, Ds, n);
   count_launch();
   SMX_TRY(check_launch("div_rows_kernel"));
+  int* flag = nullptr;
+  if (sw.iv) {  // (summask_fwd has filled lo / hi and the flag)
+    flag = sw.iv + 4 * T;
+    SMX_TRY(interval_transpose(sw.iv, sw.iv + T, T, sw.iv + 2 * T, sw.iv + 3 * T, flag, st));
+    SMX_TRY(interval_sums(dSf, Ds, B, T, Ds, sw.iv + 2 * T, sw.iv + 3 * T, flag, dS, ldd, sw.pws, st));
+  }
   GemmP p = bw_gemm();
   p.A = M; p.lda = 1; p.a_sk = T; p.a_bs = 0;   // A[m][k] = M[k][m]
   p.W = dSf; p.w_sk = Ds; p.w_sn = 1; p.w_bs = (int64_t)T * Ds;
   p.C = dS; p.ldc = ldd; p.c_bs = (int64_t)T * ldd;
   p.M = T; p.N = Ds; p.K = T; p.batches = B;
+  p.run_if_nonzero = flag;
   return gemm(p, st);
 }
 
@@ -623,12 +650,14 @@ int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int
       // written-out combiner: cat = dropout([G[:, :D_l] | mean_b]) (sum_mask: [G[:, :D_l] | Sf], per-frame summaries), zc = cat Wc^T + b_c
       BWF_BUF(cat, rows * 2 * Dl);
       float* rsm = nullptr; float* Sf = nullptr;
+      SumMaskWs smw{nullptr, nullptr};
       if (sum_mask) {
         rsm = ws.f32((size_t)T); Sf = ws.f32((size_t)rows * Dl);
+        smw = summask_ws(ws, B, T, Dl, true);
         if (!rsm || !Sf) return fail(SMX_ERR_WORKSPACE, "workspace too small (cell backward, sum_mask)");
       }
       if (!ws.dry) {
-        if (sum_mask) SMX_TRY(summask_fwd(sum_mask, rsm, G + Dl, 2 * Dl, B, T, Dl, Sf, st));
+        if (sum_mask) SMX_TRY(summask_fwd(sum_mask, rsm, G + Dl, 2 * Dl, B, T, Dl, Sf, smw, st));
         else SMX_TRY(masked_mean(G + Dl, 2 * Dl, mask, B, T, Dl, mean, SMX_F32, st));
         concat_bcast_kernel<<<ew_grid(rows * 2 * Dl), 256, 0, st>>>(G, 2 * Dl, sum_mask ? Sf : mean, sum_mask ? 1 : T, Dl, Dl, rows * 2 * Dl, cat);
         count_launch();
@@ -658,7 +687,7 @@ int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int
           take_cols_kernel<<<ew_grid(rows * Dl), 256, 0, st>>>(dcat + Dl, 2 * Dl, Dl, rows * Dl, Sf, Dl);  // (Sf is dead)
           count_launch();
           SMX_TRY(check_launch("take_cols_kernel"));
-          SMX_TRY(summask_bwd(sum_mask, rsm, Sf, B, T, Dl, dG + Dl, 2 * Dl, st));
+          SMX_TRY(summask_bwd(sum_mask, rsm, Sf, B, T, Dl, dG + Dl, 2 * Dl, smw, st));
         } else {
         colsum_kernel<<<dim3((Dl + 31) / 32, B), 256, 0, st>>>(dcat + Dl, 2 * Dl, rows, T, Dl, dmean);  // d mean_b = sum_t dcat[b,t,D_l:]
         count_launch();
@@ -753,10 +782,12 @@ int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int
 
   // "SummaryMixing-expdecay" (summary_mixing.py:223-224): the sum mask is the Laplace-shaped weight matrix decay^|t - t'| (times the
   // caller's binary mask, if any); decay_constant is not trainable (requires_grad=False, :159-161), so this is the sum_mask path
+  bool try_intervals = sum_mask != nullptr;
   if (w->mode == SMX_MODE_EXPDECAY) {
     BW_BUF(lap, (size_t)T * T);
     BW_RUN(laplace(w->decay_constant, sum_mask, T, lap, st));
     sum_mask = lap;
+    try_intervals = false;
   }
   // ---- forward recomputation ----
   const float* x32 = (const float*)x;
@@ -779,11 +810,13 @@ int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int
   // the summary: one row per utterance (the masked mean), or one per frame under a sum mask
   const int64_t srows = sum_mask ? rows : B;
   float* rsm = nullptr;
+  SumMaskWs smw{nullptr, nullptr};
   BW_BUF(mean, (size_t)srows * Ds);
   if (sum_mask) {
     rsm = ws.f32((size_t)T);
+    smw = summask_ws(ws, B, T, Ds, try_intervals);
     if (!rsm) return fail(SMX_ERR_WORKSPACE, "workspace too small (cell backward, sum_mask)");
-    BW_RUN(summask_fwd(sum_mask, rsm, Sm, Ds, B, T, Ds, mean, st));
+    BW_RUN(summask_fwd(sum_mask, rsm, Sm, Ds, B, T, Ds, mean, smw, st));
   } else {
     BW_RUN(masked_mean(Sm, Ds, mask, B, T, Ds, mean, SMX_F32, st));
   }
@@ -862,7 +895,7 @@ int cell_bwd_generic(const smx_cell_weights* w, int B, int T, const void* x, int
   BW_BUF(inv, (size_t)B);
   BW_BUF(dS, rows * Ds);
   if (sum_mask) {
-    BW_RUN(summask_bwd(sum_mask, rsm, dmu, B, T, Ds, dS, Ds, st));
+    BW_RUN(summask_bwd(sum_mask, rsm, dmu, B, T, Ds, dS, Ds, smw, st));
   } else if (!ws.dry) {
     inv_count_kernel<<<B, 32, 0, st>>>(mask, T, inv);
     count_launch();

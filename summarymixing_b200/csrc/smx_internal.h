@@ -85,6 +85,9 @@ int rowsum(const float* m, int rows, int cols, float* out, cudaStream_t st);
 // (fp64 running sums) -- O(T D) per utterance instead of the (T,T) @ (T,D) product.  Both are no-ops once the flag is set.
 int interval_detect(const float* M, int T, int* lo, int* hi, int* not_interval, cudaStream_t st);
 size_t interval_means_workspace_bytes(int B, int T, int D);
+int interval_transpose(const int* lo, const int* hi, int T, int* tlo, int* thi, int* not_interval, cudaStream_t st);
+int interval_sums(const float* S, int64_t ldS, int B, int T, int D, const int* lo, const int* hi, const int* not_interval, float* out, int64_t ldo,
+                  void* workspace, cudaStream_t st);  // the gradient form: sums over the (transposed) intervals, workspace as interval_means
 int interval_means(const float* S, int64_t ldS, int B, int T, int D, const int* lo, const int* hi, const int* not_interval, float* Sm,
                    void* workspace, cudaStream_t st);
 int convert(const void* src, int s_dtype, void* dst, int d_dtype, int64_t n, cudaStream_t st);

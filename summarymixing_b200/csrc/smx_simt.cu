@@ -525,7 +525,8 @@ __global__ void __launch_bounds__(256) prefix_time_kernel(const float* __restric
   }
 }
 __global__ void __launch_bounds__(256) interval_mean_kernel(const double* __restrict__ P, const int* __restrict__ lo, const int* __restrict__ hi, int B,
-                                                            int T, int D, const int* __restrict__ skip, float* __restrict__ Sm) {
+                                                            int T, int D, const int* __restrict__ skip, float* __restrict__ Sm, int64_t ldo = 0,
+                                                            int as_sum = 0) {
   if (*skip) return;
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= (int64_t)B * T * D) return;
@@ -535,7 +536,42 @@ __global__ void __launch_bounds__(256) interval_mean_kernel(const double* __rest
   const int l = lo[t], h = hi[t];
   const double* p = P + (int64_t)b * (T + 1) * D + d;
   // the reference divides by the row sum of the mask: padding is NOT removed from the denominator (summary_mixing.py:239-246)
+  if (as_sum) { Sm[bt * ldo + d] = h > l ? (float)(p[(int64_t)h * D] - p[(int64_t)l * D]) : 0.0f; return; }  // (the gradient form)
   Sm[i] = (float)((p[(int64_t)h * D] - p[(int64_t)l * D]) / (double)(h - l));
+}
+// The transposed intervals of a mask whose rows t are runs [lo_t, hi_t) with lo and hi non-decreasing in t (the dynamic-chunk masks):
+// column t' is covered by the rows [tlo, thi) with tlo = first t with hi_t > t', thi = first t with lo_t > t'.  Any other structure sets
+// *not_interval (one block).
+__global__ void __launch_bounds__(256) interval_transpose_kernel(const int* __restrict__ lo, const int* __restrict__ hi, int T, int* __restrict__ tlo,
+                                                                 int* __restrict__ thi, int* __restrict__ not_interval) {
+  if (*not_interval) return;
+  for (int t = threadIdx.x + 1; t < T; t += 256)
+    if (lo[t] < lo[t - 1] || hi[t] < hi[t - 1]) atomicExch(not_interval, 1);
+  for (int c = threadIdx.x; c < T; c += 256) {
+    int a = 0, b = T;   // first t with hi[t] > c
+    while (a < b) { const int m = (a + b) >> 1; if (hi[m] > c) b = m; else a = m + 1; }
+    tlo[c] = a;
+    a = 0; b = T;       // first t with lo[t] > c
+    while (a < b) { const int m = (a + b) >> 1; if (lo[m] > c) b = m; else a = m + 1; }
+    thi[c] = a;
+  }
+}
+int interval_transpose(const int* lo, const int* hi, int T, int* tlo, int* thi, int* not_interval, cudaStream_t st) {
+  interval_transpose_kernel<<<1, 256, 0, st>>>(lo, hi, T, tlo, thi, not_interval);
+  count_launch();
+  return check_launch("interval_transpose_kernel");
+}
+// out[b,t,:] (row stride ldo) = sum_{j in [lo_t, hi_t)} S[b,j,:]; skipped when *not_interval
+int interval_sums(const float* S, int64_t ldS, int B, int T, int D, const int* lo, const int* hi, const int* not_interval, float* out, int64_t ldo,
+                  void* workspace, cudaStream_t st) {
+  double* P = (double*)workspace;
+  const int64_t n1 = (int64_t)B * D, n2 = (int64_t)B * T * D;
+  prefix_time_kernel<<<(unsigned)((n1 + 255) / 256), 256, 0, st>>>(S, ldS, B, T, D, not_interval, P);
+  count_launch();
+  SMX_TRY(check_launch("prefix_time_kernel"));
+  interval_mean_kernel<<<(unsigned)((n2 + 255) / 256), 256, 0, st>>>(P, lo, hi, B, T, D, not_interval, out, ldo, 1);
+  count_launch();
+  return check_launch("interval_mean_kernel");
 }
 size_t interval_means_workspace_bytes(int B, int T, int D) { return align_up((size_t)B * (T + 1) * D * sizeof(double)); }
 int interval_means(const float* S, int64_t ldS, int B, int T, int D, const int* lo, const int* hi, const int* not_interval, float* Sm,

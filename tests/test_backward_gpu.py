@@ -221,3 +221,32 @@ def test_branchformer_backward_properties_and_sum_mask():
     for k, p in m.named_parameters():
         if sd[k].grad is not None:
             _close(p.grad, sd[k].grad, 3e-4, k)
+
+
+@pytest.mark.parametrize("structure", ["chunks", "weights"])
+def test_cell_sum_mask_backward_both_forms(structure):
+    """A chunked 0/1 sum mask takes the prefix-sum form of the summaries and of their gradient (O(T D) per utterance), a mask of
+    arbitrary weights the (T,T) products: both against torch.autograd of the oracle, at a T that is not a multiple of the chunk."""
+    import summarymixing_b200 as S
+
+    torch.manual_seed(41)
+    m = _perturbed(S.SummaryMixing(64, 4, [64], 64, [64], 64, activation=nn.GELU, global_dropout=0.0), 41).to(DEV).eval()
+    B, T, chunk = 3, 203, 24
+    x = torch.randn(B, T, 64, device=DEV, requires_grad=True)
+    mask = (torch.arange(T)[None] < torch.tensor([T, 150, 31])[:, None]).to(DEV)
+    dy = torch.randn(B, T, 64, device=DEV)
+    if structure == "chunks":   # a frame sees the previous chunk, its own and nothing else (limited left context)
+        ci = torch.arange(T) // chunk
+        smask = ((ci[None, :] <= ci[:, None]) & (ci[None, :] >= ci[:, None] - 1)).float()
+    else:
+        smask = torch.rand(T, T, generator=torch.Generator().manual_seed(5)) + 0.1
+    y = m(x, sum_mask=smask.to(DEV), src_padding_mask=mask)
+    y.backward(dy)
+    sd = {k: v.detach().cpu().float().clone().requires_grad_(True) for k, v in m.state_dict().items()}
+    xo = x.detach().cpu().clone().requires_grad_(True)
+    yo = O.summary_mixing(xo, sd, mode="SummaryMixing", act="gelu", use_layernorm=True, src_padding_mask=mask.cpu(), sum_mask=smask)
+    yo.backward(dy.cpu())
+    _close(y, yo.detach(), 1e-4, "forward")
+    _close(x.grad, xo.grad, 1e-4, "dx")
+    for k, p in m.named_parameters():
+        _close(p.grad, sd[k].grad, 1e-4, k)
