@@ -6,7 +6,7 @@ Both arms: 12-layer Conformer encoder, D=256, d_ffn=1024, h=4, k=31, B=8, T = 50
                     its own PyTorch path would run on the GPU: the oracle restatement (oracle.conformer_encoder_mhsa, pinned to the
                     unmodified reference by tests/golden/mhsa/) executed with torch CUDA ops -- cuBLAS linears, torch SDPA
                     (flash attention), cuDNN depthwise conv.  Library kernels, the comparison baseline, not product code.
-Reports ms per forward, frames/s and RTF = t / (B*T*0.04 s) (40 ms of audio per frame after 4x subsampling of 10 ms hops).
+Both arms are timed as CUDA-graph replays (and, for reference, with eager launches).  Reports ms per forward, frames/s and RTF = t / (B*T*0.04 s) (40 ms of audio per frame after 4x subsampling of 10 ms hops).
 
     python tools/rtf_sweep.py [--quick]     # --quick: T = 1000, 4000, 8000 only
 """
@@ -18,6 +18,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 
 import bench
+import summarymixing_b200 as S
 from oracle import smx_oracle as O  # comparison arm only
 
 dev = torch.device("cuda", 0)
@@ -71,13 +72,31 @@ with torch.no_grad():
         lens = torch.randint(T // 2, T + 1, (B,), generator=g)
         lens[0] = T
         mask = (torch.arange(T)[None] < lens[:, None]).to(dev)
-        ms_sm = timed(lambda: enc(x, src_key_padding_mask=mask))
-        ms_at = timed(lambda: O.conformer_encoder_mhsa(x, sd, NL, H, act="swish", key_padding_mask=~mask))
+        ms_sm_eager = timed(lambda: enc(x, src_key_padding_mask=mask))
+        ms_at_eager = timed(lambda: O.conformer_encoder_mhsa(x, sd, NL, H, act="swish", key_padding_mask=~mask))
+        # both arms replayed as CUDA graphs (what a serving process does: no host launch work in the timed region)
+        gf = S.GraphedForward(enc, x, mask)
+        ms_sm = timed(gf.replay)
+        try:
+            nm = ~mask
+            side = torch.cuda.Stream(dev)
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                O.conformer_encoder_mhsa(x, sd, NL, H, act="swish", key_padding_mask=nm)
+            torch.cuda.current_stream(dev).wait_stream(side)
+            ga = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(ga):
+                O.conformer_encoder_mhsa(x, sd, NL, H, act="swish", key_padding_mask=nm)
+            ms_at = timed(ga.replay)
+        except Exception:  # (capture is an optimisation of the host side only)
+            ms_at = ms_at_eager
+        del gf
         audio_s = B * T * 0.04
         rows.append({"T": T, "B": B, "summarymixing_ms": round(ms_sm, 3), "mhsa_torch_ms": round(ms_at, 3),
+                     "summarymixing_eager_ms": round(ms_sm_eager, 3), "mhsa_torch_eager_ms": round(ms_at_eager, 3),
                      "summarymixing_frames_per_s": round(B * T / ms_sm * 1e3), "mhsa_torch_frames_per_s": round(B * T / ms_at * 1e3),
                      "summarymixing_rtf": ms_sm / 1e3 / audio_s, "mhsa_torch_rtf": ms_at / 1e3 / audio_s, "speedup": ms_at / ms_sm})
         print(f"T={T:5d}  SummaryMixing (libsmx) {ms_sm:8.3f} ms  RTF {rows[-1]['summarymixing_rtf']:.2e}   |   self-attention (torch, flash SDPA) "
-              f"{ms_at:8.3f} ms  RTF {rows[-1]['mhsa_torch_rtf']:.2e}   |   x{ms_at / ms_sm:.2f}")
+              f"{ms_at:8.3f} ms  RTF {rows[-1]['mhsa_torch_rtf']:.2e}   |   x{ms_at / ms_sm:.2f}   (eager launches: {ms_sm_eager:.3f} / {ms_at_eager:.3f} ms)")
 print(json.dumps({"config": "cfg5: utterance-length sweep, SummaryMixing (libsmx) vs self-attention Conformer (reference algorithm, torch CUDA ops)",
                   "batch": B, "layers": NL, "d_model": D, "io": "bf16", "rows": rows}))
