@@ -191,6 +191,7 @@ struct GemmTc {
   float* out_f32 = nullptr; const float* resid_f32 = nullptr;   // fp32 output / residual instead of out / resid
   int split3 = 0;                                     // set by tc_linear_split3
   int ksplit = 1; int64_t out_split_stride = 0;       // split-K: fp32 partials out_f32 + ks * out_split_stride (summed by the caller)
+  int bd_in = 0, bd_out = 0;                          // W is block-diagonal (ParallelLinear as dense with zero blocks): per-head input / output width
 };
 bool tc_gemm_supported(int K, int N);
 // fp32 linears on the tensor cores with split-bf16 operands (smx_tc_gemm.cu)

@@ -35,8 +35,20 @@ struct GemmTcP {
   int split3;                                // A and W hold [hi | lo] halves of width K: accumulate hi*hi + hi*lo + lo*hi
   int ksplit, kb_per_split;                  // split-K: slice ks covers K-blocks [ks kb_per_split, ...) and writes out_f32 + ks * out_split_stride
   int64_t out_split_stride;
+  int bd_in, bd_out;                         // block-diagonal W (ParallelLinear as dense with zero blocks): head widths; 0 = dense.  An N tile
+                                             // only visits the K-blocks of the heads it covers (the others are zero)
   int n_stages; uint32_t stage_bytes; uint32_t tmem_cols;
 };
+// K-block range [kb0, kb0 + nloc) of one (split-K slice, N tile)
+__device__ __forceinline__ void gm_krange(const GemmTcP& p, int ks, int nt, int nkb1, int& kb0, int& nloc) {
+  kb0 = ks * p.kb_per_split;
+  nloc = min(p.kb_per_split, nkb1 - kb0);
+  if (p.bd_in) {
+    const int h0 = (nt * p.NT) / p.bd_out, h1 = (nt * p.NT + p.NT - 1) / p.bd_out;
+    kb0 = (h0 * p.bd_in) >> 6;
+    nloc = min(nkb1, ((h1 + 1) * p.bd_in + 63) >> 6) - kb0;
+  }
+}
 
 __device__ __forceinline__ void gm_tma_load_2d(void* smem_dst, const CUtensorMap* tmap, int c0, int c1, uint64_t* bar) {
   asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
@@ -88,7 +100,8 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
       for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
         const int ks = tile / mn_tiles, t2 = tile - ks * mn_tiles;
         const int nt = t2 / p.m_tiles, mt = t2 - nt * p.m_tiles;
-        const int kb0 = ks * p.kb_per_split, nloc = min(p.kb_per_split, nkb1 - kb0);
+        int kb0, nloc;
+        gm_krange(p, ks, nt, nkb1, kb0, nloc);
 #pragma unroll 1
         for (int kb = 0; kb < nseg * nloc; ++kb) {
           tc::mbar_wait(&empty_bar[s], ph ^ 1u);
@@ -113,8 +126,10 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
       tc::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator (first two uses: fresh)
       tc::tc_fence_after();
       const uint32_t d_addr = tmem + (uint32_t)buf * (uint32_t)NT;
-      const int ks = tile / mn_tiles;
-      const int nkb = nseg * min(p.kb_per_split, nkb1 - ks * p.kb_per_split);
+      const int ks = tile / mn_tiles, nt_i = (tile - ks * mn_tiles) / p.m_tiles;
+      int kb0_i, nloc_i;
+      gm_krange(p, ks, nt_i, nkb1, kb0_i, nloc_i);
+      const int nkb = nseg * nloc_i;
 #pragma unroll 1
       for (int kb = 0; kb < nkb; ++kb) {
         tc::mbar_wait_spin(&full_bar[s], ph);
@@ -277,6 +292,9 @@ int tc_gemm_launch(const GemmTc& g, cudaStream_t st) {
     p.kb_per_split = (nkb1 + want - 1) / want;
     p.ksplit = (nkb1 + p.kb_per_split - 1) / p.kb_per_split;   // no empty slice
     p.out_split_stride = g.out_split_stride;
+  }
+  if (g.bd_in > 0 && g.bd_out > 0 && p.ksplit == 1 && g.bd_in % 64 == 0 && g.K % g.bd_in == 0 && g.N % g.bd_out == 0 && g.K / g.bd_in == g.N / g.bd_out) {
+    p.bd_in = g.bd_in; p.bd_out = g.bd_out;
   }
   p.stage_bytes = kblock_bytes(128) + (uint32_t)p.NT * 128u;
   int stages = (int)((227 * 1024 - 2048) / p.stage_bytes);

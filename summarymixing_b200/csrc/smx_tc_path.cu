@@ -402,6 +402,7 @@ int tc_cell_fwd(const smx_cell_weights* w, const void* packed, int B, int T, con
           g.w = (const __nv_bfloat16*)(pk + l.summary_d[i]); g.bias = w->summary[i].b; g.act = w->act; g.alpha = 1.0f;
           g.rowmask = last ? mask : nullptr;
           g.out = hb[i & 1]; g.ldo = g.N;
+          if (w->summary[i].n_split > 1) { g.bd_in = g.K / w->summary[i].n_split; g.bd_out = g.N / w->summary[i].n_split; }  // skip the zero blocks
           SMX_TRY(tc_gemm_launch(g, st));
           cur = g.out; ld = g.ldo;
           if (last) SMX_TRY(colsum_tiles(cur, B, T, Ds, o.colsum, st));
@@ -495,6 +496,7 @@ int tc_cell_fwd(const smx_cell_weights* w, const void* packed, int B, int T, con
     g.act = act_code; g.rowmask = rowmask;
     g.resid = resid; g.ldr = L.out_dim; g.alpha = 1.0f;
     g.out = out; g.ldo = L.out_dim;
+    if (L.n_split > 1 && K == L.in_dim) { g.bd_in = L.in_dim / L.n_split; g.bd_out = L.out_dim / L.n_split; }  // skip the zero blocks
     return tc_gemm_launch(g, st);
   };
   const __nv_bfloat16* x_in = x;      // input of the first block of both branches
