@@ -168,9 +168,11 @@ __global__ void __launch_bounds__(256) ln_kernel(const void* x, int x_dt, int64_
 
 // bf16 -> bf16 rows of D = 256 NCH elements: one warp per row, the row held in registers (128-bit loads and stores, one pass over
 // memory; two-pass statistics like the generic kernel).  The generic kernel's 2-byte accesses and three passes ran at 1.7 TB/s
-// (38 us for 32 000 x 512), a fifth of the D = 512 layers' time.
-template <int NCH>
-__global__ void __launch_bounds__(256) ln_bf16_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+// (38 us for 32 000 x 512), a fifth of the D = 512 layers' time.  The pass is latency-bound: bytes in flight per SM = resident warps x
+// 2 rows, so the plain (no activation) instance is compiled without the activation switch and for 5 / 4 resident blocks
+// (48 / 64 registers): 15.1 -> 8.4 us at 32 000 x 256, 20.8 -> 15.3 us at x 512 (3.9 / 4.3 TB/s; tools/ln_time.py).
+template <int NCH, bool IDENT>   // IDENT: no activation after the normalisation (the common case; the activation switch costs registers, i.e. resident warps)
+__global__ void __launch_bounds__(256, (!IDENT ? 2 : (NCH == 1 ? 5 : (NCH == 2 ? 4 : 2)))) ln_bf16_rows_kernel(const __nv_bfloat16* __restrict__ x, int64_t ldx, const float* __restrict__ w,
                                                            const float* __restrict__ b, float eps, int act, __nv_bfloat16* __restrict__ y,
                                                            int64_t ldy, int64_t rows) {
   constexpr int RPW = 2;  // rows per warp: both rows' loads are in flight before the first reduction
@@ -213,7 +215,10 @@ __global__ void __launch_bounds__(256) ln_bf16_rows_kernel(const __nv_bfloat16* 
       const float ww[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w}, bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
       float o[8];
 #pragma unroll
-      for (int e = 0; e < 8; ++e) o[e] = apply_act(act, (v[c][e] - mean) * rstd * ww[e] + bb[e]);
+      for (int e = 0; e < 8; ++e) {
+        const float t = (v[c][e] - mean) * rstd * ww[e] + bb[e];
+        o[e] = IDENT ? t : apply_act(act, t);
+      }
       uint4 out;
       __nv_bfloat162* ho = reinterpret_cast<__nv_bfloat162*>(&out);
 #pragma unroll
@@ -232,10 +237,15 @@ int layernorm(const void* x, int x_dtype, int64_t ldx, const float* w, const flo
     const __nv_bfloat16* xb = (const __nv_bfloat16*)x;
     __nv_bfloat16* yb = (__nv_bfloat16*)y;
     switch (D / 256) {
-      case 1: ln_bf16_rows_kernel<1><<<grid, 256, 0, st>>>(xb, ldx, w, b, eps, act, yb, ldy, rows); break;
-      case 2: ln_bf16_rows_kernel<2><<<grid, 256, 0, st>>>(xb, ldx, w, b, eps, act, yb, ldy, rows); break;
-      case 3: ln_bf16_rows_kernel<3><<<grid, 256, 0, st>>>(xb, ldx, w, b, eps, act, yb, ldy, rows); break;
-      default: ln_bf16_rows_kernel<4><<<grid, 256, 0, st>>>(xb, ldx, w, b, eps, act, yb, ldy, rows); break;
+#define SMX_LN_CASE(n) \
+      if (act == SMX_ACT_IDENTITY) ln_bf16_rows_kernel<n, true><<<grid, 256, 0, st>>>(xb, ldx, w, b, eps, act, yb, ldy, rows); \
+      else ln_bf16_rows_kernel<n, false><<<grid, 256, 0, st>>>(xb, ldx, w, b, eps, act, yb, ldy, rows); \
+      break
+      case 1: SMX_LN_CASE(1);
+      case 2: SMX_LN_CASE(2);
+      case 3: SMX_LN_CASE(3);
+      default: SMX_LN_CASE(4);
+#undef SMX_LN_CASE
     }
     count_launch();
     return check_launch("ln_bf16_rows_kernel");
