@@ -598,7 +598,7 @@ __global__ void __launch_bounds__(256) csgu_kernel(const __nv_bfloat16* __restri
 // one packed fma.rn.f32x2 per tap and frame for both channels (the depthwise phase of K-CONV, smx_tc_conv.cu).  The first
 // generation (32 x 128 tiles, scalar FMAs) ran at 13 % of the fp32 rate: 329 us for 32 000 x 1536 -- a third of a
 // Branchformer-lite layer (profiles/r02_notes.md).
-constexpr int CS2_FR = 128, CS2_CH = 256, CS2_THREADS = 384;
+constexpr int CS2_FR = 128, CS2_CH = 128, CS2_THREADS = 256;   // 98 KB of shared memory per block: two blocks per SM (one stages while the other convolves), 4 frame blocks per thread
 __device__ __forceinline__ float2 cs2_fma2(float2 a, float2 b, float2 c) {
   unsigned long long d;
   asm("fma.rn.f32x2 %0, %1, %2, %3;"
@@ -608,7 +608,7 @@ __device__ __forceinline__ float2 cs2_fma2(float2 a, float2 b, float2 c) {
   return *reinterpret_cast<float2*>(&d);
 }
 template <int KS>
-__global__ void __launch_bounds__(CS2_THREADS, 1) csgu2_kernel(const __nv_bfloat16* __restrict__ u, const float2* __restrict__ stats,
+__global__ void __launch_bounds__(CS2_THREADS, 2) csgu2_kernel(const __nv_bfloat16* __restrict__ u, const float2* __restrict__ stats,
                                                                const float* __restrict__ ln_w, const float* __restrict__ ln_b,
                                                                const float* __restrict__ dw_w, const float* __restrict__ dw_b, int gate_act,
                                                                int T, int H, __nv_bfloat16* __restrict__ out, int64_t ldo) {
