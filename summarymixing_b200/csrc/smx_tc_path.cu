@@ -719,40 +719,44 @@ __global__ void __launch_bounds__(256) dwconv_ln_act_kernel(const __nv_bfloat16*
   }
 }
 
-// Tiled variant for kernel size K and D % 128 == 0, D <= 512.  A block takes 32 output frames of one utterance:
-// the (32 + K - 1) input frames are staged once in shared memory; phase 1 gives every thread one channel pair and
+// Tiled variant for kernel size K and D % 128 == 0, D <= 512.  A block takes DWT_FRAMES output frames of one utterance:
+// the (DWT_FRAMES + K - 1) input frames are staged once in shared memory; phase 1 gives every thread one channel pair and
 // blocks of eight consecutive frames (taps and accumulators in registers: 8*K*2 FMAs per K+7 shared-memory loads);
 // phase 2 normalises each frame over the channels (one warp per frame) and applies the activation.
-constexpr int DWT_FRAMES = 32;
+constexpr int DWT_FRAMES = 24;   // 104 KB of shared memory at D = 512: two blocks per SM (one stages while the other computes)
 template <int K>
-__global__ void __launch_bounds__(256) dwconv_tiled_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ dw_w,
-                                                           const float* __restrict__ dw_b, const float* __restrict__ ln_w,
-                                                           const float* __restrict__ ln_b, int act, int T, int D,
-                                                           __nv_bfloat16* __restrict__ out) {
+__global__ void __launch_bounds__(256, 2) dwconv_tiled_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ dw_w,
+                                                              const float* __restrict__ dw_b, const float* __restrict__ ln_w,
+                                                              const float* __restrict__ ln_b, int act, int T, int D,
+                                                              __nv_bfloat16* __restrict__ out) {
   constexpr int PAD = (K - 1) / 2, NIN = DWT_FRAMES + K - 1;
   extern __shared__ __align__(16) uint8_t dsm[];
   __nv_bfloat16* sIn = reinterpret_cast<__nv_bfloat16*>(dsm);                          // [NIN][D]
-  float* sOut = reinterpret_cast<float*>(dsm + (size_t)NIN * D * sizeof(__nv_bfloat16));  // [32][D]
+  float* sOut = reinterpret_cast<float*>(dsm + (size_t)NIN * D * sizeof(__nv_bfloat16));  // [DWT_FRAMES][D]
   const int b = blockIdx.y, t0 = blockIdx.x * DWT_FRAMES;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cpr = D / 8;
+  const int pairs = D / 2, pr = tid % pairs, fb0 = tid / pairs, nfbp = 256 / pairs;
+  const int c0 = pr * 2;
+  float w0[K], w1[K];
+  {
+    // the D x K taps pass through the (still unused) shared memory with coalesced loads: read per thread straight from global
+    // memory -- rows 4 K bytes apart between lanes -- they throttle the load/store queue (profiles/r02_notes.md)
+    float* sTap = reinterpret_cast<float*>(dsm);
+    for (int i = tid; i < D * K; i += 256) sTap[i] = dw_w[i];
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < K; ++j) { w0[j] = sTap[c0 * K + j]; w1[j] = sTap[(c0 + 1) * K + j]; }
+    __syncthreads();  // every thread holds its taps before the input rows overwrite them
+  }
   for (int idx = tid; idx < NIN * cpr; idx += 256) {
     const int row = idx / cpr, ch = idx - row * cpr, u = t0 - PAD + row;
     uint4 val = make_uint4(0, 0, 0, 0);  // zero padding at the utterance edges (Conformer.py:142-151)
     if (u >= 0 && u < T) val = *reinterpret_cast<const uint4*>(g + ((size_t)b * T + u) * D + ch * 8);
     *reinterpret_cast<uint4*>(sIn + (size_t)row * D + ch * 8) = val;
   }
-  // the D x K taps pass through the (still unused) output tile with coalesced loads: read per thread straight from global
-  // memory -- rows 4 K bytes apart between lanes -- they throttle the load/store queue (profiles/r02_notes.md)
-  for (int i = tid; i < D * K; i += 256) sOut[i] = dw_w[i];
   __syncthreads();
   {
-    const int pairs = D / 2, pr = tid % pairs, fb0 = tid / pairs, nfbp = 256 / pairs;
-    const int c0 = pr * 2;
-    float w0[K], w1[K];
-#pragma unroll
-    for (int j = 0; j < K; ++j) { w0[j] = sOut[c0 * K + j]; w1[j] = sOut[(c0 + 1) * K + j]; }
-    __syncthreads();  // every thread holds its taps before the first output rows are written
     const float b0 = dw_b ? dw_b[c0] : 0.0f, b1 = dw_b ? dw_b[c0 + 1] : 0.0f;
     for (int fb = fb0; fb < DWT_FRAMES / 8; fb += nfbp) {
       float a0[8], a1[8];
@@ -816,7 +820,8 @@ int tc_dwconv_ln_act(const __nv_bfloat16* g, const float* dw_w, const float* dw_
                      const float* ln_b, int act, int B, int T, int D, int k, __nv_bfloat16* out, cudaStream_t st) {
   if (D % 8 || D > 512) return fail(SMX_ERR_UNSUPPORTED, "dwconv: D=%d", D);
   if (k == 31 && D % 128 == 0) {
-    const size_t smem = (size_t)(DWT_FRAMES + 30) * D * 2 + (size_t)DWT_FRAMES * D * 4;
+    size_t smem = (size_t)(DWT_FRAMES + 30) * D * 2 + (size_t)DWT_FRAMES * D * 4;
+    if (smem < (size_t)D * 31 * 4) smem = (size_t)D * 31 * 4;   // (the taps pass through it first)
     cudaError_t e = cudaFuncSetAttribute(dwconv_tiled_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(dwconv_tiled): %s", cudaGetErrorString(e));
     dim3 grid((T + DWT_FRAMES - 1) / DWT_FRAMES, B);
