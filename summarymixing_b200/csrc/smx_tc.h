@@ -191,6 +191,7 @@ struct GemmTc {
   float* out_f32 = nullptr; const float* resid_f32 = nullptr;   // fp32 output / residual instead of out / resid
   int split3 = 0;                                     // set by tc_linear_split3
   int ksplit = 1; int64_t out_split_stride = 0;       // split-K: fp32 partials out_f32 + ks * out_split_stride (summed by the caller)
+  int glu = 0;                                        // GLU epilogue over an interleaved image (tc_glu_dense_bf16): N = 2 x output width
   int bd_in = 0, bd_out = 0;                          // W is block-diagonal (ParallelLinear as dense with zero blocks): per-head input / output width
 };
 bool tc_gemm_supported(int K, int N);
@@ -206,7 +207,9 @@ int tc_wgrad_slices(int64_t rows);
 int tc_wgrad_split3(const float* A, int64_t lda, int M, const float* Bm, int64_t ldb, int N, int64_t rows, float* P, int* ns, void* scratch,
                     cudaStream_t st);  // P[slice][M][N] = partial sums over row slices of A^T B
 int tc_gemm_launch(const GemmTc& g, cudaStream_t st);
-int tc_dense_bf16(const smx_linear& L, int k_offset, int K, void* out, cudaStream_t st);  // (out_dim, K) bf16 copy of columns [k_offset, +K)
+int tc_dense_bf16(const smx_linear& L, int k_offset, int K, void* out, cudaStream_t st);
+size_t tc_glu_dense_bytes(int K, int N);
+int tc_glu_dense_bf16(const smx_linear& L, void* out, cudaStream_t st);  // [bf16 image | fp32 bias], rows interleaved per 256-wide N tile for the GLU epilogue  // (out_dim, K) bf16 copy of columns [k_offset, +K)
 size_t tc_csgu_workspace_bytes(int64_t rows);
 int tc_csgu_fwd(const __nv_bfloat16* u, int B, int T, int H, const float* ln_w, const float* ln_b, const float* dw_w, const float* dw_b,
                 int kernel_size, int gate_act, __nv_bfloat16* out, int64_t ldo, void* stats_ws, cudaStream_t st);

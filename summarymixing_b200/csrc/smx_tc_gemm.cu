@@ -35,6 +35,8 @@ struct GemmTcP {
   int split3;                                // A and W hold [hi | lo] halves of width K: accumulate hi*hi + hi*lo + lo*hi
   int ksplit, kb_per_split;                  // split-K: slice ks covers K-blocks [ks kb_per_split, ...) and writes out_f32 + ks * out_split_stride
   int64_t out_split_stride;
+  int glu;                                   // GLU epilogue: W / bias rows are interleaved per N tile ([NT/2 value rows | their NT/2 gate rows], tc_glu_dense_bf16);
+                                             // out (width N/2) = (v + bv) * sigmoid(g + bg)                                   Conformer.py:322-324
   int bd_in, bd_out;                         // block-diagonal W (ParallelLinear as dense with zero blocks): head widths; 0 = dense.  An N tile
                                              // only visits the K-blocks of the heads it covers (the others are zero)
   int n_stages; uint32_t stage_bytes; uint32_t tmem_cols;
@@ -163,6 +165,37 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
       const float* rb = (live && p.rowbias) ? p.rowbias + (grow / p.rows_per_group) * p.rowbias_ld : nullptr;
       tc::mbar_wait(&acc_full[buf], (it >> 1) & 1);
       tc::tc_fence_after();
+      if (p.glu) {
+#pragma unroll 1
+        for (int pc = 0; pc < (NT >> 7); ++pc) {
+          const int c = half * (NT >> 2) + pc * 32;       // channel inside the tile's NT/2 channels: value column c, gate column NT/2 + c
+          float v[32], gt[32];
+          tc::tmem_ld32(tmem + lane_sel + (uint32_t)buf * (uint32_t)NT + c, v);
+          tc::tmem_ld32(tmem + lane_sel + (uint32_t)buf * (uint32_t)NT + (NT >> 1) + c, gt);
+          tc::tmem_ld_wait();
+          const float4* bv = reinterpret_cast<const float4*>(p.bias + nt * NT + c);
+          const float4* bg = reinterpret_cast<const float4*>(p.bias + nt * NT + (NT >> 1) + c);
+          uint32_t o[16];
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const float4 a = __ldg(bv + j), g4 = __ldg(bg + j);
+            const float av[4] = {a.x, a.y, a.z, a.w}, gv[4] = {g4.x, g4.y, g4.z, g4.w};
+            float r[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float hv = 0.5f * (v[4 * j + e] + av[e]);
+              r[e] = fmaf(hv, tc::tanh_approx(0.5f * (gt[4 * j + e] + gv[e])), hv);   // a * sigmoid(z) = a/2 * tanh(z/2) + a/2
+            }
+            o[2 * j] = tc::pack_bf16x2(r[0], r[1]);
+            o[2 * j + 1] = tc::pack_bf16x2(r[2], r[3]);
+          }
+          if (live) {
+            __nv_bfloat16* op = p.out + grow * p.ldo + nt * (NT >> 1) + c;
+            gm_stg256(op, o);
+            gm_stg256(op + 16, o + 8);
+          }
+        }
+      } else
 #pragma unroll 1
       for (int pc = 0; pc < npc; ++pc) {
         const int col = half * (NT >> 1) + pc * 32;       // column inside the tile
@@ -284,6 +317,11 @@ int tc_gemm_launch(const GemmTc& g, cudaStream_t st) {
   p.bias = g.bias; p.rowbias = g.rowbias; p.rowbias_ld = g.rowbias_ld; p.rows_per_group = g.rows_per_group > 0 ? g.rows_per_group : 1;
   p.act = g.act; p.rowmask = g.rowmask; p.resid = g.resid; p.ldr = g.ldr; p.alpha = g.alpha;
   p.out = g.out; p.ldo = g.ldo; p.out_f32 = g.out_f32; p.resid_f32 = g.resid_f32; p.split3 = g.split3;
+  if (g.glu) {
+    if (p.NT < 128 || !g.out || !g.bias || g.split3 || g.ksplit > 1 || g.resid || g.rowbias || g.rowmask || g.ldo % 16)
+      return fail(SMX_ERR_UNSUPPORTED, "tc gemm: GLU epilogue needs N %% 128 == 0, bf16 output, an (interleaved) bias and no other epilogue term");
+    p.glu = 1;
+  }
   {
     const int nkb1 = g.K / 64;
     int want = g.ksplit > 1 ? g.ksplit : 1;
@@ -359,6 +397,30 @@ __global__ void __launch_bounds__(256) split_rows_kernel(const float* __restrict
   *reinterpret_cast<uint2*>(o + K) = *reinterpret_cast<const uint2*>(lo);
 }
 // W' (N, 2K) = [hi | lo] of columns [k_offset, k_offset + K) of the dense (N, in_dim) view of an smx_linear
+// GLU weights for the K-GEMM GLU epilogue: row nt * NT + j of the image is value row nt * NT/2 + j (j < NT/2) or gate row
+// N/2 + nt * NT/2 + (j - NT/2) of the dense (N, K) linear; the bias likewise (fp32).  NT as tc_gemm_launch picks it for N.
+__global__ void glu_dense_bf16_kernel(const float* __restrict__ w, const float* __restrict__ b, int K, int N, int NT, __nv_bfloat16* __restrict__ out,
+                                      float* __restrict__ bias_out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)N * K) return;
+  const int n = (int)(i / K), k = (int)(i - (int64_t)n * K);
+  const int nt = n / NT, j = n - nt * NT, h = NT >> 1;
+  const int src = j < h ? nt * h + j : (N >> 1) + nt * h + (j - h);
+  out[i] = __float2bfloat16_rn(w[(int64_t)src * K + k]);
+  if (k == 0) bias_out[n] = b[src];
+}
+size_t tc_glu_dense_bytes(int K, int N) { return align_up((size_t)N * K * 2, 1024) + align_up((size_t)N * 4, 1024); }
+int tc_glu_dense_bf16(const smx_linear& L, void* out, cudaStream_t st) {
+  const int N = L.out_dim, K = L.in_dim;
+  if (L.n_split > 1 || !L.b || N % 256) return fail(SMX_ERR_UNSUPPORTED, "GLU image: dense linear with a bias and out_dim %% 256 == 0");
+  const int NT = 256;
+  const int64_t n = (int64_t)N * K;
+  glu_dense_bf16_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(L.w, L.b, K, N, NT, (__nv_bfloat16*)out,
+                                                                     (float*)((char*)out + align_up((size_t)N * K * 2, 1024)));
+  count_launch();
+  return check_launch("glu_dense_bf16_kernel");
+}
+
 __global__ void __launch_bounds__(256) split_weight_kernel(const float* __restrict__ w, int in_dim, int out_dim, int n_split, int k_offset, int K, int N,
                                                            __nv_bfloat16* __restrict__ out) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
