@@ -69,6 +69,7 @@ __device__ __forceinline__ void gm_stg256(void* p, const uint32_t* r) {
                : "memory");
 }
 
+template <bool GLU>   // (the GLU epilogue is its own instantiation: the plain epilogue's code and register allocation stay as they were)
 __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA,
                                                                 const __grid_constant__ CUtensorMap tmW, const GemmTcP p) {
   extern __shared__ __align__(1024) uint8_t smem[];  // ring stages: [A block 128 x 64 | W block NT x 64]
@@ -165,7 +166,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
       const float* rb = (live && p.rowbias) ? p.rowbias + (grow / p.rows_per_group) * p.rowbias_ld : nullptr;
       tc::mbar_wait(&acc_full[buf], (it >> 1) & 1);
       tc::tc_fence_after();
-      if (p.glu) {
+      if constexpr (GLU) {
 #pragma unroll 1
         for (int pc = 0; pc < (NT >> 7); ++pc) {
           const int c = half * (NT >> 2) + pc * 32;       // channel inside the tile's NT/2 channels: value column c, gate column NT/2 + c
@@ -344,11 +345,13 @@ int tc_gemm_launch(const GemmTc& g, cudaStream_t st) {
   SMX_TRY(gm_map_2d(&tmA, g.a, kw, (uint64_t)g.M, (uint64_t)g.lda * 2, 128));
   SMX_TRY(gm_map_2d(&tmW, g.w, kw, (uint64_t)g.N, kw * 2, (uint32_t)p.NT));
   const size_t smem = (size_t)stages * p.stage_bytes + 1024;
-  cudaError_t e = cudaFuncSetAttribute(gemm_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  cudaError_t e = p.glu ? cudaFuncSetAttribute(gemm_tc_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)
+                        : cudaFuncSetAttribute(gemm_tc_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(gemm_tc_kernel): %s", cudaGetErrorString(e));
   const int total = p.m_tiles * p.n_tiles * p.ksplit;
   const unsigned grid = (unsigned)(total < gm_sms() ? total : gm_sms());
-  e = launch_pdl(gemm_tc_kernel, dim3(grid), dim3(GM_THREADS), smem, st, 1u, tmA, tmW, p);
+  e = p.glu ? launch_pdl(gemm_tc_kernel<true>, dim3(grid), dim3(GM_THREADS), smem, st, 1u, tmA, tmW, p)
+            : launch_pdl(gemm_tc_kernel<false>, dim3(grid), dim3(GM_THREADS), smem, st, 1u, tmA, tmW, p);
   if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaLaunchKernelEx(gemm_tc_kernel): %s", cudaGetErrorString(e));
   count_tc_launch();
   return check_launch("gemm_tc_kernel");
