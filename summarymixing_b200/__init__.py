@@ -20,6 +20,7 @@ from .lobes.models.transformer.Branchformer import (  # noqa: F401
 )
 
 from .graphs import GraphedForward, HostPipeline  # noqa: F401
+from ._host import invalidate_weights  # noqa: F401
 from . import frontend  # noqa: F401
 
 __version__ = "0.1.0"

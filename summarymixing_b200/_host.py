@@ -111,6 +111,22 @@ class WeightView:
         return t.data_ptr()
 
 
+def invalidate_weights(module: nn.Module) -> int:
+    """Drop the cached weight views / packed tensor-core images of `module` and its sub-modules, so that the next call rebuilds them
+    from the parameters' current values.  The caches are keyed on the parameters' storage and version counters: every tracked
+    in-place update (an optimizer step, load_state_dict, p.copy_()) is seen automatically, but a write that bypasses the version
+    counter (p.data.mul_(...), an EMA or a weight clip through .data, raw pointer writes) is not — call this after such a write
+    (and re-capture any GraphedForward / HostPipeline built on the module: a captured graph keeps the old images' addresses).
+    Returns the number of caches dropped."""
+    n = 0
+    for m in module.modules():
+        wv = getattr(m, "_wv", None)
+        if isinstance(wv, WeightView):
+            wv._key = None
+            n += 1
+    return n
+
+
 _workspaces = {}
 
 
@@ -147,10 +163,12 @@ def p_or_none(t: Optional[torch.Tensor]) -> Optional[int]:
 
 
 def check_grad_mode(module: nn.Module) -> None:
+    """The inference entry points refuse a training-mode call under autograd that the differentiable path did not take (nothing
+    requires grad: no trainable parameter, input detached): training-mode behaviour (dropout, layerdrop) lives on the autograd path."""
     if module.training and torch.is_grad_enabled():
         raise NotImplementedError(
-            "summarymixing_b200 implements the forward (inference) path; call .eval() or wrap the call in "
-            "torch.no_grad() — training-mode forward (dropout, layerdrop, autograd) is not implemented yet"
+            "summarymixing_b200: this call is in training mode with autograd enabled, but neither the input nor any parameter requires "
+            "grad, so it is not on the differentiable (training) path; call .eval() or wrap the call in torch.no_grad() for inference"
         )
 
 

@@ -90,3 +90,18 @@ def test_product_package_never_imports_the_oracle():
     for f in glob.glob(os.path.join(ROOT, "summarymixing_b200", "**", "*.py"), recursive=True):
         src = open(f).read()
         assert not re.search(r"^\s*(from|import)\s+\.*oracle|smx_oracle|sbshim", src, flags=re.M), f
+
+
+def test_invalidate_weights_drops_every_cache():
+    """summarymixing_b200.invalidate_weights: every module holding a weight cache forgets its key (the next call re-reads the
+    parameters and re-packs the tensor-core images): the escape hatch for writes that bypass the version counters (p.data...)."""
+    import summarymixing_b200 as S
+
+    enc = S.ConformerEncoder(2, 64, 128, 4, 31, attention_type="SummaryMixing", local_proj_hid_dim=[64], local_proj_out_dim=64,
+                             summary_hid_dim=[64])
+    holders = [m for m in enc.modules() if hasattr(m, "_wv")]
+    assert len(holders) >= 5
+    for m in holders:
+        m._wv._key = ("stale",)
+    assert S.invalidate_weights(enc) == len(holders)
+    assert all(m._wv._key is None for m in holders)

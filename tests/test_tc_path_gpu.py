@@ -488,3 +488,21 @@ def test_tensor_core_arm_is_bit_exactly_batch_invariant():
     assert torch.equal(yp, y[perm])
     assert torch.equal(ys, y[5:18])
     assert torch.equal(y1, y[31:32])
+
+
+def test_invalidate_weights_after_a_data_write():
+    """A write through .data does not bump the version counter: the cached packed images stay; invalidate_weights makes the next call
+    re-read the parameters."""
+    import summarymixing_b200 as S
+
+    torch.manual_seed(3)
+    m = S.SummaryMixing(256, 4, [256], 256, [256], 256, activation=S.Swish).to("cuda:0").eval()
+    x = torch.randn(2, 200, 256, device="cuda:0").bfloat16()
+    with torch.no_grad():
+        y0 = m(x).clone()
+        m.summary_local_merging["linear"].w.weight.data.mul_(1.5)   # (a GEMM weight: the tensor-core arm reads its packed bf16 image)
+        y_cached = m(x).clone()
+        assert torch.equal(y_cached, y0)          # (documented behaviour: the write was invisible to the cache)
+        assert S.invalidate_weights(m) >= 1
+        y1 = m(x)
+    assert float((y1.float() - y0.float()).abs().max()) > 1e-2
