@@ -289,6 +289,15 @@ def other_configs(dev, steps: int = 5):
         return {"ms_per_step": ms, "frames_per_s": Bx * Tx / ms * 1e3, "valid_frames_per_s": valid_frames / ms * 1e3,
                 "batch": Bx, "T": Tx, "tcgen05_launches_per_step": tc, "launch": "eager", "io": "bf16"}
 
+    def with_roofline(r, mflop_per_frame_layer, layers):
+        # whole-step GEMM FLOPs (2 per multiply-add; padded frames are computed) against the sustained bf16 tensor peak
+        pk = peaks()
+        fl = mflop_per_frame_layer * 1e6 * layers * r["batch"] * r["T"]
+        r["roofline_step"] = {"bound": "tensor", "flops_per_step": fl, "mflop_per_frame_layer": mflop_per_frame_layer,
+                              "achieved": fl / (r["ms_per_step"] * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                              "frac": fl / (r["ms_per_step"] * 1e-3) / 1e12 / pk["bf16_tflops_sustained"], "peak_source": pk["source"]}
+        return r
+
     g = torch.Generator().manual_seed(7)
     try:
         torch.manual_seed(3)
@@ -298,7 +307,9 @@ def other_configs(dev, steps: int = 5):
         lens = torch.randint(500, 1001, (32,), generator=g)
         lens[0] = 1000
         mask = (torch.arange(1000)[None] < lens[:, None]).to(dev)
-        out["cfg3_conformer_large_D512"] = timed(enc, x, mask, int(lens.sum()))
+        # MFLOP per frame and layer: 2 FFNs of 2 linears 512 x 2048 (8.39), cell with h=8 (four block-diagonal 512 x 512 / 8 linears
+        # 0.26, combiner's local half 0.52), conv module (pointwise 512 -> 1024 1.05, depthwise k=31 0.03, linear 0.52)
+        out["cfg3_conformer_large_D512"] = with_roofline(timed(enc, x, mask, int(lens.sum())), 8.39 + 0.26 + 0.52 + 1.05 + 0.03 + 0.52, 12)
         del enc, x
     except Exception as exc:  # a secondary line must never take the headline down
         out["cfg3_conformer_large_D512"] = {"error": repr(exc)[:200]}
@@ -310,7 +321,9 @@ def other_configs(dev, steps: int = 5):
         Tm = int(lens.max())
         x = torch.randn(16, Tm, 512, generator=g).to(torch.bfloat16).to(dev)
         mask = (torch.arange(Tm)[None] < lens[:, None]).to(dev)
-        out["cfg4_branchformer_lite_D512"] = timed(enc, x, mask, int(lens.sum()))
+        # MFLOP per frame and layer: pre-projection 512 -> 3072 (3.15), CSGU depthwise over 1536 channels (0.10), post-projection
+        # 1536 -> 512 (1.57), lite cell's summary MLP 2 x 512 x 512 (1.05), merge_proj 1024 -> 512 -> 512 (1.57)
+        out["cfg4_branchformer_lite_D512"] = with_roofline(timed(enc, x, mask, int(lens.sum())), 3.15 + 0.10 + 1.57 + 1.05 + 1.57, 18)
         del enc, x
     except Exception as exc:
         out["cfg4_branchformer_lite_D512"] = {"error": repr(exc)[:200]}
