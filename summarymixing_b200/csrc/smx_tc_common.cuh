@@ -355,7 +355,23 @@ __device__ __forceinline__ float tanh_approx(float x) {
 // rounding the result receives); gelu(erf) keeps erff for parity with nn.GELU().
 __device__ __forceinline__ float act_swish(float x) { float h = 0.5f * x; return fmaf(h, tanh_approx(h), h); }
 __device__ __forceinline__ float act_sigmoid(float x) { return fmaf(0.5f, tanh_approx(0.5f * x), 0.5f); }
-__device__ __forceinline__ float act_gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// exact (erf) GELU of nn.GELU(): x * Phi(x) with erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7 on erf: three orders of magnitude
+// below the bf16 rounding the result receives), branch-free: one rcp, one ex2, ten FMA-pipe instructions.  erff() costs about twice
+// the instructions with divergent ranges; as the epilogue of the Branchformer's 512 -> 3072 pre-projection (3072 activations per frame
+// against 512 MACs each) it bounded that GEMM: 229 us against 145 us of tensor time at 43.7 k frames.
+__device__ __forceinline__ float act_gelu_erf(float x) {
+  const float u = fabsf(x) * 0.70710678118654752440f;
+  float t;
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, u, 1.0f)));
+  float pl = fmaf(0.5f * 1.061405429f, t, 0.5f * -1.453152027f);
+  pl = fmaf(pl, t, 0.5f * 1.421413741f);
+  pl = fmaf(pl, t, 0.5f * -0.284496736f);
+  pl = fmaf(pl, t, 0.5f * 0.254829592f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(-1.4426950408889634f * u * u));
+  const float q = pl * t * e;                 // 0.5 * erfc(|x| / sqrt 2) = Phi(-|x|)
+  return x * (x >= 0.0f ? 1.0f - q : q);
+}
 __device__ __forceinline__ float act_gelu_tanh(float x) {
   float u = 0.7978845608028654f * (x + 0.044715f * x * x * x);
   float h = 0.5f * x;
