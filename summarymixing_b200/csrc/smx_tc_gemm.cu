@@ -102,7 +102,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
       uint32_t ph = 0;
       for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x) {
         const int ks = tile / mn_tiles, t2 = tile - ks * mn_tiles;
-        const int nt = t2 / p.m_tiles, mt = t2 - nt * p.m_tiles;
+        const int mt = t2 / p.n_tiles, nt = t2 - mt * p.n_tiles;   // N tiles of one row tile run side by side (on neighbouring CTAs): its A tile leaves HBM once
         int kb0, nloc;
         gm_krange(p, ks, nt, nkb1, kb0, nloc);
 #pragma unroll 1
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
       tc::mbar_wait(&acc_empty[buf], ((it >> 1) & 1) ^ 1);  // the epilogue has drained this accumulator (first two uses: fresh)
       tc::tc_fence_after();
       const uint32_t d_addr = tmem + (uint32_t)buf * (uint32_t)NT;
-      const int ks = tile / mn_tiles, nt_i = (tile - ks * mn_tiles) / p.m_tiles;
+      const int ks = tile / mn_tiles, nt_i = (tile - ks * mn_tiles) % p.n_tiles;
       int kb0_i, nloc_i;
       gm_krange(p, ks, nt_i, nkb1, kb0_i, nloc_i);
       const int nkb = nseg * nloc_i;
@@ -159,7 +159,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const __grid_con
     for (int tile = blockIdx.x; tile < n_tiles_total; tile += gridDim.x, ++it) {
       const int buf = it & 1;
       const int ks = tile / mn_tiles, t2 = tile - ks * mn_tiles;
-      const int nt = t2 / p.m_tiles, mt = t2 - nt * p.m_tiles;
+      const int mt = t2 / p.n_tiles, nt = t2 - mt * p.n_tiles;
       const int64_t grow = (int64_t)mt * 128 + r;
       const bool live = grow < p.M;
       const float rscale = (live && p.rowmask) ? (float)p.rowmask[grow] : 1.0f;
