@@ -735,13 +735,13 @@ constexpr int DWT_FRAMES = 24;   // 104 KB of shared memory at D = 512: two bloc
 template <int K>
 __global__ void __launch_bounds__(256, 2) dwconv_tiled_kernel(const __nv_bfloat16* __restrict__ g, const float* __restrict__ dw_w,
                                                               const float* __restrict__ dw_b, const float* __restrict__ ln_w,
-                                                              const float* __restrict__ ln_b, int act, int T, int D,
+                                                              const float* __restrict__ ln_b, int act, int B, int T, int D,
                                                               __nv_bfloat16* __restrict__ out) {
   constexpr int PAD = (K - 1) / 2, NIN = DWT_FRAMES + K - 1;
   extern __shared__ __align__(16) uint8_t dsm[];
   __nv_bfloat16* sIn = reinterpret_cast<__nv_bfloat16*>(dsm);                          // [NIN][D]
   float* sOut = reinterpret_cast<float*>(dsm + (size_t)NIN * D * sizeof(__nv_bfloat16));  // [DWT_FRAMES][D]
-  const int b = blockIdx.y, t0 = blockIdx.x * DWT_FRAMES;
+  const int tiles_t = (T + DWT_FRAMES - 1) / DWT_FRAMES, n_tiles = tiles_t * B;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int cpr = D / 8;
   const int pairs = D / 2, pr = tid % pairs, fb0 = tid / pairs, nfbp = 256 / pairs;
@@ -757,6 +757,10 @@ __global__ void __launch_bounds__(256, 2) dwconv_tiled_kernel(const __nv_bfloat1
     for (int j = 0; j < K; ++j) { w0[j] = sTap[c0 * K + j]; w1[j] = sTap[(c0 + 1) * K + j]; }
     __syncthreads();  // every thread holds its taps before the input rows overwrite them
   }
+  // persistent over the (utterance, frame tile) pairs: the taps (D x K x 4 bytes per block) are fetched once per block, not per tile
+#pragma unroll 1
+  for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+  const int b = tile / tiles_t, t0 = (tile - b * tiles_t) * DWT_FRAMES;
   for (int idx = tid; idx < NIN * cpr; idx += 256) {
     const int row = idx / cpr, ch = idx - row * cpr, u = t0 - PAD + row;
     uint4 val = make_uint4(0, 0, 0, 0);  // zero padding at the utterance edges (Conformer.py:142-151)
@@ -822,6 +826,7 @@ __global__ void __launch_bounds__(256, 2) dwconv_tiled_kernel(const __nv_bfloat1
         *reinterpret_cast<uint2*>(out + ((size_t)b * T + t) * D + c) = make_uint2(tc::pack_bf16x2(o[0], o[1]), tc::pack_bf16x2(o[2], o[3]));
       }
   }
+  }  // tile loop (the next tile's staging barrier also orders this tile's reads of sOut before its overwrite)
 }
 
 int tc_dwconv_ln_act(const __nv_bfloat16* g, const float* dw_w, const float* dw_b, const float* ln_w,
@@ -832,8 +837,11 @@ int tc_dwconv_ln_act(const __nv_bfloat16* g, const float* dw_w, const float* dw_
     if (smem < (size_t)D * 31 * 4) smem = (size_t)D * 31 * 4;   // (the taps pass through it first)
     cudaError_t e = cudaFuncSetAttribute(dwconv_tiled_kernel<31>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return fail(SMX_ERR_CUDA, "cudaFuncSetAttribute(dwconv_tiled): %s", cudaGetErrorString(e));
-    dim3 grid((T + DWT_FRAMES - 1) / DWT_FRAMES, B);
-    dwconv_tiled_kernel<31><<<grid, 256, smem, st>>>(g, dw_w, dw_b, ln_w, ln_b, act, T, D, out);
+    const int n_tiles = ((T + DWT_FRAMES - 1) / DWT_FRAMES) * B;
+    int sms = 148;
+    { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev); if (sms <= 0) sms = 148; }
+    const unsigned grid = (unsigned)(n_tiles < 2 * sms ? n_tiles : 2 * sms);   // two resident blocks per SM
+    dwconv_tiled_kernel<31><<<grid, 256, smem, st>>>(g, dw_w, dw_b, ln_w, ln_b, act, B, T, D, out);
     count_launch();
     return check_launch("dwconv_tiled_kernel");
   }
