@@ -761,11 +761,22 @@ __global__ void __launch_bounds__(256, 2) dwconv_tiled_kernel(const __nv_bfloat1
 #pragma unroll 1
   for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
   const int b = tile / tiles_t, t0 = (tile - b * tiles_t) * DWT_FRAMES;
-  for (int idx = tid; idx < NIN * cpr; idx += 256) {
-    const int row = idx / cpr, ch = idx - row * cpr, u = t0 - PAD + row;
-    uint4 val = make_uint4(0, 0, 0, 0);  // zero padding at the utterance edges (Conformer.py:142-151)
-    if (u >= 0 && u < T) val = *reinterpret_cast<const uint4*>(g + ((size_t)b * T + u) * D + ch * 8);
-    *reinterpret_cast<uint4*>(sIn + (size_t)row * D + ch * 8) = val;
+  // four 16-byte chunks per thread and round, all four loads issued before the first is stored (a load-then-store loop is a chain of
+  // L2 round trips: ~14 per tile at D = 512)
+  for (int base = 0; base < NIN * cpr; base += 4 * 256) {
+    uint4 raw[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx = base + k * 256 + tid;
+      const int row = idx / cpr, ch = idx - row * cpr, u = t0 - PAD + row;
+      raw[k] = make_uint4(0, 0, 0, 0);  // zero padding at the utterance edges (Conformer.py:142-151)
+      if (idx < NIN * cpr && u >= 0 && u < T) raw[k] = *reinterpret_cast<const uint4*>(g + ((size_t)b * T + u) * D + ch * 8);
+    }
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const int idx = base + k * 256 + tid;
+      if (idx < NIN * cpr) *reinterpret_cast<uint4*>(sIn + (size_t)idx * 8) = raw[k];   // (row * D + ch * 8 == idx * 8)
+    }
   }
   __syncthreads();
   {
